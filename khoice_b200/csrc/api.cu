@@ -1,0 +1,669 @@
+// api.cu -- C ABI of libkhoice_b200.so (see include/khoice_b200.h): context, memory, thin wrappers
+// around the kernels, K7 hash partition, and the fused per-group / across-group stages.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "khb_common.cuh"
+
+// implemented in the kernel translation units
+int khb_pack_fasta_impl(khb_ctx *, const uint8_t *, size_t, u64 *, u32 *, size_t, u64 *, u64 *);
+int khb_fasta_separators_impl(khb_ctx *, uint8_t *, const u64 *, const u64 *, int, u64);
+int khb_extract_kmers_impl(khb_ctx *, const u64 *, const u32 *, size_t, int, void *);
+int khb_sort_keys_impl(khb_ctx *, void *, void *, const u64 *, int, int, int *);
+int khb_unique_impl(khb_ctx *, const void *, size_t, int, void *, u64 *);
+int khb_count_runs_impl(khb_ctx *, const void *, size_t, int, u32, u32, u64 *, void *, u32 *, u64 *);
+
+static char g_init_error[512] = "";
+
+int khb_fail(khb_ctx *ctx, int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx ? ctx->err : g_init_error, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int khb_cuda_fail(khb_ctx *ctx, cudaError_t e, const char *what, const char *file, int line)
+{
+    if (ctx && !ctx->sticky) ctx->sticky = (int)e;
+    const char *base = strrchr(file, '/');
+    return khb_fail(ctx, e == cudaErrorMemoryAllocation ? KHB_ERR_NOMEM : KHB_ERR_CUDA, "CUDA error %d (%s) at %s:%d: %s",
+                    (int)e, cudaGetErrorString(e), base ? base + 1 : file, line, what);
+}
+
+int khb_scratch_get(khb_ctx *ctx, int slot, size_t bytes, void **out)
+{
+    khb_scratch *s = &ctx->scratch[slot];
+    if (s->bytes < bytes) {
+        if (s->ptr) {
+            KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            KHB_CUDA(ctx, cudaFree(s->ptr));
+            s->ptr = nullptr;
+            s->bytes = 0;
+        }
+        size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMalloc(&s->ptr, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&s->ptr, want);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            s->ptr = nullptr;
+            return khb_fail(ctx, KHB_ERR_NOMEM, "device allocation of %zu bytes failed (scratch slot %d)", bytes, slot);
+        }
+        s->bytes = want;
+    }
+    *out = s->ptr;
+    return KHB_OK;
+}
+
+extern "C" {
+
+int khb_abi_version(void) { return KHB_ABI_VERSION; }
+
+const char *khb_last_error(const khb_ctx *ctx) { return ctx ? ctx->err : g_init_error; }
+
+int khb_init(int device, khb_ctx **out)
+{
+    if (!out) return KHB_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return khb_fail(nullptr, KHB_ERR_NODEV, "no CUDA device (%s); libkhoice_b200 has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return khb_fail(nullptr, KHB_ERR_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return khb_fail(nullptr, KHB_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    if (prop.major != 10)
+        return khb_fail(nullptr, KHB_ERR_NODEV, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                        prop.major, prop.minor);
+    khb_ctx *ctx = (khb_ctx *)calloc(1, sizeof(khb_ctx));
+    if (!ctx) return khb_fail(nullptr, KHB_ERR_NOMEM, "host allocation failed");
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+        (e = cudaMallocHost((void **)&ctx->h_mail, 1 << 20)) != cudaSuccess ||
+        (e = cudaMalloc((void **)&ctx->d_mail, 1 << 20)) != cudaSuccess) {
+        khb_fail(nullptr, KHB_ERR_CUDA, "context setup: %s", cudaGetErrorString(e));
+        free(ctx);
+        return KHB_ERR_CUDA;
+    }
+    *out = ctx;
+    return KHB_OK;
+}
+
+int khb_destroy(khb_ctx *ctx)
+{
+    if (!ctx) return KHB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 8; i++)
+        if (ctx->scratch[i].ptr) cudaFree(ctx->scratch[i].ptr);
+    if (ctx->gs_buf) cudaFree(ctx->gs_buf);
+    if (ctx->stage_dev) cudaFree(ctx->stage_dev);
+    if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
+    if (ctx->d_mail) cudaFree(ctx->d_mail);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    free(ctx);
+    return KHB_OK;
+}
+
+int khb_device_info(khb_ctx *ctx, int *num_sms, size_t *free_bytes, size_t *total_bytes)
+{
+    KHB_CHECK_CTX(ctx);
+    size_t f = 0, t = 0;
+    KHB_CUDA(ctx, cudaMemGetInfo(&f, &t));
+    if (num_sms) *num_sms = ctx->num_sms;
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return KHB_OK;
+}
+
+uint64_t khb_launch_count(const khb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void *khb_stream(khb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int khb_alloc(khb_ctx *ctx, size_t bytes, void **d_ptr)
+{
+    KHB_CHECK_CTX(ctx);
+    if (!d_ptr) return khb_fail(ctx, KHB_ERR_ARG, "khb_alloc: null out pointer");
+    *d_ptr = nullptr;
+    cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return khb_fail(ctx, KHB_ERR_NOMEM, "khb_alloc: device allocation of %zu bytes failed", bytes);
+    }
+    return KHB_OK;
+}
+int khb_free(khb_ctx *ctx, void *d_ptr)
+{
+    KHB_CHECK_CTX(ctx);
+    if (!d_ptr) return KHB_OK;
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    KHB_CUDA(ctx, cudaFree(d_ptr));
+    return KHB_OK;
+}
+int khb_alloc_host(khb_ctx *ctx, size_t bytes, void **h_ptr)
+{
+    KHB_CHECK_CTX(ctx);
+    if (!h_ptr) return khb_fail(ctx, KHB_ERR_ARG, "khb_alloc_host: null out pointer");
+    cudaError_t e = cudaMallocHost(h_ptr, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return khb_fail(ctx, KHB_ERR_NOMEM, "khb_alloc_host: pinned allocation of %zu bytes failed", bytes);
+    }
+    return KHB_OK;
+}
+int khb_free_host(khb_ctx *ctx, void *h_ptr)
+{
+    KHB_CHECK_CTX(ctx);
+    if (h_ptr) KHB_CUDA(ctx, cudaFreeHost(h_ptr));
+    return KHB_OK;
+}
+int khb_memcpy_h2d(khb_ctx *ctx, void *d, const void *h, size_t bytes)
+{
+    KHB_CHECK_CTX(ctx);
+    if (bytes) KHB_CUDA(ctx, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return KHB_OK;
+}
+int khb_memcpy_d2h(khb_ctx *ctx, void *h, const void *d, size_t bytes)
+{
+    KHB_CHECK_CTX(ctx);
+    if (bytes) KHB_CUDA(ctx, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return KHB_OK;
+}
+int khb_memset(khb_ctx *ctx, void *d, int value, size_t bytes)
+{
+    KHB_CHECK_CTX(ctx);
+    if (bytes) KHB_CUDA(ctx, cudaMemsetAsync(d, value, bytes, ctx->stream));
+    return KHB_OK;
+}
+int khb_sync(khb_ctx *ctx)
+{
+    KHB_CHECK_CTX(ctx);
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KHB_OK;
+}
+
+// ---- staging ---------------------------------------------------------------------------------------
+static inline size_t staged_len(size_t n) { return (n + 3 + KHB_FASTA_TILE - 1) / KHB_FASTA_TILE * KHB_FASTA_TILE; }
+
+size_t khb_staged_size(int n_files, const size_t *h_sizes)
+{
+    size_t t = 0;
+    for (int i = 0; i < n_files; i++) t += staged_len(h_sizes[i]);
+    return t;
+}
+
+int khb_stage_fasta(khb_ctx *ctx, int n_files, const uint8_t *const *h_files, const size_t *h_sizes, uint8_t *d_fasta,
+                    size_t d_capacity, uint64_t *h_begin)
+{
+    KHB_CHECK_CTX(ctx);
+    if (n_files < 0 || (n_files > 0 && (!h_files || !h_sizes)) || !h_begin) return khb_fail(ctx, KHB_ERR_ARG, "khb_stage_fasta: bad arguments");
+    std::vector<u64> tab(2 * (size_t)n_files + 2);
+    u64 off = 0;
+    for (int i = 0; i < n_files; i++) {
+        h_begin[i] = off;
+        tab[i] = off;
+        tab[n_files + i] = h_sizes[i];
+        off += staged_len(h_sizes[i]);
+    }
+    h_begin[n_files] = off;
+    if (off > d_capacity) return khb_fail(ctx, KHB_ERR_CAPACITY, "khb_stage_fasta: need %llu bytes, buffer has %zu", off, d_capacity);
+    if (n_files == 0) return KHB_OK;
+    for (int i = 0; i < n_files; i++)
+        if (h_sizes[i]) KHB_CUDA(ctx, cudaMemcpyAsync(d_fasta + h_begin[i], h_files[i], h_sizes[i], cudaMemcpyHostToDevice, ctx->stream));
+    void *p;
+    int rc = khb_scratch_get(ctx, SCR_MISC, tab.size() * sizeof(u64), &p);
+    if (rc) return rc;
+    KHB_CUDA(ctx, cudaMemcpyAsync(p, tab.data(), 2 * (size_t)n_files * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // tab is pageable and dies with this frame
+    return khb_fasta_separators_impl(ctx, d_fasta, (const u64 *)p, (const u64 *)p + n_files, n_files, off);
+}
+
+// ---- thin kernel wrappers ------------------------------------------------------------------------
+int khb_pack_fasta(khb_ctx *ctx, const uint8_t *d_fasta, size_t nbytes, uint64_t *d_codes, uint32_t *d_valid,
+                   size_t cap_symbols, uint64_t *d_tile_base, uint64_t *d_counts)
+{
+    KHB_CHECK_CTX(ctx);
+    return khb_pack_fasta_impl(ctx, d_fasta, nbytes, (u64 *)d_codes, d_valid, cap_symbols, (u64 *)d_tile_base, (u64 *)d_counts);
+}
+
+int khb_extract_kmers(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, size_t n_symbols, int k, void *d_keys)
+{
+    KHB_CHECK_CTX(ctx);
+    return khb_extract_kmers_impl(ctx, (const u64 *)d_codes, d_valid, n_symbols, k, d_keys);
+}
+
+int khb_sort_keys(khb_ctx *ctx, void *d_keys, void *d_tmp, const uint64_t *h_seg_off, int n_segments, int k, int *result_in_tmp)
+{
+    KHB_CHECK_CTX(ctx);
+    int dummy;
+    return khb_sort_keys_impl(ctx, d_keys, d_tmp, (const u64 *)h_seg_off, n_segments, k, result_in_tmp ? result_in_tmp : &dummy);
+}
+
+int khb_unique(khb_ctx *ctx, const void *d_sorted, size_t n, int k, void *d_out, uint64_t *h_count)
+{
+    KHB_CHECK_CTX(ctx);
+    int rc = khb_unique_impl(ctx, d_sorted, n, k, d_out, ctx->d_mail);
+    if (rc) return rc;
+    KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, ctx->d_mail, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_count) *h_count = ctx->h_mail[0];
+    return KHB_OK;
+}
+
+int khb_count_runs(khb_ctx *ctx, const void *d_sorted, size_t n, int k, uint32_t cs, uint32_t nbins, uint64_t *h_hist,
+                   void *d_out_keys, uint32_t *d_out_counts, uint64_t *h_runs)
+{
+    KHB_CHECK_CTX(ctx);
+    if (!h_hist) return khb_fail(ctx, KHB_ERR_ARG, "khb_count_runs: null histogram");
+    u64 *d_hist = ctx->d_mail + 8, *d_runs = ctx->d_mail;
+    int rc = khb_count_runs_impl(ctx, d_sorted, n, k, cs, nbins, d_hist, d_out_keys, d_out_counts, d_runs);
+    if (rc) return rc;
+    KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, ctx->d_mail, (nbins + 9) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(h_hist, ctx->h_mail + 8, ((size_t)nbins + 1) * sizeof(u64));
+    if (h_runs) *h_runs = ctx->h_mail[0];
+    return KHB_OK;
+}
+
+}  // extern "C"
+
+// ---- K7: hash partition ------------------------------------------------------------------------------
+__device__ __forceinline__ u64 mix64(u64 x)
+{
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ u32 part_of(const Key64 &k, u32 nparts) { return (u32)__umul64hi(mix64(k.v), (u64)nparts); }
+__device__ __forceinline__ u32 part_of(const Key128 &k, u32 nparts)
+{
+    return (u32)__umul64hi(mix64(k.lo ^ mix64(k.hi)), (u64)nparts);
+}
+
+#define PT_BLOCK 256
+#define PT_ITEMS 16
+#define PT_MAXPARTS 64
+
+// counts[p] += number of keys of bucket p  (mode 0)   or   scatter (mode 1: cursor[p] holds the next free slot)
+template <typename Key, int MODE>
+__global__ void __launch_bounds__(PT_BLOCK)
+partition_kernel(const Key *__restrict__ in, u64 n, u32 nparts, u64 *__restrict__ counts_or_cursor, Key *__restrict__ out)
+{
+    __shared__ u32 sc[PT_MAXPARTS];
+    __shared__ u64 sbase[PT_MAXPARTS];
+    const u32 tid = threadIdx.x;
+    const u64 begin = (u64)blockIdx.x * (PT_BLOCK * PT_ITEMS);
+    if (tid < PT_MAXPARTS) sc[tid] = 0;
+    __syncthreads();
+    Key keys[PT_ITEMS];
+    u32 part[PT_ITEMS], slot[PT_ITEMS];
+#pragma unroll
+    for (int r = 0; r < PT_ITEMS; r++) {
+        const u64 g = begin + (u64)r * PT_BLOCK + tid;
+        part[r] = 0xffffffffu;
+        if (g < n) {
+            keys[r] = in[g];
+            part[r] = part_of(keys[r], nparts);
+            slot[r] = atomicAdd(&sc[part[r]], 1u);
+        }
+    }
+    __syncthreads();
+    if (tid < nparts) {
+        const u32 c = sc[tid];
+        if (MODE == 0) {
+            if (c) atomicAdd(&counts_or_cursor[tid], (u64)c);
+        } else {
+            sbase[tid] = c ? atomicAdd(&counts_or_cursor[tid], (u64)c) : 0ull;
+        }
+    }
+    if (MODE == 1) {
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < PT_ITEMS; r++)
+            if (part[r] != 0xffffffffu) out[sbase[part[r]] + slot[r]] = keys[r];
+    }
+}
+
+template <typename Key>
+static int partition_impl(khb_ctx *ctx, const Key *d_keys, u64 n, int nparts, Key *d_out, u64 *h_off)
+{
+    u64 *d_cnt = ctx->d_mail + 16384;  // 64 counters + 64 cursors, away from the histogram mailbox
+    KHB_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 2 * PT_MAXPARTS * sizeof(u64), ctx->stream));
+    const u64 blocks = div_up(n, PT_BLOCK * PT_ITEMS);
+    if (n) {
+        partition_kernel<Key, 0><<<(unsigned)blocks, PT_BLOCK, 0, ctx->stream>>>(d_keys, n, (u32)nparts, d_cnt, nullptr);
+        KHB_LAUNCH_CHECK(ctx);
+    }
+    KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 16384, d_cnt, PT_MAXPARTS * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    u64 cursor[PT_MAXPARTS];
+    u64 off = 0;
+    for (int p = 0; p < nparts; p++) {
+        h_off[p] = off;
+        cursor[p] = off;
+        off += ctx->h_mail[16384 + p];
+    }
+    h_off[nparts] = off;
+    if (n) {
+        KHB_CUDA(ctx, cudaMemcpyAsync(d_cnt + PT_MAXPARTS, cursor, nparts * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+        KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        partition_kernel<Key, 1><<<(unsigned)blocks, PT_BLOCK, 0, ctx->stream>>>(d_keys, n, (u32)nparts, d_cnt + PT_MAXPARTS, d_out);
+        KHB_LAUNCH_CHECK(ctx);
+    }
+    return KHB_OK;
+}
+
+// ---- fused stages ----------------------------------------------------------------------------------------
+static int gs_reserve(khb_ctx *ctx, int k, u64 extra)
+{
+    const size_t W = (size_t)khb_key_bytes(k);
+    if (ctx->gs_k && ctx->gs_k != k) return khb_fail(ctx, KHB_ERR_STATE, "retained group sets were built with k=%d, not k=%d; call khb_group_sets_reset", ctx->gs_k, k);
+    const u64 need = ctx->gs_len + extra + 2;
+    if (need > ctx->gs_cap) {
+        u64 cap = ctx->gs_cap ? ctx->gs_cap : (1u << 20);
+        while (cap < need) cap += cap / 2 + 1;
+        void *nb = nullptr;
+        cudaError_t e = cudaMalloc(&nb, cap * W);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cap = need;
+            e = cudaMalloc(&nb, cap * W);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return khb_fail(ctx, KHB_ERR_NOMEM, "group set store: device allocation of %llu bytes failed", (u64)(cap * W));
+        }
+        if (ctx->gs_len) KHB_CUDA(ctx, cudaMemcpyAsync(nb, ctx->gs_buf, ctx->gs_len * W, cudaMemcpyDeviceToDevice, ctx->stream));
+        KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->gs_buf) KHB_CUDA(ctx, cudaFree(ctx->gs_buf));
+        ctx->gs_buf = nb;
+        ctx->gs_cap = cap;
+    }
+    ctx->gs_k = k;
+    return KHB_OK;
+}
+
+struct PhaseTimer {
+    khb_ctx *ctx;
+    cudaEvent_t ev[12];
+    int n;
+    bool ok;
+    explicit PhaseTimer(khb_ctx *c) : ctx(c), n(0), ok(true)
+    {
+        for (int i = 0; i < 12; i++)
+            if (cudaEventCreate(&ev[i]) != cudaSuccess) ok = false;
+    }
+    ~PhaseTimer()
+    {
+        for (int i = 0; i < 12; i++) cudaEventDestroy(ev[i]);
+    }
+    void mark()
+    {
+        if (n < 12) cudaEventRecord(ev[n++], ctx->stream);
+    }
+    float ms(int a, int b)
+    {
+        float t = 0.f;
+        if (a < n && b < n) cudaEventElapsedTime(&t, ev[a], ev[b]);
+        return t;
+    }
+};
+
+static int group_from_staged_impl(khb_ctx *ctx, int k, int n_genomes, const uint8_t *d_fasta, const u64 *h_begin, u32 nbins,
+                                  u64 *h_hist, int keep_set, khb_stats *stats, PhaseTimer &tm)
+{
+    if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "k=%d outside 1..64", k);
+    if (n_genomes < 1 || !h_begin || !h_hist) return khb_fail(ctx, KHB_ERR_ARG, "group stage: bad arguments");
+    if (nbins < 1 || nbins > 8192) return khb_fail(ctx, KHB_ERR_ARG, "nbins=%u outside 1..8192", nbins);
+    const size_t W = (size_t)khb_key_bytes(k);
+    const size_t nbytes = h_begin[n_genomes];
+    const size_t ntiles = nbytes / KHB_FASTA_TILE;
+    int rc;
+    void *p;
+    // K1
+    const size_t cw = khb_codes_words(nbytes), vw = khb_valid_words(nbytes);
+    const size_t pack_bytes = cw * 8 + vw * 4 + (ntiles + 1) * 8 + 64;
+    if ((rc = khb_scratch_get(ctx, SCR_PACK, pack_bytes, &p))) return rc;
+    u64 *d_codes = (u64 *)p;
+    u64 *d_tile_base = d_codes + cw;
+    u64 *d_counts = d_tile_base + ntiles + 1;
+    u32 *d_valid = (u32 *)(d_counts + 4);
+    if ((rc = khb_pack_fasta_impl(ctx, d_fasta, nbytes, d_codes, d_valid, nbytes, d_tile_base, d_counts))) return rc;
+    std::vector<u64> tile_base(ntiles + 1);
+    u64 counts[2];
+    KHB_CUDA(ctx, cudaMemcpyAsync(tile_base.data(), d_tile_base, (ntiles + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    KHB_CUDA(ctx, cudaMemcpyAsync(counts, d_counts, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    tm.mark();  // 2: pack done
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const u64 n_sym = counts[0];
+    // K2
+    const size_t key_bytes = (n_sym + 4) * W;
+    if ((rc = khb_scratch_get(ctx, SCR_KEYS_A, key_bytes, &p))) return rc;
+    void *bufA = p;
+    if ((rc = khb_scratch_get(ctx, SCR_KEYS_B, key_bytes, &p))) return rc;
+    void *bufB = p;
+    if ((rc = khb_extract_kmers_impl(ctx, d_codes, d_valid, n_sym, k, bufA))) return rc;
+    tm.mark();  // 3: extract done
+    // K3 per genome (segmented)
+    std::vector<u64> seg(n_genomes + 1);
+    for (int g = 0; g < n_genomes; g++) seg[g] = tile_base[h_begin[g] / KHB_FASTA_TILE];
+    seg[n_genomes] = n_sym;
+    int in_tmp = 0;
+    if ((rc = khb_sort_keys_impl(ctx, bufA, bufB, seg.data(), n_genomes, k, &in_tmp))) return rc;
+    void *sorted = in_tmp ? bufB : bufA, *other = in_tmp ? bufA : bufB;
+    tm.mark();  // 4: sort1 done
+    // K4
+    if ((rc = khb_unique_impl(ctx, sorted, n_sym, k, other, ctx->d_mail))) return rc;
+    KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, ctx->d_mail, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    tm.mark();  // 5: unique done
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const u64 s_g = ctx->h_mail[0];
+    // K3' group sort
+    u64 one_seg[2] = {0, s_g};
+    if ((rc = khb_sort_keys_impl(ctx, other, sorted, one_seg, 1, k, &in_tmp))) return rc;
+    void *gsorted = in_tmp ? sorted : other;
+    tm.mark();  // 6: sort2 done
+    // K5
+    void *out_keys = nullptr;
+    if (keep_set) {
+        if ((rc = gs_reserve(ctx, k, s_g))) return rc;
+        out_keys = (char *)ctx->gs_buf + ctx->gs_len * W;
+    }
+    u64 *d_hist = ctx->d_mail + 8, *d_runs = ctx->d_mail;
+    if ((rc = khb_count_runs_impl(ctx, gsorted, s_g, k, KHB_COUNTER_MAX, nbins, d_hist, out_keys, nullptr, d_runs))) return rc;
+    KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, ctx->d_mail, (nbins + 9) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    tm.mark();  // 7: count done
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(h_hist, ctx->h_mail + 8, ((size_t)nbins + 1) * sizeof(u64));
+    const u64 d_g = ctx->h_mail[0];
+    if (keep_set) {
+        ctx->gs_len += d_g;
+        ctx->gs_groups += 1;
+    }
+    if (stats) {
+        stats->fasta_bytes = nbytes;
+        stats->bases = n_sym - counts[1];
+        stats->windows = n_sym;
+        stats->genome_distinct = s_g;
+        stats->distinct = d_g;
+    }
+    return KHB_OK;
+}
+
+static void fill_times(khb_stats *stats, PhaseTimer &tm)
+{
+    if (!stats) return;
+    // marks: 0 start, 1 h2d done, 2 pack, 3 extract, 4 sort1, 5 unique, 6 sort2, 7 count
+    stats->ms_h2d = tm.ms(0, 1);
+    stats->ms_pack = tm.ms(1, 2);
+    stats->ms_extract = tm.ms(2, 3);
+    stats->ms_sort1 = tm.ms(3, 4);
+    stats->ms_unique = tm.ms(4, 5);
+    stats->ms_sort2 = tm.ms(5, 6);
+    stats->ms_count = tm.ms(6, 7);
+    stats->ms_total = tm.ms(0, 7);
+}
+
+extern "C" {
+
+int khb_group_from_staged(khb_ctx *ctx, int k, int n_genomes, const uint8_t *d_fasta, const uint64_t *h_begin, uint32_t nbins,
+                          uint64_t *h_hist, int keep_set, khb_stats *stats)
+{
+    KHB_CHECK_CTX(ctx);
+    if (stats) memset(stats, 0, sizeof(*stats));
+    PhaseTimer tm(ctx);
+    tm.mark();
+    tm.mark();
+    int rc = group_from_staged_impl(ctx, k, n_genomes, d_fasta, (const u64 *)h_begin, nbins, (u64 *)h_hist, keep_set, stats, tm);
+    if (rc == KHB_OK) fill_times(stats, tm);
+    return rc;
+}
+
+int khb_group_from_fasta(khb_ctx *ctx, int k, int n_genomes, const uint8_t *const *h_files, const size_t *h_sizes,
+                         uint32_t nbins, uint64_t *h_hist, int keep_set, khb_stats *stats)
+{
+    KHB_CHECK_CTX(ctx);
+    if (n_genomes < 1 || !h_files || !h_sizes) return khb_fail(ctx, KHB_ERR_ARG, "khb_group_from_fasta: bad arguments");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    const size_t need = khb_staged_size(n_genomes, h_sizes);
+    if (need > ctx->stage_dev_cap) {
+        if (ctx->stage_dev) {
+            KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            KHB_CUDA(ctx, cudaFree(ctx->stage_dev));
+            ctx->stage_dev = nullptr;
+            ctx->stage_dev_cap = 0;
+        }
+        const size_t cap = need + need / 8;
+        cudaError_t e = cudaMalloc((void **)&ctx->stage_dev, cap);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return khb_fail(ctx, KHB_ERR_NOMEM, "staging buffer: device allocation of %zu bytes failed", cap);
+        }
+        ctx->stage_dev_cap = cap;
+    }
+    PhaseTimer tm(ctx);
+    tm.mark();
+    std::vector<u64> begin((size_t)n_genomes + 1);
+    int rc = khb_stage_fasta(ctx, n_genomes, h_files, h_sizes, ctx->stage_dev, ctx->stage_dev_cap, (uint64_t *)begin.data());
+    if (rc) return rc;
+    tm.mark();
+    rc = group_from_staged_impl(ctx, k, n_genomes, ctx->stage_dev, begin.data(), nbins, (u64 *)h_hist, keep_set, stats, tm);
+    if (rc == KHB_OK) fill_times(stats, tm);
+    return rc;
+}
+
+int khb_across_groups(khb_ctx *ctx, uint32_t nbins, uint64_t *h_hist, khb_stats *stats)
+{
+    KHB_CHECK_CTX(ctx);
+    if (!h_hist) return khb_fail(ctx, KHB_ERR_ARG, "khb_across_groups: null histogram");
+    if (nbins < 1 || nbins > 8192) return khb_fail(ctx, KHB_ERR_ARG, "nbins=%u outside 1..8192", nbins);
+    if (!ctx->gs_k) return khb_fail(ctx, KHB_ERR_STATE, "khb_across_groups: no group set retained");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    const int k = ctx->gs_k;
+    const size_t W = (size_t)khb_key_bytes(k);
+    const u64 n = ctx->gs_len;
+    void *p;
+    int rc = khb_scratch_get(ctx, SCR_KEYS_A, (n + 4) * W, &p);
+    if (rc) return rc;
+    PhaseTimer tm(ctx);
+    tm.mark();
+    u64 one_seg[2] = {0, n};
+    int in_tmp = 0;
+    if ((rc = khb_sort_keys_impl(ctx, ctx->gs_buf, p, one_seg, 1, k, &in_tmp))) return rc;
+    tm.mark();
+    u64 *d_hist = ctx->d_mail + 8, *d_runs = ctx->d_mail;
+    if ((rc = khb_count_runs_impl(ctx, in_tmp ? p : ctx->gs_buf, n, k, KHB_COUNTER_MAX, nbins, d_hist, nullptr, nullptr, d_runs))) return rc;
+    KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, ctx->d_mail, (nbins + 9) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    tm.mark();
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(h_hist, ctx->h_mail + 8, ((size_t)nbins + 1) * sizeof(u64));
+    if (stats) {
+        stats->windows = n;
+        stats->genome_distinct = n;
+        stats->distinct = ctx->h_mail[0];
+        stats->ms_sort2 = tm.ms(0, 1);
+        stats->ms_count = tm.ms(1, 2);
+        stats->ms_total = tm.ms(0, 2);
+    }
+    return KHB_OK;
+}
+
+int khb_group_sets_info(khb_ctx *ctx, int *k, int *n_groups, uint64_t *n_keys)
+{
+    if (!ctx) return KHB_ERR_ARG;
+    if (k) *k = ctx->gs_k;
+    if (n_groups) *n_groups = ctx->gs_groups;
+    if (n_keys) *n_keys = ctx->gs_len;
+    return KHB_OK;
+}
+
+int khb_group_sets_device(khb_ctx *ctx, void **d_keys, uint64_t *n_keys)
+{
+    KHB_CHECK_CTX(ctx);
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (d_keys) *d_keys = ctx->gs_buf;
+    if (n_keys) *n_keys = ctx->gs_len;
+    return KHB_OK;
+}
+
+int khb_group_sets_append_device(khb_ctx *ctx, int k, const void *d_keys, uint64_t n_keys, int n_groups)
+{
+    KHB_CHECK_CTX(ctx);
+    if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "k=%d outside 1..64", k);
+    int rc = gs_reserve(ctx, k, n_keys);
+    if (rc) return rc;
+    const size_t W = (size_t)khb_key_bytes(k);
+    if (n_keys) KHB_CUDA(ctx, cudaMemcpyAsync((char *)ctx->gs_buf + ctx->gs_len * W, d_keys, n_keys * W, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->gs_len += n_keys;
+    ctx->gs_groups += n_groups;
+    return KHB_OK;
+}
+
+int khb_group_sets_append_host(khb_ctx *ctx, int k, const void *h_keys, uint64_t n_keys, int n_groups)
+{
+    KHB_CHECK_CTX(ctx);
+    if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "k=%d outside 1..64", k);
+    int rc = gs_reserve(ctx, k, n_keys);
+    if (rc) return rc;
+    const size_t W = (size_t)khb_key_bytes(k);
+    if (n_keys) {
+        KHB_CUDA(ctx, cudaMemcpyAsync((char *)ctx->gs_buf + ctx->gs_len * W, h_keys, n_keys * W, cudaMemcpyHostToDevice, ctx->stream));
+        KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->gs_len += n_keys;
+    ctx->gs_groups += n_groups;
+    return KHB_OK;
+}
+
+int khb_group_sets_reset(khb_ctx *ctx)
+{
+    if (!ctx) return KHB_ERR_ARG;
+    ctx->gs_len = 0;
+    ctx->gs_groups = 0;
+    ctx->gs_k = 0;
+    return KHB_OK;
+}
+
+int khb_partition_by_hash(khb_ctx *ctx, const void *d_keys, uint64_t n, int k, int n_parts, void *d_out, uint64_t *h_part_off)
+{
+    KHB_CHECK_CTX(ctx);
+    if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "k=%d outside 1..64", k);
+    if (n_parts < 1 || n_parts > PT_MAXPARTS || !h_part_off) return khb_fail(ctx, KHB_ERR_ARG, "khb_partition_by_hash: n_parts=%d outside 1..%d", n_parts, PT_MAXPARTS);
+    return k <= 32 ? partition_impl<Key64>(ctx, (const Key64 *)d_keys, n, n_parts, (Key64 *)d_out, (u64 *)h_part_off)
+                   : partition_impl<Key128>(ctx, (const Key128 *)d_keys, n, n_parts, (Key128 *)d_out, (u64 *)h_part_off);
+}
+
+}  // extern "C"

@@ -1,0 +1,304 @@
+// compact.cu -- K4 adjacent-unique compaction and K5/K6 run-length count + count-of-counts histogram.
+//
+//   unique_kernel    : sorted keys -> distinct keys (sentinels dropped).  With per-genome segments laid
+//                      end to end this yields the concatenation of the per-genome k-mer SETS, i.e. the
+//                      result of `kmc` + `kmc_tools transform ... set_counts 1`
+//                      (/root/reference/workflow/rules/exp_type_1.smk:156-173).  Every segment ends with
+//                      sentinel keys (the window starting at the genome's trailing break symbol), so the
+//                      first key of a segment never equals its predecessor and no segment table is needed.
+//   rle_hist_kernel  : sorted keys -> for every run of equal keys its length c (saturated at `cs`, the
+//                      `-cs5000` of exp_type_1.smk:61,84), hist[c]++, optionally the distinct keys and
+//                      their counters.  On the concatenated per-genome sets of a group c is the number of
+//                      genomes containing the k-mer = the counter `kmc_tools complex (set1+...+setN)`
+//                      produces (exp_type_1.smk:175-182) and hist is what `kmc_tools transform ... histogram`
+//                      prints (exp_type_1.smk:184-191); on the concatenated group sets it is the
+//                      across-group table and histogram (exp_type_1.smk:243-259).
+//
+// Both kernels are single-pass: persistent CTAs take tiles from an atomic ticket, flags are turned into
+// positions with warp ballots + popc (keys stay in registers in warp-striped order), and the running
+// output offset is chained from tile to tile with decoupled look-back (lookback.cuh).
+// Algorithmic bytes: unique W*n + W*distinct;  rle W*n (+ W*runs if keys are emitted, + 4*runs for counters).
+#include "khb_common.cuh"
+#include "lookback.cuh"
+
+#define CP_BLOCK 512
+#define CP_WARPS (CP_BLOCK / 32)
+#define CP_ITEMS 8
+#define CP_TILE (CP_BLOCK * CP_ITEMS)
+
+__device__ __forceinline__ Key64 shfl_key(const Key64 &k, int src)
+{
+    return Key64{__shfl_sync(0xffffffffu, k.v, src)};
+}
+__device__ __forceinline__ Key128 shfl_key(const Key128 &k, int src)
+{
+    return Key128{__shfl_sync(0xffffffffu, k.lo, src), __shfl_sync(0xffffffffu, k.hi, src)};
+}
+template <typename Key> __device__ __forceinline__ Key sentinel_key();
+template <> __device__ __forceinline__ Key64 sentinel_key<Key64>() { return Key64{~0ull}; }
+template <> __device__ __forceinline__ Key128 sentinel_key<Key128>() { return Key128{~0ull, ~0ull}; }
+
+// Load a tile warp-striped; keys past n become sentinels.
+template <typename Key>
+__device__ __forceinline__ void load_tile(const Key *__restrict__ in, u64 begin, u64 n, u32 wbase, u32 lane, Key (&keys)[CP_ITEMS])
+{
+#pragma unroll
+    for (int r = 0; r < CP_ITEMS; r++) {
+        const u64 g = begin + wbase + r * 32 + lane;
+        keys[r] = g < n ? in[g] : sentinel_key<Key>();
+    }
+}
+
+// Key at global index g-1 for the element held by (round r, lane); `before` is the key preceding the
+// warp's chunk (only read when the chunk does not start at index 0).
+template <typename Key>
+__device__ __forceinline__ Key prev_key(const Key (&keys)[CP_ITEMS], int r, u32 lane, const Key &before)
+{
+    Key up = shfl_key(keys[r], (int)((lane + 31) & 31));         // lane-1 (lane 0 gets lane 31: replaced below)
+    Key last = r > 0 ? shfl_key(keys[r > 0 ? r - 1 : 0], 31) : before;
+    return lane == 0 ? last : up;
+}
+
+template <typename Key>
+__global__ void __launch_bounds__(CP_BLOCK)
+unique_kernel(const Key *__restrict__ in, u64 n, Key *__restrict__ out, u64 *__restrict__ lookback,
+              u32 *__restrict__ ticket, u32 epoch, u64 *__restrict__ d_count)
+{
+    __shared__ u64 ws[33];
+    __shared__ u32 s_tile;
+    __shared__ u64 s_base;
+    const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    const u64 ntiles = (n + CP_TILE - 1) / CP_TILE;
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const u64 tile = s_tile;
+        if (tile >= ntiles) break;
+        const u64 begin = tile * CP_TILE;
+        const u32 wbase = warp * (32 * CP_ITEMS);
+        Key keys[CP_ITEMS];
+        load_tile(in, begin, n, wbase, lane, keys);
+        const u64 chunk0 = begin + wbase;
+        Key before = sentinel_key<Key>();
+        if (chunk0 > 0 && chunk0 < n) before = in[chunk0 - 1];
+        u32 ball[CP_ITEMS];
+        u32 wcount = 0;
+#pragma unroll
+        for (int r = 0; r < CP_ITEMS; r++) {
+            const u64 g = chunk0 + r * 32 + lane;
+            const Key pk = prev_key(keys, r, lane, before);
+            const bool keep = g < n && !key_is_sentinel(keys[r]) && (g == 0 || !key_eq(keys[r], pk));
+            ball[r] = __ballot_sync(0xffffffffu, keep);
+            wcount += __popc(ball[r]);
+        }
+        u64 total;
+        const u64 woff = block_excl_sum<u64>(lane == 0 ? (u64)wcount : 0ull, ws, &total);
+        // woff is only meaningful on lane 0 of each warp; broadcast
+        const u64 warp_off = __shfl_sync(0xffffffffu, woff, 0);
+        if (warp == 0) {
+            u64 excl = 0;
+            if (tile == 0) {
+                if (lane == 0) lb_store(lookback, lb_pack(LB_PREFIX, total, epoch));
+            } else {
+                if (lane == 0) lb_store(lookback + tile, lb_pack(LB_AGG, total, epoch));
+                excl = lb_walk_warp(lookback, tile, 0, epoch);
+                if (lane == 0) lb_store(lookback + tile, lb_pack(LB_PREFIX, excl + total, epoch));
+            }
+            if (lane == 0) {
+                s_base = excl;
+                if (tile == ntiles - 1) *d_count = excl + total;
+            }
+        }
+        __syncthreads();
+        u64 pos = s_base + warp_off;
+#pragma unroll
+        for (int r = 0; r < CP_ITEMS; r++) {
+            if ((ball[r] >> lane) & 1u) out[pos + __popc(ball[r] & lanemask_lt())] = keys[r];
+            pos += __popc(ball[r]);
+        }
+        __syncthreads();  // s_tile / s_base are rewritten by the next iteration
+    }
+}
+
+// Index of the first element of the run of `key` that reaches back from index `at` (exclusive): the
+// smallest j <= at such that in[j..at) are all equal to key.  Warp-cooperative.
+template <typename Key>
+__device__ __forceinline__ u64 run_head_before(const Key *__restrict__ in, u64 at, const Key &key, u32 lane)
+{
+    u64 j = at;
+    while (j > 0) {
+        const bool have = j > lane;
+        bool same = false;
+        if (have) same = key_eq(in[j - 1 - lane], key);
+        const u32 diff = __ballot_sync(0xffffffffu, !same);  // lanes beyond index 0 count as "different"
+        if (diff) {
+            j -= (u32)(__ffs(diff) - 1);
+            break;
+        }
+        j -= 32;
+    }
+    return j;
+}
+
+template <typename Key>
+__global__ void __launch_bounds__(CP_BLOCK)
+rle_hist_kernel(const Key *__restrict__ in, u64 n, u32 cs, u32 nbins, u64 *__restrict__ hist,
+                Key *__restrict__ out_keys, u32 *__restrict__ out_counts, u64 *__restrict__ lookback,
+                u32 *__restrict__ ticket, u32 epoch, u64 *__restrict__ d_runs)
+{
+    extern __shared__ u32 sh_hist[];  // [nbins+1]
+    __shared__ u64 ws[33];
+    __shared__ u32 s_tile;
+    __shared__ u64 s_base;
+    __shared__ u64 s_head0;            // global index of the head of the run that is open at the tile start
+    __shared__ u32 s_wlast[CP_WARPS];  // per warp: local index+1 of its last head, 0 = none
+    const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    const u64 ntiles = (n + CP_TILE - 1) / CP_TILE;
+    const bool emit = out_keys != nullptr || out_counts != nullptr;
+    for (u32 i = tid; i <= nbins; i += CP_BLOCK) sh_hist[i] = 0;
+    u64 my_runs = 0;
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const u64 tile = s_tile;
+        if (tile >= ntiles) break;
+        const u64 begin = tile * CP_TILE;
+        const u32 wbase = warp * (32 * CP_ITEMS);
+        Key keys[CP_ITEMS];
+        load_tile(in, begin, n, wbase, lane, keys);
+        const u64 chunk0 = begin + wbase;
+        Key before = sentinel_key<Key>();
+        if (chunk0 > 0 && chunk0 < n) before = in[chunk0 - 1];
+        const u64 after_idx = chunk0 + 32 * CP_ITEMS;
+        Key after = sentinel_key<Key>();
+        if (after_idx < n) after = in[after_idx];
+        if (warp == 0) {
+            // the run open at the tile start (only matters if the first key continues it)
+            Key k0 = shfl_key(keys[0], 0);
+            u64 h0 = begin;
+            if (begin > 0 && begin < n && !key_is_sentinel(k0)) h0 = run_head_before(in, begin, k0, lane);
+            if (lane == 0) s_head0 = h0;
+        }
+        u32 hball[CP_ITEMS], tball[CP_ITEMS], hrun[CP_ITEMS];
+        u32 carry = 0, wheads = 0;
+#pragma unroll
+        for (int r = 0; r < CP_ITEMS; r++) {
+            const u64 g = chunk0 + r * 32 + lane;
+            const Key pk = prev_key(keys, r, lane, before);
+            Key dn = shfl_key(keys[r], (int)((lane + 1) & 31));
+            Key nxt = r + 1 < CP_ITEMS ? shfl_key(keys[r + 1 < CP_ITEMS ? r + 1 : r], 0) : after;
+            const Key nk = lane == 31 ? nxt : dn;
+            const bool valid = g < n && !key_is_sentinel(keys[r]);
+            const bool head = valid && (g == 0 || !key_eq(keys[r], pk));
+            const bool tail = valid && (g + 1 >= n || !key_eq(keys[r], nk));
+            hball[r] = __ballot_sync(0xffffffffu, head);
+            tball[r] = __ballot_sync(0xffffffffu, tail);
+            wheads += __popc(hball[r]);
+            const u32 loc = wbase + r * 32 + lane + 1;  // local index + 1
+            u32 h = warp_incl_max<u32>(head ? loc : 0u);
+            h = h > carry ? h : carry;
+            hrun[r] = h;
+            carry = __shfl_sync(0xffffffffu, h, 31);
+        }
+        if (lane == 0) s_wlast[warp] = carry;
+        u64 total;
+        const u64 woff = block_excl_sum<u64>(lane == 0 ? (u64)wheads : 0ull, ws, &total);  // syncs: s_wlast, s_head0 visible
+        const u64 warp_off = __shfl_sync(0xffffffffu, woff, 0);
+        if (emit && warp == 0) {
+            u64 excl = 0;
+            if (tile == 0) {
+                if (lane == 0) lb_store(lookback, lb_pack(LB_PREFIX, total, epoch));
+            } else {
+                if (lane == 0) lb_store(lookback + tile, lb_pack(LB_AGG, total, epoch));
+                excl = lb_walk_warp(lookback, tile, 0, epoch);
+                if (lane == 0) lb_store(lookback + tile, lb_pack(LB_PREFIX, excl + total, epoch));
+            }
+            if (lane == 0) s_base = excl;
+        }
+        if (tid == 0) my_runs += total;
+        u32 wprefix = 0;  // last head (local index+1) in earlier warps of this tile
+        for (u32 w = 0; w < warp; w++) wprefix = s_wlast[w] > wprefix ? s_wlast[w] : wprefix;
+        const u64 head0 = s_head0;
+        if (emit) __syncthreads();  // s_base
+        u64 pos = (emit ? s_base : 0ull) + warp_off;  // heads before this warp's chunk (global ordinal)
+#pragma unroll
+        for (int r = 0; r < CP_ITEMS; r++) {
+            const u64 g = chunk0 + r * 32 + lane;
+            const u32 below = __popc(hball[r] & lanemask_lt());
+            const bool head = (hball[r] >> lane) & 1u;
+            if ((tball[r] >> lane) & 1u) {
+                const u32 h = hrun[r] ? hrun[r] : wprefix;
+                const u64 hg = h ? begin + (h - 1) : head0;
+                u64 len = g - hg + 1;
+                const u32 c = len > (u64)cs ? cs : (u32)len;
+                if (c <= nbins) atomicAdd(&sh_hist[c], 1u);
+                if (out_counts) out_counts[pos + below + (head ? 1u : 0u) - 1u] = c;
+            }
+            if (head && out_keys) out_keys[pos + below] = keys[r];
+            pos += __popc(hball[r]);
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    for (u32 i = tid; i <= nbins; i += CP_BLOCK) {
+        const u32 c = sh_hist[i];
+        if (c) atomicAdd(&hist[i], (u64)c);
+    }
+    if (tid == 0 && my_runs) atomicAdd(d_runs, my_runs);
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+static int compact_scratch(khb_ctx *ctx, u64 ntiles, u64 **d_lb, u32 **d_ticket)
+{
+    void *p;
+    int rc = khb_scratch_get(ctx, SCR_FLAGS, (ntiles + 8) * sizeof(u64), &p);
+    if (rc) return rc;
+    *d_lb = (u64 *)p + 1;
+    *d_ticket = (u32 *)p;
+    KHB_CUDA(ctx, cudaMemsetAsync(p, 0, (ntiles + 8) * sizeof(u64), ctx->stream));
+    return KHB_OK;
+}
+
+int khb_unique_impl(khb_ctx *ctx, const void *d_sorted, size_t n, int k, void *d_out, u64 *d_count)
+{
+    if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_unique: k=%d outside 1..64", k);
+    KHB_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(u64), ctx->stream));
+    if (n == 0) return KHB_OK;
+    const u64 ntiles = div_up(n, CP_TILE);
+    u64 *d_lb;
+    u32 *d_ticket;
+    int rc = compact_scratch(ctx, ntiles, &d_lb, &d_ticket);
+    if (rc) return rc;
+    u64 grid = (u64)ctx->num_sms * 3;
+    if (grid > ntiles) grid = ntiles;
+    if (k <= 32)
+        unique_kernel<Key64><<<(unsigned)grid, CP_BLOCK, 0, ctx->stream>>>((const Key64 *)d_sorted, n, (Key64 *)d_out, d_lb, d_ticket, 1u, d_count);
+    else
+        unique_kernel<Key128><<<(unsigned)grid, CP_BLOCK, 0, ctx->stream>>>((const Key128 *)d_sorted, n, (Key128 *)d_out, d_lb, d_ticket, 1u, d_count);
+    KHB_LAUNCH_CHECK(ctx);
+    return KHB_OK;
+}
+
+int khb_count_runs_impl(khb_ctx *ctx, const void *d_sorted, size_t n, int k, u32 cs, u32 nbins, u64 *d_hist,
+                        void *d_out_keys, u32 *d_out_counts, u64 *d_runs)
+{
+    if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_count_runs: k=%d outside 1..64", k);
+    if (nbins < 1 || nbins > 8192) return khb_fail(ctx, KHB_ERR_ARG, "khb_count_runs: nbins=%u outside 1..8192", nbins);
+    KHB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, ((size_t)nbins + 1) * sizeof(u64), ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(d_runs, 0, sizeof(u64), ctx->stream));
+    if (n == 0) return KHB_OK;
+    const u64 ntiles = div_up(n, CP_TILE);
+    u64 *d_lb;
+    u32 *d_ticket;
+    int rc = compact_scratch(ctx, ntiles, &d_lb, &d_ticket);
+    if (rc) return rc;
+    u64 grid = (u64)ctx->num_sms * 3;
+    if (grid > ntiles) grid = ntiles;
+    const size_t shm = ((size_t)nbins + 1) * sizeof(u32);
+    if (k <= 32)
+        rle_hist_kernel<Key64><<<(unsigned)grid, CP_BLOCK, shm, ctx->stream>>>((const Key64 *)d_sorted, n, cs, nbins, d_hist, (Key64 *)d_out_keys, d_out_counts, d_lb, d_ticket, 1u, d_runs);
+    else
+        rle_hist_kernel<Key128><<<(unsigned)grid, CP_BLOCK, shm, ctx->stream>>>((const Key128 *)d_sorted, n, cs, nbins, d_hist, (Key128 *)d_out_keys, d_out_counts, d_lb, d_ticket, 1u, d_runs);
+    KHB_LAUNCH_CHECK(ctx);
+    return KHB_OK;
+}

@@ -1,0 +1,265 @@
+// fasta_pack.cu -- K1: FASTA text -> 2-bit symbol stream + validity bitmap.
+//
+// Replaces the FASTA reader + splitter front end of `kmc -fm` (reference call site
+// /root/reference/workflow/rules/exp_type_1.smk:163; KMC semantics R1-R4 of SURVEY.md section 8c):
+//   R1  '>' .. end of line is a header (dropped); it contributes ONE invalid "break" symbol so that no
+//       window spans two records (R4);
+//   R2  '\n' and '\r' are skipped;
+//   R3  ACGTacgt -> 0..3; every other byte is an invalid symbol.
+//
+// Layout in HBM (MSB-first so that a k-mer is a contiguous bit range, see kmer_extract.cu):
+//   codes : u64 words, 32 symbols per word, symbol j at bits [63-2(j%32)-1, 63-2(j%32)] of word j/32
+//   valid : u32 words, 32 symbols per word, symbol j at bit 31-(j%32) of word j/32
+// Both arrays must be zero-filled by the caller (tile boundaries are merged with atomicOr).
+//
+// Three launches over tiles of KHB_FASTA_TILE = 16 KiB (1024 threads x one 16-byte vector load):
+//   fasta_summary_kernel : per tile, symbol counts for both possible entry states + last line event
+//   fasta_scan_kernel    : one CTA; resolves every tile's entry state and exclusive symbol offset
+//   fasta_pack_kernel    : re-reads the tile, builds the bit stream in shared memory (atomicOr of
+//                          per-thread fragments), copies whole words out coalesced
+// Algorithmic bytes: F (text) + B/4 (codes) + B/8 (valid); the text is read twice (2F) by design --
+// it is 1 byte/base against >100 bytes/base for the sorts that follow.
+#include "khb_common.cuh"
+
+#define TILE_BYTES KHB_FASTA_TILE
+#define TILE_THREADS 1024
+
+enum { ST_SEQ = 0, ST_HDR = 1, ST_UNK = 2 };
+
+struct __align__(16) TileSummary {
+    u32 cnt_common;  // symbols emitted after the tile's first line event (entry-state independent)
+    u32 cnt_pre;     // symbols emitted up to and including the first event IF the tile is entered in SEQ
+    u32 brk;         // break symbols: low 16 bits common, high 16 bits pre
+    u32 last_event;  // 0 none, 1 '\n', 2 '>'
+};
+
+__device__ __forceinline__ u32 byte_of(const uint4 &d, int j)
+{
+    u32 w = j < 4 ? d.x : j < 8 ? d.y : j < 12 ? d.z : d.w;
+    return (w >> (8 * (j & 3))) & 0xffu;
+}
+
+// 2-bit code of a valid symbol, or 4 for an invalid one.
+__device__ __forceinline__ u32 base_code(u32 c)
+{
+    c &= 0xdfu;  // fold case
+    return c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+}
+
+// Last '>' / '\n' in this thread's 16 bytes, encoded for a max-scan: ((pos_in_tile+1) << 1) | is_gt.
+__device__ __forceinline__ u32 chunk_last_event(const uint4 &d, u32 tid)
+{
+    u32 ev = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        u32 c = byte_of(d, j);
+        if (c == '>') ev = ((tid * 16 + j + 1) << 1) | 1u;
+        else if (c == '\n') ev = ((tid * 16 + j + 1) << 1);
+    }
+    return ev;
+}
+
+__global__ void __launch_bounds__(TILE_THREADS)
+fasta_summary_kernel(const uint4 *__restrict__ fasta, size_t ntiles, TileSummary *__restrict__ out)
+{
+    __shared__ u64 ws[33];
+    const size_t tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    const u32 tid = threadIdx.x;
+    const uint4 d = __ldg(fasta + tile * TILE_THREADS + tid);
+    const u32 my_ev = chunk_last_event(d, tid);
+    u64 tot_ev;
+    const u64 prev = block_excl_max<u64>((u64)my_ev, ws, &tot_ev);
+    int st = prev == 0 ? ST_UNK : ((prev & 1) ? ST_HDR : ST_SEQ);
+    u32 cc = 0, cp = 0, bc = 0, bp = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const u32 c = byte_of(d, j);
+        const bool gt = c == '>', nl = c == '\n', cr = c == '\r';
+        if (st == ST_HDR) {
+            if (nl) st = ST_SEQ;
+        } else if (st == ST_SEQ) {
+            if (gt) { cc++; bc++; st = ST_HDR; }
+            else if (!nl && !cr) cc++;
+        } else {
+            if (gt) { cp++; bp++; st = ST_HDR; }
+            else if (nl) st = ST_SEQ;
+            else if (!cr) cp++;
+        }
+    }
+    u64 packed = (u64)cc | ((u64)cp << 16) | ((u64)bc << 32) | ((u64)bp << 48);
+    u64 total;
+    (void)block_excl_sum<u64>(packed, ws, &total);
+    if (tid == 0) {
+        TileSummary s;
+        s.cnt_common = (u32)(total & 0xffffu);
+        s.cnt_pre = (u32)((total >> 16) & 0xffffu);
+        s.brk = (u32)((total >> 32) & 0xffffu) | ((u32)((total >> 48) & 0xffffu) << 16);
+        s.last_event = tot_ev == 0 ? 0u : ((tot_ev & 1) ? 2u : 1u);
+        out[tile] = s;
+    }
+}
+// NOTE on the 16-bit fields: a tile emits at most 16384 symbols, and the per-thread counters are summed
+// over the block in 16-bit lanes of one u64; 16384 < 65536 so no lane overflows into its neighbour.
+
+__global__ void __launch_bounds__(TILE_THREADS)
+fasta_scan_kernel(const TileSummary *__restrict__ summ, size_t ntiles, u64 *__restrict__ tile_base,
+                  uint8_t *__restrict__ tile_state, u64 *__restrict__ counts)
+{
+    __shared__ u64 ws[33];
+    const u32 tid = threadIdx.x;
+    int carry_state = ST_SEQ;
+    u64 carry_sym = 0, carry_brk = 0;
+    for (size_t base = 0; base < ntiles; base += TILE_THREADS) {
+        const size_t t = base + tid;
+        TileSummary s = {0, 0, 0, 0};
+        if (t < ntiles) s = summ[t];
+        const u64 e = s.last_event ? (((u64)(tid + 1) << 2) | s.last_event) : 0ull;
+        u64 tot_e;
+        const u64 prev = block_excl_max<u64>(e, ws, &tot_e);
+        const int s0 = prev ? (((prev & 3) == 2) ? ST_HDR : ST_SEQ) : carry_state;
+        const u32 cnt = s.cnt_common + (s0 == ST_SEQ ? s.cnt_pre : 0u);
+        const u32 brk = (s.brk & 0xffffu) + (s0 == ST_SEQ ? (s.brk >> 16) : 0u);
+        u64 total;
+        const u64 ex = block_excl_sum<u64>((u64)cnt | ((u64)brk << 32), ws, &total);
+        if (t < ntiles) {
+            tile_base[t] = carry_sym + (ex & 0xffffffffull);
+            tile_state[t] = (uint8_t)s0;
+        }
+        carry_sym += total & 0xffffffffull;
+        carry_brk += total >> 32;
+        if (tot_e) carry_state = ((tot_e & 3) == 2) ? ST_HDR : ST_SEQ;
+    }
+    if (tid == 0) {
+        tile_base[ntiles] = carry_sym;
+        counts[0] = carry_sym;              // stream symbols (bases + one break per header)
+        counts[1] = carry_brk;              // break symbols (= header lines)
+    }
+}
+
+#define CW_WORDS (TILE_BYTES / 16 + 4)   // u32 code words in shared memory (16 symbols each) + shift slack
+#define VW_WORDS (TILE_BYTES / 32 + 2)   // u32 validity words (32 symbols each)
+
+__global__ void __launch_bounds__(TILE_THREADS)
+fasta_pack_kernel(const uint4 *__restrict__ fasta, size_t ntiles, const u64 *__restrict__ tile_base,
+                  const uint8_t *__restrict__ tile_state, u64 *__restrict__ codes, u32 *__restrict__ valid)
+{
+    __shared__ u64 ws[33];
+    __shared__ u32 cw[CW_WORDS];
+    __shared__ u32 vw[VW_WORDS];
+    const size_t tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    const u32 tid = threadIdx.x;
+    for (u32 i = tid; i < CW_WORDS; i += TILE_THREADS) cw[i] = 0;
+    for (u32 i = tid; i < VW_WORDS; i += TILE_THREADS) vw[i] = 0;
+    const uint4 d = __ldg(fasta + tile * TILE_THREADS + tid);
+    const u32 my_ev = chunk_last_event(d, tid);
+    u64 tot_ev;
+    const u64 prev = block_excl_max<u64>((u64)my_ev, ws, &tot_ev);  // also orders the zero-fill above
+    int st = prev == 0 ? (int)tile_state[tile] : ((prev & 1) ? ST_HDR : ST_SEQ);
+    u32 frag_c = 0, frag_v = 0, n = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const u32 c = byte_of(d, j);
+        const bool gt = c == '>', nl = c == '\n', cr = c == '\r';
+        if (st == ST_HDR) {
+            if (nl) st = ST_SEQ;
+        } else {
+            if (gt) {
+                frag_c <<= 2; frag_v <<= 1; n++;      // break symbol: code 0, invalid
+                st = ST_HDR;
+            } else if (!nl && !cr) {
+                const u32 code = base_code(c);
+                frag_c = (frag_c << 2) | (code & 3u);
+                frag_v = (frag_v << 1) | (code < 4u ? 1u : 0u);
+                n++;
+            }
+        }
+    }
+    u64 total;
+    const u64 pos = block_excl_sum<u64>((u64)n, ws, &total);
+    const u32 cnt = (u32)total;
+    const u64 base = tile_base[tile];
+    const u32 shift = (u32)(base & 31ull);
+    if (n) {
+        const u32 p = (u32)pos + shift;
+        {   // codes: 2n bits at bit offset 2p (MSB-first)
+            const u32 b = 2u * p, w = b >> 5, s = b & 31u;
+            const u64 x = (u64)frag_c << (64u - 2u * n - s);
+            atomicOr(&cw[w], (u32)(x >> 32));
+            if ((u32)x) atomicOr(&cw[w + 1], (u32)x);
+        }
+        {   // validity: n bits at bit offset p
+            const u32 w = p >> 5, s = p & 31u;
+            const u64 y = (u64)frag_v << (64u - n - s);
+            if ((u32)(y >> 32)) atomicOr(&vw[w], (u32)(y >> 32));
+            if ((u32)y) atomicOr(&vw[w + 1], (u32)y);
+        }
+    }
+    __syncthreads();
+    if (cnt == 0) return;
+    const u32 n_units = (shift + cnt + 31u) >> 5;   // 32-symbol units touched by this tile (<= 513)
+    for (u32 u = tid; u < n_units; u += TILE_THREADS) {
+        const u64 g = (base >> 5) + u;
+        const u64 c64 = ((u64)cw[2 * u] << 32) | (u64)cw[2 * u + 1];
+        const u32 v32 = vw[u];
+        const bool full = (u > 0 || shift == 0) && ((u + 1) * 32u <= shift + cnt);
+        if (full) {
+            codes[g] = c64;
+            valid[g] = v32;
+        } else {
+            if (c64) atomicOr(&codes[g], c64);
+            if (v32) atomicOr(&valid[g], v32);
+        }
+    }
+}
+
+// Fill the gap between two staged files: '\n' (ends an unterminated header line), '>' (break symbol),
+// then '\n' up to the next tile-aligned file start.  One thread per gap byte, gaps are tiny.
+__global__ void fasta_separator_kernel(uint8_t *__restrict__ fasta, const u64 *__restrict__ file_begin,
+                                       const u64 *__restrict__ file_len, int nfiles, u64 total_bytes)
+{
+    const int f = blockIdx.x;
+    if (f >= nfiles) return;
+    const u64 from = file_begin[f] + file_len[f];
+    const u64 to = (f + 1 < nfiles) ? file_begin[f + 1] : total_bytes;
+    for (u64 i = from + threadIdx.x; i < to; i += blockDim.x) fasta[i] = (i == from + 1) ? '>' : '\n';
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+
+int khb_pack_fasta_impl(khb_ctx *ctx, const uint8_t *d_fasta, size_t nbytes, u64 *d_codes, u32 *d_valid,
+                        size_t cap_symbols, u64 *d_tile_base, u64 *d_counts)
+{
+    if (nbytes % TILE_BYTES) return khb_fail(ctx, KHB_ERR_ARG, "khb_pack_fasta: nbytes %zu is not a multiple of %d", nbytes, TILE_BYTES);
+    if (cap_symbols < nbytes) return khb_fail(ctx, KHB_ERR_CAPACITY, "khb_pack_fasta: cap_symbols %zu < nbytes %zu", cap_symbols, nbytes);
+    const size_t ntiles = nbytes / TILE_BYTES;
+    KHB_CUDA(ctx, cudaMemsetAsync(d_codes, 0, khb_codes_words(cap_symbols) * sizeof(u64), ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(d_valid, 0, khb_valid_words(cap_symbols) * sizeof(u32), ctx->stream));
+    if (ntiles == 0) {
+        KHB_CUDA(ctx, cudaMemsetAsync(d_tile_base, 0, sizeof(u64), ctx->stream));
+        KHB_CUDA(ctx, cudaMemsetAsync(d_counts, 0, 2 * sizeof(u64), ctx->stream));
+        return KHB_OK;
+    }
+    void *scr;
+    int rc = khb_scratch_get(ctx, SCR_TILE, ntiles * (sizeof(TileSummary) + 1) + 64, &scr);
+    if (rc) return rc;
+    TileSummary *summ = (TileSummary *)scr;
+    uint8_t *state = (uint8_t *)(summ + ntiles);
+    fasta_summary_kernel<<<(unsigned)ntiles, TILE_THREADS, 0, ctx->stream>>>((const uint4 *)d_fasta, ntiles, summ);
+    KHB_LAUNCH_CHECK(ctx);
+    fasta_scan_kernel<<<1, TILE_THREADS, 0, ctx->stream>>>(summ, ntiles, d_tile_base, state, d_counts);
+    KHB_LAUNCH_CHECK(ctx);
+    fasta_pack_kernel<<<(unsigned)ntiles, TILE_THREADS, 0, ctx->stream>>>((const uint4 *)d_fasta, ntiles, d_tile_base, state, d_codes, d_valid);
+    KHB_LAUNCH_CHECK(ctx);
+    return KHB_OK;
+}
+
+int khb_fasta_separators_impl(khb_ctx *ctx, uint8_t *d_fasta, const u64 *d_file_begin, const u64 *d_file_len,
+                              int nfiles, u64 total_bytes)
+{
+    if (nfiles <= 0) return KHB_OK;
+    fasta_separator_kernel<<<nfiles, 256, 0, ctx->stream>>>(d_fasta, d_file_begin, d_file_len, nfiles, total_bytes);
+    KHB_LAUNCH_CHECK(ctx);
+    return KHB_OK;
+}

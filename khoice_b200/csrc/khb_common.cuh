@@ -1,0 +1,168 @@
+// khb_common.cuh -- shared device/host helpers of libkhoice_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/khoice_b200.h"
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// ---- k-mer words ---------------------------------------------------------------------------
+// k <= 32 : one 64-bit word.  k <= 64 : 128-bit, stored little-endian (lo word first, 16-byte records).
+struct __align__(8) Key64 {
+    u64 v;
+};
+struct __align__(16) Key128 {
+    u64 lo, hi;
+};
+
+__host__ __device__ __forceinline__ bool key_eq(const Key64 &a, const Key64 &b) { return a.v == b.v; }
+__host__ __device__ __forceinline__ bool key_eq(const Key128 &a, const Key128 &b) { return a.lo == b.lo && a.hi == b.hi; }
+__host__ __device__ __forceinline__ bool key_is_sentinel(const Key64 &a) { return a.v == ~0ull; }
+__host__ __device__ __forceinline__ bool key_is_sentinel(const Key128 &a) { return (a.lo & a.hi) == ~0ull; }
+__host__ __device__ __forceinline__ u32 key_digit(const Key64 &a, int pass) { return (u32)(a.v >> (8 * pass)) & 0xffu; }
+__host__ __device__ __forceinline__ u32 key_digit(const Key128 &a, int pass)
+{
+    return (u32)((pass < 8 ? a.lo >> (8 * pass) : a.hi >> (8 * (pass - 8)))) & 0xffu;
+}
+
+// ---- context ------------------------------------------------------------------------------
+struct khb_scratch {
+    void *ptr;
+    size_t bytes;
+};
+
+struct khb_ctx {
+    int device;
+    int num_sms;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    char err[512];
+    int sticky;  // first CUDA error code seen (0 = none); CUDA errors are sticky per ctx
+    khb_scratch scratch[8];
+    // pinned host mailbox for small device->host results
+    u64 *h_mail;
+    u64 *d_mail;
+    // kernel launch counter (bench.py's gpu_launches)
+    u64 launches;
+    // accumulated group sets for the across-group stage (fused mode)
+    void *gs_buf;       // device buffer holding the concatenation of kept group sets
+    size_t gs_cap;      // capacity in keys
+    size_t gs_len;      // keys stored
+    int gs_k;           // k the stored sets were built with (0 = none)
+    int gs_groups;      // number of groups stored
+    // staging (fused host entry points)
+    uint8_t *stage_dev;
+    size_t stage_dev_cap;
+    uint8_t *stage_host;
+    size_t stage_host_cap;
+    // timing of the last fused call (ms, CUDA events on ctx->stream)
+    float last_ms[8];
+};
+
+enum { SCR_TILE = 0, SCR_LOOKBACK = 1, SCR_HIST = 2, SCR_MISC = 3, SCR_KEYS_A = 4, SCR_KEYS_B = 5, SCR_PACK = 6, SCR_FLAGS = 7 };
+
+int khb_fail(khb_ctx *ctx, int code, const char *fmt, ...);
+int khb_cuda_fail(khb_ctx *ctx, cudaError_t e, const char *what, const char *file, int line);
+int khb_scratch_get(khb_ctx *ctx, int slot, size_t bytes, void **out);
+
+#define KHB_CUDA(ctx, expr)                                                           \
+    do {                                                                              \
+        cudaError_t e__ = (expr);                                                     \
+        if (e__ != cudaSuccess) return khb_cuda_fail((ctx), e__, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define KHB_LAUNCH_CHECK(ctx)                                                         \
+    do {                                                                              \
+        (ctx)->launches++;                                                            \
+        cudaError_t e__ = cudaGetLastError();                                         \
+        if (e__ != cudaSuccess) return khb_cuda_fail((ctx), e__, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+#define KHB_CHECK_CTX(ctx)                                                            \
+    do {                                                                              \
+        if (!(ctx)) return KHB_ERR_ARG;                                               \
+        if ((ctx)->sticky) return KHB_ERR_CUDA;                                       \
+        KHB_CUDA((ctx), cudaSetDevice((ctx)->device));                                \
+    } while (0)
+
+static inline size_t div_up(size_t a, size_t b) { return (a + b - 1) / b; }
+
+// ---- warp / block scan helpers ---------------------------------------------------------------
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ u32 lanemask_lt()
+{
+    u32 m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_incl_sum(T v)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane_id() >= (u32)o) v += n;
+    }
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_incl_max(T v)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane_id() >= (u32)o) v = n > v ? n : v;
+    }
+    return v;
+}
+
+// Block-wide exclusive sum over blockDim.x threads (multiple of 32, <= 1024).
+// `ws` is a 33-entry shared array.  Returns the exclusive prefix; *total = block sum.
+template <typename T>
+__device__ __forceinline__ T block_excl_sum(T v, T *ws, T *total)
+{
+    const u32 w = threadIdx.x >> 5, l = lane_id(), nw = blockDim.x >> 5;
+    T inc = warp_incl_sum(v);
+    if (l == 31) ws[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        T x = l < nw ? ws[l] : (T)0;
+        T xi = warp_incl_sum(x);
+        ws[l] = xi - x;
+        if (l == 31) ws[32] = xi;
+    }
+    __syncthreads();
+    T r = ws[w] + inc - v;
+    *total = ws[32];
+    __syncthreads();
+    return r;
+}
+// Block-wide exclusive max (identity 0).
+template <typename T>
+__device__ __forceinline__ T block_excl_max(T v, T *ws, T *total)
+{
+    const u32 w = threadIdx.x >> 5, l = lane_id(), nw = blockDim.x >> 5;
+    T inc = warp_incl_max(v);
+    T up = __shfl_up_sync(0xffffffffu, inc, 1);
+    T exc = l == 0 ? (T)0 : up;
+    if (l == 31) ws[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        T x = l < nw ? ws[l] : (T)0;
+        T xi = warp_incl_max(x);
+        T xu = __shfl_up_sync(0xffffffffu, xi, 1);
+        ws[l] = l == 0 ? (T)0 : xu;
+        if (l == 31) ws[32] = xi;
+    }
+    __syncthreads();
+    T base = ws[w];
+    T r = base > exc ? base : exc;
+    *total = ws[32];
+    __syncthreads();
+    return r;
+}

@@ -1,0 +1,115 @@
+// kmer_extract.cu -- K2: canonical k-mer of every window of the packed symbol stream.
+//
+// Replaces KMC's splitter / k-mer enumeration (`kmc -k{k}` without -b, reference call site
+// /root/reference/workflow/rules/exp_type_1.smk:163; rule R5 of SURVEY.md section 8c): the value of a
+// k-mer is its base-4 number with the first base most significant, the canonical form is
+// min(k-mer, reverse complement) (the reference's own statement: /root/reference/src/merge_lists.py:60-73).
+//
+// Because K1 packs MSB-first, the forward k-mer of the window starting at symbol i is the bit range
+// [2i, 2i+2k) of the code stream: two funnel shifts, no rolling dependency.  The reverse complement is
+// a complement + bit reversal (BREV) + swap inside each 2-bit pair.  A window is valid iff its k
+// validity bits are all ones.  Output index = window start, so the kernel is a pure streaming map:
+// invalid windows get the all-ones sentinel, which is never a canonical k-mer (T^k's reverse complement
+// A^k = 0 is smaller) and therefore sorts behind every real key and is dropped by the unique pass.
+//
+// Algorithmic bytes: B/4 + B/8 read, W bytes per window written (W = 8 for k <= 32, 16 for k <= 64).
+#include "khb_common.cuh"
+
+__device__ __forceinline__ u64 swap_pairs(u64 r)
+{
+    return ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+}
+
+// k <= 32.  One thread produces the two windows starting at i and i+1 (i even) -> one 16-byte store.
+__global__ void __launch_bounds__(256)
+extract64_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, size_t n_sym, int k,
+                 ulonglong2 *__restrict__ out)
+{
+    const size_t npairs = (n_sym + 1) >> 1;
+    const u64 ones_k = k == 64 ? ~0ull : ((1ull << k) - 1ull);
+    const int rs = 64 - 2 * k;  // right shift that brings the 2k window bits to the low end
+    for (size_t pr = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pr < npairs; pr += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = pr << 1;
+        const size_t m = i >> 5;
+        const u32 o = (u32)(i & 31);  // even, <= 30
+        const u64 c0 = __ldg(codes + m), c1 = __ldg(codes + m + 1);
+        const u64 vv = ((u64)__ldg(valid + m) << 32) | (u64)__ldg(valid + m + 1);
+        u64 res[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            const u32 ot = o + t;  // <= 31
+            const u64 x = ot ? ((c0 << (2 * ot)) | (c1 >> (64 - 2 * ot))) : c0;
+            const u64 fwd = x >> rs;
+            u64 rc = swap_pairs(__brevll(~x) << rs >> rs);
+            // note: ~x has the complemented window in its top 2k bits; brev moves them to the low 2k bits
+            // (reversed), the shift pair clears the bits that came from below the window.
+            const bool ok = (((vv << ot) >> (64 - k)) == ones_k) && (i + t < n_sym);
+            const u64 can = fwd < rc ? fwd : rc;
+            res[t] = ok ? can : ~0ull;
+        }
+        if (i + 1 < n_sym) {
+            out[pr] = make_ulonglong2(res[0], res[1]);
+        } else {
+            ((u64 *)out)[i] = res[0];
+        }
+    }
+}
+
+// 33 <= k <= 64.  One thread per window -> one 16-byte store (lo, hi).
+__global__ void __launch_bounds__(256)
+extract128_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, size_t n_sym, int k,
+                  ulonglong2 *__restrict__ out)
+{
+    const u64 ones_k = k == 64 ? ~0ull : ((1ull << k) - 1ull);
+    const int rs = 128 - 2 * k;  // 0..62
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sym; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t m = i >> 5;
+        const u32 o = (u32)(i & 31);
+        const u64 c0 = __ldg(codes + m), c1 = __ldg(codes + m + 1), c2 = __ldg(codes + m + 2);
+        const u64 va = ((u64)__ldg(valid + m) << 32) | (u64)__ldg(valid + m + 1);
+        const u64 vb = ((u64)__ldg(valid + m + 2) << 32) | (u64)__ldg(valid + m + 3);
+        // 128-bit window starting at bit 2o of (c0:c1:c2)
+        const u64 xh = o ? ((c0 << (2 * o)) | (c1 >> (64 - 2 * o))) : c0;
+        const u64 xl = o ? ((c1 << (2 * o)) | (c2 >> (64 - 2 * o))) : c1;
+        // forward value = (xh:xl) >> rs
+        const u64 fh = xh >> rs;
+        const u64 fl = rs ? ((xl >> rs) | (xh << (64 - rs))) : xl;
+        // reverse complement: bit-reverse the complemented 128-bit window, keep its low 2k bits, fix pairs
+        const u64 nh = ~xh, nl = ~xl;
+        const u64 bh = __brevll(nl), bl = __brevll(nh);   // reversed (bh:bl); window bits now lowest
+        u64 rh, rl;
+        if (rs) {
+            // clear the 128-2k top bits that came from below the window
+            rh = (bh << rs) >> rs;
+            rl = bl;
+        } else {
+            rh = bh;
+            rl = bl;
+        }
+        rh = swap_pairs(rh);
+        rl = swap_pairs(rl);
+        const u64 vwin = o ? ((va << o) | (vb >> (64 - o))) : va;
+        const bool ok = ((vwin >> (64 - k)) == ones_k);
+        const bool f_lt = fh < rh || (fh == rh && fl < rl);
+        ulonglong2 r;
+        r.x = ok ? (f_lt ? fl : rl) : ~0ull;   // lo
+        r.y = ok ? (f_lt ? fh : rh) : ~0ull;   // hi
+        out[i] = r;
+    }
+}
+
+int khb_extract_kmers_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, size_t n_sym, int k, void *d_keys)
+{
+    if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_extract_kmers: k=%d outside 1..64", k);
+    if (n_sym == 0) return KHB_OK;
+    const size_t work = k <= 32 ? (n_sym + 1) / 2 : n_sym;
+    size_t blocks = div_up(work, 256);
+    const size_t cap = (size_t)ctx->num_sms * 32;
+    if (blocks > cap) blocks = cap;
+    if (k <= 32)
+        extract64_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_codes, d_valid, n_sym, k, (ulonglong2 *)d_keys);
+    else
+        extract128_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_codes, d_valid, n_sym, k, (ulonglong2 *)d_keys);
+    KHB_LAUNCH_CHECK(ctx);
+    return KHB_OK;
+}

@@ -1,0 +1,356 @@
+"""ctypes binding of libkhoice_b200.so (include/khoice_b200.h) -- the only way the Python host code
+reaches the GPU.  There is no CPU fallback: if the library is missing, or no B200 is visible,
+construction of :class:`Engine` raises :class:`KhbError`.
+
+The reference reaches its engine by exec'ing the KMC command line tools from Snakemake rules
+(/root/reference/workflow/rules/exp_type_1.smk:156-259); ``Engine.group_from_fasta`` /
+``Engine.across_groups`` are the fused equivalents of those rule chains, the remaining methods expose
+the individual kernels for the rule-compatible mode (khoice_b200/cli.py) and for the parity tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libkhoice_b200.so")
+CSRC = os.path.join(_PKG, "csrc")
+
+FASTA_TILE = 16384
+COUNTER_MAX = 5000  # -cs5000, exp_type_1.smk:61,84
+
+ERRORS = {0: "ok", -1: "invalid argument", -2: "CUDA error", -3: "out of memory", -4: "no CUDA device",
+          -5: "buffer too small", -6: "call sequence error"}
+
+
+class KhbError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"khoice_b200 error {code} ({ERRORS.get(code, '?')}): {message}")
+        self.code = code
+
+
+class Stats(C.Structure):
+    """Mirror of ``khb_stats``."""
+    _fields_ = [("fasta_bytes", C.c_uint64), ("bases", C.c_uint64), ("windows", C.c_uint64),
+                ("genome_distinct", C.c_uint64), ("distinct", C.c_uint64), ("ms_total", C.c_float),
+                ("ms_h2d", C.c_float), ("ms_pack", C.c_float), ("ms_extract", C.c_float), ("ms_sort1", C.c_float),
+                ("ms_unique", C.c_float), ("ms_sort2", C.c_float), ("ms_count", C.c_float)]
+
+    def as_dict(self) -> dict:
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+# every symbol include/khoice_b200.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+_SIGNATURES = [
+    ("khb_abi_version", C.c_int, []),
+    ("khb_init", C.c_int, [C.c_int, C.POINTER(_P)]),
+    ("khb_destroy", C.c_int, [_P]),
+    ("khb_last_error", C.c_char_p, [_P]),
+    ("khb_device_info", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    ("khb_launch_count", C.c_uint64, [_P]),
+    ("khb_stream", _P, [_P]),
+    ("khb_alloc", C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+    ("khb_free", C.c_int, [_P, _P]),
+    ("khb_alloc_host", C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+    ("khb_free_host", C.c_int, [_P, _P]),
+    ("khb_memcpy_h2d", C.c_int, [_P, _P, _P, C.c_size_t]),
+    ("khb_memcpy_d2h", C.c_int, [_P, _P, _P, C.c_size_t]),
+    ("khb_memset", C.c_int, [_P, _P, C.c_int, C.c_size_t]),
+    ("khb_sync", C.c_int, [_P]),
+    ("khb_staged_size", C.c_size_t, [C.c_int, _P]),
+    ("khb_stage_fasta", C.c_int, [_P, C.c_int, _P, _P, _P, C.c_size_t, _P]),
+    ("khb_pack_fasta", C.c_int, [_P, _P, C.c_size_t, _P, _P, C.c_size_t, _P, _P]),
+    ("khb_extract_kmers", C.c_int, [_P, _P, _P, C.c_size_t, C.c_int, _P]),
+    ("khb_sort_keys", C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    ("khb_unique", C.c_int, [_P, _P, C.c_size_t, C.c_int, _P, C.POINTER(C.c_uint64)]),
+    ("khb_count_runs", C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_uint32, C.c_uint32, _P, _P, _P, C.POINTER(C.c_uint64)]),
+    ("khb_group_from_fasta", C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_uint32, _P, C.c_int, C.POINTER(Stats)]),
+    ("khb_group_from_staged", C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_uint32, _P, C.c_int, C.POINTER(Stats)]),
+    ("khb_across_groups", C.c_int, [_P, C.c_uint32, _P, C.POINTER(Stats)]),
+    ("khb_group_sets_info", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
+    ("khb_group_sets_device", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    ("khb_group_sets_append_device", C.c_int, [_P, C.c_int, _P, C.c_uint64, C.c_int]),
+    ("khb_group_sets_append_host", C.c_int, [_P, C.c_int, _P, C.c_uint64, C.c_int]),
+    ("khb_group_sets_reset", C.c_int, [_P]),
+    ("khb_partition_by_hash", C.c_int, [_P, _P, C.c_uint64, C.c_int, C.c_int, _P, _P]),
+]
+EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
+
+_lib = None
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libkhoice_b200.so for sm_100a with nvcc (khoice_b200/csrc/Makefile)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(_PKG, "..", "include", "khoice_b200.h"))
+    newest = max(os.path.getmtime(s) for s in srcs)
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
+        r = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+        if verbose or r.returncode:
+            print(r.stdout[-4000:], r.stderr[-4000:])
+        if r.returncode:
+            raise RuntimeError("nvcc build of libkhoice_b200.so failed")
+    return LIB_PATH
+
+
+def load_library():
+    """dlopen the library and attach signatures.  Fails loudly when it is missing (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise KhbError(-4, f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(nvcc, sm_100a). There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, res, args in _SIGNATURES:
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def key_words(k: int) -> int:
+    return 1 if k <= 32 else 2
+
+
+def key_shape(n: int, k: int):
+    return (n,) if k <= 32 else (n, 2)
+
+
+class DeviceBuffer:
+    """A khb_alloc'd device buffer."""
+
+    def __init__(self, eng: "Engine", nbytes: int):
+        self.eng = eng
+        self.nbytes = int(nbytes)
+        p = _P()
+        eng._chk(eng.lib.khb_alloc(eng.ctx, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def free(self):
+        if self.ptr:
+            self.eng.lib.khb_free(self.eng.ctx, self.ptr)
+            self.ptr = None
+
+    def upload(self, arr: np.ndarray, offset: int = 0):
+        arr = np.ascontiguousarray(arr)
+        assert offset + arr.nbytes <= self.nbytes
+        self.eng._chk(self.eng.lib.khb_memcpy_h2d(self.eng.ctx, self.ptr + offset, arr.ctypes.data, arr.nbytes))
+        self.eng.sync()
+
+    def download(self, dtype, count: int, offset: int = 0) -> np.ndarray:
+        out = np.empty(count, dtype=dtype)
+        assert offset + out.nbytes <= self.nbytes
+        if out.nbytes:
+            self.eng._chk(self.eng.lib.khb_memcpy_d2h(self.eng.ctx, out.ctypes.data, self.ptr + offset, out.nbytes))
+            self.eng.sync()
+        return out
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+@dataclass
+class StagedFasta:
+    buf: DeviceBuffer
+    begin: np.ndarray  # uint64 [n_files+1], byte offsets (multiples of FASTA_TILE)
+
+    @property
+    def nbytes(self) -> int:
+        return int(self.begin[-1])
+
+
+class Engine:
+    """One context on one B200.  All methods are synchronous unless stated otherwise."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.ctx = _P()
+        rc = self.lib.khb_init(device, C.byref(self.ctx))
+        if rc != 0:
+            msg = self.lib.khb_last_error(None)
+            self.ctx = None
+            raise KhbError(rc, msg.decode() if msg else "")
+        self.device = device
+
+    # -- plumbing -------------------------------------------------------------------------------------
+    def _chk(self, rc: int):
+        if rc != 0:
+            msg = self.lib.khb_last_error(self.ctx)
+            raise KhbError(rc, msg.decode() if msg else "")
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.khb_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._chk(self.lib.khb_sync(self.ctx))
+
+    def alloc(self, nbytes: int) -> DeviceBuffer:
+        return DeviceBuffer(self, max(int(nbytes), 16))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.khb_launch_count(self.ctx))
+
+    def device_info(self) -> dict:
+        sms, fr, tot = C.c_int(), C.c_size_t(), C.c_size_t()
+        self._chk(self.lib.khb_device_info(self.ctx, C.byref(sms), C.byref(fr), C.byref(tot)))
+        return {"num_sms": sms.value, "free_bytes": fr.value, "total_bytes": tot.value}
+
+    @staticmethod
+    def _file_tables(files: Sequence):
+        arrs = [np.frombuffer(f, dtype=np.uint8) if isinstance(f, (bytes, bytearray, memoryview)) else np.ascontiguousarray(f, dtype=np.uint8)
+                for f in files]
+        n = len(arrs)
+        ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data if a.size else None for a in arrs])
+        sizes = (C.c_size_t * max(n, 1))(*[a.size for a in arrs])
+        return arrs, ptrs, sizes
+
+    # -- kernels -----------------------------------------------------------------------------------------
+    def stage_fasta(self, files: Sequence) -> StagedFasta:
+        """Host FASTA texts -> device staging buffer (tile-aligned, separator-filled)."""
+        arrs, ptrs, sizes = self._file_tables(files)
+        n = len(arrs)
+        total = int(self.lib.khb_staged_size(n, sizes))
+        buf = self.alloc(total)
+        begin = np.zeros(n + 1, dtype=np.uint64)
+        self._chk(self.lib.khb_stage_fasta(self.ctx, n, ptrs, sizes, buf.ptr, buf.nbytes, begin.ctypes.data))
+        self.sync()
+        return StagedFasta(buf, begin)
+
+    def pack_fasta(self, staged: StagedFasta):
+        """K1.  Returns dict(codes, valid (DeviceBuffers), n_symbols, n_breaks, tile_base (np.uint64))."""
+        nbytes = staged.nbytes
+        ntiles = nbytes // FASTA_TILE
+        cw, vw = nbytes // 32 + 4, nbytes // 32 + 4
+        codes, valid = self.alloc(cw * 8), self.alloc(vw * 4)
+        tile_base, counts = self.alloc((ntiles + 1) * 8), self.alloc(16)
+        self._chk(self.lib.khb_pack_fasta(self.ctx, staged.buf.ptr, nbytes, codes.ptr, valid.ptr, nbytes, tile_base.ptr, counts.ptr))
+        cnt = counts.download(np.uint64, 2)
+        tb = tile_base.download(np.uint64, ntiles + 1)
+        return {"codes": codes, "valid": valid, "n_symbols": int(cnt[0]), "n_breaks": int(cnt[1]), "tile_base": tb,
+                "codes_words": cw, "valid_words": vw}
+
+    def extract_kmers(self, packed: dict, k: int) -> DeviceBuffer:
+        """K2.  Returns a DeviceBuffer of n_symbols k-mer words (sentinel = all ones)."""
+        n = packed["n_symbols"]
+        keys = self.alloc((n + 4) * 8 * key_words(k))
+        self._chk(self.lib.khb_extract_kmers(self.ctx, packed["codes"].ptr, packed["valid"].ptr, n, k, keys.ptr))
+        self.sync()
+        return keys
+
+    def sort_keys(self, keys: DeviceBuffer, n: int, k: int, seg_off: Optional[Sequence[int]] = None) -> DeviceBuffer:
+        """K3.  Sorts segments of `keys` (default: one segment [0, n)); returns the buffer holding the result."""
+        seg = np.ascontiguousarray(seg_off if seg_off is not None else [0, n], dtype=np.uint64)
+        tmp = self.alloc(keys.nbytes)
+        flag = C.c_int(0)
+        self._chk(self.lib.khb_sort_keys(self.ctx, keys.ptr, tmp.ptr, seg.ctypes.data, len(seg) - 1, k, C.byref(flag)))
+        self.sync()
+        if flag.value:
+            return tmp
+        tmp.free()
+        return keys
+
+    def unique(self, sorted_keys: DeviceBuffer, n: int, k: int) -> Tuple[DeviceBuffer, int]:
+        """K4.  Returns (buffer of distinct non-sentinel keys, count)."""
+        out = self.alloc(sorted_keys.nbytes)
+        cnt = C.c_uint64(0)
+        self._chk(self.lib.khb_unique(self.ctx, sorted_keys.ptr, n, k, out.ptr, C.byref(cnt)))
+        return out, int(cnt.value)
+
+    def count_runs(self, sorted_keys: DeviceBuffer, n: int, k: int, nbins: int = COUNTER_MAX, cs: int = COUNTER_MAX,
+                   want_keys: bool = False, want_counts: bool = False):
+        """K5/K6.  Returns (hist uint64[nbins+1], n_distinct, keys DeviceBuffer|None, counts DeviceBuffer|None)."""
+        hist = np.zeros(nbins + 1, dtype=np.uint64)
+        runs = C.c_uint64(0)
+        ok = self.alloc(sorted_keys.nbytes) if want_keys else None
+        oc = self.alloc(max(n, 1) * 4) if want_counts else None
+        self._chk(self.lib.khb_count_runs(self.ctx, sorted_keys.ptr, n, k, cs, nbins, hist.ctypes.data,
+                                          ok.ptr if ok else None, oc.ptr if oc else None, C.byref(runs)))
+        return hist, int(runs.value), ok, oc
+
+    def partition_by_hash(self, keys: DeviceBuffer, n: int, k: int, n_parts: int) -> Tuple[DeviceBuffer, np.ndarray]:
+        """K7.  Returns (keys grouped by hash bucket, uint64 bucket offsets [n_parts+1])."""
+        out = self.alloc(keys.nbytes)
+        off = np.zeros(n_parts + 1, dtype=np.uint64)
+        self._chk(self.lib.khb_partition_by_hash(self.ctx, keys.ptr, n, k, n_parts, out.ptr, off.ctypes.data))
+        self.sync()
+        return out, off
+
+    # -- fused stages ------------------------------------------------------------------------------------
+    def group_from_fasta(self, files: Sequence, k: int, nbins: int = COUNTER_MAX, keep_set: bool = True):
+        """Rules build_kmc_database_on_genome .. within_group_union_histogram (+ build_group_kmer_set) for one
+        (k, group), from FASTA texts in host memory.  Returns (step_4 histogram uint64[nbins+1], stats dict)."""
+        arrs, ptrs, sizes = self._file_tables(files)
+        hist = np.zeros(nbins + 1, dtype=np.uint64)
+        st = Stats()
+        self._chk(self.lib.khb_group_from_fasta(self.ctx, k, len(arrs), ptrs, sizes, nbins, hist.ctypes.data, int(keep_set), C.byref(st)))
+        return hist, st.as_dict()
+
+    def group_from_staged(self, staged: StagedFasta, k: int, nbins: int = COUNTER_MAX, keep_set: bool = True,
+                          first: int = 0, count: Optional[int] = None):
+        """Same stage on text already resident in HBM (files first .. first+count of `staged`)."""
+        n = (len(staged.begin) - 1 - first) if count is None else count
+        base = int(staged.begin[first])
+        begin = np.ascontiguousarray(staged.begin[first:first + n + 1] - np.uint64(base), dtype=np.uint64)
+        hist = np.zeros(nbins + 1, dtype=np.uint64)
+        st = Stats()
+        self._chk(self.lib.khb_group_from_staged(self.ctx, k, n, staged.buf.ptr + base, begin.ctypes.data, nbins,
+                                                 hist.ctypes.data, int(keep_set), C.byref(st)))
+        return hist, st.as_dict()
+
+    def across_groups(self, nbins: int = COUNTER_MAX):
+        """Rules across_group_union + across_group_union_histogram for one k over the retained group sets."""
+        hist = np.zeros(nbins + 1, dtype=np.uint64)
+        st = Stats()
+        self._chk(self.lib.khb_across_groups(self.ctx, nbins, hist.ctypes.data, C.byref(st)))
+        return hist, st.as_dict()
+
+    def group_sets_info(self) -> dict:
+        k, g, n = C.c_int(), C.c_int(), C.c_uint64()
+        self._chk(self.lib.khb_group_sets_info(self.ctx, C.byref(k), C.byref(g), C.byref(n)))
+        return {"k": k.value, "n_groups": g.value, "n_keys": n.value}
+
+    def group_sets_download(self) -> np.ndarray:
+        """Concatenation of the retained group sets (each sorted) as host k-mer words."""
+        info = self.group_sets_info()
+        p, n = _P(), C.c_uint64()
+        self._chk(self.lib.khb_group_sets_device(self.ctx, C.byref(p), C.byref(n)))
+        w = key_words(info["k"]) if info["k"] else 1
+        out = np.empty(int(n.value) * w, dtype=np.uint64)
+        if out.nbytes:
+            self._chk(self.lib.khb_memcpy_d2h(self.ctx, out.ctypes.data, p.value, out.nbytes))
+            self.sync()
+        return out.reshape(key_shape(int(n.value), info["k"] or 1))
+
+    def group_sets_device(self) -> Tuple[int, int]:
+        p, n = _P(), C.c_uint64()
+        self._chk(self.lib.khb_group_sets_device(self.ctx, C.byref(p), C.byref(n)))
+        return (p.value or 0), int(n.value)
+
+    def group_sets_append_host(self, keys: np.ndarray, k: int, n_groups: int = 1):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        self._chk(self.lib.khb_group_sets_append_host(self.ctx, k, keys.ctypes.data, keys.shape[0], n_groups))
+
+    def group_sets_append_device(self, ptr: int, n_keys: int, k: int, n_groups: int = 1):
+        self._chk(self.lib.khb_group_sets_append_device(self.ctx, k, ptr, n_keys, n_groups))
+
+    def group_sets_reset(self):
+        self._chk(self.lib.khb_group_sets_reset(self.ctx))

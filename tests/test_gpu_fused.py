@@ -1,0 +1,75 @@
+"""Fused per-group / across-group stages against the CPU oracle (bit-exact histograms and sets)."""
+import numpy as np
+import pytest
+
+from helpers import EDGE_FASTAS, random_fasta, sort_rows
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_group_sets(oracle, groups, k):
+    sets = []
+    for genomes in groups:
+        keys, _ = oracle.union_sum([oracle.genome_set(g, k) for g in genomes], k)
+        sets.append(keys)
+    return sets
+
+
+@pytest.mark.parametrize("k", [3, 5, 13, 21, 31, 32, 33, 47, 63])
+def test_small_groups_match_oracle(engine, oracle, k):
+    from khoice_b200 import synth
+    cfg = synth.SynthConfig(n_groups=3, genomes_per_group=4, genome_len=60_000, seed=77)
+    groups = [[synth.make_genome(cfg, g, i) for i in range(1, 5)] for g in range(1, 4)]
+    groups[1].append(EDGE_FASTAS[1] + EDGE_FASTAS[3])   # ragged extra genome with N runs / IUPAC
+    groups[2].append(b"")                               # an empty file is a legal (empty) genome
+    flat = [g for grp in groups for g in grp]
+    gid = [i for i, grp in enumerate(groups) for _ in grp]
+    w_ref, a_ref, st_ref = oracle.exp1(flat, gid, len(groups), k)
+    engine.group_sets_reset()
+    tot_bases = 0
+    for i, grp in enumerate(groups):
+        hist, st = engine.group_from_fasta(grp, k)
+        assert np.array_equal(hist, w_ref[i]), f"group {i} within-group histogram"
+        tot_bases += st["bases"]
+    assert tot_bases == st_ref["symbols"]
+    info = engine.group_sets_info()
+    assert info["n_groups"] == len(groups) and info["k"] == k
+    assert info["n_keys"] == st_ref["sum_group_distinct"]
+    sets = engine.group_sets_download()
+    ref_sets = _oracle_group_sets(oracle, groups, k)
+    assert np.array_equal(sets, np.concatenate(ref_sets, axis=0))
+    hist, st = engine.across_groups()
+    assert np.array_equal(hist, a_ref)
+    assert st["distinct"] == st_ref["distinct"]
+
+
+def test_staged_equals_host_path(engine, oracle):
+    rng = np.random.default_rng(9)
+    files = [random_fasta(rng, 50_000) for _ in range(5)]
+    engine.group_sets_reset()
+    h1, s1 = engine.group_from_fasta(files, 31, keep_set=False)
+    st = engine.stage_fasta(files)
+    h2, s2 = engine.group_from_staged(st, 31, keep_set=False)
+    assert np.array_equal(h1, h2) and s1["distinct"] == s2["distinct"]
+    # sub-range of a staged buffer = that subset of genomes
+    h3, _ = engine.group_from_staged(st, 31, keep_set=False, first=1, count=3)
+    h4, _ = engine.group_from_fasta(files[1:4], 31, keep_set=False)
+    assert np.array_equal(h3, h4)
+
+
+def test_config1_full_size_matches_oracle(engine, oracle):
+    """BASELINE config 1: 2 groups x 5 genomes x 5 Mbp, k=31 -- oracle finishes in seconds."""
+    from khoice_b200 import synth
+    cfg = synth.SynthConfig(n_groups=2, genomes_per_group=5, genome_len=5_000_000)
+    groups = [[synth.make_genome(cfg, g, i) for i in range(1, 6)] for g in range(1, 3)]
+    flat = [g for grp in groups for g in grp]
+    gid = [i for i, grp in enumerate(groups) for _ in grp]
+    w_ref, a_ref, st_ref = oracle.exp1(flat, gid, 2, 31)
+    engine.group_sets_reset()
+    for i, grp in enumerate(groups):
+        hist, st = engine.group_from_fasta(grp, 31)
+        assert np.array_equal(hist, w_ref[i])
+    hist, st = engine.across_groups()
+    assert np.array_equal(hist, a_ref)
+    # size-independent properties: every distinct k-mer is counted once; occupancy <= members
+    assert int(hist.sum()) == st_ref["distinct"] and not hist[3:].any()
