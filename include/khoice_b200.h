@@ -30,6 +30,7 @@ extern "C" {
 #endif
 
 #define KHB_ABI_VERSION 1
+#define KHB_API __attribute__((visibility("default")))
 
 #define KHB_OK 0
 #define KHB_ERR_ARG (-1)      /* invalid argument                                   */
@@ -52,23 +53,23 @@ static inline int khb_key_bytes(int k) { return k <= 32 ? 8 : 16; }
 typedef struct khb_ctx khb_ctx;
 
 /* ---- context ------------------------------------------------------------------------------------- */
-int khb_abi_version(void);
-int khb_init(int device, khb_ctx **ctx);
-int khb_destroy(khb_ctx *ctx);
-const char *khb_last_error(const khb_ctx *ctx); /* ctx may be NULL: message of the last failed khb_init */
-int khb_device_info(khb_ctx *ctx, int *num_sms, size_t *free_bytes, size_t *total_bytes);
-uint64_t khb_launch_count(const khb_ctx *ctx); /* kernels launched on this context so far */
-void *khb_stream(khb_ctx *ctx);                /* the cudaStream_t all work is enqueued on */
+KHB_API int khb_abi_version(void);
+KHB_API int khb_init(int device, khb_ctx **ctx);
+KHB_API int khb_destroy(khb_ctx *ctx);
+KHB_API const char *khb_last_error(const khb_ctx *ctx); /* ctx may be NULL: message of the last failed khb_init */
+KHB_API int khb_device_info(khb_ctx *ctx, int *num_sms, size_t *free_bytes, size_t *total_bytes);
+KHB_API uint64_t khb_launch_count(const khb_ctx *ctx); /* kernels launched on this context so far */
+KHB_API void *khb_stream(khb_ctx *ctx);                /* the cudaStream_t all work is enqueued on */
 
 /* ---- memory ------------------------------------------------------------------------------------------ */
-int khb_alloc(khb_ctx *ctx, size_t bytes, void **d_ptr);
-int khb_free(khb_ctx *ctx, void *d_ptr);
-int khb_alloc_host(khb_ctx *ctx, size_t bytes, void **h_ptr); /* pinned */
-int khb_free_host(khb_ctx *ctx, void *h_ptr);
-int khb_memcpy_h2d(khb_ctx *ctx, void *d_dst, const void *h_src, size_t bytes); /* async on the ctx stream */
-int khb_memcpy_d2h(khb_ctx *ctx, void *h_dst, const void *d_src, size_t bytes); /* async on the ctx stream */
-int khb_memset(khb_ctx *ctx, void *d_dst, int value, size_t bytes);
-int khb_sync(khb_ctx *ctx);
+KHB_API int khb_alloc(khb_ctx *ctx, size_t bytes, void **d_ptr);
+KHB_API int khb_free(khb_ctx *ctx, void *d_ptr);
+KHB_API int khb_alloc_host(khb_ctx *ctx, size_t bytes, void **h_ptr); /* pinned */
+KHB_API int khb_free_host(khb_ctx *ctx, void *h_ptr);
+KHB_API int khb_memcpy_h2d(khb_ctx *ctx, void *d_dst, const void *h_src, size_t bytes); /* async on the ctx stream */
+KHB_API int khb_memcpy_d2h(khb_ctx *ctx, void *h_dst, const void *d_src, size_t bytes); /* async on the ctx stream */
+KHB_API int khb_memset(khb_ctx *ctx, void *d_dst, int value, size_t bytes);
+KHB_API int khb_sync(khb_ctx *ctx);
 
 /* ---- kernels (device buffers in, device buffers out) ----------------------------------------------- */
 
@@ -77,8 +78,8 @@ int khb_sync(khb_ctx *ctx);
  * byte offset of every file (h_begin[n_files] = staged size, a multiple of KHB_FASTA_TILE).
  * khb_staged_size() returns that size without copying.  Replaces: kmc reading {genome}.fna.gz
  * (exp_type_1.smk:158,163); inflating .gz is the caller's job. */
-size_t khb_staged_size(int n_files, const size_t *h_sizes);
-int khb_stage_fasta(khb_ctx *ctx, int n_files, const uint8_t *const *h_files, const size_t *h_sizes,
+KHB_API size_t khb_staged_size(int n_files, const size_t *h_sizes);
+KHB_API int khb_stage_fasta(khb_ctx *ctx, int n_files, const uint8_t *const *h_files, const size_t *h_sizes,
                     uint8_t *d_fasta, size_t d_capacity, uint64_t *h_begin);
 
 /* K1: FASTA text -> 2-bit codes + validity bits (`kmc -fm` input stage, exp_type_1.smk:163).
@@ -87,22 +88,22 @@ int khb_stage_fasta(khb_ctx *ctx, int n_files, const uint8_t *const *h_files, co
  * receives the symbol offset of every text tile (so the symbol range of a staged file starts at
  * d_tile_base[h_begin[f] / KHB_FASTA_TILE]); d_counts[0] = symbols in the stream, d_counts[1] = break
  * symbols (one per header line; bases = d_counts[0] - d_counts[1]). */
-int khb_pack_fasta(khb_ctx *ctx, const uint8_t *d_fasta, size_t nbytes, uint64_t *d_codes, uint32_t *d_valid,
+KHB_API int khb_pack_fasta(khb_ctx *ctx, const uint8_t *d_fasta, size_t nbytes, uint64_t *d_codes, uint32_t *d_valid,
                    size_t cap_symbols, uint64_t *d_tile_base, uint64_t *d_counts);
 
 /* K2: canonical k-mer of the window starting at every symbol (`kmc -k{k}`, both strands, exp_type_1.smk:163).
  * d_keys[i] (khb_key_bytes(k) bytes each, n_symbols entries) = canonical k-mer or the sentinel. */
-int khb_extract_kmers(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, size_t n_symbols, int k,
+KHB_API int khb_extract_kmers(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, size_t n_symbols, int k,
                       void *d_keys);
 
 /* K3: sort every segment [h_seg_off[s], h_seg_off[s+1]) of d_keys independently (LSD radix, ceil(2k/8)
  * passes).  d_tmp is a same-sized ping-pong buffer; *result_in_tmp tells where the result is. */
-int khb_sort_keys(khb_ctx *ctx, void *d_keys, void *d_tmp, const uint64_t *h_seg_off, int n_segments, int k,
+KHB_API int khb_sort_keys(khb_ctx *ctx, void *d_keys, void *d_tmp, const uint64_t *h_seg_off, int n_segments, int k,
                   int *result_in_tmp);
 
 /* K4: distinct non-sentinel keys of a sorted array (`kmc -ci1` + `kmc_tools transform ... set_counts 1`,
  * exp_type_1.smk:163,173).  d_out may not alias d_sorted.  *h_count = number of keys written. */
-int khb_unique(khb_ctx *ctx, const void *d_sorted, size_t n, int k, void *d_out, uint64_t *h_count);
+KHB_API int khb_unique(khb_ctx *ctx, const void *d_sorted, size_t n, int k, void *d_out, uint64_t *h_count);
 
 /* K5/K6: run lengths of a sorted array = union with counter sum, saturated at `cs`
  * (`kmc_tools complex (set1 + ... + setN)` with -cs5000, exp_type_1.smk:52-61,182 and :75-84,250) and their
@@ -110,7 +111,7 @@ int khb_unique(khb_ctx *ctx, const void *d_sorted, size_t n, int k, void *d_out,
  * h_hist[nbins+1]: h_hist[c] = number of distinct keys whose counter is c (index 0 unused).
  * d_out_keys / d_out_counts (optional, may be NULL) receive the distinct keys / their counters.
  * *h_runs = number of distinct keys. */
-int khb_count_runs(khb_ctx *ctx, const void *d_sorted, size_t n, int k, uint32_t cs, uint32_t nbins,
+KHB_API int khb_count_runs(khb_ctx *ctx, const void *d_sorted, size_t n, int k, uint32_t cs, uint32_t nbins,
                    uint64_t *h_hist, void *d_out_keys, uint32_t *d_out_counts, uint64_t *h_runs);
 
 /* ---- fused stages (what the drop-in rules call) ------------------------------------------------- */
@@ -131,29 +132,29 @@ typedef struct khb_stats {
  * within_group_union_histogram (exp_type_1.smk:156-191) for one (k, group).  If keep_set != 0 the group's
  * distinct k-mer set (rule build_group_kmer_set, exp_type_1.smk:233-241) is retained on the device for
  * khb_across_groups().  h_hist has nbins+1 entries. */
-int khb_group_from_fasta(khb_ctx *ctx, int k, int n_genomes, const uint8_t *const *h_files,
+KHB_API int khb_group_from_fasta(khb_ctx *ctx, int k, int n_genomes, const uint8_t *const *h_files,
                          const size_t *h_sizes, uint32_t nbins, uint64_t *h_hist, int keep_set,
                          khb_stats *stats);
 
 /* Same stage with the text already staged in device memory by khb_stage_fasta (h_begin as returned by it). */
-int khb_group_from_staged(khb_ctx *ctx, int k, int n_genomes, const uint8_t *d_fasta, const uint64_t *h_begin,
+KHB_API int khb_group_from_staged(khb_ctx *ctx, int k, int n_genomes, const uint8_t *d_fasta, const uint64_t *h_begin,
                           uint32_t nbins, uint64_t *h_hist, int keep_set, khb_stats *stats);
 
 /* Across-group union-sum + histogram over the retained group sets: rules across_group_union and
  * across_group_union_histogram (exp_type_1.smk:243-259) for one k. */
-int khb_across_groups(khb_ctx *ctx, uint32_t nbins, uint64_t *h_hist, khb_stats *stats);
+KHB_API int khb_across_groups(khb_ctx *ctx, uint32_t nbins, uint64_t *h_hist, khb_stats *stats);
 
 /* Retained group sets: count / size, copy out (host), append (from host, e.g. received from a peer or
  * read back from a step_6 file), reset. */
-int khb_group_sets_info(khb_ctx *ctx, int *k, int *n_groups, uint64_t *n_keys);
-int khb_group_sets_device(khb_ctx *ctx, void **d_keys, uint64_t *n_keys); /* device view of the retained keys */
-int khb_group_sets_append_device(khb_ctx *ctx, int k, const void *d_keys, uint64_t n_keys, int n_groups);
-int khb_group_sets_append_host(khb_ctx *ctx, int k, const void *h_keys, uint64_t n_keys, int n_groups);
-int khb_group_sets_reset(khb_ctx *ctx);
+KHB_API int khb_group_sets_info(khb_ctx *ctx, int *k, int *n_groups, uint64_t *n_keys);
+KHB_API int khb_group_sets_device(khb_ctx *ctx, void **d_keys, uint64_t *n_keys); /* device view of the retained keys */
+KHB_API int khb_group_sets_append_device(khb_ctx *ctx, int k, const void *d_keys, uint64_t n_keys, int n_groups);
+KHB_API int khb_group_sets_append_host(khb_ctx *ctx, int k, const void *h_keys, uint64_t n_keys, int n_groups);
+KHB_API int khb_group_sets_reset(khb_ctx *ctx);
 
 /* K7: split n keys into n_parts buckets by splitmix64(key) % n_parts (multi-GPU hash-range partition of the
  * k-mer space).  d_out receives the keys grouped by bucket, h_part_off[n_parts+1] the bucket offsets. */
-int khb_partition_by_hash(khb_ctx *ctx, const void *d_keys, uint64_t n, int k, int n_parts, void *d_out,
+KHB_API int khb_partition_by_hash(khb_ctx *ctx, const void *d_keys, uint64_t n, int k, int n_parts, void *d_out,
                           uint64_t *h_part_off);
 
 #ifdef __cplusplus

@@ -1,0 +1,245 @@
+"""Command-line shims for the rule-compatible mode: drop-in stand-ins for the two KMC binaries as the
+reference's rules invoke them (/root/reference/workflow/rules/exp_type_1.smk):
+
+    kmc -fm -m64 -k{k} -ci1 {in.fna.gz} {out_prefix} tmp/                    (:163)
+    kmc_tools transform {in_prefix} set_counts 1 {out_prefix}                (:173, :241)
+    kmc_tools complex {ops.txt}                                              (:182, :250)
+    kmc_tools transform {in_prefix} histogram {out.txt}                      (:191, :259)
+
+``khoice_b200/bin/kmc`` and ``khoice_b200/bin/kmc_tools`` exec this module, so putting that directory
+first on PATH makes the UNMODIFIED reference rules run on the B200 engine.  Databases use this package's
+own layout (khoice_b200/kmcdb.py).  Exit status: 0 ok, 1 on any error with partial outputs removed
+(Snakemake deletes the outputs of a failed job; the shims never leave a half-written file either).
+
+Only what the reference's exp-1 call sites use is implemented; anything else is rejected loudly.
+Every arithmetic step runs on the GPU (no CPU fallback); a process pays one CUDA context start, which is
+why the fused mode (khoice_b200/pipeline.py) is the fast path.
+"""
+from __future__ import annotations
+
+import gzip
+import os
+import re
+import sys
+from typing import List, Optional
+
+import numpy as np
+
+from . import kmcdb
+from .engine import COUNTER_MAX, Engine
+from .tables import HIST_ROWS, write_histogram_file
+
+KMC_DEFAULT_CS = 255  # KMC's default counter saturation for `kmc` (no -cs on the reference's command line)
+
+_engine: Optional[Engine] = None
+
+
+def get_engine() -> Engine:
+    global _engine
+    if _engine is None:
+        _engine = Engine(int(os.environ.get("KHB_DEVICE", "0")))
+    return _engine
+
+
+def set_engine(eng: Optional[Engine]) -> None:
+    """Let an in-process caller (the mini rule runner, tests) share one context."""
+    global _engine
+    _engine = eng
+
+
+def read_fasta(path: str) -> bytes:
+    """FASTA text of a .fna.gz (multi-member gzip handled, rule R9) or plain file."""
+    if path.endswith(".gz"):
+        with gzip.open(path, "rb") as fd:
+            return fd.read()
+    with open(path, "rb") as fd:
+        return fd.read()
+
+
+class UsageError(Exception):
+    pass
+
+
+# ---- kmc -------------------------------------------------------------------------------------------
+def kmc_count(fasta_path: str, out_prefix: str, k: int, ci: int = 1, cs: int = KMC_DEFAULT_CS) -> None:
+    """Per-genome canonical k-mer database with occurrence counters (saturating at cs, keeping >= ci)."""
+    eng = get_engine()
+    text = read_fasta(fasta_path)
+    staged = eng.stage_fasta([text])
+    packed = eng.pack_fasta(staged)
+    n = packed["n_symbols"]
+    keys = eng.extract_kmers(packed, k)
+    srt = eng.sort_keys(keys, n, k)
+    hist, runs, ok, oc = eng.count_runs(srt, n, k, nbins=HIST_ROWS, cs=cs, want_keys=True, want_counts=True)
+    w = 1 if k <= 32 else 2
+    hk = ok.download(np.uint64, runs * w).reshape((runs,) if w == 1 else (runs, 2))
+    hc = oc.download(np.uint32, runs)
+    if ci > 1:
+        keep = hc >= ci
+        hk, hc = hk[keep], hc[keep]
+        hist[:ci] = 0
+    kmcdb.write_db(out_prefix, k, hk, hc, hist, cs)
+
+
+def kmc_main(argv: List[str]) -> int:
+    k, ci, cs, fm, pos = 25, 2, KMC_DEFAULT_CS, False, []
+    for a in argv:
+        if a == "-fm":
+            fm = True
+        elif re.fullmatch(r"-k\d+", a):
+            k = int(a[2:])
+        elif re.fullmatch(r"-ci\d+", a):
+            ci = int(a[3:])
+        elif re.fullmatch(r"-cs\d+", a):
+            cs = int(a[3:])
+        elif re.fullmatch(r"-m\d+", a) or re.fullmatch(r"-t\d+", a) or a in ("-v", "-hp"):
+            pass  # memory / thread hints of the CPU tool: irrelevant here
+        elif a.startswith("-"):
+            raise UsageError(f"kmc: option {a} is not supported by the khoice-b200 shim")
+        else:
+            pos.append(a)
+    if len(pos) != 3:
+        raise UsageError("usage: kmc [options] <input.fna[.gz]> <output_prefix> <tmp_dir>")
+    if not fm:
+        raise UsageError("kmc: only multi-line FASTA input (-fm) is supported (the reference passes -fm)")
+    if not 1 <= k <= 64:
+        raise UsageError(f"kmc: -k{k} outside 1..64")
+    kmc_count(pos[0], pos[1], k, ci, cs)
+    return 0
+
+
+# ---- kmc_tools ---------------------------------------------------------------------------------------
+def transform_set_counts(in_prefix: str, value: int, out_prefix: str) -> None:
+    db = kmcdb.read_db(in_prefix)
+    hist = np.zeros(HIST_ROWS + 1, dtype=np.uint64)
+    if value <= HIST_ROWS:
+        hist[value] = db.keys.shape[0]
+    kmcdb.write_db(out_prefix, db.k, db.keys, np.full(db.keys.shape[0], value, np.uint32), hist, max(db.counter_max, value))
+
+
+def transform_histogram(in_prefix: str, out_txt: str) -> None:
+    db = kmcdb.read_db(in_prefix, header_only=True)
+    write_histogram_file(out_txt, db.hist, HIST_ROWS)
+
+
+def parse_complex(path: str):
+    """The operation file the reference generates (exp_type_1.smk:52-61, 75-84):
+    INPUT:/setN = prefix ... OUTPUT:/prefix = (set1 + set2 + ...) OUTPUT_PARAMS:/-cs5000."""
+    section, inputs, output, expr, cs = None, {}, None, None, KMC_DEFAULT_CS
+    with open(path) as fd:
+        for raw in fd:
+            line = raw.strip()
+            if not line:
+                continue
+            if line in ("INPUT:", "OUTPUT:", "OUTPUT_PARAMS:"):
+                section = line[:-1]
+                continue
+            if section == "INPUT":
+                name, _, val = line.partition("=")
+                inputs[name.strip()] = val.strip()
+            elif section == "OUTPUT":
+                out, _, e = line.partition("=")
+                output, expr = out.strip(), e.strip()
+            elif section == "OUTPUT_PARAMS":
+                for tok in line.split():
+                    if re.fullmatch(r"-cs\d+", tok):
+                        cs = int(tok[3:])
+                    elif re.fullmatch(r"-ci\d+", tok) and int(tok[3:]) <= 1:
+                        pass
+                    else:
+                        raise UsageError(f"kmc_tools complex: output parameter {tok} is not supported")
+            else:
+                raise UsageError(f"kmc_tools complex: line outside a section: {line}")
+    if output is None or expr is None:
+        raise UsageError("kmc_tools complex: no OUTPUT section")
+    body = expr.strip()
+    while body.startswith("(") and body.endswith(")"):
+        body = body[1:-1].strip()
+    names = [t.strip() for t in body.split("+")]
+    if not names or any(not re.fullmatch(r"\w+", t) for t in names):
+        raise UsageError(f"kmc_tools complex: only unions `(a + b + ...)` are supported, got: {expr}")
+    missing = [t for t in names if t not in inputs]
+    if missing:
+        raise UsageError(f"kmc_tools complex: undefined input(s) {missing}")
+    return [inputs[t] for t in names], output, cs
+
+
+def complex_union(ops_path: str) -> None:
+    """Union with counter sum, saturating at -cs (the `+` of kmc_tools complex)."""
+    in_prefixes, out_prefix, cs = parse_complex(ops_path)
+    eng = get_engine()
+    dbs = [kmcdb.read_db(p) for p in in_prefixes]
+    k = dbs[0].k
+    if any(d.k != k for d in dbs):
+        raise UsageError("kmc_tools complex: inputs were built with different k")
+    if any(d.counts.size and (d.counts != 1).any() for d in dbs):
+        raise UsageError("kmc_tools complex: the khoice-b200 shim sums SET inputs only (all counters 1, i.e. after "
+                         "`transform ... set_counts 1`, as every reference call site does)")
+    keys = np.concatenate([d.keys for d in dbs], axis=0)
+    n = keys.shape[0]
+    w = 1 if k <= 32 else 2
+    buf = eng.alloc((n + 4) * 8 * w)
+    buf.upload(keys)
+    srt = eng.sort_keys(buf, n, k)
+    hist, runs, ok, oc = eng.count_runs(srt, n, k, nbins=HIST_ROWS, cs=cs, want_keys=True, want_counts=True)
+    hk = ok.download(np.uint64, runs * w).reshape((runs,) if w == 1 else (runs, 2))
+    hc = oc.download(np.uint32, runs)
+    kmcdb.write_db(out_prefix, k, hk, hc, hist, cs)
+
+
+def kmc_tools_main(argv: List[str]) -> int:
+    args = [a for a in argv if not re.fullmatch(r"-t\d+", a) and a not in ("-v", "-hp")]
+    if not args:
+        raise UsageError("usage: kmc_tools <transform|complex> ...")
+    if args[0] == "complex":
+        if len(args) != 2:
+            raise UsageError("usage: kmc_tools complex <operations_file>")
+        complex_union(args[1])
+        return 0
+    if args[0] == "transform":
+        if len(args) == 5 and args[2] == "set_counts":
+            transform_set_counts(args[1], int(args[3]), args[4])
+            return 0
+        if len(args) == 4 and args[2] == "histogram":
+            transform_histogram(args[1], args[3])
+            return 0
+        raise UsageError("kmc_tools transform: only `set_counts <v> <out>` and `histogram <out.txt>` are supported")
+    raise UsageError(f"kmc_tools {args[0]}: not supported by the khoice-b200 shim (exp type 1 uses transform and complex)")
+
+
+def _outputs_of(tool: str, argv: List[str]) -> List[str]:
+    """Best-effort list of files a failed invocation may have started (for cleanup)."""
+    outs = []
+    try:
+        if tool == "kmc":
+            pos = [a for a in argv if not a.startswith("-")]
+            outs = [pos[1] + ".kmc_pre", pos[1] + ".kmc_suf"]
+        elif argv and argv[0] == "transform":
+            outs = [argv[-1]] if argv[2] == "histogram" else [argv[-1] + ".kmc_pre", argv[-1] + ".kmc_suf"]
+        elif argv and argv[0] == "complex":
+            _, out, _ = parse_complex(argv[1])
+            outs = [out + ".kmc_pre", out + ".kmc_suf"]
+    except Exception:
+        pass
+    return outs
+
+
+def main(argv: Optional[List[str]] = None) -> int:
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if not argv or argv[0] not in ("kmc", "kmc_tools"):
+        print("usage: python -m khoice_b200.cli <kmc|kmc_tools> ...", file=sys.stderr)
+        return 1
+    tool, rest = argv[0], argv[1:]
+    try:
+        return kmc_main(rest) if tool == "kmc" else kmc_tools_main(rest)
+    except Exception as e:  # exit-code discipline at the process boundary
+        print(f"{tool} (khoice-b200): {e}", file=sys.stderr)
+        for f in _outputs_of(tool, rest):
+            for cand in (f, f"{f}.tmp.{os.getpid()}"):
+                if os.path.exists(cand):
+                    os.remove(cand)
+        return 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -371,20 +371,20 @@ static int gs_reserve(khb_ctx *ctx, int k, u64 extra)
 {
     const size_t W = (size_t)khb_key_bytes(k);
     if (ctx->gs_k && ctx->gs_k != k) return khb_fail(ctx, KHB_ERR_STATE, "retained group sets were built with k=%d, not k=%d; call khb_group_sets_reset", ctx->gs_k, k);
-    const u64 need = ctx->gs_len + extra + 2;
+    const u64 need = (ctx->gs_len + extra + 2) * W;  // gs_cap is in BYTES (W changes with k)
     if (need > ctx->gs_cap) {
-        u64 cap = ctx->gs_cap ? ctx->gs_cap : (1u << 20);
-        while (cap < need) cap += cap / 2 + 1;
+        u64 cap = ctx->gs_cap ? ctx->gs_cap : (8u << 20);
+        while (cap < need) cap += cap / 2 + 16;
         void *nb = nullptr;
-        cudaError_t e = cudaMalloc(&nb, cap * W);
+        cudaError_t e = cudaMalloc(&nb, cap);
         if (e != cudaSuccess) {
             cudaGetLastError();
             cap = need;
-            e = cudaMalloc(&nb, cap * W);
+            e = cudaMalloc(&nb, cap);
         }
         if (e != cudaSuccess) {
             cudaGetLastError();
-            return khb_fail(ctx, KHB_ERR_NOMEM, "group set store: device allocation of %llu bytes failed", (u64)(cap * W));
+            return khb_fail(ctx, KHB_ERR_NOMEM, "group set store: device allocation of %llu bytes failed", cap);
         }
         if (ctx->gs_len) KHB_CUDA(ctx, cudaMemcpyAsync(nb, ctx->gs_buf, ctx->gs_len * W, cudaMemcpyDeviceToDevice, ctx->stream));
         KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -50,7 +50,7 @@ struct khb_ctx {
     u64 launches;
     // accumulated group sets for the across-group stage (fused mode)
     void *gs_buf;       // device buffer holding the concatenation of kept group sets
-    size_t gs_cap;      // capacity in keys
+    size_t gs_cap;      // capacity in BYTES
     size_t gs_len;      // keys stored
     int gs_k;           // k the stored sets were built with (0 = none)
     int gs_groups;      // number of groups stored

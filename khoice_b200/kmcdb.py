@@ -1,0 +1,93 @@
+"""On-disk k-mer databases for the rule-compatible mode.
+
+The reference's rules exchange KMC databases, pairs ``X.kmc_pre`` + ``X.kmc_suf``
+(/root/reference/workflow/rules/exp_type_1.smk:160-161,170-171,179-180,238-239,247-248).  BASELINE.json's
+north_star pins the rule names, their inputs and the CSV outputs, not the byte format of these
+intermediates (KMC's prefix-LUT format is not documented in the reference tree), so this package keeps
+the two file names but stores its own simple layout:
+
+``X.kmc_pre``  64-byte header  + uint64[hist_rows+1] occurrence histogram of the counters
+``X.kmc_suf``  n_keys k-mer words (8 or 16 bytes each, ascending) + n_keys uint32 counters
+
+In fused mode the intermediates are never read back, so only the header (``stub`` flag set) is written --
+enough for Snakemake's file DAG / resume semantics.
+"""
+from __future__ import annotations
+
+import os
+import struct
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+MAGIC = b"KHB200DB"
+VERSION = 1
+_HDR = struct.Struct("<8sIIQIIII24x")  # magic, version, k, n_keys, key_bytes, counter_max, hist_rows, stub
+assert _HDR.size == 64
+
+
+@dataclass
+class KmerDB:
+    k: int
+    keys: np.ndarray               # uint64 [n] or [n, 2] (lo, hi), ascending
+    counts: np.ndarray             # uint32 [n]
+    hist: np.ndarray               # uint64 [hist_rows+1]; hist[c] = #keys with counter c
+    counter_max: int = 255
+    stub: bool = False
+
+    @property
+    def n_keys(self) -> int:
+        return int(self.counts.shape[0]) if not self.stub else int(self._n)
+
+    _n: int = 0
+
+
+def _atomic_write(path: str, chunks) -> None:
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    tmp = f"{path}.tmp.{os.getpid()}"
+    with open(tmp, "wb") as fd:
+        for c in chunks:
+            fd.write(c)
+    os.replace(tmp, path)
+
+
+def write_db(prefix: str, k: int, keys: Optional[np.ndarray], counts: Optional[np.ndarray], hist: np.ndarray,
+             counter_max: int, n_keys: Optional[int] = None) -> None:
+    """Write ``prefix.kmc_pre`` / ``prefix.kmc_suf``.  ``keys is None`` writes a fused-mode stub."""
+    stub = keys is None
+    n = int(n_keys if n_keys is not None else (0 if stub else keys.shape[0]))
+    key_bytes = 8 if k <= 32 else 16
+    hist = np.ascontiguousarray(hist, dtype=np.uint64)
+    hdr = _HDR.pack(MAGIC, VERSION, k, n, key_bytes, counter_max, hist.size - 1, 1 if stub else 0)
+    if stub:
+        _atomic_write(prefix + ".kmc_suf", [b""])
+    else:
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        counts = np.ascontiguousarray(counts, dtype=np.uint32)
+        assert counts.shape[0] == keys.shape[0] == n
+        _atomic_write(prefix + ".kmc_suf", [keys.tobytes(), counts.tobytes()])
+    _atomic_write(prefix + ".kmc_pre", [hdr, hist.tobytes()])
+
+
+def read_db(prefix: str, header_only: bool = False) -> KmerDB:
+    with open(prefix + ".kmc_pre", "rb") as fd:
+        raw = fd.read()
+    if len(raw) < 64 or raw[:8] != MAGIC:
+        raise ValueError(f"{prefix}.kmc_pre is not a khoice-b200 database (a real KMC database? see INTEGRATION.md)")
+    _, version, k, n, key_bytes, cmax, rows, stub = _HDR.unpack(raw[:64])
+    if version != VERSION:
+        raise ValueError(f"{prefix}.kmc_pre: unsupported version {version}")
+    hist = np.frombuffer(raw, dtype=np.uint64, count=rows + 1, offset=64).copy()
+    shape = (n,) if key_bytes == 8 else (n, 2)
+    if stub or header_only:
+        db = KmerDB(k, np.empty((0,) + shape[1:], np.uint64), np.empty(0, np.uint32), hist, cmax, True)
+        db._n = n
+        return db
+    with open(prefix + ".kmc_suf", "rb") as fd:
+        body = fd.read()
+    if len(body) != n * key_bytes + n * 4:
+        raise ValueError(f"{prefix}.kmc_suf: size {len(body)} does not match header (n={n})")
+    keys = np.frombuffer(body, dtype=np.uint64, count=n * (key_bytes // 8)).reshape(shape).copy()
+    counts = np.frombuffer(body, dtype=np.uint32, count=n, offset=n * key_bytes).copy()
+    return KmerDB(k, keys, counts, hist, cmax, False)

@@ -1,0 +1,230 @@
+"""Host driver of experiment type 1 on the B200 engine: the rule chain of
+/root/reference/workflow/rules/exp_type_1.smk with the same rule names, inputs and outputs.
+
+Two execution modes over the same work-root layout (``data/dataset_{n}/{genome}.fna.gz`` in,
+``step_4`` / ``step_8`` histograms, ``step_5`` / ``step_9`` CSVs and ``final_results_type1/`` out):
+
+* ``fused``  -- one pass per (k, group): the four per-genome / per-group rules collapse into
+  ``Engine.group_from_fasta`` and the two across-group rules into ``Engine.across_groups``; the
+  intermediate databases of steps 1,2,3,6,7 are written as header-only stubs so the file DAG and
+  Snakemake's resume semantics still hold.  This is the fast path.
+* ``rules``  -- every rule instance runs separately through the kmc / kmc_tools shims
+  (khoice_b200/cli.py), exchanging real intermediate databases, exactly like the reference does with
+  KMC.  Either in-process (one CUDA context) or as sub-processes with khoice_b200/bin first on PATH
+  (the literal drop-in: the shell strings are the reference's own).
+
+Snakemake is not installed in this image, so ``run_rules`` is a minimal stand-in for its scheduler for
+these ten rules: it walks the same DAG, skips rule instances whose outputs exist (resume), and removes
+the outputs of a failed job.
+"""
+from __future__ import annotations
+
+import json
+import os
+import shlex
+import shutil
+import subprocess
+import time
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import cli, kmcdb, tables
+from .engine import COUNTER_MAX, Engine
+
+# /root/reference/workflow/Snakefile:36 -- a Python literal there; a config key (K_VALUES) here.
+DEFAULT_K_VALUES = [str(x) for x in range(7, 31, 1)] + [str(x) for x in range(34, 50, 3)]
+BIN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bin")
+
+
+# ---- layout helpers (paths exactly as in the rules) ---------------------------------------------------
+def genomes_of(work_root: str, num: int) -> List[str]:
+    """Genome names of data/dataset_{num}: text before ``.fna.gz`` (exp_type_1.smk:44-47), sorted."""
+    d = os.path.join(work_root, "data", f"dataset_{num}")
+    return sorted(f.split(".fna.gz")[0] for f in os.listdir(d) if f.endswith(".fna.gz"))
+
+
+def p_genome(num, g): return f"data/dataset_{num}/{g}.fna.gz"
+def p_step1(k, num, g): return f"step_1/k_{k}/dataset_{num}/{g}"
+def p_step2(k, num, g): return f"step_2/k_{k}/dataset_{num}/{g}.transformed"
+def p_step3(k, num): return f"step_3/k_{k}/dataset_{num}/dataset_{num}.transformed.combined"
+def p_step4(k, num): return f"step_4/k_{k}/dataset_{num}/dataset_{num}_k{k}_hist.txt"
+def p_step6(k, num): return f"step_6/k_{k}/dataset_{num}/dataset_{num}.transformed.combined.transformed"
+def p_step7(k): return f"step_7/k_{k}/all_datasets.transformed.combined.transformed.combined"
+def p_step8(k): return f"step_8/k_{k}/all_datasets_k{k}_hist.txt"
+P_STEP5 = "step_5/within_datasets_analysis.csv"
+P_STEP9 = "step_9/across_datasets_analysis.csv"
+P_FINAL = ("final_results_type1/within_datasets_analysis.csv", "final_results_type1/across_datasets_analysis.csv")
+def p_ops_within(k, num): return f"complex_ops/within_groups/k_{k}/dataset_{num}/within_dataset_{num}.txt"
+def p_ops_across(k): return f"complex_ops/across_groups/k_{k}/across_all_datasets.txt"
+
+
+def write_complex_ops(work_root: str, k_values: Sequence[str], num_datasets: int) -> None:
+    """The parse-time block of exp_type_1.smk:26-84: tmp/, and one `kmc_tools complex` operation file
+    per (k, group) and per k."""
+    os.makedirs(os.path.join(work_root, "tmp"), exist_ok=True)
+
+    def emit(path, inputs, output):
+        full = os.path.join(work_root, path)
+        os.makedirs(os.path.dirname(full), exist_ok=True)
+        lines = ["INPUT:"] + [f"set{i + 1} = {p}" for i, p in enumerate(inputs)]
+        expr = "(" + " + ".join(f"set{i + 1}" for i in range(len(inputs))) + ")"
+        lines += ["OUTPUT:", f"{output} = {expr}", "OUTPUT_PARAMS:", "-cs5000"]
+        with open(full, "w") as fd:
+            fd.write("\n".join(lines) + "\n")
+
+    for k in k_values:
+        for num in range(1, num_datasets + 1):
+            emit(p_ops_within(k, num), [p_step2(k, num, g) for g in genomes_of(work_root, num)], p_step3(k, num))
+        emit(p_ops_across(k), [p_step6(k, num) for num in range(1, num_datasets + 1)], p_step7(k))
+
+
+def _members_of(work_root: str):
+    return lambda num: tables.get_num_of_dataset_members(num, os.path.join(work_root, "data"))
+
+
+def build_tables(work_root: str, k_values: Sequence[str], num_datasets: int) -> None:
+    """Rules within_group_union_analysis, across_group_union_analysis, copy_final_results_type1."""
+    nums = range(1, num_datasets + 1)
+    tables.within_group_union_analysis([os.path.join(work_root, p_step4(k, n)) for k in k_values for n in nums],
+                                       os.path.join(work_root, P_STEP5), num_datasets, _members_of(work_root))
+    tables.across_group_union_analysis([os.path.join(work_root, p_step8(k)) for k in k_values],
+                                       os.path.join(work_root, P_STEP9), num_datasets)
+    for src, dst in zip((P_STEP5, P_STEP9), P_FINAL):
+        os.makedirs(os.path.dirname(os.path.join(work_root, dst)), exist_ok=True)
+        shutil.copyfile(os.path.join(work_root, src), os.path.join(work_root, dst))
+
+
+# ---- fused mode ----------------------------------------------------------------------------------------
+def run_fused(work_root: str, num_datasets: int, k_values: Optional[Sequence] = None, engine: Optional[Engine] = None,
+              stubs: bool = True, report_path: Optional[str] = None) -> Dict:
+    """All of exp type 1 for ``work_root``; returns (and optionally writes) a JSON-able run report."""
+    k_values = [str(k) for k in (k_values or DEFAULT_K_VALUES)]
+    own = engine is None
+    eng = engine or Engine(int(os.environ.get("KHB_DEVICE", "0")))
+    report = {"mode": "fused", "work_root": work_root, "num_datasets": num_datasets, "k_values": k_values, "stages": []}
+    t_start = time.time()
+    try:
+        write_complex_ops(work_root, k_values, num_datasets)
+        names = {n: genomes_of(work_root, n) for n in range(1, num_datasets + 1)}
+        texts: Dict[int, List[bytes]] = {}
+        zero = np.zeros(tables.HIST_ROWS + 1, dtype=np.uint64)
+        for k in k_values:
+            ki = int(k)
+            eng.group_sets_reset()
+            for num in range(1, num_datasets + 1):
+                if num not in texts:  # inflate once, reuse across the k sweep while host memory allows
+                    texts[num] = [cli.read_fasta(os.path.join(work_root, p_genome(num, g))) for g in names[num]]
+                hist, st = eng.group_from_fasta(texts[num], ki, nbins=tables.HIST_ROWS, keep_set=True)
+                tables.write_histogram_file(os.path.join(work_root, p_step4(k, num)), hist)
+                if stubs:
+                    one = zero.copy()
+                    for g in names[num]:
+                        kmcdb.write_db(os.path.join(work_root, p_step1(k, num, g)), ki, None, None, zero, cli.KMC_DEFAULT_CS)
+                        kmcdb.write_db(os.path.join(work_root, p_step2(k, num, g)), ki, None, None, zero, cli.KMC_DEFAULT_CS)
+                    kmcdb.write_db(os.path.join(work_root, p_step3(k, num)), ki, None, None, hist, COUNTER_MAX, st["distinct"])
+                    one[1] = st["distinct"]
+                    kmcdb.write_db(os.path.join(work_root, p_step6(k, num)), ki, None, None, one, COUNTER_MAX, st["distinct"])
+                report["stages"].append({"k": ki, "group": num, **st})
+            hist, st = eng.across_groups(nbins=tables.HIST_ROWS)
+            tables.write_histogram_file(os.path.join(work_root, p_step8(k)), hist)
+            if stubs:
+                kmcdb.write_db(os.path.join(work_root, p_step7(k)), ki, None, None, hist, COUNTER_MAX, st["distinct"])
+            report["stages"].append({"k": ki, "group": "across", **st})
+        build_tables(work_root, k_values, num_datasets)
+    finally:
+        if own:
+            eng.close()
+    report["seconds"] = time.time() - t_start
+    if report_path:
+        with open(report_path, "w") as fd:
+            json.dump(report, fd, indent=1)
+    return report
+
+
+# ---- rule-by-rule mode (mini scheduler) --------------------------------------------------------------
+def _rule_jobs(work_root: str, k_values: Sequence[str], num_datasets: int):
+    """(rule name, outputs, shell string) for every rule instance, in a valid topological order.  The
+    shell strings are the reference's own (exp_type_1.smk:163,173,182,191,241,250,259)."""
+    jobs = []
+    for k in k_values:
+        for num in range(1, num_datasets + 1):
+            for g in genomes_of(work_root, num):
+                jobs.append(("build_kmc_database_on_genome", [p_step1(k, num, g) + e for e in (".kmc_pre", ".kmc_suf")],
+                             f"kmc -fm -m64 -k{k} -ci1 {p_genome(num, g)} {p_step1(k, num, g)} tmp/"))
+                jobs.append(("transform_genome_to_set", [p_step2(k, num, g) + e for e in (".kmc_pre", ".kmc_suf")],
+                             f"kmc_tools transform {p_step1(k, num, g)} set_counts 1 {p_step2(k, num, g)}"))
+            jobs.append(("within_group_union", [p_step3(k, num) + e for e in (".kmc_pre", ".kmc_suf")],
+                         f"kmc_tools complex {p_ops_within(k, num)}"))
+            jobs.append(("within_group_union_histogram", [p_step4(k, num)],
+                         f"kmc_tools transform {p_step3(k, num)} histogram {p_step4(k, num)}"))
+            jobs.append(("build_group_kmer_set", [p_step6(k, num) + e for e in (".kmc_pre", ".kmc_suf")],
+                         f"kmc_tools transform {p_step3(k, num)} set_counts 1 {p_step6(k, num)}"))
+        jobs.append(("across_group_union", [p_step7(k) + e for e in (".kmc_pre", ".kmc_suf")],
+                     f"kmc_tools complex {p_ops_across(k)}"))
+        jobs.append(("across_group_union_histogram", [p_step8(k)],
+                     f"kmc_tools transform {p_step7(k)} histogram {p_step8(k)}"))
+    return jobs
+
+
+def run_rules(work_root: str, num_datasets: int, k_values: Optional[Sequence] = None, subprocess_mode: bool = False,
+              engine: Optional[Engine] = None) -> Dict:
+    """Run every exp-1 rule instance separately through the kmc / kmc_tools shims."""
+    k_values = [str(k) for k in (k_values or DEFAULT_K_VALUES)]
+    write_complex_ops(work_root, k_values, num_datasets)
+    cwd = os.getcwd()
+    ran, skipped = 0, 0
+    env = dict(os.environ, PATH=BIN_DIR + os.pathsep + os.environ.get("PATH", ""))
+    own = None
+    if not subprocess_mode:
+        own = engine or Engine(int(os.environ.get("KHB_DEVICE", "0")))
+        cli.set_engine(own)
+    try:
+        os.chdir(work_root)  # `workdir:` of the Snakefile (Snakefile:45)
+        for rule, outputs, shell in _rule_jobs(".", k_values, num_datasets):
+            if all(os.path.exists(o) for o in outputs):
+                skipped += 1
+                continue
+            for o in outputs:
+                os.makedirs(os.path.dirname(o) or ".", exist_ok=True)
+            if subprocess_mode:
+                rc = subprocess.run(["/bin/sh", "-c", shell], env=env).returncode
+            else:
+                argv = shlex.split(shell)
+                rc = cli.main(argv)
+            if rc != 0:
+                for o in outputs:
+                    if os.path.exists(o):
+                        os.remove(o)
+                raise RuntimeError(f"rule {rule} failed (exit {rc}): {shell}")
+            ran += 1
+    finally:
+        os.chdir(cwd)
+        if not subprocess_mode:
+            cli.set_engine(None)
+            if engine is None and own is not None:
+                own.close()
+    build_tables(work_root, k_values, num_datasets)
+    return {"mode": "rules-subprocess" if subprocess_mode else "rules", "jobs_run": ran, "jobs_skipped": skipped}
+
+
+def main(argv: Optional[List[str]] = None) -> int:
+    import argparse
+    ap = argparse.ArgumentParser(description="khoice experiment type 1 on the B200 engine")
+    ap.add_argument("--work-root", required=True, help="WORK_ROOT of the reference config (config/config.yaml)")
+    ap.add_argument("--num-datasets", type=int, required=True, help="NUM_DATASETS")
+    ap.add_argument("--k-values", default=None, help="comma separated K_VALUES (default: the reference list, Snakefile:36)")
+    ap.add_argument("--mode", choices=["fused", "rules", "rules-subprocess"], default="fused")
+    ap.add_argument("--report", default=None)
+    a = ap.parse_args(argv)
+    ks = a.k_values.split(",") if a.k_values else None
+    if a.mode == "fused":
+        rep = run_fused(a.work_root, a.num_datasets, ks, report_path=a.report)
+    else:
+        rep = run_rules(a.work_root, a.num_datasets, ks, subprocess_mode=a.mode == "rules-subprocess")
+    print(json.dumps({k: v for k, v in rep.items() if k != "stages"}))
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -1,0 +1,95 @@
+"""End-to-end drop-in check on a GPU: the exp-1 rule chain over a work root, in all three modes, against
+the oracle's histograms and byte-identical CSVs."""
+import filecmp
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+K_VALUES = ["7", "12", "21", "31", "34"]
+
+
+@pytest.fixture(scope="module")
+def work_roots(tmp_path_factory):
+    from khoice_b200 import synth
+    cfg = synth.SynthConfig(n_groups=2, genomes_per_group=3, genome_len=40_000, seed=5)
+    roots = {}
+    for mode in ("fused", "rules", "rules-subprocess"):
+        root = str(tmp_path_factory.mktemp(mode.replace("-", "_")))
+        synth.write_dataset(cfg, root)
+        roots[mode] = root
+    return cfg, roots
+
+
+def _oracle_hists(oracle, cfg, k):
+    from khoice_b200 import synth
+    flat, gid = [], []
+    for g in range(1, cfg.n_groups + 1):
+        for i in range(1, cfg.genomes_per_group + 1):
+            flat.append(synth.make_genome(cfg, g, i))
+            gid.append(g - 1)
+    return oracle.exp1(flat, gid, cfg.n_groups, k)
+
+
+def test_three_modes_agree_with_oracle(engine, oracle, work_roots):
+    from khoice_b200 import pipeline, tables
+    cfg, roots = work_roots
+    pipeline.run_fused(roots["fused"], cfg.n_groups, K_VALUES, engine=engine)
+    pipeline.run_rules(roots["rules"], cfg.n_groups, K_VALUES, engine=engine)
+    pipeline.run_rules(roots["rules-subprocess"], cfg.n_groups, K_VALUES[:2] , subprocess_mode=True)
+    for k in K_VALUES:
+        w_ref, a_ref, _ = _oracle_hists(oracle, cfg, int(k))
+        for mode in ("fused", "rules") + (("rules-subprocess",) if k in K_VALUES[:2] else ()):
+            root = roots[mode]
+            for num in range(1, cfg.n_groups + 1):
+                got = tables.read_histogram_file(os.path.join(root, pipeline.p_step4(k, num)))
+                assert len(got) == 5000
+                assert got == [int(x) for x in w_ref[num - 1][1:]], (mode, k, num)
+            got = tables.read_histogram_file(os.path.join(root, pipeline.p_step8(k)))
+            assert got == [int(x) for x in a_ref[1:]], (mode, k)
+    for f in (pipeline.P_STEP5, pipeline.P_STEP9) + pipeline.P_FINAL:
+        assert filecmp.cmp(os.path.join(roots["fused"], f), os.path.join(roots["rules"], f), shallow=False), f
+    # every declared rule output exists in both modes (file DAG / resume semantics)
+    for mode in ("fused", "rules"):
+        root = roots[mode]
+        for k in K_VALUES:
+            for num in range(1, cfg.n_groups + 1):
+                for g in pipeline.genomes_of(root, num):
+                    for p in (pipeline.p_step1(k, num, g), pipeline.p_step2(k, num, g)):
+                        assert os.path.exists(os.path.join(root, p + ".kmc_pre")) and os.path.exists(os.path.join(root, p + ".kmc_suf"))
+                for p in (pipeline.p_step3(k, num), pipeline.p_step6(k, num)):
+                    assert os.path.exists(os.path.join(root, p + ".kmc_pre"))
+            assert os.path.exists(os.path.join(root, pipeline.p_step7(k) + ".kmc_pre"))
+    # resume: a second run does nothing
+    rep = pipeline.run_rules(roots["rules"], cfg.n_groups, K_VALUES, engine=engine)
+    assert rep["jobs_run"] == 0
+
+
+def test_rule_databases_hold_the_oracle_sets(engine, oracle, work_roots):
+    from khoice_b200 import kmcdb, pipeline, synth
+    cfg, roots = work_roots
+    root = roots["rules"]
+    if not os.path.exists(os.path.join(root, pipeline.P_STEP5)):
+        pipeline.run_rules(root, cfg.n_groups, K_VALUES, engine=engine)
+    for k in ("21", "34"):
+        for num in (1, 2):
+            genomes = [synth.make_genome(cfg, num, i) for i in range(1, cfg.genomes_per_group + 1)]
+            sets = [oracle.genome_set(g, int(k)) for g in genomes]
+            for name, ref in zip(pipeline.genomes_of(root, num), sets):
+                db1 = kmcdb.read_db(os.path.join(root, pipeline.p_step1(k, num, name)))
+                db2 = kmcdb.read_db(os.path.join(root, pipeline.p_step2(k, num, name)))
+                assert np.array_equal(db1.keys, ref) and np.array_equal(db2.keys, ref)
+                assert (db2.counts == 1).all() and db1.counts.min() >= 1
+            keys, counts = oracle.union_sum(sets, int(k))
+            db3 = kmcdb.read_db(os.path.join(root, pipeline.p_step3(k, num)))
+            assert np.array_equal(db3.keys, keys) and np.array_equal(db3.counts, counts)
+
+
+def test_cli_error_behaviour(tmp_path):
+    from khoice_b200 import cli
+    assert cli.main(["kmc", "-k31", "-ci1", "x.fna", "out", "tmp"]) == 1          # no -fm
+    assert cli.main(["kmc_tools", "simple", "a", "b", "intersect", "c"]) == 1     # not an exp-1 operation
+    assert cli.main(["kmc_tools", "transform", str(tmp_path / "missing"), "histogram", str(tmp_path / "h.txt")]) == 1
+    assert not (tmp_path / "h.txt").exists()
