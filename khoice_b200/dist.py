@@ -1,0 +1,135 @@
+"""Multi-GPU execution of experiment type 1: one process per GPU, `torch.distributed` for the plumbing.
+
+How the path shards:
+
+* steps 1-6 (per genome / per group; /root/reference/workflow/rules/exp_type_1.smk:156-241) are independent per
+  group -> whole groups are dealt to ranks round-robin, NO data-path collective;
+* steps 7-8 (across groups; exp_type_1.smk:243-259) need every copy of a k-mer on one GPU -> the k-mer space is
+  hash-range partitioned (K7, ``khb_partition_by_hash``): ONE variable-size all-to-all of the retained group
+  sets over NVLink (``all_to_all_single`` on NCCL, sizes exchanged first), then a local sort + run-length
+  histogram, then an all-reduce(sum) of the <= 5001-bin histogram.  The per-group histograms are
+  all-reduced into a [G, 5001] table so that every rank can write identical step_4 / step_8 files.
+
+The reference has no distributed code at all (its parallelism is Snakemake running independent rules as
+processes); the invariant to keep is that the histograms -- hence the CSVs -- do not depend on the GPU
+count.
+
+The collective driver below is engine-agnostic: it talks to an *adapter* with four methods (group / export
+partitions / import keys / across).  ``CudaAdapter`` is the product adapter (device buffers, NCCL); the CPU
+test suite drives the same driver over gloo with a numpy stand-in defined in tests/ (never shipped).
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .engine import COUNTER_MAX, Engine, key_words
+
+
+def groups_of_rank(n_groups: int, rank: int, world: int) -> List[int]:
+    """1-based group numbers owned by `rank` (round-robin keeps big and small groups mixed)."""
+    return [g for g in range(1, n_groups + 1) if (g - 1) % world == rank]
+
+
+class CudaAdapter:
+    """Product adapter: everything stays in HBM; torch only owns the exchange buffers."""
+
+    def __init__(self, engine: Engine, device: torch.device):
+        self.eng = engine
+        self.device = device
+
+    def group(self, files: Sequence, k: int, nbins: int):
+        return self.eng.group_from_fasta(files, k, nbins=nbins, keep_set=True)
+
+    def export_partitions(self, k: int, world: int) -> Tuple[torch.Tensor, List[int]]:
+        """Retained group sets, grouped by destination rank.  Returns (int64 tensor of words, words per rank)."""
+        w = key_words(k)
+        ptr, n = self.eng.group_sets_device()
+        send = torch.empty(max(n, 1) * w, dtype=torch.int64, device=self.device)
+        off = np.zeros(world + 1, dtype=np.uint64)
+        if n:
+            self.eng._chk(self.eng.lib.khb_partition_by_hash(self.eng.ctx, ptr, n, k, world, send.data_ptr(), off.ctypes.data))
+            self.eng.sync()
+        return send[: n * w], [int(off[i + 1] - off[i]) * w for i in range(world)]
+
+    def import_keys(self, recv: torch.Tensor, k: int, n_groups: int) -> None:
+        """Replace the retained sets by the received keys of this rank's hash range."""
+        self.eng.group_sets_reset()
+        torch.cuda.synchronize(self.device)
+        self.eng.group_sets_append_device(recv.data_ptr() if recv.numel() else 0, recv.numel() // key_words(k), k, n_groups)
+        self.eng.sync()
+
+    def across(self, nbins: int):
+        return self.eng.across_groups(nbins=nbins)
+
+    def reset(self):
+        self.eng.group_sets_reset()
+
+    def new_tensor(self, n: int) -> torch.Tensor:
+        return torch.empty(n, dtype=torch.int64, device=self.device)
+
+
+def exchange_and_count(adapter, k: int, n_groups_total: int, nbins: int = COUNTER_MAX, group=None):
+    """Across-group stage on `world` ranks: hash partition -> all-to-all -> local count -> all-reduce.
+    Returns (step_8 histogram int64[nbins+1] identical on every rank, dict of exchange sizes)."""
+    world = dist.get_world_size(group)
+    send, send_words = adapter.export_partitions(k, world)
+    dev = send.device
+    # sizes first (one tiny all-to-all), then the payload
+    s = torch.tensor(send_words, dtype=torch.int64, device=dev)
+    r = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(r, s, group=group)
+    recv_words = [int(x) for x in r.tolist()]
+    recv = adapter.new_tensor(sum(recv_words))
+    dist.all_to_all_single(recv, send, output_split_sizes=recv_words, input_split_sizes=send_words, group=group)
+    adapter.import_keys(recv, k, n_groups_total)
+    hist, st = adapter.across(nbins)
+    h = torch.from_numpy(np.ascontiguousarray(hist).astype(np.int64)).to(dev)
+    dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
+    info = {"send_words": sum(send_words), "recv_words": sum(recv_words), "local_distinct": int(st.get("distinct", 0)),
+            "across_ms": float(st.get("ms_total", 0.0))}
+    return h.cpu().numpy().astype(np.uint64), info
+
+
+def run_exp1_k(adapter, groups: Dict[int, Sequence], n_groups_total: int, k: int, nbins: int = COUNTER_MAX, group=None):
+    """One k on this rank's share.  `groups` maps the 1-based numbers of the groups this rank owns to their
+    FASTA texts.  Returns (within [n_groups_total, nbins+1] uint64, across [nbins+1] uint64, stats)."""
+    adapter.reset()
+    within = np.zeros((n_groups_total, nbins + 1), dtype=np.int64)
+    stats = {"bases": 0, "windows": 0, "genome_distinct": 0, "group_distinct": 0, "group_ms": 0.0}
+    for num in sorted(groups):
+        hist, st = adapter.group(groups[num], k, nbins)
+        within[num - 1] = hist.astype(np.int64)
+        stats["bases"] += int(st["bases"])
+        stats["windows"] += int(st["windows"])
+        stats["genome_distinct"] += int(st["genome_distinct"])
+        stats["group_distinct"] += int(st["distinct"])
+        stats["group_ms"] += float(st["ms_total"])
+    across, info = exchange_and_count(adapter, k, n_groups_total, nbins, group)
+    stats.update(info)
+    dev = adapter.new_tensor(0).device
+    w = torch.from_numpy(within).to(dev)
+    dist.all_reduce(w, op=dist.ReduceOp.SUM, group=group)
+    return w.cpu().numpy().astype(np.uint64), across, stats
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """(rank, world, local_rank) from torchrun's environment; initialises the default process group."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local

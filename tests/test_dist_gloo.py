@@ -1,0 +1,114 @@
+"""World-size-2 (and 3) CPU test of the multi-GPU driver (khoice_b200/dist.py) over gloo.
+
+The collective driver is engine-agnostic; here it runs on a numpy/oracle stand-in adapter (TEST ONLY --
+the product adapter is dist.CudaAdapter and needs a B200).  What is checked is the host-side logic: group
+dealing, size exchange, variable all-to-all, histogram all-reduce, and that the result does not depend on
+the number of ranks."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleAdapter:
+    """Stand-in for dist.CudaAdapter: same four methods, CPU oracle arithmetic, CPU tensors."""
+
+    def __init__(self, k):
+        from oracle import oracle as O
+        self.O = O
+        self.sets = []
+        self.k = k
+
+    def reset(self):
+        self.sets = []
+
+    def group(self, files, k, nbins):
+        O = self.O
+        keys, counts = O.union_sum([O.genome_set(f, k) for f in files], k)
+        self.sets.append(keys)
+        nsym = sum(O.kmers(f, k)[1] for f in files)
+        st = {"bases": nsym, "windows": nsym, "genome_distinct": 0, "distinct": keys.shape[0], "ms_total": 0.0}
+        return O.histogram(counts, nbins), st
+
+    def export_partitions(self, k, world):
+        w = 1 if k <= 32 else 2
+        allk = np.concatenate(self.sets, axis=0) if self.sets else np.empty((0,) if w == 1 else (0, 2), np.uint64)
+        flat = allk.reshape(-1, w)
+        h = (flat[:, 0] * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(40)
+        if w == 2:
+            h = h ^ (flat[:, 1] * np.uint64(0xC2B2AE3D27D4EB4F) >> np.uint64(40))
+        dest = (h % np.uint64(world)).astype(np.int64)
+        order = np.argsort(dest, kind="stable")
+        words = [int((dest == r).sum()) * w for r in range(world)]
+        return torch.from_numpy(flat[order].reshape(-1).astype(np.int64)), words
+
+    def import_keys(self, recv, k, n_groups):
+        w = 1 if k <= 32 else 2
+        a = recv.numpy().astype(np.uint64)
+        self.sets = [a if w == 1 else a.reshape(-1, 2)]
+
+    def across(self, nbins):
+        keys, counts = self.O.union_sum(self.sets, self.k)
+        return self.O.histogram(counts, nbins), {"distinct": keys.shape[0], "ms_total": 0.0}
+
+    def new_tensor(self, n):
+        return torch.empty(n, dtype=torch.int64)
+
+
+def _make_groups(n_groups, k):
+    from khoice_b200 import synth
+    cfg = synth.SynthConfig(n_groups=n_groups, genomes_per_group=3, genome_len=12_000, seed=321)
+    return {g: [synth.make_genome(cfg, g, i) for i in range(1, 4)] for g in range(1, n_groups + 1)}
+
+
+def _worker(rank, world, port, n_groups, k, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from khoice_b200 import dist as kd
+    r, w, _ = kd.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    allg = _make_groups(n_groups, k)
+    mine = {g: allg[g] for g in kd.groups_of_rank(n_groups, rank, world)}
+    within, across, stats = kd.run_exp1_k(OracleAdapter(k), mine, n_groups, k)
+    np.save(os.path.join(out_dir, f"within_{world}_{rank}.npy"), within)
+    np.save(os.path.join(out_dir, f"across_{world}_{rank}.npy"), across)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("k", [21, 35])
+def test_rank_count_does_not_change_the_histograms(tmp_path, oracle, k):
+    n_groups = 5
+    allg = _make_groups(n_groups, k)
+    flat = [f for g in sorted(allg) for f in allg[g]]
+    gid = [g - 1 for g in sorted(allg) for _ in allg[g]]
+    w_ref, a_ref, _ = oracle.exp1(flat, gid, n_groups, k)
+    for world in (1, 2, 3):
+        mp.spawn(_worker, args=(world, _free_port(), n_groups, k, str(tmp_path)), nprocs=world, join=True)
+        for rank in range(world):
+            assert np.array_equal(np.load(tmp_path / f"within_{world}_{rank}.npy"), w_ref), (world, rank)
+            assert np.array_equal(np.load(tmp_path / f"across_{world}_{rank}.npy"), a_ref), (world, rank)
+
+
+def test_group_dealing():
+    from khoice_b200.dist import groups_of_rank
+    for n, world in ((10, 1), (10, 4), (3, 8), (100, 8)):
+        owned = [groups_of_rank(n, r, world) for r in range(world)]
+        assert sorted(g for o in owned for g in o) == list(range(1, n + 1))
+        assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1
