@@ -61,6 +61,20 @@ KHB_API int khb_device_info(khb_ctx *ctx, int *num_sms, size_t *free_bytes, size
 KHB_API uint64_t khb_launch_count(const khb_ctx *ctx); /* kernels launched on this context so far */
 KHB_API void *khb_stream(khb_ctx *ctx);                /* the cudaStream_t all work is enqueued on */
 
+/* Per-kernel timing for the roofline report: when enabled, every launch of the kernels below is bracketed by
+ * CUDA events on the context's stream.  khb_profile_enable() also clears what was recorded so far.
+ * khb_profile_read() sums, for one kernel id, the launches, their device time and their ALGORITHMIC bytes
+ * (compulsory traffic of the kernel's contract). */
+#define KHB_KERNEL_PACK 0       /* fasta_summary + fasta_scan + fasta_pack (one record per khb_pack_fasta) */
+#define KHB_KERNEL_EXTRACT 1    /* extract64 / extract128 */
+#define KHB_KERNEL_RADIX_HIST 2 /* radix_hist + radix_scan */
+#define KHB_KERNEL_ONESWEEP 3   /* onesweep_kernel, one record per digit pass */
+#define KHB_KERNEL_UNIQUE 4     /* unique_kernel */
+#define KHB_KERNEL_RLE 5        /* rle_hist_kernel */
+#define KHB_KERNEL_PARTITION 6  /* partition_kernel (both modes) */
+KHB_API int khb_profile_enable(khb_ctx *ctx, int on);
+KHB_API int khb_profile_read(khb_ctx *ctx, int kernel_id, uint64_t *launches, double *ms, uint64_t *alg_bytes);
+
 /* ---- memory ------------------------------------------------------------------------------------------ */
 KHB_API int khb_alloc(khb_ctx *ctx, size_t bytes, void **d_ptr);
 KHB_API int khb_free(khb_ctx *ctx, void *d_ptr);

@@ -17,6 +17,55 @@ int khb_count_runs_impl(khb_ctx *, const void *, size_t, int, u32, u32, u64 *, v
 
 static char g_init_error[512] = "";
 
+// ---- per-kernel timing ---------------------------------------------------------------------------
+struct khb_prof_rec {
+    int id;
+    cudaEvent_t a, b;
+    u64 bytes;
+};
+struct khb_prof {
+    std::vector<khb_prof_rec> recs;   // used records (in launch order)
+    std::vector<cudaEvent_t> pool;    // spare events
+    cudaEvent_t open_a;
+    bool open;
+};
+
+static cudaEvent_t prof_event(khb_prof *p)
+{
+    cudaEvent_t e = nullptr;
+    if (!p->pool.empty()) {
+        e = p->pool.back();
+        p->pool.pop_back();
+    } else {
+        cudaEventCreate(&e);
+    }
+    return e;
+}
+
+void khb_prof_begin(khb_ctx *ctx, int id)
+{
+    (void)id;
+    if (!ctx->prof_on || !ctx->prof) return;
+    khb_prof *p = ctx->prof;
+    p->open_a = prof_event(p);
+    p->open = true;
+    cudaEventRecord(p->open_a, ctx->stream);
+}
+
+void khb_prof_end(khb_ctx *ctx, int id, u64 alg_bytes)
+{
+    if (!ctx->prof_on || !ctx->prof || !ctx->prof->open) return;
+    khb_prof *p = ctx->prof;
+    khb_prof_rec r;
+    r.id = id;
+    r.a = p->open_a;
+    r.b = prof_event(p);
+    r.bytes = alg_bytes;
+    cudaEventRecord(r.b, ctx->stream);
+    p->recs.push_back(r);
+    p->open = false;
+}
+
 int khb_fail(khb_ctx *ctx, int code, const char *fmt, ...)
 {
     va_list ap;
@@ -130,6 +179,43 @@ int khb_device_info(khb_ctx *ctx, int *num_sms, size_t *free_bytes, size_t *tota
 }
 
 uint64_t khb_launch_count(const khb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int khb_profile_enable(khb_ctx *ctx, int on)
+{
+    KHB_CHECK_CTX(ctx);
+    if (!ctx->prof) ctx->prof = new khb_prof();
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &r : ctx->prof->recs) {
+        ctx->prof->pool.push_back(r.a);
+        ctx->prof->pool.push_back(r.b);
+    }
+    ctx->prof->recs.clear();
+    ctx->prof->open = false;
+    ctx->prof_on = on ? 1 : 0;
+    return KHB_OK;
+}
+
+int khb_profile_read(khb_ctx *ctx, int kernel_id, uint64_t *launches, double *ms, uint64_t *alg_bytes)
+{
+    KHB_CHECK_CTX(ctx);
+    uint64_t n = 0, bytes = 0;
+    double t = 0.0;
+    if (ctx->prof) {
+        KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (auto &r : ctx->prof->recs) {
+            if (r.id != kernel_id) continue;
+            float f = 0.f;
+            KHB_CUDA(ctx, cudaEventElapsedTime(&f, r.a, r.b));
+            t += f;
+            n++;
+            bytes += r.bytes;
+        }
+    }
+    if (launches) *launches = n;
+    if (ms) *ms = t;
+    if (alg_bytes) *alg_bytes = bytes;
+    return KHB_OK;
+}
 void *khb_stream(khb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 int khb_alloc(khb_ctx *ctx, size_t bytes, void **d_ptr)

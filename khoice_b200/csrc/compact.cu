@@ -271,11 +271,13 @@ int khb_unique_impl(khb_ctx *ctx, const void *d_sorted, size_t n, int k, void *d
     if (rc) return rc;
     u64 grid = (u64)ctx->num_sms * 3;
     if (grid > ntiles) grid = ntiles;
+    khb_prof_begin(ctx, KHB_K_UNIQUE);
     if (k <= 32)
         unique_kernel<Key64><<<(unsigned)grid, CP_BLOCK, 0, ctx->stream>>>((const Key64 *)d_sorted, n, (Key64 *)d_out, d_lb, d_ticket, 1u, d_count);
     else
         unique_kernel<Key128><<<(unsigned)grid, CP_BLOCK, 0, ctx->stream>>>((const Key128 *)d_sorted, n, (Key128 *)d_out, d_lb, d_ticket, 1u, d_count);
     KHB_LAUNCH_CHECK(ctx);
+    khb_prof_end(ctx, KHB_K_UNIQUE, 2 * (u64)n * (k <= 32 ? 8 : 16));  // upper bound: every key kept
     return KHB_OK;
 }
 
@@ -295,10 +297,12 @@ int khb_count_runs_impl(khb_ctx *ctx, const void *d_sorted, size_t n, int k, u32
     u64 grid = (u64)ctx->num_sms * 3;
     if (grid > ntiles) grid = ntiles;
     const size_t shm = ((size_t)nbins + 1) * sizeof(u32);
+    khb_prof_begin(ctx, KHB_K_RLE);
     if (k <= 32)
         rle_hist_kernel<Key64><<<(unsigned)grid, CP_BLOCK, shm, ctx->stream>>>((const Key64 *)d_sorted, n, cs, nbins, d_hist, (Key64 *)d_out_keys, d_out_counts, d_lb, d_ticket, 1u, d_runs);
     else
         rle_hist_kernel<Key128><<<(unsigned)grid, CP_BLOCK, shm, ctx->stream>>>((const Key128 *)d_sorted, n, cs, nbins, d_hist, (Key128 *)d_out_keys, d_out_counts, d_lb, d_ticket, 1u, d_runs);
     KHB_LAUNCH_CHECK(ctx);
+    khb_prof_end(ctx, KHB_K_RLE, (u64)n * (k <= 32 ? 8 : 16));  // input read; emitted keys are data dependent
     return KHB_OK;
 }

@@ -246,12 +246,14 @@ int khb_pack_fasta_impl(khb_ctx *ctx, const uint8_t *d_fasta, size_t nbytes, u64
     if (rc) return rc;
     TileSummary *summ = (TileSummary *)scr;
     uint8_t *state = (uint8_t *)(summ + ntiles);
+    khb_prof_begin(ctx, KHB_K_PACK);
     fasta_summary_kernel<<<(unsigned)ntiles, TILE_THREADS, 0, ctx->stream>>>((const uint4 *)d_fasta, ntiles, summ);
     KHB_LAUNCH_CHECK(ctx);
     fasta_scan_kernel<<<1, TILE_THREADS, 0, ctx->stream>>>(summ, ntiles, d_tile_base, state, d_counts);
     KHB_LAUNCH_CHECK(ctx);
     fasta_pack_kernel<<<(unsigned)ntiles, TILE_THREADS, 0, ctx->stream>>>((const uint4 *)d_fasta, ntiles, d_tile_base, state, d_codes, d_valid);
     KHB_LAUNCH_CHECK(ctx);
+    khb_prof_end(ctx, KHB_K_PACK, (u64)nbytes + nbytes / 4 + nbytes / 8);  // F + B/4 + B/8 with B ~ F
     return KHB_OK;
 }
 

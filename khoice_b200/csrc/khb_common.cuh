@@ -61,7 +61,15 @@ struct khb_ctx {
     size_t stage_host_cap;
     // timing of the last fused call (ms, CUDA events on ctx->stream)
     float last_ms[8];
+    // optional per-kernel timing (khb_profile_enable): CUDA event pairs around every launch
+    struct khb_prof *prof;
+    int prof_on;
 };
+
+// kernel ids for khb_profile_read
+enum { KHB_K_PACK = 0, KHB_K_EXTRACT = 1, KHB_K_RADIX_HIST = 2, KHB_K_ONESWEEP = 3, KHB_K_UNIQUE = 4, KHB_K_RLE = 5, KHB_K_PARTITION = 6, KHB_K_COUNT = 7 };
+void khb_prof_begin(khb_ctx *ctx, int id);
+void khb_prof_end(khb_ctx *ctx, int id, u64 alg_bytes);
 
 enum { SCR_TILE = 0, SCR_LOOKBACK = 1, SCR_HIST = 2, SCR_MISC = 3, SCR_KEYS_A = 4, SCR_KEYS_B = 5, SCR_PACK = 6, SCR_FLAGS = 7 };
 

@@ -106,10 +106,12 @@ int khb_extract_kmers_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid,
     size_t blocks = div_up(work, 256);
     const size_t cap = (size_t)ctx->num_sms * 32;
     if (blocks > cap) blocks = cap;
+    khb_prof_begin(ctx, KHB_K_EXTRACT);
     if (k <= 32)
         extract64_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_codes, d_valid, n_sym, k, (ulonglong2 *)d_keys);
     else
         extract128_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_codes, d_valid, n_sym, k, (ulonglong2 *)d_keys);
     KHB_LAUNCH_CHECK(ctx);
+    khb_prof_end(ctx, KHB_K_EXTRACT, (u64)n_sym / 4 + n_sym / 8 + (u64)n_sym * (k <= 32 ? 8 : 16));
     return KHB_OK;
 }

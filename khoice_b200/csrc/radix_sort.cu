@@ -243,13 +243,14 @@ static int sort_impl(khb_ctx *ctx, Key *d_keys, Key *d_tmp, const u64 *h_seg_off
     u64 *h_tab = (u64 *)malloc(sizeof(u64) * 2 * ((size_t)nseg + 1));
     if (!h_tab) return khb_fail(ctx, KHB_ERR_NOMEM, "sort: host table");
     u64 *h_off = h_tab, *h_tile = h_tab + nseg + 1;
-    u64 ntiles = 0;
+    u64 ntiles = 0, n_keys = 0;
     for (int s = 0; s < nseg; s++) {
         if (h_seg_off[s + 1] < h_seg_off[s]) { free(h_tab); return khb_fail(ctx, KHB_ERR_ARG, "sort: segment offsets not monotone"); }
         if (h_seg_off[s + 1] - h_seg_off[s] >= (1ull << 32)) { free(h_tab); return khb_fail(ctx, KHB_ERR_ARG, "sort: segment %d has >= 2^32 keys", s); }
         h_off[s] = h_seg_off[s];
         h_tile[s] = ntiles;
         ntiles += div_up(h_seg_off[s + 1] - h_seg_off[s], TILE);
+        n_keys += h_seg_off[s + 1] - h_seg_off[s];
     }
     h_off[nseg] = h_seg_off[nseg];
     h_tile[nseg] = ntiles;
@@ -282,11 +283,13 @@ static int sort_impl(khb_ctx *ctx, Key *d_keys, Key *d_tmp, const u64 *h_seg_off
         u64 grid = (u64)ctx->num_sms * 4;
         if (grid > ntiles) grid = ntiles;
         const size_t shm = (size_t)npass * 256 * sizeof(u32);
+        khb_prof_begin(ctx, KHB_K_RADIX_HIST);
         radix_hist_kernel<Key, ITEMS><<<(unsigned)grid, RS_BLOCK, shm, ctx->stream>>>(d_keys, d_off, d_tile, nseg, ntiles, npass, d_hist);
         KHB_LAUNCH_CHECK(ctx);
         const int nhist = nseg * npass;
         radix_scan_kernel<<<(unsigned)div_up(nhist, 8), 256, 0, ctx->stream>>>(d_hist, nhist);
         KHB_LAUNCH_CHECK(ctx);
+        khb_prof_end(ctx, KHB_K_RADIX_HIST, n_keys * sizeof(Key));
     }
     const size_t shm = sizeof(Key) * TILE + RS_WARPS * 256 * sizeof(unsigned short) + 256 * sizeof(u32) + 256 * sizeof(u64) + 33 * sizeof(u64);
     static bool attr_set[2] = {false, false};
@@ -297,9 +300,11 @@ static int sort_impl(khb_ctx *ctx, Key *d_keys, Key *d_tmp, const u64 *h_seg_off
     }
     Key *src = d_keys, *dst = d_tmp;
     for (int pass = 0; pass < npass; pass++) {
+        khb_prof_begin(ctx, KHB_K_ONESWEEP);
         onesweep_kernel<Key, ITEMS><<<(unsigned)ntiles, RS_BLOCK, shm, ctx->stream>>>(
             src, dst, d_off, d_tile, nseg, pass, npass, d_hist, d_lb, d_ticket + pass, (u32)(pass + 1));
         KHB_LAUNCH_CHECK(ctx);
+        khb_prof_end(ctx, KHB_K_ONESWEEP, 2 * n_keys * sizeof(Key));  // read + write every key once
         Key *t = src; src = dst; dst = t;
     }
     *result_in_tmp = (npass & 1);

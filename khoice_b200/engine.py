@@ -55,6 +55,8 @@ _SIGNATURES = [
     ("khb_device_info", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     ("khb_launch_count", C.c_uint64, [_P]),
     ("khb_stream", _P, [_P]),
+    ("khb_profile_enable", C.c_int, [_P, C.c_int]),
+    ("khb_profile_read", C.c_int, [_P, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     ("khb_alloc", C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     ("khb_free", C.c_int, [_P, _P]),
     ("khb_alloc_host", C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
@@ -208,6 +210,25 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self.lib.khb_launch_count(self.ctx))
+
+    KERNELS = {"pack": 0, "extract": 1, "radix_hist": 2, "onesweep": 3, "unique": 4, "rle_hist": 5, "partition": 6}
+
+    def profile_enable(self, on: bool = True):
+        """Bracket every kernel launch with CUDA events (clears earlier records)."""
+        self._chk(self.lib.khb_profile_enable(self.ctx, int(on)))
+
+    def profile_read(self) -> dict:
+        """{kernel: {launches, ms, alg_bytes}} accumulated since profile_enable()."""
+        out = {}
+        for name, kid in self.KERNELS.items():
+            n, ms, b = C.c_uint64(), C.c_double(), C.c_uint64()
+            self._chk(self.lib.khb_profile_read(self.ctx, kid, C.byref(n), C.byref(ms), C.byref(b)))
+            out[name] = {"launches": int(n.value), "ms": float(ms.value), "alg_bytes": int(b.value)}
+        return out
+
+    @property
+    def stream_ptr(self) -> int:
+        return int(self.lib.khb_stream(self.ctx) or 0)
 
     def device_info(self) -> dict:
         sms, fr, tot = C.c_int(), C.c_size_t(), C.c_size_t()
