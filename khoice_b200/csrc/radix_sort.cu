@@ -20,14 +20,22 @@
 //
 // Algorithmic bytes per key of width W: W (histogram read) + P x 2W (read + write per pass).
 #include "khb_common.cuh"
+#include <stdlib.h>
+
 #include "lookback.cuh"
 
 #define RS_BLOCK 512
 #define RS_WARPS (RS_BLOCK / 32)
 
+// Histogram kernel tiling (independent of the scatter-pass variant).
 template <typename Key> struct RsCfg;
 template <> struct RsCfg<Key64> { static constexpr int ITEMS = 12; };
 template <> struct RsCfg<Key128> { static constexpr int ITEMS = 8; };
+
+// Scatter-pass variants, selectable with KHB_SORT_VARIANT for tuning runs (default = the measured best).
+struct RsVariant {
+    int block, items;
+};
 
 template <typename Key> __device__ __forceinline__ Key key_max();
 template <> __device__ __forceinline__ Key64 key_max<Key64>() { return Key64{~0ull}; }
@@ -46,12 +54,11 @@ __device__ __forceinline__ int find_segment(const u64 *__restrict__ seg_tile, in
 }
 
 // ---- upfront digit histograms ------------------------------------------------------------------
-template <typename Key, int ITEMS>
+template <typename Key>
 __global__ void __launch_bounds__(RS_BLOCK)
 radix_hist_kernel(const Key *__restrict__ in, const u64 *__restrict__ seg_off, const u64 *__restrict__ seg_tile,
-                  int nseg, u64 ntiles, int npass, u32 *__restrict__ hist /* [nseg][npass][256] */)
+                  int nseg, u64 ntiles, int npass, u32 *__restrict__ hist /* [nseg][npass][256] */, u32 TILE)
 {
-    constexpr int TILE = RS_BLOCK * ITEMS;
     extern __shared__ u32 sh[];  // [npass][256]
     const u32 tid = threadIdx.x;
     for (int i = tid; i < npass * 256; i += RS_BLOCK) sh[i] = 0;
@@ -109,20 +116,40 @@ __global__ void radix_scan_kernel(u32 *__restrict__ hist, int nhist)
 }
 
 // ---- one scatter pass ------------------------------------------------------------------------------
-template <typename Key, int ITEMS>
-__global__ void __launch_bounds__(RS_BLOCK, 2)
+// peers = lanes of the warp whose digit equals mine.  MATCH 0: MATCH.ANY instruction; MATCH 1: eight ballots
+// (one per digit bit; fixed-latency ALU/vote work that pipelines across the ITEMS rounds).
+template <int MATCH>
+__device__ __forceinline__ u32 match_digit(u32 d)
+{
+    if (MATCH == 0) return __match_any_sync(0xffffffffu, d);
+    u32 peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const bool bit = (d >> b) & 1u;
+        const u32 bal = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    return peers;
+}
+
+template <typename Key, int BLOCK, int ITEMS, int MINB, int MATCH>
+__global__ void __launch_bounds__(BLOCK, MINB)
 onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__restrict__ seg_off,
                 const u64 *__restrict__ seg_tile, int nseg, int pass, int npass,
                 const u32 *__restrict__ bin_base /* [nseg][npass][256], exclusive */, u64 *__restrict__ lookback,
                 u32 *__restrict__ ticket, u32 epoch)
 {
-    constexpr int TILE = RS_BLOCK * ITEMS;
+    constexpr int TILE = BLOCK * ITEMS;
+    constexpr int NW = BLOCK / 32;
+    constexpr int LBW = 2;  // look-back window: predecessors fetched per hop
+    static_assert(BLOCK >= 256, "256 digit threads needed");
+    static_assert(TILE < 65536, "16-bit tile offsets");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Key *sorted = (Key *)smem_raw;                                          // [TILE]
-    unsigned short *wcnt = (unsigned short *)(smem_raw + sizeof(Key) * TILE);  // [RS_WARPS][256]
-    u32 *digit_start = (u32 *)(wcnt + RS_WARPS * 256);                      // [256]
-    u64 *glob_base = (u64 *)(digit_start + 256);                            // [256]
-    u64 *ws = glob_base + 256;                                              // [33] scan scratch
+    Key *sorted = (Key *)smem_raw;                                             // [TILE]
+    unsigned short *wcnt = (unsigned short *)(smem_raw + sizeof(Key) * TILE);  // [NW][256]
+    u32 *glob_off = (u32 *)(wcnt + NW * 256);                                  // [256] offset of sorted[j] in the segment, minus j
+    u32 *ws = glob_off + 256;                                                  // [36] scan scratch
+    u32 *mm = ws + 36;                                                         // [NW][256] peer masks (MATCH 2 only)
     __shared__ u32 s_tile;
     __shared__ int s_seg;
 
@@ -132,110 +159,231 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
         s_tile = t;
         s_seg = find_segment(seg_tile, nseg, t);
     }
-    for (int i = tid; i < RS_WARPS * 256 / 2; i += RS_BLOCK) ((u32 *)wcnt)[i] = 0;
+    for (int i = tid; i < NW * 256 / 2; i += BLOCK) ((u32 *)wcnt)[i] = 0;
+    if (MATCH == 2)
+        for (int i = tid; i < NW * 256; i += BLOCK) mm[i] = 0;
     __syncthreads();
     const u64 tile = s_tile;
     const int seg = s_seg;
     const u64 first_tile = seg_tile[seg];
     const u64 seg_begin = seg_off[seg];
-    const u64 begin = seg_begin + (tile - first_tile) * TILE;
+    const u64 rel = tile - first_tile;  // position of this tile in its segment's chain
+    const u64 begin = seg_begin + rel * TILE;
     const u64 seg_end = seg_off[seg + 1];
     const u32 n = (u32)(seg_end - begin < (u64)TILE ? seg_end - begin : (u64)TILE);
 
     // load: warp-striped, memory order = (warp, item, lane)
     Key keys[ITEMS];
-    u32 rank[ITEMS];
+    u32 rank2[(ITEMS + 1) / 2];  // two 16-bit ranks per register
+#pragma unroll
+    for (int r = 0; r < (ITEMS + 1) / 2; r++) rank2[r] = 0;
     const u32 wbase = warp * (32 * ITEMS);
+    const Key *src = in + begin + wbase + lane;
+    if (wbase + 32 * ITEMS <= n) {
 #pragma unroll
-    for (int r = 0; r < ITEMS; r++) {
-        const u32 idx = wbase + r * 32 + lane;
-        keys[r] = idx < n ? in[begin + idx] : key_max<Key>();
+        for (int r = 0; r < ITEMS; r++) keys[r] = src[r * 32];
+    } else {
+#pragma unroll
+        for (int r = 0; r < ITEMS; r++) keys[r] = (wbase + r * 32 + lane < n) ? src[r * 32] : key_max<Key>();
     }
-    // rank within the warp's chunk (stable): peers = lanes holding the same digit in this round
+    // rank within the warp's chunk (stable)
     unsigned short *mycnt = wcnt + warp * 256;
+    if (MATCH == 2) {
+        // peers through shared memory: every lane ORs its lane bit into the word of its digit
+        u32 *mymm = mm + warp * 256;
+        const u32 lbit = 1u << lane;
 #pragma unroll
-    for (int r = 0; r < ITEMS; r++) {
-        const u32 d = key_digit(keys[r], pass);
-        const u32 peers = __match_any_sync(0xffffffffu, d);
-        const u32 below = __popc(peers & lanemask_lt());
-        u32 old = 0;
-        if (below == 0) {
-            old = mycnt[d];
-            mycnt[d] = (unsigned short)(old + __popc(peers));
+        for (int r = 0; r < ITEMS; r++) {
+            const u32 d = key_digit(keys[r], pass);
+            atomicOr(&mymm[d], lbit);
+            __syncwarp();
+            const u32 peers = mymm[d];
+            const u32 c = mycnt[d];
+            __syncwarp();
+            const u32 below = __popc(peers & lanemask_lt());
+            if (below == 0) {
+                mymm[d] = 0;
+                mycnt[d] = (unsigned short)(c + __popc(peers));
+            }
+            rank2[r >> 1] |= (c + below) << (16 * (r & 1));
+            __syncwarp();
         }
-        old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
-        rank[r] = old + below;
-        __syncwarp();
+    } else {
+        u32 peers[ITEMS];
+#pragma unroll
+        for (int r = 0; r < ITEMS; r++) peers[r] = match_digit<MATCH>(key_digit(keys[r], pass));
+#pragma unroll
+        for (int r = 0; r < ITEMS; r++) {
+            const u32 d = key_digit(keys[r], pass);
+            const u32 c = mycnt[d];
+            __syncwarp();
+            const u32 below = __popc(peers[r] & lanemask_lt());
+            if (below == 0) mycnt[d] = (unsigned short)(c + __popc(peers[r]));
+            rank2[r >> 1] |= (c + below) << (16 * (r & 1));
+            __syncwarp();
+        }
     }
     __syncthreads();
-    // per digit: exclusive scan across warps (in place) -> tile count
+    // per digit: exclusive scan across warps -> tile count
     u32 count = 0;
     if (tid < 256) {
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; w++) {
-            const u32 c = wcnt[w * 256 + tid];
-            wcnt[w * 256 + tid] = (unsigned short)count;
-            count += c;
-        }
+        for (int w = 0; w < NW; w++) count += wcnt[w * 256 + tid];
     }
     // exclusive scan across digits (padding keys of a partial tile carry digit 255 and stay at the end)
-    u64 total;
-    const u32 dstart = (u32)block_excl_sum<u64>((u64)count, ws, &total);
-    u64 *lb = lookback + tile * 256 + tid;
-    u64 first_hop = 0;
+    u32 total;
+    const u32 dstart = block_excl_sum<u32>(count, ws, &total);
+    u64 *lbcol = lookback + first_tile * 256 + tid;  // column `tid` of the segment's look-back rows
+    u64 win[LBW];
     if (tid < 256) {
-        digit_start[tid] = dstart;
-        if (tid == 255) count -= (u32)(TILE - n);  // padding is not data
-        if (tile == first_tile) {
-            lb_store(lb, lb_pack(LB_PREFIX, count, epoch));
-        } else {
-            lb_store(lb, lb_pack(LB_AGG, count, epoch));
-            first_hop = lb_load(lb - 256);  // issued now, consumed after the reorder below
+        // per-warp start of every digit inside the sorted tile
+        u32 run = dstart;
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            const u32 c = wcnt[w * 256 + tid];
+            wcnt[w * 256 + tid] = (unsigned short)run;
+            run += c;
         }
+        if (tid == 255) count -= (u32)(TILE - n);  // padding is not data
+        lb_store(lbcol + rel * 256, lb_pack(rel == 0 ? LB_PREFIX : LB_AGG, count, epoch));
+        // first window of predecessors: issued now, consumed after the reorder below
+#pragma unroll
+        for (int i = 0; i < LBW; i++) win[i] = (rel > (u64)i) ? lb_load(lbcol + (rel - 1 - i) * 256) : 0ull;
     }
     __syncthreads();
     // reorder through shared memory
 #pragma unroll
     for (int r = 0; r < ITEMS; r++) {
         const u32 d = key_digit(keys[r], pass);
-        sorted[digit_start[d] + wcnt[warp * 256 + d] + rank[r]] = keys[r];
+        sorted[wcnt[warp * 256 + d] + ((rank2[r >> 1] >> (16 * (r & 1))) & 0xffffu)] = keys[r];
     }
     // finish the look-back (256 digit threads)
     if (tid < 256) {
-        u64 excl = 0;
-        if (tile != first_tile) {
-            u64 t = tile - 1;
-            u64 e = first_hop;
-            for (;;) {
-                u32 st = lb_status(e, epoch);
-                while (st == 0) {
-                    e = lb_load(lookback + t * 256 + tid);
-                    st = lb_status(e, epoch);
+        u32 excl = 0;
+        if (rel != 0) {
+            u64 r0 = rel;  // entries [0, r0) remain
+            bool done = false;
+            while (!done) {
+#pragma unroll
+                for (int i = 0; i < LBW; i++) {
+                    if (done || r0 <= (u64)i) continue;
+                    u64 e = win[i];
+                    u32 st = lb_status(e, epoch);
+                    while (st == 0) {
+                        e = lb_load(lbcol + (r0 - 1 - i) * 256);
+                        st = lb_status(e, epoch);
+                    }
+                    excl += (u32)e;
+                    if (st == LB_PREFIX) done = true;
                 }
-                excl += e & LB_VALUE_MASK;
-                if (st == LB_PREFIX || t == first_tile) break;
-                --t;
-                e = lb_load(lookback + t * 256 + tid);
+                if (r0 <= LBW) done = true;
+                if (!done) {
+                    r0 -= LBW;
+#pragma unroll
+                    for (int i = 0; i < LBW; i++) win[i] = (r0 > (u64)i) ? lb_load(lbcol + (r0 - 1 - i) * 256) : 0ull;
+                }
             }
-            lb_store(lb, lb_pack(LB_PREFIX, excl + count, epoch));
+            lb_store(lbcol + rel * 256, lb_pack(LB_PREFIX, (u64)excl + count, epoch));
         }
-        glob_base[tid] = seg_begin + (u64)bin_base[((size_t)seg * npass + pass) * 256 + tid] + excl - (u64)dstart;
+        glob_off[tid] = bin_base[((size_t)seg * npass + pass) * 256 + tid] + excl - dstart;
     }
     __syncthreads();
-    // coalesced store: position j of the sorted tile goes to glob_base[digit] + j
+    // coalesced store: position j of the sorted tile goes to segment offset glob_off[digit] + j
+    Key *dst = out + seg_begin;
 #pragma unroll 4
-    for (u32 j = tid; j < n; j += RS_BLOCK) {
+    for (u32 j = tid; j < n; j += BLOCK) {
         const Key key = sorted[j];
-        out[glob_base[key_digit(key, pass)] + j] = key;
+        dst[glob_off[key_digit(key, pass)] + j] = key;
     }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
+template <typename Key, int BLOCK, int ITEMS, int MINB, int MATCH>
+static int launch_passes(khb_ctx *ctx, Key *src, Key *dst, const u64 *d_off, const u64 *d_tile, int nseg, int npass, u64 ntiles,
+                         u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket)
+{
+    constexpr int TILE = BLOCK * ITEMS;
+    constexpr int NW = BLOCK / 32;
+    const size_t shm = sizeof(Key) * TILE + NW * 256 * sizeof(unsigned short) + 256 * sizeof(u32) + 36 * sizeof(u32) +
+                       (MATCH == 2 ? NW * 256 * sizeof(u32) : 0);
+    static bool attr_set = false;
+    if (!attr_set) {
+        KHB_CUDA(ctx, cudaFuncSetAttribute(onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+        attr_set = true;
+    }
+    for (int pass = 0; pass < npass; pass++) {
+        khb_prof_begin(ctx, KHB_K_ONESWEEP);
+        onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH><<<(unsigned)ntiles, BLOCK, shm, ctx->stream>>>(
+            src, dst, d_off, d_tile, nseg, pass, npass, d_hist, d_lb, d_ticket + pass, (u32)(pass + 1));
+        KHB_LAUNCH_CHECK(ctx);
+        khb_prof_end(ctx, KHB_K_ONESWEEP, 2 * n_keys * sizeof(Key));  // read + write every key once
+        Key *t = src; src = dst; dst = t;
+    }
+    return KHB_OK;
+}
+
+static int sort_variant()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("KHB_SORT_VARIANT");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
+// tile size (keys) of the scatter-pass variant `v` for key width W
+static u32 variant_tile(int v, size_t W)
+{
+    if (W == 16) return v == 2 ? 256 * 8 : 512 * 6;
+    switch (v) {
+    case 0: return 512 * 12;
+    case 1: return 512 * 12;
+    case 2: return 512 * 8;
+    case 3: return 384 * 12;
+    case 4: return 256 * 16;
+    case 5: return 512 * 12;
+    case 6: return 512 * 8;
+    case 7: return 384 * 12;
+    default: return 512 * 12;
+    }
+}
+
+template <typename Key>
+static int dispatch_passes(khb_ctx *ctx, int v, Key *src, Key *dst, const u64 *d_off, const u64 *d_tile, int nseg, int npass,
+                           u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket);
+
+template <>
+int dispatch_passes<Key64>(khb_ctx *ctx, int v, Key64 *src, Key64 *dst, const u64 *d_off, const u64 *d_tile, int nseg, int npass,
+                           u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket)
+{
+#define GO(B, I, M, MT) return launch_passes<Key64, B, I, M, MT>(ctx, src, dst, d_off, d_tile, nseg, npass, ntiles, n_keys, d_hist, d_lb, d_ticket)
+    switch (v) {
+    case 0: GO(512, 12, 2, 0);
+    case 2: GO(512, 8, 3, 1);
+    case 3: GO(384, 12, 3, 1);
+    case 4: GO(256, 16, 4, 1);
+    case 5: GO(512, 12, 2, 2);
+    case 6: GO(512, 8, 3, 2);
+    case 7: GO(384, 12, 3, 2);
+    default: GO(512, 12, 2, 1);
+    }
+#undef GO
+}
+
+template <>
+int dispatch_passes<Key128>(khb_ctx *ctx, int v, Key128 *src, Key128 *dst, const u64 *d_off, const u64 *d_tile, int nseg, int npass,
+                            u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket)
+{
+    if (v == 2) return launch_passes<Key128, 256, 8, 3, 1>(ctx, src, dst, d_off, d_tile, nseg, npass, ntiles, n_keys, d_hist, d_lb, d_ticket);
+    return launch_passes<Key128, 512, 6, 2, 1>(ctx, src, dst, d_off, d_tile, nseg, npass, ntiles, n_keys, d_hist, d_lb, d_ticket);
+}
+
 template <typename Key>
 static int sort_impl(khb_ctx *ctx, Key *d_keys, Key *d_tmp, const u64 *h_seg_off, int nseg, int k, int *result_in_tmp)
 {
-    constexpr int ITEMS = RsCfg<Key>::ITEMS;
-    constexpr int TILE = RS_BLOCK * ITEMS;
+    const int v = sort_variant();
+    const u32 TILE = variant_tile(v, sizeof(Key));
     const int npass = (2 * k + 7) / 8;
     *result_in_tmp = 0;
     if (nseg <= 0) return KHB_OK;
@@ -284,29 +432,15 @@ static int sort_impl(khb_ctx *ctx, Key *d_keys, Key *d_tmp, const u64 *h_seg_off
         if (grid > ntiles) grid = ntiles;
         const size_t shm = (size_t)npass * 256 * sizeof(u32);
         khb_prof_begin(ctx, KHB_K_RADIX_HIST);
-        radix_hist_kernel<Key, ITEMS><<<(unsigned)grid, RS_BLOCK, shm, ctx->stream>>>(d_keys, d_off, d_tile, nseg, ntiles, npass, d_hist);
+        radix_hist_kernel<Key><<<(unsigned)grid, RS_BLOCK, shm, ctx->stream>>>(d_keys, d_off, d_tile, nseg, ntiles, npass, d_hist, TILE);
         KHB_LAUNCH_CHECK(ctx);
         const int nhist = nseg * npass;
         radix_scan_kernel<<<(unsigned)div_up(nhist, 8), 256, 0, ctx->stream>>>(d_hist, nhist);
         KHB_LAUNCH_CHECK(ctx);
         khb_prof_end(ctx, KHB_K_RADIX_HIST, n_keys * sizeof(Key));
     }
-    const size_t shm = sizeof(Key) * TILE + RS_WARPS * 256 * sizeof(unsigned short) + 256 * sizeof(u32) + 256 * sizeof(u64) + 33 * sizeof(u64);
-    static bool attr_set[2] = {false, false};
-    const int which = sizeof(Key) == 8 ? 0 : 1;
-    if (!attr_set[which]) {
-        KHB_CUDA(ctx, cudaFuncSetAttribute(onesweep_kernel<Key, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-        attr_set[which] = true;
-    }
-    Key *src = d_keys, *dst = d_tmp;
-    for (int pass = 0; pass < npass; pass++) {
-        khb_prof_begin(ctx, KHB_K_ONESWEEP);
-        onesweep_kernel<Key, ITEMS><<<(unsigned)ntiles, RS_BLOCK, shm, ctx->stream>>>(
-            src, dst, d_off, d_tile, nseg, pass, npass, d_hist, d_lb, d_ticket + pass, (u32)(pass + 1));
-        KHB_LAUNCH_CHECK(ctx);
-        khb_prof_end(ctx, KHB_K_ONESWEEP, 2 * n_keys * sizeof(Key));  // read + write every key once
-        Key *t = src; src = dst; dst = t;
-    }
+    rc = dispatch_passes<Key>(ctx, v, d_keys, d_tmp, d_off, d_tile, nseg, npass, ntiles, n_keys, d_hist, d_lb, d_ticket);
+    if (rc) return rc;
     *result_in_tmp = (npass & 1);
     return KHB_OK;
 }
