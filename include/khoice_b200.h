@@ -110,6 +110,26 @@ KHB_API int khb_pack_fasta(khb_ctx *ctx, const uint8_t *d_fasta, size_t nbytes, 
 KHB_API int khb_extract_kmers(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, size_t n_symbols, int k,
                       void *d_keys);
 
+/* K2, fused-path flavour: d_keys[i] = h(canonical k-mer), h = the bijective mixer of khb_common.cuh (uniform top
+ * bits, sentinel preserved).  khb_remix_keys applies h (inverse = 0) or its inverse (inverse = 1) in place. */
+KHB_API int khb_extract_kmers_hashed(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, size_t n_symbols, int k,
+                             void *d_keys);
+KHB_API int khb_remix_keys(khb_ctx *ctx, void *d_keys, size_t n, int k, int inverse);
+
+/* Prefix plan of the fused path: instead of all ceil(2k/8) digits, hashed keys are sorted by the *npass digits
+ * starting at bit *first_bit only (enough prefix bits for segments of at most n_max keys, plus the spare bit above
+ * the key so that sentinels never share a prefix with a k-mer); equality inside a prefix run is then resolved by
+ * comparison (khb_resolve_*).  first_bit = 0 means a full sort (small k, or k = 32 / 64 which have no spare bit). */
+KHB_API int khb_prefix_plan(int k, uint64_t n_max, int *first_bit, int *npass);
+KHB_API int khb_sort_key_bits(khb_ctx *ctx, void *d_keys, void *d_tmp, const uint64_t *h_seg_off, int n_segments, int key_bytes,
+                      int first_bit, int npass, int *result_in_tmp);
+/* K4 / K5 / K6 on prefix-sorted keys (prefix = bits >= prefix_shift; 0 = fully sorted input): distinct keys in
+ * order of first occurrence, resp. histogram of multiplicities (+ optional distinct keys).  Every segment of the
+ * input must end with at least one sentinel or be the only segment. */
+KHB_API int khb_resolve_unique(khb_ctx *ctx, const void *d_sorted, size_t n, int k, int prefix_shift, void *d_out, uint64_t *h_count);
+KHB_API int khb_resolve_count(khb_ctx *ctx, const void *d_sorted, size_t n, int k, int prefix_shift, uint32_t cs, uint32_t nbins,
+                      uint64_t *h_hist, void *d_out_keys, uint64_t *h_runs);
+
 /* K3: sort every segment [h_seg_off[s], h_seg_off[s+1]) of d_keys independently (LSD radix, ceil(2k/8)
  * passes).  d_tmp is a same-sized ping-pong buffer; *result_in_tmp tells where the result is. */
 KHB_API int khb_sort_keys(khb_ctx *ctx, void *d_keys, void *d_tmp, const uint64_t *h_seg_off, int n_segments, int k,
@@ -139,6 +159,8 @@ typedef struct khb_stats {
     uint64_t distinct;        /* distinct k-mers of the group / across groups */
     float ms_total;           /* device time of the stage, CUDA events        */
     float ms_h2d, ms_pack, ms_extract, ms_sort1, ms_unique, ms_sort2, ms_count;
+    int passes_genome;        /* radix passes of the per-genome sort          */
+    int passes_group;         /* radix passes of the group / across sort      */
 } khb_stats;
 
 /* One species group, from FASTA text in HOST memory to its step_4 histogram: rules
@@ -162,7 +184,9 @@ KHB_API int khb_across_groups(khb_ctx *ctx, uint32_t nbins, uint64_t *h_hist, kh
  * read back from a step_6 file), reset. */
 KHB_API int khb_group_sets_info(khb_ctx *ctx, int *k, int *n_groups, uint64_t *n_keys);
 KHB_API int khb_group_sets_device(khb_ctx *ctx, void **d_keys, uint64_t *n_keys); /* device view of the retained keys */
-KHB_API int khb_group_sets_append_device(khb_ctx *ctx, int k, const void *d_keys, uint64_t n_keys, int n_groups);
+KHB_API int khb_group_sets_append_device(khb_ctx *ctx, int k, const void *d_keys, uint64_t n_keys, int n_groups, int hashed);
+KHB_API int khb_group_sets_hashed(khb_ctx *ctx);           /* 1 if the retained keys are h(canonical k-mer) */
+KHB_API int khb_group_sets_export(khb_ctx *ctx, void *h_out); /* retained keys as canonical k-mer values, to host */
 KHB_API int khb_group_sets_append_host(khb_ctx *ctx, int k, const void *h_keys, uint64_t n_keys, int n_groups);
 KHB_API int khb_group_sets_reset(khb_ctx *ctx);
 

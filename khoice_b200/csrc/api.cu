@@ -10,8 +10,12 @@
 // implemented in the kernel translation units
 int khb_pack_fasta_impl(khb_ctx *, const uint8_t *, size_t, u64 *, u32 *, size_t, u64 *, u64 *);
 int khb_fasta_separators_impl(khb_ctx *, uint8_t *, const u64 *, const u64 *, int, u64);
-int khb_extract_kmers_impl(khb_ctx *, const u64 *, const u32 *, size_t, int, void *);
+int khb_extract_kmers_impl(khb_ctx *, const u64 *, const u32 *, size_t, int, int, void *);
+int khb_remix_impl(khb_ctx *, void *, size_t, int, int);
 int khb_sort_keys_impl(khb_ctx *, void *, void *, const u64 *, int, int, int *);
+int khb_sort_bits_impl(khb_ctx *, void *, void *, const u64 *, int, int, int, int, int *);
+int khb_resolve_unique_impl(khb_ctx *, const void *, size_t, int, int, void *, u64 *);
+int khb_resolve_count_impl(khb_ctx *, const void *, size_t, int, int, u32, u32, u64 *, void *, u64 *);
 int khb_unique_impl(khb_ctx *, const void *, size_t, int, void *, u64 *);
 int khb_count_runs_impl(khb_ctx *, const void *, size_t, int, u32, u32, u64 *, void *, u32 *, u64 *);
 
@@ -327,7 +331,75 @@ int khb_pack_fasta(khb_ctx *ctx, const uint8_t *d_fasta, size_t nbytes, uint64_t
 int khb_extract_kmers(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, size_t n_symbols, int k, void *d_keys)
 {
     KHB_CHECK_CTX(ctx);
-    return khb_extract_kmers_impl(ctx, (const u64 *)d_codes, d_valid, n_symbols, k, d_keys);
+    return khb_extract_kmers_impl(ctx, (const u64 *)d_codes, d_valid, n_symbols, k, 0, d_keys);
+}
+
+int khb_extract_kmers_hashed(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, size_t n_symbols, int k, void *d_keys)
+{
+    KHB_CHECK_CTX(ctx);
+    return khb_extract_kmers_impl(ctx, (const u64 *)d_codes, d_valid, n_symbols, k, 1, d_keys);
+}
+
+int khb_remix_keys(khb_ctx *ctx, void *d_keys, size_t n, int k, int inverse)
+{
+    KHB_CHECK_CTX(ctx);
+    return khb_remix_impl(ctx, d_keys, n, k, inverse);
+}
+
+int khb_prefix_plan(int k, uint64_t n_max, int *first_bit, int *npass)
+{
+    if (k < 1 || k > 64 || !first_bit || !npass) return KHB_ERR_ARG;
+    const int full = (2 * k + 7) / 8;
+    *first_bit = 0;
+    *npass = full;
+    if (k == 32 || k == 64) return KHB_OK;  // no spare bit above the key: full sort
+    static int slack = -1;
+    if (slack < 0) {
+        const char *e = getenv("KHB_PREFIX_SLACK");
+        slack = e ? atoi(e) : 0;
+    }
+    int lg = 1;
+    while (lg < 63 && (1ull << lg) < n_max) lg++;
+    const int np = (lg + slack + 1 + 7) / 8;  // prefix key bits + the spare bit that separates sentinels
+    if (np < 1 || 8 * np >= 2 * k + 1) return KHB_OK;
+    *first_bit = 2 * k + 1 - 8 * np;
+    *npass = np;
+    return KHB_OK;
+}
+
+int khb_sort_key_bits(khb_ctx *ctx, void *d_keys, void *d_tmp, const uint64_t *h_seg_off, int n_segments, int key_bytes,
+                      int first_bit, int npass, int *result_in_tmp)
+{
+    KHB_CHECK_CTX(ctx);
+    int dummy;
+    return khb_sort_bits_impl(ctx, d_keys, d_tmp, (const u64 *)h_seg_off, n_segments, key_bytes, first_bit, npass,
+                              result_in_tmp ? result_in_tmp : &dummy);
+}
+
+int khb_resolve_unique(khb_ctx *ctx, const void *d_sorted, size_t n, int k, int prefix_shift, void *d_out, uint64_t *h_count)
+{
+    KHB_CHECK_CTX(ctx);
+    int rc = khb_resolve_unique_impl(ctx, d_sorted, n, k, prefix_shift, d_out, ctx->d_mail);
+    if (rc) return rc;
+    KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, ctx->d_mail, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_count) *h_count = ctx->h_mail[0];
+    return KHB_OK;
+}
+
+int khb_resolve_count(khb_ctx *ctx, const void *d_sorted, size_t n, int k, int prefix_shift, uint32_t cs, uint32_t nbins,
+                      uint64_t *h_hist, void *d_out_keys, uint64_t *h_runs)
+{
+    KHB_CHECK_CTX(ctx);
+    if (!h_hist) return khb_fail(ctx, KHB_ERR_ARG, "khb_resolve_count: null histogram");
+    u64 *d_hist = ctx->d_mail + 8, *d_runs = ctx->d_mail;
+    int rc = khb_resolve_count_impl(ctx, d_sorted, n, k, prefix_shift, cs, nbins, d_hist, d_out_keys, d_runs);
+    if (rc) return rc;
+    KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, ctx->d_mail, (nbins + 9) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(h_hist, ctx->h_mail + 8, ((size_t)nbins + 1) * sizeof(u64));
+    if (h_runs) *h_runs = ctx->h_mail[0];
+    return KHB_OK;
 }
 
 int khb_sort_keys(khb_ctx *ctx, void *d_keys, void *d_tmp, const uint64_t *h_seg_off, int n_segments, int k, int *result_in_tmp)
@@ -535,41 +607,49 @@ static int group_from_staged_impl(khb_ctx *ctx, int k, int n_genomes, const uint
     tm.mark();  // 2: pack done
     KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const u64 n_sym = counts[0];
-    // K2
+    // K2 (hashed unless k = 32 / 64, see khb_prefix_plan)
+    const int hashed = (k != 32 && k != 64) ? 1 : 0;
+    if (ctx->gs_k && keep_set && ctx->gs_hashed != hashed) return khb_fail(ctx, KHB_ERR_STATE, "retained group sets use a different key encoding");
     const size_t key_bytes = (n_sym + 4) * W;
     if ((rc = khb_scratch_get(ctx, SCR_KEYS_A, key_bytes, &p))) return rc;
     void *bufA = p;
     if ((rc = khb_scratch_get(ctx, SCR_KEYS_B, key_bytes, &p))) return rc;
     void *bufB = p;
-    if ((rc = khb_extract_kmers_impl(ctx, d_codes, d_valid, n_sym, k, bufA))) return rc;
+    if ((rc = khb_extract_kmers_impl(ctx, d_codes, d_valid, n_sym, k, hashed, bufA))) return rc;
     tm.mark();  // 3: extract done
-    // K3 per genome (segmented)
+    // K3 per genome (segmented), prefix only
     std::vector<u64> seg(n_genomes + 1);
+    u64 max_seg = 1;
     for (int g = 0; g < n_genomes; g++) seg[g] = tile_base[h_begin[g] / KHB_FASTA_TILE];
     seg[n_genomes] = n_sym;
+    for (int g = 0; g < n_genomes; g++) max_seg = seg[g + 1] - seg[g] > max_seg ? seg[g + 1] - seg[g] : max_seg;
+    int fb1, np1, fb2, np2;
+    khb_prefix_plan(k, max_seg, &fb1, &np1);
     int in_tmp = 0;
-    if ((rc = khb_sort_keys_impl(ctx, bufA, bufB, seg.data(), n_genomes, k, &in_tmp))) return rc;
+    if ((rc = khb_sort_bits_impl(ctx, bufA, bufB, seg.data(), n_genomes, (int)W, fb1, np1, &in_tmp))) return rc;
     void *sorted = in_tmp ? bufB : bufA, *other = in_tmp ? bufA : bufB;
     tm.mark();  // 4: sort1 done
     // K4
-    if ((rc = khb_unique_impl(ctx, sorted, n_sym, k, other, ctx->d_mail))) return rc;
+    if ((rc = khb_resolve_unique_impl(ctx, sorted, n_sym, k, fb1, other, ctx->d_mail))) return rc;
     KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, ctx->d_mail, 8, cudaMemcpyDeviceToHost, ctx->stream));
     tm.mark();  // 5: unique done
     KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const u64 s_g = ctx->h_mail[0];
-    // K3' group sort
+    // K3' group sort, prefix only
+    khb_prefix_plan(k, s_g, &fb2, &np2);
     u64 one_seg[2] = {0, s_g};
-    if ((rc = khb_sort_keys_impl(ctx, other, sorted, one_seg, 1, k, &in_tmp))) return rc;
+    if ((rc = khb_sort_bits_impl(ctx, other, sorted, one_seg, 1, (int)W, fb2, np2, &in_tmp))) return rc;
     void *gsorted = in_tmp ? sorted : other;
     tm.mark();  // 6: sort2 done
     // K5
     void *out_keys = nullptr;
     if (keep_set) {
         if ((rc = gs_reserve(ctx, k, s_g))) return rc;
+        ctx->gs_hashed = hashed;
         out_keys = (char *)ctx->gs_buf + ctx->gs_len * W;
     }
     u64 *d_hist = ctx->d_mail + 8, *d_runs = ctx->d_mail;
-    if ((rc = khb_count_runs_impl(ctx, gsorted, s_g, k, KHB_COUNTER_MAX, nbins, d_hist, out_keys, nullptr, d_runs))) return rc;
+    if ((rc = khb_resolve_count_impl(ctx, gsorted, s_g, k, fb2, KHB_COUNTER_MAX, nbins, d_hist, out_keys, d_runs))) return rc;
     KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, ctx->d_mail, (nbins + 9) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     tm.mark();  // 7: count done
     KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -578,6 +658,10 @@ static int group_from_staged_impl(khb_ctx *ctx, int k, int n_genomes, const uint
     if (keep_set) {
         ctx->gs_len += d_g;
         ctx->gs_groups += 1;
+    }
+    if (stats) {
+        stats->passes_genome = np1;
+        stats->passes_group = np2;
     }
     if (stats) {
         stats->fasta_bytes = nbytes;
@@ -667,11 +751,13 @@ int khb_across_groups(khb_ctx *ctx, uint32_t nbins, uint64_t *h_hist, khb_stats 
     PhaseTimer tm(ctx);
     tm.mark();
     u64 one_seg[2] = {0, n};
-    int in_tmp = 0;
-    if ((rc = khb_sort_keys_impl(ctx, ctx->gs_buf, p, one_seg, 1, k, &in_tmp))) return rc;
+    int in_tmp = 0, fb, np;
+    khb_prefix_plan(k, n, &fb, &np);
+    if (!ctx->gs_hashed) { fb = 0; np = (2 * k + 7) / 8; }  // unhashed keys (k = 32 / 64 or appended raw sets): full sort
+    if ((rc = khb_sort_bits_impl(ctx, ctx->gs_buf, p, one_seg, 1, (int)W, fb, np, &in_tmp))) return rc;
     tm.mark();
     u64 *d_hist = ctx->d_mail + 8, *d_runs = ctx->d_mail;
-    if ((rc = khb_count_runs_impl(ctx, in_tmp ? p : ctx->gs_buf, n, k, KHB_COUNTER_MAX, nbins, d_hist, nullptr, nullptr, d_runs))) return rc;
+    if ((rc = khb_resolve_count_impl(ctx, in_tmp ? p : ctx->gs_buf, n, k, fb, KHB_COUNTER_MAX, nbins, d_hist, nullptr, d_runs))) return rc;
     KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, ctx->d_mail, (nbins + 9) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     tm.mark();
     KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -683,7 +769,25 @@ int khb_across_groups(khb_ctx *ctx, uint32_t nbins, uint64_t *h_hist, khb_stats 
         stats->ms_sort2 = tm.ms(0, 1);
         stats->ms_count = tm.ms(1, 2);
         stats->ms_total = tm.ms(0, 2);
+        stats->passes_group = np;
     }
+    return KHB_OK;
+}
+
+int khb_group_sets_hashed(khb_ctx *ctx) { return ctx ? ctx->gs_hashed : 0; }
+
+int khb_group_sets_export(khb_ctx *ctx, void *h_out)
+{
+    KHB_CHECK_CTX(ctx);
+    if (!ctx->gs_len) return KHB_OK;
+    const size_t W = (size_t)khb_key_bytes(ctx->gs_k);
+    void *p;
+    int rc = khb_scratch_get(ctx, SCR_KEYS_B, (ctx->gs_len + 4) * W, &p);
+    if (rc) return rc;
+    KHB_CUDA(ctx, cudaMemcpyAsync(p, ctx->gs_buf, ctx->gs_len * W, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (ctx->gs_hashed && (rc = khb_remix_impl(ctx, p, ctx->gs_len, ctx->gs_k, 1))) return rc;
+    KHB_CUDA(ctx, cudaMemcpyAsync(h_out, p, ctx->gs_len * W, cudaMemcpyDeviceToHost, ctx->stream));
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KHB_OK;
 }
 
@@ -705,12 +809,14 @@ int khb_group_sets_device(khb_ctx *ctx, void **d_keys, uint64_t *n_keys)
     return KHB_OK;
 }
 
-int khb_group_sets_append_device(khb_ctx *ctx, int k, const void *d_keys, uint64_t n_keys, int n_groups)
+int khb_group_sets_append_device(khb_ctx *ctx, int k, const void *d_keys, uint64_t n_keys, int n_groups, int hashed)
 {
     KHB_CHECK_CTX(ctx);
     if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "k=%d outside 1..64", k);
+    if (ctx->gs_k && ctx->gs_len && ctx->gs_hashed != (hashed ? 1 : 0)) return khb_fail(ctx, KHB_ERR_STATE, "mixing hashed and raw group sets");
     int rc = gs_reserve(ctx, k, n_keys);
     if (rc) return rc;
+    ctx->gs_hashed = hashed ? 1 : 0;
     const size_t W = (size_t)khb_key_bytes(k);
     if (n_keys) KHB_CUDA(ctx, cudaMemcpyAsync((char *)ctx->gs_buf + ctx->gs_len * W, d_keys, n_keys * W, cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->gs_len += n_keys;
@@ -722,8 +828,10 @@ int khb_group_sets_append_host(khb_ctx *ctx, int k, const void *h_keys, uint64_t
 {
     KHB_CHECK_CTX(ctx);
     if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "k=%d outside 1..64", k);
+    if (ctx->gs_k && ctx->gs_len && ctx->gs_hashed) return khb_fail(ctx, KHB_ERR_STATE, "mixing hashed and raw group sets");
     int rc = gs_reserve(ctx, k, n_keys);
     if (rc) return rc;
+    ctx->gs_hashed = 0;  // host-provided sets are canonical k-mer values
     const size_t W = (size_t)khb_key_bytes(k);
     if (n_keys) {
         KHB_CUDA(ctx, cudaMemcpyAsync((char *)ctx->gs_buf + ctx->gs_len * W, h_keys, n_keys * W, cudaMemcpyHostToDevice, ctx->stream));
@@ -740,6 +848,7 @@ int khb_group_sets_reset(khb_ctx *ctx)
     ctx->gs_len = 0;
     ctx->gs_groups = 0;
     ctx->gs_k = 0;
+    ctx->gs_hashed = 0;
     return KHB_OK;
 }
 

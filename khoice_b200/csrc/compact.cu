@@ -25,6 +25,10 @@
 #define CP_WARPS (CP_BLOCK / 32)
 #define CP_ITEMS 8
 #define CP_TILE (CP_BLOCK * CP_ITEMS)
+// count_prefix_kernel: smaller CTAs, four per SM (latency-bound phases overlap across CTAs)
+#define CQ_BLOCK 256
+#define CQ_WARPS (CQ_BLOCK / 32)
+#define CQ_TILE (CQ_BLOCK * CP_ITEMS)
 
 __device__ __forceinline__ Key64 shfl_key(const Key64 &k, int src)
 {
@@ -247,6 +251,250 @@ rle_hist_kernel(const Key *__restrict__ in, u64 n, u32 cs, u32 nbins, u64 *__res
     if (tid == 0 && my_runs) atomicAdd(d_runs, my_runs);
 }
 
+// ---- prefix-run resolution (fused path) -------------------------------------------------------------------
+// The fused path sorts hashed keys by a PREFIX only (bits >= pshift, see khb_prefix_plan), which costs
+// 3-4 radix passes instead of ceil(2k/8).  Keys with equal prefix are adjacent ("prefix run") but not
+// ordered among themselves, so equality inside a run is resolved by comparison:
+//   head(i)  = no j < i in the same prefix run with in[j] == in[i]      (backward scan)
+//   count(i) = 1 + #{ j > i in the same prefix run : in[j] == in[i] }    (forward scan, heads only)
+// With a bijective mixer the prefix is uniform, a run holds O(1) distinct values, and both scans touch a
+// handful of L1-resident neighbours.  COUNT = false: emit heads (per-genome set, K4).  COUNT = true:
+// histogram of count(i) over heads (+ emit heads = the group's distinct set, K5/K6).
+// Sentinels never share a prefix with a real key (the plan covers the spare bit above 2k), and every
+// genome segment ends with at least one sentinel, so a scan never leaves its segment.
+template <typename Key, bool COUNT>
+__global__ void __launch_bounds__(CP_BLOCK)
+resolve_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 nbins, u64 *__restrict__ hist,
+               Key *__restrict__ out, u64 *__restrict__ lookback, u32 *__restrict__ ticket, u32 epoch,
+               u64 *__restrict__ d_count)
+{
+    extern __shared__ u32 sh_hist[];  // [nbins+1] when COUNT
+    __shared__ u64 ws[33];
+    __shared__ u32 s_tile;
+    __shared__ u64 s_base;
+    const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    const u64 ntiles = (n + CP_TILE - 1) / CP_TILE;
+    if (COUNT)
+        for (u32 i = tid; i <= nbins; i += CP_BLOCK) sh_hist[i] = 0;
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const u64 tile = s_tile;
+        if (tile >= ntiles) break;
+        const u64 begin = tile * CP_TILE;
+        const u32 wbase = warp * (32 * CP_ITEMS);
+        Key keys[CP_ITEMS];
+        load_tile(in, begin, n, wbase, lane, keys);
+        const u64 chunk0 = begin + wbase;
+        u32 ball[CP_ITEMS];
+        u32 wcount = 0;
+#pragma unroll
+        for (int r = 0; r < CP_ITEMS; r++) {
+            const u64 g = chunk0 + r * 32 + lane;
+            const Key key = keys[r];
+            bool head = g < n && !key_is_sentinel(key);
+            if (head) {
+                u64 j = g;
+                while (j > 0) {
+                    --j;
+                    const Key kj = in[j];
+                    if (!same_prefix(kj, key, pshift)) break;
+                    if (key_eq(kj, key)) { head = false; break; }
+                }
+            }
+            if (COUNT && head) {
+                u32 c = 1;
+                for (u64 j = g + 1; j < n; j++) {
+                    const Key kj = in[j];
+                    if (!same_prefix(kj, key, pshift)) break;
+                    c += key_eq(kj, key) ? 1u : 0u;
+                }
+                c = c > cs ? cs : c;
+                if (c <= nbins) atomicAdd(&sh_hist[c], 1u);
+            }
+            ball[r] = __ballot_sync(0xffffffffu, head);
+            wcount += __popc(ball[r]);
+        }
+        u64 total;
+        const u64 woff = block_excl_sum<u64>(lane == 0 ? (u64)wcount : 0ull, ws, &total);
+        const u64 warp_off = __shfl_sync(0xffffffffu, woff, 0);
+        if (warp == 0) {
+            u64 excl = 0;
+            if (tile == 0) {
+                if (lane == 0) lb_store(lookback, lb_pack(LB_PREFIX, total, epoch));
+            } else {
+                if (lane == 0) lb_store(lookback + tile, lb_pack(LB_AGG, total, epoch));
+                excl = lb_walk_warp(lookback, tile, 0, epoch);
+                if (lane == 0) lb_store(lookback + tile, lb_pack(LB_PREFIX, excl + total, epoch));
+            }
+            if (lane == 0) {
+                s_base = excl;
+                if (tile == ntiles - 1) *d_count = excl + total;
+            }
+        }
+        __syncthreads();
+        if (out != nullptr) {
+            u64 pos = s_base + warp_off;
+#pragma unroll
+            for (int r = 0; r < CP_ITEMS; r++) {
+                if ((ball[r] >> lane) & 1u) out[pos + __popc(ball[r] & lanemask_lt())] = keys[r];
+                pos += __popc(ball[r]);
+            }
+        }
+        __syncthreads();
+    }
+    if (COUNT) {
+        __syncthreads();
+        for (u32 i = tid; i <= nbins; i += CP_BLOCK) {
+            const u32 c = sh_hist[i];
+            if (c) atomicAdd(&hist[i], (u64)c);
+        }
+    }
+}
+
+// K5/K6 on prefix-sorted input, O(1) per key for the common case.  Works on ADJACENT runs of equal keys like
+// rle_hist_kernel (head/tail ballots, in-tile max-scan of head positions, run_head_before for the run that is
+// open at the tile start) and adds, at the tail t of every adjacent run [h, t]:
+//   first  = no key equal to in[t] precedes h inside the prefix run   (one compare unless the run is mixed)
+//   extra  = equal keys after t inside the prefix run                  (zero compares unless the run is mixed)
+// A prefix run is "mixed" when it holds more than one distinct value -- rare, because the prefix of a hashed
+// key is uniform and the plan gives it more slots than there are keys.  Runs that are `first` add
+// hist[min(len + extra, cs)] and emit their key.
+template <typename Key>
+__global__ void __launch_bounds__(CQ_BLOCK, sizeof(Key) == 8 ? 4 : 2)
+count_prefix_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 nbins, u64 *__restrict__ hist,
+                    Key *__restrict__ out_keys, u64 *__restrict__ lookback, u32 *__restrict__ ticket, u32 epoch,
+                    u64 *__restrict__ d_runs)
+{
+    extern __shared__ u32 sh_hist[];  // [nbins+1]
+    __shared__ u64 ws[33];
+    __shared__ u32 s_tile;
+    __shared__ u64 s_base;
+    __shared__ u64 s_head0;
+    __shared__ u32 s_wlast[CQ_WARPS];
+    const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    const u64 ntiles = (n + CQ_TILE - 1) / CQ_TILE;
+    for (u32 i = tid; i <= nbins; i += CQ_BLOCK) sh_hist[i] = 0;
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const u64 tile = s_tile;
+        if (tile >= ntiles) break;
+        const u64 begin = tile * CQ_TILE;
+        const u32 wbase = warp * (32 * CP_ITEMS);
+        Key keys[CP_ITEMS];
+        load_tile(in, begin, n, wbase, lane, keys);
+        const u64 chunk0 = begin + wbase;
+        Key before = sentinel_key<Key>();
+        if (chunk0 > 0 && chunk0 < n) before = in[chunk0 - 1];
+        const u64 after_idx = chunk0 + 32 * CP_ITEMS;
+        Key after = sentinel_key<Key>();
+        if (after_idx < n) after = in[after_idx];
+        if (warp == 0) {
+            Key k0 = shfl_key(keys[0], 0);
+            u64 h0 = begin;
+            if (begin > 0 && begin < n && !key_is_sentinel(k0)) h0 = run_head_before(in, begin, k0, lane);
+            if (lane == 0) s_head0 = h0;
+        }
+        u32 tball[CP_ITEMS], hrun[CP_ITEMS];
+        u32 mixed_next = 0;  // bit r: the key after this tail shares its prefix (mixed run ahead)
+        u32 carry = 0;
+#pragma unroll
+        for (int r = 0; r < CP_ITEMS; r++) {
+            const u64 g = chunk0 + r * 32 + lane;
+            const Key pk = prev_key(keys, r, lane, before);
+            Key dn = shfl_key(keys[r], (int)((lane + 1) & 31));
+            Key nxt = r + 1 < CP_ITEMS ? shfl_key(keys[r + 1 < CP_ITEMS ? r + 1 : r], 0) : after;
+            const Key nk = lane == 31 ? nxt : dn;
+            const bool valid = g < n && !key_is_sentinel(keys[r]);
+            const bool head = valid && (g == 0 || !key_eq(keys[r], pk));
+            const bool last = g + 1 >= n;
+            const bool tail = valid && (last || !key_eq(keys[r], nk));
+            if (tail && !last && !key_is_sentinel(nk) && same_prefix(nk, keys[r], pshift)) mixed_next |= 1u << r;
+            tball[r] = __ballot_sync(0xffffffffu, tail);
+            const u32 loc = wbase + r * 32 + lane + 1;
+            u32 h = warp_incl_max<u32>(head ? loc : 0u);
+            h = h > carry ? h : carry;
+            hrun[r] = h;
+            carry = __shfl_sync(0xffffffffu, h, 31);
+        }
+        if (lane == 0) s_wlast[warp] = carry;
+        __syncthreads();  // s_wlast, s_head0
+        u32 wprefix = 0;
+        for (u32 w = 0; w < warp; w++) wprefix = s_wlast[w] > wprefix ? s_wlast[w] : wprefix;
+        const u64 head0 = s_head0;
+        // per tail: adjacent length, then the (rare) mixed-run checks; `emit` = this run is the first of its value
+        u32 eball[CP_ITEMS];
+        u32 wcount = 0;
+#pragma unroll
+        for (int r = 0; r < CP_ITEMS; r++) {
+            const u64 g = chunk0 + r * 32 + lane;
+            bool emit = false;
+            if ((tball[r] >> lane) & 1u) {
+                const Key key = keys[r];
+                const u32 h = hrun[r] ? hrun[r] : wprefix;
+                const u64 hg = h ? begin + (h - 1) : head0;
+                u64 len = g - hg + 1;
+                emit = true;
+                u64 j = hg;
+                while (j > 0) {  // an earlier occurrence inside the prefix run?
+                    --j;
+                    const Key kj = in[j];
+                    if (!same_prefix(kj, key, pshift)) break;
+                    if (key_eq(kj, key)) { emit = false; break; }
+                }
+                if (emit) {
+                    if ((mixed_next >> r) & 1u) {
+                        for (u64 q = g + 1; q < n; q++) {  // later occurrences inside the prefix run
+                            const Key kq = in[q];
+                            if (!same_prefix(kq, key, pshift)) break;
+                            len += key_eq(kq, key) ? 1u : 0u;
+                        }
+                    }
+                    const u32 c = len > (u64)cs ? cs : (u32)len;
+                    if (c <= nbins) atomicAdd(&sh_hist[c], 1u);
+                }
+            }
+            eball[r] = __ballot_sync(0xffffffffu, emit);
+            wcount += __popc(eball[r]);
+        }
+        u64 total;
+        const u64 woff = block_excl_sum<u64>(lane == 0 ? (u64)wcount : 0ull, ws, &total);
+        const u64 warp_off = __shfl_sync(0xffffffffu, woff, 0);
+        if (warp == 0) {
+            u64 excl = 0;
+            if (out_keys != nullptr) {
+                if (tile == 0) {
+                    if (lane == 0) lb_store(lookback, lb_pack(LB_PREFIX, total, epoch));
+                } else {
+                    if (lane == 0) lb_store(lookback + tile, lb_pack(LB_AGG, total, epoch));
+                    excl = lb_walk_warp(lookback, tile, 0, epoch);
+                    if (lane == 0) lb_store(lookback + tile, lb_pack(LB_PREFIX, excl + total, epoch));
+                }
+            }
+            if (lane == 0) {
+                s_base = excl;
+                if (total) atomicAdd(d_runs, total);
+            }
+        }
+        __syncthreads();
+        if (out_keys != nullptr) {
+            u64 pos = s_base + warp_off;
+#pragma unroll
+            for (int r = 0; r < CP_ITEMS; r++) {
+                if ((eball[r] >> lane) & 1u) out_keys[pos + __popc(eball[r] & lanemask_lt())] = keys[r];
+                pos += __popc(eball[r]);
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    for (u32 i = tid; i <= nbins; i += CQ_BLOCK) {
+        const u32 c = sh_hist[i];
+        if (c) atomicAdd(&hist[i], (u64)c);
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------------------
 static int compact_scratch(khb_ctx *ctx, u64 ntiles, u64 **d_lb, u32 **d_ticket)
 {
@@ -304,5 +552,55 @@ int khb_count_runs_impl(khb_ctx *ctx, const void *d_sorted, size_t n, int k, u32
         rle_hist_kernel<Key128><<<(unsigned)grid, CP_BLOCK, shm, ctx->stream>>>((const Key128 *)d_sorted, n, cs, nbins, d_hist, (Key128 *)d_out_keys, d_out_counts, d_lb, d_ticket, 1u, d_runs);
     KHB_LAUNCH_CHECK(ctx);
     khb_prof_end(ctx, KHB_K_RLE, (u64)n * (k <= 32 ? 8 : 16));  // input read; emitted keys are data dependent
+    return KHB_OK;
+}
+
+// K4 on prefix-sorted input: d_count <- number of heads; d_out <- heads in input order.
+int khb_resolve_unique_impl(khb_ctx *ctx, const void *d_sorted, size_t n, int k, int pshift, void *d_out, u64 *d_count)
+{
+    if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_resolve_unique: k=%d outside 1..64", k);
+    KHB_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(u64), ctx->stream));
+    if (n == 0) return KHB_OK;
+    const u64 ntiles = div_up(n, CP_TILE);
+    u64 *d_lb;
+    u32 *d_ticket;
+    int rc = compact_scratch(ctx, ntiles, &d_lb, &d_ticket);
+    if (rc) return rc;
+    u64 grid = (u64)ctx->num_sms * 3;
+    if (grid > ntiles) grid = ntiles;
+    khb_prof_begin(ctx, KHB_K_UNIQUE);
+    if (k <= 32)
+        resolve_kernel<Key64, false><<<(unsigned)grid, CP_BLOCK, 0, ctx->stream>>>((const Key64 *)d_sorted, n, pshift, 0, 0, nullptr, (Key64 *)d_out, d_lb, d_ticket, 1u, d_count);
+    else
+        resolve_kernel<Key128, false><<<(unsigned)grid, CP_BLOCK, 0, ctx->stream>>>((const Key128 *)d_sorted, n, pshift, 0, 0, nullptr, (Key128 *)d_out, d_lb, d_ticket, 1u, d_count);
+    KHB_LAUNCH_CHECK(ctx);
+    khb_prof_end(ctx, KHB_K_UNIQUE, 2 * (u64)n * (k <= 32 ? 8 : 16));
+    return KHB_OK;
+}
+
+// K5/K6 on prefix-sorted input: histogram of multiplicities (+ optional distinct keys).
+int khb_resolve_count_impl(khb_ctx *ctx, const void *d_sorted, size_t n, int k, int pshift, u32 cs, u32 nbins, u64 *d_hist,
+                           void *d_out_keys, u64 *d_runs)
+{
+    if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_resolve_count: k=%d outside 1..64", k);
+    if (nbins < 1 || nbins > 8192) return khb_fail(ctx, KHB_ERR_ARG, "khb_resolve_count: nbins=%u outside 1..8192", nbins);
+    KHB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, ((size_t)nbins + 1) * sizeof(u64), ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(d_runs, 0, sizeof(u64), ctx->stream));
+    if (n == 0) return KHB_OK;
+    const u64 ntiles = div_up(n, CQ_TILE);
+    u64 *d_lb;
+    u32 *d_ticket;
+    int rc = compact_scratch(ctx, ntiles, &d_lb, &d_ticket);
+    if (rc) return rc;
+    u64 grid = (u64)ctx->num_sms * 4;
+    if (grid > ntiles) grid = ntiles;
+    const size_t shm = ((size_t)nbins + 1) * sizeof(u32);
+    khb_prof_begin(ctx, KHB_K_RLE);
+    if (k <= 32)
+        count_prefix_kernel<Key64><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const Key64 *)d_sorted, n, pshift, cs, nbins, d_hist, (Key64 *)d_out_keys, d_lb, d_ticket, 1u, d_runs);
+    else
+        count_prefix_kernel<Key128><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const Key128 *)d_sorted, n, pshift, cs, nbins, d_hist, (Key128 *)d_out_keys, d_lb, d_ticket, 1u, d_runs);
+    KHB_LAUNCH_CHECK(ctx);
+    khb_prof_end(ctx, KHB_K_RLE, (u64)n * (k <= 32 ? 8 : 16));
     return KHB_OK;
 }

@@ -23,10 +23,124 @@ __host__ __device__ __forceinline__ bool key_eq(const Key64 &a, const Key64 &b) 
 __host__ __device__ __forceinline__ bool key_eq(const Key128 &a, const Key128 &b) { return a.lo == b.lo && a.hi == b.hi; }
 __host__ __device__ __forceinline__ bool key_is_sentinel(const Key64 &a) { return a.v == ~0ull; }
 __host__ __device__ __forceinline__ bool key_is_sentinel(const Key128 &a) { return (a.lo & a.hi) == ~0ull; }
-__host__ __device__ __forceinline__ u32 key_digit(const Key64 &a, int pass) { return (u32)(a.v >> (8 * pass)) & 0xffu; }
-__host__ __device__ __forceinline__ u32 key_digit(const Key128 &a, int pass)
+// 8-bit digit starting at bit `shift` (any alignment; bits past the top read as zero)
+__host__ __device__ __forceinline__ u32 key_digit(const Key64 &a, int shift) { return (u32)(a.v >> shift) & 0xffu; }
+__host__ __device__ __forceinline__ u32 key_digit(const Key128 &a, int shift)
 {
-    return (u32)((pass < 8 ? a.lo >> (8 * pass) : a.hi >> (8 * (pass - 8)))) & 0xffu;
+    if (shift >= 64) return (u32)(a.hi >> (shift - 64)) & 0xffu;
+    if (shift <= 56) return (u32)(a.lo >> shift) & 0xffu;
+    return (u32)((a.lo >> shift) | (a.hi << (64 - shift))) & 0xffu;
+}
+// bits [shift, top) of a key: two keys are in the same prefix run iff these are equal (shift = 0: the whole key)
+__host__ __device__ __forceinline__ bool same_prefix(const Key64 &a, const Key64 &b, int shift) { return ((a.v ^ b.v) >> shift) == 0; }
+__host__ __device__ __forceinline__ bool same_prefix(const Key128 &a, const Key128 &b, int shift)
+{
+    const u64 xl = a.lo ^ b.lo, xh = a.hi ^ b.hi;
+    if (shift >= 64) return (xh >> (shift - 64)) == 0;
+    return xh == 0 && (xl >> shift) == 0;
+}
+
+// ---- bijective k-mer mixer -------------------------------------------------------------------
+// The fused path sorts only a PREFIX (top 8*P bits) of each key and resolves the rest by comparison
+// (compact.cu: resolve kernels).  For that the top bits must be uniformly distributed, so K2 can emit
+// h(c) instead of the canonical value c, where h is a bijection of [0, 4^k):
+//     y = ~c;  y *= C1;  y ^= y >> k;  y *= C2;  y ^= y >> k;  y *= C1;  h = ~y      (all mod 4^k)
+// Odd multiplications and the half-width xor-shift are invertible (the xor-shift is its own inverse), so
+// equality, set sizes and multiplicities are unchanged and kmer_unmix recovers c exactly.  The two
+// complements make h(all ones) = all ones, which keeps the 64/128-bit sentinel a sentinel for k = 32 / 64.
+#define KHB_MIX_C1 0x9E3779B97F4A7C15ull
+#define KHB_MIX_C2 0xBF58476D1CE4E5B9ull
+
+__host__ __device__ __forceinline__ u64 mix_mask64(int k) { return k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull); }
+__host__ __device__ __forceinline__ u64 odd_inverse64(u64 c)
+{
+    u64 x = c;  // Newton: x <- x * (2 - c x), doubles the number of correct low bits
+    for (int i = 0; i < 6; i++) x *= 2ull - c * x;
+    return x;
+}
+__host__ __device__ __forceinline__ u64 kmer_mix64(u64 c, int k)
+{
+    const u64 M = mix_mask64(k);
+    u64 y = ~c & M;
+    y = (y * KHB_MIX_C1) & M;
+    y ^= y >> k;
+    y = (y * KHB_MIX_C2) & M;
+    y ^= y >> k;
+    y = (y * KHB_MIX_C1) & M;
+    return ~y & M;
+}
+__host__ __device__ __forceinline__ u64 kmer_unmix64(u64 h, int k)
+{
+    const u64 M = mix_mask64(k);
+    const u64 i1 = odd_inverse64(KHB_MIX_C1), i2 = odd_inverse64(KHB_MIX_C2);
+    u64 y = ~h & M;
+    y = (y * i1) & M;
+    y ^= y >> k;
+    y = (y * i2) & M;
+    y ^= y >> k;
+    y = (y * i1) & M;
+    return ~y & M;
+}
+
+// 128-bit variant for 33 <= k <= 64: (hi:lo) arithmetic mod 4^k, same recipe.
+#ifdef __CUDA_ARCH__
+#define KHB_MULHI64(a, b) __umul64hi((a), (b))
+#else
+#define KHB_MULHI64(a, b) ((u64)(((unsigned __int128)(a) * (unsigned __int128)(b)) >> 64))
+#endif
+__host__ __device__ __forceinline__ void mul128(u64 &hi, u64 &lo, u64 ch, u64 cl)
+{
+    const u64 nlo = lo * cl;
+    const u64 nhi = KHB_MULHI64(lo, cl) + lo * ch + hi * cl;
+    hi = nhi;
+    lo = nlo;
+}
+__host__ __device__ __forceinline__ void xorshift128(u64 &hi, u64 &lo, int k)
+{
+    // (hi:lo) ^= (hi:lo) >> k with 33 <= k <= 64 and hi < 2^(2k-64): only lo changes
+    lo ^= k >= 64 ? hi : ((lo >> k) | (hi << (64 - k)));
+}
+__host__ __device__ __forceinline__ void mix_steps128(u64 &hi, u64 &lo, int k, u64 a_hi, u64 a_lo, u64 b_hi, u64 b_lo)
+{
+    const u64 Mh = k >= 64 ? ~0ull : ((1ull << (2 * k - 64)) - 1ull);
+    hi = ~hi & Mh;
+    lo = ~lo;
+    mul128(hi, lo, a_hi, a_lo);
+    hi &= Mh;
+    xorshift128(hi, lo, k);
+    mul128(hi, lo, b_hi, b_lo);
+    hi &= Mh;
+    xorshift128(hi, lo, k);
+    mul128(hi, lo, a_hi, a_lo);
+    hi &= Mh;
+    hi = ~hi & Mh;
+    lo = ~lo;
+}
+__host__ __device__ __forceinline__ void kmer_mix128(u64 &hi, u64 &lo, int k)
+{
+    mix_steps128(hi, lo, k, 0ull, KHB_MIX_C1, 0ull, KHB_MIX_C2);
+}
+__host__ __device__ __forceinline__ void odd_inverse128(u64 c, u64 &ih, u64 &il)
+{
+    // inverse of the 64-bit odd constant c modulo 2^128, by Newton iteration in 128-bit arithmetic
+    u64 xh = 0, xl = c;
+    for (int i = 0; i < 7; i++) {
+        // t = 2 - c * x
+        u64 th = xh, tl = xl;
+        mul128(th, tl, 0ull, c);
+        const u64 nl = 2ull - tl;
+        const u64 nh = ~th + (tl <= 2ull ? 1ull : 0ull);  // (0:2) - (th:tl)
+        mul128(xh, xl, nh, nl);
+    }
+    ih = xh;
+    il = xl;
+}
+__host__ __device__ __forceinline__ void kmer_unmix128(u64 &hi, u64 &lo, int k)
+{
+    u64 a_h, a_l, b_h, b_l;
+    odd_inverse128(KHB_MIX_C1, a_h, a_l);
+    odd_inverse128(KHB_MIX_C2, b_h, b_l);
+    mix_steps128(hi, lo, k, a_h, a_l, b_h, b_l);
 }
 
 // ---- context ------------------------------------------------------------------------------
@@ -54,6 +168,7 @@ struct khb_ctx {
     size_t gs_len;      // keys stored
     int gs_k;           // k the stored sets were built with (0 = none)
     int gs_groups;      // number of groups stored
+    int gs_hashed;      // 1: stored keys are kmer_mix(canonical), 0: canonical values
     // staging (fused host entry points)
     uint8_t *stage_dev;
     size_t stage_dev_cap;

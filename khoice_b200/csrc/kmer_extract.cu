@@ -22,7 +22,7 @@ __device__ __forceinline__ u64 swap_pairs(u64 r)
 
 // k <= 32.  One thread produces the two windows starting at i and i+1 (i even) -> one 16-byte store.
 __global__ void __launch_bounds__(256)
-extract64_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, size_t n_sym, int k,
+extract64_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, size_t n_sym, int k, int hashed,
                  ulonglong2 *__restrict__ out)
 {
     const size_t npairs = (n_sym + 1) >> 1;
@@ -44,7 +44,8 @@ extract64_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, s
             // note: ~x has the complemented window in its top 2k bits; brev moves them to the low 2k bits
             // (reversed), the shift pair clears the bits that came from below the window.
             const bool ok = (((vv << ot) >> (64 - k)) == ones_k) && (i + t < n_sym);
-            const u64 can = fwd < rc ? fwd : rc;
+            u64 can = fwd < rc ? fwd : rc;
+            if (hashed) can = kmer_mix64(can, k);
             res[t] = ok ? can : ~0ull;
         }
         if (i + 1 < n_sym) {
@@ -57,7 +58,7 @@ extract64_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, s
 
 // 33 <= k <= 64.  One thread per window -> one 16-byte store (lo, hi).
 __global__ void __launch_bounds__(256)
-extract128_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, size_t n_sym, int k,
+extract128_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, size_t n_sym, int k, int hashed,
                   ulonglong2 *__restrict__ out)
 {
     const u64 ones_k = k == 64 ? ~0ull : ((1ull << k) - 1ull);
@@ -91,14 +92,49 @@ extract128_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, 
         const u64 vwin = o ? ((va << o) | (vb >> (64 - o))) : va;
         const bool ok = ((vwin >> (64 - k)) == ones_k);
         const bool f_lt = fh < rh || (fh == rh && fl < rl);
+        u64 cl = f_lt ? fl : rl, ch = f_lt ? fh : rh;
+        if (hashed) kmer_mix128(ch, cl, k);
         ulonglong2 r;
-        r.x = ok ? (f_lt ? fl : rl) : ~0ull;   // lo
-        r.y = ok ? (f_lt ? fh : rh) : ~0ull;   // hi
+        r.x = ok ? cl : ~0ull;   // lo
+        r.y = ok ? ch : ~0ull;   // hi
         out[i] = r;
     }
 }
 
-int khb_extract_kmers_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, size_t n_sym, int k, void *d_keys)
+// keys[i] <- h(keys[i]) or h^-1(keys[i]) in place (sentinels stay sentinels)
+__global__ void __launch_bounds__(256) remix64_kernel(u64 *__restrict__ keys, size_t n, int k, int inverse)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const u64 v = keys[i];
+        if (v != ~0ull) keys[i] = inverse ? kmer_unmix64(v, k) : kmer_mix64(v, k);
+    }
+}
+__global__ void __launch_bounds__(256) remix128_kernel(ulonglong2 *__restrict__ keys, size_t n, int k, int inverse)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        ulonglong2 v = keys[i];
+        if ((v.x & v.y) != ~0ull) {
+            u64 hi = v.y, lo = v.x;
+            if (inverse) kmer_unmix128(hi, lo, k); else kmer_mix128(hi, lo, k);
+            keys[i] = make_ulonglong2(lo, hi);
+        }
+    }
+}
+
+int khb_remix_impl(khb_ctx *ctx, void *d_keys, size_t n, int k, int inverse)
+{
+    if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_remix: k=%d outside 1..64", k);
+    if (n == 0) return KHB_OK;
+    size_t blocks = div_up(n, 256);
+    const size_t cap = (size_t)ctx->num_sms * 32;
+    if (blocks > cap) blocks = cap;
+    if (k <= 32) remix64_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>((u64 *)d_keys, n, k, inverse);
+    else remix128_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>((ulonglong2 *)d_keys, n, k, inverse);
+    KHB_LAUNCH_CHECK(ctx);
+    return KHB_OK;
+}
+
+int khb_extract_kmers_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, size_t n_sym, int k, int hashed, void *d_keys)
 {
     if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_extract_kmers: k=%d outside 1..64", k);
     if (n_sym == 0) return KHB_OK;
@@ -108,9 +144,9 @@ int khb_extract_kmers_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid,
     if (blocks > cap) blocks = cap;
     khb_prof_begin(ctx, KHB_K_EXTRACT);
     if (k <= 32)
-        extract64_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_codes, d_valid, n_sym, k, (ulonglong2 *)d_keys);
+        extract64_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_codes, d_valid, n_sym, k, hashed, (ulonglong2 *)d_keys);
     else
-        extract128_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_codes, d_valid, n_sym, k, (ulonglong2 *)d_keys);
+        extract128_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_codes, d_valid, n_sym, k, hashed, (ulonglong2 *)d_keys);
     KHB_LAUNCH_CHECK(ctx);
     khb_prof_end(ctx, KHB_K_EXTRACT, (u64)n_sym / 4 + n_sym / 8 + (u64)n_sym * (k <= 32 ? 8 : 16));
     return KHB_OK;

@@ -57,7 +57,7 @@ __device__ __forceinline__ int find_segment(const u64 *__restrict__ seg_tile, in
 template <typename Key>
 __global__ void __launch_bounds__(RS_BLOCK)
 radix_hist_kernel(const Key *__restrict__ in, const u64 *__restrict__ seg_off, const u64 *__restrict__ seg_tile,
-                  int nseg, u64 ntiles, int npass, u32 *__restrict__ hist /* [nseg][npass][256] */, u32 TILE)
+                  int nseg, u64 ntiles, int npass, int first_bit, u32 *__restrict__ hist /* [nseg][npass][256] */, u32 TILE)
 {
     extern __shared__ u32 sh[];  // [npass][256]
     const u32 tid = threadIdx.x;
@@ -88,7 +88,7 @@ radix_hist_kernel(const Key *__restrict__ in, const u64 *__restrict__ seg_off, c
 #pragma unroll 4
         for (u32 i = tid; i < n; i += RS_BLOCK) {
             const Key key = in[begin + i];
-            for (int p = 0; p < npass; p++) atomicAdd(&sh[p * 256 + key_digit(key, p)], 1u);
+            for (int p = 0; p < npass; p++) atomicAdd(&sh[p * 256 + key_digit(key, first_bit + 8 * p)], 1u);
         }
     }
     __syncthreads();
@@ -135,7 +135,7 @@ __device__ __forceinline__ u32 match_digit(u32 d)
 template <typename Key, int BLOCK, int ITEMS, int MINB, int MATCH>
 __global__ void __launch_bounds__(BLOCK, MINB)
 onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__restrict__ seg_off,
-                const u64 *__restrict__ seg_tile, int nseg, int pass, int npass,
+                const u64 *__restrict__ seg_tile, int nseg, int pass_row, int shift, int npass,
                 const u32 *__restrict__ bin_base /* [nseg][npass][256], exclusive */, u64 *__restrict__ lookback,
                 u32 *__restrict__ ticket, u32 epoch)
 {
@@ -194,7 +194,7 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
         const u32 lbit = 1u << lane;
 #pragma unroll
         for (int r = 0; r < ITEMS; r++) {
-            const u32 d = key_digit(keys[r], pass);
+            const u32 d = key_digit(keys[r], shift);
             atomicOr(&mymm[d], lbit);
             __syncwarp();
             const u32 peers = mymm[d];
@@ -211,10 +211,10 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
     } else {
         u32 peers[ITEMS];
 #pragma unroll
-        for (int r = 0; r < ITEMS; r++) peers[r] = match_digit<MATCH>(key_digit(keys[r], pass));
+        for (int r = 0; r < ITEMS; r++) peers[r] = match_digit<MATCH>(key_digit(keys[r], shift));
 #pragma unroll
         for (int r = 0; r < ITEMS; r++) {
-            const u32 d = key_digit(keys[r], pass);
+            const u32 d = key_digit(keys[r], shift);
             const u32 c = mycnt[d];
             __syncwarp();
             const u32 below = __popc(peers[r] & lanemask_lt());
@@ -254,7 +254,7 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
     // reorder through shared memory
 #pragma unroll
     for (int r = 0; r < ITEMS; r++) {
-        const u32 d = key_digit(keys[r], pass);
+        const u32 d = key_digit(keys[r], shift);
         sorted[wcnt[warp * 256 + d] + ((rank2[r >> 1] >> (16 * (r & 1))) & 0xffffu)] = keys[r];
     }
     // finish the look-back (256 digit threads)
@@ -285,7 +285,7 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
             }
             lb_store(lbcol + rel * 256, lb_pack(LB_PREFIX, (u64)excl + count, epoch));
         }
-        glob_off[tid] = bin_base[((size_t)seg * npass + pass) * 256 + tid] + excl - dstart;
+        glob_off[tid] = bin_base[((size_t)seg * npass + pass_row) * 256 + tid] + excl - dstart;
     }
     __syncthreads();
     // coalesced store: position j of the sorted tile goes to segment offset glob_off[digit] + j
@@ -293,14 +293,14 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
 #pragma unroll 4
     for (u32 j = tid; j < n; j += BLOCK) {
         const Key key = sorted[j];
-        dst[glob_off[key_digit(key, pass)] + j] = key;
+        dst[glob_off[key_digit(key, shift)] + j] = key;
     }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
 template <typename Key, int BLOCK, int ITEMS, int MINB, int MATCH>
-static int launch_passes(khb_ctx *ctx, Key *src, Key *dst, const u64 *d_off, const u64 *d_tile, int nseg, int npass, u64 ntiles,
-                         u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket)
+static int launch_passes(khb_ctx *ctx, Key *src, Key *dst, const u64 *d_off, const u64 *d_tile, int nseg, int npass, int first_bit,
+                         u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket)
 {
     constexpr int TILE = BLOCK * ITEMS;
     constexpr int NW = BLOCK / 32;
@@ -314,7 +314,7 @@ static int launch_passes(khb_ctx *ctx, Key *src, Key *dst, const u64 *d_off, con
     for (int pass = 0; pass < npass; pass++) {
         khb_prof_begin(ctx, KHB_K_ONESWEEP);
         onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH><<<(unsigned)ntiles, BLOCK, shm, ctx->stream>>>(
-            src, dst, d_off, d_tile, nseg, pass, npass, d_hist, d_lb, d_ticket + pass, (u32)(pass + 1));
+            src, dst, d_off, d_tile, nseg, pass, first_bit + 8 * pass, npass, d_hist, d_lb, d_ticket + pass, (u32)(pass + 1));
         KHB_LAUNCH_CHECK(ctx);
         khb_prof_end(ctx, KHB_K_ONESWEEP, 2 * n_keys * sizeof(Key));  // read + write every key once
         Key *t = src; src = dst; dst = t;
@@ -351,13 +351,13 @@ static u32 variant_tile(int v, size_t W)
 
 template <typename Key>
 static int dispatch_passes(khb_ctx *ctx, int v, Key *src, Key *dst, const u64 *d_off, const u64 *d_tile, int nseg, int npass,
-                           u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket);
+                           int first_bit, u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket);
 
 template <>
 int dispatch_passes<Key64>(khb_ctx *ctx, int v, Key64 *src, Key64 *dst, const u64 *d_off, const u64 *d_tile, int nseg, int npass,
-                           u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket)
+                           int first_bit, u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket)
 {
-#define GO(B, I, M, MT) return launch_passes<Key64, B, I, M, MT>(ctx, src, dst, d_off, d_tile, nseg, npass, ntiles, n_keys, d_hist, d_lb, d_ticket)
+#define GO(B, I, M, MT) return launch_passes<Key64, B, I, M, MT>(ctx, src, dst, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket)
     switch (v) {
     case 0: GO(512, 12, 2, 0);
     case 2: GO(512, 8, 3, 1);
@@ -373,18 +373,17 @@ int dispatch_passes<Key64>(khb_ctx *ctx, int v, Key64 *src, Key64 *dst, const u6
 
 template <>
 int dispatch_passes<Key128>(khb_ctx *ctx, int v, Key128 *src, Key128 *dst, const u64 *d_off, const u64 *d_tile, int nseg, int npass,
-                            u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket)
+                            int first_bit, u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket)
 {
-    if (v == 2) return launch_passes<Key128, 256, 8, 3, 1>(ctx, src, dst, d_off, d_tile, nseg, npass, ntiles, n_keys, d_hist, d_lb, d_ticket);
-    return launch_passes<Key128, 512, 6, 2, 1>(ctx, src, dst, d_off, d_tile, nseg, npass, ntiles, n_keys, d_hist, d_lb, d_ticket);
+    if (v == 2) return launch_passes<Key128, 256, 8, 3, 1>(ctx, src, dst, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket);
+    return launch_passes<Key128, 512, 6, 2, 1>(ctx, src, dst, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket);
 }
 
 template <typename Key>
-static int sort_impl(khb_ctx *ctx, Key *d_keys, Key *d_tmp, const u64 *h_seg_off, int nseg, int k, int *result_in_tmp)
+static int sort_impl(khb_ctx *ctx, Key *d_keys, Key *d_tmp, const u64 *h_seg_off, int nseg, int first_bit, int npass, int *result_in_tmp)
 {
     const int v = sort_variant();
     const u32 TILE = variant_tile(v, sizeof(Key));
-    const int npass = (2 * k + 7) / 8;
     *result_in_tmp = 0;
     if (nseg <= 0) return KHB_OK;
     // tile table
@@ -432,22 +431,35 @@ static int sort_impl(khb_ctx *ctx, Key *d_keys, Key *d_tmp, const u64 *h_seg_off
         if (grid > ntiles) grid = ntiles;
         const size_t shm = (size_t)npass * 256 * sizeof(u32);
         khb_prof_begin(ctx, KHB_K_RADIX_HIST);
-        radix_hist_kernel<Key><<<(unsigned)grid, RS_BLOCK, shm, ctx->stream>>>(d_keys, d_off, d_tile, nseg, ntiles, npass, d_hist, TILE);
+        radix_hist_kernel<Key><<<(unsigned)grid, RS_BLOCK, shm, ctx->stream>>>(d_keys, d_off, d_tile, nseg, ntiles, npass, first_bit, d_hist, TILE);
         KHB_LAUNCH_CHECK(ctx);
         const int nhist = nseg * npass;
         radix_scan_kernel<<<(unsigned)div_up(nhist, 8), 256, 0, ctx->stream>>>(d_hist, nhist);
         KHB_LAUNCH_CHECK(ctx);
         khb_prof_end(ctx, KHB_K_RADIX_HIST, n_keys * sizeof(Key));
     }
-    rc = dispatch_passes<Key>(ctx, v, d_keys, d_tmp, d_off, d_tile, nseg, npass, ntiles, n_keys, d_hist, d_lb, d_ticket);
+    rc = dispatch_passes<Key>(ctx, v, d_keys, d_tmp, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket);
     if (rc) return rc;
     *result_in_tmp = (npass & 1);
     return KHB_OK;
 }
 
+// Sort every segment by the `npass` 8-bit digits starting at bit `first_bit` (stable LSD).
+int khb_sort_bits_impl(khb_ctx *ctx, void *d_keys, void *d_tmp, const u64 *h_seg_off, int nseg, int key_bytes, int first_bit, int npass,
+                       int *result_in_tmp)
+{
+    if (key_bytes != 8 && key_bytes != 16) return khb_fail(ctx, KHB_ERR_ARG, "sort: key_bytes=%d", key_bytes);
+    if (npass < 0 || npass > 16 || first_bit < 0 || first_bit + 8 * npass > 8 * key_bytes + 7)
+        return khb_fail(ctx, KHB_ERR_ARG, "sort: bad digit range first_bit=%d npass=%d", first_bit, npass);
+    *result_in_tmp = 0;
+    if (npass == 0) return KHB_OK;
+    return key_bytes == 8 ? sort_impl<Key64>(ctx, (Key64 *)d_keys, (Key64 *)d_tmp, h_seg_off, nseg, first_bit, npass, result_in_tmp)
+                          : sort_impl<Key128>(ctx, (Key128 *)d_keys, (Key128 *)d_tmp, h_seg_off, nseg, first_bit, npass, result_in_tmp);
+}
+
+// Full sort of k-mer words: all ceil(2k/8) digits.
 int khb_sort_keys_impl(khb_ctx *ctx, void *d_keys, void *d_tmp, const u64 *h_seg_off, int nseg, int k, int *result_in_tmp)
 {
     if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_sort_keys: k=%d outside 1..64", k);
-    return k <= 32 ? sort_impl<Key64>(ctx, (Key64 *)d_keys, (Key64 *)d_tmp, h_seg_off, nseg, k, result_in_tmp)
-                   : sort_impl<Key128>(ctx, (Key128 *)d_keys, (Key128 *)d_tmp, h_seg_off, nseg, k, result_in_tmp);
+    return khb_sort_bits_impl(ctx, d_keys, d_tmp, h_seg_off, nseg, k <= 32 ? 8 : 16, 0, (2 * k + 7) / 8, result_in_tmp);
 }

@@ -48,6 +48,7 @@ class CudaAdapter:
     def export_partitions(self, k: int, world: int) -> Tuple[torch.Tensor, List[int]]:
         """Retained group sets, grouped by destination rank.  Returns (int64 tensor of words, words per rank)."""
         w = key_words(k)
+        self._hashed = self.eng.group_sets_hashed
         ptr, n = self.eng.group_sets_device()
         send = torch.empty(max(n, 1) * w, dtype=torch.int64, device=self.device)
         off = np.zeros(world + 1, dtype=np.uint64)
@@ -60,7 +61,8 @@ class CudaAdapter:
         """Replace the retained sets by the received keys of this rank's hash range."""
         self.eng.group_sets_reset()
         torch.cuda.synchronize(self.device)
-        self.eng.group_sets_append_device(recv.data_ptr() if recv.numel() else 0, recv.numel() // key_words(k), k, n_groups)
+        self.eng.group_sets_append_device(recv.data_ptr() if recv.numel() else 0, recv.numel() // key_words(k), k, n_groups,
+                                          hashed=getattr(self, "_hashed", False))
         self.eng.sync()
 
     def across(self, nbins: int):

@@ -39,7 +39,8 @@ class Stats(C.Structure):
     _fields_ = [("fasta_bytes", C.c_uint64), ("bases", C.c_uint64), ("windows", C.c_uint64),
                 ("genome_distinct", C.c_uint64), ("distinct", C.c_uint64), ("ms_total", C.c_float),
                 ("ms_h2d", C.c_float), ("ms_pack", C.c_float), ("ms_extract", C.c_float), ("ms_sort1", C.c_float),
-                ("ms_unique", C.c_float), ("ms_sort2", C.c_float), ("ms_count", C.c_float)]
+                ("ms_unique", C.c_float), ("ms_sort2", C.c_float), ("ms_count", C.c_float),
+                ("passes_genome", C.c_int), ("passes_group", C.c_int)]
 
     def as_dict(self) -> dict:
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -69,6 +70,12 @@ _SIGNATURES = [
     ("khb_stage_fasta", C.c_int, [_P, C.c_int, _P, _P, _P, C.c_size_t, _P]),
     ("khb_pack_fasta", C.c_int, [_P, _P, C.c_size_t, _P, _P, C.c_size_t, _P, _P]),
     ("khb_extract_kmers", C.c_int, [_P, _P, _P, C.c_size_t, C.c_int, _P]),
+    ("khb_extract_kmers_hashed", C.c_int, [_P, _P, _P, C.c_size_t, C.c_int, _P]),
+    ("khb_remix_keys", C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_int]),
+    ("khb_prefix_plan", C.c_int, [C.c_int, C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("khb_sort_key_bits", C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    ("khb_resolve_unique", C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_int, _P, C.POINTER(C.c_uint64)]),
+    ("khb_resolve_count", C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_int, C.c_uint32, C.c_uint32, _P, _P, C.POINTER(C.c_uint64)]),
     ("khb_sort_keys", C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     ("khb_unique", C.c_int, [_P, _P, C.c_size_t, C.c_int, _P, C.POINTER(C.c_uint64)]),
     ("khb_count_runs", C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_uint32, C.c_uint32, _P, _P, _P, C.POINTER(C.c_uint64)]),
@@ -77,7 +84,9 @@ _SIGNATURES = [
     ("khb_across_groups", C.c_int, [_P, C.c_uint32, _P, C.POINTER(Stats)]),
     ("khb_group_sets_info", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
     ("khb_group_sets_device", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
-    ("khb_group_sets_append_device", C.c_int, [_P, C.c_int, _P, C.c_uint64, C.c_int]),
+    ("khb_group_sets_append_device", C.c_int, [_P, C.c_int, _P, C.c_uint64, C.c_int, C.c_int]),
+    ("khb_group_sets_hashed", C.c_int, [_P]),
+    ("khb_group_sets_export", C.c_int, [_P, _P]),
     ("khb_group_sets_append_host", C.c_int, [_P, C.c_int, _P, C.c_uint64, C.c_int]),
     ("khb_group_sets_reset", C.c_int, [_P]),
     ("khb_partition_by_hash", C.c_int, [_P, _P, C.c_uint64, C.c_int, C.c_int, _P, _P]),
@@ -269,13 +278,54 @@ class Engine:
         return {"codes": codes, "valid": valid, "n_symbols": int(cnt[0]), "n_breaks": int(cnt[1]), "tile_base": tb,
                 "codes_words": cw, "valid_words": vw}
 
-    def extract_kmers(self, packed: dict, k: int) -> DeviceBuffer:
-        """K2.  Returns a DeviceBuffer of n_symbols k-mer words (sentinel = all ones)."""
+    def extract_kmers(self, packed: dict, k: int, hashed: bool = False) -> DeviceBuffer:
+        """K2.  Returns a DeviceBuffer of n_symbols k-mer words (sentinel = all ones); hashed=True applies the
+        bijective mixer of the fused path."""
         n = packed["n_symbols"]
         keys = self.alloc((n + 4) * 8 * key_words(k))
-        self._chk(self.lib.khb_extract_kmers(self.ctx, packed["codes"].ptr, packed["valid"].ptr, n, k, keys.ptr))
+        fn = self.lib.khb_extract_kmers_hashed if hashed else self.lib.khb_extract_kmers
+        self._chk(fn(self.ctx, packed["codes"].ptr, packed["valid"].ptr, n, k, keys.ptr))
         self.sync()
         return keys
+
+    def remix_keys(self, keys: DeviceBuffer, n: int, k: int, inverse: bool):
+        """Apply the mixer (inverse=False) or its inverse (inverse=True) to n keys in place."""
+        self._chk(self.lib.khb_remix_keys(self.ctx, keys.ptr, n, k, int(inverse)))
+        self.sync()
+
+    def prefix_plan(self, k: int, n_max: int):
+        fb, np_ = C.c_int(), C.c_int()
+        self._chk(self.lib.khb_prefix_plan(k, n_max, C.byref(fb), C.byref(np_)))
+        return fb.value, np_.value
+
+    def sort_key_bits(self, keys: DeviceBuffer, n: int, k: int, first_bit: int, npass: int,
+                      seg_off: Optional[Sequence[int]] = None) -> DeviceBuffer:
+        """K3 on the digits [first_bit, first_bit + 8*npass) only."""
+        seg = np.ascontiguousarray(seg_off if seg_off is not None else [0, n], dtype=np.uint64)
+        tmp = self.alloc(keys.nbytes)
+        flag = C.c_int(0)
+        self._chk(self.lib.khb_sort_key_bits(self.ctx, keys.ptr, tmp.ptr, seg.ctypes.data, len(seg) - 1, 8 * key_words(k),
+                                             first_bit, npass, C.byref(flag)))
+        self.sync()
+        if flag.value:
+            return tmp
+        tmp.free()
+        return keys
+
+    def resolve_unique(self, sorted_keys: DeviceBuffer, n: int, k: int, prefix_shift: int) -> Tuple[DeviceBuffer, int]:
+        out = self.alloc(sorted_keys.nbytes)
+        cnt = C.c_uint64(0)
+        self._chk(self.lib.khb_resolve_unique(self.ctx, sorted_keys.ptr, n, k, prefix_shift, out.ptr, C.byref(cnt)))
+        return out, int(cnt.value)
+
+    def resolve_count(self, sorted_keys: DeviceBuffer, n: int, k: int, prefix_shift: int, nbins: int = COUNTER_MAX,
+                      cs: int = COUNTER_MAX, want_keys: bool = False):
+        hist = np.zeros(nbins + 1, dtype=np.uint64)
+        runs = C.c_uint64(0)
+        ok = self.alloc(sorted_keys.nbytes) if want_keys else None
+        self._chk(self.lib.khb_resolve_count(self.ctx, sorted_keys.ptr, n, k, prefix_shift, cs, nbins, hist.ctypes.data,
+                                             ok.ptr if ok else None, C.byref(runs)))
+        return hist, int(runs.value), ok
 
     def sort_keys(self, keys: DeviceBuffer, n: int, k: int, seg_off: Optional[Sequence[int]] = None) -> DeviceBuffer:
         """K3.  Sorts segments of `keys` (default: one segment [0, n)); returns the buffer holding the result."""
@@ -350,16 +400,19 @@ class Engine:
         return {"k": k.value, "n_groups": g.value, "n_keys": n.value}
 
     def group_sets_download(self) -> np.ndarray:
-        """Concatenation of the retained group sets (each sorted) as host k-mer words."""
+        """Concatenation of the retained group sets as canonical k-mer values (host), group after group; the
+        order inside a group is the fused path's prefix order, not numeric order."""
         info = self.group_sets_info()
-        p, n = _P(), C.c_uint64()
-        self._chk(self.lib.khb_group_sets_device(self.ctx, C.byref(p), C.byref(n)))
+        n = info["n_keys"]
         w = key_words(info["k"]) if info["k"] else 1
-        out = np.empty(int(n.value) * w, dtype=np.uint64)
+        out = np.empty(n * w, dtype=np.uint64)
         if out.nbytes:
-            self._chk(self.lib.khb_memcpy_d2h(self.ctx, out.ctypes.data, p.value, out.nbytes))
-            self.sync()
-        return out.reshape(key_shape(int(n.value), info["k"] or 1))
+            self._chk(self.lib.khb_group_sets_export(self.ctx, out.ctypes.data))
+        return out.reshape(key_shape(n, info["k"] or 1))
+
+    @property
+    def group_sets_hashed(self) -> bool:
+        return bool(self.lib.khb_group_sets_hashed(self.ctx))
 
     def group_sets_device(self) -> Tuple[int, int]:
         p, n = _P(), C.c_uint64()
@@ -370,8 +423,8 @@ class Engine:
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
         self._chk(self.lib.khb_group_sets_append_host(self.ctx, k, keys.ctypes.data, keys.shape[0], n_groups))
 
-    def group_sets_append_device(self, ptr: int, n_keys: int, k: int, n_groups: int = 1):
-        self._chk(self.lib.khb_group_sets_append_device(self.ctx, k, ptr, n_keys, n_groups))
+    def group_sets_append_device(self, ptr: int, n_keys: int, k: int, n_groups: int = 1, hashed: bool = False):
+        self._chk(self.lib.khb_group_sets_append_device(self.ctx, k, ptr, n_keys, n_groups, int(hashed)))
 
     def group_sets_reset(self):
         self._chk(self.lib.khb_group_sets_reset(self.ctx))

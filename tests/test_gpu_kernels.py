@@ -191,3 +191,59 @@ def test_partition_by_hash(engine, k, parts):
     if parts > 1:
         sizes = np.diff(off.astype(np.int64))
         assert sizes.min() > 0.8 * n / parts
+
+
+@pytest.mark.parametrize("k", [5, 12, 13, 21, 31, 32, 33, 47, 63, 64])
+def test_mixer_is_a_bijection_that_unmix_inverts(engine, k):
+    rng = np.random.default_rng(k)
+    n = 50_000
+    keys = _rand_keys(rng, n, k, dup=0.0)
+    keys[:3] = 0
+    w = 1 if k <= 32 else 2
+    sent = np.full((4,) + keys.shape[1:], 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
+    allk = np.concatenate([keys, sent], axis=0)
+    buf = engine.alloc((allk.shape[0] + 4) * 8 * w)
+    buf.upload(allk)
+    engine.remix_keys(buf, allk.shape[0], k, inverse=False)
+    mixed = buf.download(np.uint64, allk.shape[0] * w).reshape(allk.shape)
+    assert np.array_equal(mixed[-4:], sent)                       # sentinels stay sentinels
+    assert not np.array_equal(mixed[:n], keys)
+    if w == 1 and k < 32:
+        assert int(mixed[:n].max()) < (1 << (2 * k))              # stays inside [0, 4^k)
+    uniq_in = np.unique(keys, axis=0).shape[0]
+    assert np.unique(mixed[:n], axis=0).shape[0] == uniq_in       # injective on the sample
+    engine.remix_keys(buf, allk.shape[0], k, inverse=True)
+    assert np.array_equal(buf.download(np.uint64, allk.shape[0] * w).reshape(allk.shape), allk)
+
+
+@pytest.mark.parametrize("k,n,nd,slack_n", [(31, 200_000, 150_000, 200_000), (31, 300_000, 3000, 64), (21, 100_000, 99_000, 100_000),
+                                            (47, 120_000, 40_000, 120_000), (63, 90_000, 500, 8), (13, 50_000, 20_000, 50_000)])
+def test_prefix_sort_plus_resolve_equals_full_sort_results(engine, k, n, nd, slack_n):
+    """Sorting hashed keys by a prefix only and resolving runs by comparison must give the same distinct set
+    and the same multiplicity histogram as a full sort (slack_n small = a deliberately too short prefix,
+    i.e. many distinct keys per prefix run)."""
+    rng = np.random.default_rng(n + k)
+    pool = _rand_keys(rng, nd, k, dup=0.0)
+    keys = pool[rng.integers(0, nd, size=n)]
+    w = 1 if k <= 32 else 2
+    nsent = 37
+    sent = np.full((nsent,) + keys.shape[1:], 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
+    allk = np.concatenate([keys[: n // 2], sent[:10], keys[n // 2:], sent[10:]], axis=0)
+    ntot = allk.shape[0]
+    ref_keys, ref_len = _np_runs(sort_rows(allk))
+    buf = engine.alloc((ntot + 4) * 8 * w)
+    buf.upload(allk)
+    engine.remix_keys(buf, ntot, k, inverse=False)
+    fb, npass = engine.prefix_plan(k, slack_n)
+    assert 0 <= fb and 1 <= npass <= (2 * k + 7) // 8
+    srt = engine.sort_key_bits(buf, ntot, k, fb, npass)
+    out, cnt = engine.resolve_unique(srt, ntot, k, fb)
+    assert cnt == ref_keys.shape[0]
+    engine.remix_keys(out, cnt, k, inverse=True)
+    assert np.array_equal(sort_rows(out.download(np.uint64, cnt * w).reshape(ref_keys.shape)), ref_keys)
+    for cs in (5000, 3):
+        hist, runs, ok = engine.resolve_count(srt, ntot, k, fb, cs=cs, want_keys=True)
+        assert runs == ref_keys.shape[0]
+        assert np.array_equal(hist, np.bincount(np.minimum(ref_len, cs), minlength=5001).astype(np.uint64))
+        engine.remix_keys(ok, runs, k, inverse=True)
+        assert np.array_equal(sort_rows(ok.download(np.uint64, runs * w).reshape(ref_keys.shape)), ref_keys)

@@ -26,18 +26,23 @@ def test_small_groups_match_oracle(engine, oracle, k):
     gid = [i for i, grp in enumerate(groups) for _ in grp]
     w_ref, a_ref, st_ref = oracle.exp1(flat, gid, len(groups), k)
     engine.group_sets_reset()
-    tot_bases = 0
+    tot_bases, sizes = 0, []
     for i, grp in enumerate(groups):
         hist, st = engine.group_from_fasta(grp, k)
         assert np.array_equal(hist, w_ref[i]), f"group {i} within-group histogram"
         tot_bases += st["bases"]
+        sizes.append(st["distinct"])
     assert tot_bases == st_ref["symbols"]
     info = engine.group_sets_info()
     assert info["n_groups"] == len(groups) and info["k"] == k
     assert info["n_keys"] == st_ref["sum_group_distinct"]
-    sets = engine.group_sets_download()
+    sets = engine.group_sets_download()      # canonical values, group after group, prefix order inside a group
     ref_sets = _oracle_group_sets(oracle, groups, k)
-    assert np.array_equal(sets, np.concatenate(ref_sets, axis=0))
+    off = 0
+    for i, ref in enumerate(ref_sets):
+        assert sizes[i] == ref.shape[0]
+        assert np.array_equal(sort_rows(sets[off:off + sizes[i]]), ref), f"group {i} distinct k-mer set"
+        off += sizes[i]
     hist, st = engine.across_groups()
     assert np.array_equal(hist, a_ref)
     assert st["distinct"] == st_ref["distinct"]
