@@ -172,6 +172,11 @@ KHB_API int khb_group_from_fasta(khb_ctx *ctx, int k, int n_genomes, const uint8
                          const size_t *h_sizes, uint32_t nbins, uint64_t *h_hist, int keep_set,
                          khb_stats *stats);
 
+/* Double-buffered ingestion: start copying the text of the NEXT group to the device on a second stream while the
+ * current group is being processed.  A following khb_group_from_fasta call with the same file list uses the
+ * prefetched copy (it waits for it on the device) instead of copying again. */
+KHB_API int khb_group_prefetch_fasta(khb_ctx *ctx, int n_genomes, const uint8_t *const *h_files, const size_t *h_sizes);
+
 /* Same stage with the text already staged in device memory by khb_stage_fasta (h_begin as returned by it). */
 KHB_API int khb_group_from_staged(khb_ctx *ctx, int k, int n_genomes, const uint8_t *d_fasta, const uint64_t *h_begin,
                           uint32_t nbins, uint64_t *h_hist, int keep_set, khb_stats *stats);

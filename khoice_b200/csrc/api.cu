@@ -9,7 +9,13 @@
 
 // implemented in the kernel translation units
 int khb_pack_fasta_impl(khb_ctx *, const uint8_t *, size_t, u64 *, u32 *, size_t, u64 *, u64 *);
-int khb_fasta_separators_impl(khb_ctx *, uint8_t *, const u64 *, const u64 *, int, u64);
+int khb_fasta_separators_impl(khb_ctx *, uint8_t *, const u64 *, const u64 *, int, u64, cudaStream_t);
+struct khb_hostvec {
+    std::vector<u64> v;                    // begin offsets of the prefetched group
+    std::vector<const uint8_t *> d_files;  // deferred prefetch request (issued while another one is pending)
+    std::vector<size_t> d_sizes;
+    bool deferred = false;
+};
 int khb_extract_kmers_impl(khb_ctx *, const u64 *, const u32 *, size_t, int, int, void *);
 int khb_remix_impl(khb_ctx *, void *, size_t, int, int);
 int khb_sort_keys_impl(khb_ctx *, void *, void *, const u64 *, int, int, int *);
@@ -162,6 +168,11 @@ int khb_destroy(khb_ctx *ctx)
         if (ctx->scratch[i].ptr) cudaFree(ctx->scratch[i].ptr);
     if (ctx->gs_buf) cudaFree(ctx->gs_buf);
     if (ctx->stage_dev) cudaFree(ctx->stage_dev);
+    if (ctx->stage_next) cudaFree(ctx->stage_next);
+    if (ctx->pf_tab) cudaFree(ctx->pf_tab);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    delete ctx->pf_begin;
     if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
     if (ctx->d_mail) cudaFree(ctx->d_mail);
     cudaEventDestroy(ctx->ev0);
@@ -317,7 +328,7 @@ int khb_stage_fasta(khb_ctx *ctx, int n_files, const uint8_t *const *h_files, co
     if (rc) return rc;
     KHB_CUDA(ctx, cudaMemcpyAsync(p, tab.data(), 2 * (size_t)n_files * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
     KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // tab is pageable and dies with this frame
-    return khb_fasta_separators_impl(ctx, d_fasta, (const u64 *)p, (const u64 *)p + n_files, n_files, off);
+    return khb_fasta_separators_impl(ctx, d_fasta, (const u64 *)p, (const u64 *)p + n_files, n_files, off, ctx->stream);
 }
 
 // ---- thin kernel wrappers ------------------------------------------------------------------------
@@ -702,12 +713,109 @@ int khb_group_from_staged(khb_ctx *ctx, int k, int n_genomes, const uint8_t *d_f
     return rc;
 }
 
+static int ensure_stage(khb_ctx *ctx, uint8_t **buf, size_t *cap, size_t need)
+{
+    if (need <= *cap) return KHB_OK;
+    if (*buf) {
+        KHB_CUDA(ctx, cudaDeviceSynchronize());
+        KHB_CUDA(ctx, cudaFree(*buf));
+        *buf = nullptr;
+        *cap = 0;
+    }
+    const size_t want = need + need / 8;
+    cudaError_t e = cudaMalloc((void **)buf, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return khb_fail(ctx, KHB_ERR_NOMEM, "staging buffer: device allocation of %zu bytes failed", want);
+    }
+    *cap = want;
+    return KHB_OK;
+}
+
+int khb_group_prefetch_fasta(khb_ctx *ctx, int n_genomes, const uint8_t *const *h_files, const size_t *h_sizes)
+{
+    KHB_CHECK_CTX(ctx);
+    if (n_genomes < 1 || !h_files || !h_sizes) return khb_fail(ctx, KHB_ERR_ARG, "khb_group_prefetch_fasta: bad arguments");
+    if (!ctx->copy_stream) {
+        KHB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        KHB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+        ctx->pf_begin = new khb_hostvec();
+    }
+    if (ctx->pf_valid) {
+        // a prefetched group is still waiting to be consumed: its buffer cannot be overwritten.  Remember the
+        // request; khb_group_from_fasta starts it as soon as it has taken over the pending buffer.
+        ctx->pf_begin->d_files.assign(h_files, h_files + n_genomes);
+        ctx->pf_begin->d_sizes.assign(h_sizes, h_sizes + n_genomes);
+        ctx->pf_begin->deferred = true;
+        return KHB_OK;
+    }
+    ctx->pf_valid = 0;
+    const size_t need = khb_staged_size(n_genomes, h_sizes);
+    int rc = ensure_stage(ctx, &ctx->stage_next, &ctx->stage_next_cap, need);
+    if (rc) return rc;
+    const size_t tab_bytes = 2 * (size_t)n_genomes * sizeof(u64);
+    if (tab_bytes > ctx->pf_tab_cap) {
+        if (ctx->pf_tab) {
+            KHB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+            KHB_CUDA(ctx, cudaFree(ctx->pf_tab));
+        }
+        KHB_CUDA(ctx, cudaMalloc((void **)&ctx->pf_tab, tab_bytes * 2));
+        ctx->pf_tab_cap = tab_bytes * 2;
+    }
+    std::vector<u64> &begin = ctx->pf_begin->v;
+    begin.assign((size_t)n_genomes + 1, 0);
+    std::vector<u64> tab(2 * (size_t)n_genomes);
+    u64 off = 0;
+    for (int i = 0; i < n_genomes; i++) {
+        begin[i] = off;
+        tab[i] = off;
+        tab[n_genomes + i] = h_sizes[i];
+        off += staged_len(h_sizes[i]);
+    }
+    begin[n_genomes] = off;
+    for (int i = 0; i < n_genomes; i++)
+        if (h_sizes[i]) KHB_CUDA(ctx, cudaMemcpyAsync(ctx->stage_next + begin[i], h_files[i], h_sizes[i], cudaMemcpyHostToDevice, ctx->copy_stream));
+    KHB_CUDA(ctx, cudaMemcpyAsync(ctx->pf_tab, tab.data(), tab_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));  // pageable: staged before return
+    rc = khb_fasta_separators_impl(ctx, ctx->stage_next, ctx->pf_tab, ctx->pf_tab + n_genomes, n_genomes, off, ctx->copy_stream);
+    if (rc) return rc;
+    ctx->launches++;
+    KHB_CUDA(ctx, cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+    ctx->pf_valid = 1;
+    ctx->pf_n = n_genomes;
+    ctx->pf_first = h_files[0];
+    ctx->pf_bytes = off;
+    return KHB_OK;
+}
+
 int khb_group_from_fasta(khb_ctx *ctx, int k, int n_genomes, const uint8_t *const *h_files, const size_t *h_sizes,
                          uint32_t nbins, uint64_t *h_hist, int keep_set, khb_stats *stats)
 {
     KHB_CHECK_CTX(ctx);
     if (n_genomes < 1 || !h_files || !h_sizes) return khb_fail(ctx, KHB_ERR_ARG, "khb_group_from_fasta: bad arguments");
     if (stats) memset(stats, 0, sizeof(*stats));
+    if (ctx->pf_valid && ctx->pf_n == n_genomes && ctx->pf_first == (const void *)h_files[0] &&
+        ctx->pf_bytes == khb_staged_size(n_genomes, h_sizes)) {
+        // the text of this group was prefetched: swap staging buffers and wait for the copy on the device
+        ctx->pf_valid = 0;
+        uint8_t *tb = ctx->stage_dev; ctx->stage_dev = ctx->stage_next; ctx->stage_next = tb;
+        size_t tc = ctx->stage_dev_cap; ctx->stage_dev_cap = ctx->stage_next_cap; ctx->stage_next_cap = tc;
+        PhaseTimer tm(ctx);
+        tm.mark();
+        KHB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
+        tm.mark();
+        std::vector<u64> begin = ctx->pf_begin->v;
+        if (ctx->pf_begin->deferred) {  // start copying the next group now; it overlaps this group's kernels
+            ctx->pf_begin->deferred = false;
+            std::vector<const uint8_t *> nf = ctx->pf_begin->d_files;
+            std::vector<size_t> ns = ctx->pf_begin->d_sizes;
+            int prc = khb_group_prefetch_fasta(ctx, (int)nf.size(), nf.data(), ns.data());
+            if (prc) return prc;
+        }
+        int rc = group_from_staged_impl(ctx, k, n_genomes, ctx->stage_dev, begin.data(), nbins, (u64 *)h_hist, keep_set, stats, tm);
+        if (rc == KHB_OK) fill_times(stats, tm);
+        return rc;
+    }
+    ctx->pf_valid = 0;
     const size_t need = khb_staged_size(n_genomes, h_sizes);
     if (need > ctx->stage_dev_cap) {
         if (ctx->stage_dev) {

@@ -252,215 +252,123 @@ rle_hist_kernel(const Key *__restrict__ in, u64 n, u32 cs, u32 nbins, u64 *__res
 }
 
 // ---- prefix-run resolution (fused path) -------------------------------------------------------------------
-// The fused path sorts hashed keys by a PREFIX only (bits >= pshift, see khb_prefix_plan), which costs
-// 3-4 radix passes instead of ceil(2k/8).  Keys with equal prefix are adjacent ("prefix run") but not
-// ordered among themselves, so equality inside a run is resolved by comparison:
-//   head(i)  = no j < i in the same prefix run with in[j] == in[i]      (backward scan)
-//   count(i) = 1 + #{ j > i in the same prefix run : in[j] == in[i] }    (forward scan, heads only)
-// With a bijective mixer the prefix is uniform, a run holds O(1) distinct values, and both scans touch a
-// handful of L1-resident neighbours.  COUNT = false: emit heads (per-genome set, K4).  COUNT = true:
-// histogram of count(i) over heads (+ emit heads = the group's distinct set, K5/K6).
-// Sentinels never share a prefix with a real key (the plan covers the spare bit above 2k), and every
-// genome segment ends with at least one sentinel, so a scan never leaves its segment.
-template <typename Key, bool COUNT>
-__global__ void __launch_bounds__(CP_BLOCK)
-resolve_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 nbins, u64 *__restrict__ hist,
-               Key *__restrict__ out, u64 *__restrict__ lookback, u32 *__restrict__ ticket, u32 epoch,
-               u64 *__restrict__ d_count)
-{
-    extern __shared__ u32 sh_hist[];  // [nbins+1] when COUNT
-    __shared__ u64 ws[33];
-    __shared__ u32 s_tile;
-    __shared__ u64 s_base;
-    const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-    const u64 ntiles = (n + CP_TILE - 1) / CP_TILE;
-    if (COUNT)
-        for (u32 i = tid; i <= nbins; i += CP_BLOCK) sh_hist[i] = 0;
-    for (;;) {
-        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-        __syncthreads();
-        const u64 tile = s_tile;
-        if (tile >= ntiles) break;
-        const u64 begin = tile * CP_TILE;
-        const u32 wbase = warp * (32 * CP_ITEMS);
-        Key keys[CP_ITEMS];
-        load_tile(in, begin, n, wbase, lane, keys);
-        const u64 chunk0 = begin + wbase;
-        u32 ball[CP_ITEMS];
-        u32 wcount = 0;
-#pragma unroll
-        for (int r = 0; r < CP_ITEMS; r++) {
-            const u64 g = chunk0 + r * 32 + lane;
-            const Key key = keys[r];
-            bool head = g < n && !key_is_sentinel(key);
-            if (head) {
-                u64 j = g;
-                while (j > 0) {
-                    --j;
-                    const Key kj = in[j];
-                    if (!same_prefix(kj, key, pshift)) break;
-                    if (key_eq(kj, key)) { head = false; break; }
-                }
-            }
-            if (COUNT && head) {
-                u32 c = 1;
-                for (u64 j = g + 1; j < n; j++) {
-                    const Key kj = in[j];
-                    if (!same_prefix(kj, key, pshift)) break;
-                    c += key_eq(kj, key) ? 1u : 0u;
-                }
-                c = c > cs ? cs : c;
-                if (c <= nbins) atomicAdd(&sh_hist[c], 1u);
-            }
-            ball[r] = __ballot_sync(0xffffffffu, head);
-            wcount += __popc(ball[r]);
-        }
-        u64 total;
-        const u64 woff = block_excl_sum<u64>(lane == 0 ? (u64)wcount : 0ull, ws, &total);
-        const u64 warp_off = __shfl_sync(0xffffffffu, woff, 0);
-        if (warp == 0) {
-            u64 excl = 0;
-            if (tile == 0) {
-                if (lane == 0) lb_store(lookback, lb_pack(LB_PREFIX, total, epoch));
-            } else {
-                if (lane == 0) lb_store(lookback + tile, lb_pack(LB_AGG, total, epoch));
-                excl = lb_walk_warp(lookback, tile, 0, epoch);
-                if (lane == 0) lb_store(lookback + tile, lb_pack(LB_PREFIX, excl + total, epoch));
-            }
-            if (lane == 0) {
-                s_base = excl;
-                if (tile == ntiles - 1) *d_count = excl + total;
-            }
-        }
-        __syncthreads();
-        if (out != nullptr) {
-            u64 pos = s_base + warp_off;
-#pragma unroll
-            for (int r = 0; r < CP_ITEMS; r++) {
-                if ((ball[r] >> lane) & 1u) out[pos + __popc(ball[r] & lanemask_lt())] = keys[r];
-                pos += __popc(ball[r]);
-            }
-        }
-        __syncthreads();
-    }
-    if (COUNT) {
-        __syncthreads();
-        for (u32 i = tid; i <= nbins; i += CP_BLOCK) {
-            const u32 c = sh_hist[i];
-            if (c) atomicAdd(&hist[i], (u64)c);
-        }
-    }
-}
-
-// K5/K6 on prefix-sorted input, O(1) per key for the common case.  Works on ADJACENT runs of equal keys like
-// rle_hist_kernel (head/tail ballots, in-tile max-scan of head positions, run_head_before for the run that is
-// open at the tile start) and adds, at the tail t of every adjacent run [h, t]:
+// The fused path sorts hashed keys by a PREFIX only (bits >= pshift, see khb_prefix_plan), which costs 3-4 radix
+// passes instead of ceil(2k/8).  Keys with equal prefix are adjacent ("prefix run") but not ordered among
+// themselves, so equality inside a run is resolved by comparison.  Sentinels never share a prefix with a real key
+// (the plan covers the spare bit above 2k) and every genome segment ends with at least one sentinel, so a scan
+// never leaves its segment.
+// K4 / K5 / K6 on prefix-sorted input, blocked arrangement: every thread owns CQ_ITEMS CONSECUTIVE keys, so
+// head / tail detection and run lengths are register-to-register compares; one warp max-scan per thread (not
+// per key) carries the position of the last run head across threads.  At the tail t of every adjacent run
+// [h, t] of equal keys:
 //   first  = no key equal to in[t] precedes h inside the prefix run   (one compare unless the run is mixed)
 //   extra  = equal keys after t inside the prefix run                  (zero compares unless the run is mixed)
 // A prefix run is "mixed" when it holds more than one distinct value -- rare, because the prefix of a hashed
-// key is uniform and the plan gives it more slots than there are keys.  Runs that are `first` add
-// hist[min(len + extra, cs)] and emit their key.
-template <typename Key>
+// key is uniform and the plan gives it more slots than there are keys.  Runs that are `first` are emitted
+// (distinct keys, in input order) and, if COUNT, add hist[min(len + extra, cs)].
+#define CQ_ITEMS 8
+template <typename Key, bool COUNT>
 __global__ void __launch_bounds__(CQ_BLOCK, sizeof(Key) == 8 ? 4 : 2)
-count_prefix_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 nbins, u64 *__restrict__ hist,
-                    Key *__restrict__ out_keys, u64 *__restrict__ lookback, u32 *__restrict__ ticket, u32 epoch,
-                    u64 *__restrict__ d_runs)
+runs_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 nbins, u64 *__restrict__ hist,
+            Key *__restrict__ out_keys, u64 *__restrict__ lookback, u32 *__restrict__ ticket, u32 epoch,
+            u64 *__restrict__ d_runs)
 {
-    extern __shared__ u32 sh_hist[];  // [nbins+1]
+    constexpr int TILE = CQ_BLOCK * CQ_ITEMS;
+    extern __shared__ u32 sh_hist[];  // [nbins+1] when COUNT
     __shared__ u64 ws[33];
     __shared__ u32 s_tile;
     __shared__ u64 s_base;
     __shared__ u64 s_head0;
     __shared__ u32 s_wlast[CQ_WARPS];
     const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-    const u64 ntiles = (n + CQ_TILE - 1) / CQ_TILE;
-    for (u32 i = tid; i <= nbins; i += CQ_BLOCK) sh_hist[i] = 0;
+    const u64 ntiles = (n + TILE - 1) / TILE;
+    if (COUNT)
+        for (u32 i = tid; i <= nbins; i += CQ_BLOCK) sh_hist[i] = 0;
     for (;;) {
         if (tid == 0) s_tile = atomicAdd(ticket, 1u);
         __syncthreads();
         const u64 tile = s_tile;
         if (tile >= ntiles) break;
-        const u64 begin = tile * CQ_TILE;
-        const u32 wbase = warp * (32 * CP_ITEMS);
-        Key keys[CP_ITEMS];
-        load_tile(in, begin, n, wbase, lane, keys);
-        const u64 chunk0 = begin + wbase;
-        Key before = sentinel_key<Key>();
-        if (chunk0 > 0 && chunk0 < n) before = in[chunk0 - 1];
-        const u64 after_idx = chunk0 + 32 * CP_ITEMS;
-        Key after = sentinel_key<Key>();
-        if (after_idx < n) after = in[after_idx];
+        const u64 begin = tile * TILE;
+        const u32 l0 = tid * CQ_ITEMS;     // local index of this thread's first key
+        const u64 g0 = begin + l0;
+        Key k[CQ_ITEMS + 2];               // k[0] = predecessor, k[1..ITEMS] = own keys, k[ITEMS+1] = successor
+        if (g0 + CQ_ITEMS < n && g0 > 0) {
+#pragma unroll
+            for (int j = 0; j < CQ_ITEMS + 2; j++) k[j] = in[g0 - 1 + j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < CQ_ITEMS + 2; j++) {
+                const u64 g = g0 + j;  // index + 1
+                k[j] = (g >= 1 && g - 1 < n) ? in[g - 1] : sentinel_key<Key>();
+            }
+        }
         if (warp == 0) {
-            Key k0 = shfl_key(keys[0], 0);
+            Key k0 = shfl_key(k[1], 0);
             u64 h0 = begin;
             if (begin > 0 && begin < n && !key_is_sentinel(k0)) h0 = run_head_before(in, begin, k0, lane);
             if (lane == 0) s_head0 = h0;
         }
-        u32 tball[CP_ITEMS], hrun[CP_ITEMS];
-        u32 mixed_next = 0;  // bit r: the key after this tail shares its prefix (mixed run ahead)
-        u32 carry = 0;
+        // heads and tails of adjacent runs inside this thread's keys
+        u32 headm = 0, tailm = 0, lasth = 0;  // lasth = local index + 1 of the thread's last head
 #pragma unroll
-        for (int r = 0; r < CP_ITEMS; r++) {
-            const u64 g = chunk0 + r * 32 + lane;
-            const Key pk = prev_key(keys, r, lane, before);
-            Key dn = shfl_key(keys[r], (int)((lane + 1) & 31));
-            Key nxt = r + 1 < CP_ITEMS ? shfl_key(keys[r + 1 < CP_ITEMS ? r + 1 : r], 0) : after;
-            const Key nk = lane == 31 ? nxt : dn;
-            const bool valid = g < n && !key_is_sentinel(keys[r]);
-            const bool head = valid && (g == 0 || !key_eq(keys[r], pk));
-            const bool last = g + 1 >= n;
-            const bool tail = valid && (last || !key_eq(keys[r], nk));
-            if (tail && !last && !key_is_sentinel(nk) && same_prefix(nk, keys[r], pshift)) mixed_next |= 1u << r;
-            tball[r] = __ballot_sync(0xffffffffu, tail);
-            const u32 loc = wbase + r * 32 + lane + 1;
-            u32 h = warp_incl_max<u32>(head ? loc : 0u);
-            h = h > carry ? h : carry;
-            hrun[r] = h;
-            carry = __shfl_sync(0xffffffffu, h, 31);
+        for (int j = 0; j < CQ_ITEMS; j++) {
+            const u64 g = g0 + j;
+            const bool valid = g < n && !key_is_sentinel(k[j + 1]);
+            const bool head = valid && (g == 0 || !key_eq(k[j + 1], k[j]));
+            const bool tail = valid && (g + 1 >= n || !key_eq(k[j + 1], k[j + 2]));
+            headm |= (head ? 1u : 0u) << j;
+            tailm |= (tail ? 1u : 0u) << j;
+            if (head) lasth = l0 + j + 1;
         }
-        if (lane == 0) s_wlast[warp] = carry;
+        // last head before this thread: exclusive max-scan over the CTA
+        u32 inc = warp_incl_max<u32>(lasth);
+        u32 carry = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) carry = 0;
+        if (lane == 31) s_wlast[warp] = inc;
         __syncthreads();  // s_wlast, s_head0
         u32 wprefix = 0;
         for (u32 w = 0; w < warp; w++) wprefix = s_wlast[w] > wprefix ? s_wlast[w] : wprefix;
+        carry = carry > wprefix ? carry : wprefix;
         const u64 head0 = s_head0;
-        // per tail: adjacent length, then the (rare) mixed-run checks; `emit` = this run is the first of its value
-        u32 eball[CP_ITEMS];
-        u32 wcount = 0;
+        // resolve every tail
+        u32 emitm = 0;
+        u32 cur = carry;  // local index + 1 of the head of the run open at key j (0: before the tile)
 #pragma unroll
-        for (int r = 0; r < CP_ITEMS; r++) {
-            const u64 g = chunk0 + r * 32 + lane;
-            bool emit = false;
-            if ((tball[r] >> lane) & 1u) {
-                const Key key = keys[r];
-                const u32 h = hrun[r] ? hrun[r] : wprefix;
-                const u64 hg = h ? begin + (h - 1) : head0;
-                u64 len = g - hg + 1;
-                emit = true;
-                u64 j = hg;
-                while (j > 0) {  // an earlier occurrence inside the prefix run?
-                    --j;
-                    const Key kj = in[j];
-                    if (!same_prefix(kj, key, pshift)) break;
-                    if (key_eq(kj, key)) { emit = false; break; }
+        for (int j = 0; j < CQ_ITEMS; j++) {
+            if ((headm >> j) & 1u) cur = l0 + j + 1;
+            if ((tailm >> j) & 1u) {
+                const Key key = k[j + 1];
+                const u64 g = g0 + j;
+                const u64 hg = cur ? begin + (cur - 1) : head0;
+                bool first = true;
+                u64 q = hg;
+                while (q > 0) {  // an earlier occurrence inside the prefix run?
+                    --q;
+                    const Key kq = in[q];
+                    if (!same_prefix(kq, key, pshift)) break;
+                    if (key_eq(kq, key)) { first = false; break; }
                 }
-                if (emit) {
-                    if ((mixed_next >> r) & 1u) {
-                        for (u64 q = g + 1; q < n; q++) {  // later occurrences inside the prefix run
-                            const Key kq = in[q];
-                            if (!same_prefix(kq, key, pshift)) break;
-                            len += key_eq(kq, key) ? 1u : 0u;
+                if (first) {
+                    emitm |= 1u << j;
+                    if (COUNT) {
+                        u64 len = g - hg + 1;
+                        if (g + 1 < n && !key_is_sentinel(k[j + 2]) && same_prefix(k[j + 2], key, pshift)) {
+                            for (u64 r = g + 1; r < n; r++) {  // later occurrences inside the prefix run
+                                const Key kr = in[r];
+                                if (!same_prefix(kr, key, pshift)) break;
+                                len += key_eq(kr, key) ? 1u : 0u;
+                            }
                         }
+                        const u32 c = len > (u64)cs ? cs : (u32)len;
+                        if (c <= nbins) atomicAdd(&sh_hist[c], 1u);
                     }
-                    const u32 c = len > (u64)cs ? cs : (u32)len;
-                    if (c <= nbins) atomicAdd(&sh_hist[c], 1u);
                 }
             }
-            eball[r] = __ballot_sync(0xffffffffu, emit);
-            wcount += __popc(eball[r]);
         }
+        const u32 mine = __popc(emitm);
         u64 total;
-        const u64 woff = block_excl_sum<u64>(lane == 0 ? (u64)wcount : 0ull, ws, &total);
-        const u64 warp_off = __shfl_sync(0xffffffffu, woff, 0);
+        const u64 off = block_excl_sum<u64>((u64)mine, ws, &total);
         if (warp == 0) {
             u64 excl = 0;
             if (out_keys != nullptr) {
@@ -478,20 +386,20 @@ count_prefix_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 n
             }
         }
         __syncthreads();
-        if (out_keys != nullptr) {
-            u64 pos = s_base + warp_off;
+        if (out_keys != nullptr && mine) {
+            u64 pos = s_base + off;
 #pragma unroll
-            for (int r = 0; r < CP_ITEMS; r++) {
-                if ((eball[r] >> lane) & 1u) out_keys[pos + __popc(eball[r] & lanemask_lt())] = keys[r];
-                pos += __popc(eball[r]);
-            }
+            for (int j = 0; j < CQ_ITEMS; j++)
+                if ((emitm >> j) & 1u) out_keys[pos++] = k[j + 1];
         }
         __syncthreads();
     }
-    __syncthreads();
-    for (u32 i = tid; i <= nbins; i += CQ_BLOCK) {
-        const u32 c = sh_hist[i];
-        if (c) atomicAdd(&hist[i], (u64)c);
+    if (COUNT) {
+        __syncthreads();
+        for (u32 i = tid; i <= nbins; i += CQ_BLOCK) {
+            const u32 c = sh_hist[i];
+            if (c) atomicAdd(&hist[i], (u64)c);
+        }
     }
 }
 
@@ -555,24 +463,24 @@ int khb_count_runs_impl(khb_ctx *ctx, const void *d_sorted, size_t n, int k, u32
     return KHB_OK;
 }
 
-// K4 on prefix-sorted input: d_count <- number of heads; d_out <- heads in input order.
+// K4 on prefix-sorted input: d_count <- number of distinct keys; d_out <- distinct keys in input order.
 int khb_resolve_unique_impl(khb_ctx *ctx, const void *d_sorted, size_t n, int k, int pshift, void *d_out, u64 *d_count)
 {
     if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_resolve_unique: k=%d outside 1..64", k);
     KHB_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(u64), ctx->stream));
     if (n == 0) return KHB_OK;
-    const u64 ntiles = div_up(n, CP_TILE);
+    const u64 ntiles = div_up(n, CQ_BLOCK * CQ_ITEMS);
     u64 *d_lb;
     u32 *d_ticket;
     int rc = compact_scratch(ctx, ntiles, &d_lb, &d_ticket);
     if (rc) return rc;
-    u64 grid = (u64)ctx->num_sms * 3;
+    u64 grid = (u64)ctx->num_sms * (k <= 32 ? 4 : 2);
     if (grid > ntiles) grid = ntiles;
     khb_prof_begin(ctx, KHB_K_UNIQUE);
     if (k <= 32)
-        resolve_kernel<Key64, false><<<(unsigned)grid, CP_BLOCK, 0, ctx->stream>>>((const Key64 *)d_sorted, n, pshift, 0, 0, nullptr, (Key64 *)d_out, d_lb, d_ticket, 1u, d_count);
+        runs_kernel<Key64, false><<<(unsigned)grid, CQ_BLOCK, 0, ctx->stream>>>((const Key64 *)d_sorted, n, pshift, 0, 0, nullptr, (Key64 *)d_out, d_lb, d_ticket, 1u, d_count);
     else
-        resolve_kernel<Key128, false><<<(unsigned)grid, CP_BLOCK, 0, ctx->stream>>>((const Key128 *)d_sorted, n, pshift, 0, 0, nullptr, (Key128 *)d_out, d_lb, d_ticket, 1u, d_count);
+        runs_kernel<Key128, false><<<(unsigned)grid, CQ_BLOCK, 0, ctx->stream>>>((const Key128 *)d_sorted, n, pshift, 0, 0, nullptr, (Key128 *)d_out, d_lb, d_ticket, 1u, d_count);
     KHB_LAUNCH_CHECK(ctx);
     khb_prof_end(ctx, KHB_K_UNIQUE, 2 * (u64)n * (k <= 32 ? 8 : 16));
     return KHB_OK;
@@ -587,19 +495,19 @@ int khb_resolve_count_impl(khb_ctx *ctx, const void *d_sorted, size_t n, int k, 
     KHB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, ((size_t)nbins + 1) * sizeof(u64), ctx->stream));
     KHB_CUDA(ctx, cudaMemsetAsync(d_runs, 0, sizeof(u64), ctx->stream));
     if (n == 0) return KHB_OK;
-    const u64 ntiles = div_up(n, CQ_TILE);
+    const u64 ntiles = div_up(n, CQ_BLOCK * CQ_ITEMS);
     u64 *d_lb;
     u32 *d_ticket;
     int rc = compact_scratch(ctx, ntiles, &d_lb, &d_ticket);
     if (rc) return rc;
-    u64 grid = (u64)ctx->num_sms * 4;
+    u64 grid = (u64)ctx->num_sms * (k <= 32 ? 4 : 2);
     if (grid > ntiles) grid = ntiles;
     const size_t shm = ((size_t)nbins + 1) * sizeof(u32);
     khb_prof_begin(ctx, KHB_K_RLE);
     if (k <= 32)
-        count_prefix_kernel<Key64><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const Key64 *)d_sorted, n, pshift, cs, nbins, d_hist, (Key64 *)d_out_keys, d_lb, d_ticket, 1u, d_runs);
+        runs_kernel<Key64, true><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const Key64 *)d_sorted, n, pshift, cs, nbins, d_hist, (Key64 *)d_out_keys, d_lb, d_ticket, 1u, d_runs);
     else
-        count_prefix_kernel<Key128><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const Key128 *)d_sorted, n, pshift, cs, nbins, d_hist, (Key128 *)d_out_keys, d_lb, d_ticket, 1u, d_runs);
+        runs_kernel<Key128, true><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const Key128 *)d_sorted, n, pshift, cs, nbins, d_hist, (Key128 *)d_out_keys, d_lb, d_ticket, 1u, d_runs);
     KHB_LAUNCH_CHECK(ctx);
     khb_prof_end(ctx, KHB_K_RLE, (u64)n * (k <= 32 ? 8 : 16));
     return KHB_OK;

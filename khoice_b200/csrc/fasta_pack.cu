@@ -258,10 +258,10 @@ int khb_pack_fasta_impl(khb_ctx *ctx, const uint8_t *d_fasta, size_t nbytes, u64
 }
 
 int khb_fasta_separators_impl(khb_ctx *ctx, uint8_t *d_fasta, const u64 *d_file_begin, const u64 *d_file_len,
-                              int nfiles, u64 total_bytes)
+                              int nfiles, u64 total_bytes, cudaStream_t stream)
 {
     if (nfiles <= 0) return KHB_OK;
-    fasta_separator_kernel<<<nfiles, 256, 0, ctx->stream>>>(d_fasta, d_file_begin, d_file_len, nfiles, total_bytes);
+    fasta_separator_kernel<<<nfiles, 256, 0, stream>>>(d_fasta, d_file_begin, d_file_len, nfiles, total_bytes);
     KHB_LAUNCH_CHECK(ctx);
     return KHB_OK;
 }

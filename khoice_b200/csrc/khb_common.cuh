@@ -172,8 +172,18 @@ struct khb_ctx {
     // staging (fused host entry points)
     uint8_t *stage_dev;
     size_t stage_dev_cap;
-    uint8_t *stage_host;
-    size_t stage_host_cap;
+    // double-buffered ingestion (khb_group_prefetch_fasta): the next group's text is copied on copy_stream
+    // into stage_next while the current group is processed on `stream`
+    uint8_t *stage_next;
+    size_t stage_next_cap;
+    cudaStream_t copy_stream;
+    cudaEvent_t copy_done;
+    u64 *pf_tab;            // device table for the separator kernel of the prefetch
+    size_t pf_tab_cap;
+    int pf_valid, pf_n;
+    const void *pf_first;   // identity of the prefetched request: first file pointer, count, staged size
+    size_t pf_bytes;
+    struct khb_hostvec *pf_begin;
     // timing of the last fused call (ms, CUDA events on ctx->stream)
     float last_ms[8];
     // optional per-kernel timing (khb_profile_enable): CUDA event pairs around every launch

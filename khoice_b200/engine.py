@@ -80,6 +80,7 @@ _SIGNATURES = [
     ("khb_unique", C.c_int, [_P, _P, C.c_size_t, C.c_int, _P, C.POINTER(C.c_uint64)]),
     ("khb_count_runs", C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_uint32, C.c_uint32, _P, _P, _P, C.POINTER(C.c_uint64)]),
     ("khb_group_from_fasta", C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_uint32, _P, C.c_int, C.POINTER(Stats)]),
+    ("khb_group_prefetch_fasta", C.c_int, [_P, C.c_int, _P, _P]),
     ("khb_group_from_staged", C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_uint32, _P, C.c_int, C.POINTER(Stats)]),
     ("khb_across_groups", C.c_int, [_P, C.c_uint32, _P, C.POINTER(Stats)]),
     ("khb_group_sets_info", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
@@ -374,6 +375,13 @@ class Engine:
         st = Stats()
         self._chk(self.lib.khb_group_from_fasta(self.ctx, k, len(arrs), ptrs, sizes, nbins, hist.ctypes.data, int(keep_set), C.byref(st)))
         return hist, st.as_dict()
+
+    def prefetch_fasta(self, files: Sequence):
+        """Start the host->device copy of the NEXT group's FASTA texts on a second stream (double buffering).
+        The caller must keep `files` alive and unchanged until the matching group_from_fasta call."""
+        arrs, ptrs, sizes = self._file_tables(files)
+        self._pf_keepalive = getattr(self, "_pf_keepalive", [])[-2:] + [(arrs, ptrs, sizes)]
+        self._chk(self.lib.khb_group_prefetch_fasta(self.ctx, len(arrs), ptrs, sizes))
 
     def group_from_staged(self, staged: StagedFasta, k: int, nbins: int = COUNTER_MAX, keep_set: bool = True,
                           first: int = 0, count: Optional[int] = None):

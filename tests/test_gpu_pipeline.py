@@ -78,3 +78,28 @@ def test_config1_full_size_matches_oracle(engine, oracle):
     assert np.array_equal(hist, a_ref)
     # size-independent properties: every distinct k-mer is counted once; occupancy <= members
     assert int(hist.sum()) == st_ref["distinct"] and not hist[3:].any()
+
+
+def test_prefetch_double_buffering_gives_identical_results(engine):
+    rng = np.random.default_rng(12)
+    groups = [[random_fasta(rng, 30_000 + 1000 * j) for j in range(3)] for _ in range(4)]
+    ref = []
+    engine.group_sets_reset()
+    for grp in groups:
+        ref.append(engine.group_from_fasta(grp, 31)[0])
+    a_ref = engine.across_groups()[0]
+    engine.group_sets_reset()
+    views = [[np.frombuffer(f, dtype=np.uint8) for f in grp] for grp in groups]
+    engine.prefetch_fasta(views[0])
+    got = []
+    for i, grp in enumerate(views):
+        if i + 1 < len(views):
+            engine.prefetch_fasta(views[i + 1])       # deferred until the pending buffer has been taken over
+        got.append(engine.group_from_fasta(grp, 31)[0])
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)
+    assert np.array_equal(engine.across_groups()[0], a_ref)
+    # a prefetch that is never consumed must not leak into the next call
+    engine.group_sets_reset()
+    engine.prefetch_fasta(views[2])
+    assert np.array_equal(engine.group_from_fasta(views[1], 31, keep_set=False)[0], ref[1])
