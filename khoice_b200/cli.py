@@ -207,6 +207,64 @@ def kmc_tools_main(argv: List[str]) -> int:
     raise UsageError(f"kmc_tools {args[0]}: not supported by the khoice-b200 shim (exp type 1 uses transform and complex)")
 
 
+# ---- rule-granular fused commands (used by khoice_b200/workflow/exp_type_1.smk) ------------------------------
+def fused_group(k: int, genome_paths: List[str], hist_out: str, set_prefix: str, table_prefix: Optional[str] = None) -> None:
+    """Rules build_kmc_database_on_genome .. within_group_union_histogram + build_group_kmer_set for one (k, group)
+    in ONE process: step_4 histogram + the group's k-mer set (step_6 database, real; step_3 header-only)."""
+    eng = get_engine()
+    texts = [read_fasta(p) for p in genome_paths]
+    eng.group_sets_reset()
+    hist, st = eng.group_from_fasta(texts, k, nbins=HIST_ROWS, keep_set=True)
+    keys = eng.group_sets_download()
+    eng.group_sets_reset()
+    keys = np.sort(keys) if keys.ndim == 1 else keys[np.lexsort((keys[:, 0], keys[:, 1]))]
+    write_histogram_file(hist_out, hist, HIST_ROWS)
+    one = np.zeros(HIST_ROWS + 1, dtype=np.uint64)
+    one[1] = keys.shape[0]
+    kmcdb.write_db(set_prefix, k, keys, np.ones(keys.shape[0], np.uint32), one, COUNTER_MAX)
+    if table_prefix:
+        kmcdb.write_db(table_prefix, k, None, None, hist, COUNTER_MAX, n_keys=keys.shape[0])
+
+
+def fused_across(k: int, set_prefixes: List[str], hist_out: str, table_prefix: Optional[str] = None) -> None:
+    """Rules across_group_union + across_group_union_histogram for one k over the step_6 databases."""
+    eng = get_engine()
+    eng.group_sets_reset()
+    for p in set_prefixes:
+        db = kmcdb.read_db(p)
+        if db.k != k:
+            raise UsageError(f"{p}: built with k={db.k}, not {k}")
+        eng.group_sets_append_host(db.keys, k, 1)
+    hist, st = eng.across_groups(nbins=HIST_ROWS)
+    eng.group_sets_reset()
+    write_histogram_file(hist_out, hist, HIST_ROWS)
+    if table_prefix:
+        kmcdb.write_db(table_prefix, k, None, None, hist, COUNTER_MAX, n_keys=int(st["distinct"]))
+
+
+def khb_main(argv: List[str]) -> int:
+    import argparse
+    ap = argparse.ArgumentParser(prog="khb")
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    g = sub.add_parser("group")
+    g.add_argument("--k", type=int, required=True)
+    g.add_argument("--hist", required=True)
+    g.add_argument("--set", required=True, dest="set_prefix")
+    g.add_argument("--table", default=None)
+    g.add_argument("genomes", nargs="+")
+    a = sub.add_parser("across")
+    a.add_argument("--k", type=int, required=True)
+    a.add_argument("--hist", required=True)
+    a.add_argument("--table", default=None)
+    a.add_argument("sets", nargs="+")
+    ns = ap.parse_args(argv)
+    if ns.cmd == "group":
+        fused_group(ns.k, ns.genomes, ns.hist, ns.set_prefix, ns.table)
+    else:
+        fused_across(ns.k, ns.sets, ns.hist, ns.table)
+    return 0
+
+
 def _outputs_of(tool: str, argv: List[str]) -> List[str]:
     """Best-effort list of files a failed invocation may have started (for cleanup)."""
     outs = []
@@ -226,11 +284,13 @@ def _outputs_of(tool: str, argv: List[str]) -> List[str]:
 
 def main(argv: Optional[List[str]] = None) -> int:
     argv = list(sys.argv[1:] if argv is None else argv)
-    if not argv or argv[0] not in ("kmc", "kmc_tools"):
-        print("usage: python -m khoice_b200.cli <kmc|kmc_tools> ...", file=sys.stderr)
+    if not argv or argv[0] not in ("kmc", "kmc_tools", "khb"):
+        print("usage: python -m khoice_b200.cli <kmc|kmc_tools|khb> ...", file=sys.stderr)
         return 1
     tool, rest = argv[0], argv[1:]
     try:
+        if tool == "khb":
+            return khb_main(rest)
         return kmc_main(rest) if tool == "kmc" else kmc_tools_main(rest)
     except Exception as e:  # exit-code discipline at the process boundary
         print(f"{tool} (khoice-b200): {e}", file=sys.stderr)

@@ -257,42 +257,42 @@ rle_hist_kernel(const Key *__restrict__ in, u64 n, u32 cs, u32 nbins, u64 *__res
 // themselves, so equality inside a run is resolved by comparison.  Sentinels never share a prefix with a real key
 // (the plan covers the spare bit above 2k) and every genome segment ends with at least one sentinel, so a scan
 // never leaves its segment.
-// K4 / K5 / K6 on prefix-sorted input, blocked arrangement: every thread owns CQ_ITEMS CONSECUTIVE keys, so
-// head / tail detection and run lengths are register-to-register compares; one warp max-scan per thread (not
-// per key) carries the position of the last run head across threads.  At the tail t of every adjacent run
-// [h, t] of equal keys:
+// K4 / K5 / K6 on prefix-sorted input.  Blocked arrangement: every thread owns CQ_ITEMS CONSECUTIVE keys plus its
+// predecessor and successor, so heads / tails of adjacent runs and the prefix checks are register-to-register
+// compares; ONE warp max-scan per thread (not per key) carries the position of the last run head across threads,
+// and warp 0 finds the head of the run that is open at the tile start (run_head_before).  Every adjacent run
+// [h, t] of equal keys is accounted at its TAIL t in O(1):
+//   len    = t - h + 1
 //   first  = no key equal to in[t] precedes h inside the prefix run   (one compare unless the run is mixed)
-//   extra  = equal keys after t inside the prefix run                  (zero compares unless the run is mixed)
-// A prefix run is "mixed" when it holds more than one distinct value -- rare, because the prefix of a hashed
-// key is uniform and the plan gives it more slots than there are keys.  Runs that are `first` are emitted
-// (distinct keys, in input order) and, if COUNT, add hist[min(len + extra, cs)].
+//   extra  = equal keys after t inside the prefix run                  (nothing to do unless the run is mixed)
+// A prefix run is "mixed" when it holds more than one distinct value -- rare, because the prefix of a hashed key is
+// uniform and the plan gives it more slots than there are keys.  Runs that are `first` are emitted (the distinct
+// keys) and, if COUNT, add hist[min(len + extra, cs)].  A tile reserves its output range with ONE atomicAdd, so no
+// tile waits for another: the distinct keys come out in no particular order, which is all a set needs (the next
+// stage re-sorts them); histograms and counts are exact and deterministic.
 #define CQ_ITEMS 8
 template <typename Key, bool COUNT>
 __global__ void __launch_bounds__(CQ_BLOCK, sizeof(Key) == 8 ? 4 : 2)
 runs_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 nbins, u64 *__restrict__ hist,
-            Key *__restrict__ out_keys, u64 *__restrict__ lookback, u32 *__restrict__ ticket, u32 epoch,
-            u64 *__restrict__ d_runs)
+            Key *__restrict__ out_keys, u64 *__restrict__ d_cursor)
 {
     constexpr int TILE = CQ_BLOCK * CQ_ITEMS;
     extern __shared__ u32 sh_hist[];  // [nbins+1] when COUNT
     __shared__ u64 ws[33];
-    __shared__ u32 s_tile;
     __shared__ u64 s_base;
     __shared__ u64 s_head0;
     __shared__ u32 s_wlast[CQ_WARPS];
     const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const u64 ntiles = (n + TILE - 1) / TILE;
-    if (COUNT)
+    if (COUNT) {
         for (u32 i = tid; i <= nbins; i += CQ_BLOCK) sh_hist[i] = 0;
-    for (;;) {
-        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
         __syncthreads();
-        const u64 tile = s_tile;
-        if (tile >= ntiles) break;
+    }
+    for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const u64 begin = tile * TILE;
-        const u32 l0 = tid * CQ_ITEMS;     // local index of this thread's first key
+        const u32 l0 = tid * CQ_ITEMS;  // local index of this thread's first key
         const u64 g0 = begin + l0;
-        Key k[CQ_ITEMS + 2];               // k[0] = predecessor, k[1..ITEMS] = own keys, k[ITEMS+1] = successor
+        Key k[CQ_ITEMS + 2];            // k[0] = predecessor, k[1..ITEMS] = own keys, k[ITEMS+1] = successor
         if (g0 + CQ_ITEMS < n && g0 > 0) {
 #pragma unroll
             for (int j = 0; j < CQ_ITEMS + 2; j++) k[j] = in[g0 - 1 + j];
@@ -304,12 +304,12 @@ runs_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 nbins, u6
             }
         }
         if (warp == 0) {
-            Key k0 = shfl_key(k[1], 0);
+            // head of the run that is open at the tile start (only matters if the first key continues it)
+            const Key k0 = shfl_key(k[1], 0), kb = shfl_key(k[0], 0);
             u64 h0 = begin;
-            if (begin > 0 && begin < n && !key_is_sentinel(k0)) h0 = run_head_before(in, begin, k0, lane);
+            if (begin > 0 && begin < n && !key_is_sentinel(k0) && key_eq(k0, kb)) h0 = run_head_before(in, begin, k0, lane);
             if (lane == 0) s_head0 = h0;
         }
-        // heads and tails of adjacent runs inside this thread's keys
         u32 headm = 0, tailm = 0, lasth = 0;  // lasth = local index + 1 of the thread's last head
 #pragma unroll
         for (int j = 0; j < CQ_ITEMS; j++) {
@@ -322,7 +322,7 @@ runs_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 nbins, u6
             if (head) lasth = l0 + j + 1;
         }
         // last head before this thread: exclusive max-scan over the CTA
-        u32 inc = warp_incl_max<u32>(lasth);
+        const u32 inc = warp_incl_max<u32>(lasth);
         u32 carry = __shfl_up_sync(0xffffffffu, inc, 1);
         if (lane == 0) carry = 0;
         if (lane == 31) s_wlast[warp] = inc;
@@ -333,28 +333,36 @@ runs_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 nbins, u6
         const u64 head0 = s_head0;
         // resolve every tail
         u32 emitm = 0;
-        u32 cur = carry;  // local index + 1 of the head of the run open at key j (0: before the tile)
+        u32 cur = carry;          // local index + 1 of the head of the run open at key j (0: before the tile)
+        bool own = false;         // that head belongs to this thread -> its predecessor is in `pred`
+        Key pred = k[0];
 #pragma unroll
         for (int j = 0; j < CQ_ITEMS; j++) {
-            if ((headm >> j) & 1u) cur = l0 + j + 1;
+            if ((headm >> j) & 1u) { cur = l0 + j + 1; own = true; pred = k[j]; }
             if ((tailm >> j) & 1u) {
                 const Key key = k[j + 1];
                 const u64 g = g0 + j;
                 const u64 hg = cur ? begin + (cur - 1) : head0;
                 bool first = true;
-                u64 q = hg;
-                while (q > 0) {  // an earlier occurrence inside the prefix run?
-                    --q;
-                    const Key kq = in[q];
-                    if (!same_prefix(kq, key, pshift)) break;
-                    if (key_eq(kq, key)) { first = false; break; }
+                if (hg > 0) {
+                    const Key pk = own ? pred : in[hg - 1];
+                    if (!key_is_sentinel(pk) && same_prefix(pk, key, pshift)) {
+                        u64 q = hg - 1;  // in[q] differs from key but shares its prefix: mixed run, scan back
+                        while (q > 0) {
+                            --q;
+                            const Key kq = in[q];
+                            if (!same_prefix(kq, key, pshift)) break;
+                            if (key_eq(kq, key)) { first = false; break; }
+                        }
+                    }
                 }
                 if (first) {
                     emitm |= 1u << j;
                     if (COUNT) {
                         u64 len = g - hg + 1;
-                        if (g + 1 < n && !key_is_sentinel(k[j + 2]) && same_prefix(k[j + 2], key, pshift)) {
-                            for (u64 r = g + 1; r < n; r++) {  // later occurrences inside the prefix run
+                        const Key nk = k[j + 2];
+                        if (g + 1 < n && !key_is_sentinel(nk) && same_prefix(nk, key, pshift)) {
+                            for (u64 r = g + 2; r < n; r++) {  // later occurrences inside the prefix run
                                 const Key kr = in[r];
                                 if (!same_prefix(kr, key, pshift)) break;
                                 len += key_eq(kr, key) ? 1u : 0u;
@@ -369,22 +377,7 @@ runs_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 nbins, u6
         const u32 mine = __popc(emitm);
         u64 total;
         const u64 off = block_excl_sum<u64>((u64)mine, ws, &total);
-        if (warp == 0) {
-            u64 excl = 0;
-            if (out_keys != nullptr) {
-                if (tile == 0) {
-                    if (lane == 0) lb_store(lookback, lb_pack(LB_PREFIX, total, epoch));
-                } else {
-                    if (lane == 0) lb_store(lookback + tile, lb_pack(LB_AGG, total, epoch));
-                    excl = lb_walk_warp(lookback, tile, 0, epoch);
-                    if (lane == 0) lb_store(lookback + tile, lb_pack(LB_PREFIX, excl + total, epoch));
-                }
-            }
-            if (lane == 0) {
-                s_base = excl;
-                if (total) atomicAdd(d_runs, total);
-            }
-        }
+        if (tid == 0) s_base = total ? atomicAdd(d_cursor, total) : 0ull;
         __syncthreads();
         if (out_keys != nullptr && mine) {
             u64 pos = s_base + off;
@@ -463,30 +456,26 @@ int khb_count_runs_impl(khb_ctx *ctx, const void *d_sorted, size_t n, int k, u32
     return KHB_OK;
 }
 
-// K4 on prefix-sorted input: d_count <- number of distinct keys; d_out <- distinct keys in input order.
+// K4 on prefix-sorted input: d_count <- number of distinct keys; d_out <- the distinct keys (unordered).
 int khb_resolve_unique_impl(khb_ctx *ctx, const void *d_sorted, size_t n, int k, int pshift, void *d_out, u64 *d_count)
 {
     if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_resolve_unique: k=%d outside 1..64", k);
     KHB_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(u64), ctx->stream));
     if (n == 0) return KHB_OK;
     const u64 ntiles = div_up(n, CQ_BLOCK * CQ_ITEMS);
-    u64 *d_lb;
-    u32 *d_ticket;
-    int rc = compact_scratch(ctx, ntiles, &d_lb, &d_ticket);
-    if (rc) return rc;
-    u64 grid = (u64)ctx->num_sms * (k <= 32 ? 4 : 2);
+    u64 grid = (u64)ctx->num_sms * (k <= 32 ? 8 : 4);
     if (grid > ntiles) grid = ntiles;
     khb_prof_begin(ctx, KHB_K_UNIQUE);
     if (k <= 32)
-        runs_kernel<Key64, false><<<(unsigned)grid, CQ_BLOCK, 0, ctx->stream>>>((const Key64 *)d_sorted, n, pshift, 0, 0, nullptr, (Key64 *)d_out, d_lb, d_ticket, 1u, d_count);
+        runs_kernel<Key64, false><<<(unsigned)grid, CQ_BLOCK, 0, ctx->stream>>>((const Key64 *)d_sorted, n, pshift, 0, 0, nullptr, (Key64 *)d_out, d_count);
     else
-        runs_kernel<Key128, false><<<(unsigned)grid, CQ_BLOCK, 0, ctx->stream>>>((const Key128 *)d_sorted, n, pshift, 0, 0, nullptr, (Key128 *)d_out, d_lb, d_ticket, 1u, d_count);
+        runs_kernel<Key128, false><<<(unsigned)grid, CQ_BLOCK, 0, ctx->stream>>>((const Key128 *)d_sorted, n, pshift, 0, 0, nullptr, (Key128 *)d_out, d_count);
     KHB_LAUNCH_CHECK(ctx);
     khb_prof_end(ctx, KHB_K_UNIQUE, 2 * (u64)n * (k <= 32 ? 8 : 16));
     return KHB_OK;
 }
 
-// K5/K6 on prefix-sorted input: histogram of multiplicities (+ optional distinct keys).
+// K5/K6 on prefix-sorted input: histogram of multiplicities (+ optional distinct keys, unordered).
 int khb_resolve_count_impl(khb_ctx *ctx, const void *d_sorted, size_t n, int k, int pshift, u32 cs, u32 nbins, u64 *d_hist,
                            void *d_out_keys, u64 *d_runs)
 {
@@ -496,18 +485,14 @@ int khb_resolve_count_impl(khb_ctx *ctx, const void *d_sorted, size_t n, int k, 
     KHB_CUDA(ctx, cudaMemsetAsync(d_runs, 0, sizeof(u64), ctx->stream));
     if (n == 0) return KHB_OK;
     const u64 ntiles = div_up(n, CQ_BLOCK * CQ_ITEMS);
-    u64 *d_lb;
-    u32 *d_ticket;
-    int rc = compact_scratch(ctx, ntiles, &d_lb, &d_ticket);
-    if (rc) return rc;
-    u64 grid = (u64)ctx->num_sms * (k <= 32 ? 4 : 2);
+    u64 grid = (u64)ctx->num_sms * (k <= 32 ? 8 : 4);
     if (grid > ntiles) grid = ntiles;
     const size_t shm = ((size_t)nbins + 1) * sizeof(u32);
     khb_prof_begin(ctx, KHB_K_RLE);
     if (k <= 32)
-        runs_kernel<Key64, true><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const Key64 *)d_sorted, n, pshift, cs, nbins, d_hist, (Key64 *)d_out_keys, d_lb, d_ticket, 1u, d_runs);
+        runs_kernel<Key64, true><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const Key64 *)d_sorted, n, pshift, cs, nbins, d_hist, (Key64 *)d_out_keys, d_runs);
     else
-        runs_kernel<Key128, true><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const Key128 *)d_sorted, n, pshift, cs, nbins, d_hist, (Key128 *)d_out_keys, d_lb, d_ticket, 1u, d_runs);
+        runs_kernel<Key128, true><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const Key128 *)d_sorted, n, pshift, cs, nbins, d_hist, (Key128 *)d_out_keys, d_runs);
     KHB_LAUNCH_CHECK(ctx);
     khb_prof_end(ctx, KHB_K_RLE, (u64)n * (k <= 32 ? 8 : 16));
     return KHB_OK;

@@ -132,7 +132,7 @@ __device__ __forceinline__ u32 match_digit(u32 d)
     return peers;
 }
 
-template <typename Key, int BLOCK, int ITEMS, int MINB, int MATCH>
+template <typename Key, int BLOCK, int ITEMS, int MINB, int MATCH, int DIRECT>
 __global__ void __launch_bounds__(BLOCK, MINB)
 onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__restrict__ seg_off,
                 const u64 *__restrict__ seg_tile, int nseg, int pass_row, int shift, int npass,
@@ -145,8 +145,8 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
     static_assert(BLOCK >= 256, "256 digit threads needed");
     static_assert(TILE < 65536, "16-bit tile offsets");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Key *sorted = (Key *)smem_raw;                                             // [TILE]
-    unsigned short *wcnt = (unsigned short *)(smem_raw + sizeof(Key) * TILE);  // [NW][256]
+    Key *sorted = (Key *)smem_raw;                                             // [TILE] (absent when DIRECT)
+    unsigned short *wcnt = (unsigned short *)(smem_raw + (DIRECT ? 0 : sizeof(Key) * TILE));  // [NW][256]
     u32 *glob_off = (u32 *)(wcnt + NW * 256);                                  // [256] offset of sorted[j] in the segment, minus j
     u32 *ws = glob_off + 256;                                                  // [36] scan scratch
     u32 *mm = ws + 36;                                                         // [NW][256] peer masks (MATCH 2 only)
@@ -252,10 +252,12 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
     }
     __syncthreads();
     // reorder through shared memory
+    if (!DIRECT) {
 #pragma unroll
-    for (int r = 0; r < ITEMS; r++) {
-        const u32 d = key_digit(keys[r], shift);
-        sorted[wcnt[warp * 256 + d] + ((rank2[r >> 1] >> (16 * (r & 1))) & 0xffffu)] = keys[r];
+        for (int r = 0; r < ITEMS; r++) {
+            const u32 d = key_digit(keys[r], shift);
+            sorted[wcnt[warp * 256 + d] + ((rank2[r >> 1] >> (16 * (r & 1))) & 0xffffu)] = keys[r];
+        }
     }
     // finish the look-back (256 digit threads)
     if (tid < 256) {
@@ -288,8 +290,18 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
         glob_off[tid] = bin_base[((size_t)seg * npass + pass_row) * 256 + tid] + excl - dstart;
     }
     __syncthreads();
-    // coalesced store: position j of the sorted tile goes to segment offset glob_off[digit] + j
     Key *dst = out + seg_begin;
+    if (DIRECT) {
+        // scatter straight from registers: 8/16-byte stores to up to 32 runs per warp; L2 merges the sectors
+#pragma unroll
+        for (int r = 0; r < ITEMS; r++) {
+            const u32 d = key_digit(keys[r], shift);
+            const u32 j = wcnt[warp * 256 + d] + ((rank2[r >> 1] >> (16 * (r & 1))) & 0xffffu);
+            if (j < n) dst[glob_off[d] + j] = keys[r];
+        }
+        return;
+    }
+    // coalesced store: position j of the sorted tile goes to segment offset glob_off[digit] + j
 #pragma unroll 4
     for (u32 j = tid; j < n; j += BLOCK) {
         const Key key = sorted[j];
@@ -298,22 +310,22 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
-template <typename Key, int BLOCK, int ITEMS, int MINB, int MATCH>
+template <typename Key, int BLOCK, int ITEMS, int MINB, int MATCH, int DIRECT = 0>
 static int launch_passes(khb_ctx *ctx, Key *src, Key *dst, const u64 *d_off, const u64 *d_tile, int nseg, int npass, int first_bit,
                          u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket)
 {
     constexpr int TILE = BLOCK * ITEMS;
     constexpr int NW = BLOCK / 32;
-    const size_t shm = sizeof(Key) * TILE + NW * 256 * sizeof(unsigned short) + 256 * sizeof(u32) + 36 * sizeof(u32) +
+    const size_t shm = (DIRECT ? 0 : sizeof(Key) * TILE) + NW * 256 * sizeof(unsigned short) + 256 * sizeof(u32) + 36 * sizeof(u32) +
                        (MATCH == 2 ? NW * 256 * sizeof(u32) : 0);
     static bool attr_set = false;
     if (!attr_set) {
-        KHB_CUDA(ctx, cudaFuncSetAttribute(onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+        KHB_CUDA(ctx, cudaFuncSetAttribute(onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
         attr_set = true;
     }
     for (int pass = 0; pass < npass; pass++) {
         khb_prof_begin(ctx, KHB_K_ONESWEEP);
-        onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH><<<(unsigned)ntiles, BLOCK, shm, ctx->stream>>>(
+        onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH, DIRECT><<<(unsigned)ntiles, BLOCK, shm, ctx->stream>>>(
             src, dst, d_off, d_tile, nseg, pass, first_bit + 8 * pass, npass, d_hist, d_lb, d_ticket + pass, (u32)(pass + 1));
         KHB_LAUNCH_CHECK(ctx);
         khb_prof_end(ctx, KHB_K_ONESWEEP, 2 * n_keys * sizeof(Key));  // read + write every key once
@@ -327,7 +339,7 @@ static int sort_variant()
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("KHB_SORT_VARIANT");
-        v = e ? atoi(e) : 1;
+        v = e ? atoi(e) : 5;
     }
     return v;
 }
@@ -345,6 +357,10 @@ static u32 variant_tile(int v, size_t W)
     case 5: return 512 * 12;
     case 6: return 512 * 8;
     case 7: return 384 * 12;
+    case 8: return 512 * 12;
+    case 9: return 256 * 12;
+    case 10: return 256 * 12;
+    case 11: return 256 * 16;
     default: return 512 * 12;
     }
 }
@@ -357,7 +373,7 @@ template <>
 int dispatch_passes<Key64>(khb_ctx *ctx, int v, Key64 *src, Key64 *dst, const u64 *d_off, const u64 *d_tile, int nseg, int npass,
                            int first_bit, u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket)
 {
-#define GO(B, I, M, MT) return launch_passes<Key64, B, I, M, MT>(ctx, src, dst, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket)
+#define GO(B, I, M, MT, ...) return launch_passes<Key64, B, I, M, MT, ##__VA_ARGS__>(ctx, src, dst, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket)
     switch (v) {
     case 0: GO(512, 12, 2, 0);
     case 2: GO(512, 8, 3, 1);
@@ -366,7 +382,11 @@ int dispatch_passes<Key64>(khb_ctx *ctx, int v, Key64 *src, Key64 *dst, const u6
     case 5: GO(512, 12, 2, 2);
     case 6: GO(512, 8, 3, 2);
     case 7: GO(384, 12, 3, 2);
-    default: GO(512, 12, 2, 1);
+    case 8: GO(512, 12, 2, 2, 1);
+    case 9: GO(256, 12, 5, 2, 1);
+    case 10: GO(256, 12, 5, 1, 1);
+    case 11: GO(256, 16, 4, 2, 1);
+    default: GO(512, 12, 2, 2);
     }
 #undef GO
 }

@@ -167,9 +167,25 @@ def _rule_jobs(work_root: str, k_values: Sequence[str], num_datasets: int):
     return jobs
 
 
+def _fused_rule_jobs(work_root: str, k_values: Sequence[str], num_datasets: int):
+    """The two fused rules of khoice_b200/workflow/exp_type_1.smk (KHB_MODE=fused), as (rule, outputs, shell)."""
+    jobs = []
+    for k in k_values:
+        for num in range(1, num_datasets + 1):
+            ins = " ".join(p_genome(num, g) for g in genomes_of(work_root, num))
+            outs = [p_step4(k, num)] + [p + e for p in (p_step3(k, num), p_step6(k, num)) for e in (".kmc_pre", ".kmc_suf")]
+            jobs.append(("within_group_union_histogram", outs,
+                         f"khb group --k {k} --hist {p_step4(k, num)} --table {p_step3(k, num)} --set {p_step6(k, num)} {ins}"))
+        sets = " ".join(p_step6(k, n) for n in range(1, num_datasets + 1))
+        jobs.append(("across_group_union_histogram", [p_step8(k)] + [p_step7(k) + e for e in (".kmc_pre", ".kmc_suf")],
+                     f"khb across --k {k} --hist {p_step8(k)} --table {p_step7(k)} {sets}"))
+    return jobs
+
+
 def run_rules(work_root: str, num_datasets: int, k_values: Optional[Sequence] = None, subprocess_mode: bool = False,
-              engine: Optional[Engine] = None) -> Dict:
-    """Run every exp-1 rule instance separately through the kmc / kmc_tools shims."""
+              engine: Optional[Engine] = None, fused_rules: bool = False) -> Dict:
+    """Run every exp-1 rule instance separately through the kmc / kmc_tools shims (or, with fused_rules, the two
+    rule-granular fused commands of khoice_b200/workflow/exp_type_1.smk)."""
     k_values = [str(k) for k in (k_values or DEFAULT_K_VALUES)]
     write_complex_ops(work_root, k_values, num_datasets)
     cwd = os.getcwd()
@@ -181,7 +197,7 @@ def run_rules(work_root: str, num_datasets: int, k_values: Optional[Sequence] = 
         cli.set_engine(own)
     try:
         os.chdir(work_root)  # `workdir:` of the Snakefile (Snakefile:45)
-        for rule, outputs, shell in _rule_jobs(".", k_values, num_datasets):
+        for rule, outputs, shell in (_fused_rule_jobs if fused_rules else _rule_jobs)(".", k_values, num_datasets):
             if all(os.path.exists(o) for o in outputs):
                 skipped += 1
                 continue

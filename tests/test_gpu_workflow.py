@@ -16,7 +16,7 @@ def work_roots(tmp_path_factory):
     from khoice_b200 import synth
     cfg = synth.SynthConfig(n_groups=2, genomes_per_group=3, genome_len=40_000, seed=5)
     roots = {}
-    for mode in ("fused", "rules", "rules-subprocess"):
+    for mode in ("fused", "rules", "rules-subprocess", "smk-fused"):
         root = str(tmp_path_factory.mktemp(mode.replace("-", "_")))
         synth.write_dataset(cfg, root)
         roots[mode] = root
@@ -39,9 +39,10 @@ def test_three_modes_agree_with_oracle(engine, oracle, work_roots):
     pipeline.run_fused(roots["fused"], cfg.n_groups, K_VALUES, engine=engine)
     pipeline.run_rules(roots["rules"], cfg.n_groups, K_VALUES, engine=engine)
     pipeline.run_rules(roots["rules-subprocess"], cfg.n_groups, K_VALUES[:2] , subprocess_mode=True)
+    pipeline.run_rules(roots["smk-fused"], cfg.n_groups, K_VALUES, engine=engine, fused_rules=True)
     for k in K_VALUES:
         w_ref, a_ref, _ = _oracle_hists(oracle, cfg, int(k))
-        for mode in ("fused", "rules") + (("rules-subprocess",) if k in K_VALUES[:2] else ()):
+        for mode in ("fused", "rules", "smk-fused") + (("rules-subprocess",) if k in K_VALUES[:2] else ()):
             root = roots[mode]
             for num in range(1, cfg.n_groups + 1):
                 got = tables.read_histogram_file(os.path.join(root, pipeline.p_step4(k, num)))
@@ -51,6 +52,7 @@ def test_three_modes_agree_with_oracle(engine, oracle, work_roots):
             assert got == [int(x) for x in a_ref[1:]], (mode, k)
     for f in (pipeline.P_STEP5, pipeline.P_STEP9) + pipeline.P_FINAL:
         assert filecmp.cmp(os.path.join(roots["fused"], f), os.path.join(roots["rules"], f), shallow=False), f
+        assert filecmp.cmp(os.path.join(roots["fused"], f), os.path.join(roots["smk-fused"], f), shallow=False), f
     # every declared rule output exists in both modes (file DAG / resume semantics)
     for mode in ("fused", "rules"):
         root = roots[mode]
