@@ -26,7 +26,9 @@
 #define CP_ITEMS 8
 #define CP_TILE (CP_BLOCK * CP_ITEMS)
 // count_prefix_kernel: smaller CTAs, four per SM (latency-bound phases overlap across CTAs)
-#define CQ_BLOCK 256
+#ifndef CQ_BLOCK
+#define CQ_BLOCK 128
+#endif
 #define CQ_WARPS (CQ_BLOCK / 32)
 #define CQ_TILE (CQ_BLOCK * CP_ITEMS)
 
@@ -272,15 +274,13 @@ rle_hist_kernel(const Key *__restrict__ in, u64 n, u32 cs, u32 nbins, u64 *__res
 // stage re-sorts them); histograms and counts are exact and deterministic.
 #define CQ_ITEMS 8
 template <typename Key, bool COUNT>
-__global__ void __launch_bounds__(CQ_BLOCK, sizeof(Key) == 8 ? 4 : 2)
+__global__ void __launch_bounds__(CQ_BLOCK, (sizeof(Key) == 8 ? 1024 : 512) / CQ_BLOCK)
 runs_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 nbins, u64 *__restrict__ hist,
             Key *__restrict__ out_keys, u64 *__restrict__ d_cursor)
 {
     constexpr int TILE = CQ_BLOCK * CQ_ITEMS;
     extern __shared__ u32 sh_hist[];  // [nbins+1] when COUNT
-    __shared__ u64 ws[33];
-    __shared__ u64 s_base;
-    __shared__ u64 s_head0;
+    __shared__ int s_head0;           // head of the run open at the tile start, relative to the tile (<= 0)
     __shared__ u32 s_wlast[CQ_WARPS];
     const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const u64 ntiles = (n + TILE - 1) / TILE;
@@ -290,36 +290,46 @@ runs_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 nbins, u6
     }
     for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const u64 begin = tile * TILE;
+        const u32 nloc = (u32)(n - begin < (u64)TILE ? n - begin : (u64)TILE);  // keys of this tile
+        const bool last_tile = begin + TILE >= n;
         const u32 l0 = tid * CQ_ITEMS;  // local index of this thread's first key
-        const u64 g0 = begin + l0;
+        const Key *base = in + begin;
         Key k[CQ_ITEMS + 2];            // k[0] = predecessor, k[1..ITEMS] = own keys, k[ITEMS+1] = successor
-        if (g0 + CQ_ITEMS < n && g0 > 0) {
+        if (begin > 0 && !last_tile) {
 #pragma unroll
-            for (int j = 0; j < CQ_ITEMS + 2; j++) k[j] = in[g0 - 1 + j];
+            for (int j = 0; j < CQ_ITEMS + 2; j++) k[j] = base[(int)l0 - 1 + j];
         } else {
 #pragma unroll
             for (int j = 0; j < CQ_ITEMS + 2; j++) {
-                const u64 g = g0 + j;  // index + 1
+                const u64 g = begin + l0 + j;  // index + 1
                 k[j] = (g >= 1 && g - 1 < n) ? in[g - 1] : sentinel_key<Key>();
             }
         }
         if (warp == 0) {
-            // head of the run that is open at the tile start (only matters if the first key continues it)
-            const Key k0 = shfl_key(k[1], 0), kb = shfl_key(k[0], 0);
-            u64 h0 = begin;
-            if (begin > 0 && begin < n && !key_is_sentinel(k0) && key_eq(k0, kb)) h0 = run_head_before(in, begin, k0, lane);
+            // head of the run that is open at the tile start (only matters if the first key continues it).  The 32
+            // keys in front of the tile are fetched together with the tile itself, so the common case (runs shorter
+            // than 32 keys) costs no extra memory round trip.
+            Key back = sentinel_key<Key>();
+            if (begin > lane) back = in[begin - 1 - lane];
+            const Key k0 = shfl_key(k[1], 0);
+            int h0 = 0;
+            if (begin > 0 && !key_is_sentinel(k0)) {
+                const u32 diff = __ballot_sync(0xffffffffu, !(begin > lane && key_eq(back, k0)));
+                if (diff) h0 = -(int)(__ffs(diff) - 1);
+                else h0 = (int)((long long)run_head_before(in, begin - 32, k0, lane) - (long long)begin);
+            }
             if (lane == 0) s_head0 = h0;
         }
         u32 headm = 0, tailm = 0, lasth = 0;  // lasth = local index + 1 of the thread's last head
 #pragma unroll
         for (int j = 0; j < CQ_ITEMS; j++) {
-            const u64 g = g0 + j;
-            const bool valid = g < n && !key_is_sentinel(k[j + 1]);
-            const bool head = valid && (g == 0 || !key_eq(k[j + 1], k[j]));
-            const bool tail = valid && (g + 1 >= n || !key_eq(k[j + 1], k[j + 2]));
+            const u32 l = l0 + j;
+            const bool valid = l < nloc && !key_is_sentinel(k[j + 1]);
+            const bool head = valid && ((begin == 0 && l == 0) || !key_eq(k[j + 1], k[j]));
+            const bool tail = valid && (l + 1 >= nloc ? (last_tile || !key_eq(k[j + 1], k[j + 2])) : !key_eq(k[j + 1], k[j + 2]));
             headm |= (head ? 1u : 0u) << j;
             tailm |= (tail ? 1u : 0u) << j;
-            if (head) lasth = l0 + j + 1;
+            if (head) lasth = l + 1;
         }
         // last head before this thread: exclusive max-scan over the CTA
         const u32 inc = warp_incl_max<u32>(lasth);
@@ -330,24 +340,23 @@ runs_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 nbins, u6
         u32 wprefix = 0;
         for (u32 w = 0; w < warp; w++) wprefix = s_wlast[w] > wprefix ? s_wlast[w] : wprefix;
         carry = carry > wprefix ? carry : wprefix;
-        const u64 head0 = s_head0;
+        const int head0 = s_head0;
         // resolve every tail
         u32 emitm = 0;
-        u32 cur = carry;          // local index + 1 of the head of the run open at key j (0: before the tile)
-        bool own = false;         // that head belongs to this thread -> its predecessor is in `pred`
+        int cur = carry ? (int)carry - 1 : head0;  // local index of the head of the run open at key j
+        bool own = false;                          // that head belongs to this thread -> its predecessor is in `pred`
         Key pred = k[0];
 #pragma unroll
         for (int j = 0; j < CQ_ITEMS; j++) {
-            if ((headm >> j) & 1u) { cur = l0 + j + 1; own = true; pred = k[j]; }
+            if ((headm >> j) & 1u) { cur = (int)(l0 + j); own = true; pred = k[j]; }
             if ((tailm >> j) & 1u) {
                 const Key key = k[j + 1];
-                const u64 g = g0 + j;
-                const u64 hg = cur ? begin + (cur - 1) : head0;
                 bool first = true;
+                const long long hg = (long long)begin + cur;  // global index of the run's head
                 if (hg > 0) {
                     const Key pk = own ? pred : in[hg - 1];
                     if (!key_is_sentinel(pk) && same_prefix(pk, key, pshift)) {
-                        u64 q = hg - 1;  // in[q] differs from key but shares its prefix: mixed run, scan back
+                        u64 q = (u64)hg - 1;  // in[q] differs from key but shares its prefix: mixed run, scan back
                         while (q > 0) {
                             --q;
                             const Key kq = in[q];
@@ -359,8 +368,9 @@ runs_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 nbins, u6
                 if (first) {
                     emitm |= 1u << j;
                     if (COUNT) {
-                        u64 len = g - hg + 1;
+                        u32 len = (u32)((int)(l0 + j) - cur + 1);
                         const Key nk = k[j + 2];
+                        const u64 g = begin + l0 + j;
                         if (g + 1 < n && !key_is_sentinel(nk) && same_prefix(nk, key, pshift)) {
                             for (u64 r = g + 2; r < n; r++) {  // later occurrences inside the prefix run
                                 const Key kr = in[r];
@@ -368,24 +378,26 @@ runs_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 nbins, u6
                                 len += key_eq(kr, key) ? 1u : 0u;
                             }
                         }
-                        const u32 c = len > (u64)cs ? cs : (u32)len;
+                        const u32 c = len > cs ? cs : len;
                         if (c <= nbins) atomicAdd(&sh_hist[c], 1u);
                     }
                 }
             }
         }
+        // every WARP reserves its own output range with one atomicAdd (no CTA-wide scan, no CTA-wide wait)
         const u32 mine = __popc(emitm);
-        u64 total;
-        const u64 off = block_excl_sum<u64>((u64)mine, ws, &total);
-        if (tid == 0) s_base = total ? atomicAdd(d_cursor, total) : 0ull;
-        __syncthreads();
+        const u32 incl = warp_incl_sum<u32>(mine);
+        const u32 wtotal = __shfl_sync(0xffffffffu, incl, 31);
+        u64 wbase = 0;
+        if (lane == 31 && wtotal) wbase = atomicAdd(d_cursor, (u64)wtotal);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
         if (out_keys != nullptr && mine) {
-            u64 pos = s_base + off;
+            u64 pos = wbase + (incl - mine);
 #pragma unroll
             for (int j = 0; j < CQ_ITEMS; j++)
                 if ((emitm >> j) & 1u) out_keys[pos++] = k[j + 1];
         }
-        __syncthreads();
+        __syncthreads();  // s_wlast / s_head0 are rewritten by the next iteration
     }
     if (COUNT) {
         __syncthreads();
@@ -463,7 +475,7 @@ int khb_resolve_unique_impl(khb_ctx *ctx, const void *d_sorted, size_t n, int k,
     KHB_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(u64), ctx->stream));
     if (n == 0) return KHB_OK;
     const u64 ntiles = div_up(n, CQ_BLOCK * CQ_ITEMS);
-    u64 grid = (u64)ctx->num_sms * (k <= 32 ? 8 : 4);
+    u64 grid = (u64)ctx->num_sms * (k <= 32 ? 2048 : 1024) / CQ_BLOCK;
     if (grid > ntiles) grid = ntiles;
     khb_prof_begin(ctx, KHB_K_UNIQUE);
     if (k <= 32)
@@ -485,7 +497,7 @@ int khb_resolve_count_impl(khb_ctx *ctx, const void *d_sorted, size_t n, int k, 
     KHB_CUDA(ctx, cudaMemsetAsync(d_runs, 0, sizeof(u64), ctx->stream));
     if (n == 0) return KHB_OK;
     const u64 ntiles = div_up(n, CQ_BLOCK * CQ_ITEMS);
-    u64 grid = (u64)ctx->num_sms * (k <= 32 ? 8 : 4);
+    u64 grid = (u64)ctx->num_sms * (k <= 32 ? 2048 : 1024) / CQ_BLOCK;
     if (grid > ntiles) grid = ntiles;
     const size_t shm = ((size_t)nbins + 1) * sizeof(u32);
     khb_prof_begin(ctx, KHB_K_RLE);

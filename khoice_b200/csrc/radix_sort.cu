@@ -132,7 +132,69 @@ __device__ __forceinline__ u32 match_digit(u32 d)
     return peers;
 }
 
-template <typename Key, int BLOCK, int ITEMS, int MINB, int MATCH, int DIRECT>
+// Walk back over the predecessors of tile `rel` in one digit column until an inclusive prefix is found, then
+// publish this tile's inclusive prefix.  win[] holds the LBW nearest predecessors (already fetched); further hops
+// fetch LBW2 entries at a time (independent loads in flight).  Returns the exclusive prefix.
+template <int LBW>
+__device__ __forceinline__ u32 lookback_finish(u64 *lbcol, u64 rel, const u64 (&win)[LBW], u32 count, u32 epoch)
+{
+    u32 excl = 0;
+    if (rel == 0) return 0;
+    constexpr int LBW2 = 8;
+    u64 r0 = rel;  // entries [0, r0) remain to be examined, nearest first
+    bool done = false;
+#pragma unroll
+    for (int i = 0; i < LBW; i++) {
+        if (done || r0 <= (u64)i) continue;
+        u64 e = win[i];
+        u32 st = lb_status(e, epoch);
+        while (st == 0) {
+            e = lb_load(lbcol + (r0 - 1 - i) * 256);
+            st = lb_status(e, epoch);
+        }
+        excl += (u32)e;
+        if (st == LB_PREFIX) done = true;
+    }
+    if (r0 <= LBW) done = true;
+    r0 = r0 > LBW ? r0 - LBW : 0;
+    while (!done) {
+        u64 w8[LBW2];
+#pragma unroll
+        for (int i = 0; i < LBW2; i++) w8[i] = (r0 > (u64)i) ? lb_load(lbcol + (r0 - 1 - i) * 256) : 0ull;
+#pragma unroll
+        for (int i = 0; i < LBW2; i++) {
+            if (done || r0 <= (u64)i) continue;
+            u64 e = w8[i];
+            u32 st = lb_status(e, epoch);
+            while (st == 0) {
+                e = lb_load(lbcol + (r0 - 1 - i) * 256);
+                st = lb_status(e, epoch);
+            }
+            excl += (u32)e;
+            if (st == LB_PREFIX) done = true;
+        }
+        if (r0 <= LBW2) done = true;
+        r0 = r0 > LBW2 ? r0 - LBW2 : 0;
+    }
+    lb_store(lbcol + rel * 256, lb_pack(LB_PREFIX, (u64)excl + count, epoch));
+    return excl;
+}
+
+#ifdef KHB_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define PHASE_MARK(i)                                                      \
+    do {                                                                   \
+        if (threadIdx.x == 0) {                                            \
+            const long long now__ = clock64();                             \
+            atomicAdd(&g_phase_cycles[i], (unsigned long long)(now__ - t_prev__)); \
+            t_prev__ = now__;                                              \
+        }                                                                  \
+    } while (0)
+#else
+#define PHASE_MARK(i)
+#endif
+
+template <typename Key, int BLOCK, int ITEMS, int MINB, int MATCH, int DIRECT, int EARLY>
 __global__ void __launch_bounds__(BLOCK, MINB)
 onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__restrict__ seg_off,
                 const u64 *__restrict__ seg_tile, int nseg, int pass_row, int shift, int npass,
@@ -149,19 +211,25 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
     unsigned short *wcnt = (unsigned short *)(smem_raw + (DIRECT ? 0 : sizeof(Key) * TILE));  // [NW][256]
     u32 *glob_off = (u32 *)(wcnt + NW * 256);                                  // [256] offset of sorted[j] in the segment, minus j
     u32 *ws = glob_off + 256;                                                  // [36] scan scratch
-    u32 *mm = ws + 36;                                                         // [NW][256] peer masks (MATCH 2 only)
+    u32 *mm = ws + 36;                                                         // [NW][256] peer masks (MATCH >= 2 only)
+    u32 *tcnt = mm + (MATCH >= 2 ? NW * 256 : 0);                              // [256] early tile digit counts (EARLY only)
     __shared__ u32 s_tile;
     __shared__ int s_seg;
 
     const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+#ifdef KHB_PHASE_TIMING
+    long long t_prev__ = clock64();
+#endif
     if (tid == 0) {
         const u32 t = atomicAdd(ticket, 1u);
         s_tile = t;
         s_seg = find_segment(seg_tile, nseg, t);
     }
     for (int i = tid; i < NW * 256 / 2; i += BLOCK) ((u32 *)wcnt)[i] = 0;
-    if (MATCH == 2)
+    if (MATCH >= 2)
         for (int i = tid; i < NW * 256; i += BLOCK) mm[i] = 0;
+    if (EARLY)
+        for (int i = tid; i < 256; i += BLOCK) tcnt[i] = 0;
     __syncthreads();
     const u64 tile = s_tile;
     const int seg = s_seg;
@@ -171,6 +239,7 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
     const u64 begin = seg_begin + rel * TILE;
     const u64 seg_end = seg_off[seg + 1];
     const u32 n = (u32)(seg_end - begin < (u64)TILE ? seg_end - begin : (u64)TILE);
+    PHASE_MARK(0);  // ticket + segment lookup
 
     // load: warp-striped, memory order = (warp, item, lane)
     Key keys[ITEMS];
@@ -186,23 +255,63 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
 #pragma unroll
         for (int r = 0; r < ITEMS; r++) keys[r] = (wbase + r * 32 + lane < n) ? src[r * 32] : key_max<Key>();
     }
+#ifdef KHB_PHASE_TIMING
+    if (tid == 0 && key_digit(keys[0], 0) == 999u) g_phase_cycles[15] = 1;  // force the loads to complete here
+#endif
+    PHASE_MARK(1);  // key loads
+    // EARLY: count the tile's digits with plain shared-memory atomics and publish the aggregate BEFORE the (much
+    // longer) stable ranking, so that successors never wait for this tile's ranking and the prefix chain resolves
+    // while everybody is still ranking.
+    u32 count = 0, dstart = 0, excl = 0;
+    u64 *lbcol = lookback + first_tile * 256 + tid;  // column `tid` of the segment's look-back rows
+    u64 win[LBW];
+    if (EARLY) {
+#pragma unroll
+        for (int r = 0; r < ITEMS; r++) atomicAdd(&tcnt[key_digit(keys[r], shift)], 1u);
+        __syncthreads();
+        if (tid < 256) count = tcnt[tid];
+        u32 total0;
+        dstart = block_excl_sum<u32>(count, ws, &total0);
+        if (tid < 256) {
+            if (tid == 255) count -= (u32)(TILE - n);  // padding is not data
+            lb_store(lbcol + rel * 256, lb_pack(rel == 0 ? LB_PREFIX : LB_AGG, count, epoch));
+#pragma unroll
+            for (int i = 0; i < LBW; i++) win[i] = (rel > (u64)i) ? lb_load(lbcol + (rel - 1 - i) * 256) : 0ull;
+            // EARLY 2: resolve the chain NOW -- the inclusive prefix of this tile is published a few thousand cycles
+            // after its ticket instead of after ranking + reorder, so the frontier stays close behind the newest tile
+            if (EARLY == 2) excl = lookback_finish<LBW>(lbcol, rel, win, count, epoch);
+        }
+    }
     // rank within the warp's chunk (stable)
     unsigned short *mycnt = wcnt + warp * 256;
-    if (MATCH == 2) {
-        // peers through shared memory: every lane ORs its lane bit into the word of its digit
+    if (MATCH >= 2) {
+        // peers through shared memory: every lane ORs its lane bit into the word of its digit.  MATCH 3 / 4 send
+        // every 2nd / 3rd round through eight ballots instead, to balance the shared-memory pipe against the ALUs.
         u32 *mymm = mm + warp * 256;
         const u32 lbit = 1u << lane;
+        u32 bpeers[ITEMS];
 #pragma unroll
         for (int r = 0; r < ITEMS; r++) {
+            const bool by_ballot = (MATCH == 3 && (r & 1)) || (MATCH == 4 && (r % 3) == 0);
+            bpeers[r] = by_ballot ? match_digit<1>(key_digit(keys[r], shift)) : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < ITEMS; r++) {
+            const bool by_ballot = (MATCH == 3 && (r & 1)) || (MATCH == 4 && (r % 3) == 0);
             const u32 d = key_digit(keys[r], shift);
-            atomicOr(&mymm[d], lbit);
-            __syncwarp();
-            const u32 peers = mymm[d];
+            u32 peers;
+            if (by_ballot) {
+                peers = bpeers[r];
+            } else {
+                atomicOr(&mymm[d], lbit);
+                __syncwarp();
+                peers = mymm[d];
+            }
             const u32 c = mycnt[d];
             __syncwarp();
             const u32 below = __popc(peers & lanemask_lt());
             if (below == 0) {
-                mymm[d] = 0;
+                if (!by_ballot) mymm[d] = 0;
                 mycnt[d] = (unsigned short)(c + __popc(peers));
             }
             rank2[r >> 1] |= (c + below) << (16 * (r & 1));
@@ -223,18 +332,19 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
             __syncwarp();
         }
     }
+    PHASE_MARK(2);  // ranking (warp 0)
     __syncthreads();
+    PHASE_MARK(3);  // wait for the other warps
     // per digit: exclusive scan across warps -> tile count
-    u32 count = 0;
-    if (tid < 256) {
+    if (!EARLY) {
+        if (tid < 256) {
 #pragma unroll
-        for (int w = 0; w < NW; w++) count += wcnt[w * 256 + tid];
+            for (int w = 0; w < NW; w++) count += wcnt[w * 256 + tid];
+        }
+        // exclusive scan across digits (padding keys of a partial tile carry digit 255 and stay at the end)
+        u32 total;
+        dstart = block_excl_sum<u32>(count, ws, &total);
     }
-    // exclusive scan across digits (padding keys of a partial tile carry digit 255 and stay at the end)
-    u32 total;
-    const u32 dstart = block_excl_sum<u32>(count, ws, &total);
-    u64 *lbcol = lookback + first_tile * 256 + tid;  // column `tid` of the segment's look-back rows
-    u64 win[LBW];
     if (tid < 256) {
         // per-warp start of every digit inside the sorted tile
         u32 run = dstart;
@@ -244,12 +354,15 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
             wcnt[w * 256 + tid] = (unsigned short)run;
             run += c;
         }
-        if (tid == 255) count -= (u32)(TILE - n);  // padding is not data
-        lb_store(lbcol + rel * 256, lb_pack(rel == 0 ? LB_PREFIX : LB_AGG, count, epoch));
-        // first window of predecessors: issued now, consumed after the reorder below
+        if (!EARLY) {
+            if (tid == 255) count -= (u32)(TILE - n);  // padding is not data
+            lb_store(lbcol + rel * 256, lb_pack(rel == 0 ? LB_PREFIX : LB_AGG, count, epoch));
+            // first window of predecessors: issued now, consumed after the reorder below
 #pragma unroll
-        for (int i = 0; i < LBW; i++) win[i] = (rel > (u64)i) ? lb_load(lbcol + (rel - 1 - i) * 256) : 0ull;
+            for (int i = 0; i < LBW; i++) win[i] = (rel > (u64)i) ? lb_load(lbcol + (rel - 1 - i) * 256) : 0ull;
+        }
     }
+    PHASE_MARK(4);  // scans + publish
     __syncthreads();
     // reorder through shared memory
     if (!DIRECT) {
@@ -259,37 +372,15 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
             sorted[wcnt[warp * 256 + d] + ((rank2[r >> 1] >> (16 * (r & 1))) & 0xffffu)] = keys[r];
         }
     }
-    // finish the look-back (256 digit threads)
+    PHASE_MARK(5);  // reorder
+    // finish the look-back (256 digit threads) unless it already ran right after the early count (EARLY 2)
     if (tid < 256) {
-        u32 excl = 0;
-        if (rel != 0) {
-            u64 r0 = rel;  // entries [0, r0) remain
-            bool done = false;
-            while (!done) {
-#pragma unroll
-                for (int i = 0; i < LBW; i++) {
-                    if (done || r0 <= (u64)i) continue;
-                    u64 e = win[i];
-                    u32 st = lb_status(e, epoch);
-                    while (st == 0) {
-                        e = lb_load(lbcol + (r0 - 1 - i) * 256);
-                        st = lb_status(e, epoch);
-                    }
-                    excl += (u32)e;
-                    if (st == LB_PREFIX) done = true;
-                }
-                if (r0 <= LBW) done = true;
-                if (!done) {
-                    r0 -= LBW;
-#pragma unroll
-                    for (int i = 0; i < LBW; i++) win[i] = (r0 > (u64)i) ? lb_load(lbcol + (r0 - 1 - i) * 256) : 0ull;
-                }
-            }
-            lb_store(lbcol + rel * 256, lb_pack(LB_PREFIX, (u64)excl + count, epoch));
-        }
+        if (EARLY != 2) excl = lookback_finish<LBW>(lbcol, rel, win, count, epoch);
         glob_off[tid] = bin_base[((size_t)seg * npass + pass_row) * 256 + tid] + excl - dstart;
     }
+    PHASE_MARK(6);  // look-back (thread 0's column)
     __syncthreads();
+    PHASE_MARK(7);  // wait for all look-backs
     Key *dst = out + seg_begin;
     if (DIRECT) {
         // scatter straight from registers: 8/16-byte stores to up to 32 runs per warp; L2 merges the sectors
@@ -307,30 +398,47 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
         const Key key = sorted[j];
         dst[glob_off[key_digit(key, shift)] + j] = key;
     }
+    PHASE_MARK(8);  // store
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
-template <typename Key, int BLOCK, int ITEMS, int MINB, int MATCH, int DIRECT = 0>
+template <typename Key, int BLOCK, int ITEMS, int MINB, int MATCH, int DIRECT = 0, int EARLY = 0>
 static int launch_passes(khb_ctx *ctx, Key *src, Key *dst, const u64 *d_off, const u64 *d_tile, int nseg, int npass, int first_bit,
                          u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket)
 {
     constexpr int TILE = BLOCK * ITEMS;
     constexpr int NW = BLOCK / 32;
     const size_t shm = (DIRECT ? 0 : sizeof(Key) * TILE) + NW * 256 * sizeof(unsigned short) + 256 * sizeof(u32) + 36 * sizeof(u32) +
-                       (MATCH == 2 ? NW * 256 * sizeof(u32) : 0);
+                       (MATCH >= 2 ? NW * 256 * sizeof(u32) : 0) + (EARLY ? 256 * sizeof(u32) : 0);
     static bool attr_set = false;
     if (!attr_set) {
-        KHB_CUDA(ctx, cudaFuncSetAttribute(onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+        KHB_CUDA(ctx, cudaFuncSetAttribute(onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH, DIRECT, EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
         attr_set = true;
     }
     for (int pass = 0; pass < npass; pass++) {
         khb_prof_begin(ctx, KHB_K_ONESWEEP);
-        onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH, DIRECT><<<(unsigned)ntiles, BLOCK, shm, ctx->stream>>>(
+        onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH, DIRECT, EARLY><<<(unsigned)ntiles, BLOCK, shm, ctx->stream>>>(
             src, dst, d_off, d_tile, nseg, pass, first_bit + 8 * pass, npass, d_hist, d_lb, d_ticket + pass, (u32)(pass + 1));
         KHB_LAUNCH_CHECK(ctx);
         khb_prof_end(ctx, KHB_K_ONESWEEP, 2 * n_keys * sizeof(Key));  // read + write every key once
         Key *t = src; src = dst; dst = t;
     }
+#ifdef KHB_PHASE_TIMING
+    {
+        unsigned long long h[16];
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpyFromSymbol(h, g_phase_cycles, sizeof(h));
+        unsigned long long tot = 0;
+        for (int i = 0; i < 9; i++) tot += h[i];
+        const char *names[9] = {"ticket+seg", "load", "rank", "sync1", "scan+publish", "reorder", "lookback", "sync2", "store"};
+        fprintf(stderr, "[phase] tiles*passes=%llu avg cycles/tile:", (unsigned long long)(ntiles * npass));
+        for (int i = 0; i < 9; i++) fprintf(stderr, " %s=%.0f", names[i], (double)h[i] / (double)(ntiles * npass));
+        fprintf(stderr, " total=%.0f | per tile: wide hops=%.2f wide spins=%.2f wide entries=%.2f first-window spins=%.2f\n", (double)tot / (double)(ntiles * npass),
+                (double)h[10] / (ntiles * npass), (double)h[11] / (ntiles * npass), (double)h[12] / (ntiles * npass), (double)h[13] / (ntiles * npass));
+        memset(h, 0, sizeof(h));
+        cudaMemcpyToSymbol(g_phase_cycles, h, sizeof(h));
+    }
+#endif
     return KHB_OK;
 }
 
@@ -347,22 +455,9 @@ static int sort_variant()
 // tile size (keys) of the scatter-pass variant `v` for key width W
 static u32 variant_tile(int v, size_t W)
 {
-    if (W == 16) return v == 2 ? 256 * 8 : 512 * 6;
-    switch (v) {
-    case 0: return 512 * 12;
-    case 1: return 512 * 12;
-    case 2: return 512 * 8;
-    case 3: return 384 * 12;
-    case 4: return 256 * 16;
-    case 5: return 512 * 12;
-    case 6: return 512 * 8;
-    case 7: return 384 * 12;
-    case 8: return 512 * 12;
-    case 9: return 256 * 12;
-    case 10: return 256 * 12;
-    case 11: return 256 * 16;
-    default: return 512 * 12;
-    }
+    if (W == 16) return 512 * 6;
+    (void)v;
+    return 512 * 12;
 }
 
 template <typename Key>
@@ -375,18 +470,11 @@ int dispatch_passes<Key64>(khb_ctx *ctx, int v, Key64 *src, Key64 *dst, const u6
 {
 #define GO(B, I, M, MT, ...) return launch_passes<Key64, B, I, M, MT, ##__VA_ARGS__>(ctx, src, dst, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket)
     switch (v) {
-    case 0: GO(512, 12, 2, 0);
-    case 2: GO(512, 8, 3, 1);
-    case 3: GO(384, 12, 3, 1);
-    case 4: GO(256, 16, 4, 1);
-    case 5: GO(512, 12, 2, 2);
-    case 6: GO(512, 8, 3, 2);
-    case 7: GO(384, 12, 3, 2);
-    case 8: GO(512, 12, 2, 2, 1);
-    case 9: GO(256, 12, 5, 2, 1);
-    case 10: GO(256, 12, 5, 1, 1);
-    case 11: GO(256, 16, 4, 2, 1);
-    default: GO(512, 12, 2, 2);
+    case 0: GO(512, 12, 2, 0);         // MATCH.ANY            (1.46 TB/s: ~1 MATCH.ANY per 100 cycles per SM)
+    case 1: GO(512, 12, 2, 1);         // eight ballots         (2.33 TB/s: ALU-bound, 3.9 warp-instr/key)
+    case 13: GO(512, 12, 2, 4);        // every 3rd round by ballots, the others by atomicOr (2.64 TB/s)
+    case 18: GO(512, 12, 2, 2, 0, 2);  // early count + early look-back (2.45 TB/s)
+    default: GO(512, 12, 2, 2);        // shared-memory atomicOr peer masks (2.57 TB/s) -- default
     }
 #undef GO
 }
@@ -395,8 +483,8 @@ template <>
 int dispatch_passes<Key128>(khb_ctx *ctx, int v, Key128 *src, Key128 *dst, const u64 *d_off, const u64 *d_tile, int nseg, int npass,
                             int first_bit, u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket)
 {
-    if (v == 2) return launch_passes<Key128, 256, 8, 3, 1>(ctx, src, dst, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket);
-    return launch_passes<Key128, 512, 6, 2, 1>(ctx, src, dst, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket);
+    (void)v;
+    return launch_passes<Key128, 512, 6, 2, 2>(ctx, src, dst, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket);
 }
 
 template <typename Key>
