@@ -20,7 +20,7 @@ def test_random_text_groups_match_oracle(engine, oracle, groups, k):
     for i, grp in enumerate(bgroups):
         hist, stats = engine.group_from_fasta(grp, k)
         assert np.array_equal(hist, w_ref[i])
-    hist, stats = engine.across_groups() if st_ref["sum_group_distinct"] or True else (None, None)
+    hist, stats = engine.across_groups()
     assert np.array_equal(hist, a_ref)
 
 
