@@ -16,12 +16,13 @@ struct khb_hostvec {
     std::vector<size_t> d_sizes;
     bool deferred = false;
 };
-int khb_extract_kmers_impl(khb_ctx *, const u64 *, const u32 *, size_t, int, int, void *);
+int khb_extract_kmers_impl(khb_ctx *, const u64 *, const u32 *, size_t, int, int, void *, unsigned short *, const u64 *, int);
 int khb_remix_impl(khb_ctx *, void *, size_t, int, int);
 int khb_sort_keys_impl(khb_ctx *, void *, void *, const u64 *, int, int, int *);
-int khb_sort_bits_impl(khb_ctx *, void *, void *, const u64 *, int, int, int, int, int *);
+int khb_sort_bits_impl(khb_ctx *, void *, void *, const u64 *, int, int, int, int, int *, unsigned short *, unsigned short *);
 int khb_resolve_unique_impl(khb_ctx *, const void *, size_t, int, int, void *, u64 *);
 int khb_resolve_count_impl(khb_ctx *, const void *, size_t, int, int, u32, u32, u64 *, void *, u64 *);
+int khb_pairs_count_impl(khb_ctx *, const void *, const unsigned short *, size_t, int, int, u32, u32, u64 *, void *, u64 *, u64 *);
 int khb_unique_impl(khb_ctx *, const void *, size_t, int, void *, u64 *);
 int khb_count_runs_impl(khb_ctx *, const void *, size_t, int, u32, u32, u64 *, void *, u32 *, u64 *);
 
@@ -164,7 +165,7 @@ int khb_destroy(khb_ctx *ctx)
     if (!ctx) return KHB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < KHB_NSCRATCH; i++)
         if (ctx->scratch[i].ptr) cudaFree(ctx->scratch[i].ptr);
     if (ctx->gs_buf) cudaFree(ctx->gs_buf);
     if (ctx->stage_dev) cudaFree(ctx->stage_dev);
@@ -342,13 +343,13 @@ int khb_pack_fasta(khb_ctx *ctx, const uint8_t *d_fasta, size_t nbytes, uint64_t
 int khb_extract_kmers(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, size_t n_symbols, int k, void *d_keys)
 {
     KHB_CHECK_CTX(ctx);
-    return khb_extract_kmers_impl(ctx, (const u64 *)d_codes, d_valid, n_symbols, k, 0, d_keys);
+    return khb_extract_kmers_impl(ctx, (const u64 *)d_codes, d_valid, n_symbols, k, 0, d_keys, nullptr, nullptr, 0);
 }
 
 int khb_extract_kmers_hashed(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, size_t n_symbols, int k, void *d_keys)
 {
     KHB_CHECK_CTX(ctx);
-    return khb_extract_kmers_impl(ctx, (const u64 *)d_codes, d_valid, n_symbols, k, 1, d_keys);
+    return khb_extract_kmers_impl(ctx, (const u64 *)d_codes, d_valid, n_symbols, k, 1, d_keys, nullptr, nullptr, 0);
 }
 
 int khb_remix_keys(khb_ctx *ctx, void *d_keys, size_t n, int k, int inverse)
@@ -384,7 +385,7 @@ int khb_sort_key_bits(khb_ctx *ctx, void *d_keys, void *d_tmp, const uint64_t *h
     KHB_CHECK_CTX(ctx);
     int dummy;
     return khb_sort_bits_impl(ctx, d_keys, d_tmp, (const u64 *)h_seg_off, n_segments, key_bytes, first_bit, npass,
-                              result_in_tmp ? result_in_tmp : &dummy);
+                              result_in_tmp ? result_in_tmp : &dummy, nullptr, nullptr);
 }
 
 int khb_resolve_unique(khb_ctx *ctx, const void *d_sorted, size_t n, int k, int prefix_shift, void *d_out, uint64_t *h_count)
@@ -626,7 +627,67 @@ static int group_from_staged_impl(khb_ctx *ctx, int k, int n_genomes, const uint
     void *bufA = p;
     if ((rc = khb_scratch_get(ctx, SCR_KEYS_B, key_bytes, &p))) return rc;
     void *bufB = p;
-    if ((rc = khb_extract_kmers_impl(ctx, d_codes, d_valid, n_sym, k, hashed, bufA))) return rc;
+    static int single_sort = -1;
+    if (single_sort < 0) {
+        const char *e = getenv("KHB_GROUP_MODE");
+        single_sort = (e && strcmp(e, "two-sort") == 0) ? 0 : 1;
+    }
+    if (single_sort && n_genomes <= 65535) {
+        // ---- single-sort path: ONE prefix sort of all windows of the group with the genome id as payload ----
+        if ((rc = khb_scratch_get(ctx, SCR_PAY_A, (n_sym + 8) * 2, &p))) return rc;
+        unsigned short *payA = (unsigned short *)p;
+        if ((rc = khb_scratch_get(ctx, SCR_PAY_B, (n_sym + 8) * 2, &p))) return rc;
+        unsigned short *payB = (unsigned short *)p;
+        std::vector<u64> seg(n_genomes + 1);
+        for (int g = 0; g < n_genomes; g++) seg[g] = tile_base[h_begin[g] / KHB_FASTA_TILE];
+        seg[0] = 0;
+        seg[n_genomes] = n_sym;
+        u64 *d_seg = ctx->d_mail + 32768;  // up to 65536 offsets fit the 1 MiB mailbox behind the histogram area
+        if ((size_t)(n_genomes + 1) > 65536) return khb_fail(ctx, KHB_ERR_ARG, "too many genomes in one group");
+        KHB_CUDA(ctx, cudaMemcpyAsync(d_seg, seg.data(), (size_t)(n_genomes + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // seg is pageable
+        if ((rc = khb_extract_kmers_impl(ctx, d_codes, d_valid, n_sym, k, hashed, bufA, payA, d_seg, n_genomes))) return rc;
+        tm.mark();  // 3: extract done
+        int fb, np;
+        khb_prefix_plan(k, n_sym, &fb, &np);
+        u64 one_seg[2] = {0, n_sym};
+        int in_tmp = 0;
+        if ((rc = khb_sort_bits_impl(ctx, bufA, bufB, one_seg, 1, (int)W, fb, np, &in_tmp, payA, payB))) return rc;
+        void *sorted = in_tmp ? bufB : bufA;
+        unsigned short *spay = in_tmp ? payB : payA;
+        tm.mark();  // 4: sort done
+        tm.mark();  // 5
+        tm.mark();  // 6
+        void *out_keys = nullptr;
+        if (keep_set) {
+            // upper bound for the distinct keys of the group: every window distinct
+            if ((rc = gs_reserve(ctx, k, n_sym))) return rc;
+            ctx->gs_hashed = hashed;
+            out_keys = (char *)ctx->gs_buf + ctx->gs_len * W;
+        }
+        u64 *d_hist = ctx->d_mail + 8, *d_runs = ctx->d_mail, *d_pairs = ctx->d_mail + 1;
+        if ((rc = khb_pairs_count_impl(ctx, sorted, spay, n_sym, k, fb, KHB_COUNTER_MAX, nbins, d_hist, out_keys, d_runs, d_pairs))) return rc;
+        KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, ctx->d_mail, (nbins + 9) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        tm.mark();  // 7: count done
+        KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        memcpy(h_hist, ctx->h_mail + 8, ((size_t)nbins + 1) * sizeof(u64));
+        const u64 d_g = ctx->h_mail[0];
+        if (keep_set) {
+            ctx->gs_len += d_g;
+            ctx->gs_groups += 1;
+        }
+        if (stats) {
+            stats->fasta_bytes = nbytes;
+            stats->bases = n_sym - counts[1];
+            stats->windows = n_sym;
+            stats->genome_distinct = ctx->h_mail[1];
+            stats->distinct = d_g;
+            stats->passes_genome = 0;
+            stats->passes_group = np;
+        }
+        return KHB_OK;
+    }
+    if ((rc = khb_extract_kmers_impl(ctx, d_codes, d_valid, n_sym, k, hashed, bufA, nullptr, nullptr, 0))) return rc;
     tm.mark();  // 3: extract done
     // K3 per genome (segmented), prefix only
     std::vector<u64> seg(n_genomes + 1);
@@ -637,7 +698,7 @@ static int group_from_staged_impl(khb_ctx *ctx, int k, int n_genomes, const uint
     int fb1, np1, fb2, np2;
     khb_prefix_plan(k, max_seg, &fb1, &np1);
     int in_tmp = 0;
-    if ((rc = khb_sort_bits_impl(ctx, bufA, bufB, seg.data(), n_genomes, (int)W, fb1, np1, &in_tmp))) return rc;
+    if ((rc = khb_sort_bits_impl(ctx, bufA, bufB, seg.data(), n_genomes, (int)W, fb1, np1, &in_tmp, nullptr, nullptr))) return rc;
     void *sorted = in_tmp ? bufB : bufA, *other = in_tmp ? bufA : bufB;
     tm.mark();  // 4: sort1 done
     // K4
@@ -649,7 +710,7 @@ static int group_from_staged_impl(khb_ctx *ctx, int k, int n_genomes, const uint
     // K3' group sort, prefix only
     khb_prefix_plan(k, s_g, &fb2, &np2);
     u64 one_seg[2] = {0, s_g};
-    if ((rc = khb_sort_bits_impl(ctx, other, sorted, one_seg, 1, (int)W, fb2, np2, &in_tmp))) return rc;
+    if ((rc = khb_sort_bits_impl(ctx, other, sorted, one_seg, 1, (int)W, fb2, np2, &in_tmp, nullptr, nullptr))) return rc;
     void *gsorted = in_tmp ? sorted : other;
     tm.mark();  // 6: sort2 done
     // K5
@@ -862,7 +923,7 @@ int khb_across_groups(khb_ctx *ctx, uint32_t nbins, uint64_t *h_hist, khb_stats 
     int in_tmp = 0, fb, np;
     khb_prefix_plan(k, n, &fb, &np);
     if (!ctx->gs_hashed) { fb = 0; np = (2 * k + 7) / 8; }  // unhashed keys (k = 32 / 64 or appended raw sets): full sort
-    if ((rc = khb_sort_bits_impl(ctx, ctx->gs_buf, p, one_seg, 1, (int)W, fb, np, &in_tmp))) return rc;
+    if ((rc = khb_sort_bits_impl(ctx, ctx->gs_buf, p, one_seg, 1, (int)W, fb, np, &in_tmp, nullptr, nullptr))) return rc;
     tm.mark();
     u64 *d_hist = ctx->d_mail + 8, *d_runs = ctx->d_mail;
     if ((rc = khb_resolve_count_impl(ctx, in_tmp ? p : ctx->gs_buf, n, k, fb, KHB_COUNTER_MAX, nbins, d_hist, nullptr, d_runs))) return rc;

@@ -408,6 +408,214 @@ runs_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 nbins, u6
     }
 }
 
+// ---- single-sort group path: keys with a genome-id payload ------------------------------------------------------
+// Instead of a per-genome sort + dedup followed by a group sort, the windows of ALL genomes of a group are sorted
+// once (stable, prefix only) together with a 16-bit genome id.  Equal keys then sit next to each other in genome
+// order, so the number of genomes containing a k-mer is the number of (key, genome) CHANGES inside its run:
+//   F[i] = key[i] != key[i-1]  ||  gid[i] != gid[i-1]          ("new pair")
+//   c(x) = sum of F over the run of x          (= kmc per genome, set_counts 1, union-sum -- exp_type_1.smk:156-182)
+// pairs_kernel is runs_kernel with that sum in place of the run length: blocked arrangement, one segmented warp
+// scan per thread carries (count so far, mixed flag) of the run that is open at a thread / warp / tile boundary,
+// mixed prefix runs take the out-of-line scan.  It also returns sum F = the sum of the per-genome set sizes.
+__device__ __forceinline__ u32 seg_combine(u32 a, u32 b)
+{
+    // state = bit31: a run head was seen | bit30: that head's predecessor shares its prefix | low 30 bits: pair count
+    return (b >> 31) ? b : ((a & 0xC0000000u) | ((a + b) & 0x3FFFFFFFu));
+}
+
+template <typename Key>
+__device__ __noinline__ bool slow_pairs(const Key *__restrict__ in, const unsigned short *__restrict__ gid, u64 n, int pshift, u64 t,
+                                        u32 *count)
+{
+    const Key key = in[t];
+    u64 h = t;
+    while (h > 0 && key_eq(in[h - 1], key)) h--;
+    u64 q = h;
+    while (q > 0) {  // an earlier occurrence inside the prefix run?
+        --q;
+        const Key kq = in[q];
+        if (key_is_sentinel(kq) || !same_prefix(kq, key, pshift)) break;
+        if (key_eq(kq, key)) return false;
+    }
+    u32 cnt = 0, last = 0xffffffffu;
+    for (u64 r = h; r < n; r++) {
+        const Key kr = in[r];
+        if (r > t && (key_is_sentinel(kr) || !same_prefix(kr, key, pshift))) break;
+        if (key_eq(kr, key)) {
+            const u32 g = gid[r];
+            if (g != last) { cnt++; last = g; }
+        }
+    }
+    *count = cnt;
+    return true;
+}
+
+template <typename Key>
+__global__ void __launch_bounds__(CQ_BLOCK, (sizeof(Key) == 8 ? 1024 : 512) / CQ_BLOCK)
+pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid, u64 n, int pshift, u32 cs, u32 nbins,
+             u64 *__restrict__ hist, Key *__restrict__ out_keys, u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs)
+{
+    constexpr int TILE = CQ_BLOCK * CQ_ITEMS;
+    extern __shared__ u32 sh_hist[];  // [nbins+1]
+    __shared__ u32 s_open;            // state of the run that is open at the tile start
+    __shared__ u32 s_wstate[CQ_WARPS];
+    const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    const u64 ntiles = (n + TILE - 1) / TILE;
+    for (u32 i = tid; i <= nbins; i += CQ_BLOCK) sh_hist[i] = 0;
+    __syncthreads();
+    for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const u64 begin = tile * TILE;
+        const u32 nloc = (u32)(n - begin < (u64)TILE ? n - begin : (u64)TILE);
+        const bool last_tile = begin + TILE >= n;
+        const u32 l0 = tid * CQ_ITEMS;
+        Key k[CQ_ITEMS + 2];   // k[0] = predecessor, k[1..ITEMS] = own keys, k[ITEMS+1] = successor
+        u32 g[CQ_ITEMS + 1];   // g[0] = predecessor's genome, g[1..ITEMS] = own
+        if (begin > 0 && !last_tile) {
+            const Key *base = in + begin;
+            const unsigned short *gb = gid + begin;
+#pragma unroll
+            for (int j = 0; j < CQ_ITEMS + 2; j++) k[j] = base[(int)l0 - 1 + j];
+#pragma unroll
+            for (int j = 0; j < CQ_ITEMS + 1; j++) g[j] = gb[(int)l0 - 1 + j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < CQ_ITEMS + 2; j++) {
+                const u64 x = begin + l0 + j;  // index + 1
+                const bool ok = x >= 1 && x - 1 < n;
+                k[j] = ok ? in[x - 1] : sentinel_key<Key>();
+                if (j <= CQ_ITEMS) g[j] = ok ? (u32)gid[x - 1] : 0u;
+            }
+        }
+        if (warp == 0) {
+            // state of the run open at the tile start, from the 32 keys in front of the tile (fetched with the tile)
+            Key back = sentinel_key<Key>();
+            u32 gback = 0;
+            if (begin > lane) { back = in[begin - 1 - lane]; gback = gid[begin - 1 - lane]; }
+            const Key k0 = shfl_key(k[1], 0);
+            u32 state = 0;
+            if (begin > 0 && !key_is_sentinel(k0)) {
+                const u32 eq = __ballot_sync(0xffffffffu, begin > lane && key_eq(back, k0));
+                const u32 d = (u32)__ffs(~eq) - 1u;  // consecutive equal keys in front of the tile (32 if ~eq == 0)
+                if (d > 0) {
+                    if (d < 32) {
+                        const u32 gnext = __shfl_down_sync(0xffffffffu, gback, 1);  // genome of the key one further back
+                        const bool f = lane < d && (lane == d - 1 || gback != gnext);
+                        const u32 cnt = __popc(__ballot_sync(0xffffffffu, f));
+                        const Key pk = shfl_key(back, (int)d);
+                        const bool mix = begin > d && !key_is_sentinel(pk) && same_prefix(pk, k0, pshift);
+                        state = 0x80000000u | (mix ? 0x40000000u : 0u) | cnt;
+                    } else {
+                        // a run longer than 32 keys reaches the tile: count its pairs serially (rare)
+                        u32 cnt = 0, mix = 0;
+                        if (lane == 0) {
+                            u64 p = begin;  // walk back while the key equals k0
+                            u32 lastg = 0xffffffffu;
+                            while (p > 0 && key_eq(in[p - 1], k0)) {
+                                --p;
+                                const u32 gg = gid[p];
+                                if (gg != lastg) { cnt++; lastg = gg; }
+                            }
+                            if (p > 0) {
+                                const Key pk = in[p - 1];
+                                mix = (!key_is_sentinel(pk) && same_prefix(pk, k0, pshift)) ? 1u : 0u;
+                            }
+                        }
+                        cnt = __shfl_sync(0xffffffffu, cnt, 0);
+                        mix = __shfl_sync(0xffffffffu, mix, 0);
+                        state = 0x80000000u | (mix << 30) | cnt;
+                    }
+                }
+            }
+            if (lane == 0) s_open = state;
+        }
+        // per key: head / tail of its key run, "new pair" flag, prefix relation to the neighbours
+        u32 headm = 0, tailm = 0, fm = 0, hmix = 0, tmix = 0;
+#pragma unroll
+        for (int j = 0; j < CQ_ITEMS; j++) {
+            const u32 l = l0 + j;
+            const Key key = k[j + 1];
+            const bool valid = l < nloc && !key_is_sentinel(key);
+            const bool first_of_all = begin == 0 && l == 0;
+            const bool last_of_all = last_tile && l + 1 >= nloc;
+            const bool head = valid && (first_of_all || !key_eq(key, k[j]));
+            const bool tail = valid && (last_of_all || !key_eq(key, k[j + 2]));
+            const bool f = valid && (head || g[j + 1] != g[j]);
+            const bool pm = head && !first_of_all && !key_is_sentinel(k[j]) && same_prefix(k[j], key, pshift);
+            const bool nm = tail && !last_of_all && !key_is_sentinel(k[j + 2]) && same_prefix(k[j + 2], key, pshift);
+            headm |= (head ? 1u : 0u) << j;
+            tailm |= (tail ? 1u : 0u) << j;
+            fm |= (f ? 1u : 0u) << j;
+            hmix |= (pm ? 1u : 0u) << j;
+            tmix |= (nm ? 1u : 0u) << j;
+        }
+        // segmented scan of (count, mixed) over threads
+        u32 st;
+        if (headm == 0) {
+            st = __popc(fm);
+        } else {
+            const int hl = 31 - __clz(headm);
+            st = 0x80000000u | (((hmix >> hl) & 1u) << 30) | (u32)__popc(fm >> hl);
+        }
+        u32 inc = st;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (u32)o) inc = seg_combine(up, inc);
+        }
+        u32 excl = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) excl = 0;
+        if (lane == 31) s_wstate[warp] = inc;
+        __syncthreads();  // s_wstate, s_open
+        u32 carry = s_open;
+        for (u32 w = 0; w < warp; w++) carry = seg_combine(carry, s_wstate[w]);
+        carry = seg_combine(carry, excl);
+        // resolve every tail
+        u32 emitm = 0;
+        u32 open_cnt = carry & 0x3FFFFFFFu;
+        bool open_mix = (carry >> 30) & 1u;
+#pragma unroll
+        for (int j = 0; j < CQ_ITEMS; j++) {
+            if ((headm >> j) & 1u) { open_cnt = 0; open_mix = (hmix >> j) & 1u; }
+            open_cnt += (fm >> j) & 1u;
+            if ((tailm >> j) & 1u) {
+                u32 cnt = open_cnt;
+                bool first = true;
+                if (open_mix || ((tmix >> j) & 1u)) first = slow_pairs(in, gid, n, pshift, begin + l0 + j, &cnt);
+                if (first) {
+                    emitm |= 1u << j;
+                    const u32 c = cnt > cs ? cs : cnt;
+                    if (c <= nbins) atomicAdd(&sh_hist[c], 1u);
+                }
+            }
+        }
+        // per warp: one atomicAdd reserves the output range, one adds the pair count
+        const u32 mine = __popc(emitm);
+        const u32 incl = warp_incl_sum<u32>(mine);
+        const u32 wtotal = __shfl_sync(0xffffffffu, incl, 31);
+        u32 pairs = __popc(fm);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
+        u64 wbase = 0;
+        if (lane == 31) {
+            if (wtotal) wbase = atomicAdd(d_cursor, (u64)wtotal);
+            if (pairs) atomicAdd(d_pairs, (u64)pairs);
+        }
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        if (out_keys != nullptr && mine) {
+            u64 pos = wbase + (incl - mine);
+#pragma unroll
+            for (int j = 0; j < CQ_ITEMS; j++)
+                if ((emitm >> j) & 1u) out_keys[pos++] = k[j + 1];
+        }
+        __syncthreads();  // s_wstate / s_open are rewritten by the next iteration
+    }
+    __syncthreads();
+    for (u32 i = tid; i <= nbins; i += CQ_BLOCK) {
+        const u32 c = sh_hist[i];
+        if (c) atomicAdd(&hist[i], (u64)c);
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------------------
 static int compact_scratch(khb_ctx *ctx, u64 ntiles, u64 **d_lb, u32 **d_ticket)
 {
@@ -507,5 +715,29 @@ int khb_resolve_count_impl(khb_ctx *ctx, const void *d_sorted, size_t n, int k, 
         runs_kernel<Key128, true><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const Key128 *)d_sorted, n, pshift, cs, nbins, d_hist, (Key128 *)d_out_keys, d_runs);
     KHB_LAUNCH_CHECK(ctx);
     khb_prof_end(ctx, KHB_K_RLE, (u64)n * (k <= 32 ? 8 : 16));
+    return KHB_OK;
+}
+
+// Single-sort group path: histogram of genomes-per-k-mer from prefix-sorted (key, genome id) pairs.
+int khb_pairs_count_impl(khb_ctx *ctx, const void *d_sorted, const unsigned short *d_gid, size_t n, int k, int pshift, u32 cs, u32 nbins,
+                         u64 *d_hist, void *d_out_keys, u64 *d_runs, u64 *d_pairs)
+{
+    if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_pairs_count: k=%d outside 1..64", k);
+    if (nbins < 1 || nbins > 8192) return khb_fail(ctx, KHB_ERR_ARG, "khb_pairs_count: nbins=%u outside 1..8192", nbins);
+    KHB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, ((size_t)nbins + 1) * sizeof(u64), ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(d_runs, 0, sizeof(u64), ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(d_pairs, 0, sizeof(u64), ctx->stream));
+    if (n == 0) return KHB_OK;
+    const u64 ntiles = div_up(n, CQ_BLOCK * CQ_ITEMS);
+    u64 grid = (u64)ctx->num_sms * (k <= 32 ? 2048 : 1024) / CQ_BLOCK;
+    if (grid > ntiles) grid = ntiles;
+    const size_t shm = ((size_t)nbins + 1) * sizeof(u32);
+    khb_prof_begin(ctx, KHB_K_RLE);
+    if (k <= 32)
+        pairs_kernel<Key64><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const Key64 *)d_sorted, d_gid, n, pshift, cs, nbins, d_hist, (Key64 *)d_out_keys, d_runs, d_pairs);
+    else
+        pairs_kernel<Key128><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const Key128 *)d_sorted, d_gid, n, pshift, cs, nbins, d_hist, (Key128 *)d_out_keys, d_runs, d_pairs);
+    KHB_LAUNCH_CHECK(ctx);
+    khb_prof_end(ctx, KHB_K_RLE, (u64)n * ((k <= 32 ? 8 : 16) + 2));
     return KHB_OK;
 }

@@ -156,7 +156,7 @@ struct khb_ctx {
     cudaEvent_t ev0, ev1;
     char err[512];
     int sticky;  // first CUDA error code seen (0 = none); CUDA errors are sticky per ctx
-    khb_scratch scratch[8];
+    khb_scratch scratch[12];
     // pinned host mailbox for small device->host results
     u64 *h_mail;
     u64 *d_mail;
@@ -196,7 +196,8 @@ enum { KHB_K_PACK = 0, KHB_K_EXTRACT = 1, KHB_K_RADIX_HIST = 2, KHB_K_ONESWEEP =
 void khb_prof_begin(khb_ctx *ctx, int id);
 void khb_prof_end(khb_ctx *ctx, int id, u64 alg_bytes);
 
-enum { SCR_TILE = 0, SCR_LOOKBACK = 1, SCR_HIST = 2, SCR_MISC = 3, SCR_KEYS_A = 4, SCR_KEYS_B = 5, SCR_PACK = 6, SCR_FLAGS = 7 };
+enum { SCR_TILE = 0, SCR_LOOKBACK = 1, SCR_HIST = 2, SCR_MISC = 3, SCR_KEYS_A = 4, SCR_KEYS_B = 5, SCR_PACK = 6, SCR_FLAGS = 7, SCR_PAY_A = 8, SCR_PAY_B = 9 };
+#define KHB_NSCRATCH 12
 
 int khb_fail(khb_ctx *ctx, int code, const char *fmt, ...);
 int khb_cuda_fail(khb_ctx *ctx, cudaError_t e, const char *what, const char *file, int line);

@@ -20,10 +20,21 @@ __device__ __forceinline__ u64 swap_pairs(u64 r)
     return ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
 }
 
+// Index of the segment (genome) that holds window i: largest g with seg_off[g] <= i.  The table is tiny and L1 resident.
+__device__ __forceinline__ u32 segment_of(const u64 *__restrict__ seg_off, int nseg, u64 i)
+{
+    int lo = 0, hi = nseg;  // invariant: seg_off[lo] <= i < seg_off[hi] (seg_off[nseg] = n_sym)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(seg_off + mid) <= i) lo = mid; else hi = mid;
+    }
+    return (u32)lo;
+}
+
 // k <= 32.  One thread produces the two windows starting at i and i+1 (i even) -> one 16-byte store.
 __global__ void __launch_bounds__(256)
 extract64_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, size_t n_sym, int k, int hashed,
-                 ulonglong2 *__restrict__ out)
+                 ulonglong2 *__restrict__ out, unsigned short *__restrict__ gids, const u64 *__restrict__ seg_off, int nseg)
 {
     const size_t npairs = (n_sym + 1) >> 1;
     const u64 ones_k = k == 64 ? ~0ull : ((1ull << k) - 1ull);
@@ -53,13 +64,19 @@ extract64_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, s
         } else {
             ((u64 *)out)[i] = res[0];
         }
+        if (gids != nullptr) {
+            const u32 g0 = segment_of(seg_off, nseg, i);
+            const u32 g1 = (g0 + 1 < (u32)nseg && seg_off[g0 + 1] <= i + 1) ? segment_of(seg_off, nseg, i + 1) : g0;
+            if (i + 1 < n_sym) ((ushort2 *)gids)[pr] = make_ushort2((unsigned short)g0, (unsigned short)g1);
+            else gids[i] = (unsigned short)g0;
+        }
     }
 }
 
 // 33 <= k <= 64.  One thread per window -> one 16-byte store (lo, hi).
 __global__ void __launch_bounds__(256)
 extract128_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, size_t n_sym, int k, int hashed,
-                  ulonglong2 *__restrict__ out)
+                  ulonglong2 *__restrict__ out, unsigned short *__restrict__ gids, const u64 *__restrict__ seg_off, int nseg)
 {
     const u64 ones_k = k == 64 ? ~0ull : ((1ull << k) - 1ull);
     const int rs = 128 - 2 * k;  // 0..62
@@ -98,6 +115,7 @@ extract128_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, 
         r.x = ok ? cl : ~0ull;   // lo
         r.y = ok ? ch : ~0ull;   // hi
         out[i] = r;
+        if (gids != nullptr) gids[i] = (unsigned short)segment_of(seg_off, nseg, i);
     }
 }
 
@@ -134,7 +152,9 @@ int khb_remix_impl(khb_ctx *ctx, void *d_keys, size_t n, int k, int inverse)
     return KHB_OK;
 }
 
-int khb_extract_kmers_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, size_t n_sym, int k, int hashed, void *d_keys)
+// d_gids / d_seg_off (optional): also write, per window, the index of the segment (genome) it belongs to.
+int khb_extract_kmers_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, size_t n_sym, int k, int hashed, void *d_keys,
+                           unsigned short *d_gids, const u64 *d_seg_off, int nseg)
 {
     if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_extract_kmers: k=%d outside 1..64", k);
     if (n_sym == 0) return KHB_OK;
@@ -144,10 +164,10 @@ int khb_extract_kmers_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid,
     if (blocks > cap) blocks = cap;
     khb_prof_begin(ctx, KHB_K_EXTRACT);
     if (k <= 32)
-        extract64_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_codes, d_valid, n_sym, k, hashed, (ulonglong2 *)d_keys);
+        extract64_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_codes, d_valid, n_sym, k, hashed, (ulonglong2 *)d_keys, d_gids, d_seg_off, nseg);
     else
-        extract128_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_codes, d_valid, n_sym, k, hashed, (ulonglong2 *)d_keys);
+        extract128_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_codes, d_valid, n_sym, k, hashed, (ulonglong2 *)d_keys, d_gids, d_seg_off, nseg);
     KHB_LAUNCH_CHECK(ctx);
-    khb_prof_end(ctx, KHB_K_EXTRACT, (u64)n_sym / 4 + n_sym / 8 + (u64)n_sym * (k <= 32 ? 8 : 16));
+    khb_prof_end(ctx, KHB_K_EXTRACT, (u64)n_sym / 4 + n_sym / 8 + (u64)n_sym * ((k <= 32 ? 8 : 16) + (d_gids ? 2 : 0)));
     return KHB_OK;
 }

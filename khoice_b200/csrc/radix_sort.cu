@@ -194,9 +194,11 @@ __device__ unsigned long long g_phase_cycles[16];
 #define PHASE_MARK(i)
 #endif
 
-template <typename Key, int BLOCK, int ITEMS, int MINB, int MATCH, int DIRECT, int EARLY>
+// PAY = 1: every key carries a 16-bit payload (the genome id in the single-sort group path) through the pass.
+template <typename Key, int BLOCK, int ITEMS, int MINB, int MATCH, int PAY, int EARLY>
 __global__ void __launch_bounds__(BLOCK, MINB)
-onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__restrict__ seg_off,
+onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const unsigned short *__restrict__ pin,
+                unsigned short *__restrict__ pout, const u64 *__restrict__ seg_off,
                 const u64 *__restrict__ seg_tile, int nseg, int pass_row, int shift, int npass,
                 const u32 *__restrict__ bin_base /* [nseg][npass][256], exclusive */, u64 *__restrict__ lookback,
                 u32 *__restrict__ ticket, u32 epoch)
@@ -207,12 +209,13 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
     static_assert(BLOCK >= 256, "256 digit threads needed");
     static_assert(TILE < 65536, "16-bit tile offsets");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Key *sorted = (Key *)smem_raw;                                             // [TILE] (absent when DIRECT)
-    unsigned short *wcnt = (unsigned short *)(smem_raw + (DIRECT ? 0 : sizeof(Key) * TILE));  // [NW][256]
+    Key *sorted = (Key *)smem_raw;                                             // [TILE]
+    unsigned short *wcnt = (unsigned short *)(smem_raw + sizeof(Key) * TILE);  // [NW][256]
     u32 *glob_off = (u32 *)(wcnt + NW * 256);                                  // [256] offset of sorted[j] in the segment, minus j
     u32 *ws = glob_off + 256;                                                  // [36] scan scratch
     u32 *mm = ws + 36;                                                         // [NW][256] peer masks (MATCH >= 2 only)
     u32 *tcnt = mm + (MATCH >= 2 ? NW * 256 : 0);                              // [256] early tile digit counts (EARLY only)
+    unsigned short *sortedp = (unsigned short *)(tcnt + (EARLY ? 256 : 0));    // [TILE] payloads in sorted order (PAY only)
     __shared__ u32 s_tile;
     __shared__ int s_seg;
 
@@ -248,12 +251,23 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
     for (int r = 0; r < (ITEMS + 1) / 2; r++) rank2[r] = 0;
     const u32 wbase = warp * (32 * ITEMS);
     const Key *src = in + begin + wbase + lane;
+    u32 pay2[PAY ? (ITEMS + 1) / 2 : 1];  // two payloads per register
     if (wbase + 32 * ITEMS <= n) {
 #pragma unroll
         for (int r = 0; r < ITEMS; r++) keys[r] = src[r * 32];
     } else {
 #pragma unroll
         for (int r = 0; r < ITEMS; r++) keys[r] = (wbase + r * 32 + lane < n) ? src[r * 32] : key_max<Key>();
+    }
+    if (PAY) {
+        const unsigned short *psrc = pin + begin + wbase + lane;
+#pragma unroll
+        for (int r = 0; r < (ITEMS + 1) / 2; r++) pay2[r] = 0;
+#pragma unroll
+        for (int r = 0; r < ITEMS; r++) {
+            const u32 v = (wbase + r * 32 + lane < n) ? (u32)psrc[r * 32] : 0u;
+            pay2[r >> 1] |= v << (16 * (r & 1));
+        }
     }
 #ifdef KHB_PHASE_TIMING
     if (tid == 0 && key_digit(keys[0], 0) == 999u) g_phase_cycles[15] = 1;  // force the loads to complete here
@@ -365,12 +379,12 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
     PHASE_MARK(4);  // scans + publish
     __syncthreads();
     // reorder through shared memory
-    if (!DIRECT) {
 #pragma unroll
-        for (int r = 0; r < ITEMS; r++) {
-            const u32 d = key_digit(keys[r], shift);
-            sorted[wcnt[warp * 256 + d] + ((rank2[r >> 1] >> (16 * (r & 1))) & 0xffffu)] = keys[r];
-        }
+    for (int r = 0; r < ITEMS; r++) {
+        const u32 d = key_digit(keys[r], shift);
+        const u32 pos = wcnt[warp * 256 + d] + ((rank2[r >> 1] >> (16 * (r & 1))) & 0xffffu);
+        sorted[pos] = keys[r];
+        if (PAY) sortedp[pos] = (unsigned short)(pay2[r >> 1] >> (16 * (r & 1)));
     }
     PHASE_MARK(5);  // reorder
     // finish the look-back (256 digit threads) unless it already ran right after the early count (EARLY 2)
@@ -382,46 +396,40 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const u64 *__
     __syncthreads();
     PHASE_MARK(7);  // wait for all look-backs
     Key *dst = out + seg_begin;
-    if (DIRECT) {
-        // scatter straight from registers: 8/16-byte stores to up to 32 runs per warp; L2 merges the sectors
-#pragma unroll
-        for (int r = 0; r < ITEMS; r++) {
-            const u32 d = key_digit(keys[r], shift);
-            const u32 j = wcnt[warp * 256 + d] + ((rank2[r >> 1] >> (16 * (r & 1))) & 0xffffu);
-            if (j < n) dst[glob_off[d] + j] = keys[r];
-        }
-        return;
-    }
+    unsigned short *pdst = PAY ? pout + seg_begin : nullptr;
     // coalesced store: position j of the sorted tile goes to segment offset glob_off[digit] + j
 #pragma unroll 4
     for (u32 j = tid; j < n; j += BLOCK) {
         const Key key = sorted[j];
-        dst[glob_off[key_digit(key, shift)] + j] = key;
+        const u32 o = glob_off[key_digit(key, shift)] + j;
+        dst[o] = key;
+        if (PAY) pdst[o] = sortedp[j];
     }
     PHASE_MARK(8);  // store
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
-template <typename Key, int BLOCK, int ITEMS, int MINB, int MATCH, int DIRECT = 0, int EARLY = 0>
-static int launch_passes(khb_ctx *ctx, Key *src, Key *dst, const u64 *d_off, const u64 *d_tile, int nseg, int npass, int first_bit,
+template <typename Key, int BLOCK, int ITEMS, int MINB, int MATCH, int PAY = 0, int EARLY = 0>
+static int launch_passes(khb_ctx *ctx, Key *src, Key *dst, unsigned short *psrc, unsigned short *pdst, const u64 *d_off, const u64 *d_tile, int nseg, int npass, int first_bit,
                          u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket)
 {
     constexpr int TILE = BLOCK * ITEMS;
     constexpr int NW = BLOCK / 32;
-    const size_t shm = (DIRECT ? 0 : sizeof(Key) * TILE) + NW * 256 * sizeof(unsigned short) + 256 * sizeof(u32) + 36 * sizeof(u32) +
-                       (MATCH >= 2 ? NW * 256 * sizeof(u32) : 0) + (EARLY ? 256 * sizeof(u32) : 0);
+    const size_t shm = sizeof(Key) * TILE + NW * 256 * sizeof(unsigned short) + 256 * sizeof(u32) + 36 * sizeof(u32) +
+                       (MATCH >= 2 ? NW * 256 * sizeof(u32) : 0) + (EARLY ? 256 * sizeof(u32) : 0) + (PAY ? TILE * sizeof(unsigned short) : 0);
     static bool attr_set = false;
     if (!attr_set) {
-        KHB_CUDA(ctx, cudaFuncSetAttribute(onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH, DIRECT, EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+        KHB_CUDA(ctx, cudaFuncSetAttribute(onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH, PAY, EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
         attr_set = true;
     }
     for (int pass = 0; pass < npass; pass++) {
         khb_prof_begin(ctx, KHB_K_ONESWEEP);
-        onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH, DIRECT, EARLY><<<(unsigned)ntiles, BLOCK, shm, ctx->stream>>>(
-            src, dst, d_off, d_tile, nseg, pass, first_bit + 8 * pass, npass, d_hist, d_lb, d_ticket + pass, (u32)(pass + 1));
+        onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH, PAY, EARLY><<<(unsigned)ntiles, BLOCK, shm, ctx->stream>>>(
+            src, dst, psrc, pdst, d_off, d_tile, nseg, pass, first_bit + 8 * pass, npass, d_hist, d_lb, d_ticket + pass, (u32)(pass + 1));
         KHB_LAUNCH_CHECK(ctx);
-        khb_prof_end(ctx, KHB_K_ONESWEEP, 2 * n_keys * sizeof(Key));  // read + write every key once
+        khb_prof_end(ctx, KHB_K_ONESWEEP, 2 * n_keys * (sizeof(Key) + (PAY ? 2 : 0)));  // read + write every key (+ payload) once
         Key *t = src; src = dst; dst = t;
+        unsigned short *pt = psrc; psrc = pdst; pdst = pt;
     }
 #ifdef KHB_PHASE_TIMING
     {
@@ -461,34 +469,40 @@ static u32 variant_tile(int v, size_t W)
 }
 
 template <typename Key>
-static int dispatch_passes(khb_ctx *ctx, int v, Key *src, Key *dst, const u64 *d_off, const u64 *d_tile, int nseg, int npass,
-                           int first_bit, u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket);
+static int dispatch_passes(khb_ctx *ctx, int v, Key *src, Key *dst, unsigned short *psrc, unsigned short *pdst, const u64 *d_off,
+                           const u64 *d_tile, int nseg, int npass, int first_bit, u64 ntiles, u64 n_keys, const u32 *d_hist,
+                           u64 *d_lb, u32 *d_ticket);
 
+#define KHB_PASS_ARGS ctx, src, dst, psrc, pdst, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket
 template <>
-int dispatch_passes<Key64>(khb_ctx *ctx, int v, Key64 *src, Key64 *dst, const u64 *d_off, const u64 *d_tile, int nseg, int npass,
-                           int first_bit, u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket)
+int dispatch_passes<Key64>(khb_ctx *ctx, int v, Key64 *src, Key64 *dst, unsigned short *psrc, unsigned short *pdst, const u64 *d_off,
+                           const u64 *d_tile, int nseg, int npass, int first_bit, u64 ntiles, u64 n_keys, const u32 *d_hist,
+                           u64 *d_lb, u32 *d_ticket)
 {
-#define GO(B, I, M, MT, ...) return launch_passes<Key64, B, I, M, MT, ##__VA_ARGS__>(ctx, src, dst, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket)
+    if (psrc) return launch_passes<Key64, 512, 12, 2, 2, 1>(KHB_PASS_ARGS);  // keys + 16-bit payload
     switch (v) {
-    case 0: GO(512, 12, 2, 0);         // MATCH.ANY            (1.46 TB/s: ~1 MATCH.ANY per 100 cycles per SM)
-    case 1: GO(512, 12, 2, 1);         // eight ballots         (2.33 TB/s: ALU-bound, 3.9 warp-instr/key)
-    case 13: GO(512, 12, 2, 4);        // every 3rd round by ballots, the others by atomicOr (2.64 TB/s)
-    case 18: GO(512, 12, 2, 2, 0, 2);  // early count + early look-back (2.45 TB/s)
-    default: GO(512, 12, 2, 2);        // shared-memory atomicOr peer masks (2.57 TB/s) -- default
+    case 0: return launch_passes<Key64, 512, 12, 2, 0>(KHB_PASS_ARGS);         // MATCH.ANY (1.46 TB/s: ~1 MATCH.ANY per 100 cycles per SM)
+    case 1: return launch_passes<Key64, 512, 12, 2, 1>(KHB_PASS_ARGS);         // eight ballots (2.33 TB/s: ALU-bound, 3.9 warp-instr/key)
+    case 13: return launch_passes<Key64, 512, 12, 2, 4>(KHB_PASS_ARGS);        // every 3rd round by ballots, the others by atomicOr (2.64 TB/s)
+    case 18: return launch_passes<Key64, 512, 12, 2, 2, 0, 2>(KHB_PASS_ARGS);  // early count + early look-back (2.45 TB/s)
+    default: return launch_passes<Key64, 512, 12, 2, 2>(KHB_PASS_ARGS);        // shared-memory atomicOr peer masks (2.57 TB/s) -- default
     }
-#undef GO
 }
 
 template <>
-int dispatch_passes<Key128>(khb_ctx *ctx, int v, Key128 *src, Key128 *dst, const u64 *d_off, const u64 *d_tile, int nseg, int npass,
-                            int first_bit, u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket)
+int dispatch_passes<Key128>(khb_ctx *ctx, int v, Key128 *src, Key128 *dst, unsigned short *psrc, unsigned short *pdst, const u64 *d_off,
+                            const u64 *d_tile, int nseg, int npass, int first_bit, u64 ntiles, u64 n_keys, const u32 *d_hist,
+                            u64 *d_lb, u32 *d_ticket)
 {
     (void)v;
-    return launch_passes<Key128, 512, 6, 2, 2>(ctx, src, dst, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket);
+    if (psrc) return launch_passes<Key128, 512, 6, 2, 2, 1>(KHB_PASS_ARGS);
+    return launch_passes<Key128, 512, 6, 2, 2>(KHB_PASS_ARGS);
 }
+#undef KHB_PASS_ARGS
 
 template <typename Key>
-static int sort_impl(khb_ctx *ctx, Key *d_keys, Key *d_tmp, const u64 *h_seg_off, int nseg, int first_bit, int npass, int *result_in_tmp)
+static int sort_impl(khb_ctx *ctx, Key *d_keys, Key *d_tmp, unsigned short *d_pay, unsigned short *d_pay_tmp, const u64 *h_seg_off,
+                     int nseg, int first_bit, int npass, int *result_in_tmp)
 {
     const int v = sort_variant();
     const u32 TILE = variant_tile(v, sizeof(Key));
@@ -546,28 +560,30 @@ static int sort_impl(khb_ctx *ctx, Key *d_keys, Key *d_tmp, const u64 *h_seg_off
         KHB_LAUNCH_CHECK(ctx);
         khb_prof_end(ctx, KHB_K_RADIX_HIST, n_keys * sizeof(Key));
     }
-    rc = dispatch_passes<Key>(ctx, v, d_keys, d_tmp, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket);
+    rc = dispatch_passes<Key>(ctx, v, d_keys, d_tmp, d_pay, d_pay_tmp, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket);
     if (rc) return rc;
     *result_in_tmp = (npass & 1);
     return KHB_OK;
 }
 
-// Sort every segment by the `npass` 8-bit digits starting at bit `first_bit` (stable LSD).
+// Sort every segment by the `npass` 8-bit digits starting at bit `first_bit` (stable LSD).  d_pay / d_pay_tmp
+// (optional, both or none): a 16-bit payload per key that travels with it (ping-pong like the keys).
 int khb_sort_bits_impl(khb_ctx *ctx, void *d_keys, void *d_tmp, const u64 *h_seg_off, int nseg, int key_bytes, int first_bit, int npass,
-                       int *result_in_tmp)
+                       int *result_in_tmp, unsigned short *d_pay, unsigned short *d_pay_tmp)
 {
     if (key_bytes != 8 && key_bytes != 16) return khb_fail(ctx, KHB_ERR_ARG, "sort: key_bytes=%d", key_bytes);
     if (npass < 0 || npass > 16 || first_bit < 0 || first_bit + 8 * npass > 8 * key_bytes + 7)
         return khb_fail(ctx, KHB_ERR_ARG, "sort: bad digit range first_bit=%d npass=%d", first_bit, npass);
+    if ((d_pay == nullptr) != (d_pay_tmp == nullptr)) return khb_fail(ctx, KHB_ERR_ARG, "sort: payload needs both buffers");
     *result_in_tmp = 0;
     if (npass == 0) return KHB_OK;
-    return key_bytes == 8 ? sort_impl<Key64>(ctx, (Key64 *)d_keys, (Key64 *)d_tmp, h_seg_off, nseg, first_bit, npass, result_in_tmp)
-                          : sort_impl<Key128>(ctx, (Key128 *)d_keys, (Key128 *)d_tmp, h_seg_off, nseg, first_bit, npass, result_in_tmp);
+    return key_bytes == 8 ? sort_impl<Key64>(ctx, (Key64 *)d_keys, (Key64 *)d_tmp, d_pay, d_pay_tmp, h_seg_off, nseg, first_bit, npass, result_in_tmp)
+                          : sort_impl<Key128>(ctx, (Key128 *)d_keys, (Key128 *)d_tmp, d_pay, d_pay_tmp, h_seg_off, nseg, first_bit, npass, result_in_tmp);
 }
 
 // Full sort of k-mer words: all ceil(2k/8) digits.
 int khb_sort_keys_impl(khb_ctx *ctx, void *d_keys, void *d_tmp, const u64 *h_seg_off, int nseg, int k, int *result_in_tmp)
 {
     if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_sort_keys: k=%d outside 1..64", k);
-    return khb_sort_bits_impl(ctx, d_keys, d_tmp, h_seg_off, nseg, k <= 32 ? 8 : 16, 0, (2 * k + 7) / 8, result_in_tmp);
+    return khb_sort_bits_impl(ctx, d_keys, d_tmp, h_seg_off, nseg, k <= 32 ? 8 : 16, 0, (2 * k + 7) / 8, result_in_tmp, nullptr, nullptr);
 }
