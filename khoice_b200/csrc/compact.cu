@@ -273,6 +273,27 @@ rle_hist_kernel(const Key *__restrict__ in, u64 n, u32 cs, u32 nbins, u64 *__res
 // tile waits for another: the distinct keys come out in no particular order, which is all a set needs (the next
 // stage re-sorts them); histograms and counts are exact and deterministic.
 #define CQ_ITEMS 8
+
+// Blocked tile load: thread `tid` gets keys [l0-1, l0+ITEMS] of the tile at `base` (predecessor, own, successor).
+// The own keys are 64 / 128 contiguous, 16-byte aligned bytes -> 128-bit loads.
+__device__ __forceinline__ void load_blocked(const Key64 *__restrict__ base, u32 l0, Key64 (&k)[CQ_ITEMS + 2])
+{
+    const ulonglong2 *v = (const ulonglong2 *)(base + l0);
+#pragma unroll
+    for (int j = 0; j < CQ_ITEMS / 2; j++) {
+        const ulonglong2 x = v[j];
+        k[1 + 2 * j].v = x.x;
+        k[2 + 2 * j].v = x.y;
+    }
+    k[0] = base[(int)l0 - 1];
+    k[CQ_ITEMS + 1] = base[l0 + CQ_ITEMS];
+}
+__device__ __forceinline__ void load_blocked(const Key128 *__restrict__ base, u32 l0, Key128 (&k)[CQ_ITEMS + 2])
+{
+#pragma unroll
+    for (int j = 0; j < CQ_ITEMS + 2; j++) k[j] = base[(int)l0 - 1 + j];
+}
+
 template <typename Key, bool COUNT>
 __global__ void __launch_bounds__(CQ_BLOCK, (sizeof(Key) == 8 ? 1024 : 512) / CQ_BLOCK)
 runs_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 nbins, u64 *__restrict__ hist,
@@ -296,8 +317,7 @@ runs_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 nbins, u6
         const Key *base = in + begin;
         Key k[CQ_ITEMS + 2];            // k[0] = predecessor, k[1..ITEMS] = own keys, k[ITEMS+1] = successor
         if (begin > 0 && !last_tile) {
-#pragma unroll
-            for (int j = 0; j < CQ_ITEMS + 2; j++) k[j] = base[(int)l0 - 1 + j];
+            load_blocked(base, l0, k);
         } else {
 #pragma unroll
             for (int j = 0; j < CQ_ITEMS + 2; j++) {
@@ -471,12 +491,12 @@ pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid,
         Key k[CQ_ITEMS + 2];   // k[0] = predecessor, k[1..ITEMS] = own keys, k[ITEMS+1] = successor
         u32 g[CQ_ITEMS + 1];   // g[0] = predecessor's genome, g[1..ITEMS] = own
         if (begin > 0 && !last_tile) {
-            const Key *base = in + begin;
             const unsigned short *gb = gid + begin;
-#pragma unroll
-            for (int j = 0; j < CQ_ITEMS + 2; j++) k[j] = base[(int)l0 - 1 + j];
-#pragma unroll
-            for (int j = 0; j < CQ_ITEMS + 1; j++) g[j] = gb[(int)l0 - 1 + j];
+            load_blocked(in + begin, l0, k);
+            const uint4 gv = *(const uint4 *)(gb + l0);  // 8 own genome ids: 16 aligned bytes
+            g[0] = gb[(int)l0 - 1];
+            g[1] = gv.x & 0xffffu; g[2] = gv.x >> 16; g[3] = gv.y & 0xffffu; g[4] = gv.y >> 16;
+            g[5] = gv.z & 0xffffu; g[6] = gv.z >> 16; g[7] = gv.w & 0xffffu; g[8] = gv.w >> 16;
         } else {
 #pragma unroll
             for (int j = 0; j < CQ_ITEMS + 2; j++) {

@@ -39,7 +39,13 @@ extract64_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, s
     const size_t npairs = (n_sym + 1) >> 1;
     const u64 ones_k = k == 64 ? ~0ull : ((1ull << k) - 1ull);
     const int rs = 64 - 2 * k;  // right shift that brings the 2k window bits to the low end
-    for (size_t pr = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pr < npairs; pr += (size_t)gridDim.x * blockDim.x) {
+    // every CTA walks ONE contiguous chunk, so consecutive iterations stay inside one genome and the cached
+    // segment interval [seg_lo, seg_hi) almost always answers the genome-id question without a search
+    const size_t per = ((npairs + gridDim.x - 1) / gridDim.x + blockDim.x - 1) / blockDim.x * blockDim.x;
+    const size_t pr_end = (size_t)(blockIdx.x + 1) * per < npairs ? (size_t)(blockIdx.x + 1) * per : npairs;
+    u64 seg_lo = 1, seg_hi = 0;
+    u32 seg_g = 0;
+    for (size_t pr = (size_t)blockIdx.x * per + threadIdx.x; pr < pr_end; pr += blockDim.x) {
         const size_t i = pr << 1;
         const size_t m = i >> 5;
         const u32 o = (u32)(i & 31);  // even, <= 30
@@ -65,8 +71,13 @@ extract64_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, s
             ((u64 *)out)[i] = res[0];
         }
         if (gids != nullptr) {
-            const u32 g0 = segment_of(seg_off, nseg, i);
-            const u32 g1 = (g0 + 1 < (u32)nseg && seg_off[g0 + 1] <= i + 1) ? segment_of(seg_off, nseg, i + 1) : g0;
+            if (i < seg_lo || i >= seg_hi) {
+                seg_g = segment_of(seg_off, nseg, i);
+                seg_lo = __ldg(seg_off + seg_g);
+                seg_hi = __ldg(seg_off + seg_g + 1);
+            }
+            const u32 g0 = seg_g;
+            const u32 g1 = (i + 1 >= seg_hi && i + 1 < n_sym) ? segment_of(seg_off, nseg, i + 1) : g0;
             if (i + 1 < n_sym) ((ushort2 *)gids)[pr] = make_ushort2((unsigned short)g0, (unsigned short)g1);
             else gids[i] = (unsigned short)g0;
         }
@@ -80,7 +91,11 @@ extract128_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, 
 {
     const u64 ones_k = k == 64 ? ~0ull : ((1ull << k) - 1ull);
     const int rs = 128 - 2 * k;  // 0..62
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sym; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t per = ((n_sym + gridDim.x - 1) / gridDim.x + blockDim.x - 1) / blockDim.x * blockDim.x;
+    const size_t i_end = (size_t)(blockIdx.x + 1) * per < n_sym ? (size_t)(blockIdx.x + 1) * per : n_sym;
+    u64 seg_lo = 1, seg_hi = 0;
+    u32 seg_g = 0;
+    for (size_t i = (size_t)blockIdx.x * per + threadIdx.x; i < i_end; i += blockDim.x) {
         const size_t m = i >> 5;
         const u32 o = (u32)(i & 31);
         const u64 c0 = __ldg(codes + m), c1 = __ldg(codes + m + 1), c2 = __ldg(codes + m + 2);
@@ -115,7 +130,14 @@ extract128_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, 
         r.x = ok ? cl : ~0ull;   // lo
         r.y = ok ? ch : ~0ull;   // hi
         out[i] = r;
-        if (gids != nullptr) gids[i] = (unsigned short)segment_of(seg_off, nseg, i);
+        if (gids != nullptr) {
+            if (i < seg_lo || i >= seg_hi) {
+                seg_g = segment_of(seg_off, nseg, i);
+                seg_lo = __ldg(seg_off + seg_g);
+                seg_hi = __ldg(seg_off + seg_g + 1);
+            }
+            gids[i] = (unsigned short)seg_g;
+        }
     }
 }
 
