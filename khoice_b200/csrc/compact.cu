@@ -443,31 +443,57 @@ __device__ __forceinline__ u32 seg_combine(u32 a, u32 b)
     return (b >> 31) ? b : ((a & 0xC0000000u) | ((a + b) & 0x3FFFFFFFu));
 }
 
+// Mixed prefix run, per-thread part: is the adjacent run ending at t the FIRST occurrence of its key inside the prefix
+// run?  (Short: a later occurrence finds an earlier one within a few steps because equal keys interleave.)
 template <typename Key>
-__device__ __noinline__ bool slow_pairs(const Key *__restrict__ in, const unsigned short *__restrict__ gid, u64 n, int pshift, u64 t,
-                                        u32 *count)
+__device__ __noinline__ bool mixed_is_first(const Key *__restrict__ in, int pshift, u64 t)
 {
     const Key key = in[t];
-    u64 h = t;
-    while (h > 0 && key_eq(in[h - 1], key)) h--;
-    u64 q = h;
-    while (q > 0) {  // an earlier occurrence inside the prefix run?
+    u64 q = t;
+    while (q > 0) {
         --q;
         const Key kq = in[q];
-        if (key_is_sentinel(kq) || !same_prefix(kq, key, pshift)) break;
-        if (key_eq(kq, key)) return false;
-    }
-    u32 cnt = 0, last = 0xffffffffu;
-    for (u64 r = h; r < n; r++) {
-        const Key kr = in[r];
-        if (r > t && (key_is_sentinel(kr) || !same_prefix(kr, key, pshift))) break;
-        if (key_eq(kr, key)) {
-            const u32 g = gid[r];
-            if (g != last) { cnt++; last = g; }
+        if (key_eq(kq, key)) continue;                       // still inside the adjacent run
+        if (key_is_sentinel(kq) || !same_prefix(kq, key, pshift)) return true;
+        // a different key of the same prefix run: keep looking for an earlier occurrence
+        for (;;) {
+            if (q == 0) return true;
+            --q;
+            const Key k2 = in[q];
+            if (key_is_sentinel(k2) || !same_prefix(k2, key, pshift)) return true;
+            if (key_eq(k2, key)) return false;
         }
     }
-    *count = cnt;
     return true;
+}
+
+// Mixed prefix run, warp-cooperative part: (key, genome) pairs of `key` among the keys AFTER index t inside the prefix
+// run, given the genome of the last counted occurrence.  All 32 lanes scan 32 consecutive keys per step.
+template <typename Key>
+__device__ __forceinline__ u32 mixed_pairs_after(const Key *__restrict__ in, const unsigned short *__restrict__ gid, u64 n, int pshift,
+                                                 u64 t, const Key &key, u32 last_g, u32 lane)
+{
+    u32 cnt = 0;
+    for (u64 r0 = t + 1; r0 < n; r0 += 32) {
+        const u64 r = r0 + lane;
+        Key kr = sentinel_key<Key>();
+        u32 g = 0;
+        if (r < n) { kr = in[r]; g = gid[r]; }
+        const bool inside = r < n && !key_is_sentinel(kr) && same_prefix(kr, key, pshift);
+        const u32 out_mask = __ballot_sync(0xffffffffu, !inside);
+        const u32 upto = out_mask ? ((out_mask & (0u - out_mask)) - 1u) : 0xffffffffu;  // lanes before the prefix run ends
+        const u32 eq = __ballot_sync(0xffffffffu, inside && key_eq(kr, key)) & upto;
+        // equal keys come in genome order: a new pair starts where the genome differs from the previous equal key's
+        const u32 before = eq & lanemask_lt();
+        const int prev_lane = before ? 31 - __clz(before) : 0;
+        const u32 gprev = __shfl_sync(0xffffffffu, g, prev_lane);
+        const bool is_eq = (eq >> lane) & 1u;
+        const bool newpair = is_eq && (before ? g != gprev : g != last_g);
+        cnt += __popc(__ballot_sync(0xffffffffu, newpair));
+        if (eq) last_g = __shfl_sync(0xffffffffu, g, 31 - __clz(eq));
+        if (out_mask) break;
+    }
+    return cnt;
 }
 
 template <typename Key>
@@ -477,13 +503,14 @@ pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid,
 {
     constexpr int TILE = CQ_BLOCK * CQ_ITEMS;
     extern __shared__ u32 sh_hist[];  // [nbins+1]
-    __shared__ u32 s_open;            // state of the run that is open at the tile start
-    __shared__ u32 s_wstate[CQ_WARPS];
+    __shared__ u32 s_open[2];         // state of the run that is open at the tile start (double-buffered by tile parity)
+    __shared__ u32 s_wstate[2][CQ_WARPS];
     const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const u64 ntiles = (n + TILE - 1) / TILE;
     for (u32 i = tid; i <= nbins; i += CQ_BLOCK) sh_hist[i] = 0;
     __syncthreads();
-    for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    u32 par = 0;
+    for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x, par ^= 1u) {
         const u64 begin = tile * TILE;
         const u32 nloc = (u32)(n - begin < (u64)TILE ? n - begin : (u64)TILE);
         const bool last_tile = begin + TILE >= n;
@@ -546,7 +573,7 @@ pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid,
                     }
                 }
             }
-            if (lane == 0) s_open = state;
+            if (lane == 0) s_open[par] = state;
         }
         // per key: head / tail of its key run, "new pair" flag, prefix relation to the neighbours
         u32 headm = 0, tailm = 0, fm = 0, hmix = 0, tmix = 0;
@@ -584,26 +611,53 @@ pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid,
         }
         u32 excl = __shfl_up_sync(0xffffffffu, inc, 1);
         if (lane == 0) excl = 0;
-        if (lane == 31) s_wstate[warp] = inc;
-        __syncthreads();  // s_wstate, s_open
-        u32 carry = s_open;
-        for (u32 w = 0; w < warp; w++) carry = seg_combine(carry, s_wstate[w]);
+        if (lane == 31) s_wstate[par][warp] = inc;
+        __syncthreads();  // s_wstate, s_open (the only CTA-wide barrier per tile: the buffers alternate)
+        u32 carry = s_open[par];
+        for (u32 w = 0; w < warp; w++) carry = seg_combine(carry, s_wstate[par][w]);
         carry = seg_combine(carry, excl);
-        // resolve every tail
-        u32 emitm = 0;
+        // resolve every tail.  Pure prefix runs need nothing but the carried count; in a mixed prefix run a tail first
+        // checks (short scan) whether it is the first occurrence of its key, and if so queues the forward scan, which the
+        // whole warp then runs cooperatively.
+        u32 emitm = 0, pendm = 0;
+        u32 pend_cnt[CQ_ITEMS];
         u32 open_cnt = carry & 0x3FFFFFFFu;
         bool open_mix = (carry >> 30) & 1u;
 #pragma unroll
         for (int j = 0; j < CQ_ITEMS; j++) {
+            pend_cnt[j] = 0;
             if ((headm >> j) & 1u) { open_cnt = 0; open_mix = (hmix >> j) & 1u; }
             open_cnt += (fm >> j) & 1u;
             if ((tailm >> j) & 1u) {
-                u32 cnt = open_cnt;
                 bool first = true;
-                if (open_mix || ((tmix >> j) & 1u)) first = slow_pairs(in, gid, n, pshift, begin + l0 + j, &cnt);
+                const bool mixed_after = (tmix >> j) & 1u;
+                if (open_mix) first = mixed_is_first(in, pshift, begin + l0 + j);
                 if (first) {
                     emitm |= 1u << j;
-                    const u32 c = cnt > cs ? cs : cnt;
+                    if (mixed_after) {
+                        pendm |= 1u << j;
+                        pend_cnt[j] = open_cnt;
+                    } else {
+                        const u32 c = open_cnt > cs ? cs : open_cnt;
+                        if (c <= nbins) atomicAdd(&sh_hist[c], 1u);
+                    }
+                }
+            }
+        }
+        // warp-cooperative forward scans for the queued owners (rare)
+#pragma unroll
+        for (int j = 0; j < CQ_ITEMS; j++) {
+            u32 need = __ballot_sync(0xffffffffu, (pendm >> j) & 1u);
+            while (need) {
+                const int src = __ffs(need) - 1;
+                need &= need - 1;
+                const u64 t = begin + (u64)__shfl_sync(0xffffffffu, l0, src) + j;
+                const Key key = shfl_key(k[j + 1], src);
+                const u32 last_g = __shfl_sync(0xffffffffu, g[j + 1], src);
+                const u32 extra = mixed_pairs_after(in, gid, n, pshift, t, key, last_g, lane);
+                if ((int)lane == src) {
+                    const u32 tot = pend_cnt[j] + extra;
+                    const u32 c = tot > cs ? cs : tot;
                     if (c <= nbins) atomicAdd(&sh_hist[c], 1u);
                 }
             }
@@ -627,7 +681,6 @@ pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid,
             for (int j = 0; j < CQ_ITEMS; j++)
                 if ((emitm >> j) & 1u) out_keys[pos++] = k[j + 1];
         }
-        __syncthreads();  // s_wstate / s_open are rewritten by the next iteration
     }
     __syncthreads();
     for (u32 i = tid; i <= nbins; i += CQ_BLOCK) {
