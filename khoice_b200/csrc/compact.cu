@@ -501,20 +501,20 @@ __global__ void __launch_bounds__(CQ_BLOCK, (sizeof(Key) == 8 ? 1024 : 512) / CQ
 pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid, u64 n, int pshift, u32 cs, u32 nbins,
              u64 *__restrict__ hist, Key *__restrict__ out_keys, u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs)
 {
-    constexpr int TILE = CQ_BLOCK * CQ_ITEMS;
+    // Every WARP owns chunks of 32 x CQ_ITEMS consecutive keys and is completely independent of the other warps of
+    // its CTA (no shared state, no barrier inside the loop): the state of the run that is open at the chunk start
+    // comes from the 32 keys in front of the chunk, which the warp fetches together with the chunk.
+    constexpr int TILE = 32 * CQ_ITEMS;
     extern __shared__ u32 sh_hist[];  // [nbins+1]
-    __shared__ u32 s_open[2];         // state of the run that is open at the tile start (double-buffered by tile parity)
-    __shared__ u32 s_wstate[2][CQ_WARPS];
     const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const u64 ntiles = (n + TILE - 1) / TILE;
     for (u32 i = tid; i <= nbins; i += CQ_BLOCK) sh_hist[i] = 0;
     __syncthreads();
-    u32 par = 0;
-    for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x, par ^= 1u) {
+    for (u64 tile = (u64)blockIdx.x * CQ_WARPS + warp; tile < ntiles; tile += (u64)gridDim.x * CQ_WARPS) {
         const u64 begin = tile * TILE;
         const u32 nloc = (u32)(n - begin < (u64)TILE ? n - begin : (u64)TILE);
         const bool last_tile = begin + TILE >= n;
-        const u32 l0 = tid * CQ_ITEMS;
+        const u32 l0 = lane * CQ_ITEMS;
         Key k[CQ_ITEMS + 2];   // k[0] = predecessor, k[1..ITEMS] = own keys, k[ITEMS+1] = successor
         u32 g[CQ_ITEMS + 1];   // g[0] = predecessor's genome, g[1..ITEMS] = own
         if (begin > 0 && !last_tile) {
@@ -533,8 +533,9 @@ pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid,
                 if (j <= CQ_ITEMS) g[j] = ok ? (u32)gid[x - 1] : 0u;
             }
         }
-        if (warp == 0) {
-            // state of the run open at the tile start, from the 32 keys in front of the tile (fetched with the tile)
+        u32 open_state;
+        {
+            // state of the run open at the chunk start, from the 32 keys in front of the chunk (fetched with it)
             Key back = sentinel_key<Key>();
             u32 gback = 0;
             if (begin > lane) { back = in[begin - 1 - lane]; gback = gid[begin - 1 - lane]; }
@@ -573,7 +574,7 @@ pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid,
                     }
                 }
             }
-            if (lane == 0) s_open[par] = state;
+            open_state = state;
         }
         // per key: head / tail of its key run, "new pair" flag, prefix relation to the neighbours
         u32 headm = 0, tailm = 0, fm = 0, hmix = 0, tmix = 0;
@@ -611,11 +612,7 @@ pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid,
         }
         u32 excl = __shfl_up_sync(0xffffffffu, inc, 1);
         if (lane == 0) excl = 0;
-        if (lane == 31) s_wstate[par][warp] = inc;
-        __syncthreads();  // s_wstate, s_open (the only CTA-wide barrier per tile: the buffers alternate)
-        u32 carry = s_open[par];
-        for (u32 w = 0; w < warp; w++) carry = seg_combine(carry, s_wstate[par][w]);
-        carry = seg_combine(carry, excl);
+        const u32 carry = seg_combine(open_state, excl);
         // resolve every tail.  Pure prefix runs need nothing but the carried count; in a mixed prefix run a tail first
         // checks (short scan) whether it is the first occurrence of its key, and if so queues the forward scan, which the
         // whole warp then runs cooperatively.
@@ -801,7 +798,7 @@ int khb_pairs_count_impl(khb_ctx *ctx, const void *d_sorted, const unsigned shor
     KHB_CUDA(ctx, cudaMemsetAsync(d_runs, 0, sizeof(u64), ctx->stream));
     KHB_CUDA(ctx, cudaMemsetAsync(d_pairs, 0, sizeof(u64), ctx->stream));
     if (n == 0) return KHB_OK;
-    const u64 ntiles = div_up(n, CQ_BLOCK * CQ_ITEMS);
+    const u64 ntiles = div_up(n, CQ_BLOCK * CQ_ITEMS);  // CTA-sized groups of warp chunks
     u64 grid = (u64)ctx->num_sms * (k <= 32 ? 2048 : 1024) / CQ_BLOCK;
     if (grid > ntiles) grid = ntiles;
     const size_t shm = ((size_t)nbins + 1) * sizeof(u32);
