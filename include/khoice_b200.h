@@ -181,6 +181,17 @@ KHB_API int khb_group_prefetch_fasta(khb_ctx *ctx, int n_genomes, const uint8_t 
 KHB_API int khb_group_from_staged(khb_ctx *ctx, int k, int n_genomes, const uint8_t *d_fasta, const uint64_t *h_begin,
                           uint32_t nbins, uint64_t *h_hist, int keep_set, khb_stats *stats);
 
+/* Pack once, sweep k: the reference runs 30 values of k over the same genomes (workflow/Snakefile:36) and lets KMC
+ * re-read and re-parse every .fna.gz for each of them (exp_type_1.smk:156-163).  khb_pack_group stages and packs a
+ * group ONCE (K1) and keeps the 2-bit stream resident (3/8 byte per base); khb_group_from_packed runs K2..K5 for one k
+ * on it.  Results are identical to khb_group_from_fasta. */
+typedef struct khb_packed khb_packed;
+KHB_API int khb_pack_group(khb_ctx *ctx, int n_genomes, const uint8_t *const *h_files, const size_t *h_sizes, khb_packed **out);
+KHB_API int khb_packed_info(const khb_packed *pk, uint64_t *n_symbols, uint64_t *bases, uint64_t *device_bytes);
+KHB_API int khb_packed_free(khb_ctx *ctx, khb_packed *pk);
+KHB_API int khb_group_from_packed(khb_ctx *ctx, int k, const khb_packed *pk, uint32_t nbins, uint64_t *h_hist, int keep_set,
+                          khb_stats *stats);
+
 /* Across-group union-sum + histogram over the retained group sets: rules across_group_union and
  * across_group_union_histogram (exp_type_1.smk:243-259) for one k. */
 KHB_API int khb_across_groups(khb_ctx *ctx, uint32_t nbins, uint64_t *h_hist, khb_stats *stats);

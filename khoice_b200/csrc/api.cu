@@ -592,18 +592,25 @@ struct PhaseTimer {
     }
 };
 
-static int group_from_staged_impl(khb_ctx *ctx, int k, int n_genomes, const uint8_t *d_fasta, const u64 *h_begin, u32 nbins,
-                                  u64 *h_hist, int keep_set, khb_stats *stats, PhaseTimer &tm)
+// A group after K1: the packed symbol stream plus the symbol offset of every genome.  Either a transient view of the
+// context's scratch (fused calls) or a persistent allocation (khb_pack_group: pack once, sweep k).
+struct khb_packed {
+    u64 *d_codes;
+    u32 *d_valid;
+    u64 n_sym, n_breaks, fasta_bytes;
+    int n_genomes;
+    std::vector<u64> seg;  // n_genomes + 1 symbol offsets
+    bool owned;
+};
+
+// K1 into the context's scratch.
+static int pack_stage(khb_ctx *ctx, int n_genomes, const uint8_t *d_fasta, const u64 *h_begin, khb_packed &pk, PhaseTimer &tm)
 {
-    if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "k=%d outside 1..64", k);
-    if (n_genomes < 1 || !h_begin || !h_hist) return khb_fail(ctx, KHB_ERR_ARG, "group stage: bad arguments");
-    if (nbins < 1 || nbins > 8192) return khb_fail(ctx, KHB_ERR_ARG, "nbins=%u outside 1..8192", nbins);
-    const size_t W = (size_t)khb_key_bytes(k);
+    if (n_genomes < 1 || !h_begin) return khb_fail(ctx, KHB_ERR_ARG, "group stage: bad arguments");
     const size_t nbytes = h_begin[n_genomes];
     const size_t ntiles = nbytes / KHB_FASTA_TILE;
     int rc;
     void *p;
-    // K1
     const size_t cw = khb_codes_words(nbytes), vw = khb_valid_words(nbytes);
     const size_t pack_bytes = cw * 8 + vw * 4 + (ntiles + 1) * 8 + 64;
     if ((rc = khb_scratch_get(ctx, SCR_PACK, pack_bytes, &p))) return rc;
@@ -618,7 +625,35 @@ static int group_from_staged_impl(khb_ctx *ctx, int k, int n_genomes, const uint
     KHB_CUDA(ctx, cudaMemcpyAsync(counts, d_counts, 16, cudaMemcpyDeviceToHost, ctx->stream));
     tm.mark();  // 2: pack done
     KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const u64 n_sym = counts[0];
+    pk.d_codes = d_codes;
+    pk.d_valid = d_valid;
+    pk.n_sym = counts[0];
+    pk.n_breaks = counts[1];
+    pk.fasta_bytes = nbytes;
+    pk.n_genomes = n_genomes;
+    pk.owned = false;
+    pk.seg.resize((size_t)n_genomes + 1);
+    for (int g = 0; g < n_genomes; g++) pk.seg[g] = tile_base[h_begin[g] / KHB_FASTA_TILE];
+    pk.seg[0] = 0;
+    pk.seg[n_genomes] = pk.n_sym;
+    return KHB_OK;
+}
+
+// K2 .. K5 for one k on a packed group.
+static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64 *h_hist, int keep_set, khb_stats *stats, PhaseTimer &tm)
+{
+    if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "k=%d outside 1..64", k);
+    if (!h_hist) return khb_fail(ctx, KHB_ERR_ARG, "group stage: null histogram");
+    if (nbins < 1 || nbins > 8192) return khb_fail(ctx, KHB_ERR_ARG, "nbins=%u outside 1..8192", nbins);
+    const size_t W = (size_t)khb_key_bytes(k);
+    const int n_genomes = pk.n_genomes;
+    const u64 n_sym = pk.n_sym;
+    const size_t nbytes = pk.fasta_bytes;
+    const u64 counts[2] = {pk.n_sym, pk.n_breaks};
+    u64 *d_codes = pk.d_codes;
+    u32 *d_valid = pk.d_valid;
+    int rc;
+    void *p;
     // K2 (hashed unless k = 32 / 64, see khb_prefix_plan)
     const int hashed = (k != 32 && k != 64) ? 1 : 0;
     if (ctx->gs_k && keep_set && ctx->gs_hashed != hashed) return khb_fail(ctx, KHB_ERR_STATE, "retained group sets use a different key encoding");
@@ -638,10 +673,7 @@ static int group_from_staged_impl(khb_ctx *ctx, int k, int n_genomes, const uint
         unsigned short *payA = (unsigned short *)p;
         if ((rc = khb_scratch_get(ctx, SCR_PAY_B, (n_sym + 8) * 2, &p))) return rc;
         unsigned short *payB = (unsigned short *)p;
-        std::vector<u64> seg(n_genomes + 1);
-        for (int g = 0; g < n_genomes; g++) seg[g] = tile_base[h_begin[g] / KHB_FASTA_TILE];
-        seg[0] = 0;
-        seg[n_genomes] = n_sym;
+        const std::vector<u64> &seg = pk.seg;
         u64 *d_seg = ctx->d_mail + 32768;  // up to 65536 offsets fit the 1 MiB mailbox behind the histogram area
         if ((size_t)(n_genomes + 1) > 65536) return khb_fail(ctx, KHB_ERR_ARG, "too many genomes in one group");
         KHB_CUDA(ctx, cudaMemcpyAsync(d_seg, seg.data(), (size_t)(n_genomes + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -690,10 +722,8 @@ static int group_from_staged_impl(khb_ctx *ctx, int k, int n_genomes, const uint
     if ((rc = khb_extract_kmers_impl(ctx, d_codes, d_valid, n_sym, k, hashed, bufA, nullptr, nullptr, 0))) return rc;
     tm.mark();  // 3: extract done
     // K3 per genome (segmented), prefix only
-    std::vector<u64> seg(n_genomes + 1);
+    const std::vector<u64> &seg = pk.seg;
     u64 max_seg = 1;
-    for (int g = 0; g < n_genomes; g++) seg[g] = tile_base[h_begin[g] / KHB_FASTA_TILE];
-    seg[n_genomes] = n_sym;
     for (int g = 0; g < n_genomes; g++) max_seg = seg[g + 1] - seg[g] > max_seg ? seg[g + 1] - seg[g] : max_seg;
     int fb1, np1, fb2, np2;
     khb_prefix_plan(k, max_seg, &fb1, &np1);
@@ -743,6 +773,16 @@ static int group_from_staged_impl(khb_ctx *ctx, int k, int n_genomes, const uint
         stats->distinct = d_g;
     }
     return KHB_OK;
+}
+
+static int group_from_staged_impl(khb_ctx *ctx, int k, int n_genomes, const uint8_t *d_fasta, const u64 *h_begin, u32 nbins,
+                                  u64 *h_hist, int keep_set, khb_stats *stats, PhaseTimer &tm)
+{
+    if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "k=%d outside 1..64", k);
+    khb_packed pk;
+    int rc = pack_stage(ctx, n_genomes, d_fasta, h_begin, pk, tm);
+    if (rc) return rc;
+    return count_stage(ctx, k, pk, nbins, h_hist, keep_set, stats, tm);
 }
 
 static void fill_times(khb_stats *stats, PhaseTimer &tm)
@@ -900,6 +940,76 @@ int khb_group_from_fasta(khb_ctx *ctx, int k, int n_genomes, const uint8_t *cons
     if (rc) return rc;
     tm.mark();
     rc = group_from_staged_impl(ctx, k, n_genomes, ctx->stage_dev, begin.data(), nbins, (u64 *)h_hist, keep_set, stats, tm);
+    if (rc == KHB_OK) fill_times(stats, tm);
+    return rc;
+}
+
+int khb_pack_group(khb_ctx *ctx, int n_genomes, const uint8_t *const *h_files, const size_t *h_sizes, khb_packed **out)
+{
+    KHB_CHECK_CTX(ctx);
+    if (n_genomes < 1 || !h_files || !h_sizes || !out) return khb_fail(ctx, KHB_ERR_ARG, "khb_pack_group: bad arguments");
+    *out = nullptr;
+    const size_t need = khb_staged_size(n_genomes, h_sizes);
+    int rc = ensure_stage(ctx, &ctx->stage_dev, &ctx->stage_dev_cap, need);
+    if (rc) return rc;
+    ctx->pf_valid = 0;
+    std::vector<u64> begin((size_t)n_genomes + 1);
+    rc = khb_stage_fasta(ctx, n_genomes, h_files, h_sizes, ctx->stage_dev, ctx->stage_dev_cap, (uint64_t *)begin.data());
+    if (rc) return rc;
+    PhaseTimer tm(ctx);
+    khb_packed tmp;
+    if ((rc = pack_stage(ctx, n_genomes, ctx->stage_dev, begin.data(), tmp, tm))) return rc;
+    // keep a compact private copy: the scratch is reused by the next call
+    khb_packed *pk = new khb_packed(tmp);
+    const size_t cw = khb_codes_words(tmp.n_sym), vw = khb_valid_words(tmp.n_sym);
+    void *mem = nullptr;
+    cudaError_t e = cudaMalloc(&mem, cw * 8 + vw * 4);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        delete pk;
+        return khb_fail(ctx, KHB_ERR_NOMEM, "khb_pack_group: device allocation of %zu bytes failed", cw * 8 + vw * 4);
+    }
+    pk->d_codes = (u64 *)mem;
+    pk->d_valid = (u32 *)(pk->d_codes + cw);
+    pk->owned = true;
+    KHB_CUDA(ctx, cudaMemcpyAsync(pk->d_codes, tmp.d_codes, cw * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    KHB_CUDA(ctx, cudaMemcpyAsync(pk->d_valid, tmp.d_valid, vw * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = pk;
+    return KHB_OK;
+}
+
+int khb_packed_info(const khb_packed *pk, uint64_t *n_symbols, uint64_t *bases, uint64_t *device_bytes)
+{
+    if (!pk) return KHB_ERR_ARG;
+    if (n_symbols) *n_symbols = pk->n_sym;
+    if (bases) *bases = pk->n_sym - pk->n_breaks;
+    if (device_bytes) *device_bytes = khb_codes_words(pk->n_sym) * 8 + khb_valid_words(pk->n_sym) * 4;
+    return KHB_OK;
+}
+
+int khb_packed_free(khb_ctx *ctx, khb_packed *pk)
+{
+    KHB_CHECK_CTX(ctx);
+    if (!pk) return KHB_OK;
+    if (pk->owned && pk->d_codes) {
+        KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        KHB_CUDA(ctx, cudaFree(pk->d_codes));
+    }
+    delete pk;
+    return KHB_OK;
+}
+
+int khb_group_from_packed(khb_ctx *ctx, int k, const khb_packed *pk, uint32_t nbins, uint64_t *h_hist, int keep_set, khb_stats *stats)
+{
+    KHB_CHECK_CTX(ctx);
+    if (!pk) return khb_fail(ctx, KHB_ERR_ARG, "khb_group_from_packed: null handle");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    PhaseTimer tm(ctx);
+    tm.mark();
+    tm.mark();
+    tm.mark();  // 2: nothing to pack
+    int rc = count_stage(ctx, k, *pk, nbins, (u64 *)h_hist, keep_set, stats, tm);
     if (rc == KHB_OK) fill_times(stats, tm);
     return rc;
 }

@@ -82,6 +82,10 @@ _SIGNATURES = [
     ("khb_group_from_fasta", C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_uint32, _P, C.c_int, C.POINTER(Stats)]),
     ("khb_group_prefetch_fasta", C.c_int, [_P, C.c_int, _P, _P]),
     ("khb_group_from_staged", C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_uint32, _P, C.c_int, C.POINTER(Stats)]),
+    ("khb_pack_group", C.c_int, [_P, C.c_int, _P, _P, C.POINTER(_P)]),
+    ("khb_packed_info", C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("khb_packed_free", C.c_int, [_P, _P]),
+    ("khb_group_from_packed", C.c_int, [_P, C.c_int, _P, C.c_uint32, _P, C.c_int, C.POINTER(Stats)]),
     ("khb_across_groups", C.c_int, [_P, C.c_uint32, _P, C.POINTER(Stats)]),
     ("khb_group_sets_info", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
     ("khb_group_sets_device", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
@@ -167,6 +171,30 @@ class DeviceBuffer:
     def __del__(self):
         try:
             self.free()
+        except Exception:
+            pass
+
+
+class PackedGroup:
+    """Handle of a group packed by khb_pack_group (2-bit symbol stream resident in HBM)."""
+
+    def __init__(self, eng: "Engine", handle):
+        self.eng, self.handle = eng, handle
+
+    def info(self) -> dict:
+        n, b, d = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.eng._chk(self.eng.lib.khb_packed_info(self.handle, C.byref(n), C.byref(b), C.byref(d)))
+        return {"n_symbols": n.value, "bases": b.value, "device_bytes": d.value}
+
+    def free(self):
+        if self.handle:
+            self.eng.lib.khb_packed_free(self.eng.ctx, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            if getattr(self.eng, "ctx", None):
+                self.free()
         except Exception:
             pass
 
@@ -393,6 +421,20 @@ class Engine:
         st = Stats()
         self._chk(self.lib.khb_group_from_staged(self.ctx, k, n, staged.buf.ptr + base, begin.ctypes.data, nbins,
                                                  hist.ctypes.data, int(keep_set), C.byref(st)))
+        return hist, st.as_dict()
+
+    def pack_group(self, files: Sequence) -> "PackedGroup":
+        """K1 once for a group; the 2-bit stream stays in HBM for a sweep over k (see group_from_packed)."""
+        arrs, ptrs, sizes = self._file_tables(files)
+        h = _P()
+        self._chk(self.lib.khb_pack_group(self.ctx, len(arrs), ptrs, sizes, C.byref(h)))
+        return PackedGroup(self, h)
+
+    def group_from_packed(self, packed: "PackedGroup", k: int, nbins: int = COUNTER_MAX, keep_set: bool = True):
+        """K2..K5 for one k on a packed group; same results as group_from_fasta."""
+        hist = np.zeros(nbins + 1, dtype=np.uint64)
+        st = Stats()
+        self._chk(self.lib.khb_group_from_packed(self.ctx, k, packed.handle, nbins, hist.ctypes.data, int(keep_set), C.byref(st)))
         return hist, st.as_dict()
 
     def across_groups(self, nbins: int = COUNTER_MAX):

@@ -104,18 +104,20 @@ def run_fused(work_root: str, num_datasets: int, k_values: Optional[Sequence] = 
     eng = engine or Engine(int(os.environ.get("KHB_DEVICE", "0")))
     report = {"mode": "fused", "work_root": work_root, "num_datasets": num_datasets, "k_values": k_values, "stages": []}
     t_start = time.time()
+    packed: Dict[int, object] = {}
     try:
         write_complex_ops(work_root, k_values, num_datasets)
         names = {n: genomes_of(work_root, n) for n in range(1, num_datasets + 1)}
-        texts: Dict[int, List[bytes]] = {}
         zero = np.zeros(tables.HIST_ROWS + 1, dtype=np.uint64)
         for k in k_values:
             ki = int(k)
             eng.group_sets_reset()
             for num in range(1, num_datasets + 1):
-                if num not in texts:  # inflate once, reuse across the k sweep while host memory allows
-                    texts[num] = [cli.read_fasta(os.path.join(work_root, p_genome(num, g))) for g in names[num]]
-                hist, st = eng.group_from_fasta(texts[num], ki, nbins=tables.HIST_ROWS, keep_set=True)
+                if num not in packed:  # inflate + pack ONCE; the 2-bit stream (3/8 byte per base) stays in HBM for the k sweep
+                    texts = [cli.read_fasta(os.path.join(work_root, p_genome(num, g))) for g in names[num]]
+                    packed[num] = eng.pack_group(texts)
+                    del texts
+                hist, st = eng.group_from_packed(packed[num], ki, nbins=tables.HIST_ROWS, keep_set=True)
                 tables.write_histogram_file(os.path.join(work_root, p_step4(k, num)), hist)
                 if stubs:
                     one = zero.copy()
@@ -133,6 +135,8 @@ def run_fused(work_root: str, num_datasets: int, k_values: Optional[Sequence] = 
             report["stages"].append({"k": ki, "group": "across", **st})
         build_tables(work_root, k_values, num_datasets)
     finally:
+        for pk in packed.values():
+            pk.free()
         if own:
             eng.close()
     report["seconds"] = time.time() - t_start

@@ -103,3 +103,24 @@ def test_prefetch_double_buffering_gives_identical_results(engine):
     engine.group_sets_reset()
     engine.prefetch_fasta(views[2])
     assert np.array_equal(engine.group_from_fasta(views[1], 31, keep_set=False)[0], ref[1])
+
+
+def test_pack_once_sweep_k_equals_per_k_pipeline(engine):
+    """khb_pack_group + khb_group_from_packed (pack once, sweep k) == khb_group_from_fasta for every k."""
+    rng = np.random.default_rng(21)
+    groups = [[random_fasta(rng, 40_000 + 777 * j, p_n=0.003) for j in range(3)] + [EDGE_FASTAS[2]] for _ in range(2)]
+    packed = [engine.pack_group(g) for g in groups]
+    info = packed[0].info()
+    assert info["bases"] > 100_000 and info["device_bytes"] < info["n_symbols"]  # 3/8 byte per symbol
+    for k in (9, 31, 45, 64):
+        engine.group_sets_reset()
+        ref = [engine.group_from_fasta(g, k)[0] for g in groups]
+        a_ref = engine.across_groups()[0]
+        engine.group_sets_reset()
+        got = [engine.group_from_packed(p, k)[0] for p in packed]
+        a_got = engine.across_groups()[0]
+        for a, b in zip(ref, got):
+            assert np.array_equal(a, b), k
+        assert np.array_equal(a_ref, a_got), k
+    for p in packed:
+        p.free()
