@@ -22,7 +22,7 @@ int khb_sort_keys_impl(khb_ctx *, void *, void *, const u64 *, int, int, int *);
 int khb_sort_bits_impl(khb_ctx *, void *, void *, const u64 *, int, int, int, int, int *, unsigned short *, unsigned short *);
 int khb_resolve_unique_impl(khb_ctx *, const void *, size_t, int, int, void *, u64 *);
 int khb_resolve_count_impl(khb_ctx *, const void *, size_t, int, int, u32, u32, u64 *, void *, u64 *);
-int khb_pairs_count_impl(khb_ctx *, const void *, const unsigned short *, size_t, int, int, u32, u32, u64 *, void *, u64 *, u64 *);
+int khb_pairs_count_impl(khb_ctx *, const void *, const unsigned short *, size_t, int, int, u32, u32, u32, u64 *, void *, u64 *, u64 *);
 int khb_unique_impl(khb_ctx *, const void *, size_t, int, void *, u64 *);
 int khb_count_runs_impl(khb_ctx *, const void *, size_t, int, u32, u32, u64 *, void *, u32 *, u64 *);
 
@@ -698,7 +698,7 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
             out_keys = (char *)ctx->gs_buf + ctx->gs_len * W;
         }
         u64 *d_hist = ctx->d_mail + 8, *d_runs = ctx->d_mail, *d_pairs = ctx->d_mail + 1;
-        if ((rc = khb_pairs_count_impl(ctx, sorted, spay, n_sym, k, fb, KHB_COUNTER_MAX, nbins, d_hist, out_keys, d_runs, d_pairs))) return rc;
+        if ((rc = khb_pairs_count_impl(ctx, sorted, spay, n_sym, k, fb, KHB_COUNTER_MAX, nbins, (u32)n_genomes, d_hist, out_keys, d_runs, d_pairs))) return rc;
         KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, ctx->d_mail, (nbins + 9) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
         tm.mark();  // 7: count done
         KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -434,167 +434,179 @@ runs_kernel(const Key *__restrict__ in, u64 n, int pshift, u32 cs, u32 nbins, u6
 // order, so the number of genomes containing a k-mer is the number of (key, genome) CHANGES inside its run:
 //   F[i] = key[i] != key[i-1]  ||  gid[i] != gid[i-1]          ("new pair")
 //   c(x) = sum of F over the run of x          (= kmc per genome, set_counts 1, union-sum -- exp_type_1.smk:156-182)
-// pairs_kernel is runs_kernel with that sum in place of the run length: blocked arrangement, one segmented warp
-// scan per thread carries (count so far, mixed flag) of the run that is open at a thread / warp / tile boundary,
-// mixed prefix runs take the out-of-line scan.  It also returns sum F = the sum of the per-genome set sizes.
+//
+// Two kernels:
+//   pairs_kernel       handles every CLEAN run -- a run of equal keys whose neighbours on both sides have a different
+//                      prefix -- with nothing but register compares: blocked arrangement (CQ_ITEMS consecutive keys per
+//                      thread), relations between neighbours collected as bit masks, one segmented warp scan per thread
+//                      carries (pair count, mixed flag) of the run that is open at a thread boundary, and the run open
+//                      at the chunk start is recovered from the keys in front of the chunk (cooperative look-back, 32
+//                      keys per step), so every warp is independent.  Keys of MIXED prefix runs (more than one distinct
+//                      value under one prefix: ~1-2 % of the runs, because the hashed prefix has more slots than there
+//                      are keys) are skipped; the tail of the first run of every mixed prefix run is marked in a bitmap.
+//   mixed_runs_kernel  compacts the bitmap per CTA and resolves one mixed prefix run per thread with a small register
+//                      table of its distinct keys (count, last genome); more than MIXED_MAXD distinct keys under one
+//                      prefix take an exact quadratic fallback.
+// Both add hist[min(c, cs)], emit the distinct keys (unordered) and return sum c = the sum of the per-genome set sizes.
 __device__ __forceinline__ u32 seg_combine(u32 a, u32 b)
 {
     // state = bit31: a run head was seen | bit30: that head's predecessor shares its prefix | low 30 bits: pair count
     return (b >> 31) ? b : ((a & 0xC0000000u) | ((a + b) & 0x3FFFFFFFu));
 }
 
-// Mixed prefix run, per-thread part: is the adjacent run ending at t the FIRST occurrence of its key inside the prefix
-// run?  (Short: a later occurrence finds an earlier one within a few steps because equal keys interleave.)
-template <typename Key>
-__device__ __noinline__ bool mixed_is_first(const Key *__restrict__ in, int pshift, u64 t)
+// Relation bits between two neighbouring keys: bit 0 = they differ, bit 1 = they differ but share the prefix.
+__device__ __forceinline__ u32 key_relation(const Key64 &a, const Key64 &b, int pshift)
 {
-    const Key key = in[t];
-    u64 q = t;
-    while (q > 0) {
-        --q;
-        const Key kq = in[q];
-        if (key_eq(kq, key)) continue;                       // still inside the adjacent run
-        if (key_is_sentinel(kq) || !same_prefix(kq, key, pshift)) return true;
-        // a different key of the same prefix run: keep looking for an earlier occurrence
-        for (;;) {
-            if (q == 0) return true;
-            --q;
-            const Key k2 = in[q];
-            if (key_is_sentinel(k2) || !same_prefix(k2, key, pshift)) return true;
-            if (key_eq(k2, key)) return false;
-        }
-    }
-    return true;
+    const u64 x = a.v ^ b.v;
+    const u32 ne = x != 0 ? 1u : 0u;
+    const u32 sp = (x >> pshift) == 0 ? 2u : 0u;
+    return ne | (ne ? sp : 0u);
+}
+__device__ __forceinline__ u32 key_relation(const Key128 &a, const Key128 &b, int pshift)
+{
+    const u32 ne = key_eq(a, b) ? 0u : 1u;
+    return ne | ((ne && same_prefix(a, b, pshift)) ? 2u : 0u);
 }
 
-// Mixed prefix run, warp-cooperative part: (key, genome) pairs of `key` among the keys AFTER index t inside the prefix
-// run, given the genome of the last counted occurrence.  All 32 lanes scan 32 consecutive keys per step.
+// One warp chunk in registers: CQ_ITEMS consecutive keys per lane with both neighbours, their genome ids (two per
+// word), and the first step of the look-back in front of the chunk (lane i: key begin-1-i and its predecessor).
+template <typename Key> struct PairChunk {
+    Key k[CQ_ITEMS + 2];          // k[0] = predecessor, k[1..ITEMS] = own keys, k[ITEMS+1] = successor
+    u32 gw[CQ_ITEMS / 2], g0;     // own genome ids, packed; predecessor's genome id
+    Key kp, kq;                   // in[begin-1-lane], in[begin-2-lane]   (sentinel where there is none)
+    u32 gp, gq;
+};
+
 template <typename Key>
-__device__ __forceinline__ u32 mixed_pairs_after(const Key *__restrict__ in, const unsigned short *__restrict__ gid, u64 n, int pshift,
-                                                 u64 t, const Key &key, u32 last_g, u32 lane)
+__device__ __forceinline__ void pair_chunk_load(PairChunk<Key> &c, const Key *__restrict__ in, const unsigned short *__restrict__ gid,
+                                                u64 n, u64 tile, u32 lane)
+{
+    constexpr int TILE = 32 * CQ_ITEMS;
+    const u64 begin = tile * TILE;
+    const u32 l0 = lane * CQ_ITEMS;
+    if (begin > 0 && begin + TILE < n) {
+        const unsigned short *gb = gid + begin;
+        load_blocked(in + begin, l0, c.k);
+        const uint4 gv = *(const uint4 *)(gb + l0);  // 8 own genome ids: 16 aligned bytes
+        c.g0 = gb[(int)l0 - 1];
+        c.gw[0] = gv.x; c.gw[1] = gv.y; c.gw[2] = gv.z; c.gw[3] = gv.w;
+    } else {
+        // first / last chunk: indices outside [0, n) read as sentinels, which never equal a real key
+        u32 g[CQ_ITEMS + 1];
+#pragma unroll
+        for (int j = 0; j < CQ_ITEMS + 2; j++) {
+            const u64 x = begin + l0 + j;  // index + 1
+            const bool ok = x >= 1 && x - 1 < n;
+            c.k[j] = ok ? in[x - 1] : sentinel_key<Key>();
+            if (j <= CQ_ITEMS) g[j] = ok ? (u32)gid[x - 1] : 0u;
+        }
+        c.g0 = g[0];
+#pragma unroll
+        for (int j = 0; j < CQ_ITEMS / 2; j++) c.gw[j] = g[1 + 2 * j] | (g[2 + 2 * j] << 16);
+    }
+    c.kp = sentinel_key<Key>();
+    c.kq = sentinel_key<Key>();
+    c.gp = 0;
+    c.gq = 0xffffffffu;
+    if (begin > lane) {
+        const u64 p = begin - 1 - lane;
+        c.kp = in[p];
+        c.gp = gid[p];
+        if (p > 0) { c.kq = in[p - 1]; c.gq = gid[p - 1]; }
+    }
+}
+
+// State (seg_combine encoding) of the run of `k0` that ends right in front of index `begin` (> 0): number of
+// (key, genome) pairs in it and whether the predecessor of its head shares its prefix.  0 if in[begin-1] != k0.
+// Warp-cooperative, 32 keys per step; the first step's keys come preloaded with the chunk, further steps (only for
+// runs that reach back more than 32 keys) load their own.
+template <typename Key>
+__device__ __forceinline__ u32 open_run_state(const Key *__restrict__ in, const unsigned short *__restrict__ gid, u64 begin,
+                                              const Key &k0, int pshift, u32 lane, Key kp, Key kq, u32 gp, u32 gq)
 {
     u32 cnt = 0;
-    for (u64 r0 = t + 1; r0 < n; r0 += 32) {
-        const u64 r = r0 + lane;
-        Key kr = sentinel_key<Key>();
-        u32 g = 0;
-        if (r < n) { kr = in[r]; g = gid[r]; }
-        const bool inside = r < n && !key_is_sentinel(kr) && same_prefix(kr, key, pshift);
-        const u32 out_mask = __ballot_sync(0xffffffffu, !inside);
-        const u32 upto = out_mask ? ((out_mask & (0u - out_mask)) - 1u) : 0xffffffffu;  // lanes before the prefix run ends
-        const u32 eq = __ballot_sync(0xffffffffu, inside && key_eq(kr, key)) & upto;
-        // equal keys come in genome order: a new pair starts where the genome differs from the previous equal key's
-        const u32 before = eq & lanemask_lt();
-        const int prev_lane = before ? 31 - __clz(before) : 0;
-        const u32 gprev = __shfl_sync(0xffffffffu, g, prev_lane);
-        const bool is_eq = (eq >> lane) & 1u;
-        const bool newpair = is_eq && (before ? g != gprev : g != last_g);
-        cnt += __popc(__ballot_sync(0xffffffffu, newpair));
-        if (eq) last_g = __shfl_sync(0xffffffffu, g, 31 - __clz(eq));
-        if (out_mask) break;
+    for (u64 top = begin;;) {            // lanes look at p = top-1-lane (kp, gp) and its predecessor p-1 (kq, gq)
+        const bool have = top > lane;
+        const u64 p = top - 1 - lane;
+        const bool eq = have && key_eq(kp, k0);
+        const u32 neq = __ballot_sync(0xffffffffu, !eq);
+        const u32 inrun = neq ? ((neq & (0u - neq)) - 1u) : 0xffffffffu;  // lanes before the first mismatch
+        const bool mine = (inrun >> lane) & 1u;
+        const bool head = mine && (p == 0 || !key_eq(kq, k0));
+        cnt += __popc(__ballot_sync(0xffffffffu, mine && (head || gp != gq)));
+        const u32 headb = __ballot_sync(0xffffffffu, head);
+        if (headb || neq) {
+            if (cnt == 0) return 0u;
+            const u32 mix = __ballot_sync(0xffffffffu, head && p > 0 && !key_is_sentinel(kq) && same_prefix(kq, k0, pshift));
+            return 0x80000000u | (mix ? 0x40000000u : 0u) | cnt;
+        }
+        top -= 32;  // all 32 keys belong to the run and none is its head: keep walking
+        kp = sentinel_key<Key>();
+        kq = sentinel_key<Key>();
+        gp = 0;
+        gq = 0xffffffffu;
+        if (top > lane) {
+            const u64 q = top - 1 - lane;
+            kp = in[q];
+            gp = gid[q];
+            if (q > 0) { kq = in[q - 1]; gq = gid[q - 1]; }
+        }
     }
-    return cnt;
 }
 
+#ifndef PAIRS_MINB
+#define PAIRS_MINB 5
+#endif
 template <typename Key>
-__global__ void __launch_bounds__(CQ_BLOCK, (sizeof(Key) == 8 ? 1024 : 512) / CQ_BLOCK)
-pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid, u64 n, int pshift, u32 cs, u32 nbins,
-             u64 *__restrict__ hist, Key *__restrict__ out_keys, u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs)
+__global__ void __launch_bounds__(CQ_BLOCK, (sizeof(Key) == 8 ? PAIRS_MINB : 3))
+pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid, u64 n, int pshift, u32 cs, u32 nbins, u32 hot_bin,
+             u64 *__restrict__ hist, Key *__restrict__ out_keys, u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs,
+             unsigned char *__restrict__ mixed_map /* one byte per lane chunk: bit j = key j ends the first run of a mixed prefix run */)
 {
-    // Every WARP owns chunks of 32 x CQ_ITEMS consecutive keys and is completely independent of the other warps of
-    // its CTA (no shared state, no barrier inside the loop): the state of the run that is open at the chunk start
-    // comes from the 32 keys in front of the chunk, which the warp fetches together with the chunk.
     constexpr int TILE = 32 * CQ_ITEMS;
     extern __shared__ u32 sh_hist[];  // [nbins+1]
     const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const u64 ntiles = (n + TILE - 1) / TILE;
+    const u64 stride = (u64)gridDim.x * CQ_WARPS;
     for (u32 i = tid; i <= nbins; i += CQ_BLOCK) sh_hist[i] = 0;
     __syncthreads();
-    for (u64 tile = (u64)blockIdx.x * CQ_WARPS + warp; tile < ntiles; tile += (u64)gridDim.x * CQ_WARPS) {
+    u32 my_pairs = 0, my_ones = 0, my_hots = 0;  // multiplicities 1 and hot_bin are counted in registers
+    u64 tile = (u64)blockIdx.x * CQ_WARPS + warp;
+    PairChunk<Key> c;
+    if (tile < ntiles) pair_chunk_load(c, in, gid, n, tile, lane);
+    while (tile < ntiles) {
+        // the next chunk's loads are in flight while this one is processed
+        PairChunk<Key> nx;
+        const u64 next = tile + stride;
+        if (next < ntiles) pair_chunk_load(nx, in, gid, n, next, lane);
         const u64 begin = tile * TILE;
-        const u32 nloc = (u32)(n - begin < (u64)TILE ? n - begin : (u64)TILE);
-        const bool last_tile = begin + TILE >= n;
-        const u32 l0 = lane * CQ_ITEMS;
-        Key k[CQ_ITEMS + 2];   // k[0] = predecessor, k[1..ITEMS] = own keys, k[ITEMS+1] = successor
-        u32 g[CQ_ITEMS + 1];   // g[0] = predecessor's genome, g[1..ITEMS] = own
-        if (begin > 0 && !last_tile) {
-            const unsigned short *gb = gid + begin;
-            load_blocked(in + begin, l0, k);
-            const uint4 gv = *(const uint4 *)(gb + l0);  // 8 own genome ids: 16 aligned bytes
-            g[0] = gb[(int)l0 - 1];
-            g[1] = gv.x & 0xffffu; g[2] = gv.x >> 16; g[3] = gv.y & 0xffffu; g[4] = gv.y >> 16;
-            g[5] = gv.z & 0xffffu; g[6] = gv.z >> 16; g[7] = gv.w & 0xffffu; g[8] = gv.w >> 16;
-        } else {
+        u32 g[CQ_ITEMS + 1];
+        g[0] = c.g0;
 #pragma unroll
-            for (int j = 0; j < CQ_ITEMS + 2; j++) {
-                const u64 x = begin + l0 + j;  // index + 1
-                const bool ok = x >= 1 && x - 1 < n;
-                k[j] = ok ? in[x - 1] : sentinel_key<Key>();
-                if (j <= CQ_ITEMS) g[j] = ok ? (u32)gid[x - 1] : 0u;
-            }
-        }
-        u32 open_state;
-        {
-            // state of the run open at the chunk start, from the 32 keys in front of the chunk (fetched with it)
-            Key back = sentinel_key<Key>();
-            u32 gback = 0;
-            if (begin > lane) { back = in[begin - 1 - lane]; gback = gid[begin - 1 - lane]; }
-            const Key k0 = shfl_key(k[1], 0);
-            u32 state = 0;
-            if (begin > 0 && !key_is_sentinel(k0)) {
-                const u32 eq = __ballot_sync(0xffffffffu, begin > lane && key_eq(back, k0));
-                const u32 d = (u32)__ffs(~eq) - 1u;  // consecutive equal keys in front of the tile (32 if ~eq == 0)
-                if (d > 0) {
-                    if (d < 32) {
-                        const u32 gnext = __shfl_down_sync(0xffffffffu, gback, 1);  // genome of the key one further back
-                        const bool f = lane < d && (lane == d - 1 || gback != gnext);
-                        const u32 cnt = __popc(__ballot_sync(0xffffffffu, f));
-                        const Key pk = shfl_key(back, (int)d);
-                        const bool mix = begin > d && !key_is_sentinel(pk) && same_prefix(pk, k0, pshift);
-                        state = 0x80000000u | (mix ? 0x40000000u : 0u) | cnt;
-                    } else {
-                        // a run longer than 32 keys reaches the tile: count its pairs serially (rare)
-                        u32 cnt = 0, mix = 0;
-                        if (lane == 0) {
-                            u64 p = begin;  // walk back while the key equals k0
-                            u32 lastg = 0xffffffffu;
-                            while (p > 0 && key_eq(in[p - 1], k0)) {
-                                --p;
-                                const u32 gg = gid[p];
-                                if (gg != lastg) { cnt++; lastg = gg; }
-                            }
-                            if (p > 0) {
-                                const Key pk = in[p - 1];
-                                mix = (!key_is_sentinel(pk) && same_prefix(pk, k0, pshift)) ? 1u : 0u;
-                            }
-                        }
-                        cnt = __shfl_sync(0xffffffffu, cnt, 0);
-                        mix = __shfl_sync(0xffffffffu, mix, 0);
-                        state = 0x80000000u | (mix << 30) | cnt;
-                    }
-                }
-            }
-            open_state = state;
-        }
-        // per key: head / tail of its key run, "new pair" flag, prefix relation to the neighbours
-        u32 headm = 0, tailm = 0, fm = 0, hmix = 0, tmix = 0;
+        for (int j = 0; j < CQ_ITEMS / 2; j++) { g[1 + 2 * j] = c.gw[j] & 0xffffu; g[2 + 2 * j] = c.gw[j] >> 16; }
+        // run open at the chunk start (lane 0's first key continues it)
+        u32 open_state = 0;
+        if (begin > 0) open_state = open_run_state(in, gid, begin, shfl_key(c.k[1], 0), pshift, lane, c.kp, c.kq, c.gp, c.gq);
+        // relations between neighbours, one bit per own key:
+        //   headm: differs from its predecessor       hmix: ... which shares its prefix
+        //   tailm: differs from its successor         tmix: ... which shares its prefix
+        //   fm   : starts a new (key, genome) pair
+        u32 nem = 0, spm = 0, gdm = 0;
 #pragma unroll
-        for (int j = 0; j < CQ_ITEMS; j++) {
-            const u32 l = l0 + j;
-            const Key key = k[j + 1];
-            const bool valid = l < nloc && !key_is_sentinel(key);
-            const bool first_of_all = begin == 0 && l == 0;
-            const bool last_of_all = last_tile && l + 1 >= nloc;
-            const bool head = valid && (first_of_all || !key_eq(key, k[j]));
-            const bool tail = valid && (last_of_all || !key_eq(key, k[j + 2]));
-            const bool f = valid && (head || g[j + 1] != g[j]);
-            const bool pm = head && !first_of_all && !key_is_sentinel(k[j]) && same_prefix(k[j], key, pshift);
-            const bool nm = tail && !last_of_all && !key_is_sentinel(k[j + 2]) && same_prefix(k[j + 2], key, pshift);
-            headm |= (head ? 1u : 0u) << j;
-            tailm |= (tail ? 1u : 0u) << j;
-            fm |= (f ? 1u : 0u) << j;
-            hmix |= (pm ? 1u : 0u) << j;
-            tmix |= (nm ? 1u : 0u) << j;
+        for (int j = 0; j <= CQ_ITEMS; j++) {
+            const u32 r = key_relation(c.k[j], c.k[j + 1], pshift);
+            nem |= (r & 1u) << j;
+            spm |= (r >> 1) << j;
+            if (j < CQ_ITEMS) gdm |= (g[j] != g[j + 1] ? 1u : 0u) << j;
+        }
+        constexpr u32 OWN = (1u << CQ_ITEMS) - 1u;
+        const u32 headm = nem & OWN, hmix = spm & OWN, tmix = (spm >> 1) & OWN;
+        u32 tailm = (nem >> 1) & OWN;
+        const u32 fm = headm | gdm;
+        if (key_is_sentinel(c.k[CQ_ITEMS])) {  // the padding at the very end of the sorted array: never a result
+#pragma unroll
+            for (int j = 0; j < CQ_ITEMS; j++)
+                if (key_is_sentinel(c.k[j + 1])) tailm &= ~(1u << j);
         }
         // segmented scan of (count, mixed) over threads
         u32 st;
@@ -613,74 +625,205 @@ pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid,
         u32 excl = __shfl_up_sync(0xffffffffu, inc, 1);
         if (lane == 0) excl = 0;
         const u32 carry = seg_combine(open_state, excl);
-        // resolve every tail.  Pure prefix runs need nothing but the carried count; in a mixed prefix run a tail first
-        // checks (short scan) whether it is the first occurrence of its key, and if so queues the forward scan, which the
-        // whole warp then runs cooperatively.
-        u32 emitm = 0, pendm = 0;
-        u32 pend_cnt[CQ_ITEMS];
+        // resolve every tail
+        u32 emitm = 0, itemm = 0;
         u32 open_cnt = carry & 0x3FFFFFFFu;
-        bool open_mix = (carry >> 30) & 1u;
+        u32 open_mix = (carry >> 30) & 1u;
 #pragma unroll
         for (int j = 0; j < CQ_ITEMS; j++) {
-            pend_cnt[j] = 0;
             if ((headm >> j) & 1u) { open_cnt = 0; open_mix = (hmix >> j) & 1u; }
             open_cnt += (fm >> j) & 1u;
             if ((tailm >> j) & 1u) {
-                bool first = true;
-                const bool mixed_after = (tmix >> j) & 1u;
-                if (open_mix) first = mixed_is_first(in, pshift, begin + l0 + j);
-                if (first) {
+                const u32 after = (tmix >> j) & 1u;
+                if ((open_mix | after) == 0) {
                     emitm |= 1u << j;
-                    if (mixed_after) {
-                        pendm |= 1u << j;
-                        pend_cnt[j] = open_cnt;
+                    my_pairs += open_cnt;
+                    if (open_cnt == 1u) my_ones++;
+                    else if (open_cnt == hot_bin) my_hots++;
+                    else {
+                        const u32 cc = open_cnt > cs ? cs : open_cnt;
+                        if (cc <= nbins) atomicAdd(&sh_hist[cc], 1u);
+                    }
+                } else if (open_mix == 0) {
+                    itemm |= 1u << j;
+                }
+            }
+        }
+        mixed_map[tile * 32 + lane] = (unsigned char)itemm;
+        // per warp: one atomicAdd reserves the output range
+        const u32 mine = __popc(emitm);
+        const u32 incl = warp_incl_sum<u32>(mine);
+        const u32 wtotal = __shfl_sync(0xffffffffu, incl, 31);
+        u64 wbase = 0;
+        if (lane == 31 && wtotal) wbase = atomicAdd(d_cursor, (u64)wtotal);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        if (out_keys != nullptr && mine) {
+            Key *dst = out_keys + wbase + (incl - mine);
+#pragma unroll
+            for (int j = 0; j < CQ_ITEMS; j++)
+                if ((emitm >> j) & 1u) *dst++ = c.k[j + 1];
+        }
+        c = nx;
+        tile = next;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, o);
+        my_ones += __shfl_xor_sync(0xffffffffu, my_ones, o);
+        my_hots += __shfl_xor_sync(0xffffffffu, my_hots, o);
+    }
+    if (lane == 0) {
+        if (my_pairs) atomicAdd(d_pairs, (u64)my_pairs);
+        if (my_ones && 1u <= nbins) atomicAdd(&sh_hist[1], my_ones);   // cs >= 1
+        if (my_hots) atomicAdd(&sh_hist[hot_bin], my_hots);            // hot_bin <= min(cs, nbins) or 0 (never matched)
+    }
+    __syncthreads();
+    for (u32 i = tid; i <= nbins; i += CQ_BLOCK) {
+        const u32 cc = sh_hist[i];
+        if (cc) atomicAdd(&hist[i], (u64)cc);
+    }
+}
+
+#define MIXED_BLOCK 256
+#define MIXED_MAXD 6
+// Bitmap -> work list of the marked tails (positions), one list slot reservation per CTA and span.
+__global__ void __launch_bounds__(MIXED_BLOCK)
+mixed_collect_kernel(const u32 *__restrict__ mixed_map, u64 nwords, u32 *__restrict__ items, u64 *__restrict__ d_nitems)
+{
+    __shared__ u32 s_count;
+    __shared__ u64 s_base;
+    const u32 tid = threadIdx.x;
+    for (u64 w0 = (u64)blockIdx.x * MIXED_BLOCK; w0 < nwords; w0 += (u64)gridDim.x * MIXED_BLOCK) {
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        u32 bits = (w0 + tid < nwords) ? mixed_map[w0 + tid] : 0u;  // bit i <-> key 32 * (w0 + tid) + i
+        u32 at = 0;
+        if (bits) at = atomicAdd(&s_count, (u32)__popc(bits));
+        __syncthreads();
+        if (tid == 0 && s_count) s_base = atomicAdd(d_nitems, (u64)s_count);
+        __syncthreads();
+        if (bits) {
+            u64 pos = s_base + at;
+            while (bits) {
+                const u32 b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                items[pos++] = (u32)((w0 + tid) * 32 + b);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Exact fallback for a mixed prefix run [s, e) with more than MIXED_MAXD distinct keys: every first occurrence counts
+// its own pairs by scanning forward.  Quadratic in the run length; practically never taken for hashed keys.
+template <typename Key>
+__device__ __noinline__ void mixed_run_slow(const Key *__restrict__ in, const unsigned short *__restrict__ gid, u64 s, u64 e, u32 cs,
+                                            u32 nbins, u32 *sh_hist, Key *__restrict__ out_keys, u64 *__restrict__ d_cursor,
+                                            u64 *__restrict__ d_pairs)
+{
+    for (u64 i = s; i < e; i++) {
+        const Key ki = in[i];
+        bool first = true;
+        for (u64 q = s; q < i && first; q++) first = !key_eq(in[q], ki);
+        if (!first) continue;
+        u32 cnt = 1, lastg = gid[i];
+        for (u64 r = i + 1; r < e; r++) {
+            if (!key_eq(in[r], ki)) continue;
+            const u32 gr = gid[r];
+            if (gr != lastg) { cnt++; lastg = gr; }
+        }
+        const u32 c = cnt > cs ? cs : cnt;
+        if (c <= nbins) atomicAdd(&sh_hist[c], 1u);
+        atomicAdd(d_pairs, (u64)cnt);
+        const u64 pos = atomicAdd(d_cursor, 1ull);
+        if (out_keys != nullptr) out_keys[pos] = ki;
+    }
+}
+
+// One mixed prefix run per thread: a small register table of its distinct keys (pair count, last genome seen).
+template <typename Key>
+__global__ void __launch_bounds__(MIXED_BLOCK)
+mixed_runs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid, u64 n, int pshift, u32 cs, u32 nbins,
+                  u64 *__restrict__ hist, Key *__restrict__ out_keys, u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs,
+                  const u32 *__restrict__ items, const u64 *__restrict__ d_nitems)
+{
+    extern __shared__ u32 sh_hist[];            // [nbins+1]
+    const u32 tid = threadIdx.x, lane = lane_id();
+    const u64 count = *d_nitems;
+    if ((u64)blockIdx.x * MIXED_BLOCK >= count) return;
+    for (u32 i = tid; i <= nbins; i += MIXED_BLOCK) sh_hist[i] = 0;
+    __syncthreads();
+    for (u64 i0 = (u64)blockIdx.x * MIXED_BLOCK; i0 < count; i0 += (u64)gridDim.x * MIXED_BLOCK) {
+        const u64 i = i0 + tid;
+        Key lk[MIXED_MAXD];
+        u32 lc[MIXED_MAXD], lg[MIXED_MAXD];
+        u32 d = 0, pairs = 0;
+        if (i < count) {
+            const u64 t = items[i];
+            const Key key0 = in[t];
+            u64 s = t;  // the first run of the prefix run is all key0 and starts the prefix run
+            while (s > 0 && key_eq(in[s - 1], key0)) --s;
+            bool overflow = false;
+            u64 e = s;
+            for (; e < n; e++) {
+                const Key ke = in[e];
+                if (key_is_sentinel(ke) || !same_prefix(ke, key0, pshift)) break;
+                if (overflow) continue;  // only looking for the end of the prefix run
+                const u32 ge = gid[e];
+                bool found = false;
+#pragma unroll
+                for (int q = 0; q < MIXED_MAXD; q++) {
+                    if ((u32)q < d && key_eq(lk[q], ke)) {
+                        found = true;
+                        if (lg[q] != ge) { lc[q]++; lg[q] = ge; }
+                    }
+                }
+                if (!found) {
+                    if (d < MIXED_MAXD) {
+#pragma unroll
+                        for (int q = 0; q < MIXED_MAXD; q++)
+                            if ((u32)q == d) { lk[q] = ke; lc[q] = 1; lg[q] = ge; }
+                        d++;
                     } else {
-                        const u32 c = open_cnt > cs ? cs : open_cnt;
+                        overflow = true;
+                    }
+                }
+            }
+            if (overflow) {
+                mixed_run_slow(in, gid, s, e, cs, nbins, sh_hist, out_keys, d_cursor, d_pairs);
+                d = 0;
+            } else {
+#pragma unroll
+                for (int q = 0; q < MIXED_MAXD; q++) {
+                    if ((u32)q < d) {
+                        pairs += lc[q];
+                        const u32 c = lc[q] > cs ? cs : lc[q];
                         if (c <= nbins) atomicAdd(&sh_hist[c], 1u);
                     }
                 }
             }
         }
-        // warp-cooperative forward scans for the queued owners (rare)
-#pragma unroll
-        for (int j = 0; j < CQ_ITEMS; j++) {
-            u32 need = __ballot_sync(0xffffffffu, (pendm >> j) & 1u);
-            while (need) {
-                const int src = __ffs(need) - 1;
-                need &= need - 1;
-                const u64 t = begin + (u64)__shfl_sync(0xffffffffu, l0, src) + j;
-                const Key key = shfl_key(k[j + 1], src);
-                const u32 last_g = __shfl_sync(0xffffffffu, g[j + 1], src);
-                const u32 extra = mixed_pairs_after(in, gid, n, pshift, t, key, last_g, lane);
-                if ((int)lane == src) {
-                    const u32 tot = pend_cnt[j] + extra;
-                    const u32 c = tot > cs ? cs : tot;
-                    if (c <= nbins) atomicAdd(&sh_hist[c], 1u);
-                }
-            }
-        }
         // per warp: one atomicAdd reserves the output range, one adds the pair count
-        const u32 mine = __popc(emitm);
-        const u32 incl = warp_incl_sum<u32>(mine);
+        const u32 incl = warp_incl_sum<u32>(d);
         const u32 wtotal = __shfl_sync(0xffffffffu, incl, 31);
-        u32 pairs = __popc(fm);
+        u32 wpairs = pairs;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
+        for (int o = 16; o > 0; o >>= 1) wpairs += __shfl_xor_sync(0xffffffffu, wpairs, o);
         u64 wbase = 0;
         if (lane == 31) {
             if (wtotal) wbase = atomicAdd(d_cursor, (u64)wtotal);
-            if (pairs) atomicAdd(d_pairs, (u64)pairs);
+            if (wpairs) atomicAdd(d_pairs, (u64)wpairs);
         }
         wbase = __shfl_sync(0xffffffffu, wbase, 31);
-        if (out_keys != nullptr && mine) {
-            u64 pos = wbase + (incl - mine);
+        if (out_keys != nullptr) {
+            const u64 pos = wbase + (incl - d);
 #pragma unroll
-            for (int j = 0; j < CQ_ITEMS; j++)
-                if ((emitm >> j) & 1u) out_keys[pos++] = k[j + 1];
+            for (int q = 0; q < MIXED_MAXD; q++)
+                if ((u32)q < d) out_keys[pos + q] = lk[q];
         }
     }
     __syncthreads();
-    for (u32 i = tid; i <= nbins; i += CQ_BLOCK) {
+    for (u32 i = tid; i <= nbins; i += MIXED_BLOCK) {
         const u32 c = sh_hist[i];
         if (c) atomicAdd(&hist[i], (u64)c);
     }
@@ -790,23 +933,47 @@ int khb_resolve_count_impl(khb_ctx *ctx, const void *d_sorted, size_t n, int k, 
 
 // Single-sort group path: histogram of genomes-per-k-mer from prefix-sorted (key, genome id) pairs.
 int khb_pairs_count_impl(khb_ctx *ctx, const void *d_sorted, const unsigned short *d_gid, size_t n, int k, int pshift, u32 cs, u32 nbins,
-                         u64 *d_hist, void *d_out_keys, u64 *d_runs, u64 *d_pairs)
+                         u32 n_genomes, u64 *d_hist, void *d_out_keys, u64 *d_runs, u64 *d_pairs)
 {
     if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_pairs_count: k=%d outside 1..64", k);
     if (nbins < 1 || nbins > 8192) return khb_fail(ctx, KHB_ERR_ARG, "khb_pairs_count: nbins=%u outside 1..8192", nbins);
+    if ((u64)n >= (1ull << 32)) return khb_fail(ctx, KHB_ERR_ARG, "khb_pairs_count: %zu keys in one group (limit 2^32 - 1)", n);
     KHB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, ((size_t)nbins + 1) * sizeof(u64), ctx->stream));
     KHB_CUDA(ctx, cudaMemsetAsync(d_runs, 0, sizeof(u64), ctx->stream));
     KHB_CUDA(ctx, cudaMemsetAsync(d_pairs, 0, sizeof(u64), ctx->stream));
     if (n == 0) return KHB_OK;
-    const u64 ntiles = div_up(n, CQ_BLOCK * CQ_ITEMS);  // CTA-sized groups of warp chunks
-    u64 grid = (u64)ctx->num_sms * (k <= 32 ? 2048 : 1024) / CQ_BLOCK;
-    if (grid > ntiles) grid = ntiles;
+    const u64 nchunks = div_up(n, 32 * CQ_ITEMS);  // warp chunks
+    const int minb = k <= 32 ? PAIRS_MINB : 3;     // resident CTAs per SM (launch bounds): one persistent wave
+    u64 grid = (u64)ctx->num_sms * minb;
+    if (grid > div_up(nchunks, CQ_WARPS)) grid = div_up(nchunks, CQ_WARPS);
     const size_t shm = ((size_t)nbins + 1) * sizeof(u32);
+    // multiplicity counted in registers besides 1: "in every genome of the group"
+    const u32 hot = (n_genomes >= 2 && n_genomes <= nbins && n_genomes <= cs) ? n_genomes : 0u;
+    // scratch: [item count][bitmap of the mixed prefix runs: one byte per 8 keys, written completely by pairs_kernel]
+    //          [work list: at most one entry per two keys]
+    const u64 nwords = nchunks * (32 * CQ_ITEMS / 32);
+    void *p;
+    int rc = khb_scratch_get(ctx, SCR_FLAGS, 64 + nwords * sizeof(u32) + (n / 2 + 2) * sizeof(u32), &p);
+    if (rc) return rc;
+    u64 *d_nitems = (u64 *)p;
+    u32 *d_map = (u32 *)((char *)p + 64);
+    u32 *d_items = d_map + nwords;
+    KHB_CUDA(ctx, cudaMemsetAsync(d_nitems, 0, sizeof(u64), ctx->stream));
+    u64 grid2 = div_up(nwords, MIXED_BLOCK);
+    if (grid2 > (u64)ctx->num_sms * 8) grid2 = (u64)ctx->num_sms * 8;
+    const u64 grid3 = (u64)ctx->num_sms * 4;  // CTAs past the item count exit at once
     khb_prof_begin(ctx, KHB_K_RLE);
     if (k <= 32)
-        pairs_kernel<Key64><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const Key64 *)d_sorted, d_gid, n, pshift, cs, nbins, d_hist, (Key64 *)d_out_keys, d_runs, d_pairs);
+        pairs_kernel<Key64><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const Key64 *)d_sorted, d_gid, n, pshift, cs, nbins, hot, d_hist, (Key64 *)d_out_keys, d_runs, d_pairs, (unsigned char *)d_map);
     else
-        pairs_kernel<Key128><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const Key128 *)d_sorted, d_gid, n, pshift, cs, nbins, d_hist, (Key128 *)d_out_keys, d_runs, d_pairs);
+        pairs_kernel<Key128><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const Key128 *)d_sorted, d_gid, n, pshift, cs, nbins, hot, d_hist, (Key128 *)d_out_keys, d_runs, d_pairs, (unsigned char *)d_map);
+    KHB_LAUNCH_CHECK(ctx);
+    mixed_collect_kernel<<<(unsigned)grid2, MIXED_BLOCK, 0, ctx->stream>>>(d_map, nwords, d_items, d_nitems);
+    KHB_LAUNCH_CHECK(ctx);
+    if (k <= 32)
+        mixed_runs_kernel<Key64><<<(unsigned)grid3, MIXED_BLOCK, shm, ctx->stream>>>((const Key64 *)d_sorted, d_gid, n, pshift, cs, nbins, d_hist, (Key64 *)d_out_keys, d_runs, d_pairs, d_items, d_nitems);
+    else
+        mixed_runs_kernel<Key128><<<(unsigned)grid3, MIXED_BLOCK, shm, ctx->stream>>>((const Key128 *)d_sorted, d_gid, n, pshift, cs, nbins, d_hist, (Key128 *)d_out_keys, d_runs, d_pairs, d_items, d_nitems);
     KHB_LAUNCH_CHECK(ctx);
     khb_prof_end(ctx, KHB_K_RLE, (u64)n * ((k <= 32 ? 8 : 16) + 2));
     return KHB_OK;

@@ -1,6 +1,6 @@
-"""Summarise an ncu report: key raw metrics + top stall SASS lines.  usage: python scripts/ncu_top.py report.ncu-rep [n]"""
+"""Summarise an ncu report: key raw metrics + top stall SASS lines.  usage: python scripts/ncu_top.py report.ncu-rep [n] [kernel-index]"""
 import csv, subprocess, sys, io
-rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 30; kidx = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
@@ -18,11 +18,12 @@ for i, h in enumerate(hdr):
         if max(vals) > 0.3: print(f"  stall {h.split('issue_stalled_')[1].split('_per_')[0]:20s} {vals}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hdr = None; data = []
+hdr = None; data = []; seen = -1
 for r in rows:
     if r and r[0] == "Address":
-        if hdr is not None: break
-        hdr = r; continue
+        seen += 1
+        if seen > kidx: break
+        hdr = r; data = []; continue
     if hdr and len(r) == len(hdr): data.append(r)
 iS = hdr.index("# Samples"); iSrc = hdr.index("Source"); iInst = hdr.index("Instructions Executed")
 tot = sum(int(r[iS] or 0) for r in data); ninst = sum(int(r[iInst] or 0) for r in data)
