@@ -20,6 +20,7 @@
 // Algorithmic bytes: unique W*n + W*distinct;  rle W*n (+ W*runs if keys are emitted, + 4*runs for counters).
 #include "khb_common.cuh"
 #include "lookback.cuh"
+#include <stdlib.h>
 
 #define CP_BLOCK 512
 #define CP_WARPS (CP_BLOCK / 32)
@@ -472,9 +473,9 @@ __device__ __forceinline__ u32 key_relation(const Key128 &a, const Key128 &b, in
 // word), and the first step of the look-back in front of the chunk (lane i: key begin-1-i and its predecessor).
 template <typename Key> struct PairChunk {
     Key k[CQ_ITEMS + 2];          // k[0] = predecessor, k[1..ITEMS] = own keys, k[ITEMS+1] = successor
-    u32 gw[CQ_ITEMS / 2], g0;     // own genome ids, packed; predecessor's genome id
+    u32 gw[CQ_ITEMS / 2], g0w;    // own genome ids, packed; the word in front of them (predecessor's id on top)
     Key kp, kq;                   // in[begin-1-lane], in[begin-2-lane]   (sentinel where there is none)
-    u32 gp, gq;
+    unsigned short gp, gq;        // kept as loaded: widening at the point of use keeps the loads free of consumers
 };
 
 template <typename Key>
@@ -488,7 +489,7 @@ __device__ __forceinline__ void pair_chunk_load(PairChunk<Key> &c, const Key *__
         const unsigned short *gb = gid + begin;
         load_blocked(in + begin, l0, c.k);
         const uint4 gv = *(const uint4 *)(gb + l0);  // 8 own genome ids: 16 aligned bytes
-        c.g0 = gb[(int)l0 - 1];
+        c.g0w = *(const u32 *)(gb + (int)l0 - 2);     // 4-byte aligned: begin and l0 are multiples of 8
         c.gw[0] = gv.x; c.gw[1] = gv.y; c.gw[2] = gv.z; c.gw[3] = gv.w;
     } else {
         // first / last chunk: indices outside [0, n) read as sentinels, which never equal a real key
@@ -500,14 +501,14 @@ __device__ __forceinline__ void pair_chunk_load(PairChunk<Key> &c, const Key *__
             c.k[j] = ok ? in[x - 1] : sentinel_key<Key>();
             if (j <= CQ_ITEMS) g[j] = ok ? (u32)gid[x - 1] : 0u;
         }
-        c.g0 = g[0];
+        c.g0w = g[0] << 16;
 #pragma unroll
         for (int j = 0; j < CQ_ITEMS / 2; j++) c.gw[j] = g[1 + 2 * j] | (g[2 + 2 * j] << 16);
     }
     c.kp = sentinel_key<Key>();
     c.kq = sentinel_key<Key>();
     c.gp = 0;
-    c.gq = 0xffffffffu;
+    c.gq = 0;
     if (begin > lane) {
         const u64 p = begin - 1 - lane;
         c.kp = in[p];
@@ -554,11 +555,10 @@ __device__ __forceinline__ u32 open_run_state(const Key *__restrict__ in, const 
     }
 }
 
-#ifndef PAIRS_MINB
-#define PAIRS_MINB 5
-#endif
-template <typename Key>
-__global__ void __launch_bounds__(CQ_BLOCK, (sizeof(Key) == 8 ? PAIRS_MINB : 3))
+// PF: the next chunk's loads are issued before the current chunk is processed (more registers, fewer resident warps).
+template <typename Key, bool PF> struct PairsCfg { static constexpr int MINB = sizeof(Key) == 8 ? (PF ? 5 : 8) : (PF ? 3 : 4); };
+template <typename Key, bool PF>
+__global__ void __launch_bounds__(CQ_BLOCK, (PairsCfg<Key, PF>::MINB))
 pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid, u64 n, int pshift, u32 cs, u32 nbins, u32 hot_bin,
              u64 *__restrict__ hist, Key *__restrict__ out_keys, u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs,
              unsigned char *__restrict__ mixed_map /* one byte per lane chunk: bit j = key j ends the first run of a mixed prefix run */)
@@ -573,15 +573,19 @@ pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid,
     u32 my_pairs = 0, my_ones = 0, my_hots = 0;  // multiplicities 1 and hot_bin are counted in registers
     u64 tile = (u64)blockIdx.x * CQ_WARPS + warp;
     PairChunk<Key> c;
-    if (tile < ntiles) pair_chunk_load(c, in, gid, n, tile, lane);
+    if (PF && tile < ntiles) pair_chunk_load(c, in, gid, n, tile, lane);
     while (tile < ntiles) {
-        // the next chunk's loads are in flight while this one is processed
+        // PF: the next chunk's loads are in flight while this one is processed
         PairChunk<Key> nx;
         const u64 next = tile + stride;
-        if (next < ntiles) pair_chunk_load(nx, in, gid, n, next, lane);
+        if (PF) {
+            if (next < ntiles) pair_chunk_load(nx, in, gid, n, next, lane);
+        } else {
+            pair_chunk_load(c, in, gid, n, tile, lane);
+        }
         const u64 begin = tile * TILE;
         u32 g[CQ_ITEMS + 1];
-        g[0] = c.g0;
+        g[0] = c.g0w >> 16;
 #pragma unroll
         for (int j = 0; j < CQ_ITEMS / 2; j++) { g[1 + 2 * j] = c.gw[j] & 0xffffu; g[2 + 2 * j] = c.gw[j] >> 16; }
         // run open at the chunk start (lane 0's first key continues it)
@@ -663,7 +667,7 @@ pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid,
             for (int j = 0; j < CQ_ITEMS; j++)
                 if ((emitm >> j) & 1u) *dst++ = c.k[j + 1];
         }
-        c = nx;
+        if (PF) c = nx;
         tile = next;
     }
 #pragma unroll
@@ -943,7 +947,13 @@ int khb_pairs_count_impl(khb_ctx *ctx, const void *d_sorted, const unsigned shor
     KHB_CUDA(ctx, cudaMemsetAsync(d_pairs, 0, sizeof(u64), ctx->stream));
     if (n == 0) return KHB_OK;
     const u64 nchunks = div_up(n, 32 * CQ_ITEMS);  // warp chunks
-    const int minb = k <= 32 ? PAIRS_MINB : 3;     // resident CTAs per SM (launch bounds): one persistent wave
+    static int pf = -1;
+    if (pf < 0) {
+        const char *e = getenv("KHB_PAIRS_PREFETCH");
+        pf = e ? atoi(e) : 0;  // measured on config 2: 2.1 ms per group without, 2.3 ms with (fewer resident warps)
+    }
+    const int minb = k <= 32 ? (pf ? PairsCfg<Key64, true>::MINB : PairsCfg<Key64, false>::MINB)
+                             : (pf ? PairsCfg<Key128, true>::MINB : PairsCfg<Key128, false>::MINB);  // resident CTAs per SM: one persistent wave
     u64 grid = (u64)ctx->num_sms * minb;
     if (grid > div_up(nchunks, CQ_WARPS)) grid = div_up(nchunks, CQ_WARPS);
     const size_t shm = ((size_t)nbins + 1) * sizeof(u32);
@@ -963,10 +973,10 @@ int khb_pairs_count_impl(khb_ctx *ctx, const void *d_sorted, const unsigned shor
     if (grid2 > (u64)ctx->num_sms * 8) grid2 = (u64)ctx->num_sms * 8;
     const u64 grid3 = (u64)ctx->num_sms * 4;  // CTAs past the item count exit at once
     khb_prof_begin(ctx, KHB_K_RLE);
-    if (k <= 32)
-        pairs_kernel<Key64><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const Key64 *)d_sorted, d_gid, n, pshift, cs, nbins, hot, d_hist, (Key64 *)d_out_keys, d_runs, d_pairs, (unsigned char *)d_map);
-    else
-        pairs_kernel<Key128><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const Key128 *)d_sorted, d_gid, n, pshift, cs, nbins, hot, d_hist, (Key128 *)d_out_keys, d_runs, d_pairs, (unsigned char *)d_map);
+#define PAIRS_LAUNCH(KEY, PFV) pairs_kernel<KEY, PFV><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const KEY *)d_sorted, d_gid, n, pshift, cs, nbins, hot, d_hist, (KEY *)d_out_keys, d_runs, d_pairs, (unsigned char *)d_map)
+    if (k <= 32) { if (pf) PAIRS_LAUNCH(Key64, true); else PAIRS_LAUNCH(Key64, false); }
+    else { if (pf) PAIRS_LAUNCH(Key128, true); else PAIRS_LAUNCH(Key128, false); }
+#undef PAIRS_LAUNCH
     KHB_LAUNCH_CHECK(ctx);
     mixed_collect_kernel<<<(unsigned)grid2, MIXED_BLOCK, 0, ctx->stream>>>(d_map, nwords, d_items, d_nitems);
     KHB_LAUNCH_CHECK(ctx);
