@@ -206,6 +206,33 @@ KHB_API int khb_group_sets_export(khb_ctx *ctx, void *h_out); /* retained keys a
 KHB_API int khb_group_sets_append_host(khb_ctx *ctx, int k, const void *h_keys, uint64_t n_keys, int n_groups);
 KHB_API int khb_group_sets_reset(khb_ctx *ctx);
 
+/* ---- experiment type 2: pivot analysis (next row N1 of SURVEY.md section 8f) -------------------------------------- */
+
+/* One group of experiment type 2 for one k: `pk` holds the group's rest-of-set genomes followed by the PIVOT genome as
+ * its LAST member (khb_pack_group order).  Replaces, for one (k, dataset): build_kmc_database_on_{genome,pivot}_exp_type_2,
+ * transform_{genome,pivot}_to_set_exp_type2, within_group_union_exp_type2, pivot_intersect_within_group_exp_type2,
+ * pivot_subtract_within_group_exp_type2 and within_group_histogram_exp_type2 (exp_type_2.smk:297-393):
+ *   h_hist[c], c = 1..nbins = number of pivot k-mers x with 1 + #{rest genomes containing x} = c
+ *   -> h_hist[1] is the size of `kmc_tools simple pivot rest kmers_subtract` (its histogram has that one row),
+ *      h_hist[c >= 2] is the histogram of `kmc_tools simple pivot rest intersect -ocsum`.
+ * If keep_sets != 0 the rest-of-set union (transform_rest_of_set_to_single_counts, exp_type_2.smk:428-438) and the pivot's
+ * k-mer set stay on the device for khb_pivot_across().  Do not mix with khb_group_from_* in one store
+ * (khb_group_sets_reset() clears both). */
+KHB_API int khb_pivot_group_from_packed(khb_ctx *ctx, int k, const khb_packed *pk, uint32_t nbins, uint64_t *h_hist,
+                                int keep_sets, khb_stats *stats);
+KHB_API int khb_pivot_sets_info(khb_ctx *ctx, int *n_pivots, uint64_t *n_pivot_keys, uint64_t *n_union_keys);
+
+/* Across groups, for every retained pivot j = 1..G at once: rules across_group_union_for_pivot_exp_type2,
+ * pivot_{intersect,subtract}_across_group_exp_type2 and across_group_histogram_exp_type2 (exp_type_2.smk:440-508).
+ *   h_hists[(j-1) * (nbins+1) + c] = number of k-mers x of pivot j with 1 + #{groups i != j whose rest-of-set union
+ *   contains x} = c   (c = 1: kmers_subtract, c >= 2: intersect -ocsum). */
+KHB_API int khb_pivot_across(khb_ctx *ctx, uint32_t nbins, uint64_t *h_hists, khb_stats *stats);
+
+/* Rule-compatible `kmc_tools simple A B intersect|kmers_subtract` (exp_type_2.smk:354-380): d_index[i] = position of
+ * d_a[i] in the sorted, duplicate-free d_b, or UINT64_MAX.  Keys are canonical k-mer values (khb_key_bytes(k) each). */
+KHB_API int khb_sorted_lookup(khb_ctx *ctx, const void *d_a, uint64_t n_a, const void *d_b, uint64_t n_b, int k,
+                      uint64_t *d_index);
+
 /* K7: split n keys into n_parts buckets by splitmix64(key) % n_parts (multi-GPU hash-range partition of the
  * k-mer space).  d_out receives the keys grouped by bucket, h_part_off[n_parts+1] the bucket offsets. */
 KHB_API int khb_partition_by_hash(khb_ctx *ctx, const void *d_keys, uint64_t n, int k, int n_parts, void *d_out,

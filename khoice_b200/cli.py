@@ -6,6 +6,11 @@ reference's rules invoke them (/root/reference/workflow/rules/exp_type_1.smk):
     kmc_tools complex {ops.txt}                                              (:182, :250)
     kmc_tools transform {in_prefix} histogram {out.txt}                      (:191, :259)
 
+and, for experiment type 2 (/root/reference/workflow/rules/exp_type_2.smk:354-380, 470-496):
+
+    kmc_tools simple {A} {B} intersect {out_prefix} -ocsum
+    kmc_tools simple {A} {B} kmers_subtract {out_prefix}
+
 ``khoice_b200/bin/kmc`` and ``khoice_b200/bin/kmc_tools`` exec this module, so putting that directory
 first on PATH makes the UNMODIFIED reference rules run on the B200 engine.  Databases use this package's
 own layout (khoice_b200/kmcdb.py).  Exit status: 0 ok, 1 on any error with partial outputs removed
@@ -187,10 +192,40 @@ def complex_union(ops_path: str) -> None:
     kmcdb.write_db(out_prefix, k, hk, hc, hist, cs)
 
 
+def simple_op(a_prefix: str, b_prefix: str, op: str, out_prefix: str, ocsum: bool) -> None:
+    """`kmc_tools simple A B intersect O -ocsum` (counter = c_A + c_B) and `kmc_tools simple A B kmers_subtract O`
+    (k-mers of A absent from B, A's counters).  The join runs on the GPU (khb_sorted_lookup)."""
+    if op not in ("intersect", "kmers_subtract"):
+        raise UsageError(f"kmc_tools simple: operation {op} is not supported by the khoice-b200 shim")
+    if op == "intersect" and not ocsum:
+        raise UsageError("kmc_tools simple intersect: only the -ocsum counter mode is supported (the reference passes -ocsum)")
+    A, B = kmcdb.read_db(a_prefix), kmcdb.read_db(b_prefix)
+    if A.k != B.k:
+        raise UsageError("kmc_tools simple: inputs were built with different k")
+    idx = get_engine().sorted_lookup(A.keys, B.keys, A.k)
+    cmax = max(A.counter_max, B.counter_max)
+    if op == "intersect":
+        keep = idx >= 0
+        counts = np.minimum(A.counts[keep].astype(np.uint64) + B.counts[idx[keep]].astype(np.uint64), cmax).astype(np.uint32)
+    else:
+        keep = idx < 0
+        counts = A.counts[keep]
+    hist = np.bincount(np.minimum(counts, HIST_ROWS + 1), minlength=HIST_ROWS + 2)[:HIST_ROWS + 1].astype(np.uint64)
+    hist[0] = 0
+    kmcdb.write_db(out_prefix, A.k, A.keys[keep], counts, hist, cmax)
+
+
 def kmc_tools_main(argv: List[str]) -> int:
     args = [a for a in argv if not re.fullmatch(r"-t\d+", a) and a not in ("-v", "-hp")]
     if not args:
-        raise UsageError("usage: kmc_tools <transform|complex> ...")
+        raise UsageError("usage: kmc_tools <transform|complex|simple> ...")
+    if args[0] == "simple":
+        flags = [a for a in args[1:] if a.startswith("-")]
+        pos = [a for a in args[1:] if not a.startswith("-")]
+        if len(pos) != 4 or any(f != "-ocsum" for f in flags):
+            raise UsageError("usage: kmc_tools simple <A> <B> <intersect|kmers_subtract> <out> [-ocsum]")
+        simple_op(pos[0], pos[1], pos[2], pos[3], "-ocsum" in flags)
+        return 0
     if args[0] == "complex":
         if len(args) != 2:
             raise UsageError("usage: kmc_tools complex <operations_file>")
@@ -277,6 +312,9 @@ def _outputs_of(tool: str, argv: List[str]) -> List[str]:
         elif argv and argv[0] == "complex":
             _, out, _ = parse_complex(argv[1])
             outs = [out + ".kmc_pre", out + ".kmc_suf"]
+        elif argv and argv[0] == "simple":
+            pos = [a for a in argv[1:] if not a.startswith("-")]
+            outs = [pos[3] + ".kmc_pre", pos[3] + ".kmc_suf"]
     except Exception:
         pass
     return outs

@@ -22,7 +22,19 @@ int khb_sort_keys_impl(khb_ctx *, void *, void *, const u64 *, int, int, int *);
 int khb_sort_bits_impl(khb_ctx *, void *, void *, const u64 *, int, int, int, int, int *, unsigned short *, unsigned short *);
 int khb_resolve_unique_impl(khb_ctx *, const void *, size_t, int, int, void *, u64 *);
 int khb_resolve_count_impl(khb_ctx *, const void *, size_t, int, int, u32, u32, u64 *, void *, u64 *);
-int khb_pairs_count_impl(khb_ctx *, const void *, const unsigned short *, size_t, int, int, u32, u32, u32, u64 *, void *, u64 *, u64 *);
+int khb_pairs_count_impl(khb_ctx *, const void *, const unsigned short *, size_t, int, int, u32, u32, u32, u64 *, void *, u64 *, u64 *, int, void *, u64 *);
+int khb_fill_segment_ids_impl(khb_ctx *, unsigned short *, const u64 *, int, u64);
+int khb_pivot_across_impl(khb_ctx *, const void *, const unsigned short *, size_t, int, int, u32, u32, u32, u64 *);
+int khb_sorted_lookup_impl(khb_ctx *, const void *, u64, const void *, u64, int, u64 *);
+// Experiment type 2: the pivot k-mer sets P_1 .. P_G (device, concatenated) and, for every pivot group call, the range its
+// rest-of-set union occupies in the group-set store.
+struct khb_pivot_store {
+    void *buf = nullptr;
+    size_t cap = 0;            // bytes
+    u64 len = 0;               // keys
+    std::vector<u64> p_off;    // pivot set j = [p_off[j], p_off[j+1])
+    std::vector<u64> u_off;    // union set j = gs_buf[u_off[j], u_off[j+1])
+};
 int khb_unique_impl(khb_ctx *, const void *, size_t, int, void *, u64 *);
 int khb_count_runs_impl(khb_ctx *, const void *, size_t, int, u32, u32, u64 *, void *, u32 *, u64 *);
 
@@ -174,6 +186,10 @@ int khb_destroy(khb_ctx *ctx)
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
     delete ctx->pf_begin;
+    if (ctx->pv) {
+        if (ctx->pv->buf) cudaFree(ctx->pv->buf);
+        delete ctx->pv;
+    }
     if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
     if (ctx->d_mail) cudaFree(ctx->d_mail);
     cudaEventDestroy(ctx->ev0);
@@ -566,6 +582,29 @@ static int gs_reserve(khb_ctx *ctx, int k, u64 extra)
     return KHB_OK;
 }
 
+static int pv_reserve(khb_ctx *ctx, int k, u64 extra)
+{
+    if (!ctx->pv) ctx->pv = new khb_pivot_store();
+    khb_pivot_store *pv = ctx->pv;
+    const size_t W = (size_t)khb_key_bytes(k);
+    const u64 need = (pv->len + extra + 2) * W;
+    if (need > pv->cap) {
+        u64 cap = pv->cap ? pv->cap : (8u << 20);
+        while (cap < need) cap += cap / 2 + 16;
+        void *nb = nullptr;
+        if (cudaMalloc(&nb, cap) != cudaSuccess) {
+            cudaGetLastError();
+            return khb_fail(ctx, KHB_ERR_NOMEM, "pivot set store: device allocation of %llu bytes failed", cap);
+        }
+        if (pv->len) KHB_CUDA(ctx, cudaMemcpyAsync(nb, pv->buf, pv->len * W, cudaMemcpyDeviceToDevice, ctx->stream));
+        KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (pv->buf) KHB_CUDA(ctx, cudaFree(pv->buf));
+        pv->buf = nb;
+        pv->cap = cap;
+    }
+    return KHB_OK;
+}
+
 struct PhaseTimer {
     khb_ctx *ctx;
     cudaEvent_t ev[12];
@@ -640,7 +679,11 @@ static int pack_stage(khb_ctx *ctx, int n_genomes, const uint8_t *d_fasta, const
 }
 
 // K2 .. K5 for one k on a packed group.
-static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64 *h_hist, int keep_set, khb_stats *stats, PhaseTimer &tm)
+static int pv_reserve(khb_ctx *ctx, int k, u64 extra);
+
+// pivot != 0: experiment type 2 -- the last genome of the group is the pivot (khb_pivot_group_from_packed).
+static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64 *h_hist, int keep_set, khb_stats *stats, PhaseTimer &tm,
+                       int pivot = 0)
 {
     if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "k=%d outside 1..64", k);
     if (!h_hist) return khb_fail(ctx, KHB_ERR_ARG, "group stage: null histogram");
@@ -667,6 +710,7 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
         const char *e = getenv("KHB_GROUP_MODE");
         single_sort = (e && strcmp(e, "two-sort") == 0) ? 0 : 1;
     }
+    if (pivot && !(single_sort && n_genomes <= 65535)) return khb_fail(ctx, KHB_ERR_STATE, "pivot analysis needs the single-sort group path");
     if (single_sort && n_genomes <= 65535) {
         // ---- single-sort path: ONE prefix sort of all windows of the group with the genome id as payload ----
         if ((rc = khb_scratch_get(ctx, SCR_PAY_A, (n_sym + 8) * 2, &p))) return rc;
@@ -697,14 +741,29 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
             ctx->gs_hashed = hashed;
             out_keys = (char *)ctx->gs_buf + ctx->gs_len * W;
         }
-        u64 *d_hist = ctx->d_mail + 8, *d_runs = ctx->d_mail, *d_pairs = ctx->d_mail + 1;
-        if ((rc = khb_pairs_count_impl(ctx, sorted, spay, n_sym, k, fb, KHB_COUNTER_MAX, nbins, (u32)n_genomes, d_hist, out_keys, d_runs, d_pairs))) return rc;
+        u64 *d_hist = ctx->d_mail + 8, *d_runs = ctx->d_mail, *d_pairs = ctx->d_mail + 1, *d_pruns = ctx->d_mail + 2;
+        void *out_pivot = nullptr;
+        if (pivot && keep_set) {
+            // upper bound for the pivot's distinct keys: its windows
+            if ((rc = pv_reserve(ctx, k, seg[n_genomes] - seg[n_genomes - 1]))) return rc;
+            out_pivot = (char *)ctx->pv->buf + ctx->pv->len * W;
+        }
+        if ((rc = khb_pairs_count_impl(ctx, sorted, spay, n_sym, k, fb, KHB_COUNTER_MAX, nbins, (u32)n_genomes, d_hist, out_keys, d_runs, d_pairs,
+                                       pivot, out_pivot, d_pruns))) return rc;
         KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, ctx->d_mail, (nbins + 9) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
         tm.mark();  // 7: count done
         KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         memcpy(h_hist, ctx->h_mail + 8, ((size_t)nbins + 1) * sizeof(u64));
         const u64 d_g = ctx->h_mail[0];
         if (keep_set) {
+            if (pivot) {
+                if (ctx->pv->u_off.empty()) ctx->pv->u_off.push_back(ctx->gs_len);
+                if (ctx->pv->u_off.back() != ctx->gs_len) return khb_fail(ctx, KHB_ERR_STATE, "pivot groups and plain groups were mixed in the group-set store");
+                ctx->pv->u_off.push_back(ctx->gs_len + d_g);
+                if (ctx->pv->p_off.empty()) ctx->pv->p_off.push_back(0);
+                ctx->pv->len += ctx->h_mail[2];
+                ctx->pv->p_off.push_back(ctx->pv->len);
+            }
             ctx->gs_len += d_g;
             ctx->gs_groups += 1;
         }
@@ -1128,7 +1187,110 @@ int khb_group_sets_reset(khb_ctx *ctx)
     ctx->gs_groups = 0;
     ctx->gs_k = 0;
     ctx->gs_hashed = 0;
+    if (ctx->pv) {
+        ctx->pv->len = 0;
+        ctx->pv->p_off.clear();
+        ctx->pv->u_off.clear();
+    }
     return KHB_OK;
+}
+
+// ---- experiment type 2 (pivot analysis) -------------------------------------------------------------------------------
+int khb_pivot_group_from_packed(khb_ctx *ctx, int k, const khb_packed *pk, uint32_t nbins, uint64_t *h_hist, int keep_sets, khb_stats *stats)
+{
+    KHB_CHECK_CTX(ctx);
+    if (!pk) return khb_fail(ctx, KHB_ERR_ARG, "khb_pivot_group_from_packed: null handle");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (!ctx->pv) ctx->pv = new khb_pivot_store();
+    if (keep_sets && ctx->gs_groups != (int)(ctx->pv->p_off.empty() ? 0 : ctx->pv->p_off.size() - 1))
+        return khb_fail(ctx, KHB_ERR_STATE, "pivot groups and plain groups were mixed in the group-set store; call khb_group_sets_reset");
+    PhaseTimer tm(ctx);
+    tm.mark();
+    tm.mark();
+    tm.mark();  // 2: nothing to pack
+    int rc = count_stage(ctx, k, *pk, nbins, (u64 *)h_hist, keep_sets, stats, tm, 1);
+    if (rc == KHB_OK) fill_times(stats, tm);
+    return rc;
+}
+
+int khb_pivot_sets_info(khb_ctx *ctx, int *n_pivots, uint64_t *n_pivot_keys, uint64_t *n_union_keys)
+{
+    if (!ctx) return KHB_ERR_ARG;
+    const khb_pivot_store *pv = ctx->pv;
+    if (n_pivots) *n_pivots = (pv && !pv->p_off.empty()) ? (int)pv->p_off.size() - 1 : 0;
+    if (n_pivot_keys) *n_pivot_keys = pv ? pv->len : 0;
+    if (n_union_keys) *n_union_keys = ctx->gs_len;
+    return KHB_OK;
+}
+
+int khb_pivot_across(khb_ctx *ctx, uint32_t nbins, uint64_t *h_hists, khb_stats *stats)
+{
+    KHB_CHECK_CTX(ctx);
+    if (!h_hists) return khb_fail(ctx, KHB_ERR_ARG, "khb_pivot_across: null histogram");
+    if (nbins < 1 || nbins > 8192) return khb_fail(ctx, KHB_ERR_ARG, "nbins=%u outside 1..8192", nbins);
+    khb_pivot_store *pv = ctx->pv;
+    const int G = (pv && !pv->p_off.empty()) ? (int)pv->p_off.size() - 1 : 0;
+    if (G < 1 || !ctx->gs_k) return khb_fail(ctx, KHB_ERR_STATE, "khb_pivot_across: no pivot group retained");
+    if (2 * G > 65535) return khb_fail(ctx, KHB_ERR_ARG, "khb_pivot_across: %d groups (limit 32767)", G);
+    if (pv->u_off.front() != 0 || pv->u_off.back() != ctx->gs_len) return khb_fail(ctx, KHB_ERR_STATE, "khb_pivot_across: group-set store holds other sets");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    const int k = ctx->gs_k;
+    const size_t W = (size_t)khb_key_bytes(k);
+    const u64 nu = ctx->gs_len, np_keys = pv->len, n = nu + np_keys;
+    if (n >= (1ull << 32)) return khb_fail(ctx, KHB_ERR_ARG, "khb_pivot_across: %llu keys (limit 2^32 - 1)", n);
+    int rc;
+    void *p;
+    if ((rc = khb_scratch_get(ctx, SCR_KEYS_A, (n + 4) * W, &p))) return rc;
+    void *bufA = p;
+    if ((rc = khb_scratch_get(ctx, SCR_KEYS_B, (n + 4) * W, &p))) return rc;
+    void *bufB = p;
+    if ((rc = khb_scratch_get(ctx, SCR_PAY_A, (n + 8) * 2, &p))) return rc;
+    unsigned short *payA = (unsigned short *)p;
+    if ((rc = khb_scratch_get(ctx, SCR_PAY_B, (n + 8) * 2, &p))) return rc;
+    unsigned short *payB = (unsigned short *)p;
+    const size_t hist_bytes = (size_t)G * (nbins + 1) * sizeof(u64);
+    if ((rc = khb_scratch_get(ctx, SCR_MISC, hist_bytes + (size_t)(2 * G + 1) * 8 + 64, &p))) return rc;
+    u64 *d_hist = (u64 *)p;
+    u64 *d_seg = d_hist + (size_t)G * (nbins + 1);
+    PhaseTimer tm(ctx);
+    tm.mark();
+    // concatenate U_1 .. U_G, P_1 .. P_G; payload = set index
+    std::vector<u64> seg((size_t)2 * G + 1);
+    u64 max_len = 0;
+    for (int j = 0; j <= G; j++) seg[j] = pv->u_off[j];
+    for (int j = 1; j <= G; j++) seg[G + j] = nu + pv->p_off[j];
+    for (int j = 0; j < 2 * G; j++) max_len = seg[j + 1] - seg[j] > max_len ? seg[j + 1] - seg[j] : max_len;
+    KHB_CUDA(ctx, cudaMemcpyAsync(bufA, ctx->gs_buf, nu * W, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (np_keys) KHB_CUDA(ctx, cudaMemcpyAsync((char *)bufA + nu * W, pv->buf, np_keys * W, cudaMemcpyDeviceToDevice, ctx->stream));
+    KHB_CUDA(ctx, cudaMemcpyAsync(d_seg, seg.data(), seg.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // seg is pageable
+    if ((rc = khb_fill_segment_ids_impl(ctx, payA, d_seg, 2 * G, max_len))) return rc;
+    int in_tmp = 0, fb, npass;
+    khb_prefix_plan(k, n, &fb, &npass);
+    if (!ctx->gs_hashed) { fb = 0; npass = (2 * k + 7) / 8; }
+    u64 one_seg[2] = {0, n};
+    if ((rc = khb_sort_bits_impl(ctx, bufA, bufB, one_seg, 1, (int)W, fb, npass, &in_tmp, payA, payB))) return rc;
+    tm.mark();
+    if ((rc = khb_pivot_across_impl(ctx, in_tmp ? bufB : bufA, in_tmp ? payB : payA, n, k, fb, (u32)G, KHB_COUNTER_MAX, nbins, d_hist))) return rc;
+    KHB_CUDA(ctx, cudaMemcpyAsync(h_hists, d_hist, hist_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    tm.mark();
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (stats) {
+        stats->windows = n;
+        stats->genome_distinct = nu;
+        stats->distinct = np_keys;
+        stats->ms_sort2 = tm.ms(0, 1);
+        stats->ms_count = tm.ms(1, 2);
+        stats->ms_total = tm.ms(0, 2);
+        stats->passes_group = npass;
+    }
+    return KHB_OK;
+}
+
+int khb_sorted_lookup(khb_ctx *ctx, const void *d_a, uint64_t n_a, const void *d_b, uint64_t n_b, int k, uint64_t *d_index)
+{
+    KHB_CHECK_CTX(ctx);
+    return khb_sorted_lookup_impl(ctx, d_a, n_a, d_b, n_b, k, (u64 *)d_index);
 }
 
 int khb_partition_by_hash(khb_ctx *ctx, const void *d_keys, uint64_t n, int k, int n_parts, void *d_out, uint64_t *h_part_off)

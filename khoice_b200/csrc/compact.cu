@@ -557,11 +557,17 @@ __device__ __forceinline__ u32 open_run_state(const Key *__restrict__ in, const 
 
 // PF: the next chunk's loads are issued before the current chunk is processed (more registers, fewer resident warps).
 template <typename Key, bool PF> struct PairsCfg { static constexpr int MINB = sizeof(Key) == 8 ? (PF ? 5 : 8) : (PF ? 3 : 4); };
-template <typename Key, bool PF>
+// PIVOT (experiment type 2, exp_type_2.smk:354-380): genome `pivot_gid` -- the LAST of the group -- is the pivot and the
+// other genomes are the rest of the set.  A run whose last pair belongs to the pivot is a pivot k-mer: hist[c] counts
+// it with c = 1 + (rest genomes containing it), i.e. c = 1 is `kmc_tools simple pivot rest kmers_subtract` and c >= 2 the
+// counter of `... intersect -ocsum`; its key goes to out_pivot.  out_keys receives the union of the REST only (k-mers
+// seen in nothing but the pivot are left out).
+template <typename Key, bool PF, bool PIVOT>
 __global__ void __launch_bounds__(CQ_BLOCK, (PairsCfg<Key, PF>::MINB))
 pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid, u64 n, int pshift, u32 cs, u32 nbins, u32 hot_bin,
              u64 *__restrict__ hist, Key *__restrict__ out_keys, u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs,
-             unsigned char *__restrict__ mixed_map /* one byte per lane chunk: bit j = key j ends the first run of a mixed prefix run */)
+             unsigned char *__restrict__ mixed_map /* one byte per lane chunk: bit j = key j ends the first run of a mixed prefix run */,
+             u32 pivot_gid, Key *__restrict__ out_pivot, u64 *__restrict__ d_pcursor)
 {
     constexpr int TILE = 32 * CQ_ITEMS;
     extern __shared__ u32 sh_hist[];  // [nbins+1]
@@ -630,7 +636,7 @@ pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid,
         if (lane == 0) excl = 0;
         const u32 carry = seg_combine(open_state, excl);
         // resolve every tail
-        u32 emitm = 0, itemm = 0;
+        u32 emitm = 0, itemm = 0, pemitm = 0;
         u32 open_cnt = carry & 0x3FFFFFFFu;
         u32 open_mix = (carry >> 30) & 1u;
 #pragma unroll
@@ -640,13 +646,17 @@ pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid,
             if ((tailm >> j) & 1u) {
                 const u32 after = (tmix >> j) & 1u;
                 if ((open_mix | after) == 0) {
-                    emitm |= 1u << j;
-                    my_pairs += open_cnt;
-                    if (open_cnt == 1u) my_ones++;
-                    else if (open_cnt == hot_bin) my_hots++;
-                    else {
-                        const u32 cc = open_cnt > cs ? cs : open_cnt;
-                        if (cc <= nbins) atomicAdd(&sh_hist[cc], 1u);
+                    const bool pv = PIVOT && g[j + 1] == pivot_gid;
+                    if (!PIVOT || !(pv && open_cnt == 1u)) emitm |= 1u << j;
+                    if (pv) pemitm |= 1u << j;
+                    my_pairs += open_cnt - (pv ? 1u : 0u);
+                    if (!PIVOT || pv) {
+                        if (open_cnt == 1u) my_ones++;
+                        else if (open_cnt == hot_bin) my_hots++;
+                        else {
+                            const u32 cc = open_cnt > cs ? cs : open_cnt;
+                            if (cc <= nbins) atomicAdd(&sh_hist[cc], 1u);
+                        }
                     }
                 } else if (open_mix == 0) {
                     itemm |= 1u << j;
@@ -666,6 +676,20 @@ pairs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid,
 #pragma unroll
             for (int j = 0; j < CQ_ITEMS; j++)
                 if ((emitm >> j) & 1u) *dst++ = c.k[j + 1];
+        }
+        if (PIVOT) {
+            const u32 pmine = __popc(pemitm);
+            const u32 pincl = warp_incl_sum<u32>(pmine);
+            const u32 ptotal = __shfl_sync(0xffffffffu, pincl, 31);
+            u64 pbase = 0;
+            if (lane == 31 && ptotal) pbase = atomicAdd(d_pcursor, (u64)ptotal);
+            pbase = __shfl_sync(0xffffffffu, pbase, 31);
+            if (out_pivot != nullptr && pmine) {
+                Key *dst = out_pivot + pbase + (pincl - pmine);
+#pragma unroll
+                for (int j = 0; j < CQ_ITEMS; j++)
+                    if ((pemitm >> j) & 1u) *dst++ = c.k[j + 1];
+            }
         }
         if (PF) c = nx;
         tile = next;
@@ -720,10 +744,11 @@ mixed_collect_kernel(const u32 *__restrict__ mixed_map, u64 nwords, u32 *__restr
 
 // Exact fallback for a mixed prefix run [s, e) with more than MIXED_MAXD distinct keys: every first occurrence counts
 // its own pairs by scanning forward.  Quadratic in the run length; practically never taken for hashed keys.
-template <typename Key>
+template <typename Key, bool PIVOT>
 __device__ __noinline__ void mixed_run_slow(const Key *__restrict__ in, const unsigned short *__restrict__ gid, u64 s, u64 e, u32 cs,
                                             u32 nbins, u32 *sh_hist, Key *__restrict__ out_keys, u64 *__restrict__ d_cursor,
-                                            u64 *__restrict__ d_pairs)
+                                            u64 *__restrict__ d_pairs, u32 pivot_gid, Key *__restrict__ out_pivot,
+                                            u64 *__restrict__ d_pcursor)
 {
     for (u64 i = s; i < e; i++) {
         const Key ki = in[i];
@@ -737,19 +762,27 @@ __device__ __noinline__ void mixed_run_slow(const Key *__restrict__ in, const un
             if (gr != lastg) { cnt++; lastg = gr; }
         }
         const u32 c = cnt > cs ? cs : cnt;
-        if (c <= nbins) atomicAdd(&sh_hist[c], 1u);
-        atomicAdd(d_pairs, (u64)cnt);
-        const u64 pos = atomicAdd(d_cursor, 1ull);
-        if (out_keys != nullptr) out_keys[pos] = ki;
+        const bool pv = PIVOT && lastg == pivot_gid;  // the pivot is the last genome, so it is the last one seen
+        if ((!PIVOT || pv) && c <= nbins) atomicAdd(&sh_hist[c], 1u);
+        atomicAdd(d_pairs, (u64)(cnt - (pv ? 1u : 0u)));
+        if (!PIVOT || !(pv && cnt == 1u)) {
+            const u64 pos = atomicAdd(d_cursor, 1ull);
+            if (out_keys != nullptr) out_keys[pos] = ki;
+        }
+        if (pv) {
+            const u64 pos = atomicAdd(d_pcursor, 1ull);
+            if (out_pivot != nullptr) out_pivot[pos] = ki;
+        }
     }
 }
 
 // One mixed prefix run per thread: a small register table of its distinct keys (pair count, last genome seen).
-template <typename Key>
+template <typename Key, bool PIVOT>
 __global__ void __launch_bounds__(MIXED_BLOCK)
 mixed_runs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ gid, u64 n, int pshift, u32 cs, u32 nbins,
                   u64 *__restrict__ hist, Key *__restrict__ out_keys, u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs,
-                  const u32 *__restrict__ items, const u64 *__restrict__ d_nitems)
+                  const u32 *__restrict__ items, const u64 *__restrict__ d_nitems, u32 pivot_gid, Key *__restrict__ out_pivot,
+                  u64 *__restrict__ d_pcursor)
 {
     extern __shared__ u32 sh_hist[];            // [nbins+1]
     const u32 tid = threadIdx.x, lane = lane_id();
@@ -762,6 +795,7 @@ mixed_runs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__
         Key lk[MIXED_MAXD];
         u32 lc[MIXED_MAXD], lg[MIXED_MAXD];
         u32 d = 0, pairs = 0;
+        u32 gm = 0, pm = 0;  // table entries that go to the group set / to the pivot set
         if (i < count) {
             const u64 t = items[i];
             const Key key0 = in[t];
@@ -794,36 +828,49 @@ mixed_runs_kernel(const Key *__restrict__ in, const unsigned short *__restrict__
                 }
             }
             if (overflow) {
-                mixed_run_slow(in, gid, s, e, cs, nbins, sh_hist, out_keys, d_cursor, d_pairs);
-                d = 0;
+                mixed_run_slow<Key, PIVOT>(in, gid, s, e, cs, nbins, sh_hist, out_keys, d_cursor, d_pairs, pivot_gid, out_pivot, d_pcursor);
             } else {
 #pragma unroll
                 for (int q = 0; q < MIXED_MAXD; q++) {
                     if ((u32)q < d) {
-                        pairs += lc[q];
+                        const bool pv = PIVOT && lg[q] == pivot_gid;  // the pivot is the last genome of the group
+                        pairs += lc[q] - (pv ? 1u : 0u);
+                        if (!PIVOT || !(pv && lc[q] == 1u)) gm |= 1u << q;
+                        if (pv) pm |= 1u << q;
                         const u32 c = lc[q] > cs ? cs : lc[q];
-                        if (c <= nbins) atomicAdd(&sh_hist[c], 1u);
+                        if ((!PIVOT || pv) && c <= nbins) atomicAdd(&sh_hist[c], 1u);
                     }
                 }
             }
         }
-        // per warp: one atomicAdd reserves the output range, one adds the pair count
-        const u32 incl = warp_incl_sum<u32>(d);
+        // per warp: one atomicAdd reserves each output range, one adds the pair count
+        const u32 mine = (u32)__popc(gm) | ((u32)__popc(pm) << 16);
+        const u32 incl = warp_incl_sum<u32>(mine);
         const u32 wtotal = __shfl_sync(0xffffffffu, incl, 31);
         u32 wpairs = pairs;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) wpairs += __shfl_xor_sync(0xffffffffu, wpairs, o);
-        u64 wbase = 0;
+        u64 wbase = 0, pbase = 0;
         if (lane == 31) {
-            if (wtotal) wbase = atomicAdd(d_cursor, (u64)wtotal);
+            if (wtotal & 0xffffu) wbase = atomicAdd(d_cursor, (u64)(wtotal & 0xffffu));
+            if (PIVOT && (wtotal >> 16)) pbase = atomicAdd(d_pcursor, (u64)(wtotal >> 16));
             if (wpairs) atomicAdd(d_pairs, (u64)wpairs);
         }
         wbase = __shfl_sync(0xffffffffu, wbase, 31);
         if (out_keys != nullptr) {
-            const u64 pos = wbase + (incl - d);
+            u64 pos = wbase + ((incl - mine) & 0xffffu);
 #pragma unroll
             for (int q = 0; q < MIXED_MAXD; q++)
-                if ((u32)q < d) out_keys[pos + q] = lk[q];
+                if ((gm >> q) & 1u) out_keys[pos++] = lk[q];
+        }
+        if (PIVOT) {
+            pbase = __shfl_sync(0xffffffffu, pbase, 31);
+            if (out_pivot != nullptr) {
+                u64 pos = pbase + ((incl - mine) >> 16);
+#pragma unroll
+                for (int q = 0; q < MIXED_MAXD; q++)
+                    if ((pm >> q) & 1u) out_pivot[pos++] = lk[q];
+            }
         }
     }
     __syncthreads();
@@ -937,14 +984,18 @@ int khb_resolve_count_impl(khb_ctx *ctx, const void *d_sorted, size_t n, int k, 
 
 // Single-sort group path: histogram of genomes-per-k-mer from prefix-sorted (key, genome id) pairs.
 int khb_pairs_count_impl(khb_ctx *ctx, const void *d_sorted, const unsigned short *d_gid, size_t n, int k, int pshift, u32 cs, u32 nbins,
-                         u32 n_genomes, u64 *d_hist, void *d_out_keys, u64 *d_runs, u64 *d_pairs)
+                         u32 n_genomes, u64 *d_hist, void *d_out_keys, u64 *d_runs, u64 *d_pairs, int pivot, void *d_out_pivot,
+                         u64 *d_pruns)
 {
+    // pivot != 0 (experiment type 2): the last genome (id n_genomes - 1) is the pivot, see pairs_kernel
     if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_pairs_count: k=%d outside 1..64", k);
     if (nbins < 1 || nbins > 8192) return khb_fail(ctx, KHB_ERR_ARG, "khb_pairs_count: nbins=%u outside 1..8192", nbins);
     if ((u64)n >= (1ull << 32)) return khb_fail(ctx, KHB_ERR_ARG, "khb_pairs_count: %zu keys in one group (limit 2^32 - 1)", n);
+    if (pivot && (n_genomes < 1 || !d_pruns)) return khb_fail(ctx, KHB_ERR_ARG, "khb_pairs_count: pivot mode needs the genome count");
     KHB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, ((size_t)nbins + 1) * sizeof(u64), ctx->stream));
     KHB_CUDA(ctx, cudaMemsetAsync(d_runs, 0, sizeof(u64), ctx->stream));
     KHB_CUDA(ctx, cudaMemsetAsync(d_pairs, 0, sizeof(u64), ctx->stream));
+    if (pivot) KHB_CUDA(ctx, cudaMemsetAsync(d_pruns, 0, sizeof(u64), ctx->stream));
     if (n == 0) return KHB_OK;
     const u64 nchunks = div_up(n, 32 * CQ_ITEMS);  // warp chunks
     static int pf = -1;
@@ -959,6 +1010,7 @@ int khb_pairs_count_impl(khb_ctx *ctx, const void *d_sorted, const unsigned shor
     const size_t shm = ((size_t)nbins + 1) * sizeof(u32);
     // multiplicity counted in registers besides 1: "in every genome of the group"
     const u32 hot = (n_genomes >= 2 && n_genomes <= nbins && n_genomes <= cs) ? n_genomes : 0u;
+    const u32 pgid = pivot ? n_genomes - 1u : 0xffffffffu;
     // scratch: [item count][bitmap of the mixed prefix runs: one byte per 8 keys, written completely by pairs_kernel]
     //          [work list: at most one entry per two keys]
     const u64 nwords = nchunks * (32 * CQ_ITEMS / 32);
@@ -973,18 +1025,154 @@ int khb_pairs_count_impl(khb_ctx *ctx, const void *d_sorted, const unsigned shor
     if (grid2 > (u64)ctx->num_sms * 8) grid2 = (u64)ctx->num_sms * 8;
     const u64 grid3 = (u64)ctx->num_sms * 4;  // CTAs past the item count exit at once
     khb_prof_begin(ctx, KHB_K_RLE);
-#define PAIRS_LAUNCH(KEY, PFV) pairs_kernel<KEY, PFV><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const KEY *)d_sorted, d_gid, n, pshift, cs, nbins, hot, d_hist, (KEY *)d_out_keys, d_runs, d_pairs, (unsigned char *)d_map)
-    if (k <= 32) { if (pf) PAIRS_LAUNCH(Key64, true); else PAIRS_LAUNCH(Key64, false); }
-    else { if (pf) PAIRS_LAUNCH(Key128, true); else PAIRS_LAUNCH(Key128, false); }
+#define PAIRS_LAUNCH(KEY, PFV, PIV)                                                                                                      \
+    pairs_kernel<KEY, PFV, PIV><<<(unsigned)grid, CQ_BLOCK, shm, ctx->stream>>>((const KEY *)d_sorted, d_gid, n, pshift, cs, nbins, hot, d_hist, \
+                                                                                (KEY *)d_out_keys, d_runs, d_pairs, (unsigned char *)d_map, pgid, \
+                                                                                (KEY *)d_out_pivot, d_pruns)
+#define PAIRS_DISPATCH(KEY)                                           \
+    do {                                                              \
+        if (pivot) { if (pf) PAIRS_LAUNCH(KEY, true, true); else PAIRS_LAUNCH(KEY, false, true); }   \
+        else { if (pf) PAIRS_LAUNCH(KEY, true, false); else PAIRS_LAUNCH(KEY, false, false); }       \
+    } while (0)
+    if (k <= 32) PAIRS_DISPATCH(Key64); else PAIRS_DISPATCH(Key128);
+#undef PAIRS_DISPATCH
 #undef PAIRS_LAUNCH
     KHB_LAUNCH_CHECK(ctx);
     mixed_collect_kernel<<<(unsigned)grid2, MIXED_BLOCK, 0, ctx->stream>>>(d_map, nwords, d_items, d_nitems);
     KHB_LAUNCH_CHECK(ctx);
-    if (k <= 32)
-        mixed_runs_kernel<Key64><<<(unsigned)grid3, MIXED_BLOCK, shm, ctx->stream>>>((const Key64 *)d_sorted, d_gid, n, pshift, cs, nbins, d_hist, (Key64 *)d_out_keys, d_runs, d_pairs, d_items, d_nitems);
-    else
-        mixed_runs_kernel<Key128><<<(unsigned)grid3, MIXED_BLOCK, shm, ctx->stream>>>((const Key128 *)d_sorted, d_gid, n, pshift, cs, nbins, d_hist, (Key128 *)d_out_keys, d_runs, d_pairs, d_items, d_nitems);
+#define MIXED_LAUNCH(KEY, PIV)                                                                                                           \
+    mixed_runs_kernel<KEY, PIV><<<(unsigned)grid3, MIXED_BLOCK, shm, ctx->stream>>>((const KEY *)d_sorted, d_gid, n, pshift, cs, nbins, d_hist, \
+                                                                                    (KEY *)d_out_keys, d_runs, d_pairs, d_items, d_nitems, pgid, \
+                                                                                    (KEY *)d_out_pivot, d_pruns)
+    if (k <= 32) { if (pivot) MIXED_LAUNCH(Key64, true); else MIXED_LAUNCH(Key64, false); }
+    else { if (pivot) MIXED_LAUNCH(Key128, true); else MIXED_LAUNCH(Key128, false); }
+#undef MIXED_LAUNCH
     KHB_LAUNCH_CHECK(ctx);
     khb_prof_end(ctx, KHB_K_RLE, (u64)n * ((k <= 32 ? 8 : 16) + 2));
+    return KHB_OK;
+}
+
+// ---- experiment type 2, across groups (exp_type_2.smk:440-496) ---------------------------------------------------------
+// Input: the distinct k-mer sets U_1 .. U_G of the groups' rest-of-set unions followed by the pivot sets P_1 .. P_G,
+// sorted (stable, by prefix) with payload = set index (U_i: i-1, P_j: G+j-1).  Inside a prefix run the order of the
+// payloads is preserved, so every U element precedes every P element.  For a pivot element x of P_j:
+//   g = #{ i != j : x in U_i },  hist[j][1 + g]++     (1 = kmers_subtract, >= 2 = counter of intersect -ocsum)
+// One thread per element; pivot elements walk back over their prefix run (at most a few times 2G keys).
+template <typename Key>
+__global__ void __launch_bounds__(256)
+pivot_across_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ pay, u64 n, int pshift, u32 n_groups, u32 cs, u32 nbins,
+                    u64 *__restrict__ hist /* [n_groups][nbins+1] */, u32 sh_bins /* columns of the shared histogram, 0 = none */)
+{
+    extern __shared__ u32 sh_hist[];  // [n_groups][sh_bins]
+    const u32 tid = threadIdx.x;
+    for (u32 i = tid; i < n_groups * sh_bins; i += blockDim.x) sh_hist[i] = 0;
+    __syncthreads();
+    for (u64 i = (u64)blockIdx.x * blockDim.x + tid; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const u32 p = pay[i];
+        if (p < n_groups) continue;
+        const u32 j = p - n_groups;
+        const Key key = in[i];
+        if (key_is_sentinel(key)) continue;
+        u32 n_u = 0, own = 0;
+        for (u64 q = i; q > 0;) {
+            --q;
+            const Key kq = in[q];
+            if (key_is_sentinel(kq) || !same_prefix(kq, key, pshift)) break;
+            if (!key_eq(kq, key)) continue;
+            const u32 pq = pay[q];
+            if (pq < n_groups) { n_u++; own |= (pq == j) ? 1u : 0u; }
+        }
+        u32 c = 1u + n_u - own;
+        c = c > cs ? cs : c;
+        if (c > nbins) continue;
+        if (c < sh_bins) atomicAdd(&sh_hist[j * sh_bins + c], 1u);
+        else atomicAdd(&hist[(size_t)j * (nbins + 1) + c], 1ull);
+    }
+    __syncthreads();
+    for (u32 i = tid; i < n_groups * sh_bins; i += blockDim.x) {
+        const u32 v = sh_hist[i];
+        if (v) atomicAdd(&hist[(size_t)(i / sh_bins) * (nbins + 1) + (i % sh_bins)], (u64)v);
+    }
+}
+
+// pay[i] = s for seg_off[s] <= i < seg_off[s+1]  (blockIdx.y = s)
+__global__ void fill_segment_ids_kernel(unsigned short *__restrict__ pay, const u64 *__restrict__ seg_off)
+{
+    const u32 s = blockIdx.y;
+    const u64 b = seg_off[s], e = seg_off[s + 1];
+    for (u64 i = b + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (u64)gridDim.x * blockDim.x) pay[i] = (unsigned short)s;
+}
+
+int khb_fill_segment_ids_impl(khb_ctx *ctx, unsigned short *d_pay, const u64 *d_seg_off, int nseg, u64 max_len)
+{
+    if (nseg <= 0) return KHB_OK;
+    u64 bx = div_up(max_len, 256 * 8);
+    if (bx < 1) bx = 1;
+    if (bx > 1024) bx = 1024;
+    fill_segment_ids_kernel<<<dim3((unsigned)bx, (unsigned)nseg), 256, 0, ctx->stream>>>(d_pay, d_seg_off);
+    KHB_LAUNCH_CHECK(ctx);
+    return KHB_OK;
+}
+
+int khb_pivot_across_impl(khb_ctx *ctx, const void *d_sorted, const unsigned short *d_pay, size_t n, int k, int pshift, u32 n_groups,
+                          u32 cs, u32 nbins, u64 *d_hist /* [n_groups][nbins+1], zeroed here */)
+{
+    if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_pivot_across: k=%d outside 1..64", k);
+    KHB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, (size_t)n_groups * (nbins + 1) * sizeof(u64), ctx->stream));
+    if (n == 0) return KHB_OK;
+    // every count is at most n_groups: a [G][G+1] shared histogram takes all updates when it fits
+    u32 sh_bins = (n_groups + 1 < nbins + 1) ? n_groups + 1 : nbins + 1;
+    if ((size_t)n_groups * sh_bins * sizeof(u32) > 96 * 1024) sh_bins = 0;
+    const size_t shm = (size_t)n_groups * sh_bins * sizeof(u32);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(pivot_across_kernel<Key64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(pivot_across_kernel<Key128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr = true;
+    }
+    u64 grid = div_up(n, 256);
+    if (grid > (u64)ctx->num_sms * 8) grid = (u64)ctx->num_sms * 8;
+    khb_prof_begin(ctx, KHB_K_RLE);
+    if (k <= 32)
+        pivot_across_kernel<Key64><<<(unsigned)grid, 256, shm, ctx->stream>>>((const Key64 *)d_sorted, d_pay, n, pshift, n_groups, cs, nbins, d_hist, sh_bins);
+    else
+        pivot_across_kernel<Key128><<<(unsigned)grid, 256, shm, ctx->stream>>>((const Key128 *)d_sorted, d_pay, n, pshift, n_groups, cs, nbins, d_hist, sh_bins);
+    KHB_LAUNCH_CHECK(ctx);
+    khb_prof_end(ctx, KHB_K_RLE, (u64)n * ((k <= 32 ? 8 : 16) + 2));
+    return KHB_OK;
+}
+
+// ---- sorted-set lookup (rule-compatible `kmc_tools simple A B intersect / kmers_subtract`, exp_type_2.smk:354-380) ------
+// idx[i] = position of a[i] in the sorted, duplicate-free array b, or ~0 if it is not there.
+template <typename Key> __device__ __forceinline__ bool key_less(const Key &a, const Key &b);
+template <> __device__ __forceinline__ bool key_less<Key64>(const Key64 &a, const Key64 &b) { return a.v < b.v; }
+template <> __device__ __forceinline__ bool key_less<Key128>(const Key128 &a, const Key128 &b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+
+template <typename Key>
+__global__ void __launch_bounds__(256)
+sorted_lookup_kernel(const Key *__restrict__ a, u64 na, const Key *__restrict__ b, u64 nb, u64 *__restrict__ idx)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < na; i += (u64)gridDim.x * blockDim.x) {
+        const Key x = a[i];
+        u64 lo = 0, hi = nb;  // first position with b[pos] >= x
+        while (lo < hi) {
+            const u64 mid = lo + ((hi - lo) >> 1);
+            if (key_less(b[mid], x)) lo = mid + 1; else hi = mid;
+        }
+        idx[i] = (lo < nb && key_eq(b[lo], x)) ? lo : ~0ull;
+    }
+}
+
+int khb_sorted_lookup_impl(khb_ctx *ctx, const void *d_a, u64 na, const void *d_b, u64 nb, int k, u64 *d_idx)
+{
+    if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_sorted_lookup: k=%d outside 1..64", k);
+    if (na == 0) return KHB_OK;
+    u64 grid = div_up(na, 256);
+    if (grid > (u64)ctx->num_sms * 16) grid = (u64)ctx->num_sms * 16;
+    if (k <= 32)
+        sorted_lookup_kernel<Key64><<<(unsigned)grid, 256, 0, ctx->stream>>>((const Key64 *)d_a, na, (const Key64 *)d_b, nb, d_idx);
+    else
+        sorted_lookup_kernel<Key128><<<(unsigned)grid, 256, 0, ctx->stream>>>((const Key128 *)d_a, na, (const Key128 *)d_b, nb, d_idx);
+    KHB_LAUNCH_CHECK(ctx);
     return KHB_OK;
 }

@@ -189,6 +189,8 @@ struct khb_ctx {
     // optional per-kernel timing (khb_profile_enable): CUDA event pairs around every launch
     struct khb_prof *prof;
     int prof_on;
+    // experiment type 2: retained pivot sets (api.cu)
+    struct khb_pivot_store *pv;
 };
 
 // kernel ids for khb_profile_read

@@ -94,6 +94,10 @@ _SIGNATURES = [
     ("khb_group_sets_export", C.c_int, [_P, _P]),
     ("khb_group_sets_append_host", C.c_int, [_P, C.c_int, _P, C.c_uint64, C.c_int]),
     ("khb_group_sets_reset", C.c_int, [_P]),
+    ("khb_pivot_group_from_packed", C.c_int, [_P, C.c_int, _P, C.c_uint32, _P, C.c_int, C.POINTER(Stats)]),
+    ("khb_pivot_sets_info", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("khb_pivot_across", C.c_int, [_P, C.c_uint32, _P, C.POINTER(Stats)]),
+    ("khb_sorted_lookup", C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.c_int, _P]),
     ("khb_partition_by_hash", C.c_int, [_P, _P, C.c_uint64, C.c_int, C.c_int, _P, _P]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
@@ -443,6 +447,48 @@ class Engine:
         st = Stats()
         self._chk(self.lib.khb_across_groups(self.ctx, nbins, hist.ctypes.data, C.byref(st)))
         return hist, st.as_dict()
+
+    # -- experiment type 2 (pivot analysis, /root/reference/workflow/rules/exp_type_2.smk) ----------------------
+    def pivot_group_from_packed(self, packed: "PackedGroup", k: int, nbins: int = COUNTER_MAX, keep_sets: bool = True):
+        """One (k, dataset) of experiment type 2.  `packed` = pack_group(rest-of-set genomes + [pivot]), the pivot LAST.
+        Returns (hist uint64[nbins+1], stats): hist[1] = size of `pivot kmers_subtract rest` (exp_type_2.smk:367-380),
+        hist[c >= 2] = histogram of `pivot intersect rest -ocsum` (exp_type_2.smk:354-365), c = 1 + #rest genomes."""
+        hist = np.zeros(nbins + 1, dtype=np.uint64)
+        st = Stats()
+        self._chk(self.lib.khb_pivot_group_from_packed(self.ctx, k, packed.handle, nbins, hist.ctypes.data, int(keep_sets), C.byref(st)))
+        return hist, st.as_dict()
+
+    def pivot_sets_info(self) -> dict:
+        g, npk, nuk = C.c_int(), C.c_uint64(), C.c_uint64()
+        self._chk(self.lib.khb_pivot_sets_info(self.ctx, C.byref(g), C.byref(npk), C.byref(nuk)))
+        return {"n_pivots": g.value, "n_pivot_keys": npk.value, "n_union_keys": nuk.value}
+
+    def pivot_across(self, nbins: int = COUNTER_MAX):
+        """Across-group stage of experiment type 2 for all retained pivots (exp_type_2.smk:440-508).
+        Returns (hists uint64[G, nbins+1], stats): hists[j, c] = #k-mers of pivot j+1 seen in c-1 OTHER groups' unions."""
+        g = self.pivot_sets_info()["n_pivots"]
+        hists = np.zeros((max(g, 1), nbins + 1), dtype=np.uint64)
+        st = Stats()
+        self._chk(self.lib.khb_pivot_across(self.ctx, nbins, hists.ctypes.data, C.byref(st)))
+        return hists[:g], st.as_dict()
+
+    def sorted_lookup(self, a: np.ndarray, b: np.ndarray, k: int) -> np.ndarray:
+        """Position of every key of `a` in the sorted, duplicate-free `b` (int64, -1 = absent): the join behind the
+        rule-compatible `kmc_tools simple A B intersect|kmers_subtract` (exp_type_2.smk:354-380)."""
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        b = np.ascontiguousarray(b, dtype=np.uint64)
+        na, nb = a.shape[0], b.shape[0]
+        if na == 0:
+            return np.empty(0, dtype=np.int64)
+        da, db, di = self.alloc(max(a.nbytes, 16)), self.alloc(max(b.nbytes, 16)), self.alloc(na * 8)
+        try:
+            da.upload(a)
+            if nb:
+                db.upload(b)
+            self._chk(self.lib.khb_sorted_lookup(self.ctx, da.ptr, na, db.ptr, nb, k, di.ptr))
+            return di.download(np.uint64, na).view(np.int64)
+        finally:
+            da.free(); db.free(); di.free()
 
     def group_sets_info(self) -> dict:
         k, g, n = C.c_int(), C.c_int(), C.c_uint64()

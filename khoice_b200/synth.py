@@ -180,3 +180,23 @@ def write_dataset(cfg: SynthConfig, work_root: str, compresslevel: int = 1) -> N
         for i in range(1, cfg.genomes_per_group + 1):
             with gzip.open(os.path.join(d, genome_name(g, i) + ".fna.gz"), "wb", compresslevel=compresslevel) as fd:
                 fd.write(make_genome(cfg, g, i))
+
+
+def write_dataset_type2(cfg: SynthConfig, work_root: str, compresslevel: int = 1) -> None:
+    """Experiment type 2 layout (/root/reference/workflow/rules/exp_type_2.smk:31-48): the LAST genome of every
+    group is the held-out pivot ``input_type_2/pivot/dataset_{n}/pivot_{n}.fna.gz``, the others go to
+    ``input_type_2/rest_of_set/dataset_{n}/`` (next to a ``nonpivot_names.txt`` like the reference's database)."""
+    for g in range(1, cfg.n_groups + 1):
+        d = os.path.join(work_root, "input_type_2", "rest_of_set", f"dataset_{g}")
+        os.makedirs(d, exist_ok=True)
+        names = []
+        for i in range(1, cfg.genomes_per_group):
+            names.append(genome_name(g, i))
+            with gzip.open(os.path.join(d, genome_name(g, i) + ".fna.gz"), "wb", compresslevel=compresslevel) as fd:
+                fd.write(make_genome(cfg, g, i))
+        with open(os.path.join(d, "nonpivot_names.txt"), "w") as fd:
+            fd.write("\n".join(names) + "\n")
+        p = os.path.join(work_root, "input_type_2", "pivot", f"dataset_{g}")
+        os.makedirs(p, exist_ok=True)
+        with gzip.open(os.path.join(p, f"pivot_{g}.fna.gz"), "wb", compresslevel=compresslevel) as fd:
+            fd.write(make_genome(cfg, g, cfg.genomes_per_group))

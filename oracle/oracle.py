@@ -129,5 +129,80 @@ def exp1(genomes, group_of, n_groups: int, k: int, cs: int = CS_DEFAULT, nbins: 
     return within, across, dict(zip(names, (int(x) for x in stats)))
 
 
+def _row_ids(arrays, k: int):
+    """Map k-mer words of several arrays to dense integer ids that compare like the k-mers (k <= 32: the values
+    themselves; k <= 64: ranks of the (hi, lo) pairs)."""
+    if k <= 32:
+        return [np.ascontiguousarray(a, dtype=np.uint64).reshape(-1) for a in arrays]
+    cat = np.concatenate([np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 2) for a in arrays], axis=0)
+    if cat.shape[0] == 0:
+        return [np.empty(0, np.uint64) for _ in arrays]
+    order = np.lexsort((cat[:, 0], cat[:, 1]))  # by hi, then lo
+    srt = cat[order]
+    new = np.ones(srt.shape[0], dtype=bool)
+    new[1:] = np.any(srt[1:] != srt[:-1], axis=1)
+    ranks = np.empty(cat.shape[0], dtype=np.uint64)
+    ranks[order] = (np.cumsum(new) - 1).astype(np.uint64)
+    out, at = [], 0
+    for a in arrays:
+        n = np.asarray(a).reshape(-1, 2).shape[0]
+        out.append(ranks[at:at + n])
+        at += n
+    return out
+
+
+def simple_intersect_ocsum(a_keys, a_counts, b_keys, b_counts, k: int, cs: int = CS_DEFAULT):
+    """`kmc_tools simple A B intersect O -ocsum` (/root/reference/workflow/rules/exp_type_2.smk:354-365, 470-481):
+    k-mers present in both inputs, counter = c_A + c_B saturated at cs (rule R10, [KMC-ext]: the saturation value of
+    the output is not visible in the reference; every counter on this path is far below either candidate).
+    Inputs sorted and duplicate-free.  Returns (keys, uint32 counts)."""
+    ia, ib = _row_ids([a_keys, b_keys], k)
+    pos = np.searchsorted(ib, ia)
+    pos_c = np.minimum(pos, max(ib.shape[0] - 1, 0))
+    hit = (pos < ib.shape[0]) & (ib[pos_c] == ia) if ib.shape[0] else np.zeros(ia.shape[0], dtype=bool)
+    cnt = np.minimum(np.asarray(a_counts, dtype=np.uint64)[hit] + np.asarray(b_counts, dtype=np.uint64)[pos_c[hit]], cs).astype(np.uint32)
+    return np.asarray(a_keys)[hit], cnt
+
+
+def simple_kmers_subtract(a_keys, a_counts, b_keys, k: int):
+    """`kmc_tools simple A B kmers_subtract O` (exp_type_2.smk:367-380, 483-496): k-mers of A absent from B, with A's
+    counters."""
+    ia, ib = _row_ids([a_keys, b_keys], k)
+    pos = np.searchsorted(ib, ia)
+    pos_c = np.minimum(pos, max(ib.shape[0] - 1, 0))
+    hit = (pos < ib.shape[0]) & (ib[pos_c] == ia) if ib.shape[0] else np.zeros(ia.shape[0], dtype=bool)
+    return np.asarray(a_keys)[~hit], np.asarray(a_counts, dtype=np.uint32)[~hit]
+
+
+def exp2(groups, pivots, k: int, cs: int = CS_DEFAULT, nbins: int = NBINS_DEFAULT):
+    """Whole exp-2 arithmetic for one k (rule chain of exp_type_2.smk:297-508), built from the same primitives.
+
+    groups: list of lists of FASTA texts (rest_of_set of every dataset); pivots: one FASTA text per dataset.
+    Returns (within, across), each uint64 [n_datasets, 2, nbins+1]: [:, 0] = histogram of the kmers_subtract result,
+    [:, 1] = histogram of the intersect -ocsum result."""
+    n = len(groups)
+    within = np.zeros((n, 2, nbins + 1), dtype=np.uint64)
+    across = np.zeros((n, 2, nbins + 1), dtype=np.uint64)
+    unions, psets = [], []
+    for d in range(n):
+        pset = genome_set(pivots[d], k)
+        ones = np.ones(pset.shape[0], dtype=np.uint32)
+        ukeys, ucnt = union_sum([genome_set(g, k) for g in groups[d]], k, cs)
+        _, c = simple_intersect_ocsum(pset, ones, ukeys, ucnt, k, cs)
+        within[d, 1] = histogram(c, nbins)
+        _, c = simple_kmers_subtract(pset, ones, ukeys, k)
+        within[d, 0] = histogram(c, nbins)
+        unions.append(ukeys)
+        psets.append(pset)
+    for d in range(n):
+        ones = np.ones(psets[d].shape[0], dtype=np.uint32)
+        okeys, ocnt = union_sum([unions[i] for i in range(n) if i != d], k, cs)
+        _, c = simple_intersect_ocsum(psets[d], ones, okeys, ocnt, k, cs)
+        across[d, 1] = histogram(c, nbins)
+        _, c = simple_kmers_subtract(psets[d], ones, okeys, k)
+        across[d, 0] = histogram(c, nbins)
+    return within, across
+
+
 def num_threads() -> int:
     return int(lib().ko_num_threads())

@@ -100,3 +100,26 @@ def exp1(groups, k: int, cs: int = 5000, nbins: int = 5000):
         group_sets.append([x for x, _ in t])
     across_table = union_sum(group_sets, cs)
     return within, histogram(across_table, nbins), tables
+
+
+def exp2(groups, pivots, k: int, cs: int = 5000, nbins: int = 5000):
+    """Experiment type 2 (exp_type_2.smk:297-508) with Python sets and dicts.  groups: rest_of_set FASTA texts per
+    dataset; pivots: one FASTA text per dataset.  Returns (within, across): per dataset (sub_hist, inter_hist) where
+    sub = `pivot kmers_subtract union` (all counters 1) and inter = `pivot intersect union -ocsum` (1 + union counter)."""
+    unions, psets = [], []
+    for genomes in groups:
+        unions.append(dict(union_sum([genome_set(g, k) for g in genomes], cs)))
+    for p in pivots:
+        psets.append(genome_set(p, k))
+
+    def versus(pset, table):
+        sub = [(x, 1) for x in pset if x not in table]
+        inter = [(x, min(1 + table[x], cs)) for x in pset if x in table]
+        return histogram(sub, nbins), histogram(inter, nbins)
+
+    within = [versus(psets[d], unions[d]) for d in range(len(groups))]
+    across = []
+    for d in range(len(groups)):
+        others = dict(union_sum([sorted(unions[i]) for i in range(len(groups)) if i != d], cs))
+        across.append(versus(psets[d], others))
+    return within, across

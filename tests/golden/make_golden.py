@@ -9,6 +9,10 @@ The GPU box has no /root/reference, so the outputs are committed:
                          across_group_union_analysis (:268-297) executed on synthetic histogram files
   complex_ops.json       the operation files written by the parse-time block (exp_type_1.smk:26-84)
   canonical.json         get_canonical_kmer (src/merge_lists.py:60-73) on random k-mers
+  summarize_type2.json   inputs/outputs of summarize_histogram_type2 (exp_type_2.smk:171-216)
+  t2_within_case*.csv, t2_across_case*.csv + tables_cases_type2.json
+                         the `run:` bodies of within_group_analysis_exp_type2 (exp_type_2.smk:404-438) and
+                         across_group_analysis_exp_type2 (:521-554) executed on synthetic histogram files
 
 Nothing from the reference is copied into the repo: its source is read from /root/reference at run time,
 sliced by line number and exec'd.  The reference environment is Python 3.10, where sum() over floats is
@@ -206,6 +210,101 @@ def make_canonical():
     print("canonical vectors:", len(vec))
 
 
+def load_summarize2(sum_impl):
+    ns = {"sum": sum_impl}
+    exec(slice_source(f"{REF}/workflow/rules/exp_type_2.smk", 171, 216), ns)
+    return ns["summarize_histogram_type2"]
+
+
+def t2_hist_pair(rnd, members, rows, scale):
+    """(sub_counts, inter_counts) like the two kmc_tools histograms of exp 2: sub has only row 1, inter has no row 1."""
+    sub = [0] * rows
+    sub[0] = rnd.randrange(0, scale)
+    inter = [0] * rows
+    for i in range(1, min(members + 1, rows)):
+        if rnd.random() < 0.85:
+            inter[i] = rnd.randrange(0, scale)
+    if sub[0] + sum(inter) == 0:
+        sub[0] = 1
+    return sub, inter
+
+
+def make_summarize2():
+    f310, f312 = load_summarize2(py310_sum), load_summarize2(sum)
+    rnd = random.Random(4321)
+    cases = [([5] + [0] * 19, [0, 3, 2] + [0] * 17, 4, False, 31),
+             ([5] + [0] * 19, [1, 3, 2] + [0] * 17, 4, False, 31),        # raises: intersection has unique k-mers
+             ([5, 1] + [0] * 18, [0, 3, 2] + [0] * 17, 4, False, 31),     # raises: subtract has non-unique k-mers
+             ([0] * 5000, [0, 7] + [0] * 4998, 9, True, 12)]
+    for _ in range(60):
+        members = rnd.choice([1, 2, 3, 4, 5, 9, 10, 37, 50, 100, 200])
+        across = rnd.random() < 0.5
+        rows = rnd.choice([20, 255, 5000])
+        sub, inter = t2_hist_pair(rnd, members, rows, rnd.choice([10, 1000, 10**6, 10**9]))
+        cases.append((sub, inter, members, across, rnd.choice([7, 8, 15, 21, 30, 31, 34, 49, 63])))
+    out, differs = [], 0
+    for sub, inter, members, across, k in cases:
+        rec = {"sub": trim(sub), "inter": trim(inter), "rows": len(inter), "members": members, "across": across, "k": k}
+        try:
+            m = f310(list(sub), list(inter), members, across, k)
+            m2 = f312(list(sub), list(inter), members, across, k)
+            differs += int([float(x) for x in m] != [float(x) for x in m2])
+            rec.update(metrics=[float(x) for x in m], repr=[str(x) for x in m])
+        except (AssertionError, IndexError, ZeroDivisionError) as e:
+            rec["raises"] = type(e).__name__
+        out.append(rec)
+    with open(os.path.join(HERE, "summarize_type2.json"), "w") as fd:
+        json.dump({"source": "exp_type_2.smk:171-216 exec'd with py3.10 sum", "py312_sum_differs": differs, "cases": out}, fd)
+    print("summarize2 cases:", len(out), "raising:", sum(1 for c in out if "raises" in c), "py3.12-sum differences:", differs)
+
+
+def make_tables2():
+    rnd = random.Random(777)
+    cases = []
+    for case, (num_datasets, members, k_values) in enumerate([(2, [4, 4], ["7", "15", "31"]), (3, [3, 8, 1], ["8", "21", "30", "34"]),
+                                                              (10, [49] * 10, ["31"])]):
+        work = tempfile.mkdtemp(prefix="khb_golden_")
+        cwd = os.getcwd()
+        os.chdir(work)
+        try:
+            for n in range(1, num_datasets + 1):
+                os.makedirs(f"input_type_2/rest_of_set/dataset_{n}")
+                for g in range(members[n - 1]):
+                    open(f"input_type_2/rest_of_set/dataset_{n}/genome_{g}.fna.gz", "wb").close()
+                open(f"input_type_2/rest_of_set/dataset_{n}/nonpivot_names.txt", "w").close()  # must not be counted
+            hists = {}
+            for scope, top_of in (("within", lambda n: members[n - 1]), ("across", lambda n: num_datasets - 1)):
+                for n in range(1, num_datasets + 1):
+                    for k in k_values:
+                        sub, inter = t2_hist_pair(rnd, top_of(n), 5000, 4 ** min(int(k), 11))
+                        base = f"{scope}_dataset_results_type_2/k_{k}/dataset_{n}"
+                        hists[f"{base}/subtract/dataset_{n}_pivot_subtract_group.hist.txt"] = sub
+                        hists[f"{base}/intersect/dataset_{n}_pivot_intersect_group.hist.txt"] = inter
+            for p, h in hists.items():
+                write_hist(p, h)
+            ns = {"sum": py310_sum, "os": os, "num_datasets": num_datasets, "k_values": k_values}
+            exec(slice_source(f"{REF}/workflow/rules/exp_type_2.smk", 123, 129), ns)   # get_num_of_dataset_members_exp2
+            exec(slice_source(f"{REF}/workflow/rules/exp_type_2.smk", 153, 216), ns)   # file lists + summarize_histogram_type2
+            os.makedirs("within_dataset_analysis_type_2"); os.makedirs("across_dataset_analysis_type_2")
+            ns["input"] = ns["get_within_group_histogram_files"](None)
+            ns["output"] = ["within_dataset_analysis_type_2/within_dataset_analysis.csv"]
+            exec(slice_source(f"{REF}/workflow/rules/exp_type_2.smk", 404, 438, dedent=8), ns)
+            ns["input"] = ns["get_across_group_histogram_files"](None)
+            ns["output"] = ["across_dataset_analysis_type_2/across_dataset_analysis.csv"]
+            exec(slice_source(f"{REF}/workflow/rules/exp_type_2.smk", 521, 554, dedent=8), ns)
+            shutil.copyfile(ns["output"][0], os.path.join(HERE, f"t2_across_case{case}.csv"))
+            shutil.copyfile("within_dataset_analysis_type_2/within_dataset_analysis.csv", os.path.join(HERE, f"t2_within_case{case}.csv"))
+            cases.append({"num_datasets": num_datasets, "members": members, "k_values": k_values,
+                          "hists": {p: h[:max(max(members), num_datasets) + 3] for p, h in hists.items()}})
+        finally:
+            os.chdir(cwd)
+            shutil.rmtree(work)
+    with open(os.path.join(HERE, "tables_cases_type2.json"), "w") as fd:
+        json.dump({"source": "exp_type_2.smk:404-438 and :521-554 exec'd with py3.10 sum; hists truncated (rest is zeros, 5000 rows)",
+                   "cases": cases}, fd)
+    print("type-2 table cases:", len(cases))
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("needs /root/reference (build container only)")
@@ -213,3 +312,5 @@ if __name__ == "__main__":
     make_tables()
     make_complex_ops()
     make_canonical()
+    make_summarize2()
+    make_tables2()

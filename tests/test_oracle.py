@@ -97,3 +97,25 @@ def test_generator_counts_and_determinism(oracle):
     assert synth.count_bases(g) == P.n_symbols(g) == oracle.kmers(g, 31)[1]
     assert b">" in g and b"N" in g and any(c in g for c in b"acgt")
     assert max(len(l) for l in g.split(b"\n") if not l.startswith(b">")) <= 80
+
+
+@pytest.mark.parametrize("k", [4, 11, 31, 33, 47])
+def test_exp2_c_oracle_equals_python_oracle(oracle, k):
+    """Experiment type 2 (exp_type_2.smk:297-508): the numpy/C statement against the set/dict statement, and the
+    invariants the reference asserts (exp_type_2.smk:184-185): the intersect histogram has no row 1, the subtract
+    histogram has nothing but row 1."""
+    from khoice_b200 import synth
+    from oracle import pyoracle
+    cfg = synth.SynthConfig(n_groups=3, genomes_per_group=4, genome_len=2500, seed=17)
+    groups = [[synth.make_genome(cfg, g, i) for i in range(1, 4)] for g in (1, 2, 3)]
+    pivots = [synth.make_genome(cfg, g, 4) for g in (1, 2, 3)]
+    groups[2] = []  # a dataset with an empty rest of set
+    w, a = oracle.exp2(groups, pivots, k, nbins=30)
+    pw, pa = pyoracle.exp2(groups, pivots, k, nbins=30)
+    for d in range(3):
+        for ref, got in ((pw, w), (pa, a)):
+            assert list(got[d, 0]) == ref[d][0] and list(got[d, 1]) == ref[d][1], (k, d)
+            assert got[d, 1, 1] == 0 and got[d, 0, 2:].sum() == 0
+        n_pivot = len(pyoracle.genome_set(pivots[d], k))
+        assert int(w[d].sum()) == n_pivot and int(a[d].sum()) == n_pivot
+    assert w[2, 1].sum() == 0  # nothing to intersect with
