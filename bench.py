@@ -64,22 +64,31 @@ def generate_groups(cfg, group_numbers, procs):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms.  The process is started BEFORE the warm-up (its
+    start-up alone takes a few hundred ms, longer than a short timed region); samples carry nvidia-smi's own
+    timestamp and only those inside [begin(), end()] -- the timed region -- are reported."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
+        self.t0 = self.t1 = None
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(index)],
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.15)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -87,22 +96,34 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons, pw = [], [], set(), []
+        import datetime
+        rows = []
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 7:
+            if len(c) < 8:
                 continue
             try:
-                sm.append(float(c[0])); mx.append(float(c[1])); pw.append(float(c[2]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(c[1]), float(c[2]), float(c[3]), c[4:8]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
         self.f.close()
         os.unlink(self.f.name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.05 <= r[0] <= (self.t1 or r[0]) + 0.05]
+        where = "timed region"
+        if not inside and rows and self.t0 is not None:
+            # region shorter than the sampling period: the sample closest to it (taken under the same load, in the warm-up)
+            inside = [min(rows, key=lambda r: abs(r[0] - self.t0))]
+            where = "nearest sample (region shorter than the 100 ms period)"
+        reasons = set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm = [r[1] for r in inside]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(r[2] for r in inside) if inside else None,
+                "power_w_max": max(r[3] for r in inside) if inside else None, "samples": len(inside), "samples_total": len(rows),
+                "window": where, "reasons": sorted(reasons)}
 
 
 def measured_peak():
@@ -297,11 +318,12 @@ def main():
         ha, _ = finish(hs)
         return hs, ha, nb
 
-    def timed(fn, steps, profile=False):
+    def timed(fn, steps, profile=False, sampler=None):
         barrier()
         if profile:
             eng.profile_enable(True)
-        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.begin()
         launches0 = eng.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(ext_stream)
@@ -316,6 +338,8 @@ def main():
         prof = eng.profile_read() if profile else None
         if profile:
             eng.profile_enable(False)
+        if sampler:
+            sampler.end()
         clocks = sampler.stop() if sampler else None
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -323,9 +347,10 @@ def main():
         return out, float(t.item()), wall, eng.launch_count - launches0, prof, clocks
 
     # 3. device-resident leg
+    sampler = ClockSampler(local) if rank == 0 else None  # started before the warm-up, filtered to the timed region
     for _ in range(args.warmup):
         ref_out = step_device()
-    (hs, ha, nb), ms_dev, wall_dev, launches, prof, clocks = timed(step_device, args.steps, profile=True)
+    (hs, ha, nb), ms_dev, wall_dev, launches, prof, clocks = timed(step_device, args.steps, profile=True, sampler=sampler)
     # 4. end-to-end leg (host buffers)
     for _ in range(min(args.warmup, 2)):
         step_e2e()
