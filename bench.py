@@ -376,6 +376,14 @@ def main():
         kernels = {name: {"launches": v["launches"], "ms": round(v["ms"], 3),
                           "alg_GBps": round(v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None,
                           "share_of_step": round(v["ms"] / ms_dev, 4)} for name, v in prof.items()}
+        # whole step against the roofline: algorithmic bytes of every kernel launched in the timed steps (this design's own
+        # per-kernel contracts) / device time of the steps.  Rank 0's kernels x world (weak scaling).
+        total_alg = float(sum(v["alg_bytes"] for v in prof.values())) * world
+        pipeline = {"algorithmic_bytes_per_base": total_alg / max(bases_all * args.steps, 1.0),
+                    "achieved": total_alg / (ms_dev * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                    "frac": total_alg / (ms_dev * 1e-3) / 1e9 / (peak * world) if peak else None,
+                    "note": "single-sort contract (~110 B/base); the KMC-shaped chain of SURVEY.md 8d (sort, unique, sort, count: ~329 B/base) "
+                            "would need 3x these bytes for the same tables"}
         hist_bytes = (len(mine) + 1) * 5001 * 8
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -393,6 +401,7 @@ def main():
                          "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "traffic": (ratio * per_launch_alg) if ratio else None, "algorithmic_bytes_per_launch": per_launch_alg,
                          "launches": osw["launches"], "avg_launch_ms": osw["ms"] / max(osw["launches"], 1), "peak_source": peak_src},
+            "pipeline_roofline": pipeline,
             "kernels": kernels,
             "clocks": clocks,
             "wall_ms_per_step": wall_dev * 1e3 / args.steps,

@@ -201,7 +201,7 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const unsigne
                 unsigned short *__restrict__ pout, const u64 *__restrict__ seg_off,
                 const u64 *__restrict__ seg_tile, int nseg, int pass_row, int shift, int npass,
                 const u32 *__restrict__ bin_base /* [nseg][npass][256], exclusive */, u64 *__restrict__ lookback,
-                u32 *__restrict__ ticket, u32 epoch)
+                u32 *__restrict__ ticket, u32 epoch, int debug_nolb)
 {
     constexpr int TILE = BLOCK * ITEMS;
     constexpr int NW = BLOCK / 32;
@@ -389,7 +389,7 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const unsigne
     PHASE_MARK(5);  // reorder
     // finish the look-back (256 digit threads) unless it already ran right after the early count (EARLY 2)
     if (tid < 256) {
-        if (EARLY != 2) excl = lookback_finish<LBW>(lbcol, rel, win, count, epoch);
+        if (EARLY != 2) excl = debug_nolb ? 0u : lookback_finish<LBW>(lbcol, rel, win, count, epoch);  // debug_nolb: timing experiment only (wrong output)
         glob_off[tid] = bin_base[((size_t)seg * npass + pass_row) * 256 + tid] + excl - dstart;
     }
     PHASE_MARK(6);  // look-back (thread 0's column)
@@ -422,10 +422,15 @@ static int launch_passes(khb_ctx *ctx, Key *src, Key *dst, unsigned short *psrc,
         KHB_CUDA(ctx, cudaFuncSetAttribute(onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH, PAY, EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
         attr_set = true;
     }
+    static int nolb = -1;
+    if (nolb < 0) {
+        const char *e = getenv("KHB_SORT_DEBUG_NOLB");
+        nolb = e ? atoi(e) : 0;
+    }
     for (int pass = 0; pass < npass; pass++) {
         khb_prof_begin(ctx, KHB_K_ONESWEEP);
         onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH, PAY, EARLY><<<(unsigned)ntiles, BLOCK, shm, ctx->stream>>>(
-            src, dst, psrc, pdst, d_off, d_tile, nseg, pass, first_bit + 8 * pass, npass, d_hist, d_lb, d_ticket + pass, (u32)(pass + 1));
+            src, dst, psrc, pdst, d_off, d_tile, nseg, pass, first_bit + 8 * pass, npass, d_hist, d_lb, d_ticket + pass, (u32)(pass + 1), nolb);
         KHB_LAUNCH_CHECK(ctx);
         khb_prof_end(ctx, KHB_K_ONESWEEP, 2 * n_keys * (sizeof(Key) + (PAY ? 2 : 0)));  // read + write every key (+ payload) once
         Key *t = src; src = dst; dst = t;
