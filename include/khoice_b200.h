@@ -82,6 +82,7 @@ KHB_API int khb_alloc_host(khb_ctx *ctx, size_t bytes, void **h_ptr); /* pinned 
 KHB_API int khb_free_host(khb_ctx *ctx, void *h_ptr);
 KHB_API int khb_memcpy_h2d(khb_ctx *ctx, void *d_dst, const void *h_src, size_t bytes); /* async on the ctx stream */
 KHB_API int khb_memcpy_d2h(khb_ctx *ctx, void *h_dst, const void *d_src, size_t bytes); /* async on the ctx stream */
+KHB_API int khb_memcpy_d2d(khb_ctx *ctx, void *d_dst, const void *d_src, size_t bytes); /* async on the ctx stream */
 KHB_API int khb_memset(khb_ctx *ctx, void *d_dst, int value, size_t bytes);
 KHB_API int khb_sync(khb_ctx *ctx);
 
@@ -232,6 +233,16 @@ KHB_API int khb_pivot_across(khb_ctx *ctx, uint32_t nbins, uint64_t *h_hists, kh
  * d_a[i] in the sorted, duplicate-free d_b, or UINT64_MAX.  Keys are canonical k-mer values (khb_key_bytes(k) each). */
 KHB_API int khb_sorted_lookup(khb_ctx *ctx, const void *d_a, uint64_t n_a, const void *d_b, uint64_t n_b, int k,
                       uint64_t *d_index);
+
+/* Experiment type 4 (confusion matrix, exp_type_4.smk:217-270 + src/merge_lists.py:14-33): for every k-mer of
+ * n_query_sets query sets (the pivots' k-mers; canonical values, ASCENDING and duplicate-free inside each set, concatenated
+ * in d_queries with host offsets h_query_off[n_query_sets+1]) the set of retained group sets that contain it -- what the
+ * reference obtains from G x G `kmc_tools simple ... intersect` runs, G x G text dumps and a Python dictionary join.
+ * The retained group sets are the groups given to khb_group_from_* with keep_set since the last reset, group g occupying
+ * keys [h_group_off[g], h_group_off[g+1]) of the store (khb_group_sets_info after each group).
+ * d_mask[(i) * mask_words + w] bit b is set iff group 64 w + b contains query key i.  mask_words >= ceil(n_groups / 64), <= 4. */
+KHB_API int khb_group_membership(khb_ctx *ctx, int n_groups, const uint64_t *h_group_off, const void *d_queries, int n_query_sets,
+                         const uint64_t *h_query_off, uint64_t *d_mask, int mask_words);
 
 /* K7: split n keys into n_parts buckets by splitmix64(key) % n_parts (multi-GPU hash-range partition of the
  * k-mer space).  d_out receives the keys grouped by bucket, h_part_off[n_parts+1] the bucket offsets. */

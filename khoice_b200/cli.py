@@ -11,6 +11,10 @@ and, for experiment type 2 (/root/reference/workflow/rules/exp_type_2.smk:354-38
     kmc_tools simple {A} {B} intersect {out_prefix} -ocsum
     kmc_tools simple {A} {B} kmers_subtract {out_prefix}
 
+and for experiment type 4 (exp_type_4.smk:254-271):
+
+    kmc_tools transform {in_prefix} dump -s {out.txt}
+
 ``khoice_b200/bin/kmc`` and ``khoice_b200/bin/kmc_tools`` exec this module, so putting that directory
 first on PATH makes the UNMODIFIED reference rules run on the B200 engine.  Databases use this package's
 own layout (khoice_b200/kmcdb.py).  Exit status: 0 ok, 1 on any error with partial outputs removed
@@ -122,6 +126,12 @@ def transform_set_counts(in_prefix: str, value: int, out_prefix: str) -> None:
     kmcdb.write_db(out_prefix, db.k, db.keys, np.full(db.keys.shape[0], value, np.uint32), hist, max(db.counter_max, value))
 
 
+def transform_dump(in_prefix: str, out_txt: str) -> None:
+    """`kmc_tools transform X dump -s out.txt` (exp_type_4.smk:254-258, 267-271): sorted text dump."""
+    db = kmcdb.read_db(in_prefix)
+    kmcdb.write_text_dump(out_txt, db.keys, db.counts, db.k)
+
+
 def transform_histogram(in_prefix: str, out_txt: str) -> None:
     db = kmcdb.read_db(in_prefix, header_only=True)
     write_histogram_file(out_txt, db.hist, HIST_ROWS)
@@ -219,6 +229,8 @@ def kmc_tools_main(argv: List[str]) -> int:
     args = [a for a in argv if not re.fullmatch(r"-t\d+", a) and a not in ("-v", "-hp")]
     if not args:
         raise UsageError("usage: kmc_tools <transform|complex|simple> ...")
+    if args[0] == "transform" and "dump" in args and "-s" not in args:
+        raise UsageError("kmc_tools transform dump: only the sorted dump (-s) is supported (the reference passes -s)")
     if args[0] == "simple":
         flags = [a for a in args[1:] if a.startswith("-")]
         pos = [a for a in args[1:] if not a.startswith("-")]
@@ -238,7 +250,10 @@ def kmc_tools_main(argv: List[str]) -> int:
         if len(args) == 4 and args[2] == "histogram":
             transform_histogram(args[1], args[3])
             return 0
-        raise UsageError("kmc_tools transform: only `set_counts <v> <out>` and `histogram <out.txt>` are supported")
+        if len(args) == 5 and args[2] == "dump" and args[3] == "-s":
+            transform_dump(args[1], args[4])
+            return 0
+        raise UsageError("kmc_tools transform: only `set_counts <v> <out>`, `histogram <out.txt>` and `dump -s <out.txt>` are supported")
     raise UsageError(f"kmc_tools {args[0]}: not supported by the khoice-b200 shim (exp type 1 uses transform and complex)")
 
 
@@ -308,7 +323,7 @@ def _outputs_of(tool: str, argv: List[str]) -> List[str]:
             pos = [a for a in argv if not a.startswith("-")]
             outs = [pos[1] + ".kmc_pre", pos[1] + ".kmc_suf"]
         elif argv and argv[0] == "transform":
-            outs = [argv[-1]] if argv[2] == "histogram" else [argv[-1] + ".kmc_pre", argv[-1] + ".kmc_suf"]
+            outs = [argv[-1]] if argv[2] in ("histogram", "dump") else [argv[-1] + ".kmc_pre", argv[-1] + ".kmc_suf"]
         elif argv and argv[0] == "complex":
             _, out, _ = parse_complex(argv[1])
             outs = [out + ".kmc_pre", out + ".kmc_suf"]

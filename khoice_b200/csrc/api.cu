@@ -26,6 +26,7 @@ int khb_pairs_count_impl(khb_ctx *, const void *, const unsigned short *, size_t
 int khb_fill_segment_ids_impl(khb_ctx *, unsigned short *, const u64 *, int, u64);
 int khb_pivot_across_impl(khb_ctx *, const void *, const unsigned short *, size_t, int, int, u32, u32, u32, u64 *);
 int khb_sorted_lookup_impl(khb_ctx *, const void *, u64, const void *, u64, int, u64 *);
+int khb_membership_impl(khb_ctx *, const void *, const unsigned short *, size_t, int, int, u32, int, const void *, const u64 *, int, u64 *);
 // Experiment type 2: the pivot k-mer sets P_1 .. P_G (device, concatenated) and, for every pivot group call, the range its
 // rest-of-set union occupies in the group-set store.
 struct khb_pivot_store {
@@ -297,6 +298,12 @@ int khb_memcpy_d2h(khb_ctx *ctx, void *h, const void *d, size_t bytes)
 {
     KHB_CHECK_CTX(ctx);
     if (bytes) KHB_CUDA(ctx, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return KHB_OK;
+}
+int khb_memcpy_d2d(khb_ctx *ctx, void *d_dst, const void *d_src, size_t bytes)
+{
+    KHB_CHECK_CTX(ctx);
+    if (bytes) KHB_CUDA(ctx, cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return KHB_OK;
 }
 int khb_memset(khb_ctx *ctx, void *d, int value, size_t bytes)
@@ -1249,7 +1256,7 @@ int khb_pivot_across(khb_ctx *ctx, uint32_t nbins, uint64_t *h_hists, khb_stats 
     if ((rc = khb_scratch_get(ctx, SCR_PAY_B, (n + 8) * 2, &p))) return rc;
     unsigned short *payB = (unsigned short *)p;
     const size_t hist_bytes = (size_t)G * (nbins + 1) * sizeof(u64);
-    if ((rc = khb_scratch_get(ctx, SCR_MISC, hist_bytes + (size_t)(2 * G + 1) * 8 + 64, &p))) return rc;
+    if ((rc = khb_scratch_get(ctx, SCR_AUX, hist_bytes + (size_t)(2 * G + 1) * 8 + 64, &p))) return rc;
     u64 *d_hist = (u64 *)p;
     u64 *d_seg = d_hist + (size_t)G * (nbins + 1);
     PhaseTimer tm(ctx);
@@ -1291,6 +1298,61 @@ int khb_sorted_lookup(khb_ctx *ctx, const void *d_a, uint64_t n_a, const void *d
 {
     KHB_CHECK_CTX(ctx);
     return khb_sorted_lookup_impl(ctx, d_a, n_a, d_b, n_b, k, (u64 *)d_index);
+}
+
+// ---- group membership of query k-mers (experiment type 4) ---------------------------------------------------------
+int khb_group_membership(khb_ctx *ctx, int n_groups, const uint64_t *h_group_off, const void *d_queries, int n_query_sets,
+                         const uint64_t *h_query_off, uint64_t *d_mask, int mask_words)
+{
+    KHB_CHECK_CTX(ctx);
+    if (n_groups < 1 || n_query_sets < 1 || !h_group_off || !h_query_off || !d_queries || !d_mask)
+        return khb_fail(ctx, KHB_ERR_ARG, "khb_group_membership: bad arguments");
+    if (!ctx->gs_k) return khb_fail(ctx, KHB_ERR_STATE, "khb_group_membership: no group set retained");
+    if (h_group_off[0] != 0 || h_group_off[n_groups] != ctx->gs_len) return khb_fail(ctx, KHB_ERR_ARG, "khb_group_membership: group offsets do not cover the retained sets");
+    if (mask_words < (n_groups + 63) / 64 || mask_words > 4) return khb_fail(ctx, KHB_ERR_ARG, "khb_group_membership: %d groups need %d mask words (limit 4)", n_groups, (n_groups + 63) / 64);
+    if (n_groups + n_query_sets > 65535) return khb_fail(ctx, KHB_ERR_ARG, "khb_group_membership: too many sets");
+    const int k = ctx->gs_k;
+    const size_t W = (size_t)khb_key_bytes(k);
+    const u64 nu = ctx->gs_len, nq = h_query_off[n_query_sets], n = nu + nq;
+    if (n >= (1ull << 32)) return khb_fail(ctx, KHB_ERR_ARG, "khb_group_membership: %llu keys (limit 2^32 - 1)", n);
+    int rc;
+    void *p;
+    if ((rc = khb_scratch_get(ctx, SCR_KEYS_A, (n + 4) * W, &p))) return rc;
+    void *bufA = p;
+    if ((rc = khb_scratch_get(ctx, SCR_KEYS_B, (n + 4) * W, &p))) return rc;
+    void *bufB = p;
+    if ((rc = khb_scratch_get(ctx, SCR_PAY_A, (n + 8) * 2, &p))) return rc;
+    unsigned short *payA = (unsigned short *)p;
+    if ((rc = khb_scratch_get(ctx, SCR_PAY_B, (n + 8) * 2, &p))) return rc;
+    unsigned short *payB = (unsigned short *)p;
+    const int nsets = n_groups + n_query_sets;
+    if ((rc = khb_scratch_get(ctx, SCR_AUX, (size_t)(nsets + 1 + n_query_sets + 1) * 8 + 64, &p))) return rc;
+    u64 *d_seg = (u64 *)p, *d_qoff = d_seg + nsets + 1;
+    std::vector<u64> seg((size_t)nsets + 1);
+    u64 max_len = 0;
+    for (int j = 0; j <= n_groups; j++) seg[j] = h_group_off[j];
+    for (int j = 1; j <= n_query_sets; j++) seg[n_groups + j] = nu + h_query_off[j];
+    for (int j = 0; j < nsets; j++) {
+        if (seg[j + 1] < seg[j]) return khb_fail(ctx, KHB_ERR_ARG, "khb_group_membership: offsets not monotone");
+        max_len = seg[j + 1] - seg[j] > max_len ? seg[j + 1] - seg[j] : max_len;
+    }
+    KHB_CUDA(ctx, cudaMemcpyAsync(bufA, ctx->gs_buf, nu * W, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (nq) KHB_CUDA(ctx, cudaMemcpyAsync((char *)bufA + nu * W, d_queries, nq * W, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (nq && ctx->gs_hashed && (rc = khb_remix_impl(ctx, (char *)bufA + nu * W, nq, k, 0))) return rc;  // queries are canonical values
+    KHB_CUDA(ctx, cudaMemcpyAsync(d_seg, seg.data(), seg.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    KHB_CUDA(ctx, cudaMemcpyAsync(d_qoff, h_query_off, (size_t)(n_query_sets + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // pageable sources
+    if ((rc = khb_fill_segment_ids_impl(ctx, payA, d_seg, nsets, max_len))) return rc;
+    KHB_CUDA(ctx, cudaMemsetAsync(d_mask, 0, nq * (size_t)mask_words * 8, ctx->stream));
+    int in_tmp = 0, fb, npass;
+    khb_prefix_plan(k, n, &fb, &npass);
+    if (!ctx->gs_hashed) { fb = 0; npass = (2 * k + 7) / 8; }
+    u64 one_seg[2] = {0, n};
+    if ((rc = khb_sort_bits_impl(ctx, bufA, bufB, one_seg, 1, (int)W, fb, npass, &in_tmp, payA, payB))) return rc;
+    if ((rc = khb_membership_impl(ctx, in_tmp ? bufB : bufA, in_tmp ? payB : payA, n, k, fb, (u32)n_groups, ctx->gs_hashed, d_queries, d_qoff,
+                                  mask_words, (u64 *)d_mask))) return rc;
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KHB_OK;
 }
 
 int khb_partition_by_hash(khb_ctx *ctx, const void *d_keys, uint64_t n, int k, int n_parts, void *d_out, uint64_t *h_part_off)

@@ -1176,3 +1176,74 @@ int khb_sorted_lookup_impl(khb_ctx *ctx, const void *d_a, u64 na, const void *d_
     KHB_LAUNCH_CHECK(ctx);
     return KHB_OK;
 }
+
+// ---- group membership of query k-mers (experiment type 4: src/merge_lists.py:14-33, exp_type_4.smk:217-270) -------------
+// Input: the retained group sets U_1 .. U_G followed by the query sets Q_1 .. Q_P (here: the pivots' k-mers), sorted
+// (stable, by prefix) with payload = set index.  Inside a prefix run every U element precedes every Q element, so a Q
+// element finds all groups that hold its k-mer by walking back over its prefix run.  The result goes to the position the
+// k-mer has in its query set's own (canonical, ascending) order, found by binary search of the un-mixed key:
+//   mask[(q_off[p] + rank) * words + w] bit b  <=>  group 64 w + b contains the k-mer
+template <typename Key> __device__ __forceinline__ Key key_unmix(const Key &x, int k);
+template <> __device__ __forceinline__ Key64 key_unmix<Key64>(const Key64 &x, int k) { return Key64{kmer_unmix64(x.v, k)}; }
+template <> __device__ __forceinline__ Key128 key_unmix<Key128>(const Key128 &x, int k)
+{
+    u64 hi = x.hi, lo = x.lo;
+    kmer_unmix128(hi, lo, k);
+    return Key128{lo, hi};
+}
+
+#define MEMBER_MAXW 4
+template <typename Key>
+__global__ void __launch_bounds__(256)
+membership_kernel(const Key *__restrict__ in, const unsigned short *__restrict__ pay, u64 n, int pshift, u32 n_groups, int k, int hashed,
+                  const Key *__restrict__ q_sorted /* canonical, ascending per query set */, const u64 *__restrict__ q_off, int words,
+                  u64 *__restrict__ mask_out)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const u32 p = pay[i];
+        if (p < n_groups) continue;
+        const u32 q = p - n_groups;
+        const Key key = in[i];
+        if (key_is_sentinel(key)) continue;
+        u64 m[MEMBER_MAXW] = {0, 0, 0, 0};
+        for (u64 j = i; j > 0;) {
+            --j;
+            const Key kj = in[j];
+            if (key_is_sentinel(kj) || !same_prefix(kj, key, pshift)) break;
+            if (!key_eq(kj, key)) continue;
+            const u32 pj = pay[j];
+            if (pj < n_groups) {
+#pragma unroll
+                for (int w = 0; w < MEMBER_MAXW; w++)
+                    if ((int)(pj >> 6) == w) m[w] |= 1ull << (pj & 63u);
+            }
+        }
+        const Key c = hashed ? key_unmix(key, k) : key;
+        u64 lo = q_off[q], hi = q_off[q + 1];  // first position with q_sorted[pos] >= c
+        while (lo < hi) {
+            const u64 mid = lo + ((hi - lo) >> 1);
+            if (key_less(q_sorted[mid], c)) lo = mid + 1; else hi = mid;
+        }
+#pragma unroll
+        for (int w = 0; w < MEMBER_MAXW; w++)
+            if (w < words) mask_out[lo * (u64)words + w] = m[w];
+    }
+}
+
+int khb_membership_impl(khb_ctx *ctx, const void *d_sorted, const unsigned short *d_pay, size_t n, int k, int pshift, u32 n_groups, int hashed,
+                        const void *d_q_sorted, const u64 *d_q_off, int words, u64 *d_mask_out)
+{
+    if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_membership: k=%d outside 1..64", k);
+    if (words < 1 || words > MEMBER_MAXW) return khb_fail(ctx, KHB_ERR_ARG, "khb_membership: %u groups (limit %d)", n_groups, 64 * MEMBER_MAXW);
+    if (n == 0) return KHB_OK;
+    u64 grid = div_up(n, 256);
+    if (grid > (u64)ctx->num_sms * 8) grid = (u64)ctx->num_sms * 8;
+    khb_prof_begin(ctx, KHB_K_RLE);
+    if (k <= 32)
+        membership_kernel<Key64><<<(unsigned)grid, 256, 0, ctx->stream>>>((const Key64 *)d_sorted, d_pay, n, pshift, n_groups, k, hashed, (const Key64 *)d_q_sorted, d_q_off, words, d_mask_out);
+    else
+        membership_kernel<Key128><<<(unsigned)grid, 256, 0, ctx->stream>>>((const Key128 *)d_sorted, d_pay, n, pshift, n_groups, k, hashed, (const Key128 *)d_q_sorted, d_q_off, words, d_mask_out);
+    KHB_LAUNCH_CHECK(ctx);
+    khb_prof_end(ctx, KHB_K_RLE, (u64)n * ((k <= 32 ? 8 : 16) + 2));
+    return KHB_OK;
+}

@@ -198,7 +198,7 @@ enum { KHB_K_PACK = 0, KHB_K_EXTRACT = 1, KHB_K_RADIX_HIST = 2, KHB_K_ONESWEEP =
 void khb_prof_begin(khb_ctx *ctx, int id);
 void khb_prof_end(khb_ctx *ctx, int id, u64 alg_bytes);
 
-enum { SCR_TILE = 0, SCR_LOOKBACK = 1, SCR_HIST = 2, SCR_MISC = 3, SCR_KEYS_A = 4, SCR_KEYS_B = 5, SCR_PACK = 6, SCR_FLAGS = 7, SCR_PAY_A = 8, SCR_PAY_B = 9 };
+enum { SCR_TILE = 0, SCR_LOOKBACK = 1, SCR_HIST = 2, SCR_MISC = 3, SCR_KEYS_A = 4, SCR_KEYS_B = 5, SCR_PACK = 6, SCR_FLAGS = 7, SCR_PAY_A = 8, SCR_PAY_B = 9, SCR_AUX = 10 };  // SCR_MISC belongs to the sort (segment tables, tickets)
 #define KHB_NSCRATCH 12
 
 int khb_fail(khb_ctx *ctx, int code, const char *fmt, ...);

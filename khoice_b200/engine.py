@@ -64,6 +64,7 @@ _SIGNATURES = [
     ("khb_free_host", C.c_int, [_P, _P]),
     ("khb_memcpy_h2d", C.c_int, [_P, _P, _P, C.c_size_t]),
     ("khb_memcpy_d2h", C.c_int, [_P, _P, _P, C.c_size_t]),
+    ("khb_memcpy_d2d", C.c_int, [_P, _P, _P, C.c_size_t]),
     ("khb_memset", C.c_int, [_P, _P, C.c_int, C.c_size_t]),
     ("khb_sync", C.c_int, [_P]),
     ("khb_staged_size", C.c_size_t, [C.c_int, _P]),
@@ -98,6 +99,7 @@ _SIGNATURES = [
     ("khb_pivot_sets_info", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("khb_pivot_across", C.c_int, [_P, C.c_uint32, _P, C.POINTER(Stats)]),
     ("khb_sorted_lookup", C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.c_int, _P]),
+    ("khb_group_membership", C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int]),
     ("khb_partition_by_hash", C.c_int, [_P, _P, C.c_uint64, C.c_int, C.c_int, _P, _P]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
@@ -489,6 +491,44 @@ class Engine:
             return di.download(np.uint64, na).view(np.int64)
         finally:
             da.free(); db.free(); di.free()
+
+    # -- experiment type 4 (confusion matrix, exp_type_4.smk + src/merge_lists.py) -----------------------------------
+    def kmer_counts(self, fasta: bytes, k: int, cs: int = 255):
+        """`kmc -fm -k{k} -ci1` of one FASTA text (exp_type_4.smk:146-153): (keys DeviceBuffer [canonical, ascending],
+        counts uint32 ndarray, n).  The keys stay on the device for group_membership()."""
+        staged = self.stage_fasta([fasta])
+        packed = self.pack_fasta(staged)
+        n = packed["n_symbols"]
+        keys = self.extract_kmers(packed, k)
+        srt = self.sort_keys(keys, n, k)
+        _, runs, ok, oc = self.count_runs(srt, n, k, nbins=16, cs=cs, want_keys=True, want_counts=True)
+        counts = oc.download(np.uint32, runs)
+        for b in (oc, srt, keys, staged.buf, packed["codes"], packed["valid"]):
+            if b is not ok:
+                b.free()
+        return ok, counts, runs
+
+    def group_membership(self, group_off: Sequence[int], query_bufs: Sequence[DeviceBuffer], query_sizes: Sequence[int], k: int) -> np.ndarray:
+        """For every k-mer of the query sets (device buffers of canonical, ascending keys) the bitmask of retained group
+        sets containing it: uint64 [sum(query_sizes), words].  group_off[g] = n_keys of the store before group g."""
+        g = len(group_off) - 1
+        words = max(1, (g + 63) // 64)
+        w = key_words(k)
+        q_off = np.zeros(len(query_bufs) + 1, dtype=np.uint64)
+        q_off[1:] = np.cumsum(np.asarray(query_sizes, dtype=np.uint64))
+        nq = int(q_off[-1])
+        cat = self.alloc(max(nq, 1) * 8 * w + 64)
+        mask = self.alloc(max(nq, 1) * 8 * words)
+        try:
+            for buf, off, sz in zip(query_bufs, q_off[:-1], query_sizes):
+                if sz:
+                    self._chk(self.lib.khb_memcpy_d2d(self.ctx, cat.ptr + int(off) * 8 * w, buf.ptr, int(sz) * 8 * w))
+            goff = np.ascontiguousarray(group_off, dtype=np.uint64)
+            self._chk(self.lib.khb_group_membership(self.ctx, g, goff.ctypes.data, cat.ptr, len(query_bufs), q_off.ctypes.data, mask.ptr, words))
+            return mask.download(np.uint64, nq * words).reshape(nq, words)
+        finally:
+            cat.free()
+            mask.free()
 
     def group_sets_info(self) -> dict:
         k, g, n = C.c_int(), C.c_int(), C.c_uint64()

@@ -91,3 +91,27 @@ def read_db(prefix: str, header_only: bool = False) -> KmerDB:
     keys = np.frombuffer(body, dtype=np.uint64, count=n * (key_bytes // 8)).reshape(shape).copy()
     counts = np.frombuffer(body, dtype=np.uint32, count=n, offset=n * key_bytes).copy()
     return KmerDB(k, keys, counts, hist, cmax, False)
+
+
+def kmer_strings(keys: np.ndarray, k: int) -> np.ndarray:
+    """k-mer words -> uint8 [n, k] ASCII letters (first base = most significant 2 bits, A C G T = 0 1 2 3)."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    n = keys.shape[0]
+    out = np.empty((n, k), dtype=np.uint8)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for j in range(k):
+        bit = 2 * (k - 1 - j)
+        word = keys if keys.ndim == 1 else (keys[:, 1] if bit >= 64 else keys[:, 0])
+        out[:, j] = lut[((word >> np.uint64(bit % 64)) & np.uint64(3)).astype(np.intp)]
+    return out
+
+
+def write_text_dump(path: str, keys: np.ndarray, counts: np.ndarray, k: int) -> None:
+    """`kmc_tools transform X dump -s out.txt`: one "<kmer>\t<count>" line per k-mer, ascending (the format
+    /root/reference/src/merge_lists.py:14-33 parses)."""
+    letters = kmer_strings(keys, k)
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    tmp = f"{path}.tmp.{os.getpid()}"
+    with open(tmp, "wb") as fd:
+        fd.write(b"".join(letters[i].tobytes() + b"\t%d\n" % int(counts[i]) for i in range(letters.shape[0])))
+    os.replace(tmp, path)

@@ -200,3 +200,21 @@ def write_dataset_type2(cfg: SynthConfig, work_root: str, compresslevel: int = 1
         os.makedirs(p, exist_ok=True)
         with gzip.open(os.path.join(p, f"pivot_{g}.fna.gz"), "wb", compresslevel=compresslevel) as fd:
             fd.write(make_genome(cfg, g, cfg.genomes_per_group))
+
+
+def write_dataset_type4(cfg: SynthConfig, work_root: str, compresslevel: int = 1, out_pivot: bool = True) -> None:
+    """Experiment type 4 layout (exp_type_4.smk:31-52): like type 2 but under ``input_type4/`` with all pivots in one
+    directory; with out_pivot=False the pivot is also a member of its rest of set."""
+    os.makedirs(os.path.join(work_root, "input_type4", "pivot"), exist_ok=True)
+    for g in range(1, cfg.n_groups + 1):
+        d = os.path.join(work_root, "input_type4", "rest_of_set", f"dataset_{g}")
+        os.makedirs(d, exist_ok=True)
+        for i in range(1, cfg.genomes_per_group):
+            with gzip.open(os.path.join(d, genome_name(g, i) + ".fna.gz"), "wb", compresslevel=compresslevel) as fd:
+                fd.write(make_genome(cfg, g, i))
+        pivot = make_genome(cfg, g, cfg.genomes_per_group)
+        with gzip.open(os.path.join(work_root, "input_type4", "pivot", f"pivot_{g}.fna.gz"), "wb", compresslevel=compresslevel) as fd:
+            fd.write(pivot)
+        if not out_pivot:
+            with gzip.open(os.path.join(d, f"pivot_{g}.fna.gz"), "wb", compresslevel=compresslevel) as fd:
+                fd.write(pivot)

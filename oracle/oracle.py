@@ -204,5 +204,44 @@ def exp2(groups, pivots, k: int, cs: int = CS_DEFAULT, nbins: int = NBINS_DEFAUL
     return within, across
 
 
+def kmer_counts(fasta, k: int, cs: int = 255):
+    """`kmc -fm -k{k} -ci1` (exp_type_4.smk:146-153): distinct canonical k-mers, ascending, with their occurrence
+    counts saturated at KMC's default -cs255.  Returns (keys, uint32 counts)."""
+    keys, _ = kmers(fasta, k)
+    if keys.shape[0] == 0:
+        return keys, np.empty(0, np.uint32)
+    if k <= 32:
+        u, c = np.unique(keys, return_counts=True)
+    else:
+        order = np.lexsort((keys[:, 0], keys[:, 1]))
+        srt = keys[order]
+        new = np.ones(srt.shape[0], dtype=bool)
+        new[1:] = np.any(srt[1:] != srt[:-1], axis=1)
+        u = srt[new]
+        starts = np.flatnonzero(new)
+        c = np.diff(np.append(starts, srt.shape[0]))
+    return u, np.minimum(c, cs).astype(np.uint32)
+
+
+def exp4(groups, pivots, k: int, cs: int = CS_DEFAULT):
+    """Experiment type 4's databases for one k (exp_type_4.smk:136-243): per pivot its counted k-mers, and for every
+    (pivot, dataset) the result of `kmc_tools simple union_d pivot_p intersect -ocsum`.
+    Returns (pivot_tables [(keys, counts)], intersections [[(keys, counts)] per pivot])."""
+    unions = []
+    for genomes in groups:
+        ukeys, _ = union_sum([genome_set(g, k) for g in genomes], k, cs)
+        unions.append(ukeys)
+    tables, inters = [], []
+    for p in pivots:
+        pk, pc = kmer_counts(p, k)
+        tables.append((pk, pc))
+        row = []
+        for ukeys in unions:
+            ones = np.ones(ukeys.shape[0], dtype=np.uint32)
+            row.append(simple_intersect_ocsum(ukeys, ones, pk, pc, k, cs))
+        inters.append(row)
+    return tables, inters
+
+
 def num_threads() -> int:
     return int(lib().ko_num_threads())
