@@ -484,7 +484,11 @@ int dispatch_passes<Key64>(khb_ctx *ctx, int v, Key64 *src, Key64 *dst, unsigned
                            const u64 *d_tile, int nseg, int npass, int first_bit, u64 ntiles, u64 n_keys, const u32 *d_hist,
                            u64 *d_lb, u32 *d_ticket)
 {
-    if (psrc) return launch_passes<Key64, 512, 12, 2, 2, 1>(KHB_PASS_ARGS);  // keys + 16-bit payload
+    if (psrc) {  // keys + 16-bit payload
+        if (v == 13) return launch_passes<Key64, 512, 12, 2, 4, 1>(KHB_PASS_ARGS);
+        if (v == 12) return launch_passes<Key64, 512, 12, 2, 3, 1>(KHB_PASS_ARGS);
+        return launch_passes<Key64, 512, 12, 2, 2, 1>(KHB_PASS_ARGS);
+    }
     switch (v) {
     case 0: return launch_passes<Key64, 512, 12, 2, 0>(KHB_PASS_ARGS);         // MATCH.ANY (1.46 TB/s: ~1 MATCH.ANY per 100 cycles per SM)
     case 1: return launch_passes<Key64, 512, 12, 2, 1>(KHB_PASS_ARGS);         // eight ballots (2.33 TB/s: ALU-bound, 3.9 warp-instr/key)

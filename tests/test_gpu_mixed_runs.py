@@ -13,6 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 SCRIPT = r"""
+import os
 import sys
 import numpy as np
 sys.path.insert(0, %(root)r)
@@ -25,7 +26,7 @@ pivots = [synth.make_genome(cfg, g, 4) for g in (1, 2)]
 # a k-mer that repeats many times inside one genome, so that long runs meet mixed prefixes
 groups[0][0] += b">rep\n" + b"ACGTTGCATTGACCAGTAGGATCCATGCAAGT" * 40 + b"\n"
 eng = Engine(0)
-for k in (15, 31, 47):
+for k in (7, 15, 31, 47):
     flat = [f for g in groups for f in g]
     w_ref, a_ref, st_ref = O.exp1(flat, [0, 0, 0, 1, 1, 1], 2, k, nbins=64)
     eng.group_sets_reset()
@@ -33,7 +34,8 @@ for k in (15, 31, 47):
     for d in range(2):
         hist, st = eng.group_from_fasta(groups[d], k, nbins=64)
         assert np.array_equal(hist, w_ref[d]), ("within", k, d)
-        assert st["passes_group"] <= 2, st
+        if int(os.environ["KHB_PREFIX_SLACK"]) < 0:
+            assert st["passes_group"] <= 2, st   # 0 on the direct-address path (small k)
         total += st["genome_distinct"]
     assert total == st_ref["sum_genome_distinct"], (total, st_ref)
     hist, st = eng.across_groups(nbins=64)
@@ -58,8 +60,10 @@ print("mixed ok")
 """
 
 
-@pytest.mark.parametrize("slack", ["-6", "-10", "-13"])
-def test_short_prefixes_give_the_same_answers(slack, oracle):
-    env = dict(os.environ, KHB_PREFIX_SLACK=slack)
+@pytest.mark.parametrize("slack,smallk_mb", [("-6", "1024"), ("-10", "1024"), ("-13", "0"), ("0", "0")])
+def test_short_prefixes_give_the_same_answers(slack, smallk_mb, oracle):
+    """smallk_mb = 0 switches the direct-address path for small k off, so k = 7 goes through the sort path too (runs of
+    thousands of equal keys)."""
+    env = dict(os.environ, KHB_PREFIX_SLACK=slack, KHB_SMALLK_TABLE_MB=smallk_mb)
     r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "mixed ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

@@ -124,3 +124,30 @@ def test_pack_once_sweep_k_equals_per_k_pipeline(engine):
         assert np.array_equal(a_ref, a_got), k
     for p in packed:
         p.free()
+
+
+@pytest.mark.parametrize("k", [4, 5, 6, 7, 8, 9, 10])
+def test_small_k_direct_address_path_and_its_switch_over(engine, oracle, k):
+    """k small enough for the presence table (4^k x ceil(N/32) words <= windows / 4) skips the sort (presence.cu); the
+    sweep crosses the switch-over, and both sides must give the oracle's histograms, set sizes and sets."""
+    from khoice_b200 import synth
+    cfg = synth.SynthConfig(n_groups=2, genomes_per_group=3, genome_len=200_000, seed=31)
+    groups = [[synth.make_genome(cfg, g, i) for i in range(1, 4)] for g in (1, 2)]
+    flat = [f for grp in groups for f in grp]
+    w_ref, a_ref, st_ref = oracle.exp1(flat, [0, 0, 0, 1, 1, 1], 2, k, nbins=32)
+    engine.group_sets_reset()
+    total = 0
+    used_table = []
+    for d, grp in enumerate(groups):
+        hist, st = engine.group_from_fasta(grp, k, nbins=32)
+        assert np.array_equal(hist, w_ref[d]), (k, d)
+        total += st["genome_distinct"]
+        used_table.append(st["passes_group"] == 0)
+    assert total == st_ref["sum_genome_distinct"]
+    assert all(used_table) == (k <= 8), (k, used_table)     # 600 k windows: 4^8 words x 4 <= windows < 4^9 words x 4
+    got = engine.group_sets_download()
+    ref = np.concatenate([oracle.union_sum([oracle.genome_set(g, k) for g in grp], k)[0] for grp in groups])
+    assert np.array_equal(np.sort(got), np.sort(ref))
+    hist, st = engine.across_groups(nbins=32)
+    assert np.array_equal(hist, a_ref) and st["distinct"] == st_ref["distinct"]
+    engine.group_sets_reset()
