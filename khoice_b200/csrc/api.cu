@@ -16,10 +16,11 @@ struct khb_hostvec {
     std::vector<size_t> d_sizes;
     bool deferred = false;
 };
-int khb_extract_kmers_impl(khb_ctx *, const u64 *, const u32 *, size_t, int, int, void *, unsigned short *, const u64 *, int);
+int khb_extract_kmers_impl(khb_ctx *, const u64 *, const u32 *, size_t, int, int, void *, unsigned short *, const u64 *, int, u32 *, int, int);
+int khb_sort_hist_buffer(khb_ctx *, int, u32 **);
 int khb_remix_impl(khb_ctx *, void *, size_t, int, int);
 int khb_sort_keys_impl(khb_ctx *, void *, void *, const u64 *, int, int, int *);
-int khb_sort_bits_impl(khb_ctx *, void *, void *, const u64 *, int, int, int, int, int *, unsigned short *, unsigned short *);
+int khb_sort_bits_impl(khb_ctx *, void *, void *, const u64 *, int, int, int, int, int *, unsigned short *, unsigned short *, int hist_ready = 0);
 int khb_resolve_unique_impl(khb_ctx *, const void *, size_t, int, int, void *, u64 *);
 int khb_resolve_count_impl(khb_ctx *, const void *, size_t, int, int, u32, u32, u64 *, void *, u64 *);
 int khb_pairs_count_impl(khb_ctx *, const void *, const unsigned short *, size_t, int, int, u32, u32, u32, u64 *, void *, u64 *, u64 *, int, void *, u64 *);
@@ -369,13 +370,13 @@ int khb_pack_fasta(khb_ctx *ctx, const uint8_t *d_fasta, size_t nbytes, uint64_t
 int khb_extract_kmers(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, size_t n_symbols, int k, void *d_keys)
 {
     KHB_CHECK_CTX(ctx);
-    return khb_extract_kmers_impl(ctx, (const u64 *)d_codes, d_valid, n_symbols, k, 0, d_keys, nullptr, nullptr, 0);
+    return khb_extract_kmers_impl(ctx, (const u64 *)d_codes, d_valid, n_symbols, k, 0, d_keys, nullptr, nullptr, 0, nullptr, 0, 0);
 }
 
 int khb_extract_kmers_hashed(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, size_t n_symbols, int k, void *d_keys)
 {
     KHB_CHECK_CTX(ctx);
-    return khb_extract_kmers_impl(ctx, (const u64 *)d_codes, d_valid, n_symbols, k, 1, d_keys, nullptr, nullptr, 0);
+    return khb_extract_kmers_impl(ctx, (const u64 *)d_codes, d_valid, n_symbols, k, 1, d_keys, nullptr, nullptr, 0, nullptr, 0, 0);
 }
 
 int khb_remix_keys(khb_ctx *ctx, void *d_keys, size_t n, int k, int inverse)
@@ -766,12 +767,20 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
             if ((rc = khb_presence_count_impl(ctx, d_codes, d_valid, n_sym, k, hashed, d_seg, n_genomes, (u32 *)p, KHB_COUNTER_MAX, nbins, d_hist, out_keys,
                                               d_runs, d_pairs, pivot, out_pivot, d_pruns))) return rc;
         } else {
-            if ((rc = khb_extract_kmers_impl(ctx, d_codes, d_valid, n_sym, k, hashed, bufA, payA, d_seg, n_genomes))) return rc;
-            tm.mark();  // 3: extract done
+            // K2 also counts the digits of the prefix passes while the keys are in registers (the sort skips its histogram sweep)
             khb_prefix_plan(k, n_sym, &fb, &np);
+            static int fuse_hist = -1;
+            if (fuse_hist < 0) {
+                const char *e = getenv("KHB_FUSE_HIST");
+                fuse_hist = e ? atoi(e) : 1;
+            }
+            u32 *d_dig = nullptr;
+            if (fuse_hist && (rc = khb_sort_hist_buffer(ctx, np, &d_dig))) return rc;
+            if ((rc = khb_extract_kmers_impl(ctx, d_codes, d_valid, n_sym, k, hashed, bufA, payA, d_seg, n_genomes, d_dig, np, fb))) return rc;
+            tm.mark();  // 3: extract done
             u64 one_seg[2] = {0, n_sym};
             int in_tmp = 0;
-            if ((rc = khb_sort_bits_impl(ctx, bufA, bufB, one_seg, 1, (int)W, fb, np, &in_tmp, payA, payB))) return rc;
+            if ((rc = khb_sort_bits_impl(ctx, bufA, bufB, one_seg, 1, (int)W, fb, np, &in_tmp, payA, payB, d_dig ? 1 : 0))) return rc;
             void *sorted = in_tmp ? bufB : bufA;
             unsigned short *spay = in_tmp ? payB : payA;
             tm.mark();  // 4: sort done
@@ -808,7 +817,7 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
         }
         return KHB_OK;
     }
-    if ((rc = khb_extract_kmers_impl(ctx, d_codes, d_valid, n_sym, k, hashed, bufA, nullptr, nullptr, 0))) return rc;
+    if ((rc = khb_extract_kmers_impl(ctx, d_codes, d_valid, n_sym, k, hashed, bufA, nullptr, nullptr, 0, nullptr, 0, 0))) return rc;
     tm.mark();  // 3: extract done
     // K3 per genome (segmented), prefix only
     const std::vector<u64> &seg = pk.seg;

@@ -34,8 +34,16 @@ __device__ __forceinline__ u32 segment_of(const u64 *__restrict__ seg_off, int n
 // k <= 32.  One thread produces the two windows starting at i and i+1 (i even) -> one 16-byte store.
 __global__ void __launch_bounds__(256)
 extract64_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, size_t n_sym, int k, int hashed,
-                 ulonglong2 *__restrict__ out, unsigned short *__restrict__ gids, const u64 *__restrict__ seg_off, int nseg)
+                 ulonglong2 *__restrict__ out, unsigned short *__restrict__ gids, const u64 *__restrict__ seg_off, int nseg,
+                 u32 *__restrict__ hist /* [hist_npass][256] digit counts of the emitted keys, or null */, int hist_npass, int hist_first_bit)
 {
+    // hist: the radix sort that follows needs the digit histogram of every pass; counting while the keys are still in
+    // registers saves the sort's own histogram sweep (one more read of all keys)
+    extern __shared__ u32 sh_hist[];  // [hist_npass][256]
+    if (hist != nullptr) {
+        for (int i = threadIdx.x; i < hist_npass * 256; i += blockDim.x) sh_hist[i] = 0;
+        __syncthreads();
+    }
     const size_t npairs = (n_sym + 1) >> 1;
     const u64 ones_k = k == 64 ? ~0ull : ((1ull << k) - 1ull);
     const int rs = 64 - 2 * k;  // right shift that brings the 2k window bits to the low end
@@ -70,6 +78,13 @@ extract64_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, s
         } else {
             ((u64 *)out)[i] = res[0];
         }
+        if (hist != nullptr) {
+            for (int p = 0; p < hist_npass; p++) {
+                const int sh = hist_first_bit + 8 * p;
+                atomicAdd(&sh_hist[p * 256 + ((u32)(res[0] >> sh) & 0xffu)], 1u);
+                if (i + 1 < n_sym) atomicAdd(&sh_hist[p * 256 + ((u32)(res[1] >> sh) & 0xffu)], 1u);
+            }
+        }
         if (gids != nullptr) {
             if (i < seg_lo || i >= seg_hi) {
                 seg_g = segment_of(seg_off, nseg, i);
@@ -82,13 +97,26 @@ extract64_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, s
             else gids[i] = (unsigned short)g0;
         }
     }
+    if (hist != nullptr) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < hist_npass * 256; i += blockDim.x) {
+            const u32 c = sh_hist[i];
+            if (c) atomicAdd(&hist[i], c);
+        }
+    }
 }
 
 // 33 <= k <= 64.  One thread per window -> one 16-byte store (lo, hi).
 __global__ void __launch_bounds__(256)
 extract128_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, size_t n_sym, int k, int hashed,
-                  ulonglong2 *__restrict__ out, unsigned short *__restrict__ gids, const u64 *__restrict__ seg_off, int nseg)
+                  ulonglong2 *__restrict__ out, unsigned short *__restrict__ gids, const u64 *__restrict__ seg_off, int nseg,
+                  u32 *__restrict__ hist, int hist_npass, int hist_first_bit)
 {
+    extern __shared__ u32 sh_hist[];  // [hist_npass][256], see extract64_kernel
+    if (hist != nullptr) {
+        for (int i = threadIdx.x; i < hist_npass * 256; i += blockDim.x) sh_hist[i] = 0;
+        __syncthreads();
+    }
     const u64 ones_k = k == 64 ? ~0ull : ((1ull << k) - 1ull);
     const int rs = 128 - 2 * k;  // 0..62
     const size_t per = ((n_sym + gridDim.x - 1) / gridDim.x + blockDim.x - 1) / blockDim.x * blockDim.x;
@@ -130,6 +158,10 @@ extract128_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, 
         r.x = ok ? cl : ~0ull;   // lo
         r.y = ok ? ch : ~0ull;   // hi
         out[i] = r;
+        if (hist != nullptr) {
+            const Key128 kk{r.x, r.y};
+            for (int p = 0; p < hist_npass; p++) atomicAdd(&sh_hist[p * 256 + key_digit(kk, hist_first_bit + 8 * p)], 1u);
+        }
         if (gids != nullptr) {
             if (i < seg_lo || i >= seg_hi) {
                 seg_g = segment_of(seg_off, nseg, i);
@@ -137,6 +169,13 @@ extract128_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, 
                 seg_hi = __ldg(seg_off + seg_g + 1);
             }
             gids[i] = (unsigned short)seg_g;
+        }
+    }
+    if (hist != nullptr) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < hist_npass * 256; i += blockDim.x) {
+            const u32 c = sh_hist[i];
+            if (c) atomicAdd(&hist[i], c);
         }
     }
 }
@@ -176,19 +215,23 @@ int khb_remix_impl(khb_ctx *ctx, void *d_keys, size_t n, int k, int inverse)
 
 // d_gids / d_seg_off (optional): also write, per window, the index of the segment (genome) it belongs to.
 int khb_extract_kmers_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, size_t n_sym, int k, int hashed, void *d_keys,
-                           unsigned short *d_gids, const u64 *d_seg_off, int nseg)
+                           unsigned short *d_gids, const u64 *d_seg_off, int nseg, u32 *d_hist, int hist_npass, int hist_first_bit)
 {
+    // d_hist (optional, zeroed by the caller): [hist_npass][256] digit counts of the keys written, for the sort that follows
     if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_extract_kmers: k=%d outside 1..64", k);
     if (n_sym == 0) return KHB_OK;
     const size_t work = k <= 32 ? (n_sym + 1) / 2 : n_sym;
     size_t blocks = div_up(work, 256);
     const size_t cap = (size_t)ctx->num_sms * 32;
     if (blocks > cap) blocks = cap;
+    const size_t shm = d_hist ? (size_t)hist_npass * 256 * sizeof(u32) : 0;  // at most 16 passes: 16 KiB
     khb_prof_begin(ctx, KHB_K_EXTRACT);
     if (k <= 32)
-        extract64_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_codes, d_valid, n_sym, k, hashed, (ulonglong2 *)d_keys, d_gids, d_seg_off, nseg);
+        extract64_kernel<<<(unsigned)blocks, 256, shm, ctx->stream>>>(d_codes, d_valid, n_sym, k, hashed, (ulonglong2 *)d_keys, d_gids, d_seg_off, nseg,
+                                                                      d_hist, hist_npass, hist_first_bit);
     else
-        extract128_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_codes, d_valid, n_sym, k, hashed, (ulonglong2 *)d_keys, d_gids, d_seg_off, nseg);
+        extract128_kernel<<<(unsigned)blocks, 256, shm, ctx->stream>>>(d_codes, d_valid, n_sym, k, hashed, (ulonglong2 *)d_keys, d_gids, d_seg_off, nseg,
+                                                                       d_hist, hist_npass, hist_first_bit);
     KHB_LAUNCH_CHECK(ctx);
     khb_prof_end(ctx, KHB_K_EXTRACT, (u64)n_sym / 4 + n_sym / 8 + (u64)n_sym * ((k <= 32 ? 8 : 16) + (d_gids ? 2 : 0)));
     return KHB_OK;

@@ -511,8 +511,10 @@ int dispatch_passes<Key128>(khb_ctx *ctx, int v, Key128 *src, Key128 *dst, unsig
 
 template <typename Key>
 static int sort_impl(khb_ctx *ctx, Key *d_keys, Key *d_tmp, unsigned short *d_pay, unsigned short *d_pay_tmp, const u64 *h_seg_off,
-                     int nseg, int first_bit, int npass, int *result_in_tmp)
+                     int nseg, int first_bit, int npass, int *result_in_tmp, int hist_ready)
 {
+    // hist_ready: the SCR_HIST scratch already holds the raw digit counts [1][npass][256] of the single segment (K2 counted
+    // them while it produced the keys, khb_sort_hist_buffer), so the histogram sweep over the keys is skipped
     const int v = sort_variant();
     const u32 TILE = variant_tile(v, sizeof(Key));
     *result_in_tmp = 0;
@@ -550,7 +552,8 @@ static int sort_impl(khb_ctx *ctx, Key *d_keys, Key *d_tmp, unsigned short *d_pa
     rc = khb_scratch_get(ctx, SCR_HIST, hist_bytes, &p);
     if (rc) return rc;
     u32 *d_hist = (u32 *)p;
-    KHB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, hist_bytes, ctx->stream));
+    if (hist_ready && nseg != 1) return khb_fail(ctx, KHB_ERR_ARG, "sort: precomputed histograms need a single segment");
+    if (!hist_ready) KHB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, hist_bytes, ctx->stream));
     const size_t lb_bytes = (size_t)ntiles * 256 * sizeof(u64);
     rc = khb_scratch_get(ctx, SCR_LOOKBACK, lb_bytes, &p);
     if (rc) return rc;
@@ -562,12 +565,14 @@ static int sort_impl(khb_ctx *ctx, Key *d_keys, Key *d_tmp, unsigned short *d_pa
         if (grid > ntiles) grid = ntiles;
         const size_t shm = (size_t)npass * 256 * sizeof(u32);
         khb_prof_begin(ctx, KHB_K_RADIX_HIST);
-        radix_hist_kernel<Key><<<(unsigned)grid, RS_BLOCK, shm, ctx->stream>>>(d_keys, d_off, d_tile, nseg, ntiles, npass, first_bit, d_hist, TILE);
-        KHB_LAUNCH_CHECK(ctx);
+        if (!hist_ready) {
+            radix_hist_kernel<Key><<<(unsigned)grid, RS_BLOCK, shm, ctx->stream>>>(d_keys, d_off, d_tile, nseg, ntiles, npass, first_bit, d_hist, TILE);
+            KHB_LAUNCH_CHECK(ctx);
+        }
         const int nhist = nseg * npass;
         radix_scan_kernel<<<(unsigned)div_up(nhist, 8), 256, 0, ctx->stream>>>(d_hist, nhist);
         KHB_LAUNCH_CHECK(ctx);
-        khb_prof_end(ctx, KHB_K_RADIX_HIST, n_keys * sizeof(Key));
+        khb_prof_end(ctx, KHB_K_RADIX_HIST, hist_ready ? 0 : n_keys * sizeof(Key));
     }
     rc = dispatch_passes<Key>(ctx, v, d_keys, d_tmp, d_pay, d_pay_tmp, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket);
     if (rc) return rc;
@@ -577,8 +582,20 @@ static int sort_impl(khb_ctx *ctx, Key *d_keys, Key *d_tmp, unsigned short *d_pa
 
 // Sort every segment by the `npass` 8-bit digits starting at bit `first_bit` (stable LSD).  d_pay / d_pay_tmp
 // (optional, both or none): a 16-bit payload per key that travels with it (ping-pong like the keys).
+// Zeroed [npass][256] digit-count buffer that a key producer may fill before khb_sort_bits_impl(..., hist_ready = 1).
+int khb_sort_hist_buffer(khb_ctx *ctx, int npass, u32 **d_hist)
+{
+    void *p;
+    const size_t bytes = (size_t)npass * 256 * sizeof(u32);
+    int rc = khb_scratch_get(ctx, SCR_HIST, bytes, &p);
+    if (rc) return rc;
+    KHB_CUDA(ctx, cudaMemsetAsync(p, 0, bytes, ctx->stream));
+    *d_hist = (u32 *)p;
+    return KHB_OK;
+}
+
 int khb_sort_bits_impl(khb_ctx *ctx, void *d_keys, void *d_tmp, const u64 *h_seg_off, int nseg, int key_bytes, int first_bit, int npass,
-                       int *result_in_tmp, unsigned short *d_pay, unsigned short *d_pay_tmp)
+                       int *result_in_tmp, unsigned short *d_pay, unsigned short *d_pay_tmp, int hist_ready)
 {
     if (key_bytes != 8 && key_bytes != 16) return khb_fail(ctx, KHB_ERR_ARG, "sort: key_bytes=%d", key_bytes);
     if (npass < 0 || npass > 16 || first_bit < 0 || first_bit + 8 * npass > 8 * key_bytes + 7)
@@ -586,13 +603,13 @@ int khb_sort_bits_impl(khb_ctx *ctx, void *d_keys, void *d_tmp, const u64 *h_seg
     if ((d_pay == nullptr) != (d_pay_tmp == nullptr)) return khb_fail(ctx, KHB_ERR_ARG, "sort: payload needs both buffers");
     *result_in_tmp = 0;
     if (npass == 0) return KHB_OK;
-    return key_bytes == 8 ? sort_impl<Key64>(ctx, (Key64 *)d_keys, (Key64 *)d_tmp, d_pay, d_pay_tmp, h_seg_off, nseg, first_bit, npass, result_in_tmp)
-                          : sort_impl<Key128>(ctx, (Key128 *)d_keys, (Key128 *)d_tmp, d_pay, d_pay_tmp, h_seg_off, nseg, first_bit, npass, result_in_tmp);
+    return key_bytes == 8 ? sort_impl<Key64>(ctx, (Key64 *)d_keys, (Key64 *)d_tmp, d_pay, d_pay_tmp, h_seg_off, nseg, first_bit, npass, result_in_tmp, hist_ready)
+                          : sort_impl<Key128>(ctx, (Key128 *)d_keys, (Key128 *)d_tmp, d_pay, d_pay_tmp, h_seg_off, nseg, first_bit, npass, result_in_tmp, hist_ready);
 }
 
 // Full sort of k-mer words: all ceil(2k/8) digits.
 int khb_sort_keys_impl(khb_ctx *ctx, void *d_keys, void *d_tmp, const u64 *h_seg_off, int nseg, int k, int *result_in_tmp)
 {
     if (k < 1 || k > 64) return khb_fail(ctx, KHB_ERR_ARG, "khb_sort_keys: k=%d outside 1..64", k);
-    return khb_sort_bits_impl(ctx, d_keys, d_tmp, h_seg_off, nseg, k <= 32 ? 8 : 16, 0, (2 * k + 7) / 8, result_in_tmp, nullptr, nullptr);
+    return khb_sort_bits_impl(ctx, d_keys, d_tmp, h_seg_off, nseg, k <= 32 ? 8 : 16, 0, (2 * k + 7) / 8, result_in_tmp, nullptr, nullptr, 0);
 }
