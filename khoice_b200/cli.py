@@ -26,7 +26,6 @@ why the fused mode (khoice_b200/pipeline.py) is the fast path.
 """
 from __future__ import annotations
 
-import gzip
 import os
 import re
 import sys
@@ -34,7 +33,7 @@ from typing import List, Optional
 
 import numpy as np
 
-from . import kmcdb
+from . import ingest, kmcdb
 from .engine import COUNTER_MAX, Engine
 from .tables import HIST_ROWS, write_histogram_file
 
@@ -58,11 +57,7 @@ def set_engine(eng: Optional[Engine]) -> None:
 
 def read_fasta(path: str) -> bytes:
     """FASTA text of a .fna.gz (multi-member gzip handled, rule R9) or plain file."""
-    if path.endswith(".gz"):
-        with gzip.open(path, "rb") as fd:
-            return fd.read()
-    with open(path, "rb") as fd:
-        return fd.read()
+    return ingest.read_fasta(path)
 
 
 class UsageError(Exception):
@@ -262,7 +257,7 @@ def fused_group(k: int, genome_paths: List[str], hist_out: str, set_prefix: str,
     """Rules build_kmc_database_on_genome .. within_group_union_histogram + build_group_kmer_set for one (k, group)
     in ONE process: step_4 histogram + the group's k-mer set (step_6 database, real; step_3 header-only)."""
     eng = get_engine()
-    texts = [read_fasta(p) for p in genome_paths]
+    texts = ingest.read_many(genome_paths)
     eng.group_sets_reset()
     hist, st = eng.group_from_fasta(texts, k, nbins=HIST_ROWS, keep_set=True)
     keys = eng.group_sets_download()

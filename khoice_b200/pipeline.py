@@ -29,7 +29,7 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-from . import cli, kmcdb, tables
+from . import cli, ingest, kmcdb, tables
 from .engine import COUNTER_MAX, Engine
 
 # /root/reference/workflow/Snakefile:36 -- a Python literal there; a config key (K_VALUES) here.
@@ -109,12 +109,14 @@ def run_fused(work_root: str, num_datasets: int, k_values: Optional[Sequence] = 
         write_complex_ops(work_root, k_values, num_datasets)
         names = {n: genomes_of(work_root, n) for n in range(1, num_datasets + 1)}
         zero = np.zeros(tables.HIST_ROWS + 1, dtype=np.uint64)
+        # parallel inflate, one group ahead of the GPU (khoice_b200/ingest.py)
+        reader = ingest.GroupReader({n: [os.path.join(work_root, p_genome(n, g)) for g in names[n]] for n in names}, sorted(names))
         for k in k_values:
             ki = int(k)
             eng.group_sets_reset()
             for num in range(1, num_datasets + 1):
                 if num not in packed:  # inflate + pack ONCE; the 2-bit stream (3/8 byte per base) stays in HBM for the k sweep
-                    texts = [cli.read_fasta(os.path.join(work_root, p_genome(num, g))) for g in names[num]]
+                    texts = reader.get(num)
                     packed[num] = eng.pack_group(texts)
                     del texts
                 hist, st = eng.group_from_packed(packed[num], ki, nbins=tables.HIST_ROWS, keep_set=True)
@@ -135,6 +137,8 @@ def run_fused(work_root: str, num_datasets: int, k_values: Optional[Sequence] = 
             report["stages"].append({"k": ki, "group": "across", **st})
         build_tables(work_root, k_values, num_datasets)
     finally:
+        if "reader" in locals():
+            reader.close()
         for pk in packed.values():
             pk.free()
         if own:

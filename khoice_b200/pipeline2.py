@@ -32,7 +32,7 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-from . import cli, kmcdb, tables
+from . import cli, ingest, kmcdb, tables
 from .engine import COUNTER_MAX, Engine
 from .pipeline import BIN_DIR, DEFAULT_K_VALUES
 
@@ -149,13 +149,15 @@ def run_fused(work_root: str, num_datasets: int, k_values: Optional[Sequence] = 
     try:
         write_complex_ops(work_root, k_values, num_datasets)
         names = {n: rest_genomes_of(work_root, n) for n in range(1, num_datasets + 1)}
+        # parallel inflate, one dataset ahead of the GPU; rest-of-set genomes first, the pivot LAST
+        reader = ingest.GroupReader({n: [os.path.join(work_root, p_rest(n, g)) for g in names[n]] + [os.path.join(work_root, p_pivot(n))]
+                                     for n in names}, sorted(names))
         for k in k_values:
             ki = int(k)
             eng.group_sets_reset()
             for num in range(1, num_datasets + 1):
-                if num not in packed:  # inflate + pack once per dataset: rest-of-set genomes, then the pivot LAST
-                    texts = [cli.read_fasta(os.path.join(work_root, p_rest(num, g))) for g in names[num]]
-                    texts.append(cli.read_fasta(os.path.join(work_root, p_pivot(num))))
+                if num not in packed:  # inflate + pack once per dataset
+                    texts = reader.get(num)
                     packed[num] = eng.pack_group(texts)
                     del texts
                 hist, st = eng.pivot_group_from_packed(packed[num], ki, nbins=tables.HIST_ROWS, keep_sets=True)
@@ -179,6 +181,8 @@ def run_fused(work_root: str, num_datasets: int, k_values: Optional[Sequence] = 
             report["stages"].append({"k": ki, "dataset": "across", **st})
         build_tables(work_root, k_values, num_datasets)
     finally:
+        if "reader" in locals():
+            reader.close()
         for pk in packed.values():
             pk.free()
         if own:

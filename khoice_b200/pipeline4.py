@@ -29,7 +29,7 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-from . import cli, merge_lists, tables
+from . import cli, ingest, merge_lists, tables
 from .engine import Engine
 from .pipeline import DEFAULT_K_VALUES
 
@@ -122,13 +122,14 @@ def run_fused(work_root: str, num_datasets: int, k_values: Optional[Sequence] = 
     try:
         write_parse_time_files(work_root, k_values, num_datasets)
         names = {n: rest_genomes_of(work_root, n) for n in range(1, num_datasets + 1)}
+        reader = ingest.GroupReader({n: [os.path.join(work_root, p_rest(n, g)) for g in names[n]] for n in names}, sorted(names))
         for k in k_values:
             ki = int(k)
             eng.group_sets_reset()
             group_off = [0]
             for num in range(1, num_datasets + 1):
                 if num not in packed:
-                    packed[num] = eng.pack_group([cli.read_fasta(os.path.join(work_root, p_rest(num, g))) for g in names[num]])
+                    packed[num] = eng.pack_group(reader.get(num))
                 hist, st = eng.group_from_packed(packed[num], ki, nbins=tables.HIST_ROWS, keep_set=True)
                 tables.write_histogram_file(os.path.join(work_root, p_union_hist(k, num)), hist)   # rule union_histogram_exp_type_4
                 group_off.append(eng.group_sets_info()["n_keys"])
@@ -137,7 +138,7 @@ def run_fused(work_root: str, num_datasets: int, k_values: Optional[Sequence] = 
             try:
                 for piv in range(1, num_datasets + 1):
                     if piv not in pivot_text:
-                        pivot_text[piv] = cli.read_fasta(os.path.join(work_root, p_pivot(piv)))
+                        pivot_text[piv] = ingest.read_fasta(os.path.join(work_root, p_pivot(piv)))
                     buf, cnt, n = eng.kmer_counts(pivot_text[piv], ki, cs=cli.KMC_DEFAULT_CS)
                     bufs.append(buf); counts.append(cnt); sizes.append(n)
                 masks = eng.group_membership(group_off, bufs, sizes, ki)
@@ -153,6 +154,8 @@ def run_fused(work_root: str, num_datasets: int, k_values: Optional[Sequence] = 
             report["stages"].append({"k": ki, "dataset": "pivots", "pivot_kmers": int(sum(sizes))})
         concatenate_accuracies(work_root)
     finally:
+        if "reader" in locals():
+            reader.close()
         for pk in packed.values():
             pk.free()
         if own:
