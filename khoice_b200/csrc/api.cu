@@ -28,6 +28,9 @@ int khb_fill_segment_ids_impl(khb_ctx *, unsigned short *, const u64 *, int, u64
 size_t khb_presence_table_bytes(int, int);
 int khb_presence_count_impl(khb_ctx *, const u64 *, const u32 *, size_t, int, int, const u64 *, int, u32 *, u32, u32, u64 *, void *, u64 *, u64 *, int,
                             void *, u64 *);
+size_t khb_hash_table_bytes(int, int, u64, int *, int *);
+int khb_hash_count_impl(khb_ctx *, const u64 *, const u32 *, u64, int, const u64 *, const u64 *, int, u32 *, int, int, u32, u32, u64 *, void *, u64 *, u64 *, int,
+                        void *, u64 *, u32 *);
 int khb_pivot_across_impl(khb_ctx *, const void *, const unsigned short *, size_t, int, int, u32, u32, u32, u64 *);
 int khb_sorted_lookup_impl(khb_ctx *, const void *, u64, const void *, u64, int, u64 *);
 int khb_membership_impl(khb_ctx *, const void *, const unsigned short *, size_t, int, int, u32, int, const void *, const u64 *, int, u64 *);
@@ -165,6 +168,11 @@ int khb_init(int device, khb_ctx **out)
     if (!ctx) return khb_fail(nullptr, KHB_ERR_NOMEM, "host allocation failed");
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
+    {
+        const char *gm = getenv("KHB_GROUP_MODE");
+        ctx->group_mode = !gm ? KHB_GROUP_AUTO : strcmp(gm, "two-sort") == 0 ? KHB_GROUP_TWO_SORT : strcmp(gm, "single-sort") == 0 ? KHB_GROUP_SINGLE_SORT
+                          : strcmp(gm, "hash") == 0 ? KHB_GROUP_HASH : KHB_GROUP_AUTO;
+    }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
         (e = cudaMallocHost((void **)&ctx->h_mail, 1 << 20)) != cudaSuccess ||
@@ -185,6 +193,7 @@ int khb_destroy(khb_ctx *ctx)
     for (int i = 0; i < KHB_NSCRATCH; i++)
         if (ctx->scratch[i].ptr) cudaFree(ctx->scratch[i].ptr);
     if (ctx->gs_buf) cudaFree(ctx->gs_buf);
+    if (ctx->hs_tab) cudaFree(ctx->hs_tab);
     if (ctx->stage_dev) cudaFree(ctx->stage_dev);
     if (ctx->stage_next) cudaFree(ctx->stage_next);
     if (ctx->pf_tab) cudaFree(ctx->pf_tab);
@@ -692,6 +701,33 @@ static int pack_stage(khb_ctx *ctx, int n_genomes, const uint8_t *d_fasta, const
 // K2 .. K5 for one k on a packed group.
 static int pv_reserve(khb_ctx *ctx, int k, u64 extra);
 
+// The context's hash table for the sort-free group stage: at least `bytes`, all zero.
+static int hash_table_get(khb_ctx *ctx, size_t bytes, u32 **out)
+{
+    if (ctx->hs_bytes < bytes) {
+        if (ctx->hs_tab) {
+            KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            KHB_CUDA(ctx, cudaFree(ctx->hs_tab));
+            ctx->hs_tab = nullptr;
+            ctx->hs_bytes = 0;
+        }
+        cudaError_t e = cudaMalloc((void **)&ctx->hs_tab, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            ctx->hs_tab = nullptr;
+            return khb_fail(ctx, KHB_ERR_NOMEM, "device allocation of %zu bytes failed (group hash table)", bytes);
+        }
+        ctx->hs_bytes = bytes;
+        ctx->hs_dirty = 1;
+    }
+    if (ctx->hs_dirty) {
+        KHB_CUDA(ctx, cudaMemsetAsync(ctx->hs_tab, 0, ctx->hs_bytes, ctx->stream));
+        ctx->hs_dirty = 0;
+    }
+    *out = ctx->hs_tab;
+    return KHB_OK;
+}
+
 // pivot != 0: experiment type 2 -- the last genome of the group is the pivot (khb_pivot_group_from_packed).
 static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64 *h_hist, int keep_set, khb_stats *stats, PhaseTimer &tm,
                        int pivot = 0)
@@ -712,22 +748,11 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
     const int hashed = (k != 32 && k != 64) ? 1 : 0;
     if (ctx->gs_k && keep_set && ctx->gs_hashed != hashed) return khb_fail(ctx, KHB_ERR_STATE, "retained group sets use a different key encoding");
     const size_t key_bytes = (n_sym + 4) * W;
-    if ((rc = khb_scratch_get(ctx, SCR_KEYS_A, key_bytes, &p))) return rc;
-    void *bufA = p;
-    if ((rc = khb_scratch_get(ctx, SCR_KEYS_B, key_bytes, &p))) return rc;
-    void *bufB = p;
-    static int single_sort = -1;
-    if (single_sort < 0) {
-        const char *e = getenv("KHB_GROUP_MODE");
-        single_sort = (e && strcmp(e, "two-sort") == 0) ? 0 : 1;
-    }
+    void *bufA = nullptr, *bufB = nullptr;  // sort buffers, taken only by the branches that sort
+    const int single_sort = ctx->group_mode != KHB_GROUP_TWO_SORT;
     if (pivot && !(single_sort && n_genomes <= 65535)) return khb_fail(ctx, KHB_ERR_STATE, "pivot analysis needs the single-sort group path");
     if (single_sort && n_genomes <= 65535) {
         // ---- single-sort path: ONE prefix sort of all windows of the group with the genome id as payload ----
-        if ((rc = khb_scratch_get(ctx, SCR_PAY_A, (n_sym + 8) * 2, &p))) return rc;
-        unsigned short *payA = (unsigned short *)p;
-        if ((rc = khb_scratch_get(ctx, SCR_PAY_B, (n_sym + 8) * 2, &p))) return rc;
-        unsigned short *payB = (unsigned short *)p;
         const std::vector<u64> &seg = pk.seg;
         u64 *d_seg = ctx->d_mail + 32768;  // up to 65536 offsets fit the 1 MiB mailbox behind the histogram area
         if ((size_t)(n_genomes + 1) > 65536) return khb_fail(ctx, KHB_ERR_ARG, "too many genomes in one group");
@@ -758,7 +783,26 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
             if ((rc = pv_reserve(ctx, k, seg[n_genomes] - seg[n_genomes - 1]))) return rc;
             out_pivot = (char *)ctx->pv->buf + ctx->pv->len * W;
         }
-        if (small_k) {
+        // group stage without a sort (hashset.cu): K2 fused with an open-addressing table, one record per distinct k-mer
+        int hs_R = 0, hs_L = 0;
+        const size_t hs_bytes = (!small_k && hashed && ctx->group_mode == KHB_GROUP_HASH) ? khb_hash_table_bytes(k, n_genomes, n_sym, &hs_R, &hs_L) : 0;
+        static long long hash_budget = -1;
+        if (hash_budget < 0) {
+            const char *e = getenv("KHB_HASH_TABLE_MB");  // 0 disables the path
+            hash_budget = (e ? atoll(e) : 98304) << 20;
+        }
+        bool use_hash = hs_bytes > 0 && (long long)hs_bytes <= hash_budget;
+      again:
+        if (use_hash) {
+            u32 *tab = nullptr;
+            if ((rc = hash_table_get(ctx, hs_bytes, &tab))) return rc;
+            tm.mark();  // 3
+            tm.mark();  // 4
+            tm.mark();  // 5
+            tm.mark();  // 6
+            if ((rc = khb_hash_count_impl(ctx, d_codes, d_valid, n_sym, k, d_seg, seg.data(), n_genomes, tab, hs_R, hs_L, KHB_COUNTER_MAX, nbins, d_hist,
+                                          out_keys, d_runs, d_pairs, pivot, out_pivot, d_pruns, (u32 *)(ctx->d_mail + 3)))) return rc;
+        } else if (small_k) {
             if ((rc = khb_scratch_get(ctx, SCR_AUX, table_bytes + 64, &p))) return rc;
             tm.mark();  // 3
             tm.mark();  // 4
@@ -767,6 +811,12 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
             if ((rc = khb_presence_count_impl(ctx, d_codes, d_valid, n_sym, k, hashed, d_seg, n_genomes, (u32 *)p, KHB_COUNTER_MAX, nbins, d_hist, out_keys,
                                               d_runs, d_pairs, pivot, out_pivot, d_pruns))) return rc;
         } else {
+            if ((rc = khb_scratch_get(ctx, SCR_KEYS_A, key_bytes, &bufA))) return rc;
+            if ((rc = khb_scratch_get(ctx, SCR_KEYS_B, key_bytes, &bufB))) return rc;
+            if ((rc = khb_scratch_get(ctx, SCR_PAY_A, (n_sym + 8) * 2, &p))) return rc;
+            unsigned short *payA = (unsigned short *)p;
+            if ((rc = khb_scratch_get(ctx, SCR_PAY_B, (n_sym + 8) * 2, &p))) return rc;
+            unsigned short *payB = (unsigned short *)p;
             // K2 also counts the digits of the prefix passes while the keys are in registers (the sort skips its histogram sweep)
             khb_prefix_plan(k, n_sym, &fb, &np);
             static int fuse_hist = -1;
@@ -792,6 +842,14 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
         KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, ctx->d_mail, (nbins + 9) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
         tm.mark();  // 7: count done
         KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (use_hash && ctx->h_mail[3]) {
+            // a probe sequence hit the limit (table nearly full of distinct k-mers): redo this group by sorting
+            ctx->hs_dirty = 1;
+            ctx->hs_overflows++;
+            use_hash = false;
+            tm.n = 3;
+            goto again;
+        }
         memcpy(h_hist, ctx->h_mail + 8, ((size_t)nbins + 1) * sizeof(u64));
         const u64 d_g = ctx->h_mail[0];
         if (keep_set) {
@@ -817,6 +875,8 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
         }
         return KHB_OK;
     }
+    if ((rc = khb_scratch_get(ctx, SCR_KEYS_A, key_bytes, &bufA))) return rc;
+    if ((rc = khb_scratch_get(ctx, SCR_KEYS_B, key_bytes, &bufB))) return rc;
     if ((rc = khb_extract_kmers_impl(ctx, d_codes, d_valid, n_sym, k, hashed, bufA, nullptr, nullptr, 0, nullptr, 0, 0))) return rc;
     tm.mark();  // 3: extract done
     // K3 per genome (segmented), prefix only
@@ -1111,6 +1171,16 @@ int khb_group_from_packed(khb_ctx *ctx, int k, const khb_packed *pk, uint32_t nb
     if (rc == KHB_OK) fill_times(stats, tm);
     return rc;
 }
+
+int khb_set_group_mode(khb_ctx *ctx, int mode)
+{
+    KHB_CHECK_CTX(ctx);
+    if (mode < KHB_GROUP_AUTO || mode > KHB_GROUP_HASH) return khb_fail(ctx, KHB_ERR_ARG, "khb_set_group_mode: mode %d", mode);
+    ctx->group_mode = mode;
+    return KHB_OK;
+}
+
+uint64_t khb_hash_overflows(const khb_ctx *ctx) { return ctx ? ctx->hs_overflows : 0; }
 
 int khb_across_groups(khb_ctx *ctx, uint32_t nbins, uint64_t *h_hist, khb_stats *stats)
 {

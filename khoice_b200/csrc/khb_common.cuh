@@ -191,10 +191,16 @@ struct khb_ctx {
     int prof_on;
     // experiment type 2: retained pivot sets (api.cu)
     struct khb_pivot_store *pv;
+    // hash group stage (hashset.cu): the table is all zero between calls unless hs_dirty
+    u32 *hs_tab;
+    size_t hs_bytes;
+    int hs_dirty;
+    u64 hs_overflows;  // groups that fell back to the sort path because a probe sequence hit the limit
+    int group_mode;    // KHB_GROUP_* (khb_set_group_mode; initial value from the environment variable KHB_GROUP_MODE)
 };
 
 // kernel ids for khb_profile_read
-enum { KHB_K_PACK = 0, KHB_K_EXTRACT = 1, KHB_K_RADIX_HIST = 2, KHB_K_ONESWEEP = 3, KHB_K_UNIQUE = 4, KHB_K_RLE = 5, KHB_K_PARTITION = 6, KHB_K_COUNT = 7 };
+enum { KHB_K_PACK = 0, KHB_K_EXTRACT = 1, KHB_K_RADIX_HIST = 2, KHB_K_ONESWEEP = 3, KHB_K_UNIQUE = 4, KHB_K_RLE = 5, KHB_K_PARTITION = 6, KHB_K_HASH_INSERT = 7, KHB_K_HASH_COUNT = 8, KHB_K_COUNT = 9 };
 void khb_prof_begin(khb_ctx *ctx, int id);
 void khb_prof_end(khb_ctx *ctx, int id, u64 alg_bytes);
 

@@ -101,6 +101,8 @@ _SIGNATURES = [
     ("khb_sorted_lookup", C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.c_int, _P]),
     ("khb_group_membership", C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int]),
     ("khb_partition_by_hash", C.c_int, [_P, _P, C.c_uint64, C.c_int, C.c_int, _P, _P]),
+    ("khb_set_group_mode", C.c_int, [_P, C.c_int]),
+    ("khb_hash_overflows", C.c_uint64, [_P]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
 
@@ -255,7 +257,18 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.khb_launch_count(self.ctx))
 
-    KERNELS = {"pack": 0, "extract": 1, "radix_hist": 2, "onesweep": 3, "unique": 4, "rle_hist": 5, "partition": 6}
+    KERNELS = {"pack": 0, "extract": 1, "radix_hist": 2, "onesweep": 3, "unique": 4, "rle_hist": 5, "partition": 6,
+               "hash_insert": 7, "hash_count": 8}
+
+    GROUP_MODES = {"auto": 0, "single-sort": 1, "two-sort": 2, "hash": 3}
+
+    def set_group_mode(self, mode: str):
+        """How the group stage finds shared k-mers (include/khoice_b200.h: KHB_GROUP_*); results do not depend on it."""
+        self._chk(self.lib.khb_set_group_mode(self.ctx, self.GROUP_MODES[mode]))
+
+    @property
+    def hash_overflows(self) -> int:
+        return int(self.lib.khb_hash_overflows(self.ctx))
 
     def profile_enable(self, on: bool = True):
         """Bracket every kernel launch with CUDA events (clears earlier records)."""

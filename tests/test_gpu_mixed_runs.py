@@ -1,7 +1,7 @@
 """The mixed-prefix-run machinery of the single-sort path (pairs_kernel bitmap -> mixed_collect_kernel ->
 mixed_runs_kernel, including its quadratic overflow fallback) under prefixes that are far too short: KHB_PREFIX_SLACK
 removes prefix bits, so that most prefix runs hold several (or hundreds of) distinct keys.  The variable is read once
-per process, hence the sub-process."""
+per process, hence the sub-process.  KHB_GROUP_MODE=single-sort keeps the default hash path (hashset.cu) out of the way."""
 import os
 import subprocess
 import sys
@@ -64,6 +64,6 @@ print("mixed ok")
 def test_short_prefixes_give_the_same_answers(slack, smallk_mb, oracle):
     """smallk_mb = 0 switches the direct-address path for small k off, so k = 7 goes through the sort path too (runs of
     thousands of equal keys)."""
-    env = dict(os.environ, KHB_PREFIX_SLACK=slack, KHB_SMALLK_TABLE_MB=smallk_mb)
+    env = dict(os.environ, KHB_PREFIX_SLACK=slack, KHB_SMALLK_TABLE_MB=smallk_mb, KHB_GROUP_MODE="single-sort")
     r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "mixed ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
