@@ -11,6 +11,11 @@ the two file names but stores its own simple layout:
 
 In fused mode the intermediates are never read back, so only the header (``stub`` flag set) is written --
 enough for Snakemake's file DAG / resume semantics.
+
+Interoperation with the real binaries: ``read_db`` also accepts KMC's own databases (KMC1 and KMC2
+layouts, khoice_b200/kmc_format.py), and with the environment variable ``KHB_DB_FORMAT=kmc1`` ``write_db`` emits the KMC1
+layout, so that single rules can be handed to / taken over from ``kmc`` and ``kmc_tools``.  That layout is restated from
+KMC's API documentation and has not been checked against a KMC binary (none in this image).
 """
 from __future__ import annotations
 
@@ -20,6 +25,8 @@ from dataclasses import dataclass
 from typing import Optional
 
 import numpy as np
+
+from . import kmc_format
 
 MAGIC = b"KHB200DB"
 VERSION = 1
@@ -56,6 +63,9 @@ def write_db(prefix: str, k: int, keys: Optional[np.ndarray], counts: Optional[n
              counter_max: int, n_keys: Optional[int] = None) -> None:
     """Write ``prefix.kmc_pre`` / ``prefix.kmc_suf``.  ``keys is None`` writes a fused-mode stub."""
     stub = keys is None
+    if not stub and os.environ.get("KHB_DB_FORMAT", "").lower() == "kmc1":
+        kmc_format.write_kmc1(prefix, k, keys, counts, counter_max)
+        return
     n = int(n_keys if n_keys is not None else (0 if stub else keys.shape[0]))
     key_bytes = 8 if k <= 32 else 16
     hist = np.ascontiguousarray(hist, dtype=np.uint64)
@@ -71,6 +81,12 @@ def write_db(prefix: str, k: int, keys: Optional[np.ndarray], counts: Optional[n
 
 
 def read_db(prefix: str, header_only: bool = False) -> KmerDB:
+    if kmc_format.is_kmc_database(prefix):
+        hdr, keys, counts = kmc_format.read_kmc(prefix)
+        cmax = min((1 << (8 * hdr["counter_size"])) - 1, 0xFFFFFFFF) if hdr["counter_size"] else 1
+        rows = max(int(counts.max()) if counts.size else 0, 5000)
+        hist = np.bincount(counts.astype(np.int64), minlength=rows + 1).astype(np.uint64)
+        return KmerDB(hdr["k"], keys, counts, hist, cmax, False)
     with open(prefix + ".kmc_pre", "rb") as fd:
         raw = fd.read()
     if len(raw) < 64 or raw[:8] != MAGIC:

@@ -139,7 +139,6 @@ print("fallback ok")
 def test_probe_limit_hands_the_group_back_to_the_sort_path():
     """KHB_HASH_MAX_PROBE=0: the first collision raises the overflow flag; the group is redone by sorting, the dirty
     table is cleared before its next use, results stay exact."""
-    env = dict(os.environ, KHB_HASH_MAX_PROBE="0")
-    env.pop("KHB_GROUP_MODE", None)
+    env = dict(os.environ, KHB_HASH_MAX_PROBE="0", KHB_GROUP_MODE="hash")
     r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "fallback ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

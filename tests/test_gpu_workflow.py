@@ -95,3 +95,31 @@ def test_cli_error_behaviour(tmp_path):
     assert cli.main(["kmc_tools", "simple", "a", "b", "intersect", "c"]) == 1     # not an exp-1 operation
     assert cli.main(["kmc_tools", "transform", str(tmp_path / "missing"), "histogram", str(tmp_path / "h.txt")]) == 1
     assert not (tmp_path / "h.txt").exists()
+
+
+def test_rule_chain_on_kmc_layout_databases(engine, oracle, work_roots, tmp_path, monkeypatch):
+    """with KHB_DB_FORMAT=kmc1 every rule exchanges databases in KMC's own (KMC1) layout -- the files a
+    real kmc_tools would be handed -- and the histograms / CSVs do not change."""
+    from khoice_b200 import kmc_format, kmcdb, pipeline, synth
+    cfg, roots = work_roots
+    root = str(tmp_path / "kmc_layout")
+    synth.write_dataset(cfg, root)
+    ks = ["12", "31", "34"]
+    monkeypatch.setenv("KHB_DB_FORMAT", "kmc1")
+    pipeline.run_rules(root, cfg.n_groups, ks, engine=engine)
+    monkeypatch.delenv("KHB_DB_FORMAT")
+    ref_root = str(tmp_path / "own_layout")
+    synth.write_dataset(cfg, ref_root)
+    pipeline.run_rules(ref_root, cfg.n_groups, ks, engine=engine)
+    for f in (pipeline.P_STEP5, pipeline.P_STEP9):
+        assert filecmp.cmp(os.path.join(root, f), os.path.join(ref_root, f), shallow=False), f
+    for k in ks:
+        for num in range(1, cfg.n_groups + 1):
+            assert filecmp.cmp(os.path.join(root, pipeline.p_step4(k, num)), os.path.join(ref_root, pipeline.p_step4(k, num)), shallow=False)
+            p3 = os.path.join(root, pipeline.p_step3(k, num))
+            assert kmc_format.is_kmc_database(p3)
+            hdr = kmc_format.read_header(p3)
+            assert hdr["k"] == int(k) and hdr["counter_size"] == 2 and hdr["version"] == 0     # -cs5000: two counter bytes
+            a, b = kmcdb.read_db(p3), kmcdb.read_db(os.path.join(ref_root, pipeline.p_step3(k, num)))
+            assert np.array_equal(a.keys, b.keys) and np.array_equal(a.counts, b.counts)
+        assert filecmp.cmp(os.path.join(root, pipeline.p_step8(k)), os.path.join(ref_root, pipeline.p_step8(k)), shallow=False)
