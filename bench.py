@@ -385,11 +385,13 @@ def main():
                     "note": "single-sort contract (~110 B/base); the KMC-shaped chain of SURVEY.md 8d (sort, unique, sort, count: ~329 B/base) "
                             "would need 3x these bytes for the same tables"}
         hist_bytes = (len(mine) + 1) * 5001 * 8
+        default_shape = (wl["groups_per_gpu"], wl["genomes"], wl["genome_len"], k) == (10, 50, 5_000_000, 31)
+        shape_name = "config 2" if default_shape else "custom shape (KHB_BENCH_* overrides)"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"config 2: {wl['groups_per_gpu']} groups x {wl['genomes']} synthetic {wl['genome_len']} bp genomes per GPU, k={k}"
+            "config": {"workload": f"{shape_name}: {wl['groups_per_gpu']} groups x {wl['genomes']} synthetic {wl['genome_len']} bp genomes per GPU, k={k}"
                                    + (f"; {world} GPUs, {n_groups_total} groups, hash-range all-to-all for the across-group stage" if world > 1 else ", single B200"),
                        "k": k, "groups_total": n_groups_total, "genomes_per_group": wl["genomes"], "bases_per_step": bases_all,
                        "l2": "inputs exceed L2: every sort streams >= 2 GB of keys through a 126 MB L2; no explicit flush",
