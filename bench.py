@@ -8,7 +8,8 @@ the workload below: every group's step_4 histogram plus the step_8 across-group 
 
 N=1 workload: BASELINE config 2 -- 10 groups x 50 synthetic 5 Mbp genomes (2.5 Gbp), k=31, single B200.
 N>1 (torchrun, one rank per GPU): weak scaling -- every rank owns 10 such groups; steps 1-6 need no
-collective, the across-group stage is one hash-range all-to-all + a histogram all-reduce (khoice_b200/dist.py).
+collective; for the across-group stage every group's distinct k-mers are pushed to their hash-range owner over peer memory
+(csrc/peer.cu) -- or one NCCL all-to-all (KHB_EXCHANGE=nccl) -- then a local count and a histogram all-reduce (khoice_b200/dist.py).
 
 value   Gbases/s with the FASTA text already staged in HBM when the clock starts (khb_group_from_staged)
 e2e     the same job through khb_group_from_fasta with the text in pinned HOST memory: H2D copies of all
@@ -289,33 +290,34 @@ def main():
         if world > 1:
             dist.barrier()
 
-    def finish(step_hists):
-        """across-group stage: local (N=1) or hash-range all-to-all (N>1)."""
-        if world == 1:
-            h, st = eng.across_groups()
-            return h, st
-        h, info = kd.exchange_and_count(adapter, k, n_groups_total)
-        return h, info
+    # across-group stage: local (N=1); N>1: the k-mer space is hash-range partitioned and every group's new keys are stored
+    # straight into their owner's receive buffer over NVLink by one kernel behind the group's K5 (csrc/peer.cu); the first
+    # round (a warm-up step) runs over NCCL (partition + all-to-all) and sizes the regions.  KHB_EXCHANGE=nccl keeps NCCL.
+    ex = kd.AcrossExchanger(adapter, k, n_groups_total, mode=os.environ.get("KHB_EXCHANGE", "peer"))
 
     def step_device():
         eng.group_sets_reset()
+        ex.begin()
         hs, nb = {}, 0
         for g in mine:
             hs[g], st = eng.group_from_staged(staged[g], k)
+            ex.after_group()
             nb += st["bases"]
-        ha, _ = finish(hs)
+        ha, _ = ex.finish()
         return hs, ha, nb
 
     def step_e2e():
         eng.group_sets_reset()
+        ex.begin()
         hs, nb = {}, 0
         eng.prefetch_fasta(host_views[mine[0]])
         for i, g in enumerate(mine):
             if i + 1 < len(mine):
                 eng.prefetch_fasta(host_views[mine[i + 1]])      # H2D of the next group overlaps this group's kernels
             hs[g], st = eng.group_from_fasta(host_views[g], k)   # uses the prefetched copy, waits for it on the device
+            ex.after_group()
             nb += st["bases"]
-        ha, _ = finish(hs)
+        ha, _ = ex.finish()
         return hs, ha, nb
 
     def timed(fn, steps, profile=False, sampler=None):
@@ -395,7 +397,9 @@ def main():
                                    + (f"; {world} GPUs, {n_groups_total} groups, hash-range all-to-all for the across-group stage" if world > 1 else ", single B200"),
                        "k": k, "groups_total": n_groups_total, "genomes_per_group": wl["genomes"], "bases_per_step": bases_all,
                        "l2": "inputs exceed L2: every sort streams >= 2 GB of keys through a 126 MB L2; no explicit flush",
-                       "parallelism": f"groups dealt round-robin to {world} rank(s)", "data_gen_s": round(gen_s, 1)},
+                       "parallelism": f"groups dealt round-robin to {world} rank(s)", "data_gen_s": round(gen_s, 1),
+                       "exchange": (f"peer-memory push (CUDA IPC over NVLink), {ex.rounds_peer} rounds; NCCL all-to-all, {ex.rounds_nccl} rounds (sizing / fallback)"
+                                    if world > 1 else "none (one GPU)")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_all, "d2h_bytes_per_step": float(hist_bytes * world),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
@@ -411,6 +415,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl)
         print(json.dumps(line))
+    ex.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

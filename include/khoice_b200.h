@@ -266,6 +266,26 @@ KHB_API int khb_group_membership(khb_ctx *ctx, int n_groups, const uint64_t *h_g
 KHB_API int khb_partition_by_hash(khb_ctx *ctx, const void *d_keys, uint64_t n, int k, int n_parts, void *d_out,
                           uint64_t *h_part_off);
 
+/* ---- multi-GPU exchange over peer memory (csrc/peer.cu; no reference counterpart: the reference is single-host CPU) ----
+ * The across-group stage needs every copy of a k-mer on one GPU.  Instead of partition + NCCL all-to-all + copy, every rank
+ * owns a receive buffer of `world` regions (region s is written by rank s only), maps its peers' buffers (CUDA IPC over
+ * NVLink) and khb_peer_push() -- one kernel behind every group's K5 -- stores each new key of the local group-set store
+ * straight into its owner's region.  Protocol per round, on every rank:
+ *     khb_group_sets_reset, khb_peer_begin;  { khb_group_from_*(keep_set = 1), khb_peer_push } per group;
+ *     khb_peer_counts (waits for the own pushes);  exchange the count table between the ranks (any collective: it is the
+ *     barrier);  khb_peer_import(counts sent to me);  khb_across_groups;  all-reduce of the histogram (orders the next round).
+ * If *overflow is set on any rank, a region was too small: redo the round over khb_partition_by_hash + NCCL (the local store
+ * is untouched) and set the exchange up again with larger regions. */
+KHB_API int khb_peer_alloc(khb_ctx *ctx, int world, int rank, int key_bytes, uint64_t region_keys, unsigned char *handle_out /* 64 bytes */);
+KHB_API int khb_peer_open(khb_ctx *ctx, const unsigned char *handles /* world x 64 bytes, rank order */);
+KHB_API int khb_peer_begin(khb_ctx *ctx);
+KHB_API int khb_peer_push(khb_ctx *ctx);
+KHB_API int khb_peer_counts(khb_ctx *ctx, uint64_t *h_counts /* [world] */, int *overflow);
+KHB_API int khb_peer_import(khb_ctx *ctx, const uint64_t *h_recv_counts /* [world] */, int k, int n_groups, int hashed);
+KHB_API int khb_peer_unmap(khb_ctx *ctx); /* drop the peers' mappings; barrier between the ranks; then khb_peer_close frees the own buffer */
+KHB_API int khb_peer_close(khb_ctx *ctx);
+KHB_API uint64_t khb_peer_region_keys(const khb_ctx *ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,8 @@ int khb_presence_count_impl(khb_ctx *, const u64 *, const u32 *, size_t, int, in
 size_t khb_hash_table_bytes(int, int, u64, int *, int *);
 int khb_hash_count_impl(khb_ctx *, const u64 *, const u32 *, u64, int, const u64 *, const u64 *, int, u32 *, int, int, u32, u32, u64 *, void *, u64 *, u64 *, int,
                         void *, u64 *, u32 *);
+int khb_peer_regions(khb_ctx *, const void **, u64 *, int *, int *);
+extern "C" int khb_peer_close(khb_ctx *);
 int khb_pivot_across_impl(khb_ctx *, const void *, const unsigned short *, size_t, int, int, u32, u32, u32, u64 *);
 int khb_sorted_lookup_impl(khb_ctx *, const void *, u64, const void *, u64, int, u64 *);
 int khb_membership_impl(khb_ctx *, const void *, const unsigned short *, size_t, int, int, u32, int, const void *, const u64 *, int, u64 *);
@@ -194,6 +196,7 @@ int khb_destroy(khb_ctx *ctx)
         if (ctx->scratch[i].ptr) cudaFree(ctx->scratch[i].ptr);
     if (ctx->gs_buf) cudaFree(ctx->gs_buf);
     if (ctx->hs_tab) cudaFree(ctx->hs_tab);
+    khb_peer_close(ctx);
     if (ctx->stage_dev) cudaFree(ctx->stage_dev);
     if (ctx->stage_next) cudaFree(ctx->stage_next);
     if (ctx->pf_tab) cudaFree(ctx->pf_tab);
@@ -486,18 +489,7 @@ int khb_count_runs(khb_ctx *ctx, const void *d_sorted, size_t n, int k, uint32_t
 }  // extern "C"
 
 // ---- K7: hash partition ------------------------------------------------------------------------------
-__device__ __forceinline__ u64 mix64(u64 x)
-{
-    x += 0x9e3779b97f4a7c15ull;
-    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
-    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
-    return x ^ (x >> 31);
-}
-__device__ __forceinline__ u32 part_of(const Key64 &k, u32 nparts) { return (u32)__umul64hi(mix64(k.v), (u64)nparts); }
-__device__ __forceinline__ u32 part_of(const Key128 &k, u32 nparts)
-{
-    return (u32)__umul64hi(mix64(k.lo ^ mix64(k.hi)), (u64)nparts);
-}
+// (mix64 / part_of: khb_common.cuh, shared with peer.cu)
 
 #define PT_BLOCK 256
 #define PT_ITEMS 16
@@ -1268,6 +1260,36 @@ int khb_group_sets_append_device(khb_ctx *ctx, int k, const void *d_keys, uint64
     if (n_keys) KHB_CUDA(ctx, cudaMemcpyAsync((char *)ctx->gs_buf + ctx->gs_len * W, d_keys, n_keys * W, cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->gs_len += n_keys;
     ctx->gs_groups += n_groups;
+    return KHB_OK;
+}
+
+int khb_peer_import(khb_ctx *ctx, const uint64_t *h_recv_counts, int k, int n_groups, int hashed)
+{
+    KHB_CHECK_CTX(ctx);
+    const void *recv;
+    u64 region;
+    int world, kb;
+    int rc = khb_peer_regions(ctx, &recv, &region, &world, &kb);
+    if (rc) return rc;
+    if (!h_recv_counts || k < 1 || k > 64 || khb_key_bytes(k) != kb) return khb_fail(ctx, KHB_ERR_ARG, "khb_peer_import: bad arguments");
+    u64 total = 0;
+    for (int s = 0; s < world; s++) {
+        if (h_recv_counts[s] > region) return khb_fail(ctx, KHB_ERR_ARG, "khb_peer_import: rank %d reports %llu keys, a region holds %llu", s, (u64)h_recv_counts[s], region);
+        total += h_recv_counts[s];
+    }
+    ctx->gs_len = 0;
+    ctx->gs_groups = 0;
+    ctx->gs_k = 0;
+    if ((rc = gs_reserve(ctx, k, total))) return rc;
+    ctx->gs_hashed = hashed ? 1 : 0;
+    const size_t W = (size_t)kb;
+    for (int s = 0; s < world; s++) {
+        if (!h_recv_counts[s]) continue;
+        KHB_CUDA(ctx, cudaMemcpyAsync((char *)ctx->gs_buf + ctx->gs_len * W, (const char *)recv + (size_t)s * region * W, h_recv_counts[s] * W,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->gs_len += h_recv_counts[s];
+    }
+    ctx->gs_groups = n_groups;
     return KHB_OK;
 }
 

@@ -143,6 +143,20 @@ __host__ __device__ __forceinline__ void kmer_unmix128(u64 &hi, u64 &lo, int k)
     mix_steps128(hi, lo, k, a_h, a_l, b_h, b_l);
 }
 
+// ---- owner of a k-mer in the multi-GPU exchange: hash-range partition of the key space (K7, peer.cu) ----------
+__device__ __forceinline__ u64 mix64(u64 x)
+{
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ u32 part_of(const Key64 &k, u32 nparts) { return (u32)__umul64hi(mix64(k.v), (u64)nparts); }
+__device__ __forceinline__ u32 part_of(const Key128 &k, u32 nparts)
+{
+    return (u32)__umul64hi(mix64(k.lo ^ mix64(k.hi)), (u64)nparts);
+}
+
 // ---- context ------------------------------------------------------------------------------
 struct khb_scratch {
     void *ptr;
@@ -196,6 +210,7 @@ struct khb_ctx {
     size_t hs_bytes;
     int hs_dirty;
     u64 hs_overflows;  // groups that fell back to the sort path because a probe sequence hit the limit
+    struct khb_peer *peer;  // multi-GPU exchange over peer memory (peer.cu)
     int group_mode;    // KHB_GROUP_* (khb_set_group_mode; initial value from the environment variable KHB_GROUP_MODE)
 };
 

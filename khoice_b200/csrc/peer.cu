@@ -1,0 +1,236 @@
+// peer.cu -- the multi-GPU exchange of the across-group stage, written into peer memory by the producing GPU.
+//
+// The across-group union (`kmc_tools complex` over all groups, /root/reference/workflow/rules/exp_type_1.smk:243-259) needs
+// every copy of a k-mer on one GPU; the k-mer space is hash-range partitioned (part_of).  The NCCL route (dist.py:
+// exchange_and_count) partitions the retained group sets into a send buffer (two sweeps + two host round trips), runs a
+// size all-to-all, a payload all-to-all and copies the result into the store.  Here the exchange is ONE kernel per group,
+// launched right behind the group's K5 on the context's stream:
+//   every rank owns a receive buffer of `world` regions (region s is written by rank s only) and has every peer's buffer
+//   mapped (CUDA IPC, NVLink P2P);  push_kernel reads the group's new keys from the local store once, counts them per owner
+//   in shared memory, reserves space with ONE atomicAdd per (CTA, owner) on a LOCAL cursor -- no remote atomics, the sender
+//   alone writes its region -- and stores every key straight into its owner's region over NVLink (posted 8/16-byte writes).
+// The transfer of group g therefore overlaps the kernels of group g+1 on the receiving side, no send buffer exists, and
+// the only collective left on the path is the 8 x 8 table of counts at the end (which is also the barrier that makes
+// the pushed data visible).  A region that would overflow raises a flag; the caller then redoes the step over NCCL.
+#include <vector>
+
+#include "khb_common.cuh"
+
+#define PP_BLOCK 256
+#define PP_ITEMS 16
+#define PP_MAXPARTS 64
+
+struct khb_peer {
+    int world = 0, rank = 0, key_bytes = 0;
+    u64 region_keys = 0;           // capacity of one sender's region, in keys
+    void *recv = nullptr;          // my receive buffer: world regions
+    void *peer_base[PP_MAXPARTS];  // mapped base of every rank's receive buffer (own entry = recv)
+    void **d_dst = nullptr;        // device copy: where MY region starts inside every rank's buffer
+    u64 *d_cursor = nullptr;       // [world] keys pushed to every rank so far + [1] overflow flag
+    u64 pushed_upto = 0;           // keys of the local group-set store already pushed
+    bool opened = false;
+};
+
+template <typename Key>
+__global__ void __launch_bounds__(PP_BLOCK)
+push_kernel(const Key *__restrict__ in, u64 n, u32 nparts, u64 cap, u64 *__restrict__ cursor, void *const *__restrict__ dst)
+{
+    __shared__ u32 sc[PP_MAXPARTS];
+    __shared__ u64 sbase[PP_MAXPARTS];
+    const u32 tid = threadIdx.x;
+    const u64 begin = (u64)blockIdx.x * (PP_BLOCK * PP_ITEMS);
+    if (tid < PP_MAXPARTS) sc[tid] = 0;
+    __syncthreads();
+    Key keys[PP_ITEMS];
+    u32 part[PP_ITEMS], slot[PP_ITEMS];
+#pragma unroll
+    for (int r = 0; r < PP_ITEMS; r++) {
+        const u64 g = begin + (u64)r * PP_BLOCK + tid;
+        part[r] = 0xffffffffu;
+        if (g < n) {
+            keys[r] = in[g];
+            part[r] = part_of(keys[r], nparts);
+            slot[r] = atomicAdd(&sc[part[r]], 1u);
+        }
+    }
+    __syncthreads();
+    if (tid < nparts) {
+        const u32 c = sc[tid];
+        sbase[tid] = c ? atomicAdd(&cursor[tid], (u64)c) : 0ull;
+        if (c && sbase[tid] + c > cap) cursor[PP_MAXPARTS] = 1ull;  // region full: the caller falls back to NCCL
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < PP_ITEMS; r++) {
+        if (part[r] == 0xffffffffu) continue;
+        const u64 o = sbase[part[r]] + slot[r];
+        if (o < cap) ((Key *)dst[part[r]])[o] = keys[r];
+    }
+}
+
+extern "C" {
+
+// Allocate this rank's receive buffer (world regions of region_keys keys of key_bytes each) and return its IPC handle.
+int khb_peer_alloc(khb_ctx *ctx, int world, int rank, int key_bytes, uint64_t region_keys, unsigned char *handle_out /* 64 bytes */)
+{
+    KHB_CHECK_CTX(ctx);
+    if (world < 1 || world > PP_MAXPARTS || rank < 0 || rank >= world || (key_bytes != 8 && key_bytes != 16) || !region_keys || !handle_out)
+        return khb_fail(ctx, KHB_ERR_ARG, "khb_peer_alloc: bad arguments (world=%d rank=%d key_bytes=%d)", world, rank, key_bytes);
+    if (ctx->peer) return khb_fail(ctx, KHB_ERR_STATE, "khb_peer_alloc: a peer exchange is already set up (khb_peer_close first)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    khb_peer *pp = new khb_peer();
+    pp->world = world;
+    pp->rank = rank;
+    pp->key_bytes = key_bytes;
+    pp->region_keys = region_keys;
+    const size_t bytes = (size_t)world * region_keys * key_bytes;
+    cudaError_t e = cudaMalloc(&pp->recv, bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&pp->d_dst, PP_MAXPARTS * sizeof(void *));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&pp->d_cursor, (PP_MAXPARTS + 1) * sizeof(u64));
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, pp->recv);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (pp->recv) cudaFree(pp->recv);
+        if (pp->d_dst) cudaFree(pp->d_dst);
+        if (pp->d_cursor) cudaFree(pp->d_cursor);
+        delete pp;
+        return khb_fail(ctx, e == cudaErrorMemoryAllocation ? KHB_ERR_NOMEM : KHB_ERR_CUDA, "khb_peer_alloc (%zu bytes): %s", bytes, cudaGetErrorString(e));
+    }
+    memcpy(handle_out, &h, 64);
+    ctx->peer = pp;
+    return KHB_OK;
+}
+
+// Map every rank's receive buffer.  handles: world x 64 bytes, in rank order (the own entry is ignored).
+int khb_peer_open(khb_ctx *ctx, const unsigned char *handles)
+{
+    KHB_CHECK_CTX(ctx);
+    khb_peer *pp = ctx->peer;
+    if (!pp || pp->opened || !handles) return khb_fail(ctx, KHB_ERR_STATE, "khb_peer_open: call khb_peer_alloc first (once)");
+    void *dst[PP_MAXPARTS] = {nullptr};
+    for (int r = 0; r < pp->world; r++) {
+        if (r == pp->rank) {
+            pp->peer_base[r] = pp->recv;
+        } else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles + (size_t)r * 64, 64);
+            void *p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                for (int q = 0; q < r; q++)
+                    if (q != pp->rank) cudaIpcCloseMemHandle(pp->peer_base[q]);
+                return khb_fail(ctx, KHB_ERR_CUDA, "khb_peer_open: cudaIpcOpenMemHandle for rank %d: %s", r, cudaGetErrorString(e));
+            }
+            pp->peer_base[r] = p;
+        }
+        dst[r] = (char *)pp->peer_base[r] + (size_t)pp->rank * pp->region_keys * pp->key_bytes;  // my region inside rank r's buffer
+    }
+    KHB_CUDA(ctx, cudaMemcpyAsync(pp->d_dst, dst, sizeof(dst), cudaMemcpyHostToDevice, ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(pp->d_cursor, 0, (PP_MAXPARTS + 1) * sizeof(u64), ctx->stream));
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    pp->opened = true;
+    return KHB_OK;
+}
+
+// Start a new exchange round: cursors to zero, nothing of the store pushed yet.  Every rank must have finished
+// khb_peer_import of the previous round before any rank pushes again (the caller's histogram all-reduce orders that).
+int khb_peer_begin(khb_ctx *ctx)
+{
+    KHB_CHECK_CTX(ctx);
+    khb_peer *pp = ctx->peer;
+    if (!pp || !pp->opened) return khb_fail(ctx, KHB_ERR_STATE, "khb_peer_begin: no peer exchange set up");
+    KHB_CUDA(ctx, cudaMemsetAsync(pp->d_cursor, 0, (PP_MAXPARTS + 1) * sizeof(u64), ctx->stream));
+    pp->pushed_upto = 0;
+    return KHB_OK;
+}
+
+// Push the keys the group-set store gained since the last push to their owners (asynchronous, on the context's stream).
+int khb_peer_push(khb_ctx *ctx)
+{
+    KHB_CHECK_CTX(ctx);
+    khb_peer *pp = ctx->peer;
+    if (!pp || !pp->opened) return khb_fail(ctx, KHB_ERR_STATE, "khb_peer_push: no peer exchange set up");
+    if (ctx->gs_len < pp->pushed_upto) return khb_fail(ctx, KHB_ERR_STATE, "khb_peer_push: the group-set store shrank; call khb_peer_begin after a reset");
+    const u64 n = ctx->gs_len - pp->pushed_upto;
+    if (!n) return KHB_OK;
+    const size_t W = (size_t)khb_key_bytes(ctx->gs_k);
+    if ((int)W != pp->key_bytes) return khb_fail(ctx, KHB_ERR_STATE, "khb_peer_push: the exchange was set up for %d-byte keys", pp->key_bytes);
+    const char *src = (const char *)ctx->gs_buf + pp->pushed_upto * W;
+    const u64 blocks = div_up(n, PP_BLOCK * PP_ITEMS);
+    khb_prof_begin(ctx, KHB_K_PARTITION);
+    if (W == 8)
+        push_kernel<Key64><<<(unsigned)blocks, PP_BLOCK, 0, ctx->stream>>>((const Key64 *)src, n, (u32)pp->world, pp->region_keys, pp->d_cursor, pp->d_dst);
+    else
+        push_kernel<Key128><<<(unsigned)blocks, PP_BLOCK, 0, ctx->stream>>>((const Key128 *)src, n, (u32)pp->world, pp->region_keys, pp->d_cursor, pp->d_dst);
+    KHB_LAUNCH_CHECK(ctx);
+    khb_prof_end(ctx, KHB_K_PARTITION, 2 * n * W);
+    pp->pushed_upto = ctx->gs_len;
+    return KHB_OK;
+}
+
+// Wait for this rank's pushes and report how many keys went to every rank (h_counts[world]) and whether a region overflowed.
+int khb_peer_counts(khb_ctx *ctx, uint64_t *h_counts, int *overflow)
+{
+    KHB_CHECK_CTX(ctx);
+    khb_peer *pp = ctx->peer;
+    if (!pp || !pp->opened || !h_counts) return khb_fail(ctx, KHB_ERR_STATE, "khb_peer_counts: no peer exchange set up");
+    u64 *h = ctx->h_mail + 20000;
+    KHB_CUDA(ctx, cudaMemcpyAsync(h, pp->d_cursor, (PP_MAXPARTS + 1) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < pp->world; r++) h_counts[r] = h[r];
+    if (overflow) *overflow = h[PP_MAXPARTS] ? 1 : 0;
+    return KHB_OK;
+}
+
+// Replace the retained group sets by what the ranks pushed here: h_recv_counts[s] keys in region s.  Call only after every
+// rank's khb_peer_counts returned (the count exchange between the ranks is that barrier).
+int khb_peer_import(khb_ctx *ctx, const uint64_t *h_recv_counts, int k, int n_groups, int hashed);
+
+// Drop the mappings of the other ranks' buffers (pushing is over).  Every rank must have done this before any rank frees
+// its buffer with khb_peer_close: put a barrier between the two calls.
+int khb_peer_unmap(khb_ctx *ctx)
+{
+    if (!ctx || !ctx->peer) return KHB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    khb_peer *pp = ctx->peer;
+    if (pp->opened)
+        for (int r = 0; r < pp->world; r++)
+            if (r != pp->rank && pp->peer_base[r]) {
+                cudaIpcCloseMemHandle(pp->peer_base[r]);
+                pp->peer_base[r] = nullptr;
+            }
+    pp->opened = false;
+    return KHB_OK;
+}
+
+int khb_peer_close(khb_ctx *ctx)
+{
+    if (!ctx || !ctx->peer) return KHB_OK;
+    khb_peer_unmap(ctx);
+    khb_peer *pp = ctx->peer;
+    if (pp->recv) cudaFree(pp->recv);
+    if (pp->d_dst) cudaFree(pp->d_dst);
+    if (pp->d_cursor) cudaFree(pp->d_cursor);
+    delete pp;
+    ctx->peer = nullptr;
+    return KHB_OK;
+}
+
+uint64_t khb_peer_region_keys(const khb_ctx *ctx) { return ctx && ctx->peer ? ctx->peer->region_keys : 0; }
+
+}  // extern "C"
+
+// used by khb_peer_import (api.cu owns the group-set store)
+int khb_peer_regions(khb_ctx *ctx, const void **recv, u64 *region_keys, int *world, int *key_bytes)
+{
+    khb_peer *pp = ctx->peer;
+    if (!pp || !pp->opened) return khb_fail(ctx, KHB_ERR_STATE, "khb_peer_import: no peer exchange set up");
+    *recv = pp->recv;
+    *region_keys = pp->region_keys;
+    *world = pp->world;
+    *key_bytes = pp->key_bytes;
+    return KHB_OK;
+}

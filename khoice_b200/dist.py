@@ -93,8 +93,97 @@ def exchange_and_count(adapter, k: int, n_groups_total: int, nbins: int = COUNTE
     h = torch.from_numpy(np.ascontiguousarray(hist).astype(np.int64)).to(dev)
     dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
     info = {"send_words": sum(send_words), "recv_words": sum(recv_words), "local_distinct": int(st.get("distinct", 0)),
-            "across_ms": float(st.get("ms_total", 0.0))}
+            "across_ms": float(st.get("ms_total", 0.0)), "send_words_per_rank": list(send_words), "exchange": "nccl"}
     return h.cpu().numpy().astype(np.uint64), info
+
+
+class AcrossExchanger:
+    """The across-group stage of one rank, round after round (one round = one k over all groups).
+
+    ``mode="nccl"``: partition + all-to-all + copy (exchange_and_count).  ``mode="peer"`` (CUDA adapters only): every group's
+    new keys are stored straight into their owner's receive buffer by one kernel behind the group's K5 (csrc/peer.cu, CUDA
+    IPC over NVLink), the only collective on the path is the table of counts.  The first round always runs over NCCL: it
+    measures how many keys every (sender, owner) pair exchanges, which sizes the regions (x 1.3, agreed with an
+    all-reduce(max)); a round in which a region still overflows is redone over NCCL and the regions grow.
+
+    Usage per round:  begin();  after every group_from_*(keep_set=True): after_group();  finish() -> (histogram, info)."""
+
+    def __init__(self, adapter, k: int, n_groups_total: int, nbins: int = COUNTER_MAX, mode: str = "peer", group=None,
+                 region_keys: Optional[int] = None):
+        self.ad, self.k, self.n_groups, self.nbins, self.group = adapter, k, n_groups_total, nbins, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.mode = mode if self.world > 1 and hasattr(adapter, "eng") else "nccl"
+        self.ready = False
+        self.rounds_peer = self.rounds_nccl = 0
+        self.ctrl = adapter.new_tensor(0).device if dist.is_initialized() and dist.get_backend(group) == "nccl" else torch.device("cpu")
+        if self.mode == "peer" and region_keys:
+            self._setup(int(region_keys))
+
+    def _setup(self, region_keys: int):
+        eng = self.ad.eng
+        if self.ready:
+            self.close()
+        handle = eng.peer_alloc(self.world, self.rank, 8 * key_words(self.k), region_keys)
+        mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(self.ctrl)
+        allh = torch.empty(64 * self.world, dtype=torch.uint8, device=self.ctrl)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        eng.peer_open(bytes(allh.cpu().numpy().tobytes()))
+        dist.barrier(group=self.group)  # nobody pushes before everybody has mapped everybody
+        self.ready = True
+
+    def begin(self):
+        if self.ready:
+            self.ad.eng.peer_begin()
+
+    def after_group(self):
+        if self.ready:
+            self.ad.eng.peer_push()
+
+    def _grow_from(self, per_dest_keys: Sequence[int]):
+        need = torch.tensor([max(per_dest_keys) if len(per_dest_keys) else 0], dtype=torch.int64, device=self.ctrl)
+        dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
+        self._setup(max(int(need.item()) * 13 // 10, 1024))
+
+    def finish(self):
+        if self.world == 1:
+            return self.ad.across(self.nbins)
+        if not self.ready:
+            hist, info = exchange_and_count(self.ad, self.k, self.n_groups, self.nbins, self.group)
+            self.rounds_nccl += 1
+            if self.mode == "peer":
+                w = key_words(self.k)
+                self._grow_from([x // w for x in info["send_words_per_rank"]])
+            return hist, info
+        eng = self.ad.eng
+        hashed = eng.group_sets_hashed
+        counts, ovf = eng.peer_counts(self.world)
+        row = torch.from_numpy(np.concatenate([counts.astype(np.int64), [1 if ovf else 0]])).to(self.ctrl)
+        table = torch.empty((self.world, self.world + 1), dtype=torch.int64, device=self.ctrl)
+        dist.all_gather_into_tensor(table.view(-1), row, group=self.group)   # also the barrier: every rank's pushes are done
+        table = table.cpu().numpy()
+        if table[:, self.world].any():
+            hist, info = exchange_and_count(self.ad, self.k, self.n_groups, self.nbins, self.group)  # the local store is intact
+            self.rounds_nccl += 1
+            self._grow_from([int(x) for x in table[self.rank, : self.world]])
+            return hist, info
+        eng.peer_import(table[:, self.rank].astype(np.uint64), self.k, self.n_groups, hashed)
+        hist, st = self.ad.across(self.nbins)
+        dev = self.ad.new_tensor(0).device
+        h = torch.from_numpy(np.ascontiguousarray(hist).astype(np.int64)).to(dev if self.ctrl.type != "cpu" else self.ctrl)
+        dist.all_reduce(h, op=dist.ReduceOp.SUM, group=self.group)           # also orders the next round's pushes behind this import
+        self.rounds_peer += 1
+        info = {"send_words": int(counts.sum()) * key_words(self.k), "recv_words": int(table[:, self.rank].sum()) * key_words(self.k),
+                "local_distinct": int(st.get("distinct", 0)), "across_ms": float(st.get("ms_total", 0.0)), "exchange": "peer"}
+        return h.cpu().numpy().astype(np.uint64), info
+
+    def close(self):
+        """Collective: every rank drops its mappings before any rank frees its buffer."""
+        if self.ready:
+            self.ad.eng.peer_unmap()
+            dist.barrier(group=self.group)
+            self.ad.eng.peer_close()
+            self.ready = False
 
 
 def run_exp1_k(adapter, groups: Dict[int, Sequence], n_groups_total: int, k: int, nbins: int = COUNTER_MAX, group=None):

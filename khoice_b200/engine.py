@@ -101,6 +101,15 @@ _SIGNATURES = [
     ("khb_sorted_lookup", C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.c_int, _P]),
     ("khb_group_membership", C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int]),
     ("khb_partition_by_hash", C.c_int, [_P, _P, C.c_uint64, C.c_int, C.c_int, _P, _P]),
+    ("khb_peer_alloc", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_uint64, _P]),
+    ("khb_peer_open", C.c_int, [_P, _P]),
+    ("khb_peer_begin", C.c_int, [_P]),
+    ("khb_peer_push", C.c_int, [_P]),
+    ("khb_peer_counts", C.c_int, [_P, _P, C.POINTER(C.c_int)]),
+    ("khb_peer_import", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int]),
+    ("khb_peer_unmap", C.c_int, [_P]),
+    ("khb_peer_close", C.c_int, [_P]),
+    ("khb_peer_region_keys", C.c_uint64, [_P]),
     ("khb_set_group_mode", C.c_int, [_P, C.c_int]),
     ("khb_hash_overflows", C.c_uint64, [_P]),
 ]
@@ -259,6 +268,43 @@ class Engine:
 
     KERNELS = {"pack": 0, "extract": 1, "radix_hist": 2, "onesweep": 3, "unique": 4, "rle_hist": 5, "partition": 6,
                "hash_insert": 7, "hash_count": 8}
+
+    # ---- multi-GPU exchange over peer memory (csrc/peer.cu) ----
+    def peer_alloc(self, world: int, rank: int, key_bytes: int, region_keys: int) -> bytes:
+        """Allocate this rank's receive buffer; returns its 64-byte CUDA IPC handle for the other ranks."""
+        h = (C.c_ubyte * 64)()
+        self._chk(self.lib.khb_peer_alloc(self.ctx, world, rank, key_bytes, int(region_keys), h))
+        return bytes(h)
+
+    def peer_open(self, handles: bytes):
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        self._chk(self.lib.khb_peer_open(self.ctx, buf))
+
+    def peer_begin(self):
+        self._chk(self.lib.khb_peer_begin(self.ctx))
+
+    def peer_push(self):
+        self._chk(self.lib.khb_peer_push(self.ctx))
+
+    def peer_counts(self, world: int):
+        counts = np.zeros(world, dtype=np.uint64)
+        ovf = C.c_int()
+        self._chk(self.lib.khb_peer_counts(self.ctx, counts.ctypes.data, C.byref(ovf)))
+        return counts, bool(ovf.value)
+
+    def peer_import(self, recv_counts, k: int, n_groups: int, hashed: bool):
+        rc = np.ascontiguousarray(recv_counts, dtype=np.uint64)
+        self._chk(self.lib.khb_peer_import(self.ctx, rc.ctypes.data, k, n_groups, int(hashed)))
+
+    def peer_unmap(self):
+        self._chk(self.lib.khb_peer_unmap(self.ctx))
+
+    def peer_close(self):
+        self._chk(self.lib.khb_peer_close(self.ctx))
+
+    @property
+    def peer_region_keys(self) -> int:
+        return int(self.lib.khb_peer_region_keys(self.ctx))
 
     GROUP_MODES = {"auto": 0, "single-sort": 1, "two-sort": 2, "hash": 3}
 
