@@ -82,7 +82,7 @@ void khb_prof_begin(khb_ctx *ctx, int id)
     khb_prof *p = ctx->prof;
     p->open_a = prof_event(p);
     p->open = true;
-    cudaEventRecord(p->open_a, ctx->stream);
+    cudaEventRecord(p->open_a, ctx->prof_stream ? ctx->prof_stream : ctx->stream);
 }
 
 void khb_prof_end(khb_ctx *ctx, int id, u64 alg_bytes)
@@ -94,7 +94,7 @@ void khb_prof_end(khb_ctx *ctx, int id, u64 alg_bytes)
     r.a = p->open_a;
     r.b = prof_event(p);
     r.bytes = alg_bytes;
-    cudaEventRecord(r.b, ctx->stream);
+    cudaEventRecord(r.b, ctx->prof_stream ? ctx->prof_stream : ctx->stream);
     p->recs.push_back(r);
     p->open = false;
 }
@@ -571,6 +571,8 @@ static int gs_reserve(khb_ctx *ctx, int k, u64 extra)
     if (ctx->gs_k && ctx->gs_k != k) return khb_fail(ctx, KHB_ERR_STATE, "retained group sets were built with k=%d, not k=%d; call khb_group_sets_reset", ctx->gs_k, k);
     const u64 need = (ctx->gs_len + extra + 2) * W;  // gs_cap is in BYTES (W changes with k)
     if (need > ctx->gs_cap) {
+        int prc = khb_peer_wait(ctx);  // a push may still be reading the store that is about to move
+        if (prc) return prc;
         u64 cap = ctx->gs_cap ? ctx->gs_cap : (8u << 20);
         while (cap < need) cap += cap / 2 + 16;
         void *nb = nullptr;

@@ -211,6 +211,7 @@ struct khb_ctx {
     int hs_dirty;
     u64 hs_overflows;  // groups that fell back to the sort path because a probe sequence hit the limit
     struct khb_peer *peer;  // multi-GPU exchange over peer memory (peer.cu)
+    cudaStream_t prof_stream;  // stream the next khb_prof_begin/end pair records on (null: `stream`)
     int group_mode;    // KHB_GROUP_* (khb_set_group_mode; initial value from the environment variable KHB_GROUP_MODE)
 };
 
@@ -225,6 +226,7 @@ enum { SCR_TILE = 0, SCR_LOOKBACK = 1, SCR_HIST = 2, SCR_MISC = 3, SCR_KEYS_A = 
 int khb_fail(khb_ctx *ctx, int code, const char *fmt, ...);
 int khb_cuda_fail(khb_ctx *ctx, cudaError_t e, const char *what, const char *file, int line);
 int khb_scratch_get(khb_ctx *ctx, int slot, size_t bytes, void **out);
+int khb_peer_wait(khb_ctx *ctx);  // wait for pushes in flight (before the group-set store moves)
 
 #define KHB_CUDA(ctx, expr)                                                           \
     do {                                                                              \

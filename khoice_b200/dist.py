@@ -121,15 +121,38 @@ class AcrossExchanger:
             self._setup(int(region_keys))
 
     def _setup(self, region_keys: int):
+        """Collective.  (Re)allocate the receive buffers and map everybody's.  If any rank cannot (no IPC between the
+        processes, out of memory), ALL ranks drop to the NCCL route for the rest of the run."""
+        import sys
+        from .engine import KhbError
         eng = self.ad.eng
         if self.ready:
             self.close()
-        handle = eng.peer_alloc(self.world, self.rank, 8 * key_words(self.k), region_keys)
+        ok, why, handle = 1, "", bytes(64)
+        try:
+            handle = eng.peer_alloc(self.world, self.rank, 8 * key_words(self.k), region_keys)
+        except KhbError as e:
+            ok, why = 0, str(e)
         mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(self.ctrl)
         allh = torch.empty(64 * self.world, dtype=torch.uint8, device=self.ctrl)
         dist.all_gather_into_tensor(allh, mine, group=self.group)
-        eng.peer_open(bytes(allh.cpu().numpy().tobytes()))
-        dist.barrier(group=self.group)  # nobody pushes before everybody has mapped everybody
+        flag = torch.tensor([ok], dtype=torch.int64, device=self.ctrl)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()):
+            try:
+                eng.peer_open(bytes(allh.cpu().numpy().tobytes()))
+            except KhbError as e:
+                ok, why = 0, str(e)
+            flag = torch.tensor([ok], dtype=torch.int64, device=self.ctrl)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)   # also: nobody pushes before everybody has mapped everybody
+        if not int(flag.item()):
+            if why:
+                print(f"khoice_b200.dist: rank {self.rank}: peer-memory exchange unavailable ({why}); using NCCL", file=sys.stderr)
+            eng.peer_unmap()
+            dist.barrier(group=self.group)
+            eng.peer_close()
+            self.mode = "nccl"
+            return
         self.ready = True
 
     def begin(self):

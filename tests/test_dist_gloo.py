@@ -112,3 +112,120 @@ def test_group_dealing():
         owned = [groups_of_rank(n, r, world) for r in range(world)]
         assert sorted(g for o in owned for g in o) == list(range(1, n + 1))
         assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1
+
+
+# ---- the peer-memory exchange protocol (dist.AcrossExchanger) on a stand-in engine ------------------------------------
+class FakePeerEngine:
+    """TEST ONLY.  The calls of csrc/peer.cu with "peer memory" = numpy memmap files in a directory all ranks see.  What is
+    checked on CPU is the host protocol: sizing round over the all-to-all route, regions, count table, overflow -> fallback ->
+    regrow, and that the histograms do not depend on the route or the number of ranks."""
+
+    def __init__(self, adapter, shared_dir):
+        self.ad, self.dir = adapter, shared_dir
+        self.gen = 0
+        self.maps = None
+        self.group_sets_hashed = False
+
+    def _path(self, rank, gen):
+        return os.path.join(self.dir, f"recv_{rank}_{gen}.bin")
+
+    def peer_alloc(self, world, rank, key_bytes, region_keys):
+        self.gen += 1
+        self.world, self.rank, self.w, self.region = world, rank, key_bytes // 8, int(region_keys)
+        np.lib.format.open_memmap(self._path(rank, self.gen), mode="w+", dtype=np.uint64, shape=(world, self.region, self.w))
+        return self.gen.to_bytes(8, "little") + bytes(56)
+
+    def peer_open(self, handles):
+        gens = [int.from_bytes(handles[64 * r:64 * r + 8], "little") for r in range(self.world)]
+        self.maps = [np.load(self._path(r, gens[r]), mmap_mode="r+") for r in range(self.world)]
+
+    def peer_begin(self):
+        self.cursor = np.zeros(self.world, dtype=np.uint64)
+        self.ovf = False
+        self.pushed = 0
+
+    def peer_push(self):
+        new = self.ad.sets[self.pushed:]
+        self.pushed = len(self.ad.sets)
+        for keys in new:
+            flat = keys.reshape(-1, self.w)
+            dest = self.ad.owner(flat, self.world)
+            for r in range(self.world):
+                part = flat[dest == r]
+                c = int(self.cursor[r])
+                room = max(min(self.region - c, part.shape[0]), 0)
+                self.maps[r][self.rank, c:c + room] = part[:room]
+                self.ovf |= room < part.shape[0]
+                self.cursor[r] += np.uint64(part.shape[0])
+
+    def peer_counts(self, world):
+        for m in self.maps:
+            m.flush()
+        return self.cursor.copy(), self.ovf
+
+    def peer_import(self, recv_counts, k, n_groups, hashed):
+        mine = np.load(self._path(self.rank, self.gen), mmap_mode="r")
+        got = np.concatenate([np.array(mine[s, :int(recv_counts[s])]) for s in range(self.world)], axis=0)
+        self.ad.sets = [got.reshape(-1) if self.w == 1 else got]
+
+    def peer_unmap(self):
+        self.maps = None
+
+    def peer_close(self):
+        pass
+
+    @property
+    def peer_region_keys(self):
+        return self.region
+
+
+class PeerOracleAdapter(OracleAdapter):
+    def __init__(self, k, shared_dir):
+        super().__init__(k)
+        self.eng = FakePeerEngine(self, shared_dir)
+
+    @staticmethod
+    def owner(flat, world):
+        h = (flat[:, 0] * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(40)
+        if flat.shape[1] == 2:
+            h = h ^ (flat[:, 1] * np.uint64(0xC2B2AE3D27D4EB4F) >> np.uint64(40))
+        return (h % np.uint64(world)).astype(np.int64)
+
+
+def _peer_worker(rank, world, port, n_groups, k, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from khoice_b200 import dist as kd
+    kd.init_from_env("gloo")
+    allg = _make_groups(n_groups, k)
+    mine = kd.groups_of_rank(n_groups, rank, world)
+    ref = np.load(os.path.join(out_dir, "across_ref.npy"))
+    for region, expect in ((None, ["nccl", "peer", "peer"]), (8, ["nccl", "peer", "peer"]), (1 << 20, ["peer", "peer", "peer"])):
+        ad = PeerOracleAdapter(k, out_dir)
+        ex = kd.AcrossExchanger(ad, k, n_groups, nbins=64, mode="peer", region_keys=region)
+        for rnd in range(3):
+            ad.reset()
+            ex.begin()
+            for g in mine:
+                ad.group(allg[g], k, 64)
+                ex.after_group()
+            hist, info = ex.finish()
+            assert info["exchange"] == expect[rnd], (region, rnd, info["exchange"])
+            assert np.array_equal(hist, ref), (region, rnd, rank)
+        if region == 8:
+            assert ad.eng.peer_region_keys > 8          # the overflowing round made the regions grow
+        ex.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("k,world", [(21, 2), (35, 3)])
+def test_peer_exchange_protocol_on_stand_in_engine(tmp_path, oracle, k, world):
+    n_groups = 5
+    allg = _make_groups(n_groups, k)
+    flat = [f for g in sorted(allg) for f in allg[g]]
+    gid = [g - 1 for g in sorted(allg) for _ in allg[g]]
+    _, a_ref, _ = oracle.exp1(flat, gid, n_groups, k, nbins=64)
+    np.save(tmp_path / "across_ref.npy", a_ref)
+    mp.spawn(_peer_worker, args=(world, _free_port(), n_groups, k, str(tmp_path)), nprocs=world, join=True)

@@ -65,13 +65,14 @@ print("peer ok", rank)
 """
 
 
-def test_two_ranks_on_one_gpu_push_over_ipc():
+@pytest.mark.parametrize("async_push", ["0", "1"])
+def test_two_ranks_on_one_gpu_push_over_ipc(async_push):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     procs = []
     for rank in range(2):
-        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), KHB_PEER_ASYNC=async_push)
         procs.append(subprocess.Popen([sys.executable, "-c", SCRIPT % {"root": ROOT}], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     outs = []
     for p in procs:
