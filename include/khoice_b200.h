@@ -261,6 +261,17 @@ KHB_API int khb_sorted_lookup(khb_ctx *ctx, const void *d_a, uint64_t n_a, const
 KHB_API int khb_group_membership(khb_ctx *ctx, int n_groups, const uint64_t *h_group_off, const void *d_queries, int n_query_sets,
                          const uint64_t *h_query_off, uint64_t *d_mask, int mask_words);
 
+/* Experiment type 6, read level (src/merge_lists.py:149-181 as called by rule run_merge_list_exp6, exp_type_6.smk:327-346):
+ * votes of every read for every dataset.  d_index[i] = position of window i's canonical k-mer in the pivot's ascending
+ * distinct k-mer list (khb_sorted_lookup of the K2 output against that list; UINT64_MAX = no k-mer), d_mask = that list's
+ * membership masks (khb_group_membership), read r owns the windows [d_read_first[r], d_read_first[r] + d_read_nwin[r]).
+ * d_votes[r * n_groups + d] = sum over the read's windows, IN WINDOW ORDER, of 1 / len(matches) for the windows whose k-mer
+ * is in dataset d (IEEE doubles, the same additions in the same order as the reference's Python floats);
+ * d_unmatched[r] = windows whose k-mer is in no dataset.  The argmax with random tie-breaking stays on the host. */
+KHB_API int khb_read_votes(khb_ctx *ctx, const uint64_t *d_index, const uint64_t *d_mask, int mask_words, int n_groups,
+                   const uint64_t *d_read_first, const uint32_t *d_read_nwin, uint64_t n_reads, double *d_votes,
+                   uint32_t *d_unmatched);
+
 /* K7: split n keys into n_parts buckets by splitmix64(key) % n_parts (multi-GPU hash-range partition of the
  * k-mer space).  d_out receives the keys grouped by bucket, h_part_off[n_parts+1] the bucket offsets. */
 KHB_API int khb_partition_by_hash(khb_ctx *ctx, const void *d_keys, uint64_t n, int k, int n_parts, void *d_out,

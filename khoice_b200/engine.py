@@ -101,6 +101,7 @@ _SIGNATURES = [
     ("khb_sorted_lookup", C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.c_int, _P]),
     ("khb_group_membership", C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int]),
     ("khb_partition_by_hash", C.c_int, [_P, _P, C.c_uint64, C.c_int, C.c_int, _P, _P]),
+    ("khb_read_votes", C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_uint64, _P, _P]),
     ("khb_peer_alloc", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_uint64, _P]),
     ("khb_peer_open", C.c_int, [_P, _P]),
     ("khb_peer_begin", C.c_int, [_P]),
@@ -588,6 +589,44 @@ class Engine:
         finally:
             cat.free()
             mask.free()
+
+    def read_votes(self, reads: Sequence[bytes], k: int, pivot_keys: DeviceBuffer, n_pivot: int, masks: np.ndarray, n_groups: int):
+        """Experiment type 6, read level: per-read votes (src/merge_lists.py:157-174) on the GPU.  reads: upper-case ACGT
+        strings (merge_lists.split_reads); pivot_keys / masks: the pivot's ascending distinct k-mers (kmer_counts) and their
+        membership masks (group_membership).  Returns (votes float64 [n_reads, n_groups], unmatched uint32 [n_reads])."""
+        n_reads = len(reads)
+        if n_reads == 0:
+            return np.zeros((0, n_groups), np.float64), np.zeros(0, np.uint32)
+        lens = np.fromiter((len(r) for r in reads), dtype=np.int64, count=n_reads)
+        text = b"".join(b">\n" + r + b"\n" for r in reads)      # every read its own record: windows never span two reads
+        first = (np.arange(1, n_reads + 1, dtype=np.int64) + np.concatenate([[0], np.cumsum(lens)[:-1]])).astype(np.uint64)
+        nwin = np.maximum(lens - k + 1, 0).astype(np.uint32)
+        masks = np.ascontiguousarray(masks, dtype=np.uint64).reshape(n_pivot, -1)
+        words = masks.shape[1]
+        staged = self.stage_fasta([text])
+        packed = self.pack_fasta(staged)
+        n = packed["n_symbols"]
+        if not 0 <= n - (n_reads + int(lens.sum())) <= 1:        # the staging filler behind the text ends with one more break symbol
+            raise KhbError(-1, f"read_votes: {n} symbols packed, {n_reads + int(lens.sum())} expected")
+        keys = self.extract_kmers(packed, k)
+        bufs = [keys, staged.buf, packed["codes"], packed["valid"]]
+        try:
+            index = self.alloc(max(n, 1) * 8); bufs.append(index)
+            self._chk(self.lib.khb_sorted_lookup(self.ctx, keys.ptr, n, pivot_keys.ptr, n_pivot, k, index.ptr))
+            d_mask = self.alloc(max(masks.nbytes, 16)); bufs.append(d_mask)
+            if masks.nbytes:
+                d_mask.upload(masks)
+            d_first = self.alloc(n_reads * 8); bufs.append(d_first)
+            d_first.upload(first)
+            d_nwin = self.alloc(n_reads * 4); bufs.append(d_nwin)
+            d_nwin.upload(nwin)
+            d_votes = self.alloc(n_reads * n_groups * 8); bufs.append(d_votes)
+            d_un = self.alloc(n_reads * 4); bufs.append(d_un)
+            self._chk(self.lib.khb_read_votes(self.ctx, index.ptr, d_mask.ptr, words, n_groups, d_first.ptr, d_nwin.ptr, n_reads, d_votes.ptr, d_un.ptr))
+            return d_votes.download(np.float64, n_reads * n_groups).reshape(n_reads, n_groups), d_un.download(np.uint32, n_reads)
+        finally:
+            for b in bufs:
+                b.free()
 
     def group_sets_info(self) -> dict:
         k, g, n = C.c_int(), C.c_int(), C.c_uint64()

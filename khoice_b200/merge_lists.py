@@ -16,13 +16,20 @@ nothing), and columns that never receive a term stay the integer 0 like the refe
 Two front ends:
 * ``confusion_from_masks`` -- counts + group-membership bitmasks straight from the GPU (Engine.group_membership);
 * ``main`` / ``confusion_from_dumps`` -- the reference's command line over text dumps (rule-compatible mode).
-The read-level mode of the reference (``-r``, merge_lists.py:149-181) draws ties with ``random.choice`` and needs
-simulated reads; it is not part of experiment type 4's rule (exp_type_4.smk:284-290) and is not provided.
+Read level (``-r DIR``, merge_lists.py:149-181; what experiment type 6's rule passes, exp_type_6.smk:327-346): every line
+without ``>`` of ``DIR/pivot_{p}.fa`` is a read; its k-mers vote ``1 / len(M(x))`` for every dataset of M(x), in read order,
+and the read counts 1 for the dataset with the most votes -- ties (also: a read without any hit) are drawn with
+``random.choice`` from Python's global generator, UNSEEDED in the reference, so tied reads make the reference's own output
+vary from run to run.  This module makes the same calls in the same order (one ``random.choice`` per read, over the same
+candidate array), so that under one ``random.seed`` both programs print the same bytes; the votes come either from the GPU
+(``read_level_row`` over Engine.read_votes) or, in rule-compatible mode, from the text dumps (``votes_from_dump_index``).
+Like the reference, a read that is long enough to have k-mers and contains anything but upper-case ACGT is an error.
 """
 from __future__ import annotations
 
 import argparse
 import os
+import random
 import sys
 from typing import List, Sequence
 
@@ -70,6 +77,54 @@ def confusion_from_masks(pivot_counts: Sequence[np.ndarray], pivot_masks: Sequen
         matrix.append(r)
         matrix_u.append(u)
     return matrix, matrix_u
+
+
+# ---- read level (experiment type 6) ---------------------------------------------------------------------
+def split_reads(text: bytes) -> List[bytes]:
+    """The reads of a ``pivot_{p}.fa`` file as the reference sees them (merge_lists.py:150-156): ``readlines()``, lines
+    containing '>' are skipped, every other line -- stripped -- is one read (an empty line is a read without k-mers)."""
+    lines = text.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()
+    return [ln.strip() for ln in lines if b">" not in ln]
+
+
+def check_reads(reads: Sequence[bytes], k: int) -> None:
+    """The reference raises KeyError (rev_comp_dict / the pivot dictionary) for a k-mer with anything but ACGT."""
+    ok = frozenset(b"ACGT")
+    for i, r in enumerate(reads):
+        if len(r) >= k and not ok.issuperset(r):
+            raise KeyError(f"read {i + 1} contains a symbol other than upper-case ACGT (the reference's read-level code fails on it)")
+
+
+def read_level_row(votes: np.ndarray, num_datasets: int) -> list:
+    """One pivot's confusion-matrix row from the per-read votes (float64 [n_reads, num_datasets]): argmax per read,
+    ties drawn exactly like merge_lists.py:176-178 (one random.choice per read over the array of maximal indexes)."""
+    row = [0] * (num_datasets + 1)
+    for v in np.asarray(votes, dtype=np.float64).reshape(-1, num_datasets):
+        max_indexes = np.where(v == max(v.tolist()))[0]
+        row[int(random.choice(max_indexes))] += 1
+    return row
+
+
+def votes_from_dump_index(reads: Sequence[bytes], k: int, index: dict, member: np.ndarray, num_datasets: int) -> np.ndarray:
+    """Rule-compatible mode: the reference's loop (merge_lists.py:157-174) over Python ints instead of strings.
+    index: canonical k-mer value -> row of `member` (bool [n, num_datasets])."""
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    out = np.zeros((len(reads), num_datasets), dtype=np.float64)
+    n_match = member.sum(axis=1)
+    for r, read in enumerate(reads):
+        votes = [0] * num_datasets
+        for i in range(0, len(read) - k + 1):
+            kmer = read[i:i + k]
+            rc = kmer.translate(comp)[::-1]
+            row = index[int(min(kmer, rc).translate(_TO_BASE4), 4)]          # KeyError like the reference's dictionary
+            if n_match[row]:
+                w = 1 / int(n_match[row])
+                for d in np.flatnonzero(member[row]):
+                    votes[d] += w
+        out[r] = votes
+    return out
 
 
 def calculate_accuracy_values(confusion_matrix, num_datasets: int, k) -> List[list]:
@@ -124,10 +179,11 @@ def read_dump(path: str):
     return keys, np.asarray(counts, dtype=np.int64)
 
 
-def confusion_from_dumps(pivot_files: Sequence[str], intersect_files: Sequence[str], num_datasets: int):
+def confusion_from_dumps(pivot_files: Sequence[str], intersect_files: Sequence[str], num_datasets: int, reads_prefix: str = None, k: int = 0):
+    """reads_prefix (the -r argument, used as a string prefix like the reference does): read level."""
     matrix, matrix_u = [], []
     at = 0
-    for pf in pivot_files:
+    for p, pf in enumerate(pivot_files):
         keys, counts = read_dump(pf)
         index = {x: i for i, x in enumerate(keys)}
         member = np.zeros((len(keys), num_datasets), dtype=bool)
@@ -138,14 +194,20 @@ def confusion_from_dumps(pivot_files: Sequence[str], intersect_files: Sequence[s
                 if i is not None:
                     member[i, d] = True
             at += 1
-        r, u = confusion_rows(counts, member, num_datasets)
+        if reads_prefix is None:
+            r, u = confusion_rows(counts, member, num_datasets)
+        else:
+            with open(f"{reads_prefix}pivot_{p + 1}.fa", "rb") as fd:
+                reads = split_reads(fd.read())
+            r = read_level_row(votes_from_dump_index(reads, k, index, member, num_datasets), num_datasets)
+            u = list(r)
         matrix.append(r)
         matrix_u.append(u)
     return matrix, matrix_u
 
 
 def main(argv=None) -> int:
-    ap = argparse.ArgumentParser(description="merge k-mer lists into a confusion matrix (experiment type 4, feature level)")
+    ap = argparse.ArgumentParser(description="merge k-mer lists into a confusion matrix (experiment types 4 and 6)")
     ap.add_argument("-n", "--num", dest="num_datasets", required=True, type=int)
     ap.add_argument("-p", "--pivot_list", dest="pivot_filelist", required=True)
     ap.add_argument("-i", "--intersect_list", dest="intersect_list", required=True)
@@ -153,9 +215,6 @@ def main(argv=None) -> int:
     ap.add_argument("-k", "--k_value", dest="k", required=True)
     ap.add_argument("-r", "--read-level", dest="read_level", nargs=1)
     a = ap.parse_args(argv)
-    if a.read_level is not None:
-        print("Error: read-level analysis is not provided by khoice-b200 (see module docstring).", file=sys.stderr)
-        return 1
     if a.num_datasets <= 0:
         print("Error: The number of datasets needs to be positive integer.")
         return 1
@@ -170,7 +229,11 @@ def main(argv=None) -> int:
         if not os.path.isfile(f):
             print(f"Error: At least one of the file paths in the file lists is not valid ({f})")
             return 1
-    matrix, matrix_u = confusion_from_dumps(lists[0], lists[1], a.num_datasets)
+    try:
+        matrix, matrix_u = confusion_from_dumps(lists[0], lists[1], a.num_datasets, a.read_level[0] if a.read_level is not None else None, int(a.k))
+    except KeyError as e:
+        print(f"Error: {e}", file=sys.stderr)
+        return 1
     write_outputs(a.output_path, a.k, matrix, matrix_u, a.num_datasets)
     return 0
 

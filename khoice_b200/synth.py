@@ -218,3 +218,66 @@ def write_dataset_type4(cfg: SynthConfig, work_root: str, compresslevel: int = 1
         if not out_pivot:
             with gzip.open(os.path.join(d, f"pivot_{g}.fna.gz"), "wb", compresslevel=compresslevel) as fd:
                 fd.write(pivot)
+
+
+# ---- experiment type 6: simulated reads of the pivot genomes -------------------------------------------------------
+def _clean_sequence(fasta: bytes) -> np.ndarray:
+    """Upper-case ACGT symbols of a FASTA text, records joined (what a read simulator samples from); every other
+    symbol (N runs, IUPAC codes) is dropped."""
+    a = np.frombuffer(fasta, dtype=np.uint8)
+    n = a.size
+    is_gt, is_nl = a == ord(">"), a == 10
+    ev = np.where(is_gt, 2, np.where(is_nl, 1, 0)).astype(np.int8)
+    idx = np.where(ev > 0, np.arange(n), -1)
+    last = np.maximum.accumulate(idx)
+    in_hdr = np.zeros(n, dtype=bool)
+    has = last >= 0
+    in_hdr[has] = ev[last[has]] == 2
+    seq = (a[~in_hdr & ~is_nl] & 0xDF).astype(np.uint8)
+    return seq[np.isin(seq, np.frombuffer(b"ACGT", np.uint8))]
+
+
+_COMP = np.zeros(256, dtype=np.uint8)
+_COMP[np.frombuffer(b"ACGT", np.uint8)] = np.frombuffer(b"TGCA", np.uint8)
+
+
+def make_reads(cfg: SynthConfig, group: int, read_type: str, n_reads: int = 200) -> bytes:
+    """Stand-in for the reference's read simulators (ART / PBSIM2 in prepare_data.smk; not available here): reads of the
+    pivot genome of ``group`` -- the last genome of the group -- as the single-line FASTA the reference's
+    ``pivot_{n}_subset.fa`` files are (src/merge_lists.py:149-156 treats every line without '>' as one read).
+    illumina: 150 bp, 0.5 % substitutions; ont: 600-3000 bp, 6 % substitutions; both strands; upper-case ACGT only
+    (the reference's read-level code raises KeyError on anything else)."""
+    if read_type not in ("illumina", "ont"):
+        raise ValueError(read_type)
+    rng = _rng(cfg.seed + 7_000_000 + 1000 * group + (0 if read_type == "illumina" else 1))
+    seq = _clean_sequence(make_genome(cfg, group, cfg.genomes_per_group))
+    out = []
+    for i in range(n_reads):
+        ln = 150 if read_type == "illumina" else int(rng.integers(600, 3001))
+        ln = min(ln, seq.size)
+        s = int(rng.integers(0, seq.size - ln + 1))
+        r = seq[s:s + ln].copy()
+        r = _substitute(r, rng, 0.005 if read_type == "illumina" else 0.06)
+        if rng.random() < 0.5:
+            r = _COMP[r[::-1]]
+        out.append(f">pivot_{group}_{read_type}_{i + 1}\n".encode() + r.tobytes() + b"\n")
+    return b"".join(out)
+
+
+def write_dataset_type6(cfg: SynthConfig, work_root: str, n_reads: int = 200, compresslevel: int = 1) -> None:
+    """Experiment type 6 layout (exp_type_6.smk:31-57): ``exp6_input/rest_of_set/dataset_{n}/*.fna.gz``,
+    ``exp6_input/pivot/pivot_{n}.fna.gz`` and the two read files ``exp6_input/pivot_reads_subset/{illumina,ont}/pivot_{n}.fa``."""
+    os.makedirs(os.path.join(work_root, "exp6_input", "pivot"), exist_ok=True)
+    for rt in ("illumina", "ont"):
+        os.makedirs(os.path.join(work_root, "exp6_input", "pivot_reads_subset", rt), exist_ok=True)
+    for g in range(1, cfg.n_groups + 1):
+        d = os.path.join(work_root, "exp6_input", "rest_of_set", f"dataset_{g}")
+        os.makedirs(d, exist_ok=True)
+        for i in range(1, cfg.genomes_per_group):
+            with gzip.open(os.path.join(d, genome_name(g, i) + ".fna.gz"), "wb", compresslevel=compresslevel) as fd:
+                fd.write(make_genome(cfg, g, i))
+        with gzip.open(os.path.join(work_root, "exp6_input", "pivot", f"pivot_{g}.fna.gz"), "wb", compresslevel=compresslevel) as fd:
+            fd.write(make_genome(cfg, g, cfg.genomes_per_group))
+        for rt in ("illumina", "ont"):
+            with open(os.path.join(work_root, "exp6_input", "pivot_reads_subset", rt, f"pivot_{g}.fa"), "wb") as fd:
+                fd.write(make_reads(cfg, g, rt, n_reads))

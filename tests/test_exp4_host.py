@@ -55,10 +55,3 @@ def test_merge_lists_cli_matches_reference_program(oracle, tmp_path):
             a = merge_lists.confusion_from_masks(counts, masks, G)
             b = merge_lists.confusion_from_dumps(pl, il, G)
             assert a == b
-
-
-def test_read_level_is_refused(tmp_path):
-    from khoice_b200 import merge_lists
-    (tmp_path / "l.txt").write_text("")
-    assert merge_lists.main(["-p", str(tmp_path / "l.txt"), "-i", str(tmp_path / "l.txt"), "-o", str(tmp_path) + "/", "-n", "2", "-k", "7",
-                             "-r", str(tmp_path)]) == 1
