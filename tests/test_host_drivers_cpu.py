@@ -159,3 +159,49 @@ def test_pipeline4_fused_on_oracle_engine_matches_reference_merge_lists(tmp_path
         assert open(os.path.join(root, pipeline4.P_FINAL)).read() == cat
         fl = open(os.path.join(root, f"filelists_type_4/k_{ks[0]}/intersections_filelist.txt")).read().splitlines()
         assert len(fl) == case["n_groups"] ** 2 and fl[0].startswith(os.path.abspath(root))
+
+
+class OracleEngine6(OracleEngine):
+    """+ Engine.read_votes for pipeline6, as the reference's own loop over the stand-in's tables."""
+
+    def read_votes(self, reads, k, pivot_keys, n_pivot, masks, n_groups):
+        from khoice_b200 import merge_lists
+        keys = pivot_keys.keys
+        as_int = [int(x) for x in keys] if keys.ndim == 1 else [(int(h) << 64) | int(l) for l, h in keys]
+        member = np.zeros((n_pivot, n_groups), dtype=bool)
+        m = np.asarray(masks, dtype=np.uint64).reshape(n_pivot, -1)
+        for d in range(n_groups):
+            member[:, d] = (m[:, d // 64] >> np.uint64(d % 64)) & np.uint64(1)
+        votes = merge_lists.votes_from_dump_index(reads, k, {x: i for i, x in enumerate(as_int)}, member, n_groups)
+        return votes, np.zeros(len(reads), np.uint32)
+
+
+def test_pipeline6_fused_on_oracle_engine_matches_reference_merge_lists(tmp_path):
+    """Experiment type 6 driver (layout, file lists, per-(read type, k) seeding, final concatenation) without a GPU."""
+    from khoice_b200 import pipeline6, synth
+    import make_golden_exp6 as G6
+    cases = json.load(open(os.path.join(GOLDEN, "exp6_cases.json")))["cases"]
+    c, case = 1, cases[1]
+    cfg, _, reads = G6.inputs_of(case)
+    root = str(tmp_path / "w6")
+    synth.write_dataset_type6(cfg, root, n_reads=case["n_reads"])
+    for rt in G6.READ_TYPES:
+        for p in range(case["n_groups"]):
+            with open(os.path.join(root, pipeline6.p_reads(rt, p + 1)), "wb") as fd:
+                fd.write(reads[rt][p])
+    ks = [str(k) for k in case["k_values"]]
+    rep = pipeline6.run_fused(root, case["n_groups"], ks, engine=OracleEngine6(), seed_fn=lambda rt, k: G6.seed_of(c, rt, k))
+    assert rep["exp_type"] == 6 and rep["level"] == "read"
+    for rt in G6.READ_TYPES:
+        for k in ks:
+            got = open(os.path.join(root, f"exp6_accuracies/{rt}/confusion_matrix/k_{k}_confusion_matrix.txt"), "rb").read()
+            assert got == open(os.path.join(GOLDEN, f"exp6_case{c}_{rt}_k{k}_confusion_matrix.txt"), "rb").read(), (rt, k)
+            got = open(os.path.join(root, f"exp6_accuracies/{rt}/values/k_{k}_accuracy_values.csv"), "rb").read()
+            assert got == open(os.path.join(GOLDEN, f"exp6_case{c}_{rt}_k{k}_accuracy_values.csv"), "rb").read(), (rt, k)
+        final = open(os.path.join(root, pipeline6.p_final(1, rt))).read()
+        names = sorted(os.listdir(os.path.join(root, f"exp6_accuracies/{rt}/values")))
+        assert final == pipeline6.HEADER + "".join(open(os.path.join(root, f"exp6_accuracies/{rt}/values", f)).read() for f in names)
+        fl = open(os.path.join(root, f"exp6_filelists/k_{ks[0]}/{rt}/intersections_filelist.txt")).read().splitlines()
+        assert len(fl) == case["n_groups"] ** 2 and fl[0].startswith(os.path.abspath(root)) and f"/{rt}/intersection/pivot_1/" in fl[0]
+    assert os.path.exists(os.path.join(root, pipeline6.p_union_hist(ks[0], 1)))
+    assert "exp6_genome_sets/rest_of_set" in open(os.path.join(root, pipeline6.p_ops(ks[0], 2))).read()
