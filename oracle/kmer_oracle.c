@@ -87,8 +87,9 @@ KO_API void ko_histogram(const uint32_t *counts, size_t n, uint64_t *hist, size_
  *   across_hist      : (nbins+1) uint64 = step_8 histogram
  *   stats[0..4]      : total symbols, total valid k-mers, sum of per-genome distinct (S_G summed),
  *                      sum of per-group distinct (S), overall distinct (D)
- * Parallelism: OpenMP over genomes, then over groups (the reference gets its parallelism from
- * snakemake --cores running independent rule instances, exp_type_1.smk:156-191).  Returns 0 or <0. */
+ * Parallelism: OpenMP over genomes for the per-genome sets, then every union on all cores by key range (the reference gets
+ * its parallelism from snakemake --cores running independent rule instances, exp_type_1.smk:156-191, and from KMC's own
+ * threads).  Returns 0 or <0. */
 KO_API int ko_exp1(const uint8_t *const *bufs, const size_t *lens, const int32_t *group_of, int n_genomes,
                    int n_groups, int k, uint32_t cs, size_t nbins, uint64_t *within_hist,
                    uint64_t *across_hist, uint64_t *stats)
@@ -118,18 +119,24 @@ KO_API int ko_exp1(const uint8_t *const *bufs, const size_t *lens, const int32_t
     }
     if (err) goto done;
 
-    /* step_3 + step_4 (+ step_6): per-group union-sum, histogram, group set */
-#pragma omp parallel for schedule(dynamic, 1)
+    /* step_3 + step_4 (+ step_6): per-group union-sum, histogram, group set.  One group after the other, every group on all
+     * cores (key-range parallel merge): the sampled workloads have few groups, and a loop over groups would leave cores idle */
     for (int g = 0; g < n_groups; g++) {
         size_t tot = 0;
-        for (int i = 0; i < n_genomes; i++) if (group_of[i] == g) tot += (size_t)gcnt[i];
+        int m = 0;
+        for (int i = 0; i < n_genomes; i++) if (group_of[i] == g) { tot += (size_t)gcnt[i]; m++; }
         uint8_t *cat = (uint8_t *)malloc((tot + 1) * W);
         uint32_t *cnts = (uint32_t *)malloc((tot + 1) * sizeof(uint32_t));
-        if (!cat || !cnts) { err = -1; free(cat); free(cnts); continue; }
-        size_t off = 0;
+        void **members = (void **)malloc((size_t)(m + 1) * sizeof(void *));
+        int64_t *msize = (int64_t *)malloc((size_t)(m + 1) * sizeof(int64_t));
+        if (!cat || !cnts || !members || !msize) { err = -1; free(cat); free(cnts); free(members); free(msize); break; }
+        m = 0;
         for (int i = 0; i < n_genomes; i++)
-            if (group_of[i] == g) { memcpy(cat + off * W, gset[i], (size_t)gcnt[i] * W); off += (size_t)gcnt[i]; }
-        int64_t nd = ko_union_sum(cat, tot, k, cnts, cs);
+            if (group_of[i] == g) { members[m] = gset[i]; msize[m] = gcnt[i]; m++; }
+        int64_t nd = k <= 32 ? ko_union_sum_par_64((uint64_t *const *)members, msize, m, k, cs, (uint64_t *)cat, cnts)
+                             : ko_union_sum_par_128((unsigned __int128 *const *)members, msize, m, k, cs, (unsigned __int128 *)cat, cnts);
+        free(members);
+        free(msize);
         if (nd < 0) { err = -1; nd = 0; }
         ko_histogram(cnts, (size_t)nd, within_hist + (size_t)g * (nbins + 1), nbins);
         free(cnts);
@@ -145,9 +152,8 @@ KO_API int ko_exp1(const uint8_t *const *bufs, const size_t *lens, const int32_t
         uint8_t *cat = (uint8_t *)malloc((tot + 1) * W);
         uint32_t *cnts = (uint32_t *)malloc((tot + 1) * sizeof(uint32_t));
         if (!cat || !cnts) { err = -1; free(cat); free(cnts); goto done; }
-        size_t off = 0;
-        for (int g = 0; g < n_groups; g++) { memcpy(cat + off * W, grpset[g], (size_t)grpcnt[g] * W); off += (size_t)grpcnt[g]; }
-        int64_t nd = ko_union_sum(cat, tot, k, cnts, cs);
+        int64_t nd = k <= 32 ? ko_union_sum_par_64((uint64_t *const *)grpset, grpcnt, n_groups, k, cs, (uint64_t *)cat, cnts)
+                             : ko_union_sum_par_128((unsigned __int128 *const *)grpset, grpcnt, n_groups, k, cs, (unsigned __int128 *)cat, cnts);
         if (nd < 0) { err = -1; nd = 0; }
         ko_histogram(cnts, (size_t)nd, across_hist, nbins);
         if (stats) {
