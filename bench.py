@@ -170,16 +170,11 @@ def run_reference(args):
     per_genome = max(time.time() - t0, 1e-3)
     total_steps = args.steps + args.warmup
     budget = 150.0 / max(total_steps, 1)                         # seconds per step
-    n_groups = 2
-    # per-genome work parallelises over min(cores, genomes); the group stage over min(cores, groups)
-    est = lambda g: per_genome * (n_groups * g / min(cores, n_groups * g)) * 2.2
-    genomes = 2
-    while genomes < wl["genomes"] and est(genomes + 1) < budget:
-        genomes += 1
+    n_groups, genomes = sample_shape(wl, per_genome, cores, budget)
     cfg = synth.SynthConfig(n_groups=n_groups, genomes_per_group=genomes, genome_len=wl["genome_len"])
-    groups = generate_groups(cfg, [1, 2], min(cores, 2))
-    flat = [f for g in (1, 2) for f in groups[g]]
-    gid = [0] * genomes + [1] * genomes
+    groups = generate_groups(cfg, list(range(1, n_groups + 1)), min(cores, n_groups))
+    flat = [f for g in range(1, n_groups + 1) for f in groups[g]]
+    gid = [g for g in range(n_groups) for _ in range(genomes)]
     bases = sum(synth.count_bases(f) for f in flat)
     for _ in range(args.warmup):
         O.exp1(flat, gid, n_groups, k)
@@ -200,6 +195,20 @@ def run_reference(args):
     return 0
 
 
+def sample_shape(wl, per_genome, cores, seconds):
+    """(groups, genomes per group) of the bounded CPU sample: the workload's own group size if the time allows, at most 4
+    groups (about 20 GB of host memory at 50 x 5 Mbp).  per_genome = seconds of the whole oracle chain for ONE genome on one
+    thread; the per-genome stage parallelises over genomes and every union over key ranges (oracle/ko_body.inc), measured
+    at ~0.65 x per_genome x genomes / cores on 16 cores -- 0.8 keeps a margin."""
+    est = lambda ng, g: per_genome * max(ng * g / cores, 1.0) * 0.8
+    n_groups, genomes = 2, 2
+    while genomes < wl["genomes"] and est(n_groups, genomes + 1) < seconds:
+        genomes += 1
+    while genomes == wl["genomes"] and n_groups < min(4, wl["groups_per_gpu"]) and est(n_groups + 1, genomes) < seconds:
+        n_groups += 1
+    return n_groups, genomes
+
+
 def cpu_baseline(wl, seconds=20.0):
     from khoice_b200 import synth
     from oracle import oracle as O
@@ -211,16 +220,13 @@ def cpu_baseline(wl, seconds=20.0):
     t0 = time.time()
     O.exp1([probe], [0], 1, k)
     per_genome = max(time.time() - t0, 1e-3)
-    n_groups = 2
-    genomes = 2
-    while genomes < wl["genomes"] and per_genome * (n_groups * (genomes + 1) / min(cores, n_groups * (genomes + 1))) * 2.2 < seconds:
-        genomes += 1
+    n_groups, genomes = sample_shape(wl, per_genome, cores, seconds)
     cfg = synth.SynthConfig(n_groups=n_groups, genomes_per_group=genomes, genome_len=wl["genome_len"])
-    groups = generate_groups(cfg, [1, 2], 2)
-    flat = [f for g in (1, 2) for f in groups[g]]
+    groups = generate_groups(cfg, list(range(1, n_groups + 1)), min(cores, n_groups))
+    flat = [f for g in range(1, n_groups + 1) for f in groups[g]]
     bases = sum(synth.count_bases(f) for f in flat)
     t0 = time.time()
-    O.exp1(flat, [0] * genomes + [1] * genomes, n_groups, k)
+    O.exp1(flat, [g for g in range(n_groups) for _ in range(genomes)], n_groups, k)
     dt = time.time() - t0
     return {"value": bases / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"CPU oracle (oracle/kmer_oracle.c, OpenMP) on {n_groups} groups x {genomes} genomes x {wl['genome_len']} bp, k={k}: "
