@@ -123,3 +123,39 @@ def test_rule_chain_on_kmc_layout_databases(engine, oracle, work_roots, tmp_path
             a, b = kmcdb.read_db(p3), kmcdb.read_db(os.path.join(ref_root, pipeline.p_step3(k, num)))
             assert np.array_equal(a.keys, b.keys) and np.array_equal(a.counts, b.counts)
         assert filecmp.cmp(os.path.join(root, pipeline.p_step8(k)), os.path.join(ref_root, pipeline.p_step8(k)), shallow=False)
+
+
+def test_unmodified_rule_chain_through_the_worker(work_roots, tmp_path):
+    """Every rule instance is its own `sh -c "kmc ..."` process, as under Snakemake, but the shims forward to ONE long-lived
+    worker (khoice_b200/worker.py) instead of creating a CUDA context each: same files, same CSV bytes."""
+    import subprocess, sys, time
+    from khoice_b200 import pipeline, synth
+    cfg, roots = work_roots
+    root = str(tmp_path / "via_worker")
+    synth.write_dataset(cfg, root)
+    sock = str(tmp_path / "khb.sock")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    srv = subprocess.Popen([sys.executable, "-m", "khoice_b200.worker", "--socket", sock], cwd=repo, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    try:
+        assert "ready" in srv.stdout.readline()
+        os.environ["KHB_WORKER_SOCKET"] = sock
+        t0 = time.time()
+        rep = pipeline.run_rules(root, cfg.n_groups, K_VALUES[:3], subprocess_mode=True)
+        dt = time.time() - t0
+    finally:
+        os.environ.pop("KHB_WORKER_SOCKET", None)
+        subprocess.run([sys.executable, "-m", "khoice_b200.worker", "--socket", sock, "--stop"], cwd=repo, timeout=60)
+        out, err = srv.communicate(timeout=60)
+    assert srv.returncode == 0 and f"served {rep['jobs_run']} requests" in out, out + err
+    assert rep["jobs_run"] == 3 * (2 * cfg.n_groups * cfg.genomes_per_group + 3 * cfg.n_groups + 2)   # per k: kmc + set_counts per genome; union, histogram, set per group; across union + histogram
+    ref = str(tmp_path / "in_process")
+    synth.write_dataset(cfg, ref)
+    from khoice_b200.engine import Engine
+    eng = Engine(0)
+    try:
+        pipeline.run_rules(ref, cfg.n_groups, K_VALUES[:3], engine=eng)
+    finally:
+        eng.close()
+    for f in (pipeline.P_STEP5, pipeline.P_STEP9):
+        assert filecmp.cmp(os.path.join(root, f), os.path.join(ref, f), shallow=False), f
+    print(f"{rep['jobs_run']} rule processes through the worker in {dt:.1f} s ({dt / rep['jobs_run'] * 1e3:.0f} ms each)")
