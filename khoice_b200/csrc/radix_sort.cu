@@ -468,8 +468,7 @@ static int sort_variant()
 // tile size (keys) of the scatter-pass variant `v` for key width W
 static u32 variant_tile(int v, size_t W)
 {
-    if (W == 16) return 512 * 6;
-    (void)v;
+    if (W == 16) return v == 31 ? 512 * 6 : 512 * 8;
     return 512 * 12;
 }
 
@@ -503,9 +502,13 @@ int dispatch_passes<Key128>(khb_ctx *ctx, int v, Key128 *src, Key128 *dst, unsig
                             const u64 *d_tile, int nseg, int npass, int first_bit, u64 ntiles, u64 n_keys, const u32 *d_hist,
                             u64 *d_lb, u32 *d_ticket)
 {
-    (void)v;
-    if (psrc) return launch_passes<Key128, 512, 6, 2, 2, 1>(KHB_PASS_ARGS);
-    return launch_passes<Key128, 512, 6, 2, 2>(KHB_PASS_ARGS);
+    if (v == 31) {  // 6 keys per thread (3072-key tiles): the earlier default, 3.4 % slower per pass (k = 47: 146.4 vs 141.5 ms per step)
+        if (psrc) return launch_passes<Key128, 512, 6, 2, 2, 1>(KHB_PASS_ARGS);
+        return launch_passes<Key128, 512, 6, 2, 2>(KHB_PASS_ARGS);
+    }
+    // 8 keys per thread: 4096-key tiles, 2 CTAs x 97 KB of shared memory per SM, 64 registers without spills
+    if (psrc) return launch_passes<Key128, 512, 8, 2, 2, 1>(KHB_PASS_ARGS);
+    return launch_passes<Key128, 512, 8, 2, 2>(KHB_PASS_ARGS);
 }
 #undef KHB_PASS_ARGS
 
