@@ -418,7 +418,7 @@ def main():
                     "note": "steps are pipelined like a stream of jobs: the H2D copy of a step's first group overlaps the previous step's last group and "
                             "across-group stage; every step's text is copied inside the timed region"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "onesweep_kernel<Key64,12> (one 8-bit radix pass)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "onesweep_kernel<Key64,14> (one 8-bit radix pass)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "traffic": (ratio * per_launch_alg) if ratio else None, "algorithmic_bytes_per_launch": per_launch_alg,
                          "launches": osw["launches"], "avg_launch_ms": osw["ms"] / max(osw["launches"], 1), "peak_source": peak_src},

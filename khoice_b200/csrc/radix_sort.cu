@@ -469,7 +469,10 @@ static int sort_variant()
 static u32 variant_tile(int v, size_t W)
 {
     if (W == 16) return v == 31 ? 512 * 6 : 512 * 8;
-    return 512 * 12;
+    // 64-bit keys: 14 keys per thread by default (7168-key tiles, 2 CTAs per SM); 12 for the tuning variants listed in
+    // dispatch_passes, 16 for variant 41 (112 bytes of spills, measured slower)
+    if (v == 41) return 512 * 16;
+    return (v == 0 || v == 1 || v == 12 || v == 13 || v == 18 || v == 42) ? 512 * 12 : 512 * 14;
 }
 
 template <typename Key>
@@ -484,16 +487,20 @@ int dispatch_passes<Key64>(khb_ctx *ctx, int v, Key64 *src, Key64 *dst, unsigned
                            u64 *d_lb, u32 *d_ticket)
 {
     if (psrc) {  // keys + 16-bit payload
+        if (v == 41) return launch_passes<Key64, 512, 16, 2, 2, 1>(KHB_PASS_ARGS);
         if (v == 13) return launch_passes<Key64, 512, 12, 2, 4, 1>(KHB_PASS_ARGS);
         if (v == 12) return launch_passes<Key64, 512, 12, 2, 3, 1>(KHB_PASS_ARGS);
-        return launch_passes<Key64, 512, 12, 2, 2, 1>(KHB_PASS_ARGS);
+        if (v == 0 || v == 1 || v == 18 || v == 42) return launch_passes<Key64, 512, 12, 2, 2, 1>(KHB_PASS_ARGS);
+        return launch_passes<Key64, 512, 14, 2, 2, 1>(KHB_PASS_ARGS);  // default: 82.5 ms per config-2 step against 83.6 with 12 keys per thread
     }
     switch (v) {
+    case 41: return launch_passes<Key64, 512, 16, 2, 2>(KHB_PASS_ARGS);
+    case 42: return launch_passes<Key64, 512, 12, 2, 2>(KHB_PASS_ARGS);         // the default's ranking with 12 keys per thread
     case 0: return launch_passes<Key64, 512, 12, 2, 0>(KHB_PASS_ARGS);         // MATCH.ANY (1.46 TB/s: ~1 MATCH.ANY per 100 cycles per SM)
     case 1: return launch_passes<Key64, 512, 12, 2, 1>(KHB_PASS_ARGS);         // eight ballots (2.33 TB/s: ALU-bound, 3.9 warp-instr/key)
     case 13: return launch_passes<Key64, 512, 12, 2, 4>(KHB_PASS_ARGS);        // every 3rd round by ballots, the others by atomicOr (2.64 TB/s)
     case 18: return launch_passes<Key64, 512, 12, 2, 2, 0, 2>(KHB_PASS_ARGS);  // early count + early look-back (2.45 TB/s)
-    default: return launch_passes<Key64, 512, 12, 2, 2>(KHB_PASS_ARGS);        // shared-memory atomicOr peer masks (2.57 TB/s) -- default
+    default: return launch_passes<Key64, 512, 14, 2, 2>(KHB_PASS_ARGS);        // shared-memory atomicOr peer masks, 14 keys per thread -- default
     }
 }
 
