@@ -45,6 +45,13 @@ class CudaAdapter:
     def group(self, files: Sequence, k: int, nbins: int):
         return self.eng.group_from_fasta(files, k, nbins=nbins, keep_set=True)
 
+    def pack_group(self, files: Sequence):
+        """K1 once per group; the 2-bit stream stays in HBM for the k sweep (khb_pack_group)."""
+        return self.eng.pack_group(files)
+
+    def group_from_packed(self, packed, k: int, nbins: int):
+        return self.eng.group_from_packed(packed, k, nbins=nbins, keep_set=True)
+
     def export_partitions(self, k: int, world: int) -> Tuple[torch.Tensor, List[int]]:
         """Retained group sets, grouped by destination rank.  Returns (int64 tensor of words, words per rank)."""
         w = key_words(k)
@@ -81,16 +88,23 @@ def exchange_and_count(adapter, k: int, n_groups_total: int, nbins: int = COUNTE
     world = dist.get_world_size(group)
     send, send_words = adapter.export_partitions(k, world)
     dev = send.device
+    # NCCL moves device tensors; any other backend (gloo: CPU tests, two processes sharing one GPU) goes through host copies
+    wire = dev if dist.get_backend(group) == "nccl" else torch.device("cpu")
     # sizes first (one tiny all-to-all), then the payload
-    s = torch.tensor(send_words, dtype=torch.int64, device=dev)
-    r = torch.empty(world, dtype=torch.int64, device=dev)
+    s = torch.tensor(send_words, dtype=torch.int64, device=wire)
+    r = torch.empty(world, dtype=torch.int64, device=wire)
     dist.all_to_all_single(r, s, group=group)
     recv_words = [int(x) for x in r.tolist()]
-    recv = adapter.new_tensor(sum(recv_words))
-    dist.all_to_all_single(recv, send, output_split_sizes=recv_words, input_split_sizes=send_words, group=group)
+    if wire == dev:
+        recv = adapter.new_tensor(sum(recv_words))
+        dist.all_to_all_single(recv, send, output_split_sizes=recv_words, input_split_sizes=send_words, group=group)
+    else:
+        recv_w = torch.empty(sum(recv_words), dtype=torch.int64)
+        dist.all_to_all_single(recv_w, send.to(wire), output_split_sizes=recv_words, input_split_sizes=send_words, group=group)
+        recv = recv_w.to(dev)
     adapter.import_keys(recv, k, n_groups_total)
     hist, st = adapter.across(nbins)
-    h = torch.from_numpy(np.ascontiguousarray(hist).astype(np.int64)).to(dev)
+    h = torch.from_numpy(np.ascontiguousarray(hist).astype(np.int64)).to(wire)
     dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
     info = {"send_words": sum(send_words), "recv_words": sum(recv_words), "local_distinct": int(st.get("distinct", 0)),
             "across_ms": float(st.get("ms_total", 0.0)), "send_words_per_rank": list(send_words), "exchange": "nccl"}
@@ -154,6 +168,12 @@ class AcrossExchanger:
             self.mode = "nccl"
             return
         self.ready = True
+
+    def set_k(self, k: int):
+        """Reuse the exchanger (and its mapped regions) for another k of the same key width (a k sweep)."""
+        if key_words(k) != key_words(self.k):
+            raise ValueError(f"exchanger set up for {8 * key_words(self.k)}-byte keys, k={k} needs {8 * key_words(k)}")
+        self.k = k
 
     def begin(self):
         if self.ready:

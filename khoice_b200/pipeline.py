@@ -150,6 +150,102 @@ def run_fused(work_root: str, num_datasets: int, k_values: Optional[Sequence] = 
     return report
 
 
+# ---- fused mode on several GPUs ------------------------------------------------------------------------
+def run_fused_distributed(work_root: str, num_datasets: int, k_values: Optional[Sequence] = None, adapter=None, exchange: str = "peer",
+                          stubs: bool = True, report_path: Optional[str] = None) -> Dict:
+    """``run_fused`` under ``torchrun`` (one process per GPU, ``torch.distributed`` already initialised or initialisable from
+    the environment): groups are dealt to the ranks round-robin (khoice_b200/dist.py), every rank inflates and packs only
+    its own groups once and sweeps k over them; per k the across-group stage goes through ``dist.AcrossExchanger`` (peer-
+    memory push, or ``exchange="nccl"``), the per-group histograms are all-reduced, and rank 0 writes the step_4 / step_8
+    files, the stubs and the step_5 / step_9 CSVs -- byte-identical to a single-GPU run.  ``adapter``: tests pass a
+    stand-in; the product adapter is dist.CudaAdapter on this rank's GPU."""
+    import torch
+    import torch.distributed as tdist
+    from . import dist as kd
+    k_values = [str(k) for k in (k_values or DEFAULT_K_VALUES)]
+    own_eng = None
+    if not tdist.is_initialized():
+        kd.init_from_env()
+    rank, world = tdist.get_rank(), tdist.get_world_size()
+    if adapter is None:
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        own_eng = Engine(local)
+        adapter = kd.CudaAdapter(own_eng, torch.device("cuda", local))
+    report = {"mode": "fused-distributed", "world": world, "work_root": work_root, "num_datasets": num_datasets, "k_values": k_values, "stages": []}
+    t_start = time.time()
+    mine = kd.groups_of_rank(num_datasets, rank, world)
+    packed: Dict[int, object] = {}
+    exchangers: Dict[int, object] = {}
+    reader = None
+    ctrl = torch.device("cpu") if tdist.get_backend() != "nccl" else adapter.new_tensor(0).device
+    try:
+        if rank == 0:
+            write_complex_ops(work_root, k_values, num_datasets)
+        names = {n: genomes_of(work_root, n) for n in range(1, num_datasets + 1)}
+        zero = np.zeros(tables.HIST_ROWS + 1, dtype=np.uint64)
+        if mine:
+            reader = ingest.GroupReader({n: [os.path.join(work_root, p_genome(n, g)) for g in names[n]] for n in mine}, mine)
+        for k in k_values:
+            ki = int(k)
+            ex = exchangers.get(kd.key_words(ki))       # one exchanger (one set of mapped regions) per key width
+            if ex is None:
+                ex = exchangers[kd.key_words(ki)] = kd.AcrossExchanger(adapter, ki, num_datasets, nbins=tables.HIST_ROWS, mode=exchange)
+            ex.set_k(ki)
+            adapter.reset()
+            ex.begin()
+            within = np.zeros((num_datasets, tables.HIST_ROWS + 2), dtype=np.int64)     # last column: distinct k-mers of the group
+            for num in mine:
+                if num not in packed:
+                    packed[num] = adapter.pack_group(reader.get(num))
+                hist, st = adapter.group_from_packed(packed[num], ki, tables.HIST_ROWS)
+                ex.after_group()
+                within[num - 1, :-1] = hist.astype(np.int64)
+                within[num - 1, -1] = int(st["distinct"])
+                report["stages"].append({"k": ki, "group": num, "rank": rank, **{a: b for a, b in st.items() if isinstance(b, (int, float))}})
+            across, info = ex.finish()
+            w = torch.from_numpy(within).to(ctrl)
+            tdist.all_reduce(w, op=tdist.ReduceOp.SUM)
+            within = w.cpu().numpy()
+            d_all = torch.tensor([int(info.get("local_distinct", info.get("distinct", 0)))], dtype=torch.int64, device=ctrl)
+            if world > 1:
+                tdist.all_reduce(d_all, op=tdist.ReduceOp.SUM)      # every k-mer has exactly one owner
+            if rank == 0:
+                for num in range(1, num_datasets + 1):
+                    hist = within[num - 1, :-1].astype(np.uint64)
+                    distinct = int(within[num - 1, -1])
+                    tables.write_histogram_file(os.path.join(work_root, p_step4(k, num)), hist)
+                    if stubs:
+                        one = zero.copy()
+                        for g in names[num]:
+                            kmcdb.write_db(os.path.join(work_root, p_step1(k, num, g)), ki, None, None, zero, cli.KMC_DEFAULT_CS)
+                            kmcdb.write_db(os.path.join(work_root, p_step2(k, num, g)), ki, None, None, zero, cli.KMC_DEFAULT_CS)
+                        kmcdb.write_db(os.path.join(work_root, p_step3(k, num)), ki, None, None, hist, COUNTER_MAX, distinct)
+                        one[1] = distinct
+                        kmcdb.write_db(os.path.join(work_root, p_step6(k, num)), ki, None, None, one, COUNTER_MAX, distinct)
+                across = np.asarray(across, dtype=np.uint64)
+                tables.write_histogram_file(os.path.join(work_root, p_step8(k)), across)
+                if stubs:
+                    kmcdb.write_db(os.path.join(work_root, p_step7(k)), ki, None, None, across, COUNTER_MAX, int(d_all.item()))
+                report["stages"].append({"k": ki, "group": "across", "distinct": int(d_all.item()), "exchange": info.get("exchange", "local")})
+        if rank == 0:
+            build_tables(work_root, k_values, num_datasets)
+        for ex in exchangers.values():
+            ex.close()
+        tdist.barrier()
+    finally:
+        if reader is not None:
+            reader.close()
+        for pk in packed.values():
+            pk.free()
+        if own_eng is not None:
+            own_eng.close()
+    report["seconds"] = time.time() - t_start
+    if report_path and rank == 0:
+        with open(report_path, "w") as fd:
+            json.dump(report, fd, indent=1)
+    return report
+
+
 # ---- rule-by-rule mode (mini scheduler) --------------------------------------------------------------
 def _rule_jobs(work_root: str, k_values: Sequence[str], num_datasets: int):
     """(rule name, outputs, shell string) for every rule instance, in a valid topological order.  The
@@ -238,12 +334,18 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap.add_argument("--work-root", required=True, help="WORK_ROOT of the reference config (config/config.yaml)")
     ap.add_argument("--num-datasets", type=int, required=True, help="NUM_DATASETS")
     ap.add_argument("--k-values", default=None, help="comma separated K_VALUES (default: the reference list, Snakefile:36)")
-    ap.add_argument("--mode", choices=["fused", "rules", "rules-subprocess"], default="fused")
+    ap.add_argument("--mode", choices=["fused", "fused-dist", "rules", "rules-subprocess"], default="fused",
+                    help="fused-dist: under `torchrun --nproc-per-node N`, one rank per GPU")
+    ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer", help="fused-dist: across-group exchange route")
     ap.add_argument("--report", default=None)
     a = ap.parse_args(argv)
     ks = a.k_values.split(",") if a.k_values else None
     if a.mode == "fused":
         rep = run_fused(a.work_root, a.num_datasets, ks, report_path=a.report)
+    elif a.mode == "fused-dist":
+        rep = run_fused_distributed(a.work_root, a.num_datasets, ks, exchange=a.exchange, report_path=a.report)
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
     else:
         rep = run_rules(a.work_root, a.num_datasets, ks, subprocess_mode=a.mode == "rules-subprocess")
     print(json.dumps({k: v for k, v in rep.items() if k != "stages"}))

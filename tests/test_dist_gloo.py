@@ -229,3 +229,72 @@ def test_peer_exchange_protocol_on_stand_in_engine(tmp_path, oracle, k, world):
     _, a_ref, _ = oracle.exp1(flat, gid, n_groups, k, nbins=64)
     np.save(tmp_path / "across_ref.npy", a_ref)
     mp.spawn(_peer_worker, args=(world, _free_port(), n_groups, k, str(tmp_path)), nprocs=world, join=True)
+
+
+# ---- the distributed fused driver of the work-root pipeline (pipeline.run_fused_distributed) ---------------------------
+class _PackedTexts:
+    def __init__(self, texts):
+        self.texts = list(texts)
+
+    def free(self):
+        pass
+
+
+class PipelineOracleAdapter(PeerOracleAdapter):
+    """+ the two calls the work-root driver makes per group (pack once, count per k)."""
+
+    def pack_group(self, files):
+        return _PackedTexts(files)
+
+    def group_from_packed(self, packed, k, nbins):
+        self.k = k
+        return self.group(packed.texts, k, nbins)
+
+
+def _pipeline_worker(rank, world, port, root, shared, ks, exchange):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from khoice_b200 import dist as kd, pipeline
+    kd.init_from_env("gloo")
+    rep = pipeline.run_fused_distributed(root, 5, ks, adapter=PipelineOracleAdapter(int(ks[0]), shared), exchange=exchange)
+    assert rep["world"] == world
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,exchange", [(1, "peer"), (2, "peer"), (3, "nccl")])
+def test_distributed_work_root_driver_writes_the_single_process_files(tmp_path, oracle, world, exchange):
+    """step_4 / step_8 histogram files and the step_5 / step_9 CSVs do not depend on the number of ranks or the route."""
+    from khoice_b200 import pipeline, synth, tables
+    cfg = synth.SynthConfig(n_groups=5, genomes_per_group=3, genome_len=9_000, seed=321)
+    root = str(tmp_path / "w")
+    synth.write_dataset(cfg, root)
+    ks = ["11", "21", "25"]
+    shared = str(tmp_path / "shared")
+    os.makedirs(shared)
+    mp.spawn(_pipeline_worker, args=(world, _free_port(), root, shared, ks, exchange), nprocs=world, join=True)
+    flat, gid = [], []
+    for g in range(1, 6):
+        for i in range(1, 4):
+            flat.append(synth.make_genome(cfg, g, i))
+            gid.append(g - 1)
+    for k in ks:
+        w_ref, a_ref, _ = oracle.exp1(flat, gid, 5, int(k), nbins=tables.HIST_ROWS)
+        for num in range(1, 6):
+            got = tables.read_histogram_file(os.path.join(root, pipeline.p_step4(k, num)))
+            assert got == [int(x) for x in w_ref[num - 1][1:]], (k, num)
+        assert tables.read_histogram_file(os.path.join(root, pipeline.p_step8(k))) == [int(x) for x in a_ref[1:]], k
+    # the CSVs are those of the table builders over exactly these histogram files
+    ref_root = str(tmp_path / "ref")
+    synth.write_dataset(cfg, ref_root)
+    for k in ks:
+        for num in range(1, 6):
+            os.makedirs(os.path.dirname(os.path.join(ref_root, pipeline.p_step4(k, num))), exist_ok=True)
+            os.replace(os.path.join(root, pipeline.p_step4(k, num)), os.path.join(ref_root, pipeline.p_step4(k, num)))
+        os.makedirs(os.path.dirname(os.path.join(ref_root, pipeline.p_step8(k))), exist_ok=True)
+        os.replace(os.path.join(root, pipeline.p_step8(k)), os.path.join(ref_root, pipeline.p_step8(k)))
+    pipeline.build_tables(ref_root, ks, 5)
+    for f in (pipeline.P_STEP5, pipeline.P_STEP9) + pipeline.P_FINAL:
+        assert open(os.path.join(root, f), "rb").read() == open(os.path.join(ref_root, f), "rb").read(), f
+    assert os.path.exists(os.path.join(root, pipeline.p_step7(ks[0]) + ".kmc_pre"))

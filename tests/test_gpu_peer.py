@@ -84,3 +84,47 @@ def test_two_ranks_on_one_gpu_push_over_ipc(async_push):
             raise
     for rank, (p, (out, err)) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"peer ok {rank}" in out, out[-2000:] + err[-4000:]
+
+
+PIPELINE_SCRIPT = r"""
+import os, sys
+sys.path.insert(0, %(root)r)
+import torch.distributed as dist
+from khoice_b200 import pipeline
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rep = pipeline.run_fused_distributed(%(work)r, %(groups)d, %(ks)r, exchange=%(exchange)r)
+routes = [s["exchange"] for s in rep["stages"] if s.get("group") == "across"]
+print("pipeline ok", os.environ["RANK"], ",".join(routes))
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_distributed_work_root_driver_on_two_ranks_sharing_one_gpu(engine, tmp_path, exchange):
+    """pipeline.run_fused_distributed with the product adapter (two processes on cuda:0, gloo control plane): the step_4 /
+    step_8 files and both CSVs equal the single-process run's."""
+    import filecmp
+    from khoice_b200 import pipeline, synth
+    cfg = synth.SynthConfig(n_groups=5, genomes_per_group=3, genome_len=30_000, seed=77)
+    ks = ["13", "21", "31", "40"]
+    work, ref = str(tmp_path / "dist"), str(tmp_path / "single")
+    synth.write_dataset(cfg, work)
+    synth.write_dataset(cfg, ref)
+    pipeline.run_fused(ref, cfg.n_groups, ks, engine=engine)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = PIPELINE_SCRIPT % {"root": ROOT, "work": work, "groups": cfg.n_groups, "ks": ks, "exchange": exchange}
+    procs = [subprocess.Popen([sys.executable, "-c", script], env=dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK="0", MASTER_ADDR="127.0.0.1",
+                                                                     MASTER_PORT=str(port)), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    for r, (p, (out, err)) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"pipeline ok {r}" in out, out[-2000:] + err[-4000:]
+    if exchange == "peer":
+        assert "peer" in outs[0][0]          # after the sizing round the push is the route
+    for k in ks:
+        for num in range(1, cfg.n_groups + 1):
+            assert filecmp.cmp(os.path.join(work, pipeline.p_step4(k, num)), os.path.join(ref, pipeline.p_step4(k, num)), shallow=False), (k, num)
+        assert filecmp.cmp(os.path.join(work, pipeline.p_step8(k)), os.path.join(ref, pipeline.p_step8(k)), shallow=False), k
+    for f in (pipeline.P_STEP5, pipeline.P_STEP9) + pipeline.P_FINAL:
+        assert filecmp.cmp(os.path.join(work, f), os.path.join(ref, f), shallow=False), f
