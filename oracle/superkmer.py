@@ -1,0 +1,138 @@
+"""TEST INFRASTRUCTURE (like everything under oracle/): the reference statement of the NEXT design step named in DESIGN.md
+section 7 -- partition the k-mer windows of a genome by minimizer into bins, as super-k-mers -- so that the CUDA kernels of
+that step can be checked bit for bit from their first version on.  Nothing under khoice_b200/ uses this.
+
+Semantics of the windows are the oracle's (rules R1-R5 of SURVEY.md 8c, the reference's `kmc -fm` call sites
+/root/reference/workflow/rules/exp_type_1.smk:156-163): symbols `ACGTacgt` are valid, anything else breaks the window,
+windows never span `>` records, the k-mer value is base 4 with the first base most significant, canonical = min(k-mer,
+reverse complement).  On top of that, for a window with canonical m-mers c_0 .. c_{k-m} (m <= k <= 32 here):
+
+    minimizer hash   H = min_j  mix(c_j)            mix(x) = ((x ^ (x >> 15)) * 0x9E3779B97F4A7C15) ^ (... >> 29), 64-bit
+    bin              b = (H * 0xD6E8FEB86659FD93 mod 2^64) >> (64 - log2_bins)
+    super-k-mer      a maximal run of CONSECUTIVE windows (symbol positions i, i+1, ...) that are all valid and share b
+
+The bin is a function of the window's sequence content up to strand -- the same k-mer lands in the same bin in every
+genome and on both strands -- which is what lets a bin be counted independently of all others."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+
+U = np.uint64
+MIX_C = U(0x9E3779B97F4A7C15)
+BIN_C = U(0xD6E8FEB86659FD93)
+
+
+def mix(x: np.ndarray) -> np.ndarray:
+    x = (x ^ (x >> U(15))) * MIX_C
+    return x ^ (x >> U(29))
+
+
+def symbol_stream(fasta: bytes) -> Tuple[np.ndarray, np.ndarray]:
+    """(codes uint8 [n_sym], valid bool [n_sym]): one symbol per sequence character outside header lines (newlines and
+    carriage returns skipped) and one INVALID break symbol per '>' (so that windows never span records) -- the layout K1 packs."""
+    a = np.frombuffer(bytes(fasta), dtype=np.uint8)
+    n = a.size
+    if n == 0:
+        return np.zeros(0, np.uint8), np.zeros(0, bool)
+    is_nl = a == 10
+    # header state: a '>' opens a header only outside a header; scan events in order
+    ev_pos = np.flatnonzero((a == 62) | is_nl)
+    in_hdr = np.zeros(n, dtype=bool)
+    opens = np.zeros(n, dtype=bool)
+    state = False
+    start = 0
+    for p in ev_pos:                       # events are few (one per line); the per-byte work below is vectorised
+        if state:
+            if a[p] == 10:
+                in_hdr[start:p + 1] = True
+                state = False
+        elif a[p] == 62:
+            state, start = True, p
+            opens[p] = True
+    if state:
+        in_hdr[start:] = True
+    keep = opens | (~in_hdr & ~is_nl & (a != 13))
+    sym = a[keep]
+    code = np.full(sym.size, 255, dtype=np.uint8)
+    for ch, v in zip(b"ACGTacgt", (0, 1, 2, 3, 0, 1, 2, 3)):
+        code[sym == ch] = v
+    code[opens[keep]] = 255
+    valid = code != 255
+    code[~valid] = 0
+    return code, valid
+
+
+def _canonical_values(code: np.ndarray, length: int) -> np.ndarray:
+    """canonical value of the `length`-mer starting at every symbol position (garbage where the stretch is not valid)."""
+    n = code.size - length + 1
+    if n <= 0:
+        return np.zeros(0, U)
+    c = code.astype(U)
+    fwd = np.zeros(n, dtype=U)
+    rc = np.zeros(n, dtype=U)
+    for j in range(length):
+        fwd = (fwd << U(2)) | c[j:n + j]
+        rc = rc | ((U(3) - c[j:n + j]) << U(2 * j))
+    return np.minimum(fwd, rc)
+
+
+def _all_valid(valid: np.ndarray, length: int) -> np.ndarray:
+    n = valid.size - length + 1
+    if n <= 0:
+        return np.zeros(0, bool)
+    cs = np.concatenate([[0], np.cumsum(valid.astype(np.int64))])
+    return (cs[length:length + n] - cs[:n]) == length
+
+
+def window_bins(fasta: bytes, k: int, m: int, log2_bins: int):
+    """Per symbol position i (a window start): (ok bool, canonical k-mer uint64, bin int64); entries with ok False are undefined."""
+    if not (1 <= m <= k <= 32 and 1 <= log2_bins <= 32):
+        raise ValueError("1 <= m <= k <= 32 and 1 <= log2_bins <= 32")
+    code, valid = symbol_stream(fasta)
+    ok = _all_valid(valid, k)
+    n = ok.size
+    if n == 0:
+        return ok, np.zeros(0, U), np.zeros(0, np.int64)
+    kmer = _canonical_values(code, k)
+    hm = mix(_canonical_values(code, m))          # per m-mer position; only positions inside valid windows are ever used
+    w = k - m + 1
+    best = hm[:n].copy()
+    for j in range(1, w):
+        best = np.minimum(best, hm[j:n + j])
+    bins = ((best * BIN_C) >> U(64 - log2_bins)).astype(np.int64)
+    return ok, kmer, bins
+
+
+def superkmers(fasta: bytes, k: int, m: int, log2_bins: int) -> List[Tuple[int, int, int]]:
+    """[(bin, first symbol position, number of windows)] in stream order."""
+    ok, _, bins = window_bins(fasta, k, m, log2_bins)
+    n = ok.size
+    if n == 0:
+        return []
+    idx = np.flatnonzero(ok)
+    if idx.size == 0:
+        return []
+    brk = np.ones(idx.size, dtype=bool)
+    brk[1:] = (np.diff(idx) != 1) | (bins[idx][1:] != bins[idx][:-1])
+    starts = idx[brk]
+    ends = np.concatenate([idx[np.flatnonzero(brk)[1:] - 1], idx[-1:]])
+    return [(int(bins[s]), int(s), int(e - s + 1)) for s, e in zip(starts, ends)]
+
+
+def binned_group_histogram(genomes, k: int, m: int, log2_bins: int, nbins: int = 5000):
+    """The group stage computed BIN BY BIN: hist[c] = number of distinct k-mers found in exactly c genomes, and the group's
+    distinct k-mers per bin.  Must equal oracle.exp1's within-group histogram (tests/test_superkmer_oracle.py)."""
+    per_bin = {}
+    for g, text in enumerate(genomes):
+        ok, kmer, bins = window_bins(text, k, m, log2_bins)
+        for b in np.unique(bins[ok]):
+            per_bin.setdefault(int(b), []).append((g, np.unique(kmer[ok & (bins == b)])))
+    hist = np.zeros(nbins + 1, dtype=np.uint64)
+    sets = {}
+    for b, parts in per_bin.items():
+        keys, cnt = np.unique(np.concatenate([p[1] for p in parts]), return_counts=True)   # each part is one genome's distinct keys
+        np.add.at(hist, np.minimum(cnt, nbins), 1)
+        sets[b] = keys
+    return hist, sets
