@@ -102,6 +102,7 @@ _SIGNATURES = [
     ("khb_group_membership", C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int]),
     ("khb_partition_by_hash", C.c_int, [_P, _P, C.c_uint64, C.c_int, C.c_int, _P, _P]),
     ("khb_read_votes", C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_uint64, _P, _P]),
+    ("khb_superkmer_count", C.c_int, [_P, _P, _P, C.c_uint64, C.c_int, C.c_int, C.c_int, _P, _P]),
     ("khb_peer_alloc", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_uint64, _P]),
     ("khb_peer_open", C.c_int, [_P, _P]),
     ("khb_peer_begin", C.c_int, [_P]),
@@ -627,6 +628,22 @@ class Engine:
         finally:
             for b in bufs:
                 b.free()
+
+    def superkmer_count(self, packed: dict, k: int, m: int, log2_bins: int):
+        """EXPERIMENTAL: per minimizer bin the number of k-mer windows and of super-k-mers of a packed
+        stream (pack_fasta).  Returns (windows uint32 [2^log2_bins], superkmers uint32 [2^log2_bins], device ms)."""
+        nb = 1 << log2_bins
+        dw, ds = self.alloc(nb * 4), self.alloc(nb * 4)
+        try:
+            import time
+            self.sync()
+            t0 = time.perf_counter()
+            self._chk(self.lib.khb_superkmer_count(self.ctx, packed["codes"].ptr, packed["valid"].ptr, packed["n_symbols"], k, m, log2_bins, dw.ptr, ds.ptr))
+            self.sync()
+            ms = (time.perf_counter() - t0) * 1e3
+            return dw.download(np.uint32, nb), ds.download(np.uint32, nb), ms
+        finally:
+            dw.free(); ds.free()
 
     def group_sets_info(self) -> dict:
         k, g, n = C.c_int(), C.c_int(), C.c_uint64()

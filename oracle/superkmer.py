@@ -105,8 +105,9 @@ def window_bins(fasta: bytes, k: int, m: int, log2_bins: int):
     return ok, kmer, bins
 
 
-def superkmers(fasta: bytes, k: int, m: int, log2_bins: int) -> List[Tuple[int, int, int]]:
-    """[(bin, first symbol position, number of windows)] in stream order."""
+def superkmers(fasta: bytes, k: int, m: int, log2_bins: int, tile: int = 0) -> List[Tuple[int, int, int]]:
+    """[(bin, first symbol position, number of windows)] in stream order.  tile > 0: runs are also cut at every multiple of
+    `tile` symbol positions (the CUDA kernel works tile by tile: KHB_SUPERKMER_TILE)."""
     ok, _, bins = window_bins(fasta, k, m, log2_bins)
     n = ok.size
     if n == 0:
@@ -116,6 +117,8 @@ def superkmers(fasta: bytes, k: int, m: int, log2_bins: int) -> List[Tuple[int, 
         return []
     brk = np.ones(idx.size, dtype=bool)
     brk[1:] = (np.diff(idx) != 1) | (bins[idx][1:] != bins[idx][:-1])
+    if tile > 0:
+        brk |= (idx % tile) == 0
     starts = idx[brk]
     ends = np.concatenate([idx[np.flatnonzero(brk)[1:] - 1], idx[-1:]])
     return [(int(bins[s]), int(s), int(e - s + 1)) for s, e in zip(starts, ends)]
