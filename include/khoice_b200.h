@@ -280,6 +280,13 @@ KHB_API int khb_read_votes(khb_ctx *ctx, const uint64_t *d_index, const uint64_t
 #define KHB_SUPERKMER_TILE 4352
 KHB_API int khb_superkmer_count(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, uint64_t n_symbols, int k, int m,
                         int log2_bins, uint32_t *d_bin_windows, uint32_t *d_bin_superkmers);
+/* EXPERIMENTAL: the whole group stage through minimizer bins -- count pass, scatter of (canonical k-mer, genome) records into
+ * their bins, one CTA per bin counting in a shared-memory table.  <= 64 genomes, k <= 32.  h_hist[nbins + 1] as
+ * khb_group_from_*; h_totals[3] = distinct k-mers, sum of the per-genome set sizes, bins whose table overflowed (counts are
+ * then incomplete); h_ms[3] = device time of the three passes.  d_seg_off: symbol offset of every genome, n_genomes + 1. */
+KHB_API int khb_superkmer_group(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, uint64_t n_symbols,
+                        const uint64_t *d_seg_off, int n_genomes, int k, int m, int log2_bins, uint32_t nbins,
+                        uint64_t *h_hist, uint64_t *h_totals, float *h_ms);
 
 /* K7: split n keys into n_parts buckets by splitmix64(key) % n_parts (multi-GPU hash-range partition of the
  * k-mer space).  d_out receives the keys grouped by bucket, h_part_off[n_parts+1] the bucket offsets. */

@@ -1,7 +1,9 @@
-"""Time of the EXPERIMENTAL minimizer-partition count pass (csrc/superkmer.cu) on one config-2 group (50 x 5 Mbp), k = 31."""
+"""Times of the EXPERIMENTAL minimizer-bin group stage (csrc/superkmer.cu) on one config-2 group (50 x 5 Mbp), k = 31,
+next to the product path's time for the same group."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import multiprocessing as mp
+import numpy as np
 from khoice_b200 import synth
 from khoice_b200.engine import Engine
 def gen(i):
@@ -9,11 +11,13 @@ def gen(i):
 with mp.get_context("fork").Pool(16) as pool:
     files = pool.map(gen, range(1, 51))
 eng = Engine(0)
-st = eng.stage_fasta(files)
-pk = eng.pack_fasta(st)
-for m, lb in ((11, 16), (11, 14), (9, 16)):
+for _ in range(2):
+    eng.group_sets_reset()
+    ref, rst = eng.group_from_fasta(files, 31, nbins=64, keep_set=False)
+print(f"product path: extract {rst['ms_extract']:.2f} + sort {rst['ms_sort1']:.2f} + count {rst['ms_count']:.2f} ms (pack {rst['ms_pack']:.2f}); distinct {rst['distinct']}", flush=True)
+for m, lb in ((11, 16), (11, 15)):
     for _ in range(2):
-        win, sk, ms = eng.superkmer_count(pk, 31, m, lb)
-    print(f"m={m} bins=2^{lb}: {ms:.2f} ms for {pk['n_symbols']} symbols; windows {int(win.sum())}, super-k-mers {int(sk.sum())} ({win.sum() / max(sk.sum(), 1):.1f} windows each), "
-          f"largest bin {int(win.max())} windows = {win.max() / win.mean():.1f} x mean", flush=True)
+        hist, st = eng.superkmer_group(files, 31, m, lb, nbins=64)
+    print(f"m={m} bins=2^{lb}: count pass {st['ms_count']:.2f} ms (incl. host scan), scatter {st['ms_scatter']:.2f} ms, bins {st['ms_bins']:.2f} ms; distinct {st['distinct']}, "
+          f"overflowed bins {st['overflowed_bins']}, histogram equal to the product path: {bool(np.array_equal(hist, ref))}", flush=True)
 eng.close()

@@ -35,3 +35,20 @@ def test_bin_counts_match_the_oracle(engine, k, m, lb):
         assert np.array_equal(sk.astype(np.int64), ref_s), (k, m, lb)
         ok, _, _ = S.window_bins(t, k, m, lb)
         assert int(win.sum()) == int(ok.sum())
+
+
+@pytest.mark.parametrize("k,m,lb", [(31, 11, 10), (21, 9, 8), (13, 7, 6)])
+def test_group_stage_through_minimizer_bins_equals_the_product_path(engine, oracle, k, m, lb):
+    """EXPERIMENT: count pass + scatter + one CTA per bin with a shared-memory table == the single-sort path == the oracle."""
+    from khoice_b200 import synth
+    cfg = synth.SynthConfig(n_groups=1, genomes_per_group=7, genome_len=40_000, seed=23)
+    genomes = [synth.make_genome(cfg, 1, i) for i in range(1, 8)] + [EDGE_FASTAS[1] + EDGE_FASTAS[3], b""]
+    hist, st = engine.superkmer_group(genomes, k, m, lb, nbins=64)
+    assert st["overflowed_bins"] == 0
+    engine.group_sets_reset()
+    ref, rst = engine.group_from_fasta(genomes, k, nbins=64, keep_set=False)
+    w_ref, _, ost = oracle.exp1(genomes, [0] * len(genomes), 1, k, nbins=64)
+    assert np.array_equal(ref, w_ref[0])
+    assert np.array_equal(hist, w_ref[0]), (hist[:10], w_ref[0][:10])
+    assert st["distinct"] == rst["distinct"] == ost["sum_group_distinct"]
+    assert st["genome_distinct"] == ost["sum_genome_distinct"]
