@@ -275,8 +275,8 @@ KHB_API int khb_read_votes(khb_ctx *ctx, const uint64_t *d_index, const uint64_t
 /* EXPERIMENTAL (the next design step; used by no product path yet): count pass of the minimizer
  * partition.  For every k-mer window of a packed stream (the windows khb_extract_kmers emits) the bin of its minimizer --
  * minimum over the window's canonical m-mers of a 64-bit mix, re-mixed, top log2_bins bits (tests/test_gpu_superkmer.py) -- and per
- * bin the number of windows and of super-k-mers (maximal runs of consecutive windows with one bin, cut every
- * KHB_SUPERKMER_TILE windows).  1 <= m <= k <= 32.  d_bin_windows / d_bin_superkmers: uint32 [1 << log2_bins]. */
+ * bin the number of windows and of super-k-mer RECORDS (maximal runs of consecutive windows with one bin, cut every
+ * KHB_SUPERKMER_TILE windows; a run of more than 65 - k windows counts as several records).  1 <= m <= k <= 32.  d_bin_windows / d_bin_superkmers: uint32 [1 << log2_bins]. */
 #define KHB_SUPERKMER_TILE 4352
 KHB_API int khb_superkmer_count(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, uint64_t n_symbols, int k, int m,
                         int log2_bins, uint32_t *d_bin_windows, uint32_t *d_bin_superkmers);
@@ -287,6 +287,11 @@ KHB_API int khb_superkmer_count(khb_ctx *ctx, const uint64_t *d_codes, const uin
 KHB_API int khb_superkmer_group(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, uint64_t n_symbols,
                         const uint64_t *d_seg_off, int n_genomes, int k, int m, int log2_bins, uint32_t nbins,
                         uint64_t *h_hist, uint64_t *h_totals, float *h_ms);
+/* EXPERIMENTAL: the same with 24-byte super-k-mer records in the bins (genome, length, 64 symbols; runs longer than 65 - k
+ * windows are several records) instead of expanded k-mers; the per-bin kernel expands them in registers.  2 <= k <= 32. */
+KHB_API int khb_superkmer_group_compact(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, uint64_t n_symbols,
+                                const uint64_t *d_seg_off, int n_genomes, int k, int m, int log2_bins, uint32_t nbins,
+                                uint64_t *h_hist, uint64_t *h_totals, float *h_ms);
 
 /* K7: split n keys into n_parts buckets by splitmix64(key) % n_parts (multi-GPU hash-range partition of the
  * k-mer space).  d_out receives the keys grouped by bucket, h_part_off[n_parts+1] the bucket offsets. */

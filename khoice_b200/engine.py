@@ -104,6 +104,7 @@ _SIGNATURES = [
     ("khb_read_votes", C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_uint64, _P, _P]),
     ("khb_superkmer_count", C.c_int, [_P, _P, _P, C.c_uint64, C.c_int, C.c_int, C.c_int, _P, _P]),
     ("khb_superkmer_group", C.c_int, [_P, _P, _P, C.c_uint64, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, _P, _P, _P]),
+    ("khb_superkmer_group_compact", C.c_int, [_P, _P, _P, C.c_uint64, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, _P, _P, _P]),
     ("khb_peer_alloc", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_uint64, _P]),
     ("khb_peer_open", C.c_int, [_P, _P]),
     ("khb_peer_begin", C.c_int, [_P]),
@@ -646,7 +647,7 @@ class Engine:
         finally:
             dw.free(); ds.free()
 
-    def superkmer_group(self, files: Sequence, k: int, m: int, log2_bins: int, nbins: int = 64):
+    def superkmer_group(self, files: Sequence, k: int, m: int, log2_bins: int, nbins: int = 64, compact: bool = False):
         """EXPERIMENTAL: the group stage through minimizer bins.  Returns (histogram uint64[nbins+1],
         dict(distinct, genome_distinct, overflowed_bins, ms_count, ms_scatter, ms_bins))."""
         staged = self.stage_fasta(files)
@@ -663,7 +664,8 @@ class Engine:
             hist = np.zeros(nbins + 1, dtype=np.uint64)
             tot = np.zeros(3, dtype=np.uint64)
             ms = np.zeros(3, dtype=np.float32)
-            self._chk(self.lib.khb_superkmer_group(self.ctx, packed["codes"].ptr, packed["valid"].ptr, packed["n_symbols"], d_seg.ptr, n, k, m, log2_bins,
+            fn = self.lib.khb_superkmer_group_compact if compact else self.lib.khb_superkmer_group
+            self._chk(fn(self.ctx, packed["codes"].ptr, packed["valid"].ptr, packed["n_symbols"], d_seg.ptr, n, k, m, log2_bins,
                                                    nbins, hist.ctypes.data, tot.ctypes.data, ms.ctypes.data))
             return hist, {"distinct": int(tot[0]), "genome_distinct": int(tot[1]), "overflowed_bins": int(tot[2]),
                           "ms_count": float(ms[0]), "ms_scatter": float(ms[1]), "ms_bins": float(ms[2])}

@@ -15,9 +15,9 @@ for _ in range(2):
     eng.group_sets_reset()
     ref, rst = eng.group_from_fasta(files, 31, nbins=64, keep_set=False)
 print(f"product path: extract {rst['ms_extract']:.2f} + sort {rst['ms_sort1']:.2f} + count {rst['ms_count']:.2f} ms (pack {rst['ms_pack']:.2f}); distinct {rst['distinct']}", flush=True)
-for m, lb in ((11, 16), (11, 15)):
+for m, lb, compact in ((11, 16, False), (11, 16, True), (13, 16, True)):
     for _ in range(2):
-        hist, st = eng.superkmer_group(files, 31, m, lb, nbins=64)
-    print(f"m={m} bins=2^{lb}: count pass {st['ms_count']:.2f} ms (incl. host scan), scatter {st['ms_scatter']:.2f} ms, bins {st['ms_bins']:.2f} ms; distinct {st['distinct']}, "
+        hist, st = eng.superkmer_group(files, 31, m, lb, nbins=64, compact=compact)
+    print(f"m={m} bins=2^{lb} {'super-k-mer records' if compact else 'expanded k-mers'}: count pass {st['ms_count']:.2f} ms (incl. host scan), scatter {st['ms_scatter']:.2f} ms, bins {st['ms_bins']:.2f} ms; distinct {st['distinct']}, "
           f"overflowed bins {st['overflowed_bins']}, histogram equal to the product path: {bool(np.array_equal(hist, ref))}", flush=True)
 eng.close()

@@ -28,22 +28,24 @@ def test_bin_counts_match_the_oracle(engine, k, m, lb):
         # the staged text carries filler behind the file (one more break symbol): it adds no window
         ref_w = np.zeros(1 << lb, dtype=np.int64)
         ref_s = np.zeros(1 << lb, dtype=np.int64)
+        cap = 65 - k                                  # a record holds k - 1 + len <= 64 symbols: longer runs are several records
         for b, s, n in S.superkmers(t, k, m, lb, tile=TILE):
             ref_w[b] += n
-            ref_s[b] += 1
+            ref_s[b] += -(-n // cap)
         assert np.array_equal(win.astype(np.int64), ref_w), (k, m, lb)
         assert np.array_equal(sk.astype(np.int64), ref_s), (k, m, lb)
         ok, _, _ = S.window_bins(t, k, m, lb)
         assert int(win.sum()) == int(ok.sum())
 
 
-@pytest.mark.parametrize("k,m,lb", [(31, 11, 10), (21, 9, 8), (13, 7, 6)])
-def test_group_stage_through_minimizer_bins_equals_the_product_path(engine, oracle, k, m, lb):
+@pytest.mark.parametrize("compact", [False, True])
+@pytest.mark.parametrize("k,m,lb", [(31, 11, 10), (21, 9, 8), (13, 7, 6), (32, 12, 9)])
+def test_group_stage_through_minimizer_bins_equals_the_product_path(engine, oracle, k, m, lb, compact):
     """EXPERIMENT: count pass + scatter + one CTA per bin with a shared-memory table == the single-sort path == the oracle."""
     from khoice_b200 import synth
     cfg = synth.SynthConfig(n_groups=1, genomes_per_group=7, genome_len=40_000, seed=23)
     genomes = [synth.make_genome(cfg, 1, i) for i in range(1, 8)] + [EDGE_FASTAS[1] + EDGE_FASTAS[3], b""]
-    hist, st = engine.superkmer_group(genomes, k, m, lb, nbins=64)
+    hist, st = engine.superkmer_group(genomes, k, m, lb, nbins=64, compact=compact)   # compact: 24-byte super-k-mer records in the bins
     assert st["overflowed_bins"] == 0
     engine.group_sets_reset()
     ref, rst = engine.group_from_fasta(genomes, k, nbins=64, keep_set=False)
