@@ -11,6 +11,8 @@
 // turns the minimum into a bin and stores it (0xFFFF'FFFF for windows without a k-mer).  Phase 3: every window that starts a
 // super-k-mer -- first of the tile, or bin / validity differs from its predecessor -- walks to the end of its run and adds
 // (1, length) to its bin's counters: one pair of global reductions per super-k-mer (~11 windows), not per window.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "khb_common.cuh"
@@ -327,7 +329,8 @@ extern "C" int khb_superkmer_group(khb_ctx *ctx, const uint64_t *d_codes, const 
 __global__ void __launch_bounds__(SK_BLOCK)
 superkmer_scatter_compact_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, u64 n_sym, int k, int m, int log2_bins,
                                  const u64 *__restrict__ seg_off, int nseg, const u64 *__restrict__ bin_roff, u32 *__restrict__ bin_cursor,
-                                 u64 *__restrict__ rec /* 3 words per record */)
+                                 u64 *__restrict__ rec /* 3 words per record */, u32 bin_cap /* > 0: ONE-pass mode, bin b owns records [b * cap, (b + 1) * cap) */,
+                                 u64 *__restrict__ overflow)
 {
     extern __shared__ __align__(8) unsigned char sk_smem[];
     const int w = k - m + 1;
@@ -382,7 +385,12 @@ superkmer_scatter_compact_kernel(const u64 *__restrict__ codes, const u32 *__res
         u32 len = 1;
         while (j + len < SK_TILE && bins[j + len] == b) len++;
         const u32 pieces = (len + cap - 1) / cap;
-        u64 r = __ldg(bin_roff + b) + atomicAdd(&bin_cursor[b], pieces);
+        const u32 at = atomicAdd(&bin_cursor[b], pieces);
+        if (bin_cap && at + pieces > bin_cap) {            // the bin's fixed region is full: the caller redoes the group with exact sizes
+            *overflow = 1ull;
+            continue;
+        }
+        u64 r = (bin_cap ? (u64)b * bin_cap : __ldg(bin_roff + b)) + at;
         const u64 g = sk_segment_of(seg_off, nseg, tile0 + j);
         for (u32 s0 = 0; s0 < len; s0 += cap, r++) {
             const u32 pl = len - s0 < cap ? len - s0 : cap;
@@ -399,7 +407,7 @@ superkmer_scatter_compact_kernel(const u64 *__restrict__ codes, const u32 *__res
 
 __global__ void __launch_bounds__(SKC_BLOCK)
 superkmer_bin_expand_count_kernel(const u64 *__restrict__ rec, const u64 *__restrict__ bin_roff, const u32 *__restrict__ bin_records, int k, u32 nbins,
-                                  u64 *__restrict__ hist, u64 *__restrict__ totals)
+                                  u64 *__restrict__ hist, u64 *__restrict__ totals, u32 bin_cap)
 {
     extern __shared__ __align__(8) unsigned char skc_smem[];
     u64 *tkey = (u64 *)skc_smem;
@@ -407,18 +415,21 @@ superkmer_bin_expand_count_kernel(const u64 *__restrict__ rec, const u64 *__rest
     __shared__ u32 s_over;
     __shared__ u32 s_hist[65];
     const u32 tid = threadIdx.x, b = blockIdx.x;
-    const u32 n = bin_records[b];
+    const u32 n = bin_cap && bin_records[b] > bin_cap ? bin_cap : bin_records[b];
     if (n == 0) return;
     for (u32 i = tid; i < SKC_SLOTS; i += SKC_BLOCK) { tkey[i] = ~0ull; tbits[2 * i] = 0u; tbits[2 * i + 1] = 0u; }
     if (tid < 65) s_hist[tid] = 0;
     if (tid == 0) s_over = 0;
     __syncthreads();
-    const u64 off = bin_roff[b];
+    const u64 off = bin_cap ? (u64)b * bin_cap : bin_roff[b];
     const int rs = 64 - 2 * k;
-    for (u32 i = tid; i < n; i += SKC_BLOCK) {
+    // 16 lanes share a record and take its windows e = lane, lane + 16, ...: a record holds ~11 windows on average, so one
+    // thread per record (the first version: 5.3 ms per group) leaves most lanes waiting for the longest record of the warp
+    const u32 sub = tid & 15u, grp = tid >> 4;
+    for (u32 i = grp; i < n; i += SKC_BLOCK / 16) {
         const u64 w0 = rec[3 * (off + i)], w1 = rec[3 * (off + i) + 1], w2 = rec[3 * (off + i) + 2];
         const u32 g = (u32)(w0 >> 48), len = (u32)(w0 >> 40) & 0xffu;
-        for (u32 e = 0; e < len; e++) {
+        for (u32 e = sub; e < len; e += 16) {
             const u64 x = e == 0 ? w1 : e < 32 ? ((w1 << (2 * e)) | (w2 >> (64 - 2 * e))) : (w2 << (2 * (e - 32)));
             const u64 fwd = x >> rs;
             u64 r = __brevll(~x) << rs >> rs;
@@ -480,33 +491,43 @@ extern "C" int khb_superkmer_group_compact(khb_ctx *ctx, const uint64_t *d_codes
     cudaEvent_t ev[4];
     for (int i = 0; i < 4; i++) KHB_CUDA(ctx, cudaEventCreate(&ev[i]));
     KHB_CUDA(ctx, cudaEventRecord(ev[0], ctx->stream));
-    if ((rc = khb_superkmer_count(ctx, d_codes, d_valid, n_symbols, k, m, log2_bins, d_win, d_sk))) return rc;
-    std::vector<u32> h_sk(nb);
-    std::vector<u64> h_off(nb);
-    KHB_CUDA(ctx, cudaMemcpyAsync(h_sk.data(), d_sk, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    u64 run = 0;
-    for (size_t i = 0; i < nb; i++) { h_off[i] = run; run += h_sk[i]; }
+    // KHB_SUPERKMER_ONEPASS=1: no count pass -- every bin owns a fixed region of 8 x the mean number of records (+ 64); a bin
+    // that would overflow raises totals[2] (the counts are then incomplete and the caller has to fall back to exact sizes)
+    const char *one = getenv("KHB_SUPERKMER_ONEPASS");
+    const u32 bin_cap = (one && atoi(one)) ? (u32)(8 * (n_symbols / 10 / nb + 1) + 64) : 0u;
     void *pr;
-    if ((rc = khb_scratch_get(ctx, SCR_KEYS_A, (run + 4) * 24, &pr))) return rc;
-    KHB_CUDA(ctx, cudaMemcpyAsync(d_off, h_off.data(), nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+    u32 *d_records = d_sk;
+    if (bin_cap) {
+        if ((rc = khb_scratch_get(ctx, SCR_KEYS_A, ((u64)nb * bin_cap + 4) * 24, &pr))) return rc;
+        d_records = d_cur;                                  // the cursors ARE the record counts
+    } else {
+        if ((rc = khb_superkmer_count(ctx, d_codes, d_valid, n_symbols, k, m, log2_bins, d_win, d_sk))) return rc;
+        std::vector<u32> h_sk(nb);
+        std::vector<u64> h_off(nb);
+        KHB_CUDA(ctx, cudaMemcpyAsync(h_sk.data(), d_sk, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        u64 run = 0;
+        for (size_t i = 0; i < nb; i++) { h_off[i] = run; run += h_sk[i]; }
+        if ((rc = khb_scratch_get(ctx, SCR_KEYS_A, (run + 4) * 24, &pr))) return rc;
+        KHB_CUDA(ctx, cudaMemcpyAsync(d_off, h_off.data(), nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+        KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // h_off is pageable
+    }
     KHB_CUDA(ctx, cudaMemsetAsync(d_cur, 0, nb * 4, ctx->stream));
     KHB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, ((size_t)nbins + 1 + 3) * 8, ctx->stream));
-    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // h_off is pageable
     KHB_CUDA(ctx, cudaEventRecord(ev[1], ctx->stream));
     if (n_symbols) {
         const u64 tiles = div_up(n_symbols, SK_TILE);
         const size_t shm = (size_t)(SK_TILE + 32) * sizeof(u64) + (size_t)SK_TILE * sizeof(u32);
         cudaFuncSetAttribute(superkmer_scatter_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
         superkmer_scatter_compact_kernel<<<(unsigned)tiles, SK_BLOCK, shm, ctx->stream>>>((const u64 *)d_codes, d_valid, n_symbols, k, m, log2_bins, (const u64 *)d_seg_off,
-                                                                                         n_genomes, d_off, d_cur, (u64 *)pr);
+                                                                                         n_genomes, d_off, d_cur, (u64 *)pr, bin_cap, d_tot + 2);
         KHB_LAUNCH_CHECK(ctx);
     }
     KHB_CUDA(ctx, cudaEventRecord(ev[2], ctx->stream));
     {
         const size_t shm = (size_t)SKC_SLOTS * 16;
         cudaFuncSetAttribute(superkmer_bin_expand_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
-        superkmer_bin_expand_count_kernel<<<(unsigned)nb, SKC_BLOCK, shm, ctx->stream>>>((const u64 *)pr, d_off, d_sk, k, nbins, d_hist, d_tot);
+        superkmer_bin_expand_count_kernel<<<(unsigned)nb, SKC_BLOCK, shm, ctx->stream>>>((const u64 *)pr, d_off, d_records, k, nbins, d_hist, d_tot, bin_cap);
         KHB_LAUNCH_CHECK(ctx);
     }
     KHB_CUDA(ctx, cudaEventRecord(ev[3], ctx->stream));

@@ -20,4 +20,9 @@ for m, lb, compact in ((11, 16, False), (11, 16, True), (13, 16, True)):
         hist, st = eng.superkmer_group(files, 31, m, lb, nbins=64, compact=compact)
     print(f"m={m} bins=2^{lb} {'super-k-mer records' if compact else 'expanded k-mers'}: count pass {st['ms_count']:.2f} ms (incl. host scan), scatter {st['ms_scatter']:.2f} ms, bins {st['ms_bins']:.2f} ms; distinct {st['distinct']}, "
           f"overflowed bins {st['overflowed_bins']}, histogram equal to the product path: {bool(np.array_equal(hist, ref))}", flush=True)
+os.environ["KHB_SUPERKMER_ONEPASS"] = "1"
+for _ in range(2):
+    hist, st = eng.superkmer_group(files, 31, 11, 16, nbins=64, compact=True)
+print(f"ONE pass (fixed bin regions, no count pass): setup {st['ms_count']:.2f} ms, partition {st['ms_scatter']:.2f} ms, bins {st['ms_bins']:.2f} ms; distinct {st['distinct']}, "
+      f"overflow {st['overflowed_bins']}, histogram equal to the product path: {bool(np.array_equal(hist, ref))}", flush=True)
 eng.close()
