@@ -43,6 +43,41 @@ __device__ __forceinline__ u64 sk_canonical(const u64 *__restrict__ codes, u64 p
     return fwd < r ? fwd : r;
 }
 
+// Phases 1 and 2 of a tile, shared by the kernels below: hashes of the tile's canonical m-mers into hm[], then the bin of every
+// window into bins[] (~0u = no k-mer).  Phase 2 is one window per thread and round (consecutive lanes on consecutive windows,
+// k - m + 1 conflict-free shared-memory reads each); the first version walked SK_PER consecutive windows per thread with a
+// running minimum -- fewer reads, but one long dependent chain per thread.
+__device__ __forceinline__ void sk_tile_bins(const u64 *__restrict__ codes, const u32 *__restrict__ valid, u64 n_sym, int k, int m, int log2_bins,
+                                             u64 tile0, u64 *hm, u32 *bins)
+{
+    const int w = k - m + 1;
+    const u32 tid = threadIdx.x;
+    const u32 n_hash = SK_TILE + w - 1;
+    for (u32 j = tid; j < n_hash; j += SK_BLOCK) {
+        const u64 p = tile0 + j;
+        hm[j] = p + m <= n_sym ? sk_mix(sk_canonical(codes, p, m)) : ~0ull;
+    }
+    __syncthreads();
+    const u64 ones_k = k == 64 ? ~0ull : ((1ull << k) - 1ull);
+    for (u32 j = tid; j < SK_TILE; j += SK_BLOCK) {
+        const u64 i = tile0 + j;
+        bool ok = i + k <= n_sym;
+        if (ok) {
+            const u64 q = i >> 5;
+            const u32 o = (u32)(i & 31);
+            const u64 vv = ((u64)__ldg(valid + q) << 32) | (u64)__ldg(valid + q + 1);
+            ok = (((vv << o) >> (64 - k)) == ones_k);   // k validity bits from bit o of the MSB-first stream (k <= 32 here)
+        }
+        u64 cur = hm[j];
+        for (int d = 1; d < w; d++) {
+            const u64 h = hm[j + d];
+            cur = h < cur ? h : cur;
+        }
+        bins[j] = ok ? (u32)((cur * SK_BIN_C) >> (64 - log2_bins)) : ~0u;
+    }
+    __syncthreads();
+}
+
 extern "C" int khb_superkmer_count(khb_ctx *, const uint64_t *, const uint32_t *, uint64_t, int, int, int, uint32_t *, uint32_t *);
 
 __global__ void __launch_bounds__(SK_BLOCK)
@@ -55,46 +90,8 @@ superkmer_count_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ va
     u32 *bins = (u32 *)(hm + SK_TILE + 32);        // [SK_TILE] bin of every window of the tile, ~0u = no k-mer
     const u32 tid = threadIdx.x;
     const u64 tile0 = (u64)blockIdx.x * SK_TILE;
-    const u32 n_hash = SK_TILE + w - 1;
-    for (u32 j = tid; j < n_hash; j += SK_BLOCK) {
-        const u64 p = tile0 + j;
-        hm[j] = p + m <= n_sym ? sk_mix(sk_canonical(codes, p, m)) : ~0ull;
-    }
-    __syncthreads();
-    const u64 ones_k = k == 64 ? ~0ull : ((1ull << k) - 1ull);
-    const u32 base = tid * SK_PER;
-    u64 cur = ~0ull;
-    u32 cur_at = 0;                                // position (in hm) of the current minimum
-    bool have = false;
-#pragma unroll 1
-    for (u32 t = 0; t < SK_PER; t++) {
-        const u32 j = base + t;                    // window j of the tile covers hm[j .. j + w)
-        const u64 i = tile0 + j;
-        bool ok = i + k <= n_sym;
-        if (ok) {
-            const u64 q = i >> 5;
-            const u32 o = (u32)(i & 31);
-            const u64 vv = ((u64)__ldg(valid + q) << 32) | (u64)__ldg(valid + q + 1);
-            ok = (((vv << o) >> (64 - k)) == ones_k);   // k validity bits from bit o of the MSB-first stream (k <= 32 here)
-        }
-        if (!have || cur_at < j) {                 // (re)scan the whole window
-            cur = hm[j];
-            cur_at = j;
-            for (int d = 1; d < w; d++) {
-                const u64 h = hm[j + d];
-                if (h < cur) { cur = h; cur_at = j + d; }
-            }
-            have = true;
-        } else {
-            const u64 h = hm[j + w - 1];           // the one m-mer that entered
-            if (h < cur) { cur = h; cur_at = j + w - 1; }
-        }
-        bins[j] = ok ? (u32)((cur * SK_BIN_C) >> (64 - log2_bins)) : ~0u;
-    }
-    __syncthreads();
-#pragma unroll 1
-    for (u32 t = 0; t < SK_PER; t++) {
-        const u32 j = base + t;
+    sk_tile_bins(codes, valid, n_sym, k, m, log2_bins, tile0, hm, bins);
+    for (u32 j = tid; j < SK_TILE; j += SK_BLOCK) {   // consecutive lanes on consecutive windows
         const u32 b = bins[j];
         if (b == ~0u) continue;
         if (j > 0 && bins[j - 1] == b) continue;   // not a start (super-k-mers are cut at tile boundaries)
@@ -134,47 +131,9 @@ superkmer_scatter_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ 
     u32 *bins = (u32 *)(dest + SK_TILE);
     const u32 tid = threadIdx.x;
     const u64 tile0 = (u64)blockIdx.x * SK_TILE;
-    const u32 n_hash = SK_TILE + w - 1;
-    for (u32 j = tid; j < n_hash; j += SK_BLOCK) {
-        const u64 p = tile0 + j;
-        hm[j] = p + m <= n_sym ? sk_mix(sk_canonical(codes, p, m)) : ~0ull;
-    }
-    __syncthreads();
-    const u64 ones_k = k == 64 ? ~0ull : ((1ull << k) - 1ull);
-    const u32 base = tid * SK_PER;
-    u64 cur = ~0ull;
-    u32 cur_at = 0;
-    bool have = false;
-#pragma unroll 1
-    for (u32 t = 0; t < SK_PER; t++) {
-        const u32 j = base + t;
-        const u64 i = tile0 + j;
-        bool ok = i + k <= n_sym;
-        if (ok) {
-            const u64 q = i >> 5;
-            const u32 o = (u32)(i & 31);
-            const u64 vv = ((u64)__ldg(valid + q) << 32) | (u64)__ldg(valid + q + 1);
-            ok = (((vv << o) >> (64 - k)) == ones_k);
-        }
-        if (!have || cur_at < j) {
-            cur = hm[j];
-            cur_at = j;
-            for (int d = 1; d < w; d++) {
-                const u64 h = hm[j + d];
-                if (h < cur) { cur = h; cur_at = j + d; }
-            }
-            have = true;
-        } else {
-            const u64 h = hm[j + w - 1];
-            if (h < cur) { cur = h; cur_at = j + w - 1; }
-        }
-        bins[j] = ok ? (u32)((cur * SK_BIN_C) >> (64 - log2_bins)) : ~0u;
-    }
-    __syncthreads();
+    sk_tile_bins(codes, valid, n_sym, k, m, log2_bins, tile0, hm, bins);
     // phase 3: the owner of a super-k-mer's start reserves the run's slots and notes every window's destination in shared memory
-#pragma unroll 1
-    for (u32 t = 0; t < SK_PER; t++) {
-        const u32 j = base + t;
+    for (u32 j = tid; j < SK_TILE; j += SK_BLOCK) {   // consecutive lanes on consecutive windows
         const u32 b = bins[j];
         if (b == ~0u) continue;
         if (j > 0 && bins[j - 1] == b) continue;
@@ -338,47 +297,9 @@ superkmer_scatter_compact_kernel(const u64 *__restrict__ codes, const u32 *__res
     u32 *bins = (u32 *)(hm + SK_TILE + 32);
     const u32 tid = threadIdx.x;
     const u64 tile0 = (u64)blockIdx.x * SK_TILE;
-    const u32 n_hash = SK_TILE + w - 1;
-    for (u32 j = tid; j < n_hash; j += SK_BLOCK) {
-        const u64 p = tile0 + j;
-        hm[j] = p + m <= n_sym ? sk_mix(sk_canonical(codes, p, m)) : ~0ull;
-    }
-    __syncthreads();
-    const u64 ones_k = k == 64 ? ~0ull : ((1ull << k) - 1ull);
-    const u32 base = tid * SK_PER;
-    u64 cur = ~0ull;
-    u32 cur_at = 0;
-    bool have = false;
-#pragma unroll 1
-    for (u32 t = 0; t < SK_PER; t++) {
-        const u32 j = base + t;
-        const u64 i = tile0 + j;
-        bool ok = i + k <= n_sym;
-        if (ok) {
-            const u64 q = i >> 5;
-            const u32 o = (u32)(i & 31);
-            const u64 vv = ((u64)__ldg(valid + q) << 32) | (u64)__ldg(valid + q + 1);
-            ok = (((vv << o) >> (64 - k)) == ones_k);
-        }
-        if (!have || cur_at < j) {
-            cur = hm[j];
-            cur_at = j;
-            for (int d = 1; d < w; d++) {
-                const u64 h = hm[j + d];
-                if (h < cur) { cur = h; cur_at = j + d; }
-            }
-            have = true;
-        } else {
-            const u64 h = hm[j + w - 1];
-            if (h < cur) { cur = h; cur_at = j + w - 1; }
-        }
-        bins[j] = ok ? (u32)((cur * SK_BIN_C) >> (64 - log2_bins)) : ~0u;
-    }
-    __syncthreads();
+    sk_tile_bins(codes, valid, n_sym, k, m, log2_bins, tile0, hm, bins);
     const u32 cap = 65u - (u32)k;
-#pragma unroll 1
-    for (u32 t = 0; t < SK_PER; t++) {
-        const u32 j = base + t;
+    for (u32 j = tid; j < SK_TILE; j += SK_BLOCK) {   // consecutive lanes on consecutive windows
         const u32 b = bins[j];
         if (b == ~0u) continue;
         if (j > 0 && bins[j - 1] == b) continue;
