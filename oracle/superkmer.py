@@ -5,7 +5,7 @@ that step can be checked bit for bit from their first version on.  Nothing under
 Semantics of the windows are the oracle's (rules R1-R5 of SURVEY.md 8c, the reference's `kmc -fm` call sites
 /root/reference/workflow/rules/exp_type_1.smk:156-163): symbols `ACGTacgt` are valid, anything else breaks the window,
 windows never span `>` records, the k-mer value is base 4 with the first base most significant, canonical = min(k-mer,
-reverse complement).  On top of that, for a window with canonical m-mers c_0 .. c_{k-m} (m <= k <= 32 here):
+reverse complement).  On top of that, for a window with canonical m-mers c_0 .. c_{k-m} (m <= 32, m <= k <= 64):
 
     minimizer hash   H = min_j  mix(c_j)            mix(x) = ((x ^ (x >> 15)) * 0x9E3779B97F4A7C15) ^ (... >> 29), 64-bit
     bin              b = (H * 0xD6E8FEB86659FD93 mod 2^64) >> (64 - log2_bins)
@@ -87,15 +87,23 @@ def _all_valid(valid: np.ndarray, length: int) -> np.ndarray:
 
 
 def window_bins(fasta: bytes, k: int, m: int, log2_bins: int):
-    """Per symbol position i (a window start): (ok bool, canonical k-mer uint64, bin int64); entries with ok False are undefined."""
-    if not (1 <= m <= k <= 32 and 1 <= log2_bins <= 32):
-        raise ValueError("1 <= m <= k <= 32 and 1 <= log2_bins <= 32")
+    """Per symbol position i (a window start): (ok bool, canonical k-mer, bin int64); entries with ok False are undefined.
+    The k-mer column is uint64 [n] for k <= 32 and uint64 [n, 2] (lo, hi) for 33 <= k <= 64 (the oracle's own layout, taken
+    from oracle.kmers, which lists the valid windows in stream order); the minimizer length m stays <= 32."""
+    if not (1 <= m <= min(k, 32) and k <= 64 and 1 <= log2_bins <= 32):
+        raise ValueError("1 <= m <= min(k, 32), k <= 64 and 1 <= log2_bins <= 32")
     code, valid = symbol_stream(fasta)
     ok = _all_valid(valid, k)
     n = ok.size
     if n == 0:
-        return ok, np.zeros(0, U), np.zeros(0, np.int64)
-    kmer = _canonical_values(code, k)
+        return ok, np.zeros((0,) if k <= 32 else (0, 2), U), np.zeros(0, np.int64)
+    if k <= 32:
+        kmer = _canonical_values(code, k)
+    else:
+        from . import oracle as O
+        keys, _ = O.kmers(fasta, k)
+        kmer = np.zeros((n, 2), dtype=U)
+        kmer[ok] = keys
     hm = mix(_canonical_values(code, m))          # per m-mer position; only positions inside valid windows are ever used
     w = k - m + 1
     best = hm[:n].copy()
@@ -128,14 +136,16 @@ def binned_group_histogram(genomes, k: int, m: int, log2_bins: int, nbins: int =
     """The group stage computed BIN BY BIN: hist[c] = number of distinct k-mers found in exactly c genomes, and the group's
     distinct k-mers per bin.  Must equal oracle.exp1's within-group histogram (tests/test_superkmer_oracle.py)."""
     per_bin = {}
+    uniq = (lambda a: np.unique(a)) if k <= 32 else (lambda a: np.unique(a, axis=0))
     for g, text in enumerate(genomes):
         ok, kmer, bins = window_bins(text, k, m, log2_bins)
         for b in np.unique(bins[ok]):
-            per_bin.setdefault(int(b), []).append((g, np.unique(kmer[ok & (bins == b)])))
+            per_bin.setdefault(int(b), []).append((g, uniq(kmer[ok & (bins == b)])))
     hist = np.zeros(nbins + 1, dtype=np.uint64)
     sets = {}
     for b, parts in per_bin.items():
-        keys, cnt = np.unique(np.concatenate([p[1] for p in parts]), return_counts=True)   # each part is one genome's distinct keys
+        cat = np.concatenate([p[1] for p in parts])                                        # each part is one genome's distinct keys
+        keys, cnt = np.unique(cat, return_counts=True) if k <= 32 else np.unique(cat, axis=0, return_counts=True)
         np.add.at(hist, np.minimum(cnt, nbins), 1)
         sets[b] = keys
     return hist, sets

@@ -7,7 +7,7 @@ import pytest
 from helpers import EDGE_FASTAS, random_fasta, symbol_stream
 
 
-@pytest.mark.parametrize("k,m,lb", [(31, 11, 10), (21, 9, 6), (15, 15, 4), (32, 7, 12), (5, 3, 3)])
+@pytest.mark.parametrize("k,m,lb", [(31, 11, 10), (21, 9, 6), (15, 15, 4), (32, 7, 12), (5, 3, 3), (47, 13, 9), (64, 32, 5)])
 def test_superkmers_tile_the_valid_windows_exactly(oracle, k, m, lb):
     from oracle import superkmer as S
     rng = np.random.default_rng(k)
@@ -44,7 +44,7 @@ def test_bin_depends_on_the_kmer_only(oracle):
     assert d1 == d2 and len(set(d1.values())) > 100
 
 
-@pytest.mark.parametrize("k,m,lb", [(31, 11, 8), (13, 7, 5)])
+@pytest.mark.parametrize("k,m,lb", [(31, 11, 8), (13, 7, 5), (40, 11, 7)])
 def test_counting_bin_by_bin_gives_the_group_histogram(oracle, k, m, lb):
     from khoice_b200 import synth
     from oracle import superkmer as S
@@ -54,4 +54,5 @@ def test_counting_bin_by_bin_gives_the_group_histogram(oracle, k, m, lb):
     w_ref, _, st = oracle.exp1(genomes, [0] * len(genomes), 1, k, nbins=64)
     assert np.array_equal(hist, w_ref[0])
     allk = np.concatenate(list(sets.values()))
-    assert allk.size == np.unique(allk).size == st["sum_group_distinct"]      # bins are disjoint
+    n_unique = np.unique(allk).size if k <= 32 else np.unique(allk, axis=0).shape[0]
+    assert allk.shape[0] == n_unique == st["sum_group_distinct"]      # bins are disjoint
