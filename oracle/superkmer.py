@@ -149,3 +149,18 @@ def binned_group_histogram(genomes, k: int, m: int, log2_bins: int, nbins: int =
         np.add.at(hist, np.minimum(cnt, nbins), 1)
         sets[b] = keys
     return hist, sets
+
+
+def binned_across_histogram(group_bin_sets, k: int, nbins: int = 5000):
+    """The across-group stage computed BIN BY BIN: group_bin_sets[g] = {bin: distinct k-mers of group g in that bin} (the second
+    result of binned_group_histogram).  Because the bin is a function of the k-mer alone, every copy of a k-mer sits in the same
+    bin in every group: hist[c] = number of k-mers found in exactly c groups needs no exchange between bins."""
+    hist = np.zeros(nbins + 1, dtype=np.uint64)
+    total = 0
+    for b in sorted(set().union(*[set(s) for s in group_bin_sets])):
+        parts = [s[b] for s in group_bin_sets if b in s]
+        cat = np.concatenate(parts)
+        _, cnt = np.unique(cat, return_counts=True) if k <= 32 else np.unique(cat, axis=0, return_counts=True)
+        np.add.at(hist, np.minimum(cnt, nbins), 1)
+        total += cnt.size
+    return hist, total

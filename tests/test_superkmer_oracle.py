@@ -56,3 +56,21 @@ def test_counting_bin_by_bin_gives_the_group_histogram(oracle, k, m, lb):
     allk = np.concatenate(list(sets.values()))
     n_unique = np.unique(allk).size if k <= 32 else np.unique(allk, axis=0).shape[0]
     assert allk.shape[0] == n_unique == st["sum_group_distinct"]      # bins are disjoint
+
+
+@pytest.mark.parametrize("k,m,lb", [(31, 11, 8), (35, 11, 6)])
+def test_across_group_stage_bin_by_bin(oracle, k, m, lb):
+    """A k-mer lands in the same bin in every group, so the step_8 histogram is the sum of per-bin counts over the groups' sets."""
+    from khoice_b200 import synth
+    from oracle import superkmer as S
+    cfg = synth.SynthConfig(n_groups=4, genomes_per_group=3, genome_len=15_000, seed=29)
+    groups = [[synth.make_genome(cfg, g, i) for i in range(1, 4)] for g in range(1, 5)]
+    per_group = []
+    for gi, genomes in enumerate(groups):
+        hist, sets = S.binned_group_histogram(genomes, k, m, lb, nbins=64)
+        per_group.append(sets)
+    flat = [t for g in groups for t in g]
+    gid = [gi for gi, g in enumerate(groups) for _ in g]
+    w_ref, a_ref, st = oracle.exp1(flat, gid, 4, k, nbins=64)
+    across, distinct = S.binned_across_histogram(per_group, k, nbins=64)
+    assert np.array_equal(across, a_ref) and distinct == st["distinct"]
