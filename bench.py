@@ -6,26 +6,37 @@ the workload below: every group's step_4 histogram plus the step_8 across-group 
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-N=1 workload: BASELINE config 2 -- 10 groups x 50 synthetic 5 Mbp genomes (2.5 Gbp), k=31, single B200.
-N>1 (torchrun, one rank per GPU): weak scaling -- every rank owns 10 such groups; steps 1-6 need no
-collective; for the across-group stage every group's distinct k-mers are pushed to their hash-range owner over peer memory
-(csrc/peer.cu) -- or one NCCL all-to-all (KHB_EXCHANGE=nccl) -- then a local count and a histogram all-reduce (khoice_b200/dist.py).
+Workloads (KHB_BENCH_CONFIG, default 2 -- the configuration BASELINE.json's metric is quoted on):
+  2  10 groups x 50 synthetic 5 Mbp genomes PER GPU (2.5 Gbp per GPU), k=31; weak scaling
+  3  the k sweep 7..31 (odd) over the config-2 set, 2-bit stream packed once (value = bases x k values / s)
+  4  20 groups x 100 genomes in total (10 Gbp), k=47 (KHB_BENCH_K=63 for the other half), 128-bit words; strong scaling
+  5  100 groups x 200 genomes in total (~100 Gbp), k=31, groups dealt over the ranks; strong scaling -- the north-star target
+
+N>1 (torchrun, one rank per GPU): steps 1-6 need no collective; for the across-group stage every group's distinct k-mers are
+pushed to their hash-range owner over peer memory (csrc/peer.cu) -- or one NCCL all-to-all (KHB_EXCHANGE=nccl) -- then a
+local count and a histogram all-reduce (khoice_b200/dist.py).
 
 value   Gbases/s with the FASTA text already staged in HBM when the clock starts (khb_group_from_staged)
 e2e     the same job through khb_group_from_fasta with the text in pinned HOST memory: H2D copies of all
         text and D2H of every histogram inside the timed region
-roofline  dominant kernel = onesweep_kernel (one radix digit pass): algorithmic bytes 2*W per key per launch,
-        timed with CUDA events on the library's stream during the timed steps (khb_profile_*)
+roofline  the kernel with the largest share of the step: algorithmic bytes per launch over its CUDA-event
+        time on the library's stream during the timed steps (khb_profile_*)
+pipeline_roofline  the whole step, on this design's own byte contract and on SURVEY.md 8(d)'s KMC-shaped contract
 cpu_baseline  the CPU oracle (oracle/, OpenMP) on a bounded sample of the same workload, rank 0, N=1 only
+parity_in_run  the GPU histograms of that sample == the oracle's (N=1); N>1: conservation laws of the all-reduced tables and
+        one group of another rank recomputed on rank 0.  A false value fails the run (exit 2).
 
-Environment overrides for quick runs: KHB_BENCH_GROUPS, KHB_BENCH_GENOMES, KHB_BENCH_LEN, KHB_BENCH_K.
+Overrides for quick runs: KHB_BENCH_GROUPS (per GPU), KHB_BENCH_GROUPS_TOTAL, KHB_BENCH_GENOMES, KHB_BENCH_LEN, KHB_BENCH_K,
+KHB_BENCH_E2E=0 (skip the host-buffer leg), KHB_BENCH_CSV_DIR (write step_5 / step_9 CSVs of the run there).
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import multiprocessing as mp
 import os
+import shutil
 import statistics
 import subprocess
 import sys
@@ -40,28 +51,63 @@ sys.path.insert(0, ROOT)
 METRIC = "Gbases/s to final k-mer occurrence tables (k=31)"
 UNIT = "Gbases/s"
 
+CONFIGS = {
+    "2": {"name": "config 2", "groups_per_gpu": 10, "genomes": 50, "k": 31, "scaling": "weak"},
+    "3": {"name": "config 3 (k sweep 7..31 odd over the config-2 set)", "groups_per_gpu": 10, "genomes": 50, "k": 31, "scaling": "weak",
+          "ks": list(range(7, 32, 2))},
+    "4": {"name": "config 4", "groups_total": 20, "genomes": 100, "k": 47, "scaling": "strong"},
+    "5": {"name": "config 5", "groups_total": 100, "genomes": 200, "k": 31, "scaling": "strong"},
+}
+
 
 def env_int(name, default):
     return int(os.environ.get(name, default))
 
 
-def workload():
-    return {"groups_per_gpu": env_int("KHB_BENCH_GROUPS", 10), "genomes": env_int("KHB_BENCH_GENOMES", 50),
-            "genome_len": env_int("KHB_BENCH_LEN", 5_000_000), "k": env_int("KHB_BENCH_K", 31)}
+def workload(world: int = 1):
+    key = os.environ.get("KHB_BENCH_CONFIG", "2")
+    if key not in CONFIGS:
+        raise SystemExit(f"KHB_BENCH_CONFIG={key}: expected one of {sorted(CONFIGS)}")
+    c = dict(CONFIGS[key])
+    wl = {"config": key, "name": c["name"], "scaling": c["scaling"], "genomes": env_int("KHB_BENCH_GENOMES", c["genomes"]),
+          "genome_len": env_int("KHB_BENCH_LEN", 5_000_000), "k": env_int("KHB_BENCH_K", c["k"]), "ks": c.get("ks")}
+    if "KHB_BENCH_GROUPS_TOTAL" in os.environ:
+        wl["groups_total"], wl["scaling"] = env_int("KHB_BENCH_GROUPS_TOTAL", 0), "strong"
+    elif "KHB_BENCH_GROUPS" in os.environ or "groups_per_gpu" in c:
+        wl["groups_per_gpu"] = env_int("KHB_BENCH_GROUPS", c.get("groups_per_gpu", 10))
+        wl["groups_total"], wl["scaling"] = wl["groups_per_gpu"] * world, "weak"
+    else:
+        wl["groups_total"] = c["groups_total"]
+    wl["groups_per_gpu"] = wl.get("groups_per_gpu", -(-wl["groups_total"] // world))
+    overridden = any(v in os.environ for v in ("KHB_BENCH_GROUPS", "KHB_BENCH_GROUPS_TOTAL", "KHB_BENCH_GENOMES", "KHB_BENCH_LEN")) or \
+        (key != "4" and "KHB_BENCH_K" in os.environ)
+    wl["default_shape"] = not overridden
+    return wl
 
 
 def _gen_group(args):
     from khoice_b200 import synth
-    cfg, g = args
-    return g, [synth.make_genome(cfg, g, i) for i in range(1, cfg.genomes_per_group + 1)]
+    cfg, g, n = args
+    return g, [synth.make_genome(cfg, g, i) for i in range(1, n + 1)]
 
 
-def generate_groups(cfg, group_numbers, procs):
+def _gen_genome(args):
+    from khoice_b200 import synth
+    cfg, g, i = args
+    return g, i, synth.make_genome(cfg, g, i)
+
+
+def generate_groups(cfg, group_numbers, procs, genomes=None):
     """{group: [fasta bytes]} generated with a fork pool (must run before CUDA is initialised)."""
-    if procs <= 1 or len(group_numbers) <= 1:
-        return dict(_gen_group((cfg, g)) for g in group_numbers)
-    with mp.get_context("fork").Pool(min(procs, len(group_numbers))) as pool:
-        return dict(pool.imap_unordered(_gen_group, [(cfg, g) for g in group_numbers]))
+    n = genomes or cfg.genomes_per_group
+    if procs <= 1 or len(group_numbers) * n <= 2:
+        return dict(_gen_group((cfg, g, n)) for g in group_numbers)
+    out = {g: [None] * n for g in group_numbers}
+    jobs = [(cfg, g, i) for g in group_numbers for i in range(1, n + 1)]   # per genome: few big groups still use every worker
+    with mp.get_context("fork").Pool(min(procs, len(jobs))) as pool:
+        for g, i, text in pool.imap_unordered(_gen_genome, jobs, chunksize=max(1, n // 8)):
+            out[g][i - 1] = text
+    return out
 
 
 class ClockSampler:
@@ -137,62 +183,104 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-def ncu_traffic_ratio():
-    """dram bytes / algorithmic bytes of onesweep_kernel from the committed ncu capture (profiles/), or None."""
-    p = os.path.join(ROOT, "profiles", "onesweep_traffic.json")
+def ncu_traffic(kernel: str):
+    """(dram bytes / algorithmic bytes, label) of `kernel` from the committed ncu capture (profiles/<kernel>_traffic.json), or
+    (None, why).  The ratio is a property of the kernel variant named in the file, not measured in this run: ncu cannot run
+    inside the timed region."""
+    p = os.path.join(ROOT, "profiles", f"{kernel}_traffic.json")
     if os.path.exists(p):
         try:
             d = json.load(open(p))
-            return float(d["dram_bytes_per_launch"]) / float(d["algorithmic_bytes_per_launch"])
-        except Exception:
-            return None
-    return None
+            return float(d["dram_bytes_per_launch"]) / float(d["algorithmic_bytes_per_launch"]), f"ncu --set full capture {d.get('captured', '?')} of {d.get('variant', kernel)}"
+        except Exception as e:
+            return None, f"unreadable {p}: {e}"
+    return None, "no ncu capture committed for this kernel"
+
+
+# Dominant-kernel descriptions for the roofline object: profile id -> (kernel, what bounds it)
+KERNEL_INFO = {
+    "onesweep": ("onesweep_kernel (one 8-bit radix pass over (key, genome id) records)", "hbm"),
+    "pack": ("fasta_summary/scan/pack_kernel (K1)", "hbm"),
+    "extract": ("extract64/128_kernel (K2)", "hbm"),
+    "radix_hist": ("radix_hist_kernel", "hbm"),
+    "unique": ("pairs/runs kernels (K4/K5/K6)", "hbm"),
+    "rle_hist": ("rle_hist_kernel", "hbm"),
+    "partition": ("partition / push kernels (K7)", "hbm"),
+    "hash_insert": ("hash_insert_kernel", "hbm"),
+    "hash_count": ("hash_count_kernel", "hbm"),
+    "bin_partition": ("bin_partition_kernel (minimizer bins: packed stream -> super-k-mer records)", "hbm"),
+    "bin_count": ("bin_count_kernel (one CTA per bin: shared-memory (k-mer, genome bits) table)", "hbm"),
+    "bin_across": ("bin_across_kernel (one CTA per bin over the groups' distinct keys)", "hbm"),
+}
+
+# SURVEY.md 8(d): bytes per input base of the KMC-shaped chain (sort, unique, sort, count per genome / group / across) at
+# W = 8 (k <= 32) with P = ceil(2k/8) passes:  K1 1.39 + K2 (3/8 + W) + K3 W(2P+1) + K4 2W + K3' W(2P+1) + K5 W(1+rho) + K3'' W(2P+1) rho + K6 W rho
+def survey_bytes_per_base(k: int, rho: float) -> float:
+    W = 8 if k <= 32 else 16
+    P = -(-2 * k // 8)
+    return 1.39 + (0.375 + W) + W * (2 * P + 1) + 2 * W + W * (2 * P + 1) + W * (1 + rho) + W * (2 * P + 1) * rho + W * rho
 
 
 # ---------------------------------------------------------------------------------------------------------
-def run_reference(args):
-    """Reference arm: the reference's own implementation of this path is KMC 3.2.1 on the host cores; it is
-    not installable here (no source under /root/reference, no network), so the arm times the CPU oracle port
-    (oracle/kmer_oracle.c, OpenMP over genomes and groups like `snakemake --cores`) on a bounded sample."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return 0
-    from khoice_b200 import synth
-    from oracle import oracle as O
-    wl = workload()
-    O.build()
-    cores = O.num_threads()
-    k = wl["k"]
-    cfg1 = synth.SynthConfig(n_groups=1, genomes_per_group=1, genome_len=wl["genome_len"])
-    probe = synth.make_genome(cfg1, 1, 1)
+def find_kmc():
+    """SURVEY.md 8(c), last row: a real KMC 3 on PATH or under baseline/_ref/ (never shipped, never installable here)."""
+    found = {}
+    for exe in ("kmc", "kmc_tools"):
+        p = shutil.which(exe)
+        if not p:
+            hits = [h for h in glob.glob(os.path.join(ROOT, "baseline", "_ref", "**", exe), recursive=True) if os.access(h, os.X_OK)]
+            p = hits[0] if hits else None
+        if p:
+            found[exe] = p
+    return found if len(found) == 2 else None
+
+
+def run_kmc_chain(kmc, groups, k, work):
+    """The UNMODIFIED shell strings of /root/reference/workflow/rules/exp_type_1.smk:163,173,182,191,241,250,259 on `groups`
+    ({group: [fasta bytes]}) with a real KMC; returns (within hists, across hist, seconds).  Used for timing AND as the
+    parity pin: the caller diffs these histograms with the oracle's and the GPU's."""
+    import gzip
+    from khoice_b200 import pipeline, tables
+    env = dict(os.environ, PATH=os.path.dirname(kmc["kmc"]) + os.pathsep + os.path.dirname(kmc["kmc_tools"]) + os.pathsep + os.environ.get("PATH", ""))
+    nums = sorted(groups)
+    for n in nums:
+        os.makedirs(os.path.join(work, f"data/dataset_{n}"), exist_ok=True)
+        for i, text in enumerate(groups[n], 1):
+            with gzip.open(os.path.join(work, f"data/dataset_{n}/g{i}.fna.gz"), "wb", compresslevel=1) as fd:
+                fd.write(bytes(text))
+    pipeline.write_complex_ops(work, [str(k)], len(nums))
+    os.makedirs(os.path.join(work, "tmp"), exist_ok=True)
     t0 = time.time()
-    O.exp1([probe], [0], 1, k)
-    per_genome = max(time.time() - t0, 1e-3)
-    total_steps = args.steps + args.warmup
-    budget = 150.0 / max(total_steps, 1)                         # seconds per step
-    n_groups, genomes = sample_shape(wl, per_genome, cores, budget)
-    cfg = synth.SynthConfig(n_groups=n_groups, genomes_per_group=genomes, genome_len=wl["genome_len"])
-    groups = generate_groups(cfg, list(range(1, n_groups + 1)), min(cores, n_groups))
-    flat = [f for g in range(1, n_groups + 1) for f in groups[g]]
-    gid = [g for g in range(n_groups) for _ in range(genomes)]
-    bases = sum(synth.count_bases(f) for f in flat)
-    for _ in range(args.warmup):
-        O.exp1(flat, gid, n_groups, k)
-    t0 = time.time()
-    for _ in range(args.steps):
-        O.exp1(flat, gid, n_groups, k)
-    dt = (time.time() - t0) / max(args.steps, 1)
-    val = bases / dt / 1e9
-    sample = f"{n_groups} groups x {genomes} genomes x {wl['genome_len']} bp ({bases} bases) per step, k={k}"
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "bounded sample of config 2 (10 groups x 50 synthetic 5 Mbp genomes, k=31): " + sample,
-                       "note": "KMC 3.2.1 (the reference's engine) is not in /root/reference and not installed: CPU oracle port timed"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
-    return 0
+
+    def sh(cmd):
+        subprocess.run(cmd, shell=True, check=True, cwd=work, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    for n in nums:
+        for g in pipeline.genomes_of(work, n):
+            for d in (pipeline.p_step1(k, n, g), pipeline.p_step2(k, n, g)):
+                os.makedirs(os.path.dirname(os.path.join(work, d)), exist_ok=True)
+            sh(f"kmc -fm -m64 -k{k} -ci1 {pipeline.p_genome(n, g)} {pipeline.p_step1(k, n, g)} tmp/")
+            sh(f"kmc_tools transform {pipeline.p_step1(k, n, g)} set_counts 1 {pipeline.p_step2(k, n, g)}")
+        for d in (pipeline.p_step3(k, n), pipeline.p_step4(k, n), pipeline.p_step6(k, n)):
+            os.makedirs(os.path.dirname(os.path.join(work, d)), exist_ok=True)
+        sh(f"kmc_tools complex {pipeline.p_ops_within(k, n)}")
+        sh(f"kmc_tools transform {pipeline.p_step3(k, n)} histogram {pipeline.p_step4(k, n)}")
+        sh(f"kmc_tools transform {pipeline.p_step3(k, n)} set_counts 1 {pipeline.p_step6(k, n)}")
+    for d in (pipeline.p_step7(k), pipeline.p_step8(k)):
+        os.makedirs(os.path.dirname(os.path.join(work, d)), exist_ok=True)
+    sh(f"kmc_tools complex {pipeline.p_ops_across(k)}")
+    sh(f"kmc_tools transform {pipeline.p_step7(k)} histogram {pipeline.p_step8(k)}")
+    dt = time.time() - t0
+    # file row i is occurrence i + 1; the in-memory histograms are indexed by occurrence (index 0 unused)
+    within = [[0] + tables.read_histogram_file(os.path.join(work, pipeline.p_step4(k, n))) for n in nums]
+    across = [0] + tables.read_histogram_file(os.path.join(work, pipeline.p_step8(k)))
+    return within, across, dt
+
+
+def _same_hist(a, b):
+    """Histograms equal up to trailing zero rows (KMC's own row count is its default, ours is 5000)."""
+    a, b = np.asarray(a, dtype=np.uint64), np.asarray(b, dtype=np.uint64)
+    n = max(a.size, b.size)
+    return np.array_equal(np.pad(a, (0, n - a.size)), np.pad(b, (0, n - b.size)))
 
 
 def sample_shape(wl, per_genome, cores, seconds):
@@ -209,11 +297,14 @@ def sample_shape(wl, per_genome, cores, seconds):
     return n_groups, genomes
 
 
-def cpu_baseline(wl, seconds=20.0):
+def cpu_sample(wl, seconds, steps=1, warmup=0):
+    """The CPU arm on a bounded sample of the workload, with ALL host cores (explicitly: torchrun exports OMP_NUM_THREADS=1).
+    A real KMC 3 (PATH or baseline/_ref) runs the unmodified rule chain -> kind "reference"; otherwise the oracle port.
+    Returns (cpu_baseline dict, sample dict with the texts and the histograms for the in-run parity check)."""
     from khoice_b200 import synth
     from oracle import oracle as O
     O.build()
-    cores = O.num_threads()
+    cores = O.set_num_threads(O.host_cores())
     k = wl["k"]
     cfg1 = synth.SynthConfig(n_groups=1, genomes_per_group=1, genome_len=wl["genome_len"])
     probe = synth.make_genome(cfg1, 1, 1)
@@ -222,18 +313,85 @@ def cpu_baseline(wl, seconds=20.0):
     per_genome = max(time.time() - t0, 1e-3)
     n_groups, genomes = sample_shape(wl, per_genome, cores, seconds)
     cfg = synth.SynthConfig(n_groups=n_groups, genomes_per_group=genomes, genome_len=wl["genome_len"])
-    groups = generate_groups(cfg, list(range(1, n_groups + 1)), min(cores, n_groups))
+    groups = generate_groups(cfg, list(range(1, n_groups + 1)), min(cores, 16), genomes=genomes)
     flat = [f for g in range(1, n_groups + 1) for f in groups[g]]
+    gid = [g for g in range(n_groups) for _ in range(genomes)]
     bases = sum(synth.count_bases(f) for f in flat)
+    for _ in range(warmup):
+        O.exp1(flat, gid, n_groups, k)
     t0 = time.time()
-    O.exp1(flat, [g for g in range(n_groups) for _ in range(genomes)], n_groups, k)
-    dt = time.time() - t0
-    return {"value": bases / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"CPU oracle (oracle/kmer_oracle.c, OpenMP) on {n_groups} groups x {genomes} genomes x {wl['genome_len']} bp, k={k}: "
-                      f"{bases} bases in {dt:.1f} s; KMC3 itself is unavailable (not in /root/reference, not installed)"}
+    for _ in range(max(steps, 1)):
+        within, across, _ = O.exp1(flat, gid, n_groups, k)
+    dt = (time.time() - t0) / max(steps, 1)
+    shape = f"{n_groups} groups x {genomes} genomes x {wl['genome_len']} bp ({bases} bases), k={k}"
+    base = {"value": bases / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"CPU oracle (oracle/kmer_oracle.c, OpenMP, {cores} threads) on {shape}: {dt:.1f} s per pass; "
+                      "KMC3 itself is unavailable (not in /root/reference, not on PATH, nothing under baseline/_ref)"}
+    kmc = find_kmc()
+    kmc_diff = None
+    if kmc:
+        work = tempfile.mkdtemp(prefix="khb_kmc_")
+        try:
+            kw, ka, kdt = run_kmc_chain(kmc, groups, k, work)
+            kmc_diff = {"within_equal_oracle": all(_same_hist(kw[i], within[i]) for i in range(n_groups)), "across_equal_oracle": _same_hist(ka, across)}
+            base = {"value": bases / kdt / 1e9, "unit": UNIT, "cores": cores, "kind": "reference",
+                    "sample": f"KMC3 ({kmc['kmc']}) + kmc_tools, the unmodified exp_type_1.smk shell strings, on {shape}: {kdt:.1f} s; "
+                              f"histograms vs the oracle: {kmc_diff}"}
+        except Exception as e:  # a broken binary must not take the bench down: report and keep the port
+            base["sample"] += f"; a KMC binary was found ({kmc['kmc']}) but its rule chain failed: {e}"
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
+    return base, {"groups": groups, "n_groups": n_groups, "genomes": genomes, "within": within, "across": across, "bases": bases,
+                  "shape": shape, "kmc_diff": kmc_diff, "seconds": dt}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own implementation of this path is KMC 3.2.1 on the host cores.  If a KMC binary is on
+    PATH or under baseline/_ref it runs the unmodified rule chain; otherwise (this image: no source under /root/reference,
+    no network) the arm times the CPU oracle port (oracle/kmer_oracle.c, OpenMP over genomes and key ranges, like
+    `snakemake --cores`) -- on a bounded sample, on rank 0 only, with every host core whatever OMP_NUM_THREADS says."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    wl = workload(int(os.environ.get("WORLD_SIZE", "1")))
+    total_steps = args.steps + args.warmup
+    base, smp = cpu_sample(wl, 150.0 / max(total_steps, 1), steps=args.steps, warmup=args.warmup)
+    val = base["value"]
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": smp["bases"] / val / 1e6, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
+            "dtype": "u64" if wl["k"] <= 32 else "u128", "data": "synthetic",
+            "config": {"workload": f"bounded sample of {wl['name']}: " + smp["shape"] + " per step",
+                       "note": "host CPU arm; its value is a throughput on the sample and does not depend on the GPU count"},
+            "cpu_baseline": base,
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
 
 
 # ---------------------------------------------------------------------------------------------------------
+def write_csvs(out_dir, wl, within, across_by_k, n_groups_total):
+    """step_4 / step_8 histogram files and the step_5 / step_9 CSVs of this run through the product's own writers
+    (khoice_b200.tables, the rules within_group_union_analysis / across_group_union_analysis)."""
+    from khoice_b200 import pipeline, tables
+    os.makedirs(out_dir, exist_ok=True)
+    work = tempfile.mkdtemp(prefix="khb_bench_root_")
+    try:
+        for n in range(1, n_groups_total + 1):   # group membership = the *.fna.gz listing (exp_type_1.smk:107-113)
+            d = os.path.join(work, f"data/dataset_{n}")
+            os.makedirs(d)
+            for i in range(wl["genomes"]):
+                open(os.path.join(d, f"g{i + 1}.fna.gz"), "wb").close()
+        ks = sorted(across_by_k)
+        for k in ks:
+            for n in range(1, n_groups_total + 1):
+                tables.write_histogram_file(os.path.join(work, pipeline.p_step4(str(k), n)), within[k][n - 1])
+            tables.write_histogram_file(os.path.join(work, pipeline.p_step8(str(k))), across_by_k[k])
+        pipeline.build_tables(work, [str(k) for k in ks], n_groups_total)
+        for p in (pipeline.P_STEP5, pipeline.P_STEP9):
+            shutil.copyfile(os.path.join(work, p), os.path.join(out_dir, os.path.basename(p)))
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -246,14 +404,15 @@ def main():
         return run_reference(args)
 
     from khoice_b200 import synth
-    wl = workload()
-    k = wl["k"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = workload(world)
+    k = wl["k"]
+    ks = wl["ks"] or [k]
     if world != args.gpus and world > 1:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
-    n_groups_total = wl["groups_per_gpu"] * world
+    n_groups_total = wl["groups_total"]
     cfg = synth.SynthConfig(n_groups=n_groups_total, genomes_per_group=wl["genomes"], genome_len=wl["genome_len"])
 
     # 1. synthetic data for this rank's groups (fork pool: before any CUDA initialisation)
@@ -261,7 +420,13 @@ def main():
     mine = groups_of_rank(n_groups_total, rank, world)
     procs = max(1, (os.cpu_count() or 8) // max(world, 1))
     t0 = time.time()
-    groups = generate_groups(cfg, mine, min(procs, 16))
+    groups = generate_groups(cfg, mine, min(procs, 32))
+    # N>1 parity: rank 0 recomputes one group owned by another rank
+    foreign = None
+    if world > 1 and rank == 0:
+        fg = groups_of_rank(n_groups_total, 1, world)
+        if fg:
+            foreign = (fg[0], generate_groups(cfg, [fg[0]], min(procs, 32))[fg[0]])
     gen_s = time.time() - t0
 
     import torch
@@ -275,10 +440,11 @@ def main():
     eng = Engine(local)
     ext_stream = torch.cuda.ExternalStream(eng.stream_ptr, device=dev)
     adapter = kd.CudaAdapter(eng, dev)
+    do_e2e = env_int("KHB_BENCH_E2E", 1) != 0
 
     # 2. pinned host copies (e2e leg) and HBM-resident staged copies (device leg)
     total_bytes = sum(len(f) for g in mine for f in groups[g])
-    pinned = torch.empty(total_bytes, dtype=torch.uint8, pin_memory=True)
+    pinned = torch.empty(max(total_bytes, 1), dtype=torch.uint8, pin_memory=do_e2e)
     pview = pinned.numpy()
     host_views, off = {}, 0
     for g in mine:
@@ -287,8 +453,13 @@ def main():
             pview[off:off + len(f)] = np.frombuffer(f, dtype=np.uint8)
             host_views[g].append(pview[off:off + len(f)])
             off += len(f)
-    staged = {g: eng.stage_fasta(host_views[g]) for g in mine}
-    groups = None  # the bytes now live in pinned memory and in HBM
+    groups = None  # the bytes now live in pinned memory (and, below, in HBM)
+    sweep = wl["ks"] is not None
+    staged, packed = {}, {}
+    if sweep:
+        packed = {g: eng.pack_group(host_views[g]) for g in mine}      # config 3: K1 once, the 2-bit stream stays in HBM
+    else:
+        staged = {g: eng.stage_fasta(host_views[g]) for g in mine}
 
     def barrier():
         eng.sync()
@@ -301,37 +472,51 @@ def main():
     # round (a warm-up step) runs over NCCL (partition + all-to-all) and sizes the regions.  KHB_EXCHANGE=nccl keeps NCCL.
     ex = kd.AcrossExchanger(adapter, k, n_groups_total, mode=os.environ.get("KHB_EXCHANGE", "peer"))
 
-    def step_device():
+    def run_k(kk, group_fn):
         eng.group_sets_reset()
+        ex.set_k(kk)
         ex.begin()
-        hs, nb = {}, 0
-        for g in mine:
-            hs[g], st = eng.group_from_staged(staged[g], k)
+        hs, nb, dsum = {}, 0, 0
+        for i, g in enumerate(mine):
+            hs[g], st = group_fn(i, g, kk)
             ex.after_group()
             nb += st["bases"]
+            dsum += st["distinct"]
         ha, _ = ex.finish()
-        return hs, ha, nb
+        return hs, ha, nb, dsum
+
+    def step_device():
+        out = {}
+        for kk in ks:
+            if sweep:
+                out[kk] = run_k(kk, lambda i, g, kk: eng.group_from_packed(packed[g], kk))
+            else:
+                out[kk] = run_k(kk, lambda i, g, kk: eng.group_from_staged(staged[g], kk))
+        return out
 
     pipelined = {"next": False}
+
+    def e2e_group(i, g, kk):
+        nxt = mine[i + 1] if i + 1 < len(mine) else mine[0]
+        eng.prefetch_fasta(host_views[nxt])                  # H2D of the next group overlaps this group's kernels
+        return eng.group_from_fasta(host_views[g], kk)       # uses the prefetched copy, waits for it on the device
 
     def step_e2e():
         # a stream of jobs: while the last group of a job and its across-group stage run, the first group of the NEXT job is
         # already being copied (every step still copies all of its text inside the timed region; only the very first step's
         # first group is copied ahead of its compute instead of behind the previous step's tail)
-        eng.group_sets_reset()
-        ex.begin()
-        hs, nb = {}, 0
-        if not pipelined["next"]:
+        if sweep:
+            # config 3: H2D + K1 once per step, then the sweep on the resident 2-bit stream
+            pk = {g: eng.pack_group(host_views[g]) for g in mine}
+            try:
+                return {kk: run_k(kk, lambda i, g, kk: eng.group_from_packed(pk[g], kk)) for kk in ks}
+            finally:
+                for p in pk.values():
+                    p.free()
+        if not pipelined["next"] and mine:
             eng.prefetch_fasta(host_views[mine[0]])
-        for i, g in enumerate(mine):
-            nxt = mine[i + 1] if i + 1 < len(mine) else mine[0]
-            eng.prefetch_fasta(host_views[nxt])                  # H2D of the next group overlaps this group's kernels
-            hs[g], st = eng.group_from_fasta(host_views[g], k)   # uses the prefetched copy, waits for it on the device
-            ex.after_group()
-            nb += st["bases"]
         pipelined["next"] = True
-        ha, _ = ex.finish()
-        return hs, ha, nb
+        return {k: run_k(k, e2e_group)}
 
     def timed(fn, steps, profile=False, sampler=None):
         barrier()
@@ -361,81 +546,160 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return out, float(t.item()), wall, eng.launch_count - launches0, prof, clocks
 
+    def equal_runs(a, b):
+        return all(all(np.array_equal(a[kk][0][g], b[kk][0][g]) for g in mine) and np.array_equal(a[kk][1], b[kk][1]) for kk in ks)
+
     # 3. device-resident leg
     sampler = ClockSampler(local) if rank == 0 else None  # started before the warm-up, filtered to the timed region
+    ref_out = None
     for _ in range(args.warmup):
         ref_out = step_device()
-    (hs, ha, nb), ms_dev, wall_dev, launches, prof, clocks = timed(step_device, args.steps, profile=True, sampler=sampler)
+    out_dev, ms_dev, wall_dev, launches, prof, clocks = timed(step_device, args.steps, profile=True, sampler=sampler)
+    same = ref_out is None or equal_runs(out_dev, ref_out)
     # 4. end-to-end leg (host buffers)
-    for _ in range(min(args.warmup, 2)):
-        step_e2e()
-    (hs2, ha2, nb2), ms_e2e, wall_e2e, _, _, _ = timed(step_e2e, args.steps)
-    same = all(np.array_equal(hs[g], hs2[g]) for g in mine) and np.array_equal(ha, ha2) and np.array_equal(ha, ref_out[1])
+    ms_e2e = None
+    if do_e2e:
+        for _ in range(min(args.warmup, 2)):
+            step_e2e()
+        out_e2e, ms_e2e, wall_e2e, _, _, _ = timed(step_e2e, args.steps)
+        same = same and equal_runs(out_dev, out_e2e)
     if not same:
-        print("FATAL: device-resident and end-to-end legs disagree", file=sys.stderr)
+        print("FATAL: device-resident, warm-up and end-to-end legs disagree", file=sys.stderr)
         return 2
 
+    nb = sum(out_dev[kk][2] for kk in ks)          # bases processed per step (config 3: every k counts the set again)
     tb = torch.tensor([float(nb), float(total_bytes)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tb, op=dist.ReduceOp.SUM)
     bases_all, bytes_all = float(tb[0].item()), float(tb[1].item())
     value = bases_all * args.steps / (ms_dev * 1e-3) / 1e9
-    e2e_value = bases_all * args.steps / (ms_e2e * 1e-3) / 1e9
+    e2e_value = bases_all * args.steps / (ms_e2e * 1e-3) / 1e9 if ms_e2e else None
 
+    # 5. every rank's within-group histograms -> one table (what run_fused_distributed writes as step_4), conservation laws
+    nbins1 = 5001
+    within_all, dsum_all = {}, {}
+    for kk in ks:
+        w = np.zeros((n_groups_total, nbins1 + 1), dtype=np.int64)   # last column: distinct k-mers of the group
+        for g in mine:
+            w[g - 1, :nbins1] = out_dev[kk][0][g].astype(np.int64)
+            w[g - 1, nbins1] = int(out_dev[kk][0][g][1:].sum())
+        wt = torch.from_numpy(w).to(dev)
+        if world > 1:
+            dist.all_reduce(wt, op=dist.ReduceOp.SUM)
+        within_all[kk] = wt.cpu().numpy()
+        dsum_all[kk] = int(within_all[kk][:, nbins1].sum())
+    parity = {"checks": []}
+    ok = True
+    for kk in ks:
+        ha = out_dev[kk][1].astype(np.int64)
+        c = np.arange(ha.size, dtype=np.int64)
+        # every (k-mer, group) pair is counted exactly once: sum_c c * H[c] = sum_G D_G  (no counter reaches the 5000 cap here)
+        law = int((c * ha).sum()) == dsum_all[kk] and int(ha[0]) == 0
+        parity["checks"].append({"k": kk, "sum_c_times_H_equals_sum_D_G": law, "sum_D_G": dsum_all[kk], "distinct_overall": int(ha.sum())})
+        ok = ok and law
+    if foreign is not None:
+        fg, texts = foreign
+        eng.group_sets_reset()
+        h1, _ = eng.group_from_fasta(texts, k, keep_set=False)
+        eq = bool(np.array_equal(h1.astype(np.int64), within_all[k][fg - 1, :nbins1]))
+        parity["checks"].append({"group_of_rank_1_recomputed_on_rank_0": fg, "equal": eq})
+        ok = ok and eq
+        foreign = None
+
+    rc = 0
     if rank == 0:
         peak, peak_src = measured_peak()
-        osw = prof["onesweep"]
-        achieved = osw["alg_bytes"] / (osw["ms"] * 1e-3) / 1e9 if osw["ms"] > 0 else 0.0
-        ratio = ncu_traffic_ratio()
-        per_launch_alg = osw["alg_bytes"] / max(osw["launches"], 1)
+        live = {name: v for name, v in prof.items() if v["launches"]}
+        dom = max(live, key=lambda n: live[n]["ms"])
+        dk = live[dom]
+        achieved = dk["alg_bytes"] / (dk["ms"] * 1e-3) / 1e9 if dk["ms"] > 0 else 0.0
+        per_launch_alg = dk["alg_bytes"] / max(dk["launches"], 1)
+        ratio, ratio_src = ncu_traffic(dom)
         kernels = {name: {"launches": v["launches"], "ms": round(v["ms"], 3),
                           "alg_GBps": round(v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None,
-                          "share_of_step": round(v["ms"] / ms_dev, 4)} for name, v in prof.items()}
+                          "frac_of_peak": round(v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9 / peak, 3) if v["ms"] > 0 else None,
+                          "share_of_step": round(v["ms"] / ms_dev, 4)} for name, v in live.items()}
         # whole step against the roofline: algorithmic bytes of every kernel launched in the timed steps (this design's own
-        # per-kernel contracts) / device time of the steps.  Rank 0's kernels x world (weak scaling).
+        # per-kernel contracts) / device time of the steps.  Rank 0's kernels x world.
         total_alg = float(sum(v["alg_bytes"] for v in prof.values())) * world
+        rho = dsum_all[k] / max(sum(out_dev[k][0][g][1:].astype(np.float64) @ np.arange(1, nbins1) for g in mine) * world, 1.0) if mine else 0.0
+        sv = survey_bytes_per_base(k, rho)
         pipeline = {"algorithmic_bytes_per_base": total_alg / max(bases_all * args.steps, 1.0),
                     "achieved": total_alg / (ms_dev * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
                     "frac": total_alg / (ms_dev * 1e-3) / 1e9 / (peak * world) if peak else None,
-                    "note": "single-sort contract (~110 B/base); the KMC-shaped chain of SURVEY.md 8d (sort, unique, sort, count: ~329 B/base) "
-                            "would need 3x these bytes for the same tables"}
-        hist_bytes = (len(mine) + 1) * 5001 * 8
-        default_shape = (wl["groups_per_gpu"], wl["genomes"], wl["genome_len"], k) == (10, 50, 5_000_000, 31)
-        shape_name = "config 2" if default_shape else "custom shape (KHB_BENCH_* overrides)"
+                    "note": "this design's own byte contract: what its kernels must read and write once (DESIGN.md section 4)",
+                    "survey_8d": {"algorithmic_bytes_per_base": sv, "rho": rho, "achieved": sv * value, "frac": sv * value / (peak * world),
+                                  "note": "SURVEY.md 8(d)'s KMC-shaped chain (sort, unique, sort, count; P = ceil(2k/8) passes) priced at this run's "
+                                          "Gbases/s: above 1.0 means the same tables are produced faster than that chain could run at the HBM peak"}}
+        hist_bytes = (len(mine) + 1) * 5001 * 8 * len(ks)
+        shape_name = wl["name"] if wl["default_shape"] else wl["name"] + " shape with KHB_BENCH_* overrides"
+        per = f"{wl['groups_per_gpu']} groups x {wl['genomes']} synthetic {wl['genome_len']} bp genomes per GPU" if wl["scaling"] == "weak" else \
+            f"{n_groups_total} groups x {wl['genomes']} synthetic {wl['genome_len']} bp genomes in total"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"{shape_name}: {wl['groups_per_gpu']} groups x {wl['genomes']} synthetic {wl['genome_len']} bp genomes per GPU, k={k}"
-                                   + (f"; {world} GPUs, {n_groups_total} groups, hash-range all-to-all for the across-group stage" if world > 1 else ", single B200"),
-                       "k": k, "groups_total": n_groups_total, "genomes_per_group": wl["genomes"], "bases_per_step": bases_all,
-                       "l2": "inputs exceed L2: every sort streams >= 2 GB of keys through a 126 MB L2; no explicit flush",
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
+            "dtype": "u64" if max(ks) <= 32 else "u128", "data": "synthetic",
+            "config": {"workload": f"{shape_name}: {per}, k={k if not sweep else ','.join(map(str, ks))}"
+                                   + (f"; {world} GPUs, groups dealt round-robin, hash-range exchange for the across-group stage" if world > 1 else ", single B200"),
+                       "k": k if not sweep else ks, "groups_total": n_groups_total, "genomes_per_group": wl["genomes"], "bases_per_step": bases_all,
+                       "l2": "inputs exceed L2: every group streams >= 1 GB through a 126 MB L2; no explicit flush",
                        "parallelism": f"groups dealt round-robin to {world} rank(s)", "data_gen_s": round(gen_s, 1),
+                       "group_mode": os.environ.get("KHB_GROUP_MODE", "auto"),
                        "exchange": (f"peer-memory push (CUDA IPC over NVLink), {ex.rounds_peer} rounds; NCCL all-to-all, {ex.rounds_nccl} rounds (sizing / fallback)"
                                     if world > 1 else "none (one GPU)")},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_all, "d2h_bytes_per_step": float(hist_bytes * world),
-                    "ms_per_step": ms_e2e / args.steps,
-                    "note": "steps are pipelined like a stream of jobs: the H2D copy of a step's first group overlaps the previous step's last group and "
-                            "across-group stage; every step's text is copied inside the timed region"},
+            "e2e": ({"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_all, "d2h_bytes_per_step": float(hist_bytes * world),
+                     "ms_per_step": ms_e2e / args.steps,
+                     "note": "steps are pipelined like a stream of jobs: the H2D copy of a step's first group overlaps the previous step's last group and "
+                             "across-group stage; every step's text is copied inside the timed region"} if ms_e2e else None),
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "onesweep_kernel<Key64,14> (one 8-bit radix pass)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": KERNEL_INFO.get(dom, (dom, "hbm"))[1], "kernel": KERNEL_INFO.get(dom, (dom, "hbm"))[0], "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak if peak else None,
-                         "traffic": (ratio * per_launch_alg) if ratio else None, "algorithmic_bytes_per_launch": per_launch_alg,
-                         "launches": osw["launches"], "avg_launch_ms": osw["ms"] / max(osw["launches"], 1), "peak_source": peak_src},
+                         "traffic": (ratio * per_launch_alg) if ratio else None, "traffic_source": ratio_src,
+                         "algorithmic_bytes_per_launch": per_launch_alg,
+                         "launches": dk["launches"], "avg_launch_ms": dk["ms"] / max(dk["launches"], 1), "peak_source": peak_src,
+                         "share_of_step": dk["ms"] / ms_dev},
             "pipeline_roofline": pipeline,
             "kernels": kernels,
             "clocks": clocks,
             "wall_ms_per_step": wall_dev * 1e3 / args.steps,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(wl)
+            base, smp = cpu_sample(wl, 20.0)
+            line["cpu_baseline"] = base
+            # in-run parity: the GPU on exactly the sample's texts against the oracle's histograms
+            eng.group_sets_reset()
+            eqw = []
+            for g in range(1, smp["n_groups"] + 1):
+                hg, _ = eng.group_from_fasta(smp["groups"][g], k)
+                eqw.append(bool(np.array_equal(hg, smp["within"][g - 1])))
+            hga, _ = eng.across_groups()
+            eqa = bool(np.array_equal(hga, smp["across"]))
+            full = smp["genomes"] == wl["genomes"]
+            eqt = all(np.array_equal(out_dev[k][0][g], smp["within"][g - 1]) for g in range(1, smp["n_groups"] + 1) if g in out_dev[k][0]) if full else None
+            parity["checks"].append({"oracle_sample": smp["shape"], "within_equal": eqw, "across_equal": eqa,
+                                     "timed_run_groups_equal_oracle": eqt, "kmc": smp["kmc_diff"]})
+            ok = ok and all(eqw) and eqa and (eqt is not False)
+            if smp["kmc_diff"]:
+                ok = ok and all(smp["kmc_diff"].values())
+        parity["ok"] = bool(ok)
+        line["parity_in_run"] = bool(ok)
+        line["parity"] = parity
+        csv_dir = os.environ.get("KHB_BENCH_CSV_DIR")
+        if csv_dir:
+            write_csvs(csv_dir, wl, {kk: within_all[kk][:, :nbins1].astype(np.uint64) for kk in ks}, {kk: out_dev[kk][1] for kk in ks}, n_groups_total)
+            line["config"]["csv_dir"] = csv_dir
         print(json.dumps(line))
+        if not ok:
+            print("FATAL: in-run parity check failed: " + json.dumps(parity), file=sys.stderr)
+            rc = 2
     ex.close()
+    for p in packed.values():
+        p.free()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     eng.close()
-    return 0
+    return rc
 
 
 if __name__ == "__main__":

@@ -180,3 +180,14 @@ KO_API int ko_num_threads(void)
     return 1;
 #endif
 }
+
+/* The host cores the checker may use.  torchrun exports OMP_NUM_THREADS=1 to every rank; bench.py's reference arm runs on
+ * rank 0 alone and asks for all cores explicitly. */
+KO_API void ko_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

@@ -47,6 +47,8 @@ def lib():
         L.ko_exp1.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32,
                               C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ko_num_threads.restype = C.c_int
+        L.ko_set_num_threads.restype = None
+        L.ko_set_num_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -245,3 +247,17 @@ def exp4(groups, pivots, k: int, cs: int = CS_DEFAULT):
 
 def num_threads() -> int:
     return int(lib().ko_num_threads())
+
+
+def set_num_threads(n: int) -> int:
+    """Use n host threads from now on (torchrun exports OMP_NUM_THREADS=1; the reference arm asks for all cores). Returns n."""
+    lib().ko_set_num_threads(int(n))
+    return num_threads()
+
+
+def host_cores() -> int:
+    """Cores this process may run on (affinity mask if the platform has one, else os.cpu_count())."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
