@@ -114,7 +114,7 @@ def kmc_main(argv: List[str]) -> int:
 
 # ---- kmc_tools ---------------------------------------------------------------------------------------
 def transform_set_counts(in_prefix: str, value: int, out_prefix: str) -> None:
-    db = kmcdb.read_db(in_prefix)
+    db = kmcdb.read_db(in_prefix, keys_only=True)   # the counters are overwritten: a set-only step_3 table of the fused group job will do
     hist = np.zeros(HIST_ROWS + 1, dtype=np.uint64)
     if value <= HIST_ROWS:
         hist[value] = db.keys.shape[0]
@@ -253,9 +253,11 @@ def kmc_tools_main(argv: List[str]) -> int:
 
 
 # ---- rule-granular fused commands (used by khoice_b200/workflow/exp_type_1.smk) ------------------------------
-def fused_group(k: int, genome_paths: List[str], hist_out: str, set_prefix: str, table_prefix: Optional[str] = None) -> None:
-    """Rules build_kmc_database_on_genome .. within_group_union_histogram + build_group_kmer_set for one (k, group)
-    in ONE process: step_4 histogram + the group's k-mer set (step_6 database, real; step_3 header-only)."""
+def fused_group(k: int, genome_paths: List[str], hist_out: Optional[str], set_prefix: Optional[str], table_prefix: Optional[str] = None) -> None:
+    """The per-genome rules and within_group_union for one (k, group) in ONE process (the drop-in's fused
+    `within_group_union`): the step_3 table, written SET-ONLY (histogram + distinct k-mers, kmcdb.py) so that the reference's
+    own `transform ... histogram` and `transform ... set_counts 1` strings produce step_4 and step_6 from it.  With --hist /
+    --set the step_4 histogram and the step_6 database are written here as well (then the table is a header-only stub)."""
     eng = get_engine()
     texts = ingest.read_many(genome_paths)
     eng.group_sets_reset()
@@ -263,15 +265,26 @@ def fused_group(k: int, genome_paths: List[str], hist_out: str, set_prefix: str,
     keys = eng.group_sets_download()
     eng.group_sets_reset()
     keys = np.sort(keys) if keys.ndim == 1 else keys[np.lexsort((keys[:, 0], keys[:, 1]))]
-    write_histogram_file(hist_out, hist, HIST_ROWS)
-    one = np.zeros(HIST_ROWS + 1, dtype=np.uint64)
-    one[1] = keys.shape[0]
-    kmcdb.write_db(set_prefix, k, keys, np.ones(keys.shape[0], np.uint32), one, COUNTER_MAX)
+    if hist_out:
+        write_histogram_file(hist_out, hist, HIST_ROWS)
+    if set_prefix:
+        one = np.zeros(HIST_ROWS + 1, dtype=np.uint64)
+        one[1] = keys.shape[0]
+        kmcdb.write_db(set_prefix, k, keys, np.ones(keys.shape[0], np.uint32), one, COUNTER_MAX)
     if table_prefix:
-        kmcdb.write_db(table_prefix, k, None, None, hist, COUNTER_MAX, n_keys=keys.shape[0])
+        if set_prefix:
+            kmcdb.write_db(table_prefix, k, None, None, hist, COUNTER_MAX, n_keys=keys.shape[0])
+        else:
+            kmcdb.write_db(table_prefix, k, keys, None, hist, COUNTER_MAX)
 
 
-def fused_across(k: int, set_prefixes: List[str], hist_out: str, table_prefix: Optional[str] = None) -> None:
+def fused_stub(k: int, prefix: str) -> None:
+    """The drop-in's fused `build_kmc_database_on_genome` / `transform_genome_to_set`: a header-only placeholder, so that every
+    target of the reference's DAG still resolves while the group job reads the genomes itself."""
+    kmcdb.write_db(prefix, k, None, None, np.zeros(HIST_ROWS + 1, dtype=np.uint64), KMC_DEFAULT_CS)
+
+
+def fused_across(k: int, set_prefixes: List[str], hist_out: Optional[str], table_prefix: Optional[str] = None) -> None:
     """Rules across_group_union + across_group_union_histogram for one k over the step_6 databases."""
     eng = get_engine()
     eng.group_sets_reset()
@@ -282,7 +295,8 @@ def fused_across(k: int, set_prefixes: List[str], hist_out: str, table_prefix: O
         eng.group_sets_append_host(db.keys, k, 1)
     hist, st = eng.across_groups(nbins=HIST_ROWS)
     eng.group_sets_reset()
-    write_histogram_file(hist_out, hist, HIST_ROWS)
+    if hist_out:
+        write_histogram_file(hist_out, hist, HIST_ROWS)
     if table_prefix:
         kmcdb.write_db(table_prefix, k, None, None, hist, COUNTER_MAX, n_keys=int(st["distinct"]))
 
@@ -293,18 +307,25 @@ def khb_main(argv: List[str]) -> int:
     sub = ap.add_subparsers(dest="cmd", required=True)
     g = sub.add_parser("group")
     g.add_argument("--k", type=int, required=True)
-    g.add_argument("--hist", required=True)
-    g.add_argument("--set", required=True, dest="set_prefix")
+    g.add_argument("--hist", default=None)
+    g.add_argument("--set", default=None, dest="set_prefix")
     g.add_argument("--table", default=None)
     g.add_argument("genomes", nargs="+")
+    s = sub.add_parser("stub")
+    s.add_argument("--k", type=int, required=True)
+    s.add_argument("prefix")
     a = sub.add_parser("across")
     a.add_argument("--k", type=int, required=True)
-    a.add_argument("--hist", required=True)
+    a.add_argument("--hist", default=None)
     a.add_argument("--table", default=None)
     a.add_argument("sets", nargs="+")
     ns = ap.parse_args(argv)
     if ns.cmd == "group":
+        if not (ns.hist or ns.set_prefix or ns.table):
+            raise UsageError("khb group: nothing to write (give --table, --hist and / or --set)")
         fused_group(ns.k, ns.genomes, ns.hist, ns.set_prefix, ns.table)
+    elif ns.cmd == "stub":
+        fused_stub(ns.k, ns.prefix)
     else:
         fused_across(ns.k, ns.sets, ns.hist, ns.table)
     return 0

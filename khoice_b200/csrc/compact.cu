@@ -1124,12 +1124,9 @@ int khb_pivot_across_impl(khb_ctx *ctx, const void *d_sorted, const unsigned sho
     u32 sh_bins = (n_groups + 1 < nbins + 1) ? n_groups + 1 : nbins + 1;
     if ((size_t)n_groups * sh_bins * sizeof(u32) > 96 * 1024) sh_bins = 0;
     const size_t shm = (size_t)n_groups * sh_bins * sizeof(u32);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(pivot_across_kernel<Key64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        cudaFuncSetAttribute(pivot_across_kernel<Key128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        attr = true;
-    }
+    // per-device function attribute: set on every call so that every context on every GPU has it
+    cudaFuncSetAttribute(pivot_across_kernel<Key64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(pivot_across_kernel<Key128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     u64 grid = div_up(n, 256);
     if (grid > (u64)ctx->num_sms * 8) grid = (u64)ctx->num_sms * 8;
     khb_prof_begin(ctx, KHB_K_RLE);

@@ -226,11 +226,15 @@ static int hash_count_launch(khb_ctx *ctx, const u64 *d_codes, const u32 *d_vali
         const char *e = getenv("KHB_HASH_MAX_PROBE");  // tests force the fall-back to the sort path with 0
         probe_limit = e ? atoll(e) : 8192;
     }
-    static int diag = -1;  // timing experiments only (wrong results): 1 no bit update, 2 load only, 3 plain store instead of RED
+#ifdef KHB_EXPERIMENTS
+    static int diag = -1;  // timing experiments only (WRONG results): 1 no bit update, 2 load only, 3 plain store instead of RED.  Not in the product build.
     if (diag < 0) {
         const char *e = getenv("KHB_HASH_DIAG");
         diag = e ? atoi(e) : 0;
     }
+#else
+    const int diag = 0;
+#endif
     const u32 max_probe = n_slots > (u64)probe_limit ? (u32)probe_limit : (u32)n_slots;
     khb_prof_begin(ctx, KHB_K_HASH_INSERT);
     hash_insert_kernel<R><<<(unsigned)total, HS_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, k, d_seg_off, (u32)n_genomes, n_pb, interleave, d_table,

@@ -209,11 +209,7 @@ int khb_peer_push(khb_ctx *ctx)
     if (W == 8) {
         push_kernel<Key64><<<(unsigned)blocks, PP_BLOCK, shm, st>>>((const Key64 *)src, n, (u32)pp->world, pp->region_keys, pp->d_cursor, pp->d_dst);
     } else {
-        static bool attr = false;
-        if (!attr) {
-            cudaFuncSetAttribute(push_kernel<Key128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
-            attr = true;
-        }
+        cudaFuncSetAttribute(push_kernel<Key128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);   // per device: every call
         push_kernel<Key128><<<(unsigned)blocks, PP_BLOCK, shm, st>>>((const Key128 *)src, n, (u32)pp->world, pp->region_keys, pp->d_cursor, pp->d_dst);
     }
     ctx->launches++;

@@ -417,16 +417,17 @@ static int launch_passes(khb_ctx *ctx, Key *src, Key *dst, unsigned short *psrc,
     constexpr int NW = BLOCK / 32;
     const size_t shm = sizeof(Key) * TILE + NW * 256 * sizeof(unsigned short) + 256 * sizeof(u32) + 36 * sizeof(u32) +
                        (MATCH >= 2 ? NW * 256 * sizeof(u32) : 0) + (EARLY ? 256 * sizeof(u32) : 0) + (PAY ? TILE * sizeof(unsigned short) : 0);
-    static bool attr_set = false;
-    if (!attr_set) {
-        KHB_CUDA(ctx, cudaFuncSetAttribute(onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH, PAY, EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-        attr_set = true;
-    }
-    static int nolb = -1;
+    // the opt-in is a per-device function attribute: set on every call (cheap) so that every context on every GPU has it
+    KHB_CUDA(ctx, cudaFuncSetAttribute(onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH, PAY, EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+#ifdef KHB_EXPERIMENTS
+    static int nolb = -1;   // timing experiment only (WRONG output): skip the look-back.  Not in the product build.
     if (nolb < 0) {
         const char *e = getenv("KHB_SORT_DEBUG_NOLB");
         nolb = e ? atoi(e) : 0;
     }
+#else
+    const int nolb = 0;
+#endif
     for (int pass = 0; pass < npass; pass++) {
         khb_prof_begin(ctx, KHB_K_ONESWEEP);
         onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH, PAY, EARLY><<<(unsigned)ntiles, BLOCK, shm, ctx->stream>>>(

@@ -479,11 +479,7 @@ extern "C" int khb_superkmer_count(khb_ctx *ctx, const uint64_t *d_codes, const 
     if (!n_symbols) return KHB_OK;
     const u64 tiles = div_up(n_symbols, SK_TILE);
     const size_t shm = (size_t)(SK_TILE + 32) * sizeof(u64) + (size_t)SK_TILE * sizeof(u32);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(superkmer_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
-        attr = true;
-    }
+    cudaFuncSetAttribute(superkmer_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
     superkmer_count_kernel<<<(unsigned)tiles, SK_BLOCK, shm, ctx->stream>>>((const u64 *)d_codes, d_valid, n_symbols, k, m, log2_bins, d_bin_windows, d_bin_superkmers);
     KHB_LAUNCH_CHECK(ctx);
     return KHB_OK;

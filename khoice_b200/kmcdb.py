@@ -9,8 +9,12 @@ the two file names but stores its own simple layout:
 ``X.kmc_pre``  64-byte header  + uint64[hist_rows+1] occurrence histogram of the counters
 ``X.kmc_suf``  n_keys k-mer words (8 or 16 bytes each, ascending) + n_keys uint32 counters
 
-In fused mode the intermediates are never read back, so only the header (``stub`` flag set) is written --
-enough for Snakemake's file DAG / resume semantics.
+In fused mode most intermediates are never read back, so only the header (``stub`` flag 1) is written -- enough for
+Snakemake's file DAG / resume semantics; reading such a stub as a k-mer set is an error.  The fused group job writes its
+step_3 table SET-ONLY (``stub`` flag 2): the histogram in the header and the distinct k-mers in ``.kmc_suf`` without the
+per-k-mer counters (the kernels never materialise them).  ``transform X histogram`` and ``transform X set_counts v`` -- the
+only two things the reference does with a step_3 table (exp_type_1.smk:184-191, 233-241) -- work on it; anything that needs
+the counters is an error.
 
 Interoperation with the real binaries: ``read_db`` also accepts KMC's own databases (KMC1 and KMC2
 layouts, khoice_b200/kmc_format.py), and with the environment variable ``KHB_DB_FORMAT=kmc1`` ``write_db`` emits the KMC1
@@ -45,7 +49,7 @@ class KmerDB:
 
     @property
     def n_keys(self) -> int:
-        return int(self.counts.shape[0]) if not self.stub else int(self._n)
+        return int(self.keys.shape[0]) if not self.stub else int(self._n)
 
     _n: int = 0
 
@@ -61,17 +65,23 @@ def _atomic_write(path: str, chunks) -> None:
 
 def write_db(prefix: str, k: int, keys: Optional[np.ndarray], counts: Optional[np.ndarray], hist: np.ndarray,
              counter_max: int, n_keys: Optional[int] = None) -> None:
-    """Write ``prefix.kmc_pre`` / ``prefix.kmc_suf``.  ``keys is None`` writes a fused-mode stub."""
+    """Write ``prefix.kmc_pre`` / ``prefix.kmc_suf``.  ``keys is None`` writes a fused-mode stub (header + histogram);
+    ``counts is None`` with keys writes a set-only table (header + histogram + k-mers, no counters)."""
     stub = keys is None
-    if not stub and os.environ.get("KHB_DB_FORMAT", "").lower() == "kmc1":
+    set_only = not stub and counts is None
+    if not stub and not set_only and os.environ.get("KHB_DB_FORMAT", "").lower() == "kmc1":
         kmc_format.write_kmc1(prefix, k, keys, counts, counter_max)
         return
     n = int(n_keys if n_keys is not None else (0 if stub else keys.shape[0]))
     key_bytes = 8 if k <= 32 else 16
     hist = np.ascontiguousarray(hist, dtype=np.uint64)
-    hdr = _HDR.pack(MAGIC, VERSION, k, n, key_bytes, counter_max, hist.size - 1, 1 if stub else 0)
+    hdr = _HDR.pack(MAGIC, VERSION, k, n, key_bytes, counter_max, hist.size - 1, 1 if stub else 2 if set_only else 0)
     if stub:
         _atomic_write(prefix + ".kmc_suf", [b""])
+    elif set_only:
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        assert keys.shape[0] == n
+        _atomic_write(prefix + ".kmc_suf", [keys.tobytes()])
     else:
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
         counts = np.ascontiguousarray(counts, dtype=np.uint32)
@@ -80,7 +90,9 @@ def write_db(prefix: str, k: int, keys: Optional[np.ndarray], counts: Optional[n
     _atomic_write(prefix + ".kmc_pre", [hdr, hist.tobytes()])
 
 
-def read_db(prefix: str, header_only: bool = False) -> KmerDB:
+def read_db(prefix: str, header_only: bool = False, keys_only: bool = False) -> KmerDB:
+    """``header_only``: k, histogram and key count (what `transform X histogram` needs).  ``keys_only``: the caller ignores the
+    counters (`transform X set_counts v`), so a set-only table is acceptable; its ``counts`` come back as None."""
     if kmc_format.is_kmc_database(prefix):
         hdr, keys, counts = kmc_format.read_kmc(prefix)
         cmax = min((1 << (8 * hdr["counter_size"])) - 1, 0xFFFFFFFF) if hdr["counter_size"] else 1
@@ -96,6 +108,21 @@ def read_db(prefix: str, header_only: bool = False) -> KmerDB:
         raise ValueError(f"{prefix}.kmc_pre: unsupported version {version}")
     hist = np.frombuffer(raw, dtype=np.uint64, count=rows + 1, offset=64).copy()
     shape = (n,) if key_bytes == 8 else (n, 2)
+    if stub == 1 and not header_only:
+        # a fused-mode placeholder (header + histogram, no k-mers): reading it as a k-mer set would silently give an EMPTY set
+        # and wrong unions downstream (e.g. a rule-compatible `kmc_tools complex` re-run over step_2 stubs)
+        raise ValueError(f"{prefix}.kmc_pre is a header-only stub written by the fused mode (it holds a histogram, no k-mers): rebuild this "
+                         "input in rule-compatible mode (KHB_MODE=rules), or run the fused mode with stubs=False, before using it as a k-mer set")
+    if stub == 2 and not header_only:
+        if not keys_only:
+            raise ValueError(f"{prefix}.kmc_pre is a set-only table written by the fused group job (k-mers and histogram, no per-k-mer counters): "
+                             "only `transform X histogram` and `transform X set_counts v` can use it; rebuild it in rule-compatible mode "
+                             "(KHB_MODE=rules) for anything that needs the counters")
+        with open(prefix + ".kmc_suf", "rb") as fd:
+            body = fd.read()
+        if len(body) != n * key_bytes:
+            raise ValueError(f"{prefix}.kmc_suf: size {len(body)} does not match header (n={n}, set-only)")
+        return KmerDB(k, np.frombuffer(body, dtype=np.uint64).reshape(shape).copy(), None, hist, cmax, False)
     if stub or header_only:
         db = KmerDB(k, np.empty((0,) + shape[1:], np.uint64), np.empty(0, np.uint32), hist, cmax, True)
         db._n = n

@@ -175,7 +175,7 @@ def run_fused_distributed(work_root: str, num_datasets: int, k_values: Optional[
     t_start = time.time()
     mine = kd.groups_of_rank(num_datasets, rank, world)
     packed: Dict[int, object] = {}
-    exchangers: Dict[int, object] = {}
+    ex = None             # ONE exchanger at a time: a khb_ctx holds one peer exchange (one set of mapped regions, one key width)
     reader = None
     ctrl = torch.device("cpu") if tdist.get_backend() != "nccl" else adapter.new_tensor(0).device
     try:
@@ -187,9 +187,11 @@ def run_fused_distributed(work_root: str, num_datasets: int, k_values: Optional[
             reader = ingest.GroupReader({n: [os.path.join(work_root, p_genome(n, g)) for g in names[n]] for n in mine}, mine)
         for k in k_values:
             ki = int(k)
-            ex = exchangers.get(kd.key_words(ki))       # one exchanger (one set of mapped regions) per key width
+            if ex is not None and kd.key_words(ki) != kd.key_words(ex.k):
+                ex.close()                              # collective: the key width changes (k crosses 32), in either direction
+                ex = None
             if ex is None:
-                ex = exchangers[kd.key_words(ki)] = kd.AcrossExchanger(adapter, ki, num_datasets, nbins=tables.HIST_ROWS, mode=exchange)
+                ex = kd.AcrossExchanger(adapter, ki, num_datasets, nbins=tables.HIST_ROWS, mode=exchange)
             ex.set_k(ki)
             adapter.reset()
             ex.begin()
@@ -229,7 +231,7 @@ def run_fused_distributed(work_root: str, num_datasets: int, k_values: Optional[
                 report["stages"].append({"k": ki, "group": "across", "distinct": int(d_all.item()), "exchange": info.get("exchange", "local")})
         if rank == 0:
             build_tables(work_root, k_values, num_datasets)
-        for ex in exchangers.values():
+        if ex is not None:
             ex.close()
         tdist.barrier()
     finally:
@@ -272,17 +274,26 @@ def _rule_jobs(work_root: str, k_values: Sequence[str], num_datasets: int):
 
 
 def _fused_rule_jobs(work_root: str, k_values: Sequence[str], num_datasets: int):
-    """The two fused rules of khoice_b200/workflow/exp_type_1.smk (KHB_MODE=fused), as (rule, outputs, shell)."""
+    """The rules of khoice_b200/workflow/exp_type_1.smk in KHB_MODE=fused, as (rule, outputs, shell): the same ten names and
+    output patterns as the reference; `khb group` / `khb across` carry the arithmetic, `khb stub` the per-genome placeholders,
+    the three transform rules are the reference's own strings."""
     jobs = []
+    pair = lambda p: [p + e for e in (".kmc_pre", ".kmc_suf")]
     for k in k_values:
         for num in range(1, num_datasets + 1):
-            ins = " ".join(p_genome(num, g) for g in genomes_of(work_root, num))
-            outs = [p_step4(k, num)] + [p + e for p in (p_step3(k, num), p_step6(k, num)) for e in (".kmc_pre", ".kmc_suf")]
-            jobs.append(("within_group_union_histogram", outs,
-                         f"khb group --k {k} --hist {p_step4(k, num)} --table {p_step3(k, num)} --set {p_step6(k, num)} {ins}"))
+            names = genomes_of(work_root, num)
+            for g in names:
+                jobs.append(("build_kmc_database_on_genome", pair(p_step1(k, num, g)), f"khb stub --k {k} {p_step1(k, num, g)}"))
+                jobs.append(("transform_genome_to_set", pair(p_step2(k, num, g)), f"khb stub --k {k} {p_step2(k, num, g)}"))
+            ins = " ".join(p_genome(num, g) for g in names)
+            jobs.append(("within_group_union", pair(p_step3(k, num)), f"khb group --k {k} --table {p_step3(k, num)} {ins}"))
+            jobs.append(("within_group_union_histogram", [p_step4(k, num)],
+                         f"kmc_tools transform {p_step3(k, num)} histogram {p_step4(k, num)}"))
+            jobs.append(("build_group_kmer_set", pair(p_step6(k, num)),
+                         f"kmc_tools transform {p_step3(k, num)} set_counts 1 {p_step6(k, num)}"))
         sets = " ".join(p_step6(k, n) for n in range(1, num_datasets + 1))
-        jobs.append(("across_group_union_histogram", [p_step8(k)] + [p_step7(k) + e for e in (".kmc_pre", ".kmc_suf")],
-                     f"khb across --k {k} --hist {p_step8(k)} --table {p_step7(k)} {sets}"))
+        jobs.append(("across_group_union", pair(p_step7(k)), f"khb across --k {k} --table {p_step7(k)} {sets}"))
+        jobs.append(("across_group_union_histogram", [p_step8(k)], f"kmc_tools transform {p_step7(k)} histogram {p_step8(k)}"))
     return jobs
 
 

@@ -8,10 +8,12 @@
 #     (workflow/Snakefile:36).
 #   * KHB_MODE=rules (default "fused"): every rule runs the reference's own shell string; put khoice_b200/bin first
 #     on PATH and `kmc` / `kmc_tools` resolve to the B200 shims.  That also works with the UNMODIFIED reference file.
-#   * KHB_MODE=fused: the per-genome and per-group rules collapse into ONE process per (k, group) (`khb group`) and
-#     the across-group rules into one per k (`khb across`).  Rule names and outputs stay, so targets, resume
-#     semantics and downstream rules are unchanged; step_1/2/3/7 databases are header-only stubs, step_6 is real
-#     (it is the hand-off between the two processes).  Run with `--cores 1` per GPU: every job owns the device.
+#   * KHB_MODE=fused: ALL TEN rule names and output patterns stay (every reference target resolves, resume semantics and
+#     downstream rules are unchanged), but the k-mer arithmetic runs in one GPU process per (k, group) (`khb group`, rule
+#     within_group_union) and one per k (`khb across`, rule across_group_union).  step_1/2/7 databases are header-only
+#     placeholders, the step_3 table is set-only (histogram + distinct k-mers), step_6 is a real set database (the hand-off
+#     to the across-group job), and the three transform rules run the reference's own shell strings.  Run with `--cores 1`
+#     per GPU, or KHB_WORKER_SOCKET: every GPU job owns the device.
 ####################################################
 import os
 
@@ -74,17 +76,48 @@ if KHB_MODE == "rules":
         output: S8
         shell: "PATH={KHB_BIN}:$PATH kmc_tools transform step_7/k_{wildcards.k}/all_datasets.transformed.combined.transformed.combined histogram {output}"
 else:
-    # fused: the group job writes every per-genome / per-group output of its (k, group) in one go
+    # fused: all ten rule names and every output pattern of the reference stay (any reference target still resolves), but the
+    # arithmetic of the per-genome rules and of the two unions runs in ONE GPU process per (k, group) / per k:
+    #   build_kmc_database_on_genome, transform_genome_to_set  -> header-only placeholders (no GPU, no k-mers)
+    #   within_group_union    -> `khb group`: reads the group's genomes itself, writes the step_3 table set-only (histogram + k-mers)
+    #   within_group_union_histogram, build_group_kmer_set, across_group_union_histogram -> the reference's own shell strings
+    #   across_group_union    -> `khb across` over the step_6 sets; the step_7 table is header-only (histogram)
+    rule build_kmc_database_on_genome:
+        input: "data/dataset_{num}/{genome}.fna.gz"
+        output: S1 + ".kmc_pre", S1 + ".kmc_suf"
+        shell: "{KHB_BIN}/khb stub --k {wildcards.k} step_1/k_{wildcards.k}/dataset_{wildcards.num}/{wildcards.genome}"
+
+    rule transform_genome_to_set:
+        input: S1 + ".kmc_pre", S1 + ".kmc_suf"
+        output: S2 + ".kmc_pre", S2 + ".kmc_suf"
+        shell: "{KHB_BIN}/khb stub --k {wildcards.k} step_2/k_{wildcards.k}/dataset_{wildcards.num}/{wildcards.genome}.transformed"
+
+    rule within_group_union:
+        input: lambda w: [f"step_2/k_{w.k}/dataset_{w.num}/{g}.transformed.kmc_pre" for g in genomes_of(w.num)]
+        output: S3 + ".kmc_pre", S3 + ".kmc_suf"
+        params: genomes=lambda w: [f"data/dataset_{w.num}/{g}.fna.gz" for g in genomes_of(w.num)]
+        shell: "{KHB_BIN}/khb group --k {wildcards.k} --table step_3/k_{wildcards.k}/dataset_{wildcards.num}/dataset_{wildcards.num}.transformed.combined {params.genomes}"
+
     rule within_group_union_histogram:
-        input: lambda w: [f"data/dataset_{w.num}/{g}.fna.gz" for g in genomes_of(w.num)]
-        output: S4, S3 + ".kmc_pre", S3 + ".kmc_suf", S6 + ".kmc_pre", S6 + ".kmc_suf"
-        shell: "{KHB_BIN}/khb group --k {wildcards.k} --hist {output[0]} --table step_3/k_{wildcards.k}/dataset_{wildcards.num}/dataset_{wildcards.num}.transformed.combined --set step_6/k_{wildcards.k}/dataset_{wildcards.num}/dataset_{wildcards.num}.transformed.combined.transformed {input}"
+        input: S3 + ".kmc_pre", S3 + ".kmc_suf"
+        output: S4
+        shell: "PATH={KHB_BIN}:$PATH kmc_tools transform step_3/k_{wildcards.k}/dataset_{wildcards.num}/dataset_{wildcards.num}.transformed.combined histogram {output}"
+
+    rule build_group_kmer_set:
+        input: S3 + ".kmc_pre", S3 + ".kmc_suf"
+        output: S6 + ".kmc_pre", S6 + ".kmc_suf"
+        shell: "PATH={KHB_BIN}:$PATH kmc_tools transform step_3/k_{wildcards.k}/dataset_{wildcards.num}/dataset_{wildcards.num}.transformed.combined set_counts 1 step_6/k_{wildcards.k}/dataset_{wildcards.num}/dataset_{wildcards.num}.transformed.combined.transformed"
+
+    rule across_group_union:
+        input: lambda w: [f"step_6/k_{w.k}/dataset_{n}/dataset_{n}.transformed.combined.transformed.kmc_pre" for n in range(1, num_datasets + 1)]
+        output: S7 + ".kmc_pre", S7 + ".kmc_suf"
+        params: sets=lambda w: [f"step_6/k_{w.k}/dataset_{n}/dataset_{n}.transformed.combined.transformed" for n in range(1, num_datasets + 1)]
+        shell: "{KHB_BIN}/khb across --k {wildcards.k} --table step_7/k_{wildcards.k}/all_datasets.transformed.combined.transformed.combined {params.sets}"
 
     rule across_group_union_histogram:
-        input: lambda w: [f"step_6/k_{w.k}/dataset_{n}/dataset_{n}.transformed.combined.transformed.kmc_pre" for n in range(1, num_datasets + 1)]
-        output: S8, S7 + ".kmc_pre", S7 + ".kmc_suf"
-        params: sets=lambda w: [f"step_6/k_{w.k}/dataset_{n}/dataset_{n}.transformed.combined.transformed" for n in range(1, num_datasets + 1)]
-        shell: "{KHB_BIN}/khb across --k {wildcards.k} --hist {output[0]} --table step_7/k_{wildcards.k}/all_datasets.transformed.combined.transformed.combined {params.sets}"
+        input: S7 + ".kmc_pre", S7 + ".kmc_suf"
+        output: S8
+        shell: "PATH={KHB_BIN}:$PATH kmc_tools transform step_7/k_{wildcards.k}/all_datasets.transformed.combined.transformed.combined histogram {output}"
 
 rule within_group_union_analysis:
     input: expand("step_4/k_{k_len}/dataset_{num}/dataset_{num}_k{k_len}_hist.txt", k_len=k_values, num=list(range(1, num_datasets + 1)))

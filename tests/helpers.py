@@ -87,3 +87,18 @@ def sort_rows(keys: np.ndarray) -> np.ndarray:
 def is_sentinel(keys: np.ndarray) -> np.ndarray:
     full = np.uint64(0xFFFFFFFFFFFFFFFF)
     return keys == full if keys.ndim == 1 else (keys[:, 0] == full) & (keys[:, 1] == full)
+
+
+def synth_genomes(n_genomes: int, group: int = 1, genome_len: int = 5_000_000, procs: int = 16):
+    """[fasta bytes] of one synthetic group at BASELINE size, generated in forked worker processes (they only run numpy; the
+    session's CUDA context is never touched in a child -- the same pattern as bench.py's cpu_baseline leg)."""
+    import multiprocessing as mp
+    import os
+    from concurrent.futures import ProcessPoolExecutor
+    from khoice_b200 import synth
+    cfg = synth.SynthConfig(n_groups=max(group, 1), genomes_per_group=n_genomes, genome_len=genome_len)
+    procs = max(1, min(procs, os.cpu_count() or 1, n_genomes))
+    if procs == 1:
+        return [synth.make_genome(cfg, group, i) for i in range(1, n_genomes + 1)]
+    with ProcessPoolExecutor(procs, mp_context=mp.get_context("fork")) as pool:
+        return list(pool.map(synth.make_genome, [cfg] * n_genomes, [group] * n_genomes, range(1, n_genomes + 1), chunksize=max(1, n_genomes // (4 * procs))))

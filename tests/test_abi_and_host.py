@@ -64,8 +64,15 @@ def test_kmcdb_roundtrip(tmp_path):
         assert db.k == k and np.array_equal(db.keys, keys) and np.array_equal(db.counts, counts) and np.array_equal(db.hist, hist)
         assert kmcdb.read_db(p, header_only=True).n_keys == shape[0]
     kmcdb.write_db(str(tmp_path / "stub"), 31, None, None, np.zeros(5001, np.uint64), 5000, n_keys=42)
-    s = kmcdb.read_db(str(tmp_path / "stub"))
+    s = kmcdb.read_db(str(tmp_path / "stub"), header_only=True)           # `transform X histogram` may read a stub ...
     assert s.stub and s.n_keys == 42 and os.path.exists(tmp_path / "stub.kmc_suf")
+    with pytest.raises(ValueError, match="header-only stub"):               # ... nothing may read it as a k-mer set
+        kmcdb.read_db(str(tmp_path / "stub"))
+    from khoice_b200 import cli
+    for argv in (["kmc_tools", "transform", str(tmp_path / "stub"), "set_counts", "1", str(tmp_path / "o")],
+                 ["kmc_tools", "transform", str(tmp_path / "stub"), "dump", "-s", str(tmp_path / "o.txt")]):
+        assert cli.main(argv) == 1 and not os.path.exists(tmp_path / "o.kmc_pre") and not os.path.exists(tmp_path / "o.txt")
+    assert cli.main(["kmc_tools", "transform", str(tmp_path / "stub"), "histogram", str(tmp_path / "h.txt")]) == 0
     (tmp_path / "bad.kmc_pre").write_bytes(b"KMCP" + b"\0" * 100)
     with pytest.raises(ValueError):
         kmcdb.read_db(str(tmp_path / "bad"))

@@ -106,7 +106,7 @@ def test_distributed_work_root_driver_on_two_ranks_sharing_one_gpu(engine, tmp_p
     import filecmp
     from khoice_b200 import pipeline, synth
     cfg = synth.SynthConfig(n_groups=5, genomes_per_group=3, genome_len=30_000, seed=77)
-    ks = ["13", "21", "31", "40"]
+    ks = ["31", "40", "21", "13"]     # the key width changes twice, in both directions: one exchanger at a time (a ctx holds one peer exchange)
     work, ref = str(tmp_path / "dist"), str(tmp_path / "single")
     synth.write_dataset(cfg, work)
     synth.write_dataset(cfg, ref)

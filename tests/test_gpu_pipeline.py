@@ -151,3 +151,30 @@ def test_small_k_direct_address_path_and_its_switch_over(engine, oracle, k):
     hist, st = engine.across_groups(nbins=32)
     assert np.array_equal(hist, a_ref) and st["distinct"] == st_ref["distinct"]
     engine.group_sets_reset()
+
+
+def test_two_contexts_in_one_process(engine, oracle):
+    """include/khoice_b200.h promises re-entrancy across contexts: a second context (on another GPU when the box has one --
+    kernel attributes such as the dynamic shared-memory opt-in are per DEVICE -- else on the same GPU) computes the same
+    histograms, 64- and 128-bit keys, while the first context stays usable."""
+    from khoice_b200.engine import Engine
+    rng = np.random.default_rng(77)
+    files = [random_fasta(rng, 60_000) for _ in range(4)]
+    second = None
+    for dev in (1, 0):
+        try:
+            second = Engine(dev)
+            break
+        except Exception:
+            continue
+    assert second is not None
+    try:
+        for k in (31, 47):
+            w_ref, _, _ = oracle.exp1(files, [0] * 4, 1, k)
+            engine.group_sets_reset()
+            second.group_sets_reset()
+            h2, _ = second.group_from_fasta(files, k, keep_set=False)
+            h1, _ = engine.group_from_fasta(files, k, keep_set=False)
+            assert np.array_equal(h1, w_ref[0]) and np.array_equal(h2, w_ref[0])
+    finally:
+        second.close()

@@ -43,9 +43,9 @@ def test_k_sweep_config3_shape(engine, oracle, k):
 
 
 def test_domain_invariants_full_size(engine):
-    """Size-independent properties at BASELINE scale (one config-2 group, 50 x 5 Mbp) where the oracle would take
-    minutes: histogram mass = distinct count, idempotence (a group unioned with itself), reverse-complement
-    invariance of a genome's k-mer set."""
+    """Size-independent properties at BASELINE scale (one config-2 group, 50 x 5 Mbp): histogram mass = distinct count,
+    idempotence (a group unioned with itself), reverse-complement invariance of a genome's k-mer set.  The oracle comparison
+    at the same size is tests/test_gpu_fullsize.py."""
     from khoice_b200 import synth
     cfg = synth.SynthConfig(n_groups=1, genomes_per_group=50, genome_len=5_000_000)
     genomes = [synth.make_genome(cfg, 1, i) for i in range(1, 51)]

@@ -53,8 +53,8 @@ def test_three_modes_agree_with_oracle(engine, oracle, work_roots):
     for f in (pipeline.P_STEP5, pipeline.P_STEP9) + pipeline.P_FINAL:
         assert filecmp.cmp(os.path.join(roots["fused"], f), os.path.join(roots["rules"], f), shallow=False), f
         assert filecmp.cmp(os.path.join(roots["fused"], f), os.path.join(roots["smk-fused"], f), shallow=False), f
-    # every declared rule output exists in both modes (file DAG / resume semantics)
-    for mode in ("fused", "rules"):
+    # every declared rule output exists in every mode (file DAG / resume semantics)
+    for mode in ("fused", "rules", "smk-fused"):
         root = roots[mode]
         for k in K_VALUES:
             for num in range(1, cfg.n_groups + 1):
@@ -67,6 +67,24 @@ def test_three_modes_agree_with_oracle(engine, oracle, work_roots):
     # resume: a second run does nothing
     rep = pipeline.run_rules(roots["rules"], cfg.n_groups, K_VALUES, engine=engine)
     assert rep["jobs_run"] == 0
+    rep = pipeline.run_rules(roots["smk-fused"], cfg.n_groups, K_VALUES, engine=engine, fused_rules=True)
+    assert rep["jobs_run"] == 0
+    # fused placeholders are never mistaken for k-mer sets: a rule-compatible re-run over them fails loudly (exit 1), it does
+    # not write an empty union; the set-only step_3 table refuses whatever needs its counters
+    from khoice_b200 import cli
+    k = K_VALUES[0]
+    cli.set_engine(engine)
+    try:
+        cwd = os.getcwd()
+        os.chdir(roots["smk-fused"])
+        os.remove(pipeline.p_step3(k, 1) + ".kmc_pre")
+        assert cli.main(["kmc_tools", "complex", pipeline.p_ops_within(k, 1)]) == 1
+        assert not os.path.exists(pipeline.p_step3(k, 1) + ".kmc_pre")
+        assert cli.main(["kmc_tools", "transform", pipeline.p_step3(k, 2), "dump", "-s", "dump.txt"]) == 1 and not os.path.exists("dump.txt")
+        assert cli.main(["kmc_tools", "transform", pipeline.p_step3(k, 2), "histogram", "h.txt"]) == 0
+    finally:
+        os.chdir(cwd)
+        cli.set_engine(None)
 
 
 def test_rule_databases_hold_the_oracle_sets(engine, oracle, work_roots):
