@@ -74,6 +74,8 @@ KHB_API void *khb_stream(khb_ctx *ctx);                /* the cudaStream_t all w
 #define KHB_KERNEL_PARTITION 6  /* partition_kernel (both modes) */
 #define KHB_KERNEL_HASH_INSERT 7 /* hash_insert_kernel: K2 fused with the group hash table (hashset.cu) */
 #define KHB_KERNEL_HASH_COUNT 8  /* hash_count_kernel: table scan -> histogram + group set */
+#define KHB_KERNEL_BIN_PARTITION 9 /* mb_partition_kernel: symbol stream -> super-k-mer records in minimizer bins (bins.cu) */
+#define KHB_KERNEL_BIN_COUNT 10    /* mb_count_kernel: per-bin shared-memory counting -> histogram + group set */
 KHB_API int khb_profile_enable(khb_ctx *ctx, int on);
 KHB_API int khb_profile_read(khb_ctx *ctx, int kernel_id, uint64_t *launches, double *ms, uint64_t *alg_bytes);
 
@@ -196,19 +198,25 @@ KHB_API int khb_group_from_packed(khb_ctx *ctx, int k, const khb_packed *pk, uin
                           khb_stats *stats);
 
 /* How the group stage (khb_group_from_*) finds the k-mers genomes share.  AUTO: the direct-address table for small k
- * (presence.cu), else one prefix sort of all windows with the genome id as payload.  SINGLE_SORT is AUTO spelled out,
+ * (presence.cu); minimizer bins + per-bin shared-memory counting for 17 <= k <= 31 (bins.cu: no sort, ~2.3 bytes per window
+ * through HBM; a group whose bins do not fit falls back to the sort); else one prefix sort of all windows with the genome id
+ * as payload.  SINGLE_SORT forces that sort wherever AUTO would take the bins, BINS is AUTO spelled out,
  * TWO_SORT the KMC-shaped chain sort, unique, sort, count.  HASH (k <= 31, <= 448 genomes; other groups take the AUTO
  * route): K2 fused with an open-addressing table of (k-mer, genome bit set) records instead of a sort (hashset.cu) --
  * measured 20 % slower than the single sort on config 2 (profiles/r1s3_hash_group_stage.md), kept as a checked
  * alternative.  All modes give identical results.  The initial mode comes from the environment variable
- * KHB_GROUP_MODE (single-sort | two-sort | hash). */
+ * KHB_GROUP_MODE (single-sort | two-sort | hash | bins). */
 #define KHB_GROUP_AUTO 0
 #define KHB_GROUP_SINGLE_SORT 1
 #define KHB_GROUP_TWO_SORT 2
 #define KHB_GROUP_HASH 3
+#define KHB_GROUP_BINS 4
 KHB_API int khb_set_group_mode(khb_ctx *ctx, int mode);
 /* Groups the hash path handed back to the sort path because a probe sequence hit its limit (performance counter). */
 KHB_API uint64_t khb_hash_overflows(const khb_ctx *ctx);
+/* Performance counters of the minimizer-bin path: groups it handed to the sort path (a bin outgrew its region), bins it
+ * redid in hash classes because their distinct k-mers did not fit one shared-memory table. */
+KHB_API void khb_bins_counters(const khb_ctx *ctx, uint64_t *fallbacks, uint64_t *big_bins);
 
 /* Across-group union-sum + histogram over the retained group sets: rules across_group_union and
  * across_group_union_histogram (exp_type_1.smk:243-259) for one k. */

@@ -29,6 +29,8 @@ size_t khb_presence_table_bytes(int, int);
 int khb_presence_count_impl(khb_ctx *, const u64 *, const u32 *, size_t, int, int, const u64 *, int, u32 *, u32, u32, u64 *, void *, u64 *, u64 *, int,
                             void *, u64 *);
 size_t khb_hash_table_bytes(int, int, u64, int *, int *);
+int khb_bins_eligible(int, int, u64);
+int khb_bins_count_impl(khb_ctx *, const u64 *, const u32 *, u64, int, const u64 *, int, u32, u32, u64 *, void *, u64 *, u64 *, u64 *);
 int khb_hash_count_impl(khb_ctx *, const u64 *, const u32 *, u64, int, const u64 *, const u64 *, int, u32 *, int, int, u32, u32, u64 *, void *, u64 *, u64 *, int,
                         void *, u64 *, u32 *);
 int khb_peer_regions(khb_ctx *, const void **, u64 *, int *, int *);
@@ -97,6 +99,16 @@ void khb_prof_end(khb_ctx *ctx, int id, u64 alg_bytes)
     cudaEventRecord(r.b, ctx->prof_stream ? ctx->prof_stream : ctx->stream);
     p->recs.push_back(r);
     p->open = false;
+}
+
+void khb_prof_patch(khb_ctx *ctx, int id, u64 alg_bytes)
+{
+    if (!ctx->prof_on || !ctx->prof) return;
+    for (auto it = ctx->prof->recs.rbegin(); it != ctx->prof->recs.rend(); ++it)
+        if (it->id == id) {
+            it->bytes = alg_bytes;
+            return;
+        }
 }
 
 int khb_fail(khb_ctx *ctx, int code, const char *fmt, ...)
@@ -173,7 +185,7 @@ int khb_init(int device, khb_ctx **out)
     {
         const char *gm = getenv("KHB_GROUP_MODE");
         ctx->group_mode = !gm ? KHB_GROUP_AUTO : strcmp(gm, "two-sort") == 0 ? KHB_GROUP_TWO_SORT : strcmp(gm, "single-sort") == 0 ? KHB_GROUP_SINGLE_SORT
-                          : strcmp(gm, "hash") == 0 ? KHB_GROUP_HASH : KHB_GROUP_AUTO;
+                          : strcmp(gm, "hash") == 0 ? KHB_GROUP_HASH : strcmp(gm, "bins") == 0 ? KHB_GROUP_BINS : KHB_GROUP_AUTO;
     }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
@@ -786,8 +798,18 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
             hash_budget = (e ? atoll(e) : 98304) << 20;
         }
         bool use_hash = hs_bytes > 0 && (long long)hs_bytes <= hash_budget;
+        // minimizer bins + per-bin shared-memory counting (bins.cu): the default wherever it applies
+        bool use_bins = !small_k && !use_hash && hashed && !pivot && (ctx->group_mode == KHB_GROUP_AUTO || ctx->group_mode == KHB_GROUP_BINS) &&
+                        khb_bins_eligible(k, n_genomes, n_sym);
       again:
-        if (use_hash) {
+        if (use_bins) {
+            tm.mark();  // 3
+            tm.mark();  // 4
+            tm.mark();  // 5
+            tm.mark();  // 6
+            if ((rc = khb_bins_count_impl(ctx, d_codes, d_valid, n_sym, k, d_seg, n_genomes, KHB_COUNTER_MAX, nbins, d_hist, out_keys, d_runs, d_pairs,
+                                          ctx->d_mail + 3))) return rc;
+        } else if (use_hash) {
             u32 *tab = nullptr;
             if ((rc = hash_table_get(ctx, hs_bytes, &tab))) return rc;
             tm.mark();  // 3
@@ -836,6 +858,19 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
         KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, ctx->d_mail, (nbins + 9) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
         tm.mark();  // 7: count done
         KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (use_bins) {
+            if (ctx->h_mail[3]) {
+                // a bin outgrew its region or its table (very uneven minimizers): redo this group by sorting
+                ctx->bins_fallbacks++;
+                use_bins = false;
+                tm.n = 3;
+                goto again;
+            }
+            ctx->bins_bigbins += ctx->h_mail[5];
+            if (ctx->h_mail[4]) ctx->bins_rho = (double)ctx->h_mail[0] / (double)ctx->h_mail[4];
+            khb_prof_patch(ctx, KHB_K_BIN_PARTITION, n_sym * 3 / 8 + ctx->h_mail[4] * 32);
+            khb_prof_patch(ctx, KHB_K_BIN_COUNT, ctx->h_mail[4] * 32 + ctx->h_mail[0] * 8);
+        }
         if (use_hash && ctx->h_mail[3]) {
             // a probe sequence hit the limit (table nearly full of distinct k-mers): redo this group by sorting
             ctx->hs_dirty = 1;
@@ -865,7 +900,7 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
             stats->genome_distinct = ctx->h_mail[1];
             stats->distinct = d_g;
             stats->passes_genome = 0;
-            stats->passes_group = np;
+            stats->passes_group = use_bins ? 0 : np;
         }
         return KHB_OK;
     }
@@ -1169,12 +1204,17 @@ int khb_group_from_packed(khb_ctx *ctx, int k, const khb_packed *pk, uint32_t nb
 int khb_set_group_mode(khb_ctx *ctx, int mode)
 {
     KHB_CHECK_CTX(ctx);
-    if (mode < KHB_GROUP_AUTO || mode > KHB_GROUP_HASH) return khb_fail(ctx, KHB_ERR_ARG, "khb_set_group_mode: mode %d", mode);
+    if (mode < KHB_GROUP_AUTO || mode > KHB_GROUP_BINS) return khb_fail(ctx, KHB_ERR_ARG, "khb_set_group_mode: mode %d", mode);
     ctx->group_mode = mode;
     return KHB_OK;
 }
 
 uint64_t khb_hash_overflows(const khb_ctx *ctx) { return ctx ? ctx->hs_overflows : 0; }
+void khb_bins_counters(const khb_ctx *ctx, uint64_t *fallbacks, uint64_t *big_bins)
+{
+    if (fallbacks) *fallbacks = ctx ? ctx->bins_fallbacks : 0;
+    if (big_bins) *big_bins = ctx ? ctx->bins_bigbins : 0;
+}
 
 int khb_across_groups(khb_ctx *ctx, uint32_t nbins, uint64_t *h_hist, khb_stats *stats)
 {

@@ -1,0 +1,744 @@
+// bins.cu -- the minimizer-bin group stage (default group path for 17 <= k <= 31): what `kmc` + `kmc_tools complex` compute for one
+// group (/root/reference/workflow/rules/exp_type_1.smk:156-191: per-genome canonical k-mer sets, their counter-summing union, its
+// histogram) WITHOUT a sort.  KMC's own idea, rebuilt for one B200: windows that share a minimizer go to the same bin as compact
+// super-k-mer records; a bin is small enough to be counted by ONE CTA in a shared-memory table of (k-mer, genome bits).
+//
+//   pass P  mb_partition_kernel   packed symbol stream -> per-bin regions of 32-byte super-k-mer records
+//                                 (tile of 4096 window starts; 32-bit hashes of the canonical 13-mers; sliding minimum over the
+//                                 k - 12 hashes of a window by the van Herk / Gil-Werman prefix/suffix trick in shared memory;
+//                                 a maximal run of windows with one minimum = one record; ONE global atomicAdd per record)
+//   pass C  mb_count_kernel       persistent CTAs stream their bins' records through a double-buffered shared-memory ring with
+//                                 cp.async.bulk + mbarrier (the next bin is in flight while this one is counted), expand every
+//                                 window's canonical k-mer, insert it into an open-addressing table in shared memory, set the
+//                                 genome's bit; at the end of a bin: popcount per slot -> step_4 histogram, distinct keys
+//                                 (mixed like K2's) appended to the group-set store, table left clean for the next bin
+//   pass B  mb_bigbin_kernel      bins whose table filled up are redone with the key space split into hash classes
+//
+// HBM traffic: ~2.3 bytes per window written and read once (records) + 8 bytes per DISTINCT k-mer -- against ~100 bytes per window
+// of the prefix sort.  The bound is shared-memory work per window, not HBM.
+// Every result is exact; whatever does not fit (a bin region overflows, a table cannot hold a bin) makes the caller redo the group
+// on the sort path.
+#include <stdlib.h>
+
+#include "khb_common.cuh"
+
+#define MB_TILE 4096          // window starts per partition CTA
+#define MB_BLOCK 256
+#define MB_HALO 64            // k - m <= 63 extra hashes behind a tile
+#define MB_NH (MB_TILE + MB_HALO)
+#define MB_MAXW 64            // windows per record at most (one byte per window in the count kernel's map)
+
+#define MC_BLOCK 256
+#define MC_R 256              // records per stage of the ring (one per thread)
+#define MC_PROBES 48
+
+__device__ __forceinline__ u32 mb_mix32(u32 x)
+{
+    x *= 0x9E3779B1u;
+    x ^= x >> 15;
+    x *= 0x85EBCA77u;
+    x ^= x >> 13;
+    x *= 0xC2B2AE3Du;
+    x ^= x >> 16;
+    return x | 1u;            // 0 is reserved for "no m-mer here"
+}
+__device__ __forceinline__ u32 mb_bin_of(u32 minhash, u32 nbins)
+{
+    u32 b = minhash * 0xD6E8FEB9u;
+    b ^= b >> 16;
+    b *= 0x7FEB352Du;
+    return __umulhi(b, nbins);
+}
+
+__device__ __forceinline__ u32 mb_segment_of(const u64 *__restrict__ seg_off, int nseg, u64 i)
+{
+    int lo = 0, hi = nseg;  // invariant: seg_off[lo] <= i < seg_off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(seg_off + mid) <= i) lo = mid; else hi = mid;
+    }
+    return (u32)lo;
+}
+
+// ---- pass P -----------------------------------------------------------------------------------------------------------------
+// Record layout (KW + 1 words of 64 bits, KW = 3 for k <= 32): word 0 = genome << 48 | windows << 40; words 1..KW = the 32 * KW
+// symbols from the record's first window start, MSB first (window e's k-mer = bits [2e, 2e + 2k) of that string).
+template <int KW>
+__global__ void __launch_bounds__(MB_BLOCK)
+mb_partition_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, u64 n_sym, u64 last_cw, u64 last_vw, int k, int m, u32 nbins,
+                    const u64 *__restrict__ seg_off, int nseg, u32 *__restrict__ cursor, u64 *__restrict__ rec, u32 cap, u32 capw, u64 *__restrict__ flags)
+{
+    constexpr int CW = MB_TILE / 32 + KW + 2;     // 64-bit code words staged per tile
+    constexpr int VW = MB_TILE / 32 + 4;
+    __shared__ u32 A[MB_NH];                      // hashes -> suffix minima -> per-window minimum
+    __shared__ u32 P[MB_NH];                      // prefix minima
+    __shared__ u32 sc[2 * CW + 2];                // the tile's symbols as 16-symbol chunks in stream order
+    __shared__ u32 sv[VW];
+    const u32 tid = threadIdx.x;
+    const u64 tile0 = (u64)blockIdx.x * MB_TILE;  // a multiple of 32
+    const int w = k - m + 1;                      // m-mers per window
+    const u32 B = (w & 1) ? (u32)w : (u32)(w > 1 ? w - 1 : 1);   // block length of the prefix/suffix minima: w or w - 1, whichever is odd
+    const u32 NH = MB_TILE + (u32)w - 1u;
+    {
+        const u64 q0 = tile0 >> 5;
+        for (u32 i = tid; i < CW; i += MB_BLOCK) {
+            const u64 q = q0 + i < last_cw ? q0 + i : last_cw;
+            const u64 c = __ldg(codes + q);
+            sc[2 * i] = (u32)(c >> 32);
+            sc[2 * i + 1] = (u32)c;
+        }
+        for (u32 i = tid; i < VW; i += MB_BLOCK) sv[i] = q0 + i <= last_vw ? __ldg(valid + q0 + i) : 0u;
+    }
+    __syncthreads();
+    // phase 1: hash of the canonical m-mer at every symbol position of the tile (0 = not an m-mer)
+    {
+        const u32 sh = 32u - 2u * (u32)m, mask2m = (1u << (2 * m)) - 1u, ones_m = (1u << m) - 1u;
+        for (u32 j = tid; j < NH; j += MB_BLOCK) {
+            const u32 t = j >> 4, s = (j & 15u) * 2u;
+            const u32 x = __funnelshift_l(sc[t + 1], sc[t], s);
+            const u32 fwd = x >> sh;
+            u32 r = __brev(~x);
+            r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+            r &= mask2m;
+            const u32 c = fwd < r ? fwd : r;
+            const u32 vq = j >> 5;
+            const u32 vv = __funnelshift_l(sv[vq + 1], sv[vq], j & 31u);
+            const bool ok = (vv >> (32 - m)) == ones_m && tile0 + j + (u64)m <= n_sym;
+            A[j] = ok ? mb_mix32(c) : 0u;
+        }
+    }
+    __syncthreads();
+    // phase 2a: per block of B hashes the running minimum from the left (P) and from the right (A, in place); lanes are B words
+    // apart and B is odd, so the accesses of a warp fall into 32 different banks
+    {
+        const u32 nblk = (NH + B - 1) / B;
+        for (u32 b = tid; b < nblk; b += MB_BLOCK) {
+            const u32 lo = b * B, hi = lo + B < NH ? lo + B : NH;
+            u32 run = 0xFFFFFFFFu;
+            for (u32 p = lo; p < hi; p++) {
+                const u32 h = A[p];
+                run = h < run ? h : run;
+                P[p] = run;
+            }
+            run = 0xFFFFFFFFu;
+            for (u32 p = hi; p-- > lo;) {
+                const u32 h = A[p];
+                run = h < run ? h : run;
+                A[p] = run;
+            }
+        }
+    }
+    __syncthreads();
+    // phase 2b: minimum over the w hashes of window j = min(suffix minimum at j, prefix minimum at j + w - 1); 0 = no k-mer here
+    for (u32 j = tid; j < MB_TILE; j += MB_BLOCK) {
+        const u32 a = A[j], p = P[j + w - 1];
+        A[j] = a < p ? a : p;
+    }
+    __syncthreads();
+    // phase 3: the first window of every run of equal minima writes the run as one record (several if it is longer than capw)
+    const u32 g_first = mb_segment_of(seg_off, nseg, tile0);
+    const u64 g_first_end = __ldg(seg_off + g_first + 1);
+    for (u32 j = tid; j < MB_TILE; j += MB_BLOCK) {
+        const u32 mh = A[j];
+        if (mh == 0u) continue;
+        if (j > 0 && A[j - 1] == mh) continue;
+        u32 len = 1;
+        while (j + len < MB_TILE && A[j + len] == mh) len++;
+        const u32 bin = mb_bin_of(mh, nbins);
+        const u32 pieces = (len + capw - 1) / capw;
+        const u32 at = atomicAdd(&cursor[bin], pieces);
+        if (at + pieces > cap) {                   // the bin's region is full: the caller redoes the group another way
+            *flags = 1ull;
+            continue;
+        }
+        const u64 i0 = tile0 + j;
+        const u64 g = i0 < g_first_end ? g_first : mb_segment_of(seg_off, nseg, i0);
+        ulonglong2 *dst = (ulonglong2 *)(rec + ((u64)bin * cap + at) * (KW + 1));
+        for (u32 s0 = 0; s0 < len; s0 += capw) {
+            const u32 pl = len - s0 < capw ? len - s0 : capw;
+            const u32 rel = j + s0, t = rel >> 4, s = (rel & 15u) * 2u;
+            u64 W[KW + 1];
+            W[0] = (g << 48) | ((u64)pl << 40);
+#pragma unroll
+            for (int e = 0; e < KW; e++) {
+                const u32 hi = __funnelshift_l(sc[t + 2 * e + 1], sc[t + 2 * e], s);
+                const u32 lo = __funnelshift_l(sc[t + 2 * e + 2], sc[t + 2 * e + 1], s);
+                W[e + 1] = ((u64)hi << 32) | lo;
+            }
+#pragma unroll
+            for (int e = 0; e < (KW + 1) / 2; e++) *dst++ = make_ulonglong2(W[2 * e], W[2 * e + 1]);
+        }
+    }
+}
+
+// ---- pass C -----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u64 *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64 *bar, u32 bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
+{
+    u32 done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// 1-D bulk copy global -> shared (the TMA unit moves the bytes; completion is counted on the mbarrier).  16-byte aligned, multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct mc_desc {
+    u32 bin, count, flags, chunk, cls, ncls;
+};
+enum { MCF_LAST = 1 /* last stage of a pass over the bin's records */, MCF_SCAN = 2 /* ... of the last genome chunk: emit the table */, MCF_DONE = 4 };
+
+// what thread 0 knows about the stream of stages it feeds into the ring.  A bin is streamed ncls x nchunks times: once per hash
+// class of its k-mers (a bin with more distinct k-mers than the table holds is counted class by class) and per chunk of 64 genomes.
+struct mc_iter {
+    u32 bin, n, n_next, off, chunk, cls, ncls;
+};
+__device__ __forceinline__ u32 mb_class_hash(u64 key) { return (u32)((key * 0xD6E8FEB86659FD93ull) >> 32); }
+
+__device__ __forceinline__ u64 mb_canonical64(u64 x, int k)
+{
+    const int rs = 64 - 2 * k;
+    const u64 fwd = x >> rs;
+    u64 r = __brevll(~x) << rs >> rs;
+    r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+    return fwd < r ? fwd : r;
+}
+
+#define MB_EMPTY (~0ull)
+
+// Insert `key` (genome bit gb of 64) into the table.  Returns false when the probe sequence is too long (table too full).
+__device__ __forceinline__ bool mb_insert(u64 *tkey, u64 *tbits, u32 s_log2, u64 key, u32 gb, u32 *s_distinct)
+{
+    const u32 smask = (1u << s_log2) - 1u;
+    u32 slot = (u32)((key * 0x9E3779B97F4A7C15ull) >> 40) & smask;
+    for (u32 probes = 0;; probes++) {
+        const u64 c = *(volatile u64 *)&tkey[slot];
+        if (c == key) break;
+        if (c == MB_EMPTY) {
+            const u64 old = atomicCAS((unsigned long long *)&tkey[slot], MB_EMPTY, key);
+            if (old == MB_EMPTY) {
+                atomicAdd(s_distinct, 1u);
+                break;
+            }
+            if (old == key) break;
+        }
+        if (probes >= MC_PROBES) return false;
+        slot = (slot + 1) & smask;
+    }
+    u32 *bw = (u32 *)&tbits[slot] + (gb >> 5);
+    const u32 bm = 1u << (gb & 31u);
+    if (!(*(volatile u32 *)bw & bm)) atomicOr(bw, bm);
+    return true;
+}
+
+// Shared-memory carve-up of the counting kernels (dynamic): table keys, genome bits, counts (more than 64 genomes only), ring,
+// per-record window offsets, window -> record map, histogram.
+struct mc_smem {
+    u64 *tkey, *tbits;
+    u32 *tcnt;
+    u64 *ring;
+    u32 *pre;
+    unsigned char *map;
+    u32 *hist;
+};
+__host__ __device__ inline size_t mc_smem_bytes(int KW, u32 S, bool multi, u32 hrows)
+{
+    return (size_t)S * 16 + (multi ? (size_t)S * 4 : 0) + 2 * (size_t)MC_R * (KW + 1) * 8 + (size_t)(MC_R + 1) * 4 + (size_t)MC_R * MB_MAXW + ((size_t)hrows + 1) * 4 + 64;
+}
+__device__ __forceinline__ mc_smem mc_carve(unsigned char *base, int KW, u32 S, bool multi, u32 hrows)
+{
+    mc_smem s;
+    s.tkey = (u64 *)base;
+    s.tbits = s.tkey + S;
+    s.ring = s.tbits + S;
+    unsigned char *p = (unsigned char *)(s.ring + 2 * (size_t)MC_R * (KW + 1));
+    s.tcnt = (u32 *)p;
+    p += multi ? (size_t)S * 4 : 0;
+    s.pre = (u32 *)p;
+    p += (size_t)(MC_R + 1) * 4;
+    s.hist = (u32 *)p;
+    p += ((size_t)hrows + 1) * 4;
+    s.map = p;
+    return s;
+}
+
+template <int KW, bool MULTI>
+__global__ void __launch_bounds__(MC_BLOCK)
+mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32 nbins, u32 cap, int k, u32 s_log2, u32 n_genomes, u32 nchunks, u32 cs,
+                u32 hrows, u32 thr1 /* records one pass over a bin may hold */, u32 over_cap, u64 *__restrict__ hist, u64 *__restrict__ out_keys, u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs,
+                u32 *__restrict__ over_list, u32 *__restrict__ over_count, u64 *__restrict__ d_stat)
+{
+    extern __shared__ __align__(16) unsigned char mc_raw[];
+    __shared__ __align__(8) u64 bars[2];
+    __shared__ mc_desc desc[2];
+    __shared__ u32 s_over, s_distinct, ws[33];
+    __shared__ u64 s_base;
+    const u32 S = 1u << s_log2;
+    const mc_smem sm = mc_carve(mc_raw, KW, S, MULTI, hrows);
+    const u32 tid = threadIdx.x;
+    for (u32 i = tid; i < S; i += MC_BLOCK) {
+        sm.tkey[i] = MB_EMPTY;
+        sm.tbits[i] = 0ull;
+        if (MULTI) sm.tcnt[i] = 0u;
+    }
+    for (u32 i = tid; i <= hrows; i += MC_BLOCK) sm.hist[i] = 0u;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        s_over = 0;
+        s_distinct = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    mc_iter it;
+    it.bin = blockIdx.x;
+    it.off = 0;
+    it.chunk = 0;
+    it.cls = 0;
+    it.ncls = 1;
+    it.n = 0;
+    it.n_next = 0;
+    u64 my_records = 0;
+    auto bin_records = [&](u32 b) -> u32 {
+        if (b >= nbins) return 0u;
+        const u32 c = __ldg(cursor + b);
+        return c < cap ? c : cap;
+    };
+    auto produce = [&](u32 buf) {   // thread 0 only: the next stage of this CTA's stream goes into ring buffer `buf`
+        while (it.bin < nbins && it.n == 0) {
+            it.bin += gridDim.x;
+            it.n = it.n_next;
+            it.n_next = bin_records(it.bin + gridDim.x);
+        }
+        if (it.bin >= nbins) {
+            desc[buf].flags = MCF_DONE;
+            mbar_arrive(&bars[buf]);
+            return;
+        }
+        const u32 count = it.n - it.off < MC_R ? it.n - it.off : MC_R;
+        const bool last = it.off + count == it.n;
+        if (it.off == 0 && it.chunk == 0 && it.cls == 0) {
+            my_records += it.n;
+            it.ncls = (it.n + thr1 - 1) / thr1;
+        }
+        desc[buf].bin = it.bin;
+        desc[buf].count = count;
+        desc[buf].chunk = it.chunk;
+        desc[buf].cls = it.cls;
+        desc[buf].ncls = it.ncls;
+        desc[buf].flags = (last ? MCF_LAST : 0u) | (last && it.chunk + 1 == nchunks ? MCF_SCAN : 0u);
+        const u32 bytes = count * (u32)((KW + 1) * 8);
+        mbar_arrive_expect_tx(&bars[buf], bytes);
+        bulk_g2s(sm.ring + (size_t)buf * MC_R * (KW + 1), rec + ((u64)it.bin * cap + it.off) * (KW + 1), bytes, &bars[buf]);
+        it.off += count;
+        if (last) {
+            it.off = 0;
+            if (++it.chunk == nchunks) {
+                it.chunk = 0;
+                if (++it.cls == it.ncls) {
+                    it.cls = 0;
+                    it.bin += gridDim.x;
+                    it.n = it.n_next;
+                    it.n_next = bin_records(it.bin + gridDim.x);
+                }
+            }
+        }
+    };
+    if (tid == 0) {
+        it.n = bin_records(it.bin);
+        it.n_next = bin_records(it.bin + gridDim.x);
+        produce(0);
+        produce(1);
+    }
+    const u32 c_all = n_genomes < cs ? n_genomes : cs;   // the count of a k-mer every genome holds
+    u32 n_one = 0, n_all = 0;
+    u64 pairs = 0;
+    for (u32 s = 0;; s++) {
+        const u32 buf = s & 1u;
+        mbar_wait(&bars[buf], (s >> 1) & 1u);
+        const mc_desc d = desc[buf];
+        if (d.flags & MCF_DONE) break;
+        if (!s_over) {
+            const u64 *rb = sm.ring + (size_t)buf * MC_R * (KW + 1);
+            u32 len = 0;
+            if (tid < d.count) {
+                const u64 h = rb[(size_t)tid * (KW + 1)];
+                len = (u32)(h >> 40) & 0xffu;
+                if (MULTI && (u32)(h >> 54) != d.chunk) len = 0;   // genome >> 6
+            }
+            u32 total;
+            const u32 off = block_excl_sum<u32>(len, ws, &total);
+            sm.pre[tid] = off;
+            for (u32 e = 0; e < len; e++) sm.map[off + e] = (unsigned char)tid;
+            __syncthreads();
+            bool ok = true;
+            for (u32 t = tid; t < total; t += MC_BLOCK) {
+                const u32 r = sm.map[t];
+                const u32 e = t - sm.pre[r];
+                const u64 *R = rb + (size_t)r * (KW + 1);
+                const u32 q = e >> 5, o = e & 31u;
+                const u64 w0 = R[1 + q], w1 = R[2 + q];   // e + k - 1 < 32 * KW, so 2 + q <= KW ... or the value is shifted out
+                const u64 x = o ? ((w0 << (2 * o)) | (w1 >> (64 - 2 * o))) : w0;
+                const u64 key = mb_canonical64(x, k);
+                if (d.ncls > 1 && __umulhi(mb_class_hash(key), d.ncls) != d.cls) continue;
+                const u32 g = (u32)(R[0] >> 48);
+                ok = mb_insert(sm.tkey, sm.tbits, s_log2, key, g & 63u, &s_distinct) && ok;
+            }
+            if (!ok) s_over = 1;
+        }
+        __syncthreads();
+        if (s_distinct > S - S / 4) s_over = 1;     // same value in every thread (s_distinct is stable between the barriers)
+        const bool over = s_over != 0;
+        if (tid == 0) {
+            if ((d.flags & MCF_SCAN) && !over && s_distinct) s_base = atomicAdd((unsigned long long *)d_cursor, (unsigned long long)s_distinct);
+            produce(buf);
+        }
+        if (!(d.flags & MCF_LAST)) continue;
+        if (over) {
+            if (!(d.flags & MCF_SCAN)) continue;    // keep consuming the stages of this class; it is redone by mb_bigbin_kernel
+            __syncthreads();
+            for (u32 i = tid; i < S; i += MC_BLOCK) {
+                sm.tkey[i] = MB_EMPTY;
+                sm.tbits[i] = 0ull;
+                if (MULTI) sm.tcnt[i] = 0u;
+            }
+            if (tid == 0) {
+                const u32 at = atomicAdd(over_count, 1u);
+                if (at < over_cap) {
+                    over_list[3 * at] = d.bin;
+                    over_list[3 * at + 1] = d.cls;
+                    over_list[3 * at + 2] = d.ncls;
+                } else {
+                    atomicOr((unsigned long long *)d_stat, 2ull);
+                }
+                s_over = 0;
+                s_distinct = 0;
+            }
+            __syncthreads();
+            continue;
+        }
+        if (MULTI && !(d.flags & MCF_SCAN)) {       // end of a 64-genome chunk: fold the bits into the counts
+            for (u32 i = tid; i < S; i += MC_BLOCK) {
+                const u64 b = sm.tbits[i];
+                if (b) {
+                    sm.tcnt[i] += (u32)__popcll(b);
+                    sm.tbits[i] = 0ull;
+                }
+            }
+            __syncthreads();
+            continue;
+        }
+        // end of the bin: every occupied slot is one distinct k-mer of the group
+        u32 mine = 0;
+        for (u32 i = tid; i < S; i += MC_BLOCK) mine += sm.tkey[i] != MB_EMPTY;
+        u32 total;
+        u32 at = block_excl_sum<u32>(mine, ws, &total);
+        const u64 base = s_base;
+        for (u32 i = tid; i < S; i += MC_BLOCK) {
+            const u64 key = sm.tkey[i];
+            if (key == MB_EMPTY) continue;
+            u32 c = (u32)__popcll(sm.tbits[i]);
+            if (MULTI) c += sm.tcnt[i];
+            pairs += c;
+            const u32 cc = c > cs ? cs : c;
+            if (cc == 1u) n_one++;
+            else if (cc == c_all) n_all++;
+            else if (cc <= hrows) atomicAdd(&sm.hist[cc], 1u);
+            if (out_keys) out_keys[base + at] = kmer_mix64(key, k);
+            at++;
+            sm.tkey[i] = MB_EMPTY;
+            sm.tbits[i] = 0ull;
+            if (MULTI) sm.tcnt[i] = 0u;
+        }
+        __syncthreads();
+        if (tid == 0) s_distinct = 0;
+        __syncthreads();
+    }
+    // flush this CTA's counts
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_one += __shfl_xor_sync(0xffffffffu, n_one, o);
+        n_all += __shfl_xor_sync(0xffffffffu, n_all, o);
+        pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
+    }
+    if ((tid & 31u) == 0) {
+        if (n_one && 1u <= hrows) atomicAdd(&sm.hist[1], n_one);
+        if (n_all && c_all <= hrows) atomicAdd(&sm.hist[c_all], n_all);
+        if (pairs) atomicAdd((unsigned long long *)d_pairs, (unsigned long long)pairs);
+    }
+    if (tid == 0 && my_records) atomicAdd((unsigned long long *)&d_stat[1], (unsigned long long)my_records);
+    __syncthreads();
+    for (u32 i = tid; i <= hrows; i += MC_BLOCK) {
+        const u32 v = sm.hist[i];
+        if (v) atomicAdd((unsigned long long *)&hist[i], (unsigned long long)v);
+    }
+}
+
+// ---- pass B: the bins whose table filled up, redone with the keys split into P hash classes, one class per pass ------------------
+template <int KW, bool MULTI>
+__global__ void __launch_bounds__(MC_BLOCK)
+mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32 cap, int k, u32 s_log2, u32 n_genomes, u32 nchunks, u32 cs, u32 hrows,
+                 u64 *__restrict__ hist, u64 *__restrict__ out_keys, u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs,
+                 const u32 *__restrict__ over_list, const u32 *__restrict__ over_count, u32 over_cap, u64 *__restrict__ flags)
+{
+    extern __shared__ __align__(16) unsigned char mc_raw[];
+    __shared__ u32 s_over, s_distinct, ws[33];
+    __shared__ u64 s_base;
+    const u32 S = 1u << s_log2;
+    const mc_smem sm = mc_carve(mc_raw, KW, S, MULTI, hrows);
+    const u32 tid = threadIdx.x;
+    const u32 n_over = *over_count < over_cap ? *over_count : over_cap;
+    if (blockIdx.x == 0 && tid == 0) flags[2] = n_over;
+    if (blockIdx.x >= n_over) return;
+    for (u32 i = tid; i < S; i += MC_BLOCK) {
+        sm.tkey[i] = MB_EMPTY;
+        sm.tbits[i] = 0ull;
+        if (MULTI) sm.tcnt[i] = 0u;
+    }
+    for (u32 i = tid; i <= hrows; i += MC_BLOCK) sm.hist[i] = 0u;
+    if (tid == 0) {
+        s_over = 0;
+        s_distinct = 0;
+    }
+    __syncthreads();
+    u64 pairs = 0;
+    for (u32 li = blockIdx.x; li < n_over; li += gridDim.x) {
+        const u32 bin = over_list[3 * li], cls0 = over_list[3 * li + 1], ncls0 = over_list[3 * li + 2];
+        const u32 n = cursor[bin] < cap ? cursor[bin] : cap;
+        const u64 *rb = rec + (u64)bin * cap * (KW + 1);
+        // work list of hash classes (modulus M, residue r): keys with h % M == r.  A class whose distinct keys do not fit the table is
+        // split into (2M, r) and (2M, r + M), which together are exactly that class -- nothing of it was emitted yet.
+        u32 stM[40], stR[40];
+        int sp = 0;
+        stM[sp] = 2; stR[sp++] = 1;
+        stM[sp] = 2; stR[sp++] = 0;
+        while (sp > 0) {
+            const u32 M = stM[--sp], r0 = stR[sp];
+            for (u32 chunk = 0; chunk < nchunks; chunk++) {
+                const u32 sub = tid & 15u, grp = tid >> 4;   // 16 lanes share a record
+                bool ok = true;
+                for (u32 r = grp; r < n; r += MC_BLOCK / 16) {
+                    const u64 *R = rb + (size_t)r * (KW + 1);
+                    const u64 h = R[0];
+                    const u32 g = (u32)(h >> 48), len = (u32)(h >> 40) & 0xffu;
+                    if (MULTI && (g >> 6) != chunk) continue;
+                    for (u32 e = sub; e < len; e += 16) {
+                        const u32 q = e >> 5, o = e & 31u;
+                        const u64 w0 = R[1 + q], w1 = R[2 + q];
+                        const u64 x = o ? ((w0 << (2 * o)) | (w1 >> (64 - 2 * o))) : w0;
+                        const u64 key = mb_canonical64(x, k);
+                        if (ncls0 > 1 && __umulhi(mb_class_hash(key), ncls0) != cls0) continue;
+                        if ((u32)((key * 0x9E3779B97F4A7C15ull) >> 20) % M != r0) continue;
+                        ok = mb_insert(sm.tkey, sm.tbits, s_log2, key, g & 63u, &s_distinct) && ok;
+                    }
+                }
+                if (!ok) s_over = 1;
+                __syncthreads();
+                if (s_distinct > S - S / 4) s_over = 1;
+                if (s_over) break;
+                if (MULTI && chunk + 1 < nchunks) {
+                    for (u32 i = tid; i < S; i += MC_BLOCK) {
+                        const u64 b = sm.tbits[i];
+                        if (b) {
+                            sm.tcnt[i] += (u32)__popcll(b);
+                            sm.tbits[i] = 0ull;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            const bool over = s_over != 0;
+            __syncthreads();
+            if (over) {
+                for (u32 i = tid; i < S; i += MC_BLOCK) {
+                    sm.tkey[i] = MB_EMPTY;
+                    sm.tbits[i] = 0ull;
+                    if (MULTI) sm.tcnt[i] = 0u;
+                }
+                if (tid == 0) {
+                    s_over = 0;
+                    s_distinct = 0;
+                }
+                __syncthreads();
+                if (M >= (1u << 16) || sp + 2 > 40) {      // cannot happen for a bin that fits its region; the caller redoes the group by sorting
+                    if (tid == 0) atomicOr((unsigned long long *)flags, 2ull);
+                    sp = 0;
+                    break;
+                }
+                stM[sp] = 2 * M; stR[sp++] = r0 + M;
+                stM[sp] = 2 * M; stR[sp++] = r0;
+                continue;
+            }
+            if (tid == 0 && s_distinct) s_base = atomicAdd((unsigned long long *)d_cursor, (unsigned long long)s_distinct);
+            u32 mine = 0;
+            for (u32 i = tid; i < S; i += MC_BLOCK) mine += sm.tkey[i] != MB_EMPTY;
+            u32 total;
+            u32 at = block_excl_sum<u32>(mine, ws, &total);
+            const u64 base = s_base;
+            for (u32 i = tid; i < S; i += MC_BLOCK) {
+                const u64 key = sm.tkey[i];
+                if (key == MB_EMPTY) continue;
+                u32 c = (u32)__popcll(sm.tbits[i]);
+                if (MULTI) c += sm.tcnt[i];
+                pairs += c;
+                const u32 cc = c > cs ? cs : c;
+                if (cc <= hrows) atomicAdd(&sm.hist[cc], 1u);
+                if (out_keys) out_keys[base + at] = kmer_mix64(key, k);
+                at++;
+                sm.tkey[i] = MB_EMPTY;
+                sm.tbits[i] = 0ull;
+                if (MULTI) sm.tcnt[i] = 0u;
+            }
+            __syncthreads();
+            if (tid == 0) s_distinct = 0;
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
+    if ((tid & 31u) == 0 && pairs) atomicAdd((unsigned long long *)d_pairs, (unsigned long long)pairs);
+    __syncthreads();
+    for (u32 i = tid; i <= hrows; i += MC_BLOCK) {
+        const u32 v = sm.hist[i];
+        if (v) atomicAdd((unsigned long long *)&hist[i], (unsigned long long)v);
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------------
+void khb_prof_patch(khb_ctx *ctx, int id, u64 alg_bytes);
+
+static long long mb_env(const char *name, long long dflt)
+{
+    const char *e = getenv(name);
+    return e && *e ? atoll(e) : dflt;
+}
+
+// Does the minimizer-bin path apply?  (64-bit keys with a spare value, enough m-mers per window for super-k-mers to pay.)
+int khb_bins_eligible(int k, int n_genomes, u64 n_sym)
+{
+    return k >= 17 && k <= 31 && n_genomes >= 1 && n_genomes <= 4096 && n_sym >= 1 && n_sym < (1ull << 40);
+}
+
+// The group stage through minimizer bins.  d_stat: u64[4] in device memory, written here: [0] flags (1: a bin region overflowed,
+// 2: a bin could not be counted -- either way the outputs are incomplete and the caller redoes the group another way), [1] records,
+// [2] bins redone by mb_bigbin_kernel.  d_hist[nbins_hist + 1], d_runs (distinct k-mers = keys appended to d_out_keys), d_pairs
+// (sum over genomes of their distinct k-mers) are zeroed here.
+int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u64 n_sym, int k, const u64 *d_seg_off, int n_genomes, u32 cs, u32 nbins_hist,
+                        u64 *d_hist, void *d_out_keys, u64 *d_runs, u64 *d_pairs, u64 *d_stat)
+{
+    if (!khb_bins_eligible(k, n_genomes, n_sym)) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: k=%d / %d genomes not supported", k, n_genomes);
+    constexpr int KW = 3;
+    const int m = 13, w = k - m + 1;
+    const u32 capw = (u32)(32 * KW + 1 - k) < MB_MAXW ? (u32)(32 * KW + 1 - k) : MB_MAXW;
+    // Bin geometry.  All copies of a k-mer -- one per genome that holds it, ~ (w + 1) / 2 windows around each -- land in one bin together, so
+    // a bin's load comes in lumps of ~10 x n_genomes windows; with ~16 lumps per bin the largest bin stays within ~2.5 x the mean.
+    u64 wpb_dflt = 160ull * (u64)n_genomes;
+    wpb_dflt = wpb_dflt < 2048 ? 2048 : wpb_dflt > 16384 ? 16384 : wpb_dflt;
+    const u64 wpb = (u64)mb_env("KHB_BINS_WPB", (long long)wpb_dflt);
+    u64 nb64 = div_up(n_sym, wpb ? wpb : wpb_dflt);
+    if (nb64 < 16) nb64 = 16;
+    if (nb64 > (1ull << 28)) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: group too large");
+    const u32 nb = (u32)nb64;
+    const u32 s_log2 = (u32)mb_env("KHB_BINS_SLOTS_LOG2", 12);
+    if (s_log2 < 8 || s_log2 > 13) return khb_fail(ctx, KHB_ERR_ARG, "KHB_BINS_SLOTS_LOG2 outside 8..13");
+    double avg_len = (w + 1) * 0.5;
+    if (avg_len > capw) avg_len = capw;
+    const double est_records = (double)n_sym / avg_len * 1.15 + (double)div_up(n_sym, MB_TILE);
+    const double slack = (double)mb_env("KHB_BINS_SLACK_PCT", 400) / 100.0;
+    const u32 cap = (u32)(est_records / nb * slack) + 64u;
+    const size_t rec_bytes = (size_t)nb * cap * (KW + 1) * 8;
+    // Records one pass over a bin may hold so that its distinct k-mers fill at most ~55 % of the table: from the distinct k-mers per
+    // record of the previous group (ctx->bins_rho), else a guess from the group size; larger bins are counted in several hash classes.
+    double rho = ctx->bins_rho > 0.0 ? ctx->bins_rho * 1.25 : avg_len * (n_genomes >= 16 ? 0.25 : n_genomes >= 4 ? 0.5 : 1.0);
+    const long long rho_pct = mb_env("KHB_BINS_RHO_PCT", 0);   // test hook: distinct k-mers per record, in percent
+    if (rho_pct > 0) rho = rho_pct / 100.0;
+    if (rho < 0.05) rho = 0.05;
+    double thr = 0.55 * (double)(1u << s_log2) / rho;
+    const u32 thr1 = thr < 8.0 ? 8u : thr > 1e9 ? 1000000000u : (u32)thr;
+    const u32 over_cap = nb;
+    const u32 nchunks = (u32)div_up((size_t)n_genomes, 64);
+    const bool multi = nchunks > 1;
+    const u32 hrows = nbins_hist < (u32)n_genomes ? nbins_hist : (u32)n_genomes;
+    int rc;
+    void *p;
+    if ((rc = khb_scratch_get(ctx, SCR_AUX, (size_t)nb * 16 + 256, &p))) return rc;
+    u32 *d_over_count = (u32 *)p;                 // [0] bins in the list
+    u32 *d_cur = d_over_count + 16, *d_over_list = d_cur + nb;
+    void *pr;
+    if ((rc = khb_scratch_get(ctx, SCR_KEYS_A, rec_bytes + 64, &pr))) return rc;
+    KHB_CUDA(ctx, cudaMemsetAsync(d_over_count, 0, 64 + (size_t)nb * 4, ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, ((size_t)nbins_hist + 1) * sizeof(u64), ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(d_runs, 0, sizeof(u64), ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(d_pairs, 0, sizeof(u64), ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(d_stat, 0, 4 * sizeof(u64), ctx->stream));
+    const u64 last_w = n_sym / 32 + 3;            // khb_codes_words / khb_valid_words: n / 32 + 4 words each
+    {
+        const u64 tiles = div_up(n_sym, MB_TILE);
+        khb_prof_begin(ctx, KHB_K_BIN_PARTITION);
+        mb_partition_kernel<KW><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, m, nb, d_seg_off, n_genomes, d_cur,
+                                                                               (u64 *)pr, cap, capw, d_stat);
+        khb_prof_end(ctx, KHB_K_BIN_PARTITION, n_sym * 3 / 8);
+        KHB_LAUNCH_CHECK(ctx);
+    }
+    {
+        const size_t shm = mc_smem_bytes(KW, 1u << s_log2, multi, hrows);
+        int per_sm = 0;
+        if (multi) {
+            KHB_CUDA(ctx, cudaFuncSetAttribute(mb_count_kernel<KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+            KHB_CUDA(ctx, cudaFuncSetAttribute(mb_bigbin_kernel<KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+            KHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mb_count_kernel<KW, true>, MC_BLOCK, shm));
+        } else {
+            KHB_CUDA(ctx, cudaFuncSetAttribute(mb_count_kernel<KW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+            KHB_CUDA(ctx, cudaFuncSetAttribute(mb_bigbin_kernel<KW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+            KHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mb_count_kernel<KW, false>, MC_BLOCK, shm));
+        }
+        if (per_sm < 1) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: the counting kernel does not fit an SM (%zu bytes of shared memory)", shm);
+        const long long want = mb_env("KHB_BINS_CTAS_PER_SM", 0);
+        if (want > 0 && want < per_sm) per_sm = (int)want;
+        u32 grid = (u32)ctx->num_sms * (u32)per_sm;
+        if (grid > nb) grid = nb;
+        khb_prof_begin(ctx, KHB_K_BIN_COUNT);
+        if (multi)
+            mb_count_kernel<KW, true><<<grid, MC_BLOCK, shm, ctx->stream>>>((const u64 *)pr, d_cur, nb, cap, k, s_log2, (u32)n_genomes, nchunks, cs, hrows, thr1, over_cap,
+                                                                            d_hist, (u64 *)d_out_keys, d_runs, d_pairs, d_over_list, d_over_count, d_stat);
+        else
+            mb_count_kernel<KW, false><<<grid, MC_BLOCK, shm, ctx->stream>>>((const u64 *)pr, d_cur, nb, cap, k, s_log2, (u32)n_genomes, nchunks, cs, hrows, thr1, over_cap,
+                                                                             d_hist, (u64 *)d_out_keys, d_runs, d_pairs, d_over_list, d_over_count, d_stat);
+        khb_prof_end(ctx, KHB_K_BIN_COUNT, 0);
+        KHB_LAUNCH_CHECK(ctx);
+        const u32 bgrid = (u32)ctx->num_sms * 2u;
+        if (multi)
+            mb_bigbin_kernel<KW, true><<<bgrid, MC_BLOCK, shm, ctx->stream>>>((const u64 *)pr, d_cur, cap, k, s_log2, (u32)n_genomes, nchunks, cs, hrows, d_hist,
+                                                                              (u64 *)d_out_keys, d_runs, d_pairs, d_over_list, d_over_count, over_cap, d_stat);
+        else
+            mb_bigbin_kernel<KW, false><<<bgrid, MC_BLOCK, shm, ctx->stream>>>((const u64 *)pr, d_cur, cap, k, s_log2, (u32)n_genomes, nchunks, cs, hrows, d_hist,
+                                                                               (u64 *)d_out_keys, d_runs, d_pairs, d_over_list, d_over_count, over_cap, d_stat);
+        KHB_LAUNCH_CHECK(ctx);
+    }
+    return KHB_OK;
+}

@@ -212,13 +212,16 @@ struct khb_ctx {
     u64 hs_overflows;  // groups that fell back to the sort path because a probe sequence hit the limit
     struct khb_peer *peer;  // multi-GPU exchange over peer memory (peer.cu)
     cudaStream_t prof_stream;  // stream the next khb_prof_begin/end pair records on (null: `stream`)
+    double bins_rho;   // distinct k-mers per super-k-mer record in the last group the minimizer-bin path counted (sizes the next group's passes)
+    u64 bins_fallbacks, bins_bigbins;  // groups the minimizer-bin path handed to the sort path / bins redone in hash classes (bins.cu)
     int group_mode;    // KHB_GROUP_* (khb_set_group_mode; initial value from the environment variable KHB_GROUP_MODE)
 };
 
 // kernel ids for khb_profile_read
-enum { KHB_K_PACK = 0, KHB_K_EXTRACT = 1, KHB_K_RADIX_HIST = 2, KHB_K_ONESWEEP = 3, KHB_K_UNIQUE = 4, KHB_K_RLE = 5, KHB_K_PARTITION = 6, KHB_K_HASH_INSERT = 7, KHB_K_HASH_COUNT = 8, KHB_K_COUNT = 9 };
+enum { KHB_K_PACK = 0, KHB_K_EXTRACT = 1, KHB_K_RADIX_HIST = 2, KHB_K_ONESWEEP = 3, KHB_K_UNIQUE = 4, KHB_K_RLE = 5, KHB_K_PARTITION = 6, KHB_K_HASH_INSERT = 7, KHB_K_HASH_COUNT = 8, KHB_K_BIN_PARTITION = 9, KHB_K_BIN_COUNT = 10, KHB_K_COUNT = 11 };
 void khb_prof_begin(khb_ctx *ctx, int id);
 void khb_prof_end(khb_ctx *ctx, int id, u64 alg_bytes);
+void khb_prof_patch(khb_ctx *ctx, int id, u64 alg_bytes);  // algorithmic bytes of the LAST record of that kernel, once they are known
 
 enum { SCR_TILE = 0, SCR_LOOKBACK = 1, SCR_HIST = 2, SCR_MISC = 3, SCR_KEYS_A = 4, SCR_KEYS_B = 5, SCR_PACK = 6, SCR_FLAGS = 7, SCR_PAY_A = 8, SCR_PAY_B = 9, SCR_AUX = 10 };  // SCR_MISC belongs to the sort (segment tables, tickets)
 #define KHB_NSCRATCH 12

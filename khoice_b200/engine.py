@@ -116,6 +116,7 @@ _SIGNATURES = [
     ("khb_peer_region_keys", C.c_uint64, [_P]),
     ("khb_set_group_mode", C.c_int, [_P, C.c_int]),
     ("khb_hash_overflows", C.c_uint64, [_P]),
+    ("khb_bins_counters", None, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
 
@@ -271,7 +272,7 @@ class Engine:
         return int(self.lib.khb_launch_count(self.ctx))
 
     KERNELS = {"pack": 0, "extract": 1, "radix_hist": 2, "onesweep": 3, "unique": 4, "rle_hist": 5, "partition": 6,
-               "hash_insert": 7, "hash_count": 8}
+               "hash_insert": 7, "hash_count": 8, "bin_partition": 9, "bin_count": 10}
 
     # ---- multi-GPU exchange over peer memory (csrc/peer.cu) ----
     def peer_alloc(self, world: int, rank: int, key_bytes: int, region_keys: int) -> bytes:
@@ -310,7 +311,7 @@ class Engine:
     def peer_region_keys(self) -> int:
         return int(self.lib.khb_peer_region_keys(self.ctx))
 
-    GROUP_MODES = {"auto": 0, "single-sort": 1, "two-sort": 2, "hash": 3}
+    GROUP_MODES = {"auto": 0, "single-sort": 1, "two-sort": 2, "hash": 3, "bins": 4}
 
     def set_group_mode(self, mode: str):
         """How the group stage finds shared k-mers (include/khoice_b200.h: KHB_GROUP_*); results do not depend on it."""
@@ -319,6 +320,13 @@ class Engine:
     @property
     def hash_overflows(self) -> int:
         return int(self.lib.khb_hash_overflows(self.ctx))
+
+    @property
+    def bins_counters(self) -> dict:
+        """Minimizer-bin path: groups handed to the sort path, bins redone in hash classes."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self.lib.khb_bins_counters(self.ctx, C.byref(a), C.byref(b))
+        return {"fallbacks": int(a.value), "big_bins": int(b.value)}
 
     def profile_enable(self, on: bool = True):
         """Bracket every kernel launch with CUDA events (clears earlier records)."""
