@@ -644,7 +644,7 @@ def main():
                        "k": k if not sweep else ks, "groups_total": n_groups_total, "genomes_per_group": wl["genomes"], "bases_per_step": bases_all,
                        "l2": "inputs exceed L2: every group streams >= 1 GB through a 126 MB L2; no explicit flush",
                        "parallelism": f"groups dealt round-robin to {world} rank(s)", "data_gen_s": round(gen_s, 1),
-                       "group_mode": os.environ.get("KHB_GROUP_MODE", "auto"),
+                       "group_mode": os.environ.get("KHB_GROUP_MODE", "auto"), "bins_counters": eng.bins_counters,
                        "exchange": (f"peer-memory push (CUDA IPC over NVLink), {ex.rounds_peer} rounds; NCCL all-to-all, {ex.rounds_nccl} rounds (sizing / fallback)"
                                     if world > 1 else "none (one GPU)")},
             "e2e": ({"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_all, "d2h_bytes_per_step": float(hist_bytes * world),

@@ -26,7 +26,7 @@
 #define MB_BLOCK 256
 #define MB_HALO 64            // k - m <= 63 extra hashes behind a tile
 #define MB_NH (MB_TILE + MB_HALO)
-#define MB_MAXW 64            // windows per record at most (one byte per window in the count kernel's map)
+#define MB_MAXW 32            // windows per record at most: k - 1 + 32 symbols fit KW = 2 words for k <= 32
 
 #define MC_BLOCK 256
 #define MC_R 256              // records per stage of the ring (one per thread)
@@ -61,8 +61,8 @@ __device__ __forceinline__ u32 mb_segment_of(const u64 *__restrict__ seg_off, in
 }
 
 // ---- pass P -----------------------------------------------------------------------------------------------------------------
-// Record layout (KW + 1 words of 64 bits, KW = 3 for k <= 32): word 0 = genome << 48 | windows << 40; words 1..KW = the 32 * KW
-// symbols from the record's first window start, MSB first (window e's k-mer = bits [2e, 2e + 2k) of that string).
+// Record layout (KW + 1 words of 64 bits, KW = 2 for k <= 32): word 0 = genome << 48 | windows << 40; words 1..KW = the record's
+// k - 1 + windows <= 32 * KW symbols from its first window start, MSB first, zero behind them (window e's k-mer = bits [2e, 2e + 2k)).
 template <int KW>
 __global__ void __launch_bounds__(MB_BLOCK)
 mb_partition_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, u64 n_sym, u64 last_cw, u64 last_vw, int k, int m, u32 nbins,
@@ -74,6 +74,8 @@ mb_partition_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid
     __shared__ u32 P[MB_NH];                      // prefix minima
     __shared__ u32 sc[2 * CW + 2];                // the tile's symbols as 16-symbol chunks in stream order
     __shared__ u32 sv[VW];
+    __shared__ u32 cell[MB_TILE / 32 + 1];        // boundaries per 32 windows -> their exclusive prefix
+    __shared__ unsigned short blist[MB_TILE + 2]; // the tile's boundaries in window order
     const u32 tid = threadIdx.x;
     const u64 tile0 = (u64)blockIdx.x * MB_TILE;  // a multiple of 32
     const int w = k - m + 1;                      // m-mers per window
@@ -135,17 +137,56 @@ mb_partition_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid
         A[j] = a < p ? a : p;
     }
     __syncthreads();
-    // phase 3: the first window of every run of equal minima writes the run as one record (several if it is longer than capw)
+    // phase 3a: list the boundaries -- windows whose minimum differs from their predecessor's -- in window order (ballots per 32 windows,
+    // one scan over the 128 ballot counts of the tile); segment r = [blist[r], blist[r + 1]) is a run of equal minima or of non-windows
+    const u32 lane = tid & 31u, wrp = tid >> 5;
+    u32 mymask = 0;
+#pragma unroll 4
+    for (u32 it = 0; it < MB_TILE / MB_BLOCK; it++) {
+        const u32 j = it * MB_BLOCK + tid;
+        const u32 cur = A[j];
+        const bool bnd = j == 0 || A[j - 1] != cur;
+        const u32 mk = __ballot_sync(0xffffffffu, bnd);
+        if (lane == it) mymask = mk;
+        if (lane == 0) cell[it * (MB_BLOCK / 32) + wrp] = __popc(mk);
+    }
+    __syncthreads();
+    if (wrp == 0) {
+        constexpr int NC = MB_TILE / 32, PER = NC / 32;
+        u32 c[PER], sum = 0;
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            c[i] = cell[PER * lane + i];
+            sum += c[i];
+        }
+        const u32 inc = warp_incl_sum(sum);
+        u32 run = inc - sum;
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            cell[PER * lane + i] = run;
+            run += c[i];
+        }
+        if (lane == 31) cell[NC] = inc;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (u32 it = 0; it < MB_TILE / MB_BLOCK; it++) {
+        const u32 mk = __shfl_sync(0xffffffffu, mymask, it);
+        if ((mk >> lane) & 1u) blist[cell[it * (MB_BLOCK / 32) + wrp] + __popc(mk & lanemask_lt())] = (unsigned short)(it * MB_BLOCK + tid);
+    }
+    const u32 nbnd = cell[MB_TILE / 32];
+    if (tid == 0) blist[nbnd] = (unsigned short)MB_TILE;
+    __syncthreads();
+    // phase 3b: one thread per run: reserve the record slots in the bin with ONE atomicAdd, write the record(s)
     const u32 g_first = mb_segment_of(seg_off, nseg, tile0);
     const u64 g_first_end = __ldg(seg_off + g_first + 1);
-    for (u32 j = tid; j < MB_TILE; j += MB_BLOCK) {
+    for (u32 r = tid; r < nbnd; r += MB_BLOCK) {
+        const u32 j = blist[r];
         const u32 mh = A[j];
         if (mh == 0u) continue;
-        if (j > 0 && A[j - 1] == mh) continue;
-        u32 len = 1;
-        while (j + len < MB_TILE && A[j + len] == mh) len++;
+        const u32 len = (u32)blist[r + 1] - j;
         const u32 bin = mb_bin_of(mh, nbins);
-        const u32 pieces = (len + capw - 1) / capw;
+        const u32 pieces = len <= capw ? 1u : (len + capw - 1) / capw;
         const u32 at = atomicAdd(&cursor[bin], pieces);
         if (at + pieces > cap) {                   // the bin's region is full: the caller redoes the group another way
             *flags = 1ull;
@@ -153,20 +194,23 @@ mb_partition_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid
         }
         const u64 i0 = tile0 + j;
         const u64 g = i0 < g_first_end ? g_first : mb_segment_of(seg_off, nseg, i0);
-        ulonglong2 *dst = (ulonglong2 *)(rec + ((u64)bin * cap + at) * (KW + 1));
+        u64 *dst = rec + ((u64)bin * cap + at) * (KW + 1);
         for (u32 s0 = 0; s0 < len; s0 += capw) {
             const u32 pl = len - s0 < capw ? len - s0 : capw;
             const u32 rel = j + s0, t = rel >> 4, s = (rel & 15u) * 2u;
+            const int nbits = 2 * (k - 1 + (int)pl);   // the record's symbols; what follows is zeroed so that equal runs give equal records
             u64 W[KW + 1];
             W[0] = (g << 48) | ((u64)pl << 40);
 #pragma unroll
             for (int e = 0; e < KW; e++) {
                 const u32 hi = __funnelshift_l(sc[t + 2 * e + 1], sc[t + 2 * e], s);
                 const u32 lo = __funnelshift_l(sc[t + 2 * e + 2], sc[t + 2 * e + 1], s);
-                W[e + 1] = ((u64)hi << 32) | lo;
+                const int keep = nbits - 64 * e;
+                const u64 mask = keep >= 64 ? ~0ull : keep <= 0 ? 0ull : (~0ull << (64 - keep));
+                W[e + 1] = (((u64)hi << 32) | lo) & mask;
             }
 #pragma unroll
-            for (int e = 0; e < (KW + 1) / 2; e++) *dst++ = make_ulonglong2(W[2 * e], W[2 * e + 1]);
+            for (int e = 0; e <= KW; e++) *dst++ = W[e];
         }
     }
 }
@@ -231,96 +275,138 @@ __device__ __forceinline__ u64 mb_canonical64(u64 x, int k)
 
 #define MB_EMPTY (~0ull)
 
-// Insert `key` (genome bit gb of 64) into the table.  Returns false when the probe sequence is too long (table too full).
-__device__ __forceinline__ bool mb_insert(u64 *tkey, u64 *tbits, u32 s_log2, u64 key, u32 gb, u32 *s_distinct)
+
+// Find or claim the table slot of `key`; -1 when the probe sequence is too long (table too full).
+__device__ __forceinline__ int mb_find_slot(u64 *tkey, u32 s_log2, u64 key, u32 *s_distinct)
 {
     const u32 smask = (1u << s_log2) - 1u;
     u32 slot = (u32)((key * 0x9E3779B97F4A7C15ull) >> 40) & smask;
     for (u32 probes = 0;; probes++) {
         const u64 c = *(volatile u64 *)&tkey[slot];
-        if (c == key) break;
+        if (c == key) return (int)slot;
         if (c == MB_EMPTY) {
             const u64 old = atomicCAS((unsigned long long *)&tkey[slot], MB_EMPTY, key);
             if (old == MB_EMPTY) {
                 atomicAdd(s_distinct, 1u);
-                break;
+                return (int)slot;
             }
-            if (old == key) break;
+            if (old == key) return (int)slot;
         }
-        if (probes >= MC_PROBES) return false;
+        if (probes >= MC_PROBES) return -1;
         slot = (slot + 1) & smask;
     }
-    u32 *bw = (u32 *)&tbits[slot] + (gb >> 5);
+}
+// Insert `key` with genome g's bit (nchunks words of 64 genome bits per slot).  False when the table is too full.
+__device__ __forceinline__ bool mb_insert(u64 *tkey, u64 *tbits, u32 s_log2, u32 nchunks, u64 key, u32 g, u32 *s_distinct)
+{
+    const int slot = mb_find_slot(tkey, s_log2, key, s_distinct);
+    if (slot < 0) return false;
+    const u32 gb = g & 63u;
+    u32 *bw = (u32 *)&tbits[(size_t)slot * nchunks + (g >> 6)] + (gb >> 5);
     const u32 bm = 1u << (gb & 31u);
     if (!(*(volatile u32 *)bw & bm)) atomicOr(bw, bm);
     return true;
 }
-
-// Shared-memory carve-up of the counting kernels (dynamic): table keys, genome bits, counts (more than 64 genomes only), ring,
-// per-record window offsets, window -> record map, histogram.
-struct mc_smem {
-    u64 *tkey, *tbits;
-    u32 *tcnt;
-    u64 *ring;
-    u32 *pre;
-    unsigned char *map;
-    u32 *hist;
-};
-__host__ __device__ inline size_t mc_smem_bytes(int KW, u32 S, bool multi, u32 hrows)
+// OR a 64-bit genome mask into a slot's bits (two 32-bit shared-memory atomics, skipped when nothing new)
+__device__ __forceinline__ void mb_or_mask(u64 *word, u64 mask)
 {
-    return (size_t)S * 16 + (multi ? (size_t)S * 4 : 0) + 2 * (size_t)MC_R * (KW + 1) * 8 + (size_t)(MC_R + 1) * 4 + (size_t)MC_R * MB_MAXW + ((size_t)hrows + 1) * 4 + 64;
+    u32 *bw = (u32 *)word;
+    const u32 lo = (u32)mask, hi = (u32)(mask >> 32);
+    if (lo & ~*(volatile u32 *)bw) atomicOr(bw, lo);
+    if (hi & ~*(volatile u32 *)(bw + 1)) atomicOr(bw + 1, hi);
 }
-__device__ __forceinline__ mc_smem mc_carve(unsigned char *base, int KW, u32 S, bool multi, u32 hrows)
+
+// Shared-memory carve-up of the counting kernels (dynamic): k-mer table (keys, one word of genome bits per 64 genomes), the ring
+// of record stages, the distinct records of the bin (content + one genome mask per chunk of 64 genomes) with their hash index,
+// per-record window offsets, window -> record map, histogram.
+struct mc_geom {
+    u32 s_log2;      // k-mer table slots
+    u32 dcap;        // distinct records held at a time
+    u32 rt_log2;     // slots of the record index (>= 2 * dcap)
+    u32 nchunks;     // chunks of 64 genomes
+    u32 hrows;       // histogram rows kept in shared memory (+ row 0)
+};
+struct mc_smem {
+    u64 *tkey, *tbits, *ring, *dstore, *dmask;
+    u32 *rtab, *pre, *hist;
+    unsigned char *map;
+};
+__host__ __device__ inline size_t mc_smem_bytes(int KW, const mc_geom &g)
 {
+    const size_t S = (size_t)1 << g.s_log2;
+    return S * 8 * (1 + g.nchunks) + 2 * (size_t)MC_R * (KW + 1) * 8 + (size_t)g.dcap * (KW + 1) * 8 + (size_t)g.dcap * g.nchunks * 8 +
+           ((size_t)4 << g.rt_log2) + (size_t)(MC_R + 1) * 4 + ((size_t)g.hrows + 1) * 4 + (size_t)MC_R * MB_MAXW + 64;
+}
+__device__ __forceinline__ mc_smem mc_carve(unsigned char *base, int KW, const mc_geom &g)
+{
+    const size_t S = (size_t)1 << g.s_log2;
     mc_smem s;
     s.tkey = (u64 *)base;
-    s.tbits = s.tkey + S;
-    s.ring = s.tbits + S;
-    unsigned char *p = (unsigned char *)(s.ring + 2 * (size_t)MC_R * (KW + 1));
-    s.tcnt = (u32 *)p;
-    p += multi ? (size_t)S * 4 : 0;
-    s.pre = (u32 *)p;
-    p += (size_t)(MC_R + 1) * 4;
-    s.hist = (u32 *)p;
-    p += ((size_t)hrows + 1) * 4;
-    s.map = p;
+    s.tbits = s.tkey + S;                      // [S][nchunks]
+    s.ring = s.tbits + S * g.nchunks;
+    s.dstore = s.ring + 2 * (size_t)MC_R * (KW + 1);
+    s.dmask = s.dstore + (size_t)g.dcap * (KW + 1);
+    s.rtab = (u32 *)(s.dmask + (size_t)g.dcap * g.nchunks);
+    s.pre = s.rtab + ((size_t)1 << g.rt_log2);
+    s.hist = s.pre + MC_R + 1;
+    s.map = (unsigned char *)(s.hist + g.hrows + 1);
     return s;
 }
 
-template <int KW, bool MULTI>
-__global__ void __launch_bounds__(MC_BLOCK)
-mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32 nbins, u32 cap, int k, u32 s_log2, u32 n_genomes, u32 nchunks, u32 cs,
-                u32 hrows, u32 thr1 /* records one pass over a bin may hold */, u32 over_cap, u64 *__restrict__ hist, u64 *__restrict__ out_keys, u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs,
-                u32 *__restrict__ over_list, u32 *__restrict__ over_count, u64 *__restrict__ d_stat)
+__device__ __forceinline__ u64 mb_record_hash(const u64 *w, int KW, u32 len)
+{
+    u64 h = w[0] * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 32;
+    for (int i = 1; i < KW; i++) {
+        h += w[i];
+        h *= 0xBF58476D1CE4E5B9ull;
+        h ^= h >> 29;
+    }
+    h += len;
+    h *= 0x94D049BB133111EBull;
+    return h ^ (h >> 32);
+}
+
+// Genomes of one group are near copies of each other, so most super-k-mer records of a bin are byte-identical across genomes.  The
+// kernel therefore counts in two levels: every record is looked up in an index of the bin's DISTINCT records (content + genome mask:
+// one hash, one compare, one bit per record), and only the distinct records are expanded into k-mers, each k-mer taking the whole
+// genome mask of its record.  Unrelated genomes lose nothing but the lookup.
+template <int KW, bool MULTI, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32 nbins, u32 cap, int k, mc_geom geo, u32 n_genomes, u32 cs,
+                u32 thr1 /* records one pass over a bin may hold */, u32 over_cap, u64 *__restrict__ hist, u64 *__restrict__ out_keys,
+                u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs, u32 *__restrict__ over_list, u32 *__restrict__ over_count, u64 *__restrict__ d_stat)
 {
     extern __shared__ __align__(16) unsigned char mc_raw[];
     __shared__ __align__(8) u64 bars[2];
     __shared__ mc_desc desc[2];
-    __shared__ u32 s_over, s_distinct, ws[33];
+    __shared__ u32 s_over, s_distinct, s_dcount, s_dfull, ws[33];
     __shared__ u64 s_base;
-    const u32 S = 1u << s_log2;
-    const mc_smem sm = mc_carve(mc_raw, KW, S, MULTI, hrows);
+    const u32 s_log2 = geo.s_log2, S = 1u << s_log2, nchunks = geo.nchunks, hrows = geo.hrows, dcap = geo.dcap, RT = 1u << geo.rt_log2;
+    const mc_smem sm = mc_carve(mc_raw, KW, geo);
+    const u32 NCH = MULTI ? nchunks : 1u;
     const u32 tid = threadIdx.x;
-    for (u32 i = tid; i < S; i += MC_BLOCK) {
-        sm.tkey[i] = MB_EMPTY;
-        sm.tbits[i] = 0ull;
-        if (MULTI) sm.tcnt[i] = 0u;
-    }
-    for (u32 i = tid; i <= hrows; i += MC_BLOCK) sm.hist[i] = 0u;
+    if (d_stat[0] & 1ull) return;   // a bin region overflowed: its slots hold stale bytes, and the caller redoes the group anyway
+    for (u32 i = tid; i < S; i += BLOCK) sm.tkey[i] = MB_EMPTY;
+    for (u32 i = tid; i < S * NCH; i += BLOCK) sm.tbits[i] = 0ull;
+    for (u32 i = tid; i < RT; i += BLOCK) sm.rtab[i] = 0u;
+    for (u32 i = tid; i <= hrows; i += BLOCK) sm.hist[i] = 0u;
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         s_over = 0;
         s_distinct = 0;
+        s_dcount = 0;
+        s_dfull = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     mc_iter it;
     it.bin = blockIdx.x;
     it.off = 0;
-    it.chunk = 0;
     it.cls = 0;
     it.ncls = 1;
+    it.chunk = 0;
     it.n = 0;
     it.n_next = 0;
     u64 my_records = 0;
@@ -342,30 +428,27 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
         }
         const u32 count = it.n - it.off < MC_R ? it.n - it.off : MC_R;
         const bool last = it.off + count == it.n;
-        if (it.off == 0 && it.chunk == 0 && it.cls == 0) {
+        if (it.off == 0 && it.cls == 0) {
             my_records += it.n;
-            it.ncls = (it.n + thr1 - 1) / thr1;
+            it.ncls = it.n <= thr1 ? 1u : (it.n + thr1 - 1) / thr1;
         }
         desc[buf].bin = it.bin;
         desc[buf].count = count;
-        desc[buf].chunk = it.chunk;
+        desc[buf].chunk = 0;
         desc[buf].cls = it.cls;
         desc[buf].ncls = it.ncls;
-        desc[buf].flags = (last ? MCF_LAST : 0u) | (last && it.chunk + 1 == nchunks ? MCF_SCAN : 0u);
-        const u32 bytes = count * (u32)((KW + 1) * 8);
+        desc[buf].flags = last ? (MCF_LAST | MCF_SCAN) : 0u;
+        const u32 bytes = (count * (u32)((KW + 1) * 8) + 15u) & ~15u;   // an odd count of 24-byte records: 8 bytes of the next record ride along
         mbar_arrive_expect_tx(&bars[buf], bytes);
         bulk_g2s(sm.ring + (size_t)buf * MC_R * (KW + 1), rec + ((u64)it.bin * cap + it.off) * (KW + 1), bytes, &bars[buf]);
         it.off += count;
         if (last) {
             it.off = 0;
-            if (++it.chunk == nchunks) {
-                it.chunk = 0;
-                if (++it.cls == it.ncls) {
-                    it.cls = 0;
-                    it.bin += gridDim.x;
-                    it.n = it.n_next;
-                    it.n_next = bin_records(it.bin + gridDim.x);
-                }
+            if (++it.cls == it.ncls) {
+                it.cls = 0;
+                it.bin += gridDim.x;
+                it.n = it.n_next;
+                it.n_next = bin_records(it.bin + gridDim.x);
             }
         }
     };
@@ -378,55 +461,132 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
     const u32 c_all = n_genomes < cs ? n_genomes : cs;   // the count of a k-mer every genome holds
     u32 n_one = 0, n_all = 0;
     u64 pairs = 0;
+
+    // Expand the distinct records collected so far into the k-mer table (every k-mer takes its record's genome masks), then forget them.
+    auto flush_records = [&](u32 cls, u32 ncls) {
+        const u32 nd = s_dcount < dcap ? s_dcount : dcap;
+        for (u32 r0 = 0; r0 < nd; r0 += MC_R) {
+            const u32 id = r0 + tid;
+            const u32 len = (tid < MC_R && id < nd) ? (u32)sm.dstore[(size_t)id * (KW + 1)] : 0u;   // 0: a dead entry
+            u32 total;
+            const u32 off = block_excl_sum<u32>(len, ws, &total);
+            if (tid < MC_R) sm.pre[tid] = off;
+            for (u32 e = 0; e < len; e++) sm.map[off + e] = (unsigned char)tid;
+            __syncthreads();
+            bool ok = true;
+            for (u32 t = tid; t < total; t += BLOCK) {
+                const u32 r = sm.map[t];
+                const u32 e = t - sm.pre[r];
+                const u64 *R = sm.dstore + (size_t)(r0 + r) * (KW + 1);
+                const u32 q = e >> 5, o = e & 31u;
+                const u64 w0 = R[1 + q], w1 = q + 2 <= (u32)KW ? R[2 + q] : 0ull;
+                const u64 x = o ? ((w0 << (2 * o)) | (w1 >> (64 - 2 * o))) : w0;
+                const u64 key = mb_canonical64(x, k);
+                if (ncls > 1 && __umulhi(mb_class_hash(key), ncls) != cls) continue;
+                const int slot = mb_find_slot(sm.tkey, s_log2, key, &s_distinct);
+                if (slot < 0) {
+                    ok = false;
+                    continue;
+                }
+                const u64 *M = sm.dmask + (size_t)(r0 + r) * NCH;
+                u64 *B = sm.tbits + (size_t)slot * NCH;
+                for (u32 c = 0; c < NCH; c++) {
+                    const u64 mk = M[c];
+                    if (mk) mb_or_mask(B + c, mk);
+                }
+            }
+            if (!ok) s_over = 1;
+            __syncthreads();
+        }
+        for (u32 i = tid; i < RT; i += BLOCK) sm.rtab[i] = 0u;
+        if (tid == 0) {
+            s_dcount = 0;
+            s_dfull = 0;
+        }
+        __syncthreads();
+    };
+
     for (u32 s = 0;; s++) {
         const u32 buf = s & 1u;
         mbar_wait(&bars[buf], (s >> 1) & 1u);
         const mc_desc d = desc[buf];
         if (d.flags & MCF_DONE) break;
         if (!s_over) {
-            const u64 *rb = sm.ring + (size_t)buf * MC_R * (KW + 1);
-            u32 len = 0;
-            if (tid < d.count) {
-                const u64 h = rb[(size_t)tid * (KW + 1)];
-                len = (u32)(h >> 40) & 0xffu;
-                if (MULTI && (u32)(h >> 54) != d.chunk) len = 0;   // genome >> 6
+            // level 1: every record of the stage -> the index of distinct records
+            const u64 *R = sm.ring + ((size_t)buf * MC_R + tid) * (KW + 1);
+            bool todo = tid < d.count;
+            u32 g = 0, len = 0;
+            u64 w[KW], h = 0;
+            if (todo) {
+                const u64 hdr = R[0];
+                g = (u32)(hdr >> 48);
+                len = (u32)(hdr >> 40) & 0xffu;
+                len = len < MB_MAXW ? len : MB_MAXW;
+#pragma unroll
+                for (int i = 0; i < KW; i++) w[i] = R[1 + i];
+                h = mb_record_hash(w, KW, len);
             }
-            u32 total;
-            const u32 off = block_excl_sum<u32>(len, ws, &total);
-            sm.pre[tid] = off;
-            for (u32 e = 0; e < len; e++) sm.map[off + e] = (unsigned char)tid;
-            __syncthreads();
-            bool ok = true;
-            for (u32 t = tid; t < total; t += MC_BLOCK) {
-                const u32 r = sm.map[t];
-                const u32 e = t - sm.pre[r];
-                const u64 *R = rb + (size_t)r * (KW + 1);
-                const u32 q = e >> 5, o = e & 31u;
-                const u64 w0 = R[1 + q], w1 = R[2 + q];   // e + k - 1 < 32 * KW, so 2 + q <= KW ... or the value is shifted out
-                const u64 x = o ? ((w0 << (2 * o)) | (w1 >> (64 - 2 * o))) : w0;
-                const u64 key = mb_canonical64(x, k);
-                if (d.ncls > 1 && __umulhi(mb_class_hash(key), d.ncls) != d.cls) continue;
-                const u32 g = (u32)(R[0] >> 48);
-                ok = mb_insert(sm.tkey, sm.tbits, s_log2, key, g & 63u, &s_distinct) && ok;
+            for (;;) {
+                if (todo) {
+                    u32 slot = (u32)h & (RT - 1);
+                    u32 my_id = ~0u, id = ~0u;
+                    for (;;) {
+                        u32 v = *(volatile u32 *)&sm.rtab[slot];
+                        if (v == 0u) {
+                            if (my_id == ~0u) {
+                                my_id = atomicAdd(&s_dcount, 1u);
+                                if (my_id >= dcap) {      // no room: expand what is there, then this record again
+                                    s_dfull = 1;
+                                    break;
+                                }
+                                u64 *D = sm.dstore + (size_t)my_id * (KW + 1);
+                                D[0] = (u64)len;
+#pragma unroll
+                                for (int i = 0; i < KW; i++) D[1 + i] = w[i];
+                                for (u32 c = 0; c < NCH; c++) sm.dmask[(size_t)my_id * NCH + c] = 0ull;
+                                __threadfence_block();
+                            }
+                            v = atomicCAS(&sm.rtab[slot], 0u, my_id + 1u);
+                            if (v == 0u) {
+                                id = my_id;
+                                break;
+                            }
+                        }
+                        const u64 *D = sm.dstore + (size_t)(v - 1u) * (KW + 1);
+                        bool same = (u32)*(volatile u64 *)&D[0] == len;
+#pragma unroll
+                        for (int i = 0; i < KW; i++) same = same && *(volatile u64 *)&D[1 + i] == w[i];
+                        if (same) {
+                            id = v - 1u;
+                            break;
+                        }
+                        slot = (slot + 1) & (RT - 1);
+                    }
+                    if (id != ~0u) {
+                        if (my_id != ~0u && my_id != id) sm.dstore[(size_t)my_id * (KW + 1)] = 0ull;   // lost the race for the slot: a dead entry
+                        u32 *mw = (u32 *)&sm.dmask[(size_t)id * NCH + (MULTI ? (g >> 6) : 0u)] + ((g >> 5) & 1u);
+                        const u32 bm = 1u << (g & 31u);
+                        if (!(*(volatile u32 *)mw & bm)) atomicOr(mw, bm);
+                        todo = false;
+                    }
+                }
+                __syncthreads();
+                if (!s_dfull) break;
+                __syncthreads();
+                flush_records(d.cls, d.ncls);
             }
-            if (!ok) s_over = 1;
         }
         __syncthreads();
-        if (s_distinct > S - S / 4) s_over = 1;     // same value in every thread (s_distinct is stable between the barriers)
-        const bool over = s_over != 0;
-        if (tid == 0) {
-            if ((d.flags & MCF_SCAN) && !over && s_distinct) s_base = atomicAdd((unsigned long long *)d_cursor, (unsigned long long)s_distinct);
-            produce(buf);
-        }
+        if (tid == 0) produce(buf);
         if (!(d.flags & MCF_LAST)) continue;
-        if (over) {
-            if (!(d.flags & MCF_SCAN)) continue;    // keep consuming the stages of this class; it is redone by mb_bigbin_kernel
+        // the last stage of this class of the bin: expand, then every occupied slot is one distinct k-mer of the group
+        if (!s_over) flush_records(d.cls, d.ncls);
+        if (s_distinct > S - S / 4) s_over = 1;     // same value in every thread (s_distinct is stable between the barriers)
+        if (s_over) {
             __syncthreads();
-            for (u32 i = tid; i < S; i += MC_BLOCK) {
-                sm.tkey[i] = MB_EMPTY;
-                sm.tbits[i] = 0ull;
-                if (MULTI) sm.tcnt[i] = 0u;
-            }
+            for (u32 i = tid; i < S; i += BLOCK) sm.tkey[i] = MB_EMPTY;
+            for (u32 i = tid; i < S * NCH; i += BLOCK) sm.tbits[i] = 0ull;
+            for (u32 i = tid; i < RT; i += BLOCK) sm.rtab[i] = 0u;
             if (tid == 0) {
                 const u32 at = atomicAdd(over_count, 1u);
                 if (at < over_cap) {
@@ -438,32 +598,26 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
                 }
                 s_over = 0;
                 s_distinct = 0;
+                s_dcount = 0;
+                s_dfull = 0;
             }
             __syncthreads();
             continue;
         }
-        if (MULTI && !(d.flags & MCF_SCAN)) {       // end of a 64-genome chunk: fold the bits into the counts
-            for (u32 i = tid; i < S; i += MC_BLOCK) {
-                const u64 b = sm.tbits[i];
-                if (b) {
-                    sm.tcnt[i] += (u32)__popcll(b);
-                    sm.tbits[i] = 0ull;
-                }
-            }
-            __syncthreads();
-            continue;
-        }
-        // end of the bin: every occupied slot is one distinct k-mer of the group
+        if (tid == 0 && s_distinct) s_base = atomicAdd((unsigned long long *)d_cursor, (unsigned long long)s_distinct);
         u32 mine = 0;
-        for (u32 i = tid; i < S; i += MC_BLOCK) mine += sm.tkey[i] != MB_EMPTY;
+        for (u32 i = tid; i < S; i += BLOCK) mine += sm.tkey[i] != MB_EMPTY;
         u32 total;
         u32 at = block_excl_sum<u32>(mine, ws, &total);
         const u64 base = s_base;
-        for (u32 i = tid; i < S; i += MC_BLOCK) {
+        for (u32 i = tid; i < S; i += BLOCK) {
             const u64 key = sm.tkey[i];
             if (key == MB_EMPTY) continue;
-            u32 c = (u32)__popcll(sm.tbits[i]);
-            if (MULTI) c += sm.tcnt[i];
+            u32 c = 0;
+            for (u32 j = 0; j < NCH; j++) {
+                c += (u32)__popcll(sm.tbits[(size_t)i * NCH + j]);
+                sm.tbits[(size_t)i * NCH + j] = 0ull;
+            }
             pairs += c;
             const u32 cc = c > cs ? cs : c;
             if (cc == 1u) n_one++;
@@ -472,8 +626,6 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
             if (out_keys) out_keys[base + at] = kmer_mix64(key, k);
             at++;
             sm.tkey[i] = MB_EMPTY;
-            sm.tbits[i] = 0ull;
-            if (MULTI) sm.tcnt[i] = 0u;
         }
         __syncthreads();
         if (tid == 0) s_distinct = 0;
@@ -493,7 +645,7 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
     }
     if (tid == 0 && my_records) atomicAdd((unsigned long long *)&d_stat[1], (unsigned long long)my_records);
     __syncthreads();
-    for (u32 i = tid; i <= hrows; i += MC_BLOCK) {
+    for (u32 i = tid; i <= hrows; i += BLOCK) {
         const u32 v = sm.hist[i];
         if (v) atomicAdd((unsigned long long *)&hist[i], (unsigned long long)v);
     }
@@ -502,24 +654,23 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
 // ---- pass B: the bins whose table filled up, redone with the keys split into P hash classes, one class per pass ------------------
 template <int KW, bool MULTI>
 __global__ void __launch_bounds__(MC_BLOCK)
-mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32 cap, int k, u32 s_log2, u32 n_genomes, u32 nchunks, u32 cs, u32 hrows,
+mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32 cap, int k, mc_geom geo, u32 n_genomes, u32 cs,
                  u64 *__restrict__ hist, u64 *__restrict__ out_keys, u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs,
                  const u32 *__restrict__ over_list, const u32 *__restrict__ over_count, u32 over_cap, u64 *__restrict__ flags)
 {
     extern __shared__ __align__(16) unsigned char mc_raw[];
     __shared__ u32 s_over, s_distinct, ws[33];
     __shared__ u64 s_base;
-    const u32 S = 1u << s_log2;
-    const mc_smem sm = mc_carve(mc_raw, KW, S, MULTI, hrows);
+    const u32 s_log2 = geo.s_log2, S = 1u << s_log2, nchunks = geo.nchunks, hrows = geo.hrows;
+    const mc_smem sm = mc_carve(mc_raw, KW, geo);
+    const u32 NCH = MULTI ? nchunks : 1u;
     const u32 tid = threadIdx.x;
     const u32 n_over = *over_count < over_cap ? *over_count : over_cap;
+    if (flags[0] & 1ull) return;
     if (blockIdx.x == 0 && tid == 0) flags[2] = n_over;
     if (blockIdx.x >= n_over) return;
-    for (u32 i = tid; i < S; i += MC_BLOCK) {
-        sm.tkey[i] = MB_EMPTY;
-        sm.tbits[i] = 0ull;
-        if (MULTI) sm.tcnt[i] = 0u;
-    }
+    for (u32 i = tid; i < S; i += MC_BLOCK) sm.tkey[i] = MB_EMPTY;
+    for (u32 i = tid; i < S * NCH; i += MC_BLOCK) sm.tbits[i] = 0ull;
     for (u32 i = tid; i <= hrows; i += MC_BLOCK) sm.hist[i] = 0u;
     if (tid == 0) {
         s_over = 0;
@@ -539,47 +690,32 @@ mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u3
         stM[sp] = 2; stR[sp++] = 0;
         while (sp > 0) {
             const u32 M = stM[--sp], r0 = stR[sp];
-            for (u32 chunk = 0; chunk < nchunks; chunk++) {
+            {
                 const u32 sub = tid & 15u, grp = tid >> 4;   // 16 lanes share a record
                 bool ok = true;
                 for (u32 r = grp; r < n; r += MC_BLOCK / 16) {
                     const u64 *R = rb + (size_t)r * (KW + 1);
                     const u64 h = R[0];
                     const u32 g = (u32)(h >> 48), len = (u32)(h >> 40) & 0xffu;
-                    if (MULTI && (g >> 6) != chunk) continue;
                     for (u32 e = sub; e < len; e += 16) {
                         const u32 q = e >> 5, o = e & 31u;
-                        const u64 w0 = R[1 + q], w1 = R[2 + q];
+                        const u64 w0 = R[1 + q], w1 = q + 2 <= (u32)KW ? R[2 + q] : 0ull;
                         const u64 x = o ? ((w0 << (2 * o)) | (w1 >> (64 - 2 * o))) : w0;
                         const u64 key = mb_canonical64(x, k);
                         if (ncls0 > 1 && __umulhi(mb_class_hash(key), ncls0) != cls0) continue;
                         if ((u32)((key * 0x9E3779B97F4A7C15ull) >> 20) % M != r0) continue;
-                        ok = mb_insert(sm.tkey, sm.tbits, s_log2, key, g & 63u, &s_distinct) && ok;
+                        ok = mb_insert(sm.tkey, sm.tbits, s_log2, NCH, key, MULTI ? g : (g & 63u), &s_distinct) && ok;
                     }
                 }
                 if (!ok) s_over = 1;
                 __syncthreads();
                 if (s_distinct > S - S / 4) s_over = 1;
-                if (s_over) break;
-                if (MULTI && chunk + 1 < nchunks) {
-                    for (u32 i = tid; i < S; i += MC_BLOCK) {
-                        const u64 b = sm.tbits[i];
-                        if (b) {
-                            sm.tcnt[i] += (u32)__popcll(b);
-                            sm.tbits[i] = 0ull;
-                        }
-                    }
-                    __syncthreads();
-                }
             }
             const bool over = s_over != 0;
             __syncthreads();
             if (over) {
-                for (u32 i = tid; i < S; i += MC_BLOCK) {
-                    sm.tkey[i] = MB_EMPTY;
-                    sm.tbits[i] = 0ull;
-                    if (MULTI) sm.tcnt[i] = 0u;
-                }
+                for (u32 i = tid; i < S; i += MC_BLOCK) sm.tkey[i] = MB_EMPTY;
+                for (u32 i = tid; i < S * NCH; i += MC_BLOCK) sm.tbits[i] = 0ull;
                 if (tid == 0) {
                     s_over = 0;
                     s_distinct = 0;
@@ -603,16 +739,17 @@ mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u3
             for (u32 i = tid; i < S; i += MC_BLOCK) {
                 const u64 key = sm.tkey[i];
                 if (key == MB_EMPTY) continue;
-                u32 c = (u32)__popcll(sm.tbits[i]);
-                if (MULTI) c += sm.tcnt[i];
+                u32 c = 0;
+                for (u32 j = 0; j < NCH; j++) {
+                    c += (u32)__popcll(sm.tbits[(size_t)i * NCH + j]);
+                    sm.tbits[(size_t)i * NCH + j] = 0ull;
+                }
                 pairs += c;
                 const u32 cc = c > cs ? cs : c;
                 if (cc <= hrows) atomicAdd(&sm.hist[cc], 1u);
                 if (out_keys) out_keys[base + at] = kmer_mix64(key, k);
                 at++;
                 sm.tkey[i] = MB_EMPTY;
-                sm.tbits[i] = 0ull;
-                if (MULTI) sm.tcnt[i] = 0u;
             }
             __syncthreads();
             if (tid == 0) s_distinct = 0;
@@ -641,7 +778,7 @@ static long long mb_env(const char *name, long long dflt)
 // Does the minimizer-bin path apply?  (64-bit keys with a spare value, enough m-mers per window for super-k-mers to pay.)
 int khb_bins_eligible(int k, int n_genomes, u64 n_sym)
 {
-    return k >= 17 && k <= 31 && n_genomes >= 1 && n_genomes <= 4096 && n_sym >= 1 && n_sym < (1ull << 40);
+    return k >= 17 && k <= 31 && n_genomes >= 1 && n_genomes <= 512 && n_sym >= 1 && n_sym < (1ull << 40);
 }
 
 // The group stage through minimizer bins.  d_stat: u64[4] in device memory, written here: [0] flags (1: a bin region overflowed,
@@ -652,41 +789,55 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
                         u64 *d_hist, void *d_out_keys, u64 *d_runs, u64 *d_pairs, u64 *d_stat)
 {
     if (!khb_bins_eligible(k, n_genomes, n_sym)) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: k=%d / %d genomes not supported", k, n_genomes);
-    constexpr int KW = 3;
+    constexpr int KW = 2;                         // 64 symbols per record: k - 1 + 32 windows for k <= 32
     const int m = 13, w = k - m + 1;
     const u32 capw = (u32)(32 * KW + 1 - k) < MB_MAXW ? (u32)(32 * KW + 1 - k) : MB_MAXW;
     // Bin geometry.  All copies of a k-mer -- one per genome that holds it, ~ (w + 1) / 2 windows around each -- land in one bin together, so
-    // a bin's load comes in lumps of ~10 x n_genomes windows; with ~16 lumps per bin the largest bin stays within ~2.5 x the mean.
-    u64 wpb_dflt = 160ull * (u64)n_genomes;
-    wpb_dflt = wpb_dflt < 2048 ? 2048 : wpb_dflt > 16384 ? 16384 : wpb_dflt;
+    // a bin's load comes in lumps of ~10 x n_genomes windows; with ~8 lumps per bin the largest bin stays within ~3 x the mean.
+    u64 wpb_dflt = 80ull * (u64)n_genomes;
+    wpb_dflt = wpb_dflt < 1024 ? 1024 : wpb_dflt > 8192 ? 8192 : wpb_dflt;
     const u64 wpb = (u64)mb_env("KHB_BINS_WPB", (long long)wpb_dflt);
     u64 nb64 = div_up(n_sym, wpb ? wpb : wpb_dflt);
     if (nb64 < 16) nb64 = 16;
     if (nb64 > (1ull << 28)) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: group too large");
     const u32 nb = (u32)nb64;
-    const u32 s_log2 = (u32)mb_env("KHB_BINS_SLOTS_LOG2", 12);
-    if (s_log2 < 8 || s_log2 > 13) return khb_fail(ctx, KHB_ERR_ARG, "KHB_BINS_SLOTS_LOG2 outside 8..13");
+    // distinct k-mers per window: measured on the previous group (+ 25 %), else a guess from the group size
+    double rho_w = ctx->bins_rho > 0.0 ? ctx->bins_rho * 1.25 : (n_genomes >= 16 ? 0.25 : n_genomes >= 4 ? 0.5 : 1.0);
+    const long long rho_pct = mb_env("KHB_BINS_RHO_PCT", 0);   // test hook: distinct k-mers per 100 windows
+    if (rho_pct > 0) rho_w = rho_pct / 100.0;
+    if (rho_w > 1.0) rho_w = 1.0;
+    if (rho_w < 0.005) rho_w = 0.005;
+    mc_geom geo;
+    geo.nchunks = (u32)div_up((size_t)n_genomes, 64);
+    {   // table slots: the mean bin's distinct k-mers fill ~45 % (larger bins are counted in hash classes), within what an SM can hold
+        const double want = (double)(n_sym / nb + 1) * rho_w / 0.45;
+        u32 l2 = 10;
+        while (l2 < 12 && (double)(1u << l2) < want) l2++;
+        while (l2 > 10 && ((size_t)8 << l2) * (1 + geo.nchunks) > (size_t)170 * 1024) l2--;
+        geo.s_log2 = (u32)mb_env("KHB_BINS_SLOTS_LOG2", l2);
+        if (geo.s_log2 < 8 || geo.s_log2 > 13) return khb_fail(ctx, KHB_ERR_ARG, "KHB_BINS_SLOTS_LOG2 outside 8..13");
+    }
+    geo.hrows = nbins_hist < (u32)n_genomes ? nbins_hist : (u32)n_genomes;
+    geo.dcap = (u32)mb_env("KHB_BINS_DCAP", geo.nchunks <= 4 ? 256 : 128);
+    if (geo.dcap < 64 || geo.dcap > 4096) return khb_fail(ctx, KHB_ERR_ARG, "KHB_BINS_DCAP outside 64..4096");
+    geo.rt_log2 = 7;
+    while ((1u << geo.rt_log2) < 2 * geo.dcap) geo.rt_log2++;
+    const u32 s_log2 = geo.s_log2;
     double avg_len = (w + 1) * 0.5;
     if (avg_len > capw) avg_len = capw;
     const double est_records = (double)n_sym / avg_len * 1.15 + (double)div_up(n_sym, MB_TILE);
     const double slack = (double)mb_env("KHB_BINS_SLACK_PCT", 400) / 100.0;
-    const u32 cap = (u32)(est_records / nb * slack) + 64u;
+    const u32 cap = ((u32)(est_records / nb * slack) + 64u) & ~1u;   // even: every bin's region starts 16-byte aligned
     const size_t rec_bytes = (size_t)nb * cap * (KW + 1) * 8;
-    // Records one pass over a bin may hold so that its distinct k-mers fill at most ~55 % of the table: from the distinct k-mers per
-    // record of the previous group (ctx->bins_rho), else a guess from the group size; larger bins are counted in several hash classes.
-    double rho = ctx->bins_rho > 0.0 ? ctx->bins_rho * 1.25 : avg_len * (n_genomes >= 16 ? 0.25 : n_genomes >= 4 ? 0.5 : 1.0);
-    const long long rho_pct = mb_env("KHB_BINS_RHO_PCT", 0);   // test hook: distinct k-mers per record, in percent
-    if (rho_pct > 0) rho = rho_pct / 100.0;
-    if (rho < 0.05) rho = 0.05;
-    double thr = 0.55 * (double)(1u << s_log2) / rho;
+    // Records one pass over a bin may hold so that its distinct k-mers fill at most ~55 % of the table; larger bins are counted in
+    // several hash classes.
+    double thr = 0.55 * (double)(1u << s_log2) / (rho_w * avg_len);
     const u32 thr1 = thr < 8.0 ? 8u : thr > 1e9 ? 1000000000u : (u32)thr;
-    const u32 over_cap = nb;
-    const u32 nchunks = (u32)div_up((size_t)n_genomes, 64);
-    const bool multi = nchunks > 1;
-    const u32 hrows = nbins_hist < (u32)n_genomes ? nbins_hist : (u32)n_genomes;
+    const u32 over_cap = 4 * nb;
+    const bool multi = geo.nchunks > 1;
     int rc;
     void *p;
-    if ((rc = khb_scratch_get(ctx, SCR_AUX, (size_t)nb * 16 + 256, &p))) return rc;
+    if ((rc = khb_scratch_get(ctx, SCR_AUX, (size_t)nb * 52 + 256, &p))) return rc;
     u32 *d_over_count = (u32 *)p;                 // [0] bins in the list
     u32 *d_cur = d_over_count + 16, *d_over_list = d_cur + nb;
     void *pr;
@@ -706,38 +857,36 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
         KHB_LAUNCH_CHECK(ctx);
     }
     {
-        const size_t shm = mc_smem_bytes(KW, 1u << s_log2, multi, hrows);
+        const size_t shm = mc_smem_bytes(KW, geo);
+        if (shm > 227 * 1024) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: %zu bytes of shared memory per CTA", shm);
+        // two CTAs of 256 threads per SM at least; where the tables leave room for one CTA only, that one has 512 threads
+        const bool wide = 2 * (shm + 1024) > 227 * 1024;
+        const void *fn = multi ? (wide ? (const void *)mb_count_kernel<KW, true, 512> : (const void *)mb_count_kernel<KW, true, 256>)
+                               : (wide ? (const void *)mb_count_kernel<KW, false, 512> : (const void *)mb_count_kernel<KW, false, 256>);
+        const void *bfn = multi ? (const void *)mb_bigbin_kernel<KW, true> : (const void *)mb_bigbin_kernel<KW, false>;
+        const int block = wide ? 512 : 256;
         int per_sm = 0;
-        if (multi) {
-            KHB_CUDA(ctx, cudaFuncSetAttribute(mb_count_kernel<KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-            KHB_CUDA(ctx, cudaFuncSetAttribute(mb_bigbin_kernel<KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-            KHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mb_count_kernel<KW, true>, MC_BLOCK, shm));
-        } else {
-            KHB_CUDA(ctx, cudaFuncSetAttribute(mb_count_kernel<KW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-            KHB_CUDA(ctx, cudaFuncSetAttribute(mb_bigbin_kernel<KW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-            KHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mb_count_kernel<KW, false>, MC_BLOCK, shm));
-        }
+        KHB_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+        KHB_CUDA(ctx, cudaFuncSetAttribute(bfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+        KHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, shm));
         if (per_sm < 1) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: the counting kernel does not fit an SM (%zu bytes of shared memory)", shm);
         const long long want = mb_env("KHB_BINS_CTAS_PER_SM", 0);
         if (want > 0 && want < per_sm) per_sm = (int)want;
         u32 grid = (u32)ctx->num_sms * (u32)per_sm;
         if (grid > nb) grid = nb;
+        const u64 *c_rec = (const u64 *)pr;
+        const u32 *c_cur = d_cur;
+        u32 n_gen = (u32)n_genomes, cs_ = cs, nb_ = nb, cap_ = cap, thr_ = thr1, ocap_ = over_cap;
+        int k_ = k;
+        u64 *keys_ = (u64 *)d_out_keys;
+        const u32 *c_list = d_over_list, *c_cnt = d_over_count;
+        void *cargs[] = {&c_rec, &c_cur, &nb_, &cap_, &k_, &geo, &n_gen, &cs_, &thr_, &ocap_, &d_hist, &keys_, &d_runs, &d_pairs, &d_over_list, &d_over_count, &d_stat};
         khb_prof_begin(ctx, KHB_K_BIN_COUNT);
-        if (multi)
-            mb_count_kernel<KW, true><<<grid, MC_BLOCK, shm, ctx->stream>>>((const u64 *)pr, d_cur, nb, cap, k, s_log2, (u32)n_genomes, nchunks, cs, hrows, thr1, over_cap,
-                                                                            d_hist, (u64 *)d_out_keys, d_runs, d_pairs, d_over_list, d_over_count, d_stat);
-        else
-            mb_count_kernel<KW, false><<<grid, MC_BLOCK, shm, ctx->stream>>>((const u64 *)pr, d_cur, nb, cap, k, s_log2, (u32)n_genomes, nchunks, cs, hrows, thr1, over_cap,
-                                                                             d_hist, (u64 *)d_out_keys, d_runs, d_pairs, d_over_list, d_over_count, d_stat);
+        KHB_CUDA(ctx, cudaLaunchKernel(fn, dim3(grid), dim3(block), cargs, shm, ctx->stream));
         khb_prof_end(ctx, KHB_K_BIN_COUNT, 0);
         KHB_LAUNCH_CHECK(ctx);
-        const u32 bgrid = (u32)ctx->num_sms * 2u;
-        if (multi)
-            mb_bigbin_kernel<KW, true><<<bgrid, MC_BLOCK, shm, ctx->stream>>>((const u64 *)pr, d_cur, cap, k, s_log2, (u32)n_genomes, nchunks, cs, hrows, d_hist,
-                                                                              (u64 *)d_out_keys, d_runs, d_pairs, d_over_list, d_over_count, over_cap, d_stat);
-        else
-            mb_bigbin_kernel<KW, false><<<bgrid, MC_BLOCK, shm, ctx->stream>>>((const u64 *)pr, d_cur, cap, k, s_log2, (u32)n_genomes, nchunks, cs, hrows, d_hist,
-                                                                               (u64 *)d_out_keys, d_runs, d_pairs, d_over_list, d_over_count, over_cap, d_stat);
+        void *bargs[] = {&c_rec, &c_cur, &cap_, &k_, &geo, &n_gen, &cs_, &d_hist, &keys_, &d_runs, &d_pairs, &c_list, &c_cnt, &ocap_, &d_stat};
+        KHB_CUDA(ctx, cudaLaunchKernel(bfn, dim3((u32)ctx->num_sms * 2u), dim3(MC_BLOCK), bargs, shm, ctx->stream));
         KHB_LAUNCH_CHECK(ctx);
     }
     return KHB_OK;

@@ -212,7 +212,7 @@ struct khb_ctx {
     u64 hs_overflows;  // groups that fell back to the sort path because a probe sequence hit the limit
     struct khb_peer *peer;  // multi-GPU exchange over peer memory (peer.cu)
     cudaStream_t prof_stream;  // stream the next khb_prof_begin/end pair records on (null: `stream`)
-    double bins_rho;   // distinct k-mers per super-k-mer record in the last group the minimizer-bin path counted (sizes the next group's passes)
+    double bins_rho;   // distinct k-mers per window in the last group the minimizer-bin path counted (sizes the next group's passes)
     u64 bins_fallbacks, bins_bigbins;  // groups the minimizer-bin path handed to the sort path / bins redone in hash classes (bins.cu)
     int group_mode;    // KHB_GROUP_* (khb_set_group_mode; initial value from the environment variable KHB_GROUP_MODE)
 };

@@ -1,0 +1,6 @@
+# ncu --set full of the two kernels of the minimizer-bin group stage on one config-2 group (after the same command exited 0 without ncu)
+set -x
+export KHB_BENCH_GROUPS=1 KHB_BENCH_E2E=0
+CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
+$CMD > gpurun_out/ncu_bins_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'mb_partition|mb_count' -s 2 -c 2 -f -o gpurun_out/ncu_bins $CMD > gpurun_out/ncu_bins.log 2>&1
+echo "ncu rc=$?"; tail -3 gpurun_out/ncu_bins.log

@@ -2,9 +2,10 @@
 page with `nvdisasm -g` line info of the object file.
 usage: python scripts/ncu_lines.py report.ncu-rep kernel-index object.o mangled-substring [topn]"""
 import csv, io, re, subprocess, sys, tempfile, os, collections
+KSEL = (["--kernel-name", "regex:" + os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else [])  # select one kernel of a multi-kernel report
 rep, kidx, obj, sub = sys.argv[1], int(sys.argv[2]), sys.argv[3], sys.argv[4]
 topn = int(sys.argv[5]) if len(sys.argv) > 5 else 40
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"] + KSEL, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr = None; data = []; seen = -1
 for r in rows:

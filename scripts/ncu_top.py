@@ -1,7 +1,8 @@
 """Summarise an ncu report: key raw metrics + top stall SASS lines.  usage: python scripts/ncu_top.py report.ncu-rep [n] [kernel-index]"""
-import csv, subprocess, sys, io
+import os, csv, subprocess, sys, io
+KSEL = (["--kernel-name", "regex:" + os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else [])  # select one kernel of a multi-kernel report
 rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 30; kidx = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + KSEL, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
@@ -16,7 +17,7 @@ for i, h in enumerate(hdr):
     if 'issue_stalled' in h and h.endswith('per_issue_active.ratio'):
         vals = [float(r[i]) for r in rows[2:]]
         if max(vals) > 0.3: print(f"  stall {h.split('issue_stalled_')[1].split('_per_')[0]:20s} {vals}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"] + KSEL, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr = None; data = []; seen = -1
 for r in rows:

@@ -90,7 +90,7 @@ def test_edge_inputs(engine, oracle):
 
 def test_long_runs_are_split_into_several_records(engine, oracle):
     """Low-complexity sequence: thousands of consecutive windows share one minimizer, so a run is cut into records of at most
-    97 - k (<= 64) windows and into pieces at tile boundaries; homopolymers and short tandem repeats also put one k-mer into a
+    65 - k (<= 32) windows and into pieces at tile boundaries; homopolymers and short tandem repeats also put one k-mer into a
     bin thousands of times."""
     rng = np.random.default_rng(11)
     k = 25
