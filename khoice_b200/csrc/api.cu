@@ -867,6 +867,9 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
                 goto again;
             }
             ctx->bins_bigbins += ctx->h_mail[5];
+            if (getenv("KHB_BINS_VERBOSE"))
+                fprintf(stderr, "[bins] records=%llu distinct_records=%llu flushes=%llu distinct_kmers=%llu bigbins=%llu\n", (unsigned long long)ctx->h_mail[4],
+                        (unsigned long long)ctx->h_mail[7], (unsigned long long)ctx->h_mail[6], (unsigned long long)ctx->h_mail[0], (unsigned long long)ctx->h_mail[5]);
             if (n_sym) ctx->bins_rho = (double)ctx->h_mail[0] / (double)n_sym;
             khb_prof_patch(ctx, KHB_K_BIN_PARTITION, n_sym * 3 / 8 + ctx->h_mail[4] * 32);
             khb_prof_patch(ctx, KHB_K_BIN_COUNT, ctx->h_mail[4] * 32 + ctx->h_mail[0] * 8);

@@ -31,6 +31,8 @@
 #define MC_BLOCK 256
 #define MC_R 256              // records per stage of the ring (one per thread)
 #define MC_PROBES 48
+#define MC_WCAP 4096          // windows of distinct records laid out at a time
+#define MC_PENDING 0xffffffffu // an index slot whose owner is still writing its record
 
 __device__ __forceinline__ u32 mb_mix32(u32 x)
 {
@@ -66,7 +68,8 @@ __device__ __forceinline__ u32 mb_segment_of(const u64 *__restrict__ seg_off, in
 template <int KW>
 __global__ void __launch_bounds__(MB_BLOCK)
 mb_partition_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, u64 n_sym, u64 last_cw, u64 last_vw, int k, int m, u32 nbins,
-                    const u64 *__restrict__ seg_off, int nseg, u32 *__restrict__ cursor, u64 *__restrict__ rec, u32 cap, u32 capw, u64 *__restrict__ flags)
+                    const u64 *__restrict__ seg_off, int nseg, u32 nchunks, u32 *__restrict__ cursor, u64 *__restrict__ rec, u32 cap, u32 capw,
+                    u64 *__restrict__ flags)
 {
     constexpr int CW = MB_TILE / 32 + KW + 2;     // 64-bit code words staged per tile
     constexpr int VW = MB_TILE / 32 + 4;
@@ -185,16 +188,16 @@ mb_partition_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid
         const u32 mh = A[j];
         if (mh == 0u) continue;
         const u32 len = (u32)blist[r + 1] - j;
-        const u32 bin = mb_bin_of(mh, nbins);
+        const u64 i0 = tile0 + j;
+        const u64 g = i0 < g_first_end ? g_first : mb_segment_of(seg_off, nseg, i0);
+        const u32 region = mb_bin_of(mh, nbins) * nchunks + (u32)(g >> 6);   // one region per bin and chunk of 64 genomes
         const u32 pieces = len <= capw ? 1u : (len + capw - 1) / capw;
-        const u32 at = atomicAdd(&cursor[bin], pieces);
-        if (at + pieces > cap) {                   // the bin's region is full: the caller redoes the group another way
+        const u32 at = atomicAdd(&cursor[region], pieces);
+        if (at + pieces > cap) {                   // the region is full: the caller redoes the group another way
             *flags = 1ull;
             continue;
         }
-        const u64 i0 = tile0 + j;
-        const u64 g = i0 < g_first_end ? g_first : mb_segment_of(seg_off, nseg, i0);
-        u64 *dst = rec + ((u64)bin * cap + at) * (KW + 1);
+        u64 *dst = rec + ((u64)region * cap + at) * (KW + 1);
         for (u32 s0 = 0; s0 < len; s0 += capw) {
             const u32 pl = len - s0 < capw ? len - s0 : capw;
             const u32 rel = j + s0, t = rel >> 4, s = (rel & 15u) * 2u;
@@ -276,8 +279,8 @@ __device__ __forceinline__ u64 mb_canonical64(u64 x, int k)
 #define MB_EMPTY (~0ull)
 
 
-// Find or claim the table slot of `key`; -1 when the probe sequence is too long (table too full).
-__device__ __forceinline__ int mb_find_slot(u64 *tkey, u32 s_log2, u64 key, u32 *s_distinct)
+// Find or claim the table slot of `key` (a claimed slot is appended to slots[]); -1 when the probe sequence is too long (table too full).
+__device__ __forceinline__ int mb_find_slot(u64 *tkey, unsigned short *slots, u32 s_log2, u64 key, u32 *s_distinct)
 {
     const u32 smask = (1u << s_log2) - 1u;
     u32 slot = (u32)((key * 0x9E3779B97F4A7C15ull) >> 40) & smask;
@@ -287,7 +290,7 @@ __device__ __forceinline__ int mb_find_slot(u64 *tkey, u32 s_log2, u64 key, u32 
         if (c == MB_EMPTY) {
             const u64 old = atomicCAS((unsigned long long *)&tkey[slot], MB_EMPTY, key);
             if (old == MB_EMPTY) {
-                atomicAdd(s_distinct, 1u);
+                slots[atomicAdd(s_distinct, 1u)] = (unsigned short)slot;   // the occupied slots, densely: the end-of-bin pass never looks at an empty one
                 return (int)slot;
             }
             if (old == key) return (int)slot;
@@ -296,13 +299,12 @@ __device__ __forceinline__ int mb_find_slot(u64 *tkey, u32 s_log2, u64 key, u32 
         slot = (slot + 1) & smask;
     }
 }
-// Insert `key` with genome g's bit (nchunks words of 64 genome bits per slot).  False when the table is too full.
-__device__ __forceinline__ bool mb_insert(u64 *tkey, u64 *tbits, u32 s_log2, u32 nchunks, u64 key, u32 g, u32 *s_distinct)
+// Insert `key` with genome bit gb (of the 64 of the current chunk of genomes).  False when the table is too full.
+__device__ __forceinline__ bool mb_insert(u64 *tkey, u64 *tbits, unsigned short *slots, u32 s_log2, u64 key, u32 gb, u32 *s_distinct)
 {
-    const int slot = mb_find_slot(tkey, s_log2, key, s_distinct);
+    const int slot = mb_find_slot(tkey, slots, s_log2, key, s_distinct);
     if (slot < 0) return false;
-    const u32 gb = g & 63u;
-    u32 *bw = (u32 *)&tbits[(size_t)slot * nchunks + (g >> 6)] + (gb >> 5);
+    u32 *bw = (u32 *)&tbits[slot] + (gb >> 5);
     const u32 bm = 1u << (gb & 31u);
     if (!(*(volatile u32 *)bw & bm)) atomicOr(bw, bm);
     return true;
@@ -316,8 +318,8 @@ __device__ __forceinline__ void mb_or_mask(u64 *word, u64 mask)
     if (hi & ~*(volatile u32 *)(bw + 1)) atomicOr(bw + 1, hi);
 }
 
-// Shared-memory carve-up of the counting kernels (dynamic): k-mer table (keys, one word of genome bits per 64 genomes), the ring
-// of record stages, the distinct records of the bin (content + one genome mask per chunk of 64 genomes) with their hash index,
+// Shared-memory carve-up of the counting kernels (dynamic): k-mer table (keys, 64 genome bits, counts when there are more genomes), the ring
+// of record stages, the distinct records of the bin (content + genome mask) with their hash index,
 // per-record window offsets, window -> record map, histogram.
 struct mc_geom {
     u32 s_log2;      // k-mer table slots
@@ -328,28 +330,30 @@ struct mc_geom {
 };
 struct mc_smem {
     u64 *tkey, *tbits, *ring, *dstore, *dmask;
-    u32 *rtab, *pre, *hist;
-    unsigned char *map;
+    u32 *rtab, *hist;
+    unsigned short *tcnt, *slots, *dwoff, *map;
 };
-__host__ __device__ inline size_t mc_smem_bytes(int KW, const mc_geom &g)
+__host__ __device__ inline size_t mc_smem_bytes(int KW, const mc_geom &g, int block)
 {
     const size_t S = (size_t)1 << g.s_log2;
-    return S * 8 * (1 + g.nchunks) + 2 * (size_t)MC_R * (KW + 1) * 8 + (size_t)g.dcap * (KW + 1) * 8 + (size_t)g.dcap * g.nchunks * 8 +
-           ((size_t)4 << g.rt_log2) + (size_t)(MC_R + 1) * 4 + ((size_t)g.hrows + 1) * 4 + (size_t)MC_R * MB_MAXW + 64;
+    return S * 16 + 2 * (size_t)MC_R * (KW + 1) * 8 + (size_t)g.dcap * (KW + 1) * 8 + (size_t)g.dcap * 8 + ((size_t)4 << g.rt_log2) +
+           (((size_t)g.hrows + 2) & ~(size_t)1) * 4 + (g.nchunks > 1 ? S * 2 : 0) + S * 2 + (size_t)g.dcap * 2 + (size_t)MC_WCAP * 2 + 64;
 }
 __device__ __forceinline__ mc_smem mc_carve(unsigned char *base, int KW, const mc_geom &g)
 {
     const size_t S = (size_t)1 << g.s_log2;
     mc_smem s;
     s.tkey = (u64 *)base;
-    s.tbits = s.tkey + S;                      // [S][nchunks]
-    s.ring = s.tbits + S * g.nchunks;
+    s.tbits = s.tkey + S;
+    s.ring = s.tbits + S;
     s.dstore = s.ring + 2 * (size_t)MC_R * (KW + 1);
     s.dmask = s.dstore + (size_t)g.dcap * (KW + 1);
-    s.rtab = (u32 *)(s.dmask + (size_t)g.dcap * g.nchunks);
-    s.pre = s.rtab + ((size_t)1 << g.rt_log2);
-    s.hist = s.pre + MC_R + 1;
-    s.map = (unsigned char *)(s.hist + g.hrows + 1);
+    s.rtab = (u32 *)(s.dmask + g.dcap);
+    s.hist = s.rtab + ((size_t)1 << g.rt_log2);
+    s.tcnt = (unsigned short *)(s.hist + (((size_t)g.hrows + 2) & ~(size_t)1));   // [S] when there are several chunks of genomes
+    s.slots = s.tcnt + (g.nchunks > 1 ? S : 0);                                   // [S]
+    s.dwoff = s.slots + S;                                                         // [dcap]
+    s.map = s.dwoff + g.dcap;                                                      // [MC_WCAP]
     return s;
 }
 
@@ -380,15 +384,18 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
     extern __shared__ __align__(16) unsigned char mc_raw[];
     __shared__ __align__(8) u64 bars[2];
     __shared__ mc_desc desc[2];
-    __shared__ u32 s_over, s_distinct, s_dcount, s_dfull, ws[33];
+    __shared__ u32 s_over, s_distinct, s_dcount, s_wtotal, s_dfull;
+    __shared__ u32 s_cn[MULTI ? 128 : 1];   // thread 0: records per chunk of the bin it is feeding
     __shared__ u64 s_base;
     const u32 s_log2 = geo.s_log2, S = 1u << s_log2, nchunks = geo.nchunks, hrows = geo.hrows, dcap = geo.dcap, RT = 1u << geo.rt_log2;
     const mc_smem sm = mc_carve(mc_raw, KW, geo);
-    const u32 NCH = MULTI ? nchunks : 1u;
     const u32 tid = threadIdx.x;
     if (d_stat[0] & 1ull) return;   // a bin region overflowed: its slots hold stale bytes, and the caller redoes the group anyway
     for (u32 i = tid; i < S; i += BLOCK) sm.tkey[i] = MB_EMPTY;
-    for (u32 i = tid; i < S * NCH; i += BLOCK) sm.tbits[i] = 0ull;
+    for (u32 i = tid; i < S; i += BLOCK) {
+        sm.tbits[i] = 0ull;
+        if (MULTI) sm.tcnt[i] = 0u;
+    }
     for (u32 i = tid; i < RT; i += BLOCK) sm.rtab[i] = 0u;
     for (u32 i = tid; i <= hrows; i += BLOCK) sm.hist[i] = 0u;
     if (tid == 0) {
@@ -397,30 +404,61 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
         s_over = 0;
         s_distinct = 0;
         s_dcount = 0;
+        s_wtotal = 0;
         s_dfull = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // The stream of stages.  Region u = bin * nchunks + chunk holds the records of the bin that come from chunk `chunk` of 64 genomes; a bin
+    // is streamed class by class (hash classes of its k-mers, when the table cannot hold them all) and, inside a class, chunk by chunk.
     mc_iter it;
     it.bin = blockIdx.x;
     it.off = 0;
     it.cls = 0;
     it.ncls = 1;
     it.chunk = 0;
-    it.n = 0;
-    it.n_next = 0;
+    it.n = 0;        // records of the current region
+    it.n_next = 0;   // one chunk: records of this CTA's next bin, loaded one bin ahead
+    u32 it_last = 0; // several chunks: the last non-empty chunk of the current bin
     u64 my_records = 0;
-    auto bin_records = [&](u32 b) -> u32 {
-        if (b >= nbins) return 0u;
-        const u32 c = __ldg(cursor + b);
+    auto region_records = [&](u32 u, u32 lim) -> u32 {
+        if (u >= lim) return 0u;
+        const u32 c = __ldg(cursor + u);
         return c < cap ? c : cap;
     };
-    auto produce = [&](u32 buf) {   // thread 0 only: the next stage of this CTA's stream goes into ring buffer `buf`
-        while (it.bin < nbins && it.n == 0) {
-            it.bin += gridDim.x;
-            it.n = it.n_next;
-            it.n_next = bin_records(it.bin + gridDim.x);
+    auto open_bin = [&]() {   // counts of the bin it.bin (several chunks: into s_cn); false when the bin is empty
+        if (!MULTI) return it.n != 0;
+        u32 total = 0;
+        for (u32 c = 0; c < nchunks; c++) {
+            const u32 n = region_records(it.bin * nchunks + c, nbins * nchunks);
+            s_cn[c] = n;
+            total += n;
+            if (n) it_last = c;
         }
+        if (!total) return false;
+        it.chunk = 0;
+        while (s_cn[it.chunk] == 0) it.chunk++;
+        it.n = s_cn[it.chunk];
+        it.ncls = total <= thr1 ? 1u : (total + thr1 - 1) / thr1;
+        my_records += total;
+        return true;
+    };
+    auto next_bin = [&]() {
+        for (;;) {
+            it.bin += gridDim.x;
+            if (!MULTI) {
+                it.n = it.n_next;
+                it.n_next = region_records(it.bin + gridDim.x, nbins);
+            }
+            if (it.bin >= nbins) return;
+            if (open_bin()) break;
+        }
+        if (!MULTI) {
+            it.ncls = it.n <= thr1 ? 1u : (it.n + thr1 - 1) / thr1;
+            my_records += it.n;
+        }
+    };
+    auto produce = [&](u32 buf) {   // thread 0 only: the next stage of this CTA's stream goes into ring buffer `buf`
         if (it.bin >= nbins) {
             desc[buf].flags = MCF_DONE;
             mbar_arrive(&bars[buf]);
@@ -428,33 +466,46 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
         }
         const u32 count = it.n - it.off < MC_R ? it.n - it.off : MC_R;
         const bool last = it.off + count == it.n;
-        if (it.off == 0 && it.cls == 0) {
-            my_records += it.n;
-            it.ncls = it.n <= thr1 ? 1u : (it.n + thr1 - 1) / thr1;
-        }
+        const bool last_chunk = !MULTI || it.chunk == it_last;
         desc[buf].bin = it.bin;
         desc[buf].count = count;
-        desc[buf].chunk = 0;
+        desc[buf].chunk = it.chunk;
         desc[buf].cls = it.cls;
         desc[buf].ncls = it.ncls;
-        desc[buf].flags = last ? (MCF_LAST | MCF_SCAN) : 0u;
+        desc[buf].flags = (last ? MCF_LAST : 0u) | (last && last_chunk ? MCF_SCAN : 0u);
         const u32 bytes = (count * (u32)((KW + 1) * 8) + 15u) & ~15u;   // an odd count of 24-byte records: 8 bytes of the next record ride along
         mbar_arrive_expect_tx(&bars[buf], bytes);
-        bulk_g2s(sm.ring + (size_t)buf * MC_R * (KW + 1), rec + ((u64)it.bin * cap + it.off) * (KW + 1), bytes, &bars[buf]);
+        const u64 region = MULTI ? (u64)it.bin * nchunks + it.chunk : (u64)it.bin;
+        bulk_g2s(sm.ring + (size_t)buf * MC_R * (KW + 1), rec + (region * cap + it.off) * (KW + 1), bytes, &bars[buf]);
         it.off += count;
         if (last) {
             it.off = 0;
-            if (++it.cls == it.ncls) {
+            if (!last_chunk) {
+                do it.chunk++; while (s_cn[it.chunk] == 0);
+                it.n = s_cn[it.chunk];
+            } else if (++it.cls == it.ncls) {
                 it.cls = 0;
-                it.bin += gridDim.x;
-                it.n = it.n_next;
-                it.n_next = bin_records(it.bin + gridDim.x);
+                next_bin();
+            } else if (MULTI) {
+                it.chunk = 0;
+                while (s_cn[it.chunk] == 0) it.chunk++;
+                it.n = s_cn[it.chunk];
             }
         }
     };
     if (tid == 0) {
-        it.n = bin_records(it.bin);
-        it.n_next = bin_records(it.bin + gridDim.x);
+        if (!MULTI) {
+            it.n = region_records(it.bin, nbins);
+            it.n_next = region_records(it.bin + gridDim.x, nbins);
+            if (it.bin < nbins && it.n) {
+                it.ncls = it.n <= thr1 ? 1u : (it.n + thr1 - 1) / thr1;
+                my_records += it.n;
+            } else if (it.bin < nbins) {
+                next_bin();
+            }
+        } else if (it.bin < nbins && !open_bin()) {
+            next_bin();
+        }
         produce(0);
         produce(1);
     }
@@ -462,45 +513,39 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
     u32 n_one = 0, n_all = 0;
     u64 pairs = 0;
 
-    // Expand the distinct records collected so far into the k-mer table (every k-mer takes its record's genome masks), then forget them.
+    // Expand the distinct records collected so far into the k-mer table (every k-mer takes its record's genome mask), then forget them.
+    // The windows of the distinct records were laid out densely while the records were collected (map[t] = record of window t,
+    // dwoff[record] = its first t), so the threads simply share them: no prefix sum, no barrier before the loop.
+    u32 my_flushes = 0;
+    u64 my_drecords = 0;
     auto flush_records = [&](u32 cls, u32 ncls) {
-        const u32 nd = s_dcount < dcap ? s_dcount : dcap;
-        for (u32 r0 = 0; r0 < nd; r0 += MC_R) {
-            const u32 id = r0 + tid;
-            const u32 len = (tid < MC_R && id < nd) ? (u32)sm.dstore[(size_t)id * (KW + 1)] : 0u;   // 0: a dead entry
-            u32 total;
-            const u32 off = block_excl_sum<u32>(len, ws, &total);
-            if (tid < MC_R) sm.pre[tid] = off;
-            for (u32 e = 0; e < len; e++) sm.map[off + e] = (unsigned char)tid;
-            __syncthreads();
-            bool ok = true;
-            for (u32 t = tid; t < total; t += BLOCK) {
-                const u32 r = sm.map[t];
-                const u32 e = t - sm.pre[r];
-                const u64 *R = sm.dstore + (size_t)(r0 + r) * (KW + 1);
-                const u32 q = e >> 5, o = e & 31u;
-                const u64 w0 = R[1 + q], w1 = q + 2 <= (u32)KW ? R[2 + q] : 0ull;
-                const u64 x = o ? ((w0 << (2 * o)) | (w1 >> (64 - 2 * o))) : w0;
-                const u64 key = mb_canonical64(x, k);
-                if (ncls > 1 && __umulhi(mb_class_hash(key), ncls) != cls) continue;
-                const int slot = mb_find_slot(sm.tkey, s_log2, key, &s_distinct);
-                if (slot < 0) {
-                    ok = false;
-                    continue;
-                }
-                const u64 *M = sm.dmask + (size_t)(r0 + r) * NCH;
-                u64 *B = sm.tbits + (size_t)slot * NCH;
-                for (u32 c = 0; c < NCH; c++) {
-                    const u64 mk = M[c];
-                    if (mk) mb_or_mask(B + c, mk);
-                }
+        const u32 nw = s_wtotal < MC_WCAP ? s_wtotal : MC_WCAP;
+        my_flushes++;
+        my_drecords += s_dcount < dcap ? s_dcount : dcap;
+        bool ok = true;
+        for (u32 t = tid; t < nw; t += BLOCK) {
+            const u32 id = sm.map[t];
+            if (id == 0xffffu) continue;                                       // reserved by a record that found no room
+            const u64 *R = sm.dstore + (size_t)id * (KW + 1);
+            const u32 e = t - sm.dwoff[id];
+            const u32 q = e >> 5, o = e & 31u;
+            const u64 w0 = R[1 + q], w1 = q + 2 <= (u32)KW ? R[2 + q] : 0ull;
+            const u64 x = o ? ((w0 << (2 * o)) | (w1 >> (64 - 2 * o))) : w0;
+            const u64 key = mb_canonical64(x, k);
+            if (ncls > 1 && __umulhi(mb_class_hash(key), ncls) != cls) continue;
+            const int slot = mb_find_slot(sm.tkey, sm.slots, s_log2, key, &s_distinct);
+            if (slot < 0) {
+                ok = false;
+                continue;
             }
-            if (!ok) s_over = 1;
-            __syncthreads();
+            mb_or_mask(sm.tbits + slot, sm.dmask[id]);
         }
+        if (!ok) s_over = 1;
+        __syncthreads();
         for (u32 i = tid; i < RT; i += BLOCK) sm.rtab[i] = 0u;
         if (tid == 0) {
             s_dcount = 0;
+            s_wtotal = 0;
             s_dfull = 0;
         }
         __syncthreads();
@@ -526,54 +571,60 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
                 for (int i = 0; i < KW; i++) w[i] = R[1 + i];
                 h = mb_record_hash(w, KW, len);
             }
+            // Rounds: a record finds its content in the index (-> one bit), or claims an empty index slot and becomes a new distinct
+            // record, or meets a slot whose owner is still writing and looks again in the next round (copies of one record from many
+            // genomes sit in the same stage: only ONE of them may allocate).
             for (;;) {
                 if (todo) {
                     u32 slot = (u32)h & (RT - 1);
-                    u32 my_id = ~0u, id = ~0u;
                     for (;;) {
                         u32 v = *(volatile u32 *)&sm.rtab[slot];
                         if (v == 0u) {
-                            if (my_id == ~0u) {
-                                my_id = atomicAdd(&s_dcount, 1u);
-                                if (my_id >= dcap) {      // no room: expand what is there, then this record again
+                            v = atomicCAS(&sm.rtab[slot], 0u, MC_PENDING);
+                            if (v == 0u) {   // this thread owns the slot
+                                const u32 woff = atomicAdd(&s_wtotal, len);
+                                const u32 wend = woff + len < MC_WCAP ? woff + len : MC_WCAP;
+                                u32 id = ~0u;
+                                if (woff + len <= MC_WCAP) id = atomicAdd(&s_dcount, 1u);
+                                if (id >= dcap) {         // no room (records or windows): expand what is there, then this record again
+                                    for (u32 t = woff; t < wend; t++) sm.map[t] = 0xffffu;
                                     s_dfull = 1;
+                                    *(volatile u32 *)&sm.rtab[slot] = 0u;
                                     break;
                                 }
-                                u64 *D = sm.dstore + (size_t)my_id * (KW + 1);
+                                for (u32 t = woff; t < wend; t++) sm.map[t] = (unsigned short)id;
+                                sm.dwoff[id] = (unsigned short)woff;
+                                u64 *D = sm.dstore + (size_t)id * (KW + 1);
                                 D[0] = (u64)len;
 #pragma unroll
                                 for (int i = 0; i < KW; i++) D[1 + i] = w[i];
-                                for (u32 c = 0; c < NCH; c++) sm.dmask[(size_t)my_id * NCH + c] = 0ull;
+                                sm.dmask[id] = 1ull << (g & 63u);
                                 __threadfence_block();
-                            }
-                            v = atomicCAS(&sm.rtab[slot], 0u, my_id + 1u);
-                            if (v == 0u) {
-                                id = my_id;
+                                *(volatile u32 *)&sm.rtab[slot] = id + 1u;
+                                todo = false;
                                 break;
                             }
                         }
+                        if (v == MC_PENDING) break;      // its owner publishes before the next round
                         const u64 *D = sm.dstore + (size_t)(v - 1u) * (KW + 1);
                         bool same = (u32)*(volatile u64 *)&D[0] == len;
 #pragma unroll
                         for (int i = 0; i < KW; i++) same = same && *(volatile u64 *)&D[1 + i] == w[i];
                         if (same) {
-                            id = v - 1u;
+                            u32 *mw = (u32 *)&sm.dmask[v - 1u] + ((g >> 5) & 1u);
+                            const u32 bm = 1u << (g & 31u);
+                            if (!(*(volatile u32 *)mw & bm)) atomicOr(mw, bm);
+                            todo = false;
                             break;
                         }
                         slot = (slot + 1) & (RT - 1);
                     }
-                    if (id != ~0u) {
-                        if (my_id != ~0u && my_id != id) sm.dstore[(size_t)my_id * (KW + 1)] = 0ull;   // lost the race for the slot: a dead entry
-                        u32 *mw = (u32 *)&sm.dmask[(size_t)id * NCH + (MULTI ? (g >> 6) : 0u)] + ((g >> 5) & 1u);
-                        const u32 bm = 1u << (g & 31u);
-                        if (!(*(volatile u32 *)mw & bm)) atomicOr(mw, bm);
-                        todo = false;
-                    }
                 }
-                __syncthreads();
-                if (!s_dfull) break;
-                __syncthreads();
-                flush_records(d.cls, d.ncls);
+                if (!__syncthreads_or(todo)) break;
+                if (s_dfull) {
+                    __syncthreads();
+                    flush_records(d.cls, d.ncls);
+                }
             }
         }
         __syncthreads();
@@ -582,10 +633,28 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
         // the last stage of this class of the bin: expand, then every occupied slot is one distinct k-mer of the group
         if (!s_over) flush_records(d.cls, d.ncls);
         if (s_distinct > S - S / 4) s_over = 1;     // same value in every thread (s_distinct is stable between the barriers)
+        if (!(d.flags & MCF_SCAN)) {                // end of a chunk of 64 genomes, more to come: fold the bits into the counts
+            if (!s_over) {
+                const u32 nk = s_distinct;
+                for (u32 j = tid; j < nk; j += BLOCK) {
+                    const u32 i = sm.slots[j];
+                    const u64 b = sm.tbits[i];
+                    if (b) {
+                        sm.tcnt[i] += (unsigned short)__popcll(b);
+                        sm.tbits[i] = 0ull;
+                    }
+                }
+            }
+            __syncthreads();
+            continue;
+        }
         if (s_over) {
             __syncthreads();
-            for (u32 i = tid; i < S; i += BLOCK) sm.tkey[i] = MB_EMPTY;
-            for (u32 i = tid; i < S * NCH; i += BLOCK) sm.tbits[i] = 0ull;
+            for (u32 i = tid; i < S; i += BLOCK) {
+                sm.tkey[i] = MB_EMPTY;
+                sm.tbits[i] = 0ull;
+                if (MULTI) sm.tcnt[i] = 0u;
+            }
             for (u32 i = tid; i < RT; i += BLOCK) sm.rtab[i] = 0u;
             if (tid == 0) {
                 const u32 at = atomicAdd(over_count, 1u);
@@ -599,32 +668,31 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
                 s_over = 0;
                 s_distinct = 0;
                 s_dcount = 0;
+                s_wtotal = 0;
                 s_dfull = 0;
             }
             __syncthreads();
             continue;
         }
-        if (tid == 0 && s_distinct) s_base = atomicAdd((unsigned long long *)d_cursor, (unsigned long long)s_distinct);
-        u32 mine = 0;
-        for (u32 i = tid; i < S; i += BLOCK) mine += sm.tkey[i] != MB_EMPTY;
-        u32 total;
-        u32 at = block_excl_sum<u32>(mine, ws, &total);
+        const u32 nd_keys = s_distinct;
+        if (tid == 0 && nd_keys) s_base = atomicAdd((unsigned long long *)d_cursor, (unsigned long long)nd_keys);
+        __syncthreads();
         const u64 base = s_base;
-        for (u32 i = tid; i < S; i += BLOCK) {
+        for (u32 j = tid; j < nd_keys; j += BLOCK) {
+            const u32 i = sm.slots[j];
             const u64 key = sm.tkey[i];
-            if (key == MB_EMPTY) continue;
-            u32 c = 0;
-            for (u32 j = 0; j < NCH; j++) {
-                c += (u32)__popcll(sm.tbits[(size_t)i * NCH + j]);
-                sm.tbits[(size_t)i * NCH + j] = 0ull;
+            u32 c = (u32)__popcll(sm.tbits[i]);
+            sm.tbits[i] = 0ull;
+            if (MULTI) {
+                c += sm.tcnt[i];
+                sm.tcnt[i] = 0u;
             }
             pairs += c;
             const u32 cc = c > cs ? cs : c;
             if (cc == 1u) n_one++;
             else if (cc == c_all) n_all++;
             else if (cc <= hrows) atomicAdd(&sm.hist[cc], 1u);
-            if (out_keys) out_keys[base + at] = kmer_mix64(key, k);
-            at++;
+            if (out_keys) out_keys[base + j] = kmer_mix64(key, k);
             sm.tkey[i] = MB_EMPTY;
         }
         __syncthreads();
@@ -643,7 +711,11 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
         if (n_all && c_all <= hrows) atomicAdd(&sm.hist[c_all], n_all);
         if (pairs) atomicAdd((unsigned long long *)d_pairs, (unsigned long long)pairs);
     }
-    if (tid == 0 && my_records) atomicAdd((unsigned long long *)&d_stat[1], (unsigned long long)my_records);
+    if (tid == 0 && my_records) {
+        atomicAdd((unsigned long long *)&d_stat[1], (unsigned long long)my_records);
+        atomicAdd((unsigned long long *)&d_stat[3], (unsigned long long)my_flushes);
+        atomicAdd((unsigned long long *)&d_stat[4], (unsigned long long)my_drecords);
+    }
     __syncthreads();
     for (u32 i = tid; i <= hrows; i += BLOCK) {
         const u32 v = sm.hist[i];
@@ -663,14 +735,16 @@ mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u3
     __shared__ u64 s_base;
     const u32 s_log2 = geo.s_log2, S = 1u << s_log2, nchunks = geo.nchunks, hrows = geo.hrows;
     const mc_smem sm = mc_carve(mc_raw, KW, geo);
-    const u32 NCH = MULTI ? nchunks : 1u;
     const u32 tid = threadIdx.x;
     const u32 n_over = *over_count < over_cap ? *over_count : over_cap;
     if (flags[0] & 1ull) return;
     if (blockIdx.x == 0 && tid == 0) flags[2] = n_over;
     if (blockIdx.x >= n_over) return;
     for (u32 i = tid; i < S; i += MC_BLOCK) sm.tkey[i] = MB_EMPTY;
-    for (u32 i = tid; i < S * NCH; i += MC_BLOCK) sm.tbits[i] = 0ull;
+    for (u32 i = tid; i < S; i += MC_BLOCK) {
+        sm.tbits[i] = 0ull;
+        if (MULTI) sm.tcnt[i] = 0u;
+    }
     for (u32 i = tid; i <= hrows; i += MC_BLOCK) sm.hist[i] = 0u;
     if (tid == 0) {
         s_over = 0;
@@ -680,8 +754,7 @@ mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u3
     u64 pairs = 0;
     for (u32 li = blockIdx.x; li < n_over; li += gridDim.x) {
         const u32 bin = over_list[3 * li], cls0 = over_list[3 * li + 1], ncls0 = over_list[3 * li + 2];
-        const u32 n = cursor[bin] < cap ? cursor[bin] : cap;
-        const u64 *rb = rec + (u64)bin * cap * (KW + 1);
+        const u32 nch = MULTI ? nchunks : 1u;
         // work list of hash classes (modulus M, residue r): keys with h % M == r.  A class whose distinct keys do not fit the table is
         // split into (2M, r) and (2M, r + M), which together are exactly that class -- nothing of it was emitted yet.
         u32 stM[40], stR[40];
@@ -690,13 +763,18 @@ mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u3
         stM[sp] = 2; stR[sp++] = 0;
         while (sp > 0) {
             const u32 M = stM[--sp], r0 = stR[sp];
-            {
+            for (u32 chunk = 0; chunk < nch; chunk++) {
+                const u32 region = bin * nch + chunk;
+                const u32 n = cursor[region] < cap ? cursor[region] : cap;
+                const u64 *rb = rec + (u64)region * cap * (KW + 1);
                 const u32 sub = tid & 15u, grp = tid >> 4;   // 16 lanes share a record
                 bool ok = true;
                 for (u32 r = grp; r < n; r += MC_BLOCK / 16) {
                     const u64 *R = rb + (size_t)r * (KW + 1);
                     const u64 h = R[0];
-                    const u32 g = (u32)(h >> 48), len = (u32)(h >> 40) & 0xffu;
+                    const u32 g = (u32)(h >> 48);
+                    u32 len = (u32)(h >> 40) & 0xffu;
+                    len = len < MB_MAXW ? len : MB_MAXW;
                     for (u32 e = sub; e < len; e += 16) {
                         const u32 q = e >> 5, o = e & 31u;
                         const u64 w0 = R[1 + q], w1 = q + 2 <= (u32)KW ? R[2 + q] : 0ull;
@@ -704,18 +782,34 @@ mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u3
                         const u64 key = mb_canonical64(x, k);
                         if (ncls0 > 1 && __umulhi(mb_class_hash(key), ncls0) != cls0) continue;
                         if ((u32)((key * 0x9E3779B97F4A7C15ull) >> 20) % M != r0) continue;
-                        ok = mb_insert(sm.tkey, sm.tbits, s_log2, NCH, key, MULTI ? g : (g & 63u), &s_distinct) && ok;
+                        ok = mb_insert(sm.tkey, sm.tbits, sm.slots, s_log2, key, g & 63u, &s_distinct) && ok;
                     }
                 }
                 if (!ok) s_over = 1;
                 __syncthreads();
                 if (s_distinct > S - S / 4) s_over = 1;
+                if (s_over) break;
+                if (MULTI && chunk + 1 < nchunks) {
+                    const u32 nk = s_distinct;
+                    for (u32 j = tid; j < nk; j += MC_BLOCK) {
+                        const u32 i = sm.slots[j];
+                        const u64 b = sm.tbits[i];
+                        if (b) {
+                            sm.tcnt[i] += (unsigned short)__popcll(b);
+                            sm.tbits[i] = 0ull;
+                        }
+                    }
+                    __syncthreads();
+                }
             }
             const bool over = s_over != 0;
             __syncthreads();
             if (over) {
-                for (u32 i = tid; i < S; i += MC_BLOCK) sm.tkey[i] = MB_EMPTY;
-                for (u32 i = tid; i < S * NCH; i += MC_BLOCK) sm.tbits[i] = 0ull;
+                for (u32 i = tid; i < S; i += MC_BLOCK) {
+                    sm.tkey[i] = MB_EMPTY;
+                    sm.tbits[i] = 0ull;
+                    if (MULTI) sm.tcnt[i] = 0u;
+                }
                 if (tid == 0) {
                     s_over = 0;
                     s_distinct = 0;
@@ -730,25 +824,23 @@ mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u3
                 stM[sp] = 2 * M; stR[sp++] = r0;
                 continue;
             }
-            if (tid == 0 && s_distinct) s_base = atomicAdd((unsigned long long *)d_cursor, (unsigned long long)s_distinct);
-            u32 mine = 0;
-            for (u32 i = tid; i < S; i += MC_BLOCK) mine += sm.tkey[i] != MB_EMPTY;
-            u32 total;
-            u32 at = block_excl_sum<u32>(mine, ws, &total);
+            const u32 nd_keys = s_distinct;
+            if (tid == 0 && nd_keys) s_base = atomicAdd((unsigned long long *)d_cursor, (unsigned long long)nd_keys);
+            __syncthreads();
             const u64 base = s_base;
-            for (u32 i = tid; i < S; i += MC_BLOCK) {
+            for (u32 j = tid; j < nd_keys; j += MC_BLOCK) {
+                const u32 i = sm.slots[j];
                 const u64 key = sm.tkey[i];
-                if (key == MB_EMPTY) continue;
-                u32 c = 0;
-                for (u32 j = 0; j < NCH; j++) {
-                    c += (u32)__popcll(sm.tbits[(size_t)i * NCH + j]);
-                    sm.tbits[(size_t)i * NCH + j] = 0ull;
+                u32 c = (u32)__popcll(sm.tbits[i]);
+                sm.tbits[i] = 0ull;
+                if (MULTI) {
+                    c += sm.tcnt[i];
+                    sm.tcnt[i] = 0u;
                 }
                 pairs += c;
                 const u32 cc = c > cs ? cs : c;
                 if (cc <= hrows) atomicAdd(&sm.hist[cc], 1u);
-                if (out_keys) out_keys[base + at] = kmer_mix64(key, k);
-                at++;
+                if (out_keys) out_keys[base + j] = kmer_mix64(key, k);
                 sm.tkey[i] = MB_EMPTY;
             }
             __syncthreads();
@@ -778,7 +870,7 @@ static long long mb_env(const char *name, long long dflt)
 // Does the minimizer-bin path apply?  (64-bit keys with a spare value, enough m-mers per window for super-k-mers to pay.)
 int khb_bins_eligible(int k, int n_genomes, u64 n_sym)
 {
-    return k >= 17 && k <= 31 && n_genomes >= 1 && n_genomes <= 512 && n_sym >= 1 && n_sym < (1ull << 40);
+    return k >= 17 && k <= 31 && n_genomes >= 1 && n_genomes <= 8191 && n_sym >= 1 && n_sym < (1ull << 40);
 }
 
 // The group stage through minimizer bins.  d_stat: u64[4] in device memory, written here: [0] flags (1: a bin region overflowed,
@@ -802,7 +894,7 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
     if (nb64 > (1ull << 28)) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: group too large");
     const u32 nb = (u32)nb64;
     // distinct k-mers per window: measured on the previous group (+ 25 %), else a guess from the group size
-    double rho_w = ctx->bins_rho > 0.0 ? ctx->bins_rho * 1.25 : (n_genomes >= 16 ? 0.25 : n_genomes >= 4 ? 0.5 : 1.0);
+    double rho_w = ctx->bins_rho > 0.0 ? ctx->bins_rho * 1.25 : (n_genomes >= 32 ? 0.2 : n_genomes >= 16 ? 0.25 : n_genomes >= 4 ? 0.5 : 1.0);
     const long long rho_pct = mb_env("KHB_BINS_RHO_PCT", 0);   // test hook: distinct k-mers per 100 windows
     if (rho_pct > 0) rho_w = rho_pct / 100.0;
     if (rho_w > 1.0) rho_w = 1.0;
@@ -813,12 +905,11 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
         const double want = (double)(n_sym / nb + 1) * rho_w / 0.45;
         u32 l2 = 10;
         while (l2 < 12 && (double)(1u << l2) < want) l2++;
-        while (l2 > 10 && ((size_t)8 << l2) * (1 + geo.nchunks) > (size_t)170 * 1024) l2--;
         geo.s_log2 = (u32)mb_env("KHB_BINS_SLOTS_LOG2", l2);
         if (geo.s_log2 < 8 || geo.s_log2 > 13) return khb_fail(ctx, KHB_ERR_ARG, "KHB_BINS_SLOTS_LOG2 outside 8..13");
     }
     geo.hrows = nbins_hist < (u32)n_genomes ? nbins_hist : (u32)n_genomes;
-    geo.dcap = (u32)mb_env("KHB_BINS_DCAP", geo.nchunks <= 4 ? 256 : 128);
+    geo.dcap = (u32)mb_env("KHB_BINS_DCAP", geo.nchunks > 1 ? 256 : 384);
     if (geo.dcap < 64 || geo.dcap > 4096) return khb_fail(ctx, KHB_ERR_ARG, "KHB_BINS_DCAP outside 64..4096");
     geo.rt_log2 = 7;
     while ((1u << geo.rt_log2) < 2 * geo.dcap) geo.rt_log2++;
@@ -826,9 +917,11 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
     double avg_len = (w + 1) * 0.5;
     if (avg_len > capw) avg_len = capw;
     const double est_records = (double)n_sym / avg_len * 1.15 + (double)div_up(n_sym, MB_TILE);
-    const double slack = (double)mb_env("KHB_BINS_SLACK_PCT", 400) / 100.0;
-    const u32 cap = ((u32)(est_records / nb * slack) + 64u) & ~1u;   // even: every bin's region starts 16-byte aligned
-    const size_t rec_bytes = (size_t)nb * cap * (KW + 1) * 8;
+    // one region per bin and chunk of 64 genomes; the fewer lumps a region holds on average, the more room above the mean it gets
+    const u64 n_regions = (u64)nb * geo.nchunks;
+    const double slack = (double)mb_env("KHB_BINS_SLACK_PCT", geo.nchunks > 1 ? 600 : 400) / 100.0;
+    const u32 cap = ((u32)(est_records / (double)n_regions * slack) + 64u) & ~1u;   // even: every region starts 16-byte aligned
+    const size_t rec_bytes = (size_t)n_regions * cap * (KW + 1) * 8;
     // Records one pass over a bin may hold so that its distinct k-mers fill at most ~55 % of the table; larger bins are counted in
     // several hash classes.
     double thr = 0.55 * (double)(1u << s_log2) / (rho_w * avg_len);
@@ -837,27 +930,27 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
     const bool multi = geo.nchunks > 1;
     int rc;
     void *p;
-    if ((rc = khb_scratch_get(ctx, SCR_AUX, (size_t)nb * 52 + 256, &p))) return rc;
+    if ((rc = khb_scratch_get(ctx, SCR_AUX, (size_t)n_regions * 4 + (size_t)nb * 48 + 256, &p))) return rc;
     u32 *d_over_count = (u32 *)p;                 // [0] bins in the list
-    u32 *d_cur = d_over_count + 16, *d_over_list = d_cur + nb;
+    u32 *d_cur = d_over_count + 16, *d_over_list = d_cur + n_regions;
     void *pr;
     if ((rc = khb_scratch_get(ctx, SCR_KEYS_A, rec_bytes + 64, &pr))) return rc;
-    KHB_CUDA(ctx, cudaMemsetAsync(d_over_count, 0, 64 + (size_t)nb * 4, ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(d_over_count, 0, 64 + (size_t)n_regions * 4, ctx->stream));
     KHB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, ((size_t)nbins_hist + 1) * sizeof(u64), ctx->stream));
     KHB_CUDA(ctx, cudaMemsetAsync(d_runs, 0, sizeof(u64), ctx->stream));
     KHB_CUDA(ctx, cudaMemsetAsync(d_pairs, 0, sizeof(u64), ctx->stream));
-    KHB_CUDA(ctx, cudaMemsetAsync(d_stat, 0, 4 * sizeof(u64), ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(d_stat, 0, 5 * sizeof(u64), ctx->stream));
     const u64 last_w = n_sym / 32 + 3;            // khb_codes_words / khb_valid_words: n / 32 + 4 words each
     {
         const u64 tiles = div_up(n_sym, MB_TILE);
         khb_prof_begin(ctx, KHB_K_BIN_PARTITION);
-        mb_partition_kernel<KW><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, m, nb, d_seg_off, n_genomes, d_cur,
+        mb_partition_kernel<KW><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, m, nb, d_seg_off, n_genomes, geo.nchunks, d_cur,
                                                                                (u64 *)pr, cap, capw, d_stat);
         khb_prof_end(ctx, KHB_K_BIN_PARTITION, n_sym * 3 / 8);
         KHB_LAUNCH_CHECK(ctx);
     }
     {
-        const size_t shm = mc_smem_bytes(KW, geo);
+        size_t shm = mc_smem_bytes(KW, geo, 256);
         if (shm > 227 * 1024) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: %zu bytes of shared memory per CTA", shm);
         // two CTAs of 256 threads per SM at least; where the tables leave room for one CTA only, that one has 512 threads
         const bool wide = 2 * (shm + 1024) > 227 * 1024;
@@ -865,6 +958,7 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
                                : (wide ? (const void *)mb_count_kernel<KW, false, 512> : (const void *)mb_count_kernel<KW, false, 256>);
         const void *bfn = multi ? (const void *)mb_bigbin_kernel<KW, true> : (const void *)mb_bigbin_kernel<KW, false>;
         const int block = wide ? 512 : 256;
+        shm = mc_smem_bytes(KW, geo, block);
         int per_sm = 0;
         KHB_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
         KHB_CUDA(ctx, cudaFuncSetAttribute(bfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
@@ -881,6 +975,9 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
         u64 *keys_ = (u64 *)d_out_keys;
         const u32 *c_list = d_over_list, *c_cnt = d_over_count;
         void *cargs[] = {&c_rec, &c_cur, &nb_, &cap_, &k_, &geo, &n_gen, &cs_, &thr_, &ocap_, &d_hist, &keys_, &d_runs, &d_pairs, &d_over_list, &d_over_count, &d_stat};
+        if (mb_env("KHB_BINS_VERBOSE", 0))
+            fprintf(stderr, "[bins] k=%d genomes=%d windows=%llu bins=%u chunks=%u cap=%u slots=2^%u dcap=%u thr1=%u rho_w=%.3f shm=%zu ctas/sm=%d block=%d\n", k, n_genomes,
+                    (unsigned long long)n_sym, nb, geo.nchunks, cap, geo.s_log2, geo.dcap, thr1, rho_w, shm, per_sm, block);
         khb_prof_begin(ctx, KHB_K_BIN_COUNT);
         KHB_CUDA(ctx, cudaLaunchKernel(fn, dim3(grid), dim3(block), cargs, shm, ctx->stream));
         khb_prof_end(ctx, KHB_K_BIN_COUNT, 0);

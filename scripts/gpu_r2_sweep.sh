@@ -18,17 +18,9 @@ except Exception as e:
 PY
 }
 run default X=1
-run s11 KHB_BINS_SLOTS_LOG2=11
-run s12 KHB_BINS_SLOTS_LOG2=12
-run s11_w2000 KHB_BINS_SLOTS_LOG2=11 KHB_BINS_WPB=2000
-run s11_w3000 KHB_BINS_SLOTS_LOG2=11 KHB_BINS_WPB=3000
-run s12_w8000 KHB_BINS_SLOTS_LOG2=12 KHB_BINS_WPB=8000
-run s10_w2000 KHB_BINS_SLOTS_LOG2=10 KHB_BINS_WPB=2000
-run d128 KHB_BINS_DCAP=128
-run d512 KHB_BINS_DCAP=512
+run d256 KHB_BINS_DCAP=256
+run w3000 KHB_BINS_WPB=3000
 export KHB_BENCH_CONFIG=5 KHB_BENCH_GROUPS_TOTAL=2
 unset KHB_BENCH_GROUPS
 run c5_default X=1
-run c5_s11 KHB_BINS_SLOTS_LOG2=11
-run c5_w16000 KHB_BINS_WPB=16000
-run c5_w4000_s11 KHB_BINS_WPB=4000 KHB_BINS_SLOTS_LOG2=11
+run c5_w6000 KHB_BINS_WPB=6000

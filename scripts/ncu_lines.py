@@ -39,4 +39,11 @@ for (f, n), (i, s) in sorted(agg.items(), key=lambda t: -t[1][0])[:topn]:
     p = os.path.join(os.path.dirname(os.path.abspath(obj)), f)
     if p not in srcs and os.path.exists(p): srcs[p] = open(p).read().splitlines()
     text = srcs.get(p, [""] * (n + 1))[n - 1].strip()[:90] if n and p in srcs and n <= len(srcs[p]) else ""
-    print(f"{f}:{n:4d} inst {100*i/ti:5.1f}%  samples {100*s/ts:5.1f}%  {text}")
+    print(f"{f}:{n:4d} inst {100*i/ti:5.1f}% ({i/1e6:8.2f} M)  samples {100*s/ts:5.1f}%  {text}")
+# NCU_REGIONS="a-b,c-d": totals over source line ranges of the kernel's main file
+if os.environ.get("NCU_REGIONS"):
+    main = os.environ.get("NCU_FILE", "bins.cu")
+    for rg in os.environ["NCU_REGIONS"].split(","):
+        a, b = map(int, rg.split("-"))
+        i = sum(v[0] for (f, n), v in agg.items() if f == main and a <= n <= b); sm_ = sum(v[1] for (f, n), v in agg.items() if f == main and a <= n <= b)
+        print(f"region {main}:{a}-{b}: inst {100*i/ti:5.1f}% ({i/1e6:8.2f} M)  samples {100*sm_/ts:5.1f}%")
