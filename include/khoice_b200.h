@@ -214,9 +214,10 @@ KHB_API int khb_group_from_packed(khb_ctx *ctx, int k, const khb_packed *pk, uin
 KHB_API int khb_set_group_mode(khb_ctx *ctx, int mode);
 /* Groups the hash path handed back to the sort path because a probe sequence hit its limit (performance counter). */
 KHB_API uint64_t khb_hash_overflows(const khb_ctx *ctx);
-/* Performance counters of the minimizer-bin path: groups it handed to the sort path (a bin outgrew its region), bins it
- * redid in hash classes because their distinct k-mers did not fit one shared-memory table. */
-KHB_API void khb_bins_counters(const khb_ctx *ctx, uint64_t *fallbacks, uint64_t *big_bins);
+/* Performance counters of the minimizer-bin path: groups it handed to the sort path (a bin could not be counted in shared
+ * memory), bins it redid in hash classes after their table filled up, groups it partitioned a second time with exact
+ * region sizes because a bin region overflowed. */
+KHB_API void khb_bins_counters(const khb_ctx *ctx, uint64_t *fallbacks, uint64_t *big_bins, uint64_t *repartitions);
 
 /* Across-group union-sum + histogram over the retained group sets: rules across_group_union and
  * across_group_union_histogram (exp_type_1.smk:243-259) for one k. */

@@ -30,7 +30,7 @@ int khb_presence_count_impl(khb_ctx *, const u64 *, const u32 *, size_t, int, in
                             void *, u64 *);
 size_t khb_hash_table_bytes(int, int, u64, int *, int *);
 int khb_bins_eligible(int, int, u64);
-int khb_bins_count_impl(khb_ctx *, const u64 *, const u32 *, u64, int, const u64 *, int, u32, u32, u64 *, void *, u64 *, u64 *, u64 *);
+int khb_bins_count_impl(khb_ctx *, const u64 *, const u32 *, u64, int, const u64 *, int, u32, u32, u64 *, void *, u64 *, u64 *, u64 *, int);
 int khb_hash_count_impl(khb_ctx *, const u64 *, const u32 *, u64, int, const u64 *, const u64 *, int, u32 *, int, int, u32, u32, u64 *, void *, u64 *, u64 *, int,
                         void *, u64 *, u32 *);
 int khb_peer_regions(khb_ctx *, const void **, u64 *, int *, int *);
@@ -801,6 +801,7 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
         // minimizer bins + per-bin shared-memory counting (bins.cu): the default wherever it applies
         bool use_bins = !small_k && !use_hash && hashed && !pivot && (ctx->group_mode == KHB_GROUP_AUTO || ctx->group_mode == KHB_GROUP_BINS) &&
                         khb_bins_eligible(k, n_genomes, n_sym);
+        int bins_exact = 0;
       again:
         if (use_bins) {
             tm.mark();  // 3
@@ -808,7 +809,7 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
             tm.mark();  // 5
             tm.mark();  // 6
             if ((rc = khb_bins_count_impl(ctx, d_codes, d_valid, n_sym, k, d_seg, n_genomes, KHB_COUNTER_MAX, nbins, d_hist, out_keys, d_runs, d_pairs,
-                                          ctx->d_mail + 3))) return rc;
+                                          ctx->d_mail + 3, bins_exact))) return rc;
         } else if (use_hash) {
             u32 *tab = nullptr;
             if ((rc = hash_table_get(ctx, hs_bytes, &tab))) return rc;
@@ -859,20 +860,31 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
         tm.mark();  // 7: count done
         KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (use_bins) {
+            if (ctx->h_mail[3] == 1 && !bins_exact) {
+                // a region outgrew its share of the record buffer (uneven minimizers): partition again with the sizes just counted
+                ctx->bins_repartitions++;
+                bins_exact = 1;
+                tm.n = 3;
+                goto again;
+            }
             if (ctx->h_mail[3]) {
-                // a bin outgrew its region or its table (very uneven minimizers): redo this group by sorting
+                // a bin could not be counted in shared memory at all: redo this group by sorting
                 ctx->bins_fallbacks++;
                 use_bins = false;
                 tm.n = 3;
                 goto again;
             }
             ctx->bins_bigbins += ctx->h_mail[5];
+            ctx->bins_hint_k = k;
+            ctx->bins_hint_genomes = n_genomes;
+            ctx->bins_hint_regions = ctx->bins_last_regions;
+            ctx->bins_hint_max = ctx->h_mail[6];
             if (getenv("KHB_BINS_VERBOSE"))
-                fprintf(stderr, "[bins] records=%llu distinct_records=%llu flushes=%llu distinct_kmers=%llu bigbins=%llu\n", (unsigned long long)ctx->h_mail[4],
+                fprintf(stderr, "[bins] records=%llu distinct_records=%llu fullest_region=%llu distinct_kmers=%llu bigbins=%llu\n", (unsigned long long)ctx->h_mail[4],
                         (unsigned long long)ctx->h_mail[7], (unsigned long long)ctx->h_mail[6], (unsigned long long)ctx->h_mail[0], (unsigned long long)ctx->h_mail[5]);
             if (n_sym) ctx->bins_rho = (double)ctx->h_mail[0] / (double)n_sym;
-            khb_prof_patch(ctx, KHB_K_BIN_PARTITION, n_sym * 3 / 8 + ctx->h_mail[4] * 32);
-            khb_prof_patch(ctx, KHB_K_BIN_COUNT, ctx->h_mail[4] * 32 + ctx->h_mail[0] * 8);
+            khb_prof_patch(ctx, KHB_K_BIN_PARTITION, n_sym * 3 / 8 + ctx->h_mail[4] * (k <= 32 ? 24 : 32));
+            khb_prof_patch(ctx, KHB_K_BIN_COUNT, ctx->h_mail[4] * (k <= 32 ? 24 : 32) + ctx->h_mail[0] * W);
         }
         if (use_hash && ctx->h_mail[3]) {
             // a probe sequence hit the limit (table nearly full of distinct k-mers): redo this group by sorting
@@ -1213,10 +1225,11 @@ int khb_set_group_mode(khb_ctx *ctx, int mode)
 }
 
 uint64_t khb_hash_overflows(const khb_ctx *ctx) { return ctx ? ctx->hs_overflows : 0; }
-void khb_bins_counters(const khb_ctx *ctx, uint64_t *fallbacks, uint64_t *big_bins)
+void khb_bins_counters(const khb_ctx *ctx, uint64_t *fallbacks, uint64_t *big_bins, uint64_t *repartitions)
 {
     if (fallbacks) *fallbacks = ctx ? ctx->bins_fallbacks : 0;
     if (big_bins) *big_bins = ctx ? ctx->bins_bigbins : 0;
+    if (repartitions) *repartitions = ctx ? ctx->bins_repartitions : 0;
 }
 
 int khb_across_groups(khb_ctx *ctx, uint32_t nbins, uint64_t *h_hist, khb_stats *stats)

@@ -62,6 +62,46 @@ __device__ __forceinline__ u32 mb_segment_of(const u64 *__restrict__ seg_off, in
     return (u32)lo;
 }
 
+// Region r of the record buffer: the fixed layout gives every region `cap` records at r * cap; after a region overflowed, the group is
+// partitioned again into regions of exactly the sizes the first attempt counted (roff[r] .. roff[r + 1], from mb_region_scan_kernel).
+__device__ __forceinline__ u64 mb_region_base(const u64 *__restrict__ roff, u32 r, u32 cap) { return roff ? __ldg(roff + r) : (u64)r * cap; }
+__device__ __forceinline__ u32 mb_region_cap(const u64 *__restrict__ roff, u32 r, u32 cap) { return roff ? (u32)(__ldg(roff + r + 1) - __ldg(roff + r)) : cap; }
+
+// exclusive prefix sums of the region sizes a first partition attempt counted (rounded up to even: 16-byte aligned regions), one CTA
+__global__ void __launch_bounds__(1024)
+mb_region_scan_kernel(const u32 *__restrict__ cursor, u64 n_regions, u64 *__restrict__ roff)
+{
+    __shared__ u64 ws[33];
+    __shared__ u64 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (u64 base = 0; base < n_regions; base += 1024) {
+        const u64 i = base + threadIdx.x;
+        const u64 v = i < n_regions ? (((u64)cursor[i] + 1ull) & ~1ull) : 0ull;
+        u64 total;
+        const u64 ex = block_excl_sum<u64>(v, ws, &total);
+        if (i < n_regions) roff[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) roff[n_regions] = carry;
+}
+
+// the fullest region of the group (records asked for, whether they fitted or not): sizes the regions of the next group of this shape
+__global__ void __launch_bounds__(256)
+mb_region_max_kernel(const u32 *__restrict__ cursor, u64 n_regions, u64 *__restrict__ out)
+{
+    u32 m = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_regions; i += (u64)gridDim.x * blockDim.x) m = cursor[i] > m ? cursor[i] : m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const u32 n = __shfl_xor_sync(0xffffffffu, m, o);
+        m = n > m ? n : m;
+    }
+    if ((threadIdx.x & 31u) == 0 && m) atomicMax((unsigned long long *)out, (unsigned long long)m);
+}
+
 // ---- pass P -----------------------------------------------------------------------------------------------------------------
 // Record layout (KW + 1 words of 64 bits, KW = 2 for k <= 32): word 0 = genome << 48 | windows << 40; words 1..KW = the record's
 // k - 1 + windows <= 32 * KW symbols from its first window start, MSB first, zero behind them (window e's k-mer = bits [2e, 2e + 2k)).
@@ -69,7 +109,7 @@ template <int KW>
 __global__ void __launch_bounds__(MB_BLOCK)
 mb_partition_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, u64 n_sym, u64 last_cw, u64 last_vw, int k, int m, u32 nbins,
                     const u64 *__restrict__ seg_off, int nseg, u32 nchunks, u32 *__restrict__ cursor, u64 *__restrict__ rec, u32 cap, u32 capw,
-                    u64 *__restrict__ flags)
+                    const u64 *__restrict__ roff, u64 *__restrict__ flags)
 {
     constexpr int CW = MB_TILE / 32 + KW + 2;     // 64-bit code words staged per tile
     constexpr int VW = MB_TILE / 32 + 4;
@@ -193,11 +233,11 @@ mb_partition_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid
         const u32 region = mb_bin_of(mh, nbins) * nchunks + (u32)(g >> 6);   // one region per bin and chunk of 64 genomes
         const u32 pieces = len <= capw ? 1u : (len + capw - 1) / capw;
         const u32 at = atomicAdd(&cursor[region], pieces);
-        if (at + pieces > cap) {                   // the region is full: the caller redoes the group another way
+        if (at + pieces > mb_region_cap(roff, region, cap)) {   // the region is full: the caller partitions again with the sizes counted here
             *flags = 1ull;
             continue;
         }
-        u64 *dst = rec + ((u64)region * cap + at) * (KW + 1);
+        u64 *dst = rec + (mb_region_base(roff, region, cap) + at) * (KW + 1);
         for (u32 s0 = 0; s0 < len; s0 += capw) {
             const u32 pl = len - s0 < capw ? len - s0 : capw;
             const u32 rel = j + s0, t = rel >> 4, s = (rel & 15u) * 2u;
@@ -265,49 +305,99 @@ enum { MCF_LAST = 1 /* last stage of a pass over the bin's records */, MCF_SCAN 
 struct mc_iter {
     u32 bin, n, n_next, off, chunk, cls, ncls;
 };
-__device__ __forceinline__ u32 mb_class_hash(u64 key) { return (u32)((key * 0xD6E8FEB86659FD93ull) >> 32); }
+// ---- k-mers of either width: KW = 2 record words -> one 64-bit word (k <= 32), KW = 3 -> 128 bits (k <= 63) ------------------------
+template <int KW> struct mb_kmer;
+template <> struct mb_kmer<2> { u64 v; };
+template <> struct mb_kmer<3> { u64 hi, lo; };
 
-__device__ __forceinline__ u64 mb_canonical64(u64 x, int k)
+__device__ __forceinline__ u64 mb_pairswap(u64 r) { return ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1); }
+
+// canonical k-mer of window e (< 32) of a record (R[1..KW] = its symbols, MSB first)
+__device__ __forceinline__ mb_kmer<2> mb_expand(const u64 *R, u32 e, int k, mb_kmer<2> *)
 {
+    const u64 w0 = R[1], w1 = R[2];
+    const u64 x = e ? ((w0 << (2 * e)) | (w1 >> (64 - 2 * e))) : w0;
     const int rs = 64 - 2 * k;
     const u64 fwd = x >> rs;
-    u64 r = __brevll(~x) << rs >> rs;
-    r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
-    return fwd < r ? fwd : r;
+    const u64 r = mb_pairswap(__brevll(~x) << rs >> rs);
+    mb_kmer<2> o;
+    o.v = fwd < r ? fwd : r;
+    return o;
+}
+__device__ __forceinline__ mb_kmer<3> mb_expand(const u64 *R, u32 e, int k, mb_kmer<3> *)
+{
+    const u64 w0 = R[1], w1 = R[2], w2 = R[3];
+    const u64 xh = e ? ((w0 << (2 * e)) | (w1 >> (64 - 2 * e))) : w0;
+    const u64 xl = e ? ((w1 << (2 * e)) | (w2 >> (64 - 2 * e))) : w1;
+    const int rs = 128 - 2 * k;                    // 2 .. 62 for 33 <= k <= 63
+    const u64 fh = xh >> rs, fl = (xl >> rs) | (xh << (64 - rs));
+    // reverse complement: all 128 bits reversed and complemented, pairs swapped back; the k-mer's bits end up in the low 2k bits
+    const u64 rl = mb_pairswap(__brevll(~xh));
+    const u64 rh = mb_pairswap(__brevll(~xl)) & ((1ull << (2 * k - 64)) - 1ull);
+    mb_kmer<3> o;
+    const bool fwd_less = fh < rh || (fh == rh && fl < rl);
+    o.hi = fwd_less ? fh : rh;
+    o.lo = fwd_less ? fl : rl;
+    return o;
+}
+__device__ __forceinline__ u64 mb_hash(const mb_kmer<2> &a) { return a.v * 0x9E3779B97F4A7C15ull; }
+__device__ __forceinline__ u64 mb_hash(const mb_kmer<3> &a) { return (a.lo ^ (a.hi * 0xBF58476D1CE4E5B9ull)) * 0x9E3779B97F4A7C15ull; }
+template <int KW> __device__ __forceinline__ u32 mb_class_hash(const mb_kmer<KW> &a)
+{
+    const u64 h = mb_hash(a);
+    return (u32)((h ^ (h >> 29)) * 0xD6E8FEB86659FD93ull >> 32);
 }
 
 #define MB_EMPTY (~0ull)
-
+#define MB_TAG_PENDING 1u
 
 // Find or claim the table slot of `key` (a claimed slot is appended to slots[]); -1 when the probe sequence is too long (table too full).
-__device__ __forceinline__ int mb_find_slot(u64 *tkey, unsigned short *slots, u32 s_log2, u64 key, u32 *s_distinct)
+// 64-bit keys: one compare-and-swap on the key word.  128-bit keys: a 32-bit tag per slot is claimed first (PENDING), the key written,
+// the tag published; a thread that meets a pending slot waits for its owner (independent thread scheduling: the owner may sit in the
+// same warp) -- the owner publishes without any warp-level synchronisation in between.
+__device__ __forceinline__ int mb_find_slot(u64 *tkey, u64 *, u32 *, unsigned short *slots, u32 s_log2, const mb_kmer<2> &key, u32 *s_distinct)
 {
     const u32 smask = (1u << s_log2) - 1u;
-    u32 slot = (u32)((key * 0x9E3779B97F4A7C15ull) >> 40) & smask;
+    u32 slot = (u32)(mb_hash(key) >> 40) & smask;
     for (u32 probes = 0;; probes++) {
         const u64 c = *(volatile u64 *)&tkey[slot];
-        if (c == key) return (int)slot;
+        if (c == key.v) return (int)slot;
         if (c == MB_EMPTY) {
-            const u64 old = atomicCAS((unsigned long long *)&tkey[slot], MB_EMPTY, key);
+            const u64 old = atomicCAS((unsigned long long *)&tkey[slot], MB_EMPTY, key.v);
             if (old == MB_EMPTY) {
                 slots[atomicAdd(s_distinct, 1u)] = (unsigned short)slot;   // the occupied slots, densely: the end-of-bin pass never looks at an empty one
                 return (int)slot;
             }
-            if (old == key) return (int)slot;
+            if (old == key.v) return (int)slot;
         }
         if (probes >= MC_PROBES) return -1;
         slot = (slot + 1) & smask;
     }
 }
-// Insert `key` with genome bit gb (of the 64 of the current chunk of genomes).  False when the table is too full.
-__device__ __forceinline__ bool mb_insert(u64 *tkey, u64 *tbits, unsigned short *slots, u32 s_log2, u64 key, u32 gb, u32 *s_distinct)
+__device__ __forceinline__ int mb_find_slot(u64 *thi, u64 *tlo, u32 *ttag, unsigned short *slots, u32 s_log2, const mb_kmer<3> &key, u32 *s_distinct)
 {
-    const int slot = mb_find_slot(tkey, slots, s_log2, key, s_distinct);
-    if (slot < 0) return false;
-    u32 *bw = (u32 *)&tbits[slot] + (gb >> 5);
-    const u32 bm = 1u << (gb & 31u);
-    if (!(*(volatile u32 *)bw & bm)) atomicOr(bw, bm);
-    return true;
+    const u32 smask = (1u << s_log2) - 1u;
+    const u64 h = mb_hash(key);
+    const u32 mytag = (u32)h | 2u;                 // never 0 (empty) or 1 (pending)
+    u32 slot = (u32)(h >> 40) & smask;
+    for (u32 probes = 0;; probes++) {
+        u32 t = *(volatile u32 *)&ttag[slot];
+        if (t == 0u) {
+            t = atomicCAS(&ttag[slot], 0u, MB_TAG_PENDING);
+            if (t == 0u) {
+                thi[slot] = key.hi;
+                tlo[slot] = key.lo;
+                __threadfence_block();
+                *(volatile u32 *)&ttag[slot] = mytag;
+                slots[atomicAdd(s_distinct, 1u)] = (unsigned short)slot;
+                return (int)slot;
+            }
+        }
+        while (t == MB_TAG_PENDING) t = *(volatile u32 *)&ttag[slot];
+        if (t == mytag && *(volatile u64 *)&thi[slot] == key.hi && *(volatile u64 *)&tlo[slot] == key.lo) return (int)slot;
+        if (probes >= MC_PROBES) return -1;
+        slot = (slot + 1) & smask;
+    }
 }
 // OR a 64-bit genome mask into a slot's bits (two 32-bit shared-memory atomics, skipped when nothing new)
 __device__ __forceinline__ void mb_or_mask(u64 *word, u64 mask)
@@ -329,14 +419,14 @@ struct mc_geom {
     u32 hrows;       // histogram rows kept in shared memory (+ row 0)
 };
 struct mc_smem {
-    u64 *tkey, *tbits, *ring, *dstore, *dmask;
-    u32 *rtab, *hist;
+    u64 *tkey, *tlo, *tbits, *ring, *dstore, *dmask;   // tkey: the key (KW = 2) or its high word; tlo: low word (KW = 3 only)
+    u32 *ttag, *rtab, *hist;                            // ttag: slot tags (KW = 3 only)
     unsigned short *tcnt, *slots, *dwoff, *map;
 };
 __host__ __device__ inline size_t mc_smem_bytes(int KW, const mc_geom &g, int block)
 {
     const size_t S = (size_t)1 << g.s_log2;
-    return S * 16 + 2 * (size_t)MC_R * (KW + 1) * 8 + (size_t)g.dcap * (KW + 1) * 8 + (size_t)g.dcap * 8 + ((size_t)4 << g.rt_log2) +
+    return S * 16 + (KW == 3 ? S * 12 : 0) + 2 * (size_t)MC_R * (KW + 1) * 8 + (size_t)g.dcap * (KW + 1) * 8 + (size_t)g.dcap * 8 + ((size_t)4 << g.rt_log2) +
            (((size_t)g.hrows + 2) & ~(size_t)1) * 4 + (g.nchunks > 1 ? S * 2 : 0) + S * 2 + (size_t)g.dcap * 2 + (size_t)MC_WCAP * 2 + 64;
 }
 __device__ __forceinline__ mc_smem mc_carve(unsigned char *base, int KW, const mc_geom &g)
@@ -344,17 +434,53 @@ __device__ __forceinline__ mc_smem mc_carve(unsigned char *base, int KW, const m
     const size_t S = (size_t)1 << g.s_log2;
     mc_smem s;
     s.tkey = (u64 *)base;
-    s.tbits = s.tkey + S;
+    s.tlo = s.tkey + S;
+    s.tbits = s.tlo + (KW == 3 ? S : 0);
     s.ring = s.tbits + S;
     s.dstore = s.ring + 2 * (size_t)MC_R * (KW + 1);
     s.dmask = s.dstore + (size_t)g.dcap * (KW + 1);
-    s.rtab = (u32 *)(s.dmask + g.dcap);
+    s.ttag = (u32 *)(s.dmask + g.dcap);
+    s.rtab = s.ttag + (KW == 3 ? S : 0);
     s.hist = s.rtab + ((size_t)1 << g.rt_log2);
     s.tcnt = (unsigned short *)(s.hist + (((size_t)g.hrows + 2) & ~(size_t)1));   // [S] when there are several chunks of genomes
     s.slots = s.tcnt + (g.nchunks > 1 ? S : 0);                                   // [S]
     s.dwoff = s.slots + S;                                                         // [dcap]
     s.map = s.dwoff + g.dcap;                                                      // [MC_WCAP]
     return s;
+}
+
+template <int KW> __device__ __forceinline__ int mb_slot_of(const mc_smem &sm, u32 s_log2, const mb_kmer<KW> &key, u32 *s_distinct)
+{
+    return mb_find_slot(sm.tkey, sm.tlo, sm.ttag, sm.slots, s_log2, key, s_distinct);
+}
+// Insert `key` with genome bit gb (of the 64 of the current chunk of genomes).  False when the table is too full.
+template <int KW> __device__ __forceinline__ bool mb_insert(const mc_smem &sm, u32 s_log2, const mb_kmer<KW> &key, u32 gb, u32 *s_distinct)
+{
+    const int slot = mb_slot_of<KW>(sm, s_log2, key, s_distinct);
+    if (slot < 0) return false;
+    u32 *bw = (u32 *)&sm.tbits[slot] + (gb >> 5);
+    const u32 bm = 1u << (gb & 31u);
+    if (!(*(volatile u32 *)bw & bm)) atomicOr(bw, bm);
+    return true;
+}
+template <int KW> __device__ __forceinline__ void mb_slot_reset(const mc_smem &sm, u32 i)
+{
+    if (KW == 3) sm.ttag[i] = 0u;
+    else sm.tkey[i] = MB_EMPTY;
+}
+// the k-mer of slot i, mixed like K2's keys (kmer_mix64 / kmer_mix128), to position `at` of the group-set store
+template <int KW> __device__ __forceinline__ void mb_emit(const mc_smem &sm, u32 i, void *out, u64 at, int k)
+{
+    if (KW == 3) {
+        u64 hi = sm.tkey[i], lo = sm.tlo[i];
+        kmer_mix128(hi, lo, k);
+        Key128 o;
+        o.lo = lo;
+        o.hi = hi;
+        ((Key128 *)out)[at] = o;
+    } else {
+        ((u64 *)out)[at] = kmer_mix64(sm.tkey[i], k);
+    }
 }
 
 __device__ __forceinline__ u64 mb_record_hash(const u64 *w, int KW, u32 len)
@@ -378,8 +504,9 @@ __device__ __forceinline__ u64 mb_record_hash(const u64 *w, int KW, u32 len)
 template <int KW, bool MULTI, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32 nbins, u32 cap, int k, mc_geom geo, u32 n_genomes, u32 cs,
-                u32 thr1 /* records one pass over a bin may hold */, u32 over_cap, u64 *__restrict__ hist, u64 *__restrict__ out_keys,
-                u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs, u32 *__restrict__ over_list, u32 *__restrict__ over_count, u64 *__restrict__ d_stat)
+                u32 thr1 /* records one pass over a bin may hold */, u32 over_cap, u64 *__restrict__ hist, void *__restrict__ out_keys,
+                u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs, u32 *__restrict__ over_list, u32 *__restrict__ over_count, u64 *__restrict__ d_stat,
+                const u64 *__restrict__ roff)
 {
     extern __shared__ __align__(16) unsigned char mc_raw[];
     __shared__ __align__(8) u64 bars[2];
@@ -391,8 +518,8 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
     const mc_smem sm = mc_carve(mc_raw, KW, geo);
     const u32 tid = threadIdx.x;
     if (d_stat[0] & 1ull) return;   // a bin region overflowed: its slots hold stale bytes, and the caller redoes the group anyway
-    for (u32 i = tid; i < S; i += BLOCK) sm.tkey[i] = MB_EMPTY;
     for (u32 i = tid; i < S; i += BLOCK) {
+        mb_slot_reset<KW>(sm, i);
         sm.tbits[i] = 0ull;
         if (MULTI) sm.tcnt[i] = 0u;
     }
@@ -424,7 +551,8 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
     auto region_records = [&](u32 u, u32 lim) -> u32 {
         if (u >= lim) return 0u;
         const u32 c = __ldg(cursor + u);
-        return c < cap ? c : cap;
+        const u32 rcap = mb_region_cap(roff, u, cap);
+        return c < rcap ? c : rcap;
     };
     auto open_bin = [&]() {   // counts of the bin it.bin (several chunks: into s_cn); false when the bin is empty
         if (!MULTI) return it.n != 0;
@@ -476,7 +604,7 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
         const u32 bytes = (count * (u32)((KW + 1) * 8) + 15u) & ~15u;   // an odd count of 24-byte records: 8 bytes of the next record ride along
         mbar_arrive_expect_tx(&bars[buf], bytes);
         const u64 region = MULTI ? (u64)it.bin * nchunks + it.chunk : (u64)it.bin;
-        bulk_g2s(sm.ring + (size_t)buf * MC_R * (KW + 1), rec + (region * cap + it.off) * (KW + 1), bytes, &bars[buf]);
+        bulk_g2s(sm.ring + (size_t)buf * MC_R * (KW + 1), rec + (mb_region_base(roff, (u32)region, cap) + it.off) * (KW + 1), bytes, &bars[buf]);
         it.off += count;
         if (last) {
             it.off = 0;
@@ -516,11 +644,9 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
     // Expand the distinct records collected so far into the k-mer table (every k-mer takes its record's genome mask), then forget them.
     // The windows of the distinct records were laid out densely while the records were collected (map[t] = record of window t,
     // dwoff[record] = its first t), so the threads simply share them: no prefix sum, no barrier before the loop.
-    u32 my_flushes = 0;
     u64 my_drecords = 0;
     auto flush_records = [&](u32 cls, u32 ncls) {
         const u32 nw = s_wtotal < MC_WCAP ? s_wtotal : MC_WCAP;
-        my_flushes++;
         my_drecords += s_dcount < dcap ? s_dcount : dcap;
         bool ok = true;
         for (u32 t = tid; t < nw; t += BLOCK) {
@@ -528,12 +654,9 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
             if (id == 0xffffu) continue;                                       // reserved by a record that found no room
             const u64 *R = sm.dstore + (size_t)id * (KW + 1);
             const u32 e = t - sm.dwoff[id];
-            const u32 q = e >> 5, o = e & 31u;
-            const u64 w0 = R[1 + q], w1 = q + 2 <= (u32)KW ? R[2 + q] : 0ull;
-            const u64 x = o ? ((w0 << (2 * o)) | (w1 >> (64 - 2 * o))) : w0;
-            const u64 key = mb_canonical64(x, k);
-            if (ncls > 1 && __umulhi(mb_class_hash(key), ncls) != cls) continue;
-            const int slot = mb_find_slot(sm.tkey, sm.slots, s_log2, key, &s_distinct);
+            const mb_kmer<KW> key = mb_expand(R, e, k, (mb_kmer<KW> *)nullptr);
+            if (ncls > 1 && __umulhi(mb_class_hash<KW>(key), ncls) != cls) continue;
+            const int slot = mb_slot_of<KW>(sm, s_log2, key, &s_distinct);
             if (slot < 0) {
                 ok = false;
                 continue;
@@ -651,7 +774,7 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
         if (s_over) {
             __syncthreads();
             for (u32 i = tid; i < S; i += BLOCK) {
-                sm.tkey[i] = MB_EMPTY;
+                mb_slot_reset<KW>(sm, i);
                 sm.tbits[i] = 0ull;
                 if (MULTI) sm.tcnt[i] = 0u;
             }
@@ -680,7 +803,6 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
         const u64 base = s_base;
         for (u32 j = tid; j < nd_keys; j += BLOCK) {
             const u32 i = sm.slots[j];
-            const u64 key = sm.tkey[i];
             u32 c = (u32)__popcll(sm.tbits[i]);
             sm.tbits[i] = 0ull;
             if (MULTI) {
@@ -692,8 +814,8 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
             if (cc == 1u) n_one++;
             else if (cc == c_all) n_all++;
             else if (cc <= hrows) atomicAdd(&sm.hist[cc], 1u);
-            if (out_keys) out_keys[base + j] = kmer_mix64(key, k);
-            sm.tkey[i] = MB_EMPTY;
+            if (out_keys) mb_emit<KW>(sm, i, out_keys, base + j, k);
+            mb_slot_reset<KW>(sm, i);
         }
         __syncthreads();
         if (tid == 0) s_distinct = 0;
@@ -713,7 +835,6 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
     }
     if (tid == 0 && my_records) {
         atomicAdd((unsigned long long *)&d_stat[1], (unsigned long long)my_records);
-        atomicAdd((unsigned long long *)&d_stat[3], (unsigned long long)my_flushes);
         atomicAdd((unsigned long long *)&d_stat[4], (unsigned long long)my_drecords);
     }
     __syncthreads();
@@ -727,8 +848,8 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
 template <int KW, bool MULTI>
 __global__ void __launch_bounds__(MC_BLOCK)
 mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32 cap, int k, mc_geom geo, u32 n_genomes, u32 cs,
-                 u64 *__restrict__ hist, u64 *__restrict__ out_keys, u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs,
-                 const u32 *__restrict__ over_list, const u32 *__restrict__ over_count, u32 over_cap, u64 *__restrict__ flags)
+                 u64 *__restrict__ hist, void *__restrict__ out_keys, u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs,
+                 const u32 *__restrict__ over_list, const u32 *__restrict__ over_count, u32 over_cap, u64 *__restrict__ flags, const u64 *__restrict__ roff)
 {
     extern __shared__ __align__(16) unsigned char mc_raw[];
     __shared__ u32 s_over, s_distinct, ws[33];
@@ -740,8 +861,8 @@ mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u3
     if (flags[0] & 1ull) return;
     if (blockIdx.x == 0 && tid == 0) flags[2] = n_over;
     if (blockIdx.x >= n_over) return;
-    for (u32 i = tid; i < S; i += MC_BLOCK) sm.tkey[i] = MB_EMPTY;
     for (u32 i = tid; i < S; i += MC_BLOCK) {
+        mb_slot_reset<KW>(sm, i);
         sm.tbits[i] = 0ull;
         if (MULTI) sm.tcnt[i] = 0u;
     }
@@ -765,8 +886,9 @@ mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u3
             const u32 M = stM[--sp], r0 = stR[sp];
             for (u32 chunk = 0; chunk < nch; chunk++) {
                 const u32 region = bin * nch + chunk;
-                const u32 n = cursor[region] < cap ? cursor[region] : cap;
-                const u64 *rb = rec + (u64)region * cap * (KW + 1);
+                const u32 lim = mb_region_cap(roff, region, cap);
+                const u32 n = cursor[region] < lim ? cursor[region] : lim;
+                const u64 *rb = rec + mb_region_base(roff, region, cap) * (KW + 1);
                 const u32 sub = tid & 15u, grp = tid >> 4;   // 16 lanes share a record
                 bool ok = true;
                 for (u32 r = grp; r < n; r += MC_BLOCK / 16) {
@@ -776,13 +898,10 @@ mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u3
                     u32 len = (u32)(h >> 40) & 0xffu;
                     len = len < MB_MAXW ? len : MB_MAXW;
                     for (u32 e = sub; e < len; e += 16) {
-                        const u32 q = e >> 5, o = e & 31u;
-                        const u64 w0 = R[1 + q], w1 = q + 2 <= (u32)KW ? R[2 + q] : 0ull;
-                        const u64 x = o ? ((w0 << (2 * o)) | (w1 >> (64 - 2 * o))) : w0;
-                        const u64 key = mb_canonical64(x, k);
-                        if (ncls0 > 1 && __umulhi(mb_class_hash(key), ncls0) != cls0) continue;
-                        if ((u32)((key * 0x9E3779B97F4A7C15ull) >> 20) % M != r0) continue;
-                        ok = mb_insert(sm.tkey, sm.tbits, sm.slots, s_log2, key, g & 63u, &s_distinct) && ok;
+                        const mb_kmer<KW> key = mb_expand(R, e, k, (mb_kmer<KW> *)nullptr);
+                        if (ncls0 > 1 && __umulhi(mb_class_hash<KW>(key), ncls0) != cls0) continue;
+                        if ((u32)(mb_hash(key) >> 20) % M != r0) continue;
+                        ok = mb_insert<KW>(sm, s_log2, key, g & 63u, &s_distinct) && ok;
                     }
                 }
                 if (!ok) s_over = 1;
@@ -806,7 +925,7 @@ mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u3
             __syncthreads();
             if (over) {
                 for (u32 i = tid; i < S; i += MC_BLOCK) {
-                    sm.tkey[i] = MB_EMPTY;
+                    mb_slot_reset<KW>(sm, i);
                     sm.tbits[i] = 0ull;
                     if (MULTI) sm.tcnt[i] = 0u;
                 }
@@ -830,7 +949,6 @@ mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u3
             const u64 base = s_base;
             for (u32 j = tid; j < nd_keys; j += MC_BLOCK) {
                 const u32 i = sm.slots[j];
-                const u64 key = sm.tkey[i];
                 u32 c = (u32)__popcll(sm.tbits[i]);
                 sm.tbits[i] = 0ull;
                 if (MULTI) {
@@ -840,8 +958,8 @@ mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u3
                 pairs += c;
                 const u32 cc = c > cs ? cs : c;
                 if (cc <= hrows) atomicAdd(&sm.hist[cc], 1u);
-                if (out_keys) out_keys[base + j] = kmer_mix64(key, k);
-                sm.tkey[i] = MB_EMPTY;
+                if (out_keys) mb_emit<KW>(sm, i, out_keys, base + j, k);
+                mb_slot_reset<KW>(sm, i);
             }
             __syncthreads();
             if (tid == 0) s_distinct = 0;
@@ -870,29 +988,23 @@ static long long mb_env(const char *name, long long dflt)
 // Does the minimizer-bin path apply?  (64-bit keys with a spare value, enough m-mers per window for super-k-mers to pay.)
 int khb_bins_eligible(int k, int n_genomes, u64 n_sym)
 {
-    return k >= 17 && k <= 31 && n_genomes >= 1 && n_genomes <= 8191 && n_sym >= 1 && n_sym < (1ull << 40);
+    return k >= 17 && k <= 63 && k != 32 && n_genomes >= 1 && n_genomes <= 8191 && n_sym >= 1 && n_sym < (1ull << 40);
 }
 
 // The group stage through minimizer bins.  d_stat: u64[4] in device memory, written here: [0] flags (1: a bin region overflowed,
 // 2: a bin could not be counted -- either way the outputs are incomplete and the caller redoes the group another way), [1] records,
-// [2] bins redone by mb_bigbin_kernel.  d_hist[nbins_hist + 1], d_runs (distinct k-mers = keys appended to d_out_keys), d_pairs
-// (sum over genomes of their distinct k-mers) are zeroed here.
+// [2] bins redone by mb_bigbin_kernel, [3] records asked for in the fullest region, [4] distinct records.  d_hist[nbins_hist + 1], d_runs (distinct k-mers = keys appended to d_out_keys), d_pairs
+// (sum over genomes of their distinct k-mers) are zeroed here.  exact != 0: the call before this one, on the same group, ended with flag 1;
+// partition again into regions of exactly the sizes that attempt counted (they are still in the context's scratch).
 int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u64 n_sym, int k, const u64 *d_seg_off, int n_genomes, u32 cs, u32 nbins_hist,
-                        u64 *d_hist, void *d_out_keys, u64 *d_runs, u64 *d_pairs, u64 *d_stat)
+                        u64 *d_hist, void *d_out_keys, u64 *d_runs, u64 *d_pairs, u64 *d_stat, int exact)
 {
     if (!khb_bins_eligible(k, n_genomes, n_sym)) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: k=%d / %d genomes not supported", k, n_genomes);
-    constexpr int KW = 2;                         // 64 symbols per record: k - 1 + 32 windows for k <= 32
+    const int KW = k <= 32 ? 2 : 3;               // record words of symbols: k - 1 + 32 windows fit 64 (k <= 32) or 96 symbols
     const int m = 13, w = k - m + 1;
     const u32 capw = (u32)(32 * KW + 1 - k) < MB_MAXW ? (u32)(32 * KW + 1 - k) : MB_MAXW;
-    // Bin geometry.  All copies of a k-mer -- one per genome that holds it, ~ (w + 1) / 2 windows around each -- land in one bin together, so
-    // a bin's load comes in lumps of ~10 x n_genomes windows; with ~8 lumps per bin the largest bin stays within ~3 x the mean.
-    u64 wpb_dflt = 80ull * (u64)n_genomes;
-    wpb_dflt = wpb_dflt < 1024 ? 1024 : wpb_dflt > 8192 ? 8192 : wpb_dflt;
-    const u64 wpb = (u64)mb_env("KHB_BINS_WPB", (long long)wpb_dflt);
-    u64 nb64 = div_up(n_sym, wpb ? wpb : wpb_dflt);
-    if (nb64 < 16) nb64 = 16;
-    if (nb64 > (1ull << 28)) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: group too large");
-    const u32 nb = (u32)nb64;
+    double avg_len = (w + 1) * 0.5;               // windows per super-k-mer on random sequence, before the cuts at capw and at tile ends
+    if (avg_len > capw) avg_len = capw;
     // distinct k-mers per window: measured on the previous group (+ 25 %), else a guess from the group size
     double rho_w = ctx->bins_rho > 0.0 ? ctx->bins_rho * 1.25 : (n_genomes >= 32 ? 0.2 : n_genomes >= 16 ? 0.25 : n_genomes >= 4 ? 0.5 : 1.0);
     const long long rho_pct = mb_env("KHB_BINS_RHO_PCT", 0);   // test hook: distinct k-mers per 100 windows
@@ -901,10 +1013,26 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
     if (rho_w < 0.005) rho_w = 0.005;
     mc_geom geo;
     geo.nchunks = (u32)div_up((size_t)n_genomes, 64);
-    {   // table slots: the mean bin's distinct k-mers fill ~45 % (larger bins are counted in hash classes), within what an SM can hold
+    // Bin geometry.  All copies of a k-mer -- one per genome that holds it, avg_len windows around each -- land in one bin together, so a
+    // region's load (one bin, one chunk of <= 64 genomes) comes in lumps of ~avg_len x genomes windows; ~6 lumps per region keep the largest
+    // region within a few times the mean.  But a bin's distinct k-mers should fill less than half of the largest table of which two CTAs fit
+    // an SM (2^12 slots of 64-bit, 2^11 of 128-bit k-mers); where the two pull apart the table wins, the regions get more room above their
+    // mean, and a region that still overflows makes the group be partitioned a second time with exact sizes.
+    const u32 s_max = KW == 3 ? 11u : 12u;
+    const double lump = (double)(n_genomes < 64 ? n_genomes : 64) * avg_len;
+    double wpb_d = (double)geo.nchunks * 6.0 * lump;
+    const double wpb_tab = 0.45 * (double)(1u << s_max) / rho_w;
+    if (wpb_d > wpb_tab) wpb_d = wpb_tab;
+    if (wpb_d < 1024.0) wpb_d = 1024.0;
+    const u64 wpb = (u64)mb_env("KHB_BINS_WPB", (long long)wpb_d);
+    u64 nb64 = div_up(n_sym, wpb ? wpb : 1024);
+    if (nb64 < 16) nb64 = 16;
+    if (nb64 > (1ull << 28)) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: group too large");
+    const u32 nb = (u32)nb64;
+    {   // table slots: the mean bin's distinct k-mers fill ~45 % (larger bins are counted in hash classes)
         const double want = (double)(n_sym / nb + 1) * rho_w / 0.45;
         u32 l2 = 10;
-        while (l2 < 12 && (double)(1u << l2) < want) l2++;
+        while (l2 < s_max && (double)(1u << l2) < want) l2++;
         geo.s_log2 = (u32)mb_env("KHB_BINS_SLOTS_LOG2", l2);
         if (geo.s_log2 < 8 || geo.s_log2 > 13) return khb_fail(ctx, KHB_ERR_ARG, "KHB_BINS_SLOTS_LOG2 outside 8..13");
     }
@@ -914,13 +1042,15 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
     geo.rt_log2 = 7;
     while ((1u << geo.rt_log2) < 2 * geo.dcap) geo.rt_log2++;
     const u32 s_log2 = geo.s_log2;
-    double avg_len = (w + 1) * 0.5;
-    if (avg_len > capw) avg_len = capw;
     const double est_records = (double)n_sym / avg_len * 1.15 + (double)div_up(n_sym, MB_TILE);
     // one region per bin and chunk of 64 genomes; the fewer lumps a region holds on average, the more room above the mean it gets
     const u64 n_regions = (u64)nb * geo.nchunks;
-    const double slack = (double)mb_env("KHB_BINS_SLACK_PCT", geo.nchunks > 1 ? 600 : 400) / 100.0;
-    const u32 cap = ((u32)(est_records / (double)n_regions * slack) + 64u) & ~1u;   // even: every region starts 16-byte aligned
+    const double slack = (double)mb_env("KHB_BINS_SLACK_PCT", (double)(n_sym / nb) >= 5.0 * lump * geo.nchunks ? 400 : 600) / 100.0;
+    u32 cap = ((u32)(est_records / (double)n_regions * slack) + 64u) & ~1u;   // even: every region starts 16-byte aligned
+    // ... unless the group before this one had the same shape: then its fullest region (+ 40 %) is the better guide
+    if (ctx->bins_hint_k == k && ctx->bins_hint_genomes == n_genomes && ctx->bins_hint_regions > 0 && !mb_env("KHB_BINS_SLACK_PCT", 0) &&
+        (double)n_regions > 0.8 * (double)ctx->bins_hint_regions && (double)n_regions < 1.25 * (double)ctx->bins_hint_regions)
+        cap = ((u32)((double)ctx->bins_hint_max * 1.4 * (double)ctx->bins_hint_regions / (double)n_regions) + 64u) & ~1u;
     const size_t rec_bytes = (size_t)n_regions * cap * (KW + 1) * 8;
     // Records one pass over a bin may hold so that its distinct k-mers fill at most ~55 % of the table; larger bins are counted in
     // several hash classes.
@@ -930,11 +1060,23 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
     const bool multi = geo.nchunks > 1;
     int rc;
     void *p;
-    if ((rc = khb_scratch_get(ctx, SCR_AUX, (size_t)n_regions * 4 + (size_t)nb * 48 + 256, &p))) return rc;
+    if ((rc = khb_scratch_get(ctx, SCR_AUX, (size_t)n_regions * 12 + (size_t)nb * 48 + 512, &p))) return rc;
     u32 *d_over_count = (u32 *)p;                 // [0] bins in the list
     u32 *d_cur = d_over_count + 16, *d_over_list = d_cur + n_regions;
+    u64 *d_roff = (u64 *)(((uintptr_t)(d_over_list + 3 * (size_t)over_cap) + 15) & ~(uintptr_t)15);   // [n_regions + 1], exact layout only
+    const u64 *roff = nullptr;
     void *pr;
-    if ((rc = khb_scratch_get(ctx, SCR_KEYS_A, rec_bytes + 64, &pr))) return rc;
+    if (exact) {
+        mb_region_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_cur, n_regions, d_roff);
+        KHB_LAUNCH_CHECK(ctx);
+        KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, d_roff + n_regions, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const u64 total = ctx->h_mail[0];
+        if ((rc = khb_scratch_get(ctx, SCR_KEYS_A, (size_t)total * (KW + 1) * 8 + 64, &pr))) return rc;
+        roff = d_roff;
+    } else if ((rc = khb_scratch_get(ctx, SCR_KEYS_A, rec_bytes + 64, &pr))) {
+        return rc;
+    }
     KHB_CUDA(ctx, cudaMemsetAsync(d_over_count, 0, 64 + (size_t)n_regions * 4, ctx->stream));
     KHB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, ((size_t)nbins_hist + 1) * sizeof(u64), ctx->stream));
     KHB_CUDA(ctx, cudaMemsetAsync(d_runs, 0, sizeof(u64), ctx->stream));
@@ -944,8 +1086,12 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
     {
         const u64 tiles = div_up(n_sym, MB_TILE);
         khb_prof_begin(ctx, KHB_K_BIN_PARTITION);
-        mb_partition_kernel<KW><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, m, nb, d_seg_off, n_genomes, geo.nchunks, d_cur,
-                                                                               (u64 *)pr, cap, capw, d_stat);
+        if (KW == 2)
+            mb_partition_kernel<2><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, m, nb, d_seg_off, n_genomes, geo.nchunks,
+                                                                                  d_cur, (u64 *)pr, cap, capw, roff, d_stat);
+        else
+            mb_partition_kernel<3><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, m, nb, d_seg_off, n_genomes, geo.nchunks,
+                                                                                  d_cur, (u64 *)pr, cap, capw, roff, d_stat);
         khb_prof_end(ctx, KHB_K_BIN_PARTITION, n_sym * 3 / 8);
         KHB_LAUNCH_CHECK(ctx);
     }
@@ -954,9 +1100,16 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
         if (shm > 227 * 1024) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: %zu bytes of shared memory per CTA", shm);
         // two CTAs of 256 threads per SM at least; where the tables leave room for one CTA only, that one has 512 threads
         const bool wide = 2 * (shm + 1024) > 227 * 1024;
-        const void *fn = multi ? (wide ? (const void *)mb_count_kernel<KW, true, 512> : (const void *)mb_count_kernel<KW, true, 256>)
-                               : (wide ? (const void *)mb_count_kernel<KW, false, 512> : (const void *)mb_count_kernel<KW, false, 256>);
-        const void *bfn = multi ? (const void *)mb_bigbin_kernel<KW, true> : (const void *)mb_bigbin_kernel<KW, false>;
+        const void *fn, *bfn;
+        if (KW == 2) {
+            fn = multi ? (wide ? (const void *)mb_count_kernel<2, true, 512> : (const void *)mb_count_kernel<2, true, 256>)
+                       : (wide ? (const void *)mb_count_kernel<2, false, 512> : (const void *)mb_count_kernel<2, false, 256>);
+            bfn = multi ? (const void *)mb_bigbin_kernel<2, true> : (const void *)mb_bigbin_kernel<2, false>;
+        } else {
+            fn = multi ? (wide ? (const void *)mb_count_kernel<3, true, 512> : (const void *)mb_count_kernel<3, true, 256>)
+                       : (wide ? (const void *)mb_count_kernel<3, false, 512> : (const void *)mb_count_kernel<3, false, 256>);
+            bfn = multi ? (const void *)mb_bigbin_kernel<3, true> : (const void *)mb_bigbin_kernel<3, false>;
+        }
         const int block = wide ? 512 : 256;
         shm = mc_smem_bytes(KW, geo, block);
         int per_sm = 0;
@@ -972,9 +1125,9 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
         const u32 *c_cur = d_cur;
         u32 n_gen = (u32)n_genomes, cs_ = cs, nb_ = nb, cap_ = cap, thr_ = thr1, ocap_ = over_cap;
         int k_ = k;
-        u64 *keys_ = (u64 *)d_out_keys;
+        void *keys_ = d_out_keys;
         const u32 *c_list = d_over_list, *c_cnt = d_over_count;
-        void *cargs[] = {&c_rec, &c_cur, &nb_, &cap_, &k_, &geo, &n_gen, &cs_, &thr_, &ocap_, &d_hist, &keys_, &d_runs, &d_pairs, &d_over_list, &d_over_count, &d_stat};
+        void *cargs[] = {&c_rec, &c_cur, &nb_, &cap_, &k_, &geo, &n_gen, &cs_, &thr_, &ocap_, &d_hist, &keys_, &d_runs, &d_pairs, &d_over_list, &d_over_count, &d_stat, &roff};
         if (mb_env("KHB_BINS_VERBOSE", 0))
             fprintf(stderr, "[bins] k=%d genomes=%d windows=%llu bins=%u chunks=%u cap=%u slots=2^%u dcap=%u thr1=%u rho_w=%.3f shm=%zu ctas/sm=%d block=%d\n", k, n_genomes,
                     (unsigned long long)n_sym, nb, geo.nchunks, cap, geo.s_log2, geo.dcap, thr1, rho_w, shm, per_sm, block);
@@ -982,9 +1135,12 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
         KHB_CUDA(ctx, cudaLaunchKernel(fn, dim3(grid), dim3(block), cargs, shm, ctx->stream));
         khb_prof_end(ctx, KHB_K_BIN_COUNT, 0);
         KHB_LAUNCH_CHECK(ctx);
-        void *bargs[] = {&c_rec, &c_cur, &cap_, &k_, &geo, &n_gen, &cs_, &d_hist, &keys_, &d_runs, &d_pairs, &c_list, &c_cnt, &ocap_, &d_stat};
+        void *bargs[] = {&c_rec, &c_cur, &cap_, &k_, &geo, &n_gen, &cs_, &d_hist, &keys_, &d_runs, &d_pairs, &c_list, &c_cnt, &ocap_, &d_stat, &roff};
         KHB_CUDA(ctx, cudaLaunchKernel(bfn, dim3((u32)ctx->num_sms * 2u), dim3(MC_BLOCK), bargs, shm, ctx->stream));
         KHB_LAUNCH_CHECK(ctx);
+        mb_region_max_kernel<<<(unsigned)ctx->num_sms * 4u, 256, 0, ctx->stream>>>(d_cur, n_regions, d_stat + 3);
+        KHB_LAUNCH_CHECK(ctx);
+        ctx->bins_last_regions = n_regions;
     }
     return KHB_OK;
 }

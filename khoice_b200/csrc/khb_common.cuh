@@ -213,7 +213,9 @@ struct khb_ctx {
     struct khb_peer *peer;  // multi-GPU exchange over peer memory (peer.cu)
     cudaStream_t prof_stream;  // stream the next khb_prof_begin/end pair records on (null: `stream`)
     double bins_rho;   // distinct k-mers per window in the last group the minimizer-bin path counted (sizes the next group's passes)
-    u64 bins_fallbacks, bins_bigbins;  // groups the minimizer-bin path handed to the sort path / bins redone in hash classes (bins.cu)
+    u64 bins_fallbacks, bins_bigbins, bins_repartitions;
+    int bins_hint_k, bins_hint_genomes;            // shape of the last group the minimizer-bin path counted ...
+    u64 bins_hint_regions, bins_hint_max, bins_last_regions;  // ... its regions and the records of its fullest one  // groups the minimizer-bin path handed to the sort path / bins redone in hash classes (bins.cu)
     int group_mode;    // KHB_GROUP_* (khb_set_group_mode; initial value from the environment variable KHB_GROUP_MODE)
 };
 

@@ -116,7 +116,7 @@ _SIGNATURES = [
     ("khb_peer_region_keys", C.c_uint64, [_P]),
     ("khb_set_group_mode", C.c_int, [_P, C.c_int]),
     ("khb_hash_overflows", C.c_uint64, [_P]),
-    ("khb_bins_counters", None, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("khb_bins_counters", None, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
 
@@ -323,10 +323,10 @@ class Engine:
 
     @property
     def bins_counters(self) -> dict:
-        """Minimizer-bin path: groups handed to the sort path, bins redone in hash classes."""
-        a, b = C.c_uint64(), C.c_uint64()
-        self.lib.khb_bins_counters(self.ctx, C.byref(a), C.byref(b))
-        return {"fallbacks": int(a.value), "big_bins": int(b.value)}
+        """Minimizer-bin path: groups handed to the sort path, bins redone in hash classes, groups partitioned a second time."""
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.lib.khb_bins_counters(self.ctx, C.byref(a), C.byref(b), C.byref(c))
+        return {"fallbacks": int(a.value), "big_bins": int(b.value), "repartitions": int(c.value)}
 
     def profile_enable(self, on: bool = True):
         """Bracket every kernel launch with CUDA events (clears earlier records)."""

@@ -1,4 +1,4 @@
-"""The minimizer-bin group stage (csrc/bins.cu, the default group path for 17 <= k <= 31): super-k-mer records partitioned by
+"""The minimizer-bin group stage (csrc/bins.cu, the default group path for 17 <= k <= 63, k != 32): super-k-mer records partitioned by
 minimizer, every bin counted by one CTA in a shared-memory table.  It must give exactly what the single-sort path and the CPU
 oracle give (reference call sites: /root/reference/workflow/rules/exp_type_1.smk:156-191 within a group, :233-259 across groups)
 -- histograms, group sets, per-genome totals -- for every table variant (<= 64 genomes, chunks of 64 genomes), for records
@@ -57,7 +57,7 @@ def _check(res, w_ref, a_ref, st_ref, n_groups):
         assert np.array_equal(x, y)
 
 
-@pytest.mark.parametrize("k", [17, 18, 21, 24, 27, 30, 31])
+@pytest.mark.parametrize("k", [17, 18, 21, 24, 27, 30, 31, 33, 40, 47, 56, 63])   # 64-bit words up to 31, 128-bit from 33
 @pytest.mark.parametrize("n_genomes", [3, 40, 70, 200])  # one chunk of genome bits, one, two and four chunks
 def test_bins_mode_equals_sort_mode_and_oracle(engine, oracle, k, n_genomes):
     from khoice_b200 import synth
@@ -77,9 +77,9 @@ def test_bins_mode_equals_sort_mode_and_oracle(engine, oracle, k, n_genomes):
     assert engine.bins_counters["fallbacks"] == before["fallbacks"]
 
 
-def test_edge_inputs(engine, oracle):
+@pytest.mark.parametrize("k", [19, 45])
+def test_edge_inputs(engine, oracle, k):
     """Every edge FASTA of the suite as its own genome; empty genomes; a group without any k-mer."""
-    k = 19
     groups = [list(EDGE_FASTAS), [b"", b">only header\n", b"ACGT\n"], [EDGE_FASTAS[8]] * 3]
     flat = [f for grp in groups for f in grp]
     gid = [i for i, grp in enumerate(groups) for _ in grp]
@@ -88,12 +88,12 @@ def test_edge_inputs(engine, oracle):
     _check(res, w_ref, a_ref, st_ref, 3)
 
 
-def test_long_runs_are_split_into_several_records(engine, oracle):
+@pytest.mark.parametrize("k", [25, 51])
+def test_long_runs_are_split_into_several_records(engine, oracle, k):
     """Low-complexity sequence: thousands of consecutive windows share one minimizer, so a run is cut into records of at most
     65 - k (<= 32) windows and into pieces at tile boundaries; homopolymers and short tandem repeats also put one k-mer into a
     bin thousands of times."""
     rng = np.random.default_rng(11)
-    k = 25
     parts = [b">a\n" + b"A" * 30_000 + b"\n", b">b\n" + b"AC" * 9_000 + b"\n", b">c\n" + b"ACGGT" * 5_000 + b"\n",
              random_fasta(rng, 20_000), b">d\n" + b"T" * 10_000 + b"G" + b"T" * 10_000 + b"\n"]
     groups = [[b"".join(parts), parts[0] + parts[3], random_fasta(rng, 5_000)], [parts[1] + parts[2], parts[4]]]
@@ -104,12 +104,12 @@ def test_long_runs_are_split_into_several_records(engine, oracle):
     _check(res, w_ref, a_ref, st_ref, 2)
 
 
-def test_full_tables_are_redone_in_hash_classes(engine, oracle, monkeypatch):
+@pytest.mark.parametrize("k", [23, 37])
+def test_full_tables_are_redone_in_hash_classes(engine, oracle, monkeypatch, k):
     """Tiny tables (256 slots) and a planner told that records hold next to no distinct k-mers: every bin is tried in one pass,
     overflows its table and is redone by mb_bigbin_kernel, class by class.  Then the same tables with the planner's own estimate:
     the bins are counted in several hash classes inside the streaming kernel.  Same results either way."""
     rng = np.random.default_rng(12)
-    k = 23
     groups = [[random_fasta(rng, 150_000, n_records=2) for _ in range(3)], [random_fasta(rng, 40_000) for _ in range(70)]]
     flat = [f for grp in groups for f in grp]
     gid = [i for i, grp in enumerate(groups) for _ in grp]
@@ -128,8 +128,9 @@ def test_full_tables_are_redone_in_hash_classes(engine, oracle, monkeypatch):
     assert engine.bins_counters["fallbacks"] == before["fallbacks"]
 
 
-def test_region_overflow_falls_back_to_the_sort(engine, oracle, monkeypatch):
-    """Bin regions sized at 30 % of the expected records: the partition raises its flag and the group is redone by sorting."""
+def test_region_overflow_is_partitioned_again_with_exact_sizes(engine, oracle, monkeypatch):
+    """Bin regions sized at 30 % of the expected records: the partition raises its flag and the group is partitioned a second time into
+    regions of exactly the sizes the first attempt counted -- still without a sort."""
     rng = np.random.default_rng(13)
     k = 29
     groups = [[random_fasta(rng, 100_000) for _ in range(4)]]
@@ -141,7 +142,9 @@ def test_region_overflow_falls_back_to_the_sort(engine, oracle, monkeypatch):
         hists, stats, sets, ha, sta = _run_groups(engine, groups, k, nbins=32)
     finally:
         engine.set_group_mode("auto")
-    assert engine.bins_counters["fallbacks"] == before["fallbacks"] + 1
+    assert engine.bins_counters["repartitions"] == before["repartitions"] + 1
+    assert engine.bins_counters["fallbacks"] == before["fallbacks"]
+    assert stats[0]["passes_group"] == 0
     assert np.array_equal(hists[0], w_ref[0])
     assert np.array_equal(ha, a_ref)
     assert stats[0]["distinct"] == st_ref["sum_group_distinct"]
@@ -161,15 +164,16 @@ def test_tables_are_clean_between_groups(engine, oracle):
     assert np.array_equal(res["bins"][0][0], res["bins"][0][3])
 
 
-def test_config2_sized_group(engine, oracle):
-    """One config-2 group at full size (50 x 5 Mbp, k = 31) through the default mode against the CPU oracle."""
+@pytest.mark.parametrize("k", [31, 47])
+def test_config2_sized_group(engine, oracle, k):
+    """One config-2 group at full size (50 x 5 Mbp) through the default mode against the CPU oracle."""
     from khoice_b200 import synth
     cfg = synth.SynthConfig(n_groups=1, genomes_per_group=50, genome_len=5_000_000, seed=20240131)
     grp = [synth.make_genome(cfg, 1, i) for i in range(1, 51)]
-    w_ref, a_ref, st_ref = oracle.exp1(grp, [0] * 50, 1, 31, nbins=5000)
+    w_ref, a_ref, st_ref = oracle.exp1(grp, [0] * 50, 1, k, nbins=5000)
     engine.group_sets_reset()
     before = engine.bins_counters
-    h, st = engine.group_from_fasta(grp, 31, nbins=5000)
+    h, st = engine.group_from_fasta(grp, k, nbins=5000)
     assert st["passes_group"] == 0
     assert engine.bins_counters["fallbacks"] == before["fallbacks"]
     assert np.array_equal(h, w_ref[0])
