@@ -208,9 +208,17 @@ KERNEL_INFO = {
     "partition": ("partition / push kernels (K7)", "hbm"),
     "hash_insert": ("hash_insert_kernel", "hbm"),
     "hash_count": ("hash_count_kernel", "hbm"),
-    "bin_partition": ("bin_partition_kernel (minimizer bins: packed stream -> super-k-mer records)", "hbm"),
-    "bin_count": ("bin_count_kernel (one CTA per bin: shared-memory (k-mer, genome bits) table)", "hbm"),
-    "bin_across": ("bin_across_kernel (one CTA per bin over the groups' distinct keys)", "hbm"),
+    "bin_partition": ("mb_partition_kernel (minimizer bins: packed symbol stream -> super-k-mer records, csrc/bins.cu)", "hbm"),
+    "bin_count": ("mb_count_kernel (persistent CTAs, one bin at a time: distinct records, then a shared-memory (k-mer, genome bits) table, csrc/bins.cu)", "hbm"),
+}
+
+KERNEL_NOTE = {
+    "bin_count": "the minimizer-bin path moves ~2.4 bytes per window through HBM (24-byte super-k-mer records written and read once, 8 bytes per "
+                 "DISTINCT k-mer out) instead of ~100 for the prefix sort it replaced, so its HBM fraction is small by construction: the kernel is "
+                 "bound by shared-memory table work and instruction issue (profiles/r2_bin_count_top.txt); pipeline_roofline.survey_8d prices the "
+                 "same tables on SURVEY.md 8(d)'s byte contract",
+    "bin_partition": "bound by instruction issue (hashing 13-mers, sliding minimum, record emission), not HBM: it reads 3/8 byte and writes ~2.4 bytes "
+                     "per window (profiles/r2_bin_partition_top.txt)",
 }
 
 # bytes per input base of the KMC-shaped chain (sort, unique, sort, count per genome / group / across) at
@@ -604,6 +612,18 @@ def main():
         eq = bool(np.array_equal(h1.astype(np.int64), within_all[k][fg - 1, :nbins1]))
         parity["checks"].append({"group_of_rank_1_recomputed_on_rank_0": fg, "equal": eq})
         ok = ok and eq
+        # N>1: the CPU oracle on two sampled groups at full size -- one of rank 0's own and the one of rank 1 -- against the table all ranks built
+        if env_int("KHB_BENCH_ORACLE_GROUPS", 1) and not sweep:
+            from oracle import oracle as O
+            O.build()
+            O.set_num_threads(O.host_cores())
+            t_or = time.time()
+            for label, gnum, tx in (("own", mine[0], list(host_views[mine[0]])), ("of_rank_1", fg, texts)):
+                w_or, _, _ = O.exp1(tx, [0] * len(tx), 1, k)
+                eq = bool(np.array_equal(np.asarray(w_or[0][:nbins1], dtype=np.int64), within_all[k][gnum - 1, :nbins1]))
+                parity["checks"].append({"oracle_group": gnum, "which": label, "genomes": len(tx), "within_equal_oracle": eq})
+                ok = ok and eq
+            parity["oracle_seconds"] = round(time.time() - t_or, 1)
         foreign = None
 
     rc = 0
@@ -657,7 +677,8 @@ def main():
                          "traffic": (ratio * per_launch_alg) if ratio else None, "traffic_source": ratio_src,
                          "algorithmic_bytes_per_launch": per_launch_alg,
                          "launches": dk["launches"], "avg_launch_ms": dk["ms"] / max(dk["launches"], 1), "peak_source": peak_src,
-                         "share_of_step": dk["ms"] / ms_dev},
+                         "share_of_step": dk["ms"] / ms_dev,
+                         "note": KERNEL_NOTE.get(dom)},
             "pipeline_roofline": pipeline,
             "kernels": kernels,
             "clocks": clocks,

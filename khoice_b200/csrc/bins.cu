@@ -138,6 +138,8 @@ mb_partition_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid
     // phase 1: hash of the canonical m-mer at every symbol position of the tile (0 = not an m-mer)
     {
         const u32 sh = 32u - 2u * (u32)m, mask2m = (1u << (2 * m)) - 1u, ones_m = (1u << m) - 1u;
+        const u64 left = n_sym - tile0;            // symbols from the tile's first to the end of the stream
+        const u32 j_end = left >= (u64)NH + (u64)m ? NH : (left >= (u64)m ? (u32)(left - (u64)m) + 1u : 0u);   // m-mers start below j_end
         for (u32 j = tid; j < NH; j += MB_BLOCK) {
             const u32 t = j >> 4, s = (j & 15u) * 2u;
             const u32 x = __funnelshift_l(sc[t + 1], sc[t], s);
@@ -148,7 +150,7 @@ mb_partition_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid
             const u32 c = fwd < r ? fwd : r;
             const u32 vq = j >> 5;
             const u32 vv = __funnelshift_l(sv[vq + 1], sv[vq], j & 31u);
-            const bool ok = (vv >> (32 - m)) == ones_m && tile0 + j + (u64)m <= n_sym;
+            const bool ok = (vv >> (32 - m)) == ones_m && j < j_end;
             A[j] = ok ? mb_mix32(c) : 0u;
         }
     }
@@ -404,8 +406,8 @@ __device__ __forceinline__ void mb_or_mask(u64 *word, u64 mask)
 {
     u32 *bw = (u32 *)word;
     const u32 lo = (u32)mask, hi = (u32)(mask >> 32);
-    if (lo & ~*(volatile u32 *)bw) atomicOr(bw, lo);
-    if (hi & ~*(volatile u32 *)(bw + 1)) atomicOr(bw + 1, hi);
+    if (lo && (lo & ~*(volatile u32 *)bw)) atomicOr(bw, lo);
+    if (hi && (hi & ~*(volatile u32 *)(bw + 1))) atomicOr(bw + 1, hi);
 }
 
 // Shared-memory carve-up of the counting kernels (dynamic): k-mer table (keys, 64 genome bits, counts when there are more genomes), the ring
