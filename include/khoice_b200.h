@@ -281,26 +281,15 @@ KHB_API int khb_read_votes(khb_ctx *ctx, const uint64_t *d_index, const uint64_t
                    const uint64_t *d_read_first, const uint32_t *d_read_nwin, uint64_t n_reads, double *d_votes,
                    uint32_t *d_unmatched);
 
-/* EXPERIMENTAL (the next design step; used by no product path yet): count pass of the minimizer
- * partition.  For every k-mer window of a packed stream (the windows khb_extract_kmers emits) the bin of its minimizer --
- * minimum over the window's canonical m-mers of a 64-bit mix, re-mixed, top log2_bins bits (tests/test_gpu_superkmer.py) -- and per
- * bin the number of windows and of super-k-mer RECORDS (maximal runs of consecutive windows with one bin, cut every
- * KHB_SUPERKMER_TILE windows; a run of more than 65 - k windows counts as several records).  1 <= m <= k <= 32.  d_bin_windows / d_bin_superkmers: uint32 [1 << log2_bins]. */
-#define KHB_SUPERKMER_TILE 4352
-KHB_API int khb_superkmer_count(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, uint64_t n_symbols, int k, int m,
-                        int log2_bins, uint32_t *d_bin_windows, uint32_t *d_bin_superkmers);
-/* EXPERIMENTAL: the whole group stage through minimizer bins -- count pass, scatter of (canonical k-mer, genome) records into
- * their bins, one CTA per bin counting in a shared-memory table.  <= 64 genomes, k <= 32.  h_hist[nbins + 1] as
- * khb_group_from_*; h_totals[3] = distinct k-mers, sum of the per-genome set sizes, bins whose table overflowed (counts are
- * then incomplete); h_ms[3] = device time of the three passes.  d_seg_off: symbol offset of every genome, n_genomes + 1. */
-KHB_API int khb_superkmer_group(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, uint64_t n_symbols,
-                        const uint64_t *d_seg_off, int n_genomes, int k, int m, int log2_bins, uint32_t nbins,
-                        uint64_t *h_hist, uint64_t *h_totals, float *h_ms);
-/* EXPERIMENTAL: the same with 24-byte super-k-mer records in the bins (genome, length, 64 symbols; runs longer than 65 - k
- * windows are several records) instead of expanded k-mers; the per-bin kernel expands them in registers.  2 <= k <= 32. */
-KHB_API int khb_superkmer_group_compact(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, uint64_t n_symbols,
-                                const uint64_t *d_seg_off, int n_genomes, int k, int m, int log2_bins, uint32_t nbins,
-                                uint64_t *h_hist, uint64_t *h_totals, float *h_ms);
+/* The first pass of the minimizer-bin group stage (bins.cu) on its own, for tests: partition the k-mer windows of a packed stream
+ * (the windows khb_extract_kmers emits) into n_bins bins by minimizer -- the minimum over a window's canonical 13-mers of a 32-bit
+ * hash, re-mixed, scaled to [0, n_bins) -- as super-k-mer records: maximal runs of consecutive windows with one minimum, cut at every
+ * multiple of KHB_BINS_TILE window starts and into pieces of at most 32 windows.  Region r = bin * ceil(n_genomes / 64) + genome / 64.
+ * h_records[r] / h_windows[r]: records and windows of every region (the test suite states the same rules in numpy).
+ * 17 <= k <= 63, k != 32.  d_seg_off: symbol offset of every genome, n_genomes + 1 entries, device memory. */
+#define KHB_BINS_TILE 4096
+KHB_API int khb_bins_partition(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, uint64_t n_symbols,
+                       const uint64_t *d_seg_off, int n_genomes, int k, uint32_t n_bins, uint32_t *h_records, uint32_t *h_windows);
 
 /* K7: split n keys into n_parts buckets by splitmix64(key) % n_parts (multi-GPU hash-range partition of the
  * k-mer space).  d_out receives the keys grouped by bucket, h_part_off[n_parts+1] the bucket offsets. */

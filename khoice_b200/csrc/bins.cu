@@ -1146,3 +1146,57 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
     }
     return KHB_OK;
 }
+
+// ---- the partition alone, for the intermediate-level parity test (tests/test_gpu_bins.py: the same rules stated in numpy) -----------
+__global__ void __launch_bounds__(256)
+mb_region_windows_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u64 n_regions, u32 cap, int rec_words, u32 *__restrict__ windows)
+{
+    const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_regions) return;
+    const u32 n = cursor[r] < cap ? cursor[r] : cap;
+    u32 wsum = 0;
+    for (u32 i = 0; i < n; i++) wsum += (u32)(rec[(r * cap + i) * rec_words] >> 40) & 0xffu;
+    windows[r] = wsum;
+}
+
+extern "C" KHB_API int khb_bins_partition(khb_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, uint64_t n_symbols,
+                                                                       const uint64_t *d_seg_off, int n_genomes, int k, uint32_t n_bins,
+                                                                       uint32_t *h_records, uint32_t *h_windows)
+{
+    KHB_CHECK_CTX(ctx);
+    if (!khb_bins_eligible(k, n_genomes, n_symbols ? n_symbols : 1) || n_bins < 1 || n_bins > (1u << 22) || !h_records || !h_windows || !d_seg_off)
+        return khb_fail(ctx, KHB_ERR_ARG, "khb_bins_partition: 17 <= k <= 63 (k != 32), 1 .. 2^22 bins");
+    const int KW = k <= 32 ? 2 : 3, m = 13, w = k - m + 1;
+    const u32 capw = (u32)(32 * KW + 1 - k) < MB_MAXW ? (u32)(32 * KW + 1 - k) : MB_MAXW;
+    const u32 nchunks = (u32)div_up((size_t)n_genomes, 64);
+    const u64 n_regions = (u64)n_bins * nchunks;
+    double avg_len = (w + 1) * 0.5;
+    if (avg_len > capw) avg_len = capw;
+    const u32 cap = ((u32)((double)n_symbols / avg_len * 1.15 / (double)n_regions * 8.0) + 256u) & ~1u;
+    int rc;
+    void *p, *pr;
+    if ((rc = khb_scratch_get(ctx, SCR_AUX, n_regions * 8 + 64, &p))) return rc;
+    if ((rc = khb_scratch_get(ctx, SCR_KEYS_A, n_regions * cap * (size_t)(KW + 1) * 8 + 64, &pr))) return rc;
+    u32 *d_cur = (u32 *)p, *d_win = d_cur + n_regions;
+    u64 *d_flag = (u64 *)(d_win + n_regions);
+    KHB_CUDA(ctx, cudaMemsetAsync(p, 0, n_regions * 8 + 64, ctx->stream));
+    if (n_symbols) {
+        const u64 tiles = div_up(n_symbols, MB_TILE), last_w = n_symbols / 32 + 3;
+        if (KW == 2)
+            mb_partition_kernel<2><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>((const u64 *)d_codes, d_valid, n_symbols, last_w, last_w, k, m, n_bins, (const u64 *)d_seg_off,
+                                                                                  n_genomes, nchunks, d_cur, (u64 *)pr, cap, capw, nullptr, d_flag);
+        else
+            mb_partition_kernel<3><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>((const u64 *)d_codes, d_valid, n_symbols, last_w, last_w, k, m, n_bins, (const u64 *)d_seg_off,
+                                                                                  n_genomes, nchunks, d_cur, (u64 *)pr, cap, capw, nullptr, d_flag);
+        KHB_LAUNCH_CHECK(ctx);
+        mb_region_windows_kernel<<<(unsigned)div_up(n_regions, 256), 256, 0, ctx->stream>>>((const u64 *)pr, d_cur, n_regions, cap, KW + 1, d_win);
+        KHB_LAUNCH_CHECK(ctx);
+    }
+    u64 flag = 0;
+    KHB_CUDA(ctx, cudaMemcpyAsync(h_records, d_cur, n_regions * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    KHB_CUDA(ctx, cudaMemcpyAsync(h_windows, d_win, n_regions * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    KHB_CUDA(ctx, cudaMemcpyAsync(&flag, d_flag, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flag) return khb_fail(ctx, KHB_ERR_STATE, "khb_bins_partition: a region overflowed its diagnostic buffer");
+    return KHB_OK;
+}

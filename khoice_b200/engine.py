@@ -102,9 +102,7 @@ _SIGNATURES = [
     ("khb_group_membership", C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int]),
     ("khb_partition_by_hash", C.c_int, [_P, _P, C.c_uint64, C.c_int, C.c_int, _P, _P]),
     ("khb_read_votes", C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_uint64, _P, _P]),
-    ("khb_superkmer_count", C.c_int, [_P, _P, _P, C.c_uint64, C.c_int, C.c_int, C.c_int, _P, _P]),
-    ("khb_superkmer_group", C.c_int, [_P, _P, _P, C.c_uint64, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, _P, _P, _P]),
-    ("khb_superkmer_group_compact", C.c_int, [_P, _P, _P, C.c_uint64, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, _P, _P, _P]),
+    ("khb_bins_partition", C.c_int, [_P, _P, _P, C.c_uint64, _P, C.c_int, C.c_int, C.c_uint32, _P, _P]),
     ("khb_peer_alloc", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_uint64, _P]),
     ("khb_peer_open", C.c_int, [_P, _P]),
     ("khb_peer_begin", C.c_int, [_P]),
@@ -639,25 +637,10 @@ class Engine:
             for b in bufs:
                 b.free()
 
-    def superkmer_count(self, packed: dict, k: int, m: int, log2_bins: int):
-        """EXPERIMENTAL: per minimizer bin the number of k-mer windows and of super-k-mers of a packed
-        stream (pack_fasta).  Returns (windows uint32 [2^log2_bins], superkmers uint32 [2^log2_bins], device ms)."""
-        nb = 1 << log2_bins
-        dw, ds = self.alloc(nb * 4), self.alloc(nb * 4)
-        try:
-            import time
-            self.sync()
-            t0 = time.perf_counter()
-            self._chk(self.lib.khb_superkmer_count(self.ctx, packed["codes"].ptr, packed["valid"].ptr, packed["n_symbols"], k, m, log2_bins, dw.ptr, ds.ptr))
-            self.sync()
-            ms = (time.perf_counter() - t0) * 1e3
-            return dw.download(np.uint32, nb), ds.download(np.uint32, nb), ms
-        finally:
-            dw.free(); ds.free()
-
-    def superkmer_group(self, files: Sequence, k: int, m: int, log2_bins: int, nbins: int = 64, compact: bool = False):
-        """EXPERIMENTAL: the group stage through minimizer bins.  Returns (histogram uint64[nbins+1],
-        dict(distinct, genome_distinct, overflowed_bins, ms_count, ms_scatter, ms_bins))."""
+    def bins_partition(self, files: Sequence, k: int, n_bins: int):
+        """The partition pass of the minimizer-bin group stage on its own (include/khoice_b200.h: khb_bins_partition).
+        Returns (records uint32 [n_bins, chunks], windows uint32 [n_bins, chunks], first symbol of every genome in the group's stream),
+        chunks = ceil(len(files) / 64)."""
         staged = self.stage_fasta(files)
         packed = self.pack_fasta(staged)
         n = len(staged.begin) - 1
@@ -669,14 +652,12 @@ class Engine:
         d_seg = self.alloc((n + 1) * 8)
         try:
             d_seg.upload(seg)
-            hist = np.zeros(nbins + 1, dtype=np.uint64)
-            tot = np.zeros(3, dtype=np.uint64)
-            ms = np.zeros(3, dtype=np.float32)
-            fn = self.lib.khb_superkmer_group_compact if compact else self.lib.khb_superkmer_group
-            self._chk(fn(self.ctx, packed["codes"].ptr, packed["valid"].ptr, packed["n_symbols"], d_seg.ptr, n, k, m, log2_bins,
-                                                   nbins, hist.ctypes.data, tot.ctypes.data, ms.ctypes.data))
-            return hist, {"distinct": int(tot[0]), "genome_distinct": int(tot[1]), "overflowed_bins": int(tot[2]),
-                          "ms_count": float(ms[0]), "ms_scatter": float(ms[1]), "ms_bins": float(ms[2])}
+            chunks = (n + 63) // 64
+            rec = np.zeros(n_bins * chunks, dtype=np.uint32)
+            win = np.zeros(n_bins * chunks, dtype=np.uint32)
+            self._chk(self.lib.khb_bins_partition(self.ctx, packed["codes"].ptr, packed["valid"].ptr, packed["n_symbols"], d_seg.ptr, n, k, n_bins,
+                                                  rec.ctypes.data, win.ctypes.data))
+            return rec.reshape(n_bins, chunks), win.reshape(n_bins, chunks), seg[:n].astype(np.int64)
         finally:
             for b in (d_seg, staged.buf, packed["codes"], packed["valid"]):
                 b.free()

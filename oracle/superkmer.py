@@ -1,15 +1,17 @@
-"""TEST INFRASTRUCTURE (like everything under oracle/): the reference statement of the NEXT design step named in DESIGN.md
-section 7 -- partition the k-mer windows of a genome by minimizer into bins, as super-k-mers -- so that the CUDA kernels of
-that step can be checked bit for bit from their first version on.  Nothing under khoice_b200/ uses this.
+"""TEST INFRASTRUCTURE (like everything under oracle/): the numpy statement of the FIRST pass of the minimizer-bin group stage
+(khoice_b200/csrc/bins.cu) -- partition the k-mer windows of a genome by minimizer into bins, as super-k-mer records -- so that the
+CUDA partition can be checked on its own, bit for bit, below the level of the histograms.  Nothing under khoice_b200/ uses this.
 
 Semantics of the windows are the oracle's (rules R1-R5 of SURVEY.md 8c, the reference's `kmc -fm` call sites
 /root/reference/workflow/rules/exp_type_1.smk:156-163): symbols `ACGTacgt` are valid, anything else breaks the window,
 windows never span `>` records, the k-mer value is base 4 with the first base most significant, canonical = min(k-mer,
-reverse complement).  On top of that, for a window with canonical m-mers c_0 .. c_{k-m} (m <= 32, m <= k <= 64):
+reverse complement).  On top of that, for a window with canonical m-mers c_0 .. c_{k-m} (m = 13, 13 <= k <= 64):
 
-    minimizer hash   H = min_j  mix(c_j)            mix(x) = ((x ^ (x >> 15)) * 0x9E3779B97F4A7C15) ^ (... >> 29), 64-bit
-    bin              b = (H * 0xD6E8FEB86659FD93 mod 2^64) >> (64 - log2_bins)
-    super-k-mer      a maximal run of CONSECUTIVE windows (symbol positions i, i+1, ...) that are all valid and share b
+    minimizer hash   H = min_j  mix32(c_j)          32-bit: x *= 0x9E3779B1; x ^= x >> 15; x *= 0x85EBCA77; x ^= x >> 13;
+                                                    x *= 0xC2B2AE3D; x ^= x >> 16; x |= 1   (0 is kept for "no m-mer")
+    bin              b = (B * n_bins) >> 32          B = H * 0xD6E8FEB9; B ^= B >> 16; B *= 0x7FEB352D   (mod 2^32)
+    super-k-mer      a maximal run of CONSECUTIVE windows (symbol positions i, i+1, ...) that are all valid and share H,
+    record           ... cut at every multiple of 4096 window starts (the kernel's tiles) and into pieces of <= 32 windows
 
 The bin is a function of the window's sequence content up to strand -- the same k-mer lands in the same bin in every
 genome and on both strands -- which is what lets a bin be counted independently of all others."""
@@ -20,13 +22,27 @@ from typing import List, Tuple
 import numpy as np
 
 U = np.uint64
-MIX_C = U(0x9E3779B97F4A7C15)
-BIN_C = U(0xD6E8FEB86659FD93)
+M = 13
+TILE = 4096
+CAPW = 32
+_M32 = U(0xFFFFFFFF)
 
 
-def mix(x: np.ndarray) -> np.ndarray:
-    x = (x ^ (x >> U(15))) * MIX_C
-    return x ^ (x >> U(29))
+def mix32(x: np.ndarray) -> np.ndarray:
+    x = (x.astype(U) * U(0x9E3779B1)) & _M32
+    x ^= x >> U(15)
+    x = (x * U(0x85EBCA77)) & _M32
+    x ^= x >> U(13)
+    x = (x * U(0xC2B2AE3D)) & _M32
+    x ^= x >> U(16)
+    return x | U(1)
+
+
+def bin_of(minhash: np.ndarray, n_bins: int) -> np.ndarray:
+    b = (minhash.astype(U) * U(0xD6E8FEB9)) & _M32
+    b ^= b >> U(16)
+    b = (b * U(0x7FEB352D)) & _M32
+    return ((b * U(n_bins)) >> U(32)).astype(np.int64)
 
 
 def symbol_stream(fasta: bytes) -> Tuple[np.ndarray, np.ndarray]:
@@ -86,17 +102,17 @@ def _all_valid(valid: np.ndarray, length: int) -> np.ndarray:
     return (cs[length:length + n] - cs[:n]) == length
 
 
-def window_bins(fasta: bytes, k: int, m: int, log2_bins: int):
-    """Per symbol position i (a window start): (ok bool, canonical k-mer, bin int64); entries with ok False are undefined.
-    The k-mer column is uint64 [n] for k <= 32 and uint64 [n, 2] (lo, hi) for 33 <= k <= 64 (the oracle's own layout, taken
-    from oracle.kmers, which lists the valid windows in stream order); the minimizer length m stays <= 32."""
-    if not (1 <= m <= min(k, 32) and k <= 64 and 1 <= log2_bins <= 32):
-        raise ValueError("1 <= m <= min(k, 32), k <= 64 and 1 <= log2_bins <= 32")
+def window_bins(fasta: bytes, k: int, n_bins: int, m: int = M):
+    """Per symbol position i (a window start): (ok bool, canonical k-mer, minimizer hash uint64, bin int64); entries with ok False
+    are undefined.  The k-mer column is uint64 [n] for k <= 32 and uint64 [n, 2] (lo, hi) for 33 <= k <= 64 (the oracle's own
+    layout, taken from oracle.kmers, which lists the valid windows in stream order)."""
+    if not (1 <= m <= min(k, 15) and k <= 64 and n_bins >= 1):
+        raise ValueError("1 <= m <= min(k, 15), k <= 64 and n_bins >= 1")
     code, valid = symbol_stream(fasta)
     ok = _all_valid(valid, k)
     n = ok.size
     if n == 0:
-        return ok, np.zeros((0,) if k <= 32 else (0, 2), U), np.zeros(0, np.int64)
+        return ok, np.zeros((0,) if k <= 32 else (0, 2), U), np.zeros(0, U), np.zeros(0, np.int64)
     if k <= 32:
         kmer = _canonical_values(code, k)
     else:
@@ -104,41 +120,61 @@ def window_bins(fasta: bytes, k: int, m: int, log2_bins: int):
         keys, _ = O.kmers(fasta, k)
         kmer = np.zeros((n, 2), dtype=U)
         kmer[ok] = keys
-    hm = mix(_canonical_values(code, m))          # per m-mer position; only positions inside valid windows are ever used
+    hm = mix32(_canonical_values(code, m))        # per m-mer position; only positions inside valid windows are ever used
     w = k - m + 1
     best = hm[:n].copy()
     for j in range(1, w):
         best = np.minimum(best, hm[j:n + j])
-    bins = ((best * BIN_C) >> U(64 - log2_bins)).astype(np.int64)
-    return ok, kmer, bins
+    return ok, kmer, best, bin_of(best, n_bins)
 
 
-def superkmers(fasta: bytes, k: int, m: int, log2_bins: int, tile: int = 0) -> List[Tuple[int, int, int]]:
-    """[(bin, first symbol position, number of windows)] in stream order.  tile > 0: runs are also cut at every multiple of
-    `tile` symbol positions (the CUDA kernel works tile by tile: KHB_SUPERKMER_TILE)."""
-    ok, _, bins = window_bins(fasta, k, m, log2_bins)
-    n = ok.size
-    if n == 0:
-        return []
+def records(fasta: bytes, k: int, n_bins: int, first_symbol: int = 0, m: int = M, tile: int = TILE, capw: int = CAPW) -> List[Tuple[int, int, int]]:
+    """[(bin, first symbol position, number of windows)] in stream order: the records the partition kernel writes for this genome when
+    its symbols start at position `first_symbol` of the group's stream (runs are cut where first_symbol + position is a multiple of
+    `tile`, and into pieces of at most `capw` windows)."""
+    ok, _, mh, bins = window_bins(fasta, k, n_bins, m)
     idx = np.flatnonzero(ok)
     if idx.size == 0:
         return []
     brk = np.ones(idx.size, dtype=bool)
-    brk[1:] = (np.diff(idx) != 1) | (bins[idx][1:] != bins[idx][:-1])
+    brk[1:] = (np.diff(idx) != 1) | (mh[idx][1:] != mh[idx][:-1])
     if tile > 0:
-        brk |= (idx % tile) == 0
+        brk |= ((idx + first_symbol) % tile) == 0
     starts = idx[brk]
     ends = np.concatenate([idx[np.flatnonzero(brk)[1:] - 1], idx[-1:]])
-    return [(int(bins[s]), int(s), int(e - s + 1)) for s, e in zip(starts, ends)]
+    out = []
+    for s0, e0 in zip(starts.tolist(), ends.tolist()):
+        n = e0 - s0 + 1
+        for p in range(0, n, capw):
+            out.append((int(bins[s0]), s0 + p, min(capw, n - p)))
+    return out
 
 
-def binned_group_histogram(genomes, k: int, m: int, log2_bins: int, nbins: int = 5000):
+def region_counts(genomes, first_symbols, k: int, n_bins: int):
+    """(records, windows), each int64 [n_bins, ceil(len(genomes) / 64)]: what the partition kernel leaves in every region (one region per
+    bin and chunk of 64 genomes) for a group whose genome g starts at symbol first_symbols[g] of the group's stream."""
+    chunks = (len(genomes) + 63) // 64
+    rec = np.zeros((n_bins, max(chunks, 1)), dtype=np.int64)
+    win = np.zeros((n_bins, max(chunks, 1)), dtype=np.int64)
+    for g, text in enumerate(genomes):
+        for b, _, n in records(text, k, n_bins, int(first_symbols[g])):
+            rec[b, g // 64] += 1
+            win[b, g // 64] += n
+    return rec, win
+
+
+def superkmers(fasta: bytes, k: int, n_bins: int, m: int = M) -> List[Tuple[int, int, int]]:
+    """[(bin, first symbol position, number of windows)]: the maximal runs themselves (no tile cuts, no length limit)."""
+    return records(fasta, k, n_bins, 0, m, tile=0, capw=1 << 30)
+
+
+def binned_group_histogram(genomes, k: int, n_bins: int, nbins: int = 5000, m: int = M):
     """The group stage computed BIN BY BIN: hist[c] = number of distinct k-mers found in exactly c genomes, and the group's
     distinct k-mers per bin.  Must equal oracle.exp1's within-group histogram (tests/test_superkmer_oracle.py)."""
     per_bin = {}
     uniq = (lambda a: np.unique(a)) if k <= 32 else (lambda a: np.unique(a, axis=0))
     for g, text in enumerate(genomes):
-        ok, kmer, bins = window_bins(text, k, m, log2_bins)
+        ok, kmer, _, bins = window_bins(text, k, n_bins, m)
         for b in np.unique(bins[ok]):
             per_bin.setdefault(int(b), []).append((g, uniq(kmer[ok & (bins == b)])))
     hist = np.zeros(nbins + 1, dtype=np.uint64)

@@ -180,3 +180,20 @@ def test_config2_sized_group(engine, oracle, k):
     assert st["distinct"] == st_ref["sum_group_distinct"]
     ha, sta = engine.across_groups(nbins=5000)
     assert np.array_equal(ha, a_ref)
+
+
+@pytest.mark.parametrize("k,n_genomes,n_bins", [(31, 5, 97), (17, 3, 16), (24, 70, 64), (47, 4, 33), (63, 66, 50)])
+def test_partition_against_its_numpy_statement(engine, k, n_genomes, n_bins):
+    """The first pass alone: per region (bin, chunk of 64 genomes) the records and the windows the kernel wrote, against oracle/superkmer.py
+    (minimizer hash, bin function, runs of one minimum, cuts at 4096-window tiles and at 32 windows) -- bit for bit."""
+    from khoice_b200 import synth
+    from oracle import superkmer as S
+    cfg = synth.SynthConfig(n_groups=1, genomes_per_group=n_genomes, genome_len=12_000, seed=900 + k)
+    genomes = [synth.make_genome(cfg, 1, i) for i in range(1, n_genomes + 1)]
+    genomes[1] = genomes[1] + EDGE_FASTAS[1] + EDGE_FASTAS[3] + EDGE_FASTAS[8] + b">poly\n" + b"A" * 9000 + b"\n"
+    genomes[-1] = b""
+    rec, win, first = engine.bins_partition(genomes, k, n_bins)
+    rec_ref, win_ref = S.region_counts(genomes, first, k, n_bins)
+    assert np.array_equal(win.astype(np.int64), win_ref)
+    assert np.array_equal(rec.astype(np.int64), rec_ref)
+    assert int(win.sum()) > 0
