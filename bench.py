@@ -210,6 +210,7 @@ KERNEL_INFO = {
     "hash_count": ("hash_count_kernel", "hbm"),
     "bin_partition": ("mb_partition_kernel (minimizer bins: packed symbol stream -> super-k-mer records, csrc/bins.cu)", "hbm"),
     "bin_count": ("mb_count_kernel (persistent CTAs, one bin at a time: distinct records, then a shared-memory (k-mer, genome bits) table, csrc/bins.cu)", "hbm"),
+    "bin_across": ("mb_across_kernel (across-group stage bin by bin over the groups' key segments, csrc/bins.cu)", "hbm"),
 }
 
 KERNEL_NOTE = {

@@ -76,6 +76,7 @@ KHB_API void *khb_stream(khb_ctx *ctx);                /* the cudaStream_t all w
 #define KHB_KERNEL_HASH_COUNT 8  /* hash_count_kernel: table scan -> histogram + group set */
 #define KHB_KERNEL_BIN_PARTITION 9 /* mb_partition_kernel: symbol stream -> super-k-mer records in minimizer bins (bins.cu) */
 #define KHB_KERNEL_BIN_COUNT 10    /* mb_count_kernel: per-bin shared-memory counting -> histogram + group set */
+#define KHB_KERNEL_BIN_ACROSS 11   /* across-group stage bin by bin: segment events ordered by bin + mb_across_kernel (one record per call) */
 KHB_API int khb_profile_enable(khb_ctx *ctx, int on);
 KHB_API int khb_profile_read(khb_ctx *ctx, int kernel_id, uint64_t *launches, double *ms, uint64_t *alg_bytes);
 
@@ -218,6 +219,10 @@ KHB_API uint64_t khb_hash_overflows(const khb_ctx *ctx);
  * memory), bins it redid in hash classes after their table filled up, groups it partitioned a second time with exact
  * region sizes because a bin region overflowed. */
 KHB_API void khb_bins_counters(const khb_ctx *ctx, uint64_t *fallbacks, uint64_t *big_bins, uint64_t *repartitions);
+/* How khb_across_groups ran so far: bin by bin over the segments the groups' end-of-bin passes left in the store (every retained
+ * group came through the minimizer bins with the same number of bins; only with KHB_ACROSS_MODE=bins in the environment of the first
+ * call -- measured slower than the sort), or by the prefix sort of the store (default). */
+KHB_API void khb_across_counters(const khb_ctx *ctx, uint64_t *by_bins, uint64_t *by_sort);
 
 /* Across-group union-sum + histogram over the retained group sets: rules across_group_union and
  * across_group_union_histogram (exp_type_1.smk:243-259) for one k. */

@@ -30,7 +30,9 @@ int khb_presence_count_impl(khb_ctx *, const u64 *, const u32 *, size_t, int, in
                             void *, u64 *);
 size_t khb_hash_table_bytes(int, int, u64, int *, int *);
 int khb_bins_eligible(int, int, u64);
-int khb_bins_count_impl(khb_ctx *, const u64 *, const u32 *, u64, int, const u64 *, int, u32, u32, u64 *, void *, u64 *, u64 *, u64 *, int);
+int khb_bins_count_impl(khb_ctx *, const u64 *, const u32 *, u64, int, const u64 *, int, u32, u32, u64 *, void *, u64 *, u64 *, u64 *, int, u32, u32 *, void *, u64 *, u64,
+                        u64);
+int khb_bins_across_impl(khb_ctx *, int, const void *, const void *, u64, u32, int, u32, u32, u64 *, u64 *, u64 *);
 int khb_hash_count_impl(khb_ctx *, const u64 *, const u32 *, u64, int, const u64 *, const u64 *, int, u32 *, int, int, u32, u32, u64 *, void *, u64 *, u64 *, int,
                         void *, u64 *, u32 *);
 int khb_peer_regions(khb_ctx *, const void **, u64 *, int *, int *);
@@ -631,6 +633,37 @@ static int pv_reserve(khb_ctx *ctx, int k, u64 extra)
     return KHB_OK;
 }
 
+// Room for `extra` more segment events (bins.cu: mb_event, 16 bytes each) behind the ev_len logged so far.
+static int ev_reserve(khb_ctx *ctx, u64 extra)
+{
+    if (!ctx->ev_count) {
+        KHB_CUDA(ctx, cudaMalloc((void **)&ctx->ev_count, 64));
+        KHB_CUDA(ctx, cudaMemsetAsync(ctx->ev_count, 0, 64, ctx->stream));
+    }
+    const u64 need = ctx->ev_len + extra;
+    if (need <= ctx->ev_cap) return KHB_OK;
+    u64 cap = ctx->ev_cap ? ctx->ev_cap : (1u << 16);
+    while (cap < need) cap += cap / 2;
+    void *nb = nullptr;
+    if (cudaMalloc(&nb, cap * 16) != cudaSuccess) {
+        cudaGetLastError();
+        return khb_fail(ctx, KHB_ERR_NOMEM, "segment events: device allocation of %llu bytes failed", (unsigned long long)(cap * 16));
+    }
+    if (ctx->ev_len) KHB_CUDA(ctx, cudaMemcpyAsync(nb, ctx->ev_buf, ctx->ev_len * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->ev_buf) KHB_CUDA(ctx, cudaFree(ctx->ev_buf));
+    ctx->ev_buf = nb;
+    ctx->ev_cap = cap;
+    return KHB_OK;
+}
+static void ev_forget(khb_ctx *ctx)
+{
+    ctx->ev_ok = 0;
+    ctx->ev_len = 0;
+    ctx->ev_nb = 0;
+    if (ctx->ev_count) cudaMemsetAsync(ctx->ev_count, 0, 8, ctx->stream);
+}
+
 struct PhaseTimer {
     khb_ctx *ctx;
     cudaEvent_t ev[12];
@@ -802,14 +835,29 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
         bool use_bins = !small_k && !use_hash && hashed && !pivot && (ctx->group_mode == KHB_GROUP_AUTO || ctx->group_mode == KHB_GROUP_BINS) &&
                         khb_bins_eligible(k, n_genomes, n_sym);
         int bins_exact = 0;
+        // the store's segment events (across-group stage bin by bin): kept while every retained group comes through the bins
+        const bool log_events = use_bins && keep_set && (ctx->gs_len == 0 || ctx->ev_ok);
+        u32 bins_nb = 0;
+        if (keep_set && ctx->gs_len == 0) {
+            ev_forget(ctx);
+            ctx->ev_ok = log_events ? 1 : 0;
+        }
+        if (keep_set && !log_events) ctx->ev_ok = 0;
       again:
         if (use_bins) {
             tm.mark();  // 3
             tm.mark();  // 4
             tm.mark();  // 5
             tm.mark();  // 6
+            const bool ev = log_events && ctx->ev_ok;
+            if (ev) {
+                if ((rc = ev_reserve(ctx, (u64)(ctx->ev_nb ? ctx->ev_nb : n_sym / 1024 + 16) * 8 + 4096))) return rc;
+                if (bins_exact) KHB_CUDA(ctx, cudaMemcpyAsync(ctx->ev_count, &ctx->ev_len, 8, cudaMemcpyHostToDevice, ctx->stream));   // forget the failed attempt's events
+            }
             if ((rc = khb_bins_count_impl(ctx, d_codes, d_valid, n_sym, k, d_seg, n_genomes, KHB_COUNTER_MAX, nbins, d_hist, out_keys, d_runs, d_pairs,
-                                          ctx->d_mail + 3, bins_exact))) return rc;
+                                          ctx->d_mail + 3, bins_exact, ev ? ctx->ev_nb : 0u, &bins_nb, ev ? ctx->ev_buf : nullptr, ctx->ev_count, ctx->ev_cap,
+                                          ctx->gs_len))) return rc;
+            if (ev) KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 130000, ctx->ev_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
         } else if (use_hash) {
             u32 *tab = nullptr;
             if ((rc = hash_table_get(ctx, hs_bytes, &tab))) return rc;
@@ -860,19 +908,28 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
         tm.mark();  // 7: count done
         KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (use_bins) {
-            if (ctx->h_mail[3] == 1 && !bins_exact) {
+            if ((ctx->h_mail[3] & 3) == 1 && !bins_exact) {
                 // a region outgrew its share of the record buffer (uneven minimizers): partition again with the sizes just counted
                 ctx->bins_repartitions++;
                 bins_exact = 1;
                 tm.n = 3;
                 goto again;
             }
-            if (ctx->h_mail[3]) {
+            if (ctx->h_mail[3] & 3) {
                 // a bin could not be counted in shared memory at all: redo this group by sorting
                 ctx->bins_fallbacks++;
                 use_bins = false;
+                if (keep_set) ctx->ev_ok = 0;
                 tm.n = 3;
                 goto again;
+            }
+            if (log_events && ctx->ev_ok) {
+                if (ctx->h_mail[3] & 4) {
+                    ctx->ev_ok = 0;                      // more segments than reserved: the across stage sorts
+                } else {
+                    ctx->ev_len = ctx->h_mail[130000];
+                    ctx->ev_nb = bins_nb;
+                }
             }
             ctx->bins_bigbins += ctx->h_mail[5];
             ctx->bins_hint_k = k;
@@ -1225,6 +1282,11 @@ int khb_set_group_mode(khb_ctx *ctx, int mode)
 }
 
 uint64_t khb_hash_overflows(const khb_ctx *ctx) { return ctx ? ctx->hs_overflows : 0; }
+void khb_across_counters(const khb_ctx *ctx, uint64_t *by_bins, uint64_t *by_sort)
+{
+    if (by_bins) *by_bins = ctx ? ctx->across_by_bins : 0;
+    if (by_sort) *by_sort = ctx ? ctx->across_by_sort : 0;
+}
 void khb_bins_counters(const khb_ctx *ctx, uint64_t *fallbacks, uint64_t *big_bins, uint64_t *repartitions)
 {
     if (fallbacks) *fallbacks = ctx ? ctx->bins_fallbacks : 0;
@@ -1247,6 +1309,38 @@ int khb_across_groups(khb_ctx *ctx, uint32_t nbins, uint64_t *h_hist, khb_stats 
     if (rc) return rc;
     PhaseTimer tm(ctx);
     tm.mark();
+    static int across_bins = -1;
+    if (across_bins < 0) {
+        const char *e = getenv("KHB_ACROSS_MODE");   // bins: count bin by bin where the store allows it (measured slower than the sort: opt-in)
+        across_bins = e && strcmp(e, "bins") == 0 ? 1 : 0;
+    }
+    if (across_bins && ctx->ev_ok && ctx->ev_len && ctx->ev_nb && ctx->gs_hashed) {
+        // every group came through the minimizer bins: count bin by bin over the segments they left (bins.cu), no sort -- 15.3 ms against
+        // the sort's 12.8 ms at config 2 (profiles/r2_bench_history.md), so only on request
+        u64 *d_hist = ctx->d_mail + 8, *d_runs = ctx->d_mail;
+        if ((rc = khb_bins_across_impl(ctx, k, ctx->gs_buf, ctx->ev_buf, ctx->ev_len, ctx->ev_nb, ctx->gs_groups, KHB_COUNTER_MAX, nbins, d_hist, d_runs,
+                                       ctx->d_mail + 3))) return rc;
+        KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, ctx->d_mail, (nbins + 9) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        tm.mark();
+        tm.mark();
+        KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!ctx->h_mail[3]) {
+            ctx->across_by_bins++;
+            memcpy(h_hist, ctx->h_mail + 8, ((size_t)nbins + 1) * sizeof(u64));
+            if (stats) {
+                stats->windows = n;
+                stats->genome_distinct = n;
+                stats->distinct = ctx->h_mail[0];
+                stats->ms_count = tm.ms(0, 1);
+                stats->ms_total = tm.ms(0, 1);
+                stats->passes_group = 0;
+            }
+            return KHB_OK;
+        }
+        if (getenv("KHB_BINS_VERBOSE")) fprintf(stderr, "[bins] across-group stage by bins gave up (flags %llu); sorting\n", (unsigned long long)ctx->h_mail[3]);
+        tm.n = 1;   // a table filled up: sort after all
+    }
+    ctx->across_by_sort++;
     u64 one_seg[2] = {0, n};
     int in_tmp = 0, fb, np;
     khb_prefix_plan(k, n, &fb, &np);
@@ -1318,6 +1412,7 @@ int khb_group_sets_append_device(khb_ctx *ctx, int k, const void *d_keys, uint64
     if (n_keys) KHB_CUDA(ctx, cudaMemcpyAsync((char *)ctx->gs_buf + ctx->gs_len * W, d_keys, n_keys * W, cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->gs_len += n_keys;
     ctx->gs_groups += n_groups;
+    ctx->ev_ok = 0;
     return KHB_OK;
 }
 
@@ -1348,6 +1443,7 @@ int khb_peer_import(khb_ctx *ctx, const uint64_t *h_recv_counts, int k, int n_gr
         ctx->gs_len += h_recv_counts[s];
     }
     ctx->gs_groups = n_groups;
+    ctx->ev_ok = 0;
     return KHB_OK;
 }
 
@@ -1366,12 +1462,14 @@ int khb_group_sets_append_host(khb_ctx *ctx, int k, const void *h_keys, uint64_t
     }
     ctx->gs_len += n_keys;
     ctx->gs_groups += n_groups;
+    ctx->ev_ok = 0;
     return KHB_OK;
 }
 
 int khb_group_sets_reset(khb_ctx *ctx)
 {
     if (!ctx) return KHB_ERR_ARG;
+    ev_forget(ctx);
     ctx->gs_len = 0;
     ctx->gs_groups = 0;
     ctx->gs_k = 0;

@@ -297,6 +297,34 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, 
                  : "memory");
 }
 
+// One end-of-bin emission into the group-set store: `count` distinct keys of bin `bin` starting at key index `base`.  While every group of a
+// store came through the bins with the same number of bins, these segments let the across-group stage count bin by bin (mb_across_kernel).
+struct mb_event {
+    u32 bin, count, base_lo, base_hi;
+};
+struct mb_evlog {
+    mb_event *buf;      // device
+    u64 *count;         // device counter
+    u64 cap;            // events that fit
+    u64 store_base;     // key index of the group's first key inside the store
+};
+__device__ __forceinline__ void mb_log_event(const mb_evlog &ev, u32 bin, u32 count, u64 base, u64 *flags)
+{
+    if (!ev.buf) return;
+    const u64 e = atomicAdd((unsigned long long *)ev.count, 1ull);
+    if (e >= ev.cap) {
+        atomicOr((unsigned long long *)flags, 4ull);   // not an error: the store merely loses its bin-by-bin description
+        return;
+    }
+    const u64 b = ev.store_base + base;
+    mb_event o;
+    o.bin = bin;
+    o.count = count;
+    o.base_lo = (u32)b;
+    o.base_hi = (u32)(b >> 32);
+    ev.buf[e] = o;
+}
+
 struct mc_desc {
     u32 bin, count, flags, chunk, cls, ncls;
 };
@@ -357,7 +385,10 @@ template <int KW> __device__ __forceinline__ u32 mb_class_hash(const mb_kmer<KW>
 // 64-bit keys: one compare-and-swap on the key word.  128-bit keys: a 32-bit tag per slot is claimed first (PENDING), the key written,
 // the tag published; a thread that meets a pending slot waits for its owner (independent thread scheduling: the owner may sit in the
 // same warp) -- the owner publishes without any warp-level synchronisation in between.
-__device__ __forceinline__ int mb_find_slot(u64 *tkey, u64 *, u32 *, unsigned short *slots, u32 s_log2, const mb_kmer<2> &key, u32 *s_distinct)
+// claimed != nullptr: a freshly claimed slot is only reported (*claimed = true) and the caller appends it to slots[] itself, one shared-memory
+// atomic per warp instead of one per key (mb_append_claimed) -- every new key of a CTA otherwise hits the same counter.
+__device__ __forceinline__ int mb_find_slot(u64 *tkey, u64 *, u32 *, unsigned short *slots, u32 s_log2, const mb_kmer<2> &key, u32 *s_distinct,
+                                            bool *claimed = nullptr)
 {
     const u32 smask = (1u << s_log2) - 1u;
     u32 slot = (u32)(mb_hash(key) >> 40) & smask;
@@ -367,7 +398,8 @@ __device__ __forceinline__ int mb_find_slot(u64 *tkey, u64 *, u32 *, unsigned sh
         if (c == MB_EMPTY) {
             const u64 old = atomicCAS((unsigned long long *)&tkey[slot], MB_EMPTY, key.v);
             if (old == MB_EMPTY) {
-                slots[atomicAdd(s_distinct, 1u)] = (unsigned short)slot;   // the occupied slots, densely: the end-of-bin pass never looks at an empty one
+                if (claimed) *claimed = true;
+                else slots[atomicAdd(s_distinct, 1u)] = (unsigned short)slot;   // the occupied slots, densely: the end-of-bin pass never looks at an empty one
                 return (int)slot;
             }
             if (old == key.v) return (int)slot;
@@ -376,7 +408,8 @@ __device__ __forceinline__ int mb_find_slot(u64 *tkey, u64 *, u32 *, unsigned sh
         slot = (slot + 1) & smask;
     }
 }
-__device__ __forceinline__ int mb_find_slot(u64 *thi, u64 *tlo, u32 *ttag, unsigned short *slots, u32 s_log2, const mb_kmer<3> &key, u32 *s_distinct)
+__device__ __forceinline__ int mb_find_slot(u64 *thi, u64 *tlo, u32 *ttag, unsigned short *slots, u32 s_log2, const mb_kmer<3> &key, u32 *s_distinct,
+                                            bool *claimed = nullptr)
 {
     const u32 smask = (1u << s_log2) - 1u;
     const u64 h = mb_hash(key);
@@ -391,7 +424,8 @@ __device__ __forceinline__ int mb_find_slot(u64 *thi, u64 *tlo, u32 *ttag, unsig
                 tlo[slot] = key.lo;
                 __threadfence_block();
                 *(volatile u32 *)&ttag[slot] = mytag;
-                slots[atomicAdd(s_distinct, 1u)] = (unsigned short)slot;
+                if (claimed) *claimed = true;
+                else slots[atomicAdd(s_distinct, 1u)] = (unsigned short)slot;
                 return (int)slot;
             }
         }
@@ -400,6 +434,17 @@ __device__ __forceinline__ int mb_find_slot(u64 *thi, u64 *tlo, u32 *ttag, unsig
         if (probes >= MC_PROBES) return -1;
         slot = (slot + 1) & smask;
     }
+}
+// All 32 lanes of a warp, converged: the lanes that claimed a slot append it to the dense list with ONE atomic on the shared counter.
+__device__ __forceinline__ void mb_append_claimed(unsigned short *slots, u32 *s_distinct, bool claimed, int slot)
+{
+    const u32 m = __ballot_sync(0xffffffffu, claimed);
+    if (!m) return;
+    const u32 lane = threadIdx.x & 31u, leader = (u32)__ffs(m) - 1u;
+    u32 base = 0;
+    if (lane == leader) base = atomicAdd(s_distinct, (u32)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (claimed) slots[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)slot;
 }
 // OR a 64-bit genome mask into a slot's bits (two 32-bit shared-memory atomics, skipped when nothing new)
 __device__ __forceinline__ void mb_or_mask(u64 *word, u64 mask)
@@ -451,9 +496,9 @@ __device__ __forceinline__ mc_smem mc_carve(unsigned char *base, int KW, const m
     return s;
 }
 
-template <int KW> __device__ __forceinline__ int mb_slot_of(const mc_smem &sm, u32 s_log2, const mb_kmer<KW> &key, u32 *s_distinct)
+template <int KW> __device__ __forceinline__ int mb_slot_of(const mc_smem &sm, u32 s_log2, const mb_kmer<KW> &key, u32 *s_distinct, bool *claimed = nullptr)
 {
-    return mb_find_slot(sm.tkey, sm.tlo, sm.ttag, sm.slots, s_log2, key, s_distinct);
+    return mb_find_slot(sm.tkey, sm.tlo, sm.ttag, sm.slots, s_log2, key, s_distinct, claimed);
 }
 // Insert `key` with genome bit gb (of the 64 of the current chunk of genomes).  False when the table is too full.
 template <int KW> __device__ __forceinline__ bool mb_insert(const mc_smem &sm, u32 s_log2, const mb_kmer<KW> &key, u32 gb, u32 *s_distinct)
@@ -508,7 +553,7 @@ __global__ void __launch_bounds__(BLOCK)
 mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32 nbins, u32 cap, int k, mc_geom geo, u32 n_genomes, u32 cs,
                 u32 thr1 /* records one pass over a bin may hold */, u32 over_cap, u64 *__restrict__ hist, void *__restrict__ out_keys,
                 u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs, u32 *__restrict__ over_list, u32 *__restrict__ over_count, u64 *__restrict__ d_stat,
-                const u64 *__restrict__ roff)
+                const u64 *__restrict__ roff, mb_evlog evlog)
 {
     extern __shared__ __align__(16) unsigned char mc_raw[];
     __shared__ __align__(8) u64 bars[2];
@@ -651,19 +696,22 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
         const u32 nw = s_wtotal < MC_WCAP ? s_wtotal : MC_WCAP;
         my_drecords += s_dcount < dcap ? s_dcount : dcap;
         bool ok = true;
-        for (u32 t = tid; t < nw; t += BLOCK) {
-            const u32 id = sm.map[t];
-            if (id == 0xffffu) continue;                                       // reserved by a record that found no room
-            const u64 *R = sm.dstore + (size_t)id * (KW + 1);
-            const u32 e = t - sm.dwoff[id];
-            const mb_kmer<KW> key = mb_expand(R, e, k, (mb_kmer<KW> *)nullptr);
-            if (ncls > 1 && __umulhi(mb_class_hash<KW>(key), ncls) != cls) continue;
-            const int slot = mb_slot_of<KW>(sm, s_log2, key, &s_distinct);
-            if (slot < 0) {
-                ok = false;
-                continue;
+        for (u32 t0 = 0; t0 < nw; t0 += BLOCK) {                                // every lane of a warp stays in the loop: the append below is warp-wide
+            const u32 t = t0 + tid;
+            const u32 id = t < nw ? sm.map[t] : 0xffffu;                           // 0xffff: reserved by a record that found no room
+            int slot = -1;
+            bool claimed = false;
+            if (id != 0xffffu) {
+                const u64 *R = sm.dstore + (size_t)id * (KW + 1);
+                const u32 e = t - sm.dwoff[id];
+                const mb_kmer<KW> key = mb_expand(R, e, k, (mb_kmer<KW> *)nullptr);
+                if (ncls == 1 || __umulhi(mb_class_hash<KW>(key), ncls) == cls) {
+                    slot = mb_slot_of<KW>(sm, s_log2, key, &s_distinct, &claimed);
+                    if (slot < 0) ok = false;
+                    else mb_or_mask(sm.tbits + slot, sm.dmask[id]);
+                }
             }
-            mb_or_mask(sm.tbits + slot, sm.dmask[id]);
+            mb_append_claimed(sm.slots, &s_distinct, claimed, slot);
         }
         if (!ok) s_over = 1;
         __syncthreads();
@@ -800,7 +848,10 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
             continue;
         }
         const u32 nd_keys = s_distinct;
-        if (tid == 0 && nd_keys) s_base = atomicAdd((unsigned long long *)d_cursor, (unsigned long long)nd_keys);
+        if (tid == 0 && nd_keys) {
+            s_base = atomicAdd((unsigned long long *)d_cursor, (unsigned long long)nd_keys);
+            if (out_keys) mb_log_event(evlog, d.bin, nd_keys, s_base, d_stat);
+        }
         __syncthreads();
         const u64 base = s_base;
         for (u32 j = tid; j < nd_keys; j += BLOCK) {
@@ -851,7 +902,8 @@ template <int KW, bool MULTI>
 __global__ void __launch_bounds__(MC_BLOCK)
 mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32 cap, int k, mc_geom geo, u32 n_genomes, u32 cs,
                  u64 *__restrict__ hist, void *__restrict__ out_keys, u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs,
-                 const u32 *__restrict__ over_list, const u32 *__restrict__ over_count, u32 over_cap, u64 *__restrict__ flags, const u64 *__restrict__ roff)
+                 const u32 *__restrict__ over_list, const u32 *__restrict__ over_count, u32 over_cap, u64 *__restrict__ flags, const u64 *__restrict__ roff,
+                 mb_evlog evlog)
 {
     extern __shared__ __align__(16) unsigned char mc_raw[];
     __shared__ u32 s_over, s_distinct, ws[33];
@@ -946,7 +998,10 @@ mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u3
                 continue;
             }
             const u32 nd_keys = s_distinct;
-            if (tid == 0 && nd_keys) s_base = atomicAdd((unsigned long long *)d_cursor, (unsigned long long)nd_keys);
+            if (tid == 0 && nd_keys) {
+                s_base = atomicAdd((unsigned long long *)d_cursor, (unsigned long long)nd_keys);
+                if (out_keys) mb_log_event(evlog, bin, nd_keys, s_base, flags);
+            }
             __syncthreads();
             const u64 base = s_base;
             for (u32 j = tid; j < nd_keys; j += MC_BLOCK) {
@@ -999,7 +1054,8 @@ int khb_bins_eligible(int k, int n_genomes, u64 n_sym)
 // (sum over genomes of their distinct k-mers) are zeroed here.  exact != 0: the call before this one, on the same group, ended with flag 1;
 // partition again into regions of exactly the sizes that attempt counted (they are still in the context's scratch).
 int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u64 n_sym, int k, const u64 *d_seg_off, int n_genomes, u32 cs, u32 nbins_hist,
-                        u64 *d_hist, void *d_out_keys, u64 *d_runs, u64 *d_pairs, u64 *d_stat, int exact)
+                        u64 *d_hist, void *d_out_keys, u64 *d_runs, u64 *d_pairs, u64 *d_stat, int exact, u32 nb_fixed, u32 *nb_used, void *ev_buf,
+                        u64 *ev_count, u64 ev_cap, u64 store_base)
 {
     if (!khb_bins_eligible(k, n_genomes, n_sym)) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: k=%d / %d genomes not supported", k, n_genomes);
     const int KW = k <= 32 ? 2 : 3;               // record words of symbols: k - 1 + 32 windows fit 64 (k <= 32) or 96 symbols
@@ -1029,8 +1085,10 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
     const u64 wpb = (u64)mb_env("KHB_BINS_WPB", (long long)wpb_d);
     u64 nb64 = div_up(n_sym, wpb ? wpb : 1024);
     if (nb64 < 16) nb64 = 16;
+    if (nb_fixed) nb64 = nb_fixed;                 // the store's earlier groups were binned with this many bins: keep the bins comparable
     if (nb64 > (1ull << 28)) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: group too large");
     const u32 nb = (u32)nb64;
+    if (nb_used) *nb_used = nb;
     {   // table slots: the mean bin's distinct k-mers fill ~45 % (larger bins are counted in hash classes)
         const double want = (double)(n_sym / nb + 1) * rho_w / 0.45;
         u32 l2 = 10;
@@ -1128,8 +1186,13 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
         u32 n_gen = (u32)n_genomes, cs_ = cs, nb_ = nb, cap_ = cap, thr_ = thr1, ocap_ = over_cap;
         int k_ = k;
         void *keys_ = d_out_keys;
+        mb_evlog evlog;
+        evlog.buf = (mb_event *)ev_buf;
+        evlog.count = ev_count;
+        evlog.cap = ev_cap;
+        evlog.store_base = store_base;
         const u32 *c_list = d_over_list, *c_cnt = d_over_count;
-        void *cargs[] = {&c_rec, &c_cur, &nb_, &cap_, &k_, &geo, &n_gen, &cs_, &thr_, &ocap_, &d_hist, &keys_, &d_runs, &d_pairs, &d_over_list, &d_over_count, &d_stat, &roff};
+        void *cargs[] = {&c_rec, &c_cur, &nb_, &cap_, &k_, &geo, &n_gen, &cs_, &thr_, &ocap_, &d_hist, &keys_, &d_runs, &d_pairs, &d_over_list, &d_over_count, &d_stat, &roff, &evlog};
         if (mb_env("KHB_BINS_VERBOSE", 0))
             fprintf(stderr, "[bins] k=%d genomes=%d windows=%llu bins=%u chunks=%u cap=%u slots=2^%u dcap=%u thr1=%u rho_w=%.3f shm=%zu ctas/sm=%d block=%d\n", k, n_genomes,
                     (unsigned long long)n_sym, nb, geo.nchunks, cap, geo.s_log2, geo.dcap, thr1, rho_w, shm, per_sm, block);
@@ -1137,13 +1200,347 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
         KHB_CUDA(ctx, cudaLaunchKernel(fn, dim3(grid), dim3(block), cargs, shm, ctx->stream));
         khb_prof_end(ctx, KHB_K_BIN_COUNT, 0);
         KHB_LAUNCH_CHECK(ctx);
-        void *bargs[] = {&c_rec, &c_cur, &cap_, &k_, &geo, &n_gen, &cs_, &d_hist, &keys_, &d_runs, &d_pairs, &c_list, &c_cnt, &ocap_, &d_stat, &roff};
+        void *bargs[] = {&c_rec, &c_cur, &cap_, &k_, &geo, &n_gen, &cs_, &d_hist, &keys_, &d_runs, &d_pairs, &c_list, &c_cnt, &ocap_, &d_stat, &roff, &evlog};
         KHB_CUDA(ctx, cudaLaunchKernel(bfn, dim3((u32)ctx->num_sms * 2u), dim3(MC_BLOCK), bargs, shm, ctx->stream));
         KHB_LAUNCH_CHECK(ctx);
         mb_region_max_kernel<<<(unsigned)ctx->num_sms * 4u, 256, 0, ctx->stream>>>(d_cur, n_regions, d_stat + 3);
         KHB_LAUNCH_CHECK(ctx);
         ctx->bins_last_regions = n_regions;
     }
+    return KHB_OK;
+}
+
+// ---- the across-group stage, bin by bin -------------------------------------------------------------------------------------------
+// `kmc_tools complex` over the groups' sets + its histogram (/root/reference/workflow/rules/exp_type_1.smk:243-259) without the sort: a
+// k-mer's bin is the same in every group, so the segments the groups' end-of-bin passes left in the store (mb_event) are first
+// ordered by bin (a counting sort of the events, not of the keys), then one CTA per bin counts in how many segments every key occurs --
+// each group holds a key at most once -- in a shared-memory table of (key, count).  Bins with more keys than the table takes are
+// counted in hash classes (several passes over the bin's segments, which then come from L2).
+#define MA_BLOCK 256
+#define MA_EVMAX 512          // segments of a bin held in shared memory at a time
+#define MA_UNROLL 4
+#define MA_PROBES 1024        // linear probing in a table that is at most 44 % full: never reached
+
+__global__ void __launch_bounds__(256)
+ma_event_hist_kernel(const mb_event *__restrict__ ev, u64 n_ev, u32 nb, u32 *__restrict__ bin_events, u32 *__restrict__ bin_keys, u64 *__restrict__ flags)
+{
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < n_ev; e += (u64)gridDim.x * blockDim.x) {
+        const mb_event v = ev[e];
+        if (v.bin >= nb) {
+            *flags = 1ull;
+            continue;
+        }
+        atomicAdd(&bin_events[v.bin], 1u);
+        atomicAdd(&bin_keys[v.bin], v.count);
+    }
+}
+__global__ void __launch_bounds__(1024)
+ma_scan_kernel(const u32 *__restrict__ cnt, u64 n, u64 *__restrict__ off)
+{
+    __shared__ u64 ws[33];
+    __shared__ u64 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (u64 base = 0; base < n; base += 1024) {
+        const u64 i = base + threadIdx.x;
+        const u64 v = i < n ? (u64)cnt[i] : 0ull;
+        u64 total;
+        const u64 ex = block_excl_sum<u64>(v, ws, &total);
+        if (i < n) off[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[n] = carry;
+}
+__global__ void __launch_bounds__(256)
+ma_event_scatter_kernel(const mb_event *__restrict__ ev, u64 n_ev, u32 nb, const u64 *__restrict__ off, u32 *__restrict__ fill, mb_event *__restrict__ out)
+{
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < n_ev; e += (u64)gridDim.x * blockDim.x) {
+        const mb_event v = ev[e];
+        if (v.bin >= nb) continue;
+        out[off[v.bin] + atomicAdd(&fill[v.bin], 1u)] = v;
+    }
+}
+
+// KW2 = 1: 64-bit keys (u64), 2: 128-bit keys (Key128: lo, hi).  Persistent CTAs, one bin at a time: the bin's segments are copied into
+// shared memory by cp.async.bulk (one copy per segment, one mbarrier for all of them; a 64-bit segment that starts at an odd key index is
+// copied from the key before it, so that every copy is 16-byte aligned), then every hash class of the bin is counted from shared memory.
+#define MA_STAGE_BYTES 40960  // keys of a bin (or of a chunk of its segments) in shared memory
+template <int KW2>
+__global__ void __launch_bounds__(MA_BLOCK)
+mb_across_kernel(const void *__restrict__ store, const mb_event *__restrict__ ev, const u64 *__restrict__ off, const u32 *__restrict__ bin_keys, u32 nb,
+                 u32 s_log2, u32 cs, u32 hrows, u32 n_groups, u64 *__restrict__ hist, u64 *__restrict__ d_distinct, u64 *__restrict__ flags)
+{
+    extern __shared__ __align__(16) unsigned char ma_raw[];
+    __shared__ u32 e_start[MA_EVMAX];     // first real key of the segment inside the stage buffer (in keys)
+    __shared__ u32 e_pre[MA_EVMAX + 1];   // real keys of the segments before it
+    __shared__ __align__(8) u64 bar;
+    __shared__ u32 s_over, s_distinct, s_ne;
+    __shared__ u64 s_next;                // first segment of the next chunk
+    constexpr u32 KB = KW2 == 2 ? 16u : 8u;
+    constexpr u32 STAGE_KEYS = MA_STAGE_BYTES / KB;
+    const u32 S = 1u << s_log2, smask = S - 1u, tid = threadIdx.x;
+    unsigned char *stage = ma_raw;                                // [MA_STAGE_BYTES]
+    u64 *tkey = (u64 *)(ma_raw + MA_STAGE_BYTES);                 // key (KW2 = 1) or its low word
+    u64 *thi = tkey + S;                                          // high word (KW2 = 2)
+    u32 *tcnt = (u32 *)(thi + (KW2 == 2 ? S : 0));
+    u32 *ttag = tcnt + S;                                         // KW2 = 2 only
+    u32 *shist = ttag + (KW2 == 2 ? S : 0);
+    unsigned short *slots = (unsigned short *)(shist + ((hrows + 2) & ~1u));
+    for (u32 i = tid; i < S; i += MA_BLOCK) {
+        if (KW2 == 2) ttag[i] = 0u; else tkey[i] = MB_EMPTY;
+        tcnt[i] = 0u;
+    }
+    for (u32 i = tid; i <= hrows; i += MA_BLOCK) shist[i] = 0u;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        s_over = 0;
+        s_distinct = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const u32 thr = S / 4 + S / 8 + S / 16;                       // keys one pass may bring (>= its distinct keys): the table stays below 44 % full
+    const u32 c_all = n_groups < cs ? n_groups : cs;
+    u32 n_one = 0, n_all = 0, phase = 0;
+    u64 distinct = 0;
+    // the next bin's numbers are loaded while this one is counted
+    u32 b = blockIdx.x;
+    u32 total = b < nb ? __ldg(bin_keys + b) : 0u;
+    u64 e0 = b < nb ? __ldg(off + b) : 0ull, e1 = b < nb ? __ldg(off + b + 1) : 0ull;
+    while (b < nb) {
+        const u32 bn = b + gridDim.x;
+        const u32 total_n = bn < nb ? __ldg(bin_keys + bn) : 0u;
+        const u64 e0_n = bn < nb ? __ldg(off + bn) : 0ull, e1_n = bn < nb ? __ldg(off + bn + 1) : 0ull;
+        const u32 ncls = total <= thr ? 1u : (total + thr - 1) / thr;
+        bool resident = false;                                    // the whole bin sits in the stage buffer (loaded once, counted class by class)
+        bool gave_up = false;
+        for (u32 cls = 0; cls < ncls && !gave_up; cls++) {
+            bool ok = true;
+            for (u64 ec = e0; ec < e1;) {                         // chunks of segments that fit the stage buffer (normally ONE per bin)
+                if (!resident) {
+                    __syncthreads();                              // the stage buffer and the segment tables are free
+                    if (tid < 32) {
+                        // one warp lays the segments out, 32 at a time, lane i taking segment ec + i0 + i, until the buffer is full
+                        u32 keys_run = 0, real_run = 0, n_take = 0;
+                        bool full = false;
+                        for (u32 i0 = 0; i0 < MA_EVMAX && ec + i0 < e1 && !full; i0 += 32) {
+                            const u64 ei = ec + i0 + tid;
+                            mb_event v;
+                            v.count = 0;
+                            v.base_lo = v.base_hi = 0;
+                            const bool have = ei < e1 && i0 + tid < MA_EVMAX;
+                            if (have) v = ev[ei];
+                            const u64 base = ((u64)v.base_hi << 32) | v.base_lo;
+                            const u32 lead = (KW2 == 1 && have) ? (u32)(base & 1ull) : 0u;   // the key in front, for 16-byte alignment
+                            const u32 padded = !have ? 0u : KW2 == 1 ? ((v.count + lead + 1u) & ~1u) : v.count;   // keys copied
+                            const u32 inc_p = warp_incl_sum(padded), inc_r = warp_incl_sum(have ? v.count : 0u);
+                            const u32 my_start = keys_run + inc_p - padded;
+                            const bool fits = have && my_start + padded <= STAGE_KEYS;
+                            const u32 fit_mask = __ballot_sync(0xffffffffu, fits), have_mask = __ballot_sync(0xffffffffu, have);
+                            const u32 first_bad = __ffs(have_mask & ~fit_mask);              // 1-based lane of the first segment that does not fit
+                            const bool take = have && (first_bad == 0 || tid + 1 < first_bad);
+                            if (take) {
+                                const u32 idx = i0 + tid;
+                                e_start[idx] = my_start + lead;
+                                e_pre[idx] = real_run + inc_r - v.count;
+                                bulk_g2s(stage + (size_t)my_start * KB, (const unsigned char *)store + (base - lead) * KB, padded * KB, &bar);
+                            }
+                            const u32 take_mask = __ballot_sync(0xffffffffu, take);
+                            const u32 n_t = __popc(take_mask);
+                            const u32 last = n_t ? (u32)(31 - __clz(take_mask)) : 0u;
+                            const u32 add_p = __shfl_sync(0xffffffffu, inc_p, last), add_r = __shfl_sync(0xffffffffu, inc_r, last);
+                            if (n_t) {
+                                keys_run += add_p;
+                                real_run += add_r;
+                            }
+                            n_take += n_t;
+                            full = first_bad != 0;
+                        }
+                        if (tid == 0) {
+                            e_pre[n_take] = real_run;
+                            s_ne = n_take;
+                            s_next = ec + n_take;
+                            if (n_take) mbar_arrive_expect_tx(&bar, keys_run * KB);
+                        }
+                    }
+                    __syncthreads();
+                    if (!s_ne) {                                  // a single segment larger than the stage buffer: the caller sorts instead
+                        if (tid == 0) atomicOr((unsigned long long *)flags, 2ull);
+                        gave_up = true;
+                        break;
+                    }
+                    mbar_wait(&bar, phase);
+                    phase ^= 1u;
+                    if (ec == e0 && s_next >= e1) resident = true;
+                }
+                const u32 ne = s_ne;
+                const u32 nk = e_pre[ne];
+                for (u32 t0 = 0; t0 < nk; t0 += MA_BLOCK) {       // every lane of a warp stays in the loop: the append below is warp-wide
+                    const u32 t = t0 + tid;
+                    int found = -1;
+                    bool claimed = false;
+                    if (t < nk) {
+                        u32 lo = 0, hi = ne;                      // segment of key t: e_pre[lo] <= t < e_pre[lo + 1]
+                        while (hi - lo > 1) {
+                            const u32 mid = (lo + hi) >> 1;
+                            if (e_pre[mid] <= t) lo = mid; else hi = mid;
+                        }
+                        const u32 at = e_start[lo] + (t - e_pre[lo]);
+                        u64 klo, khi = 0;
+                        if (KW2 == 2) {
+                            const Key128 kk = ((const Key128 *)stage)[at];
+                            klo = kk.lo;
+                            khi = kk.hi;
+                        } else {
+                            klo = ((const u64 *)stage)[at];
+                        }
+                        const u64 h = (klo ^ (khi * 0xBF58476D1CE4E5B9ull)) * 0x9E3779B97F4A7C15ull;   // the keys are mixed already: spread the class and the slot bits
+                        if (ncls == 1 || __umulhi((u32)(h >> 8), ncls) == cls) {
+                            u32 slot = (u32)(h >> 40) & smask;
+                            if (KW2 == 1) {
+                                for (u32 probes = 0; probes <= MA_PROBES; probes++) {
+                                    const u64 c = *(volatile u64 *)&tkey[slot];
+                                    if (c == klo) { found = (int)slot; break; }
+                                    if (c == MB_EMPTY) {
+                                        const u64 old = atomicCAS((unsigned long long *)&tkey[slot], MB_EMPTY, klo);
+                                        if (old == MB_EMPTY) {
+                                            claimed = true;
+                                            found = (int)slot;
+                                            break;
+                                        }
+                                        if (old == klo) { found = (int)slot; break; }
+                                    }
+                                    slot = (slot + 1) & smask;
+                                }
+                            } else {
+                                const u32 mytag = (u32)h | 2u;
+                                for (u32 probes = 0; probes <= MA_PROBES; probes++) {
+                                    u32 tg = *(volatile u32 *)&ttag[slot];
+                                    if (tg == 0u) {
+                                        tg = atomicCAS(&ttag[slot], 0u, MB_TAG_PENDING);
+                                        if (tg == 0u) {
+                                            tkey[slot] = klo;
+                                            thi[slot] = khi;
+                                            __threadfence_block();
+                                            *(volatile u32 *)&ttag[slot] = mytag;
+                                            claimed = true;
+                                            found = (int)slot;
+                                            break;
+                                        }
+                                    }
+                                    while (tg == MB_TAG_PENDING) tg = *(volatile u32 *)&ttag[slot];
+                                    if (tg == mytag && *(volatile u64 *)&tkey[slot] == klo && *(volatile u64 *)&thi[slot] == khi) { found = (int)slot; break; }
+                                    slot = (slot + 1) & smask;
+                                }
+                            }
+                            if (found < 0) ok = false;
+                            else atomicAdd(&tcnt[found], 1u);
+                        }
+                    }
+                    mb_append_claimed(slots, &s_distinct, claimed, found);
+                }
+                ec = resident ? e1 : s_next;
+            }
+            if (!ok) s_over = 1;
+            __syncthreads();
+            if (s_distinct > S - S / 4) s_over = 1;
+            const u32 nd = s_distinct;
+            if (s_over || gave_up) {                              // the caller sorts instead
+                if (tid == 0) atomicOr((unsigned long long *)flags, 2ull);
+                for (u32 i = tid; i < S; i += MA_BLOCK) {
+                    if (KW2 == 2) ttag[i] = 0u; else tkey[i] = MB_EMPTY;
+                    tcnt[i] = 0u;
+                }
+            } else {
+                for (u32 j = tid; j < nd; j += MA_BLOCK) {
+                    const u32 i = slots[j];
+                    const u32 c = tcnt[i];
+                    tcnt[i] = 0u;
+                    if (KW2 == 2) ttag[i] = 0u; else tkey[i] = MB_EMPTY;
+                    const u32 cc = c > cs ? cs : c;
+                    if (cc == 1u) n_one++;
+                    else if (cc == c_all) n_all++;
+                    else if (cc <= hrows) atomicAdd(&shist[cc], 1u);
+                }
+                if (tid == 0) distinct += nd;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                s_over = 0;
+                s_distinct = 0;
+            }
+            __syncthreads();
+        }
+        b = bn;
+        total = total_n;
+        e0 = e0_n;
+        e1 = e1_n;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_one += __shfl_xor_sync(0xffffffffu, n_one, o);
+        n_all += __shfl_xor_sync(0xffffffffu, n_all, o);
+    }
+    if ((tid & 31u) == 0) {
+        if (n_one && 1u <= hrows) atomicAdd(&shist[1], n_one);
+        if (n_all && c_all <= hrows && c_all != 1u) atomicAdd(&shist[c_all], n_all);
+    }
+    if (tid == 0 && distinct) atomicAdd((unsigned long long *)d_distinct, (unsigned long long)distinct);
+    __syncthreads();
+    for (u32 i = tid; i <= hrows; i += MA_BLOCK) {
+        const u32 v = shist[i];
+        if (v) atomicAdd((unsigned long long *)&hist[i], (unsigned long long)v);
+    }
+}
+
+// Across-group histogram from the store's segment events.  d_hist[nbins_hist + 1] and d_runs (distinct k-mers overall) are zeroed here;
+// d_flag: != 0 afterwards means the result is incomplete and the caller has to sort instead.
+int khb_bins_across_impl(khb_ctx *ctx, int k, const void *d_store, const void *d_events, u64 n_events, u32 nb, int n_groups, u32 cs, u32 nbins_hist,
+                         u64 *d_hist, u64 *d_runs, u64 *d_flag)
+{
+    const int KW2 = k <= 32 ? 1 : 2;
+    const u32 hrows = nbins_hist < (u32)n_groups ? nbins_hist : (u32)n_groups;
+    const u32 s_log2 = (u32)mb_env("KHB_ACROSS_SLOTS_LOG2", 12);
+    if (s_log2 < 8 || s_log2 > 13) return khb_fail(ctx, KHB_ERR_ARG, "KHB_ACROSS_SLOTS_LOG2 outside 8..13");
+    const size_t S = (size_t)1 << s_log2;
+    const size_t shm = MA_STAGE_BYTES + S * 8 + (KW2 == 2 ? S * 12 : 0) + S * 4 + (((size_t)hrows + 2) & ~(size_t)1) * 4 + S * 2 + 64;
+    int rc;
+    void *p;
+    const size_t aux = (size_t)nb * 12 + ((size_t)nb + 1) * 8 + n_events * sizeof(mb_event) + 256;
+    if ((rc = khb_scratch_get(ctx, SCR_AUX, aux, &p))) return rc;
+    u64 *d_off = (u64 *)p;                                        // [nb + 1]
+    mb_event *d_sorted = (mb_event *)(d_off + nb + 2);            // [n_events] (16-byte aligned: nb + 2 words of 8 bytes ... see below)
+    d_sorted = (mb_event *)(((uintptr_t)d_sorted + 15) & ~(uintptr_t)15);
+    u32 *d_bin_events = (u32 *)(d_sorted + n_events), *d_bin_keys = d_bin_events + nb, *d_fill = d_bin_keys + nb;
+    KHB_CUDA(ctx, cudaMemsetAsync(d_bin_events, 0, (size_t)nb * 12, ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, ((size_t)nbins_hist + 1) * sizeof(u64), ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(d_runs, 0, sizeof(u64), ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(u64), ctx->stream));
+    if (!n_events) return KHB_OK;
+    const unsigned eg = (unsigned)(div_up(n_events, 256) < 4096 ? div_up(n_events, 256) : 4096);
+    khb_prof_begin(ctx, KHB_K_BIN_ACROSS);
+    ma_event_hist_kernel<<<eg, 256, 0, ctx->stream>>>((const mb_event *)d_events, n_events, nb, d_bin_events, d_bin_keys, d_flag);
+    KHB_LAUNCH_CHECK(ctx);
+    ma_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_bin_events, nb, d_off);
+    KHB_LAUNCH_CHECK(ctx);
+    ma_event_scatter_kernel<<<eg, 256, 0, ctx->stream>>>((const mb_event *)d_events, n_events, nb, d_off, d_fill, d_sorted);
+    KHB_LAUNCH_CHECK(ctx);
+    const void *fn = KW2 == 1 ? (const void *)mb_across_kernel<1> : (const void *)mb_across_kernel<2>;
+    KHB_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    int per_sm = 0;
+    KHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, MA_BLOCK, shm));
+    if (per_sm < 1) return khb_fail(ctx, KHB_ERR_ARG, "across-group stage by bins: %zu bytes of shared memory do not fit an SM", shm);
+    u32 grid = (u32)ctx->num_sms * (u32)per_sm;
+    if (grid > nb) grid = nb;
+    const mb_event *c_ev = d_sorted;
+    const u64 *c_off = d_off;
+    const u32 *c_keys = d_bin_keys;
+    u32 nb_ = nb, sl = s_log2, cs_ = cs, hr = hrows, ng = (u32)n_groups;
+    void *args[] = {&d_store, &c_ev, &c_off, &c_keys, &nb_, &sl, &cs_, &hr, &ng, &d_hist, &d_runs, &d_flag};
+    KHB_CUDA(ctx, cudaLaunchKernel(fn, dim3(grid), dim3(MA_BLOCK), args, shm, ctx->stream));
+    khb_prof_end(ctx, KHB_K_BIN_ACROSS, 0);
+    KHB_LAUNCH_CHECK(ctx);
     return KHB_OK;
 }
 

@@ -216,11 +216,19 @@ struct khb_ctx {
     u64 bins_fallbacks, bins_bigbins, bins_repartitions;
     int bins_hint_k, bins_hint_genomes;            // shape of the last group the minimizer-bin path counted ...
     u64 bins_hint_regions, bins_hint_max, bins_last_regions;  // ... its regions and the records of its fullest one  // groups the minimizer-bin path handed to the sort path / bins redone in hash classes (bins.cu)
+    // segment events of the group-set store (bins.cu: mb_event): while every retained group came through the minimizer bins with the same
+    // number of bins, the across-group stage counts bin by bin instead of sorting the store
+    void *ev_buf;       // device, ev_cap events of 16 bytes
+    u64 *ev_count;      // device counter
+    u64 ev_cap, ev_len; // capacity; events logged so far (host copy, read back with every group's mailbox)
+    int ev_ok;          // 1: the events describe the whole store
+    u32 ev_nb;          // bins of the groups in the store
+    u64 across_by_bins, across_by_sort;   // performance counters
     int group_mode;    // KHB_GROUP_* (khb_set_group_mode; initial value from the environment variable KHB_GROUP_MODE)
 };
 
 // kernel ids for khb_profile_read
-enum { KHB_K_PACK = 0, KHB_K_EXTRACT = 1, KHB_K_RADIX_HIST = 2, KHB_K_ONESWEEP = 3, KHB_K_UNIQUE = 4, KHB_K_RLE = 5, KHB_K_PARTITION = 6, KHB_K_HASH_INSERT = 7, KHB_K_HASH_COUNT = 8, KHB_K_BIN_PARTITION = 9, KHB_K_BIN_COUNT = 10, KHB_K_COUNT = 11 };
+enum { KHB_K_PACK = 0, KHB_K_EXTRACT = 1, KHB_K_RADIX_HIST = 2, KHB_K_ONESWEEP = 3, KHB_K_UNIQUE = 4, KHB_K_RLE = 5, KHB_K_PARTITION = 6, KHB_K_HASH_INSERT = 7, KHB_K_HASH_COUNT = 8, KHB_K_BIN_PARTITION = 9, KHB_K_BIN_COUNT = 10, KHB_K_BIN_ACROSS = 11, KHB_K_COUNT = 12 };
 void khb_prof_begin(khb_ctx *ctx, int id);
 void khb_prof_end(khb_ctx *ctx, int id, u64 alg_bytes);
 void khb_prof_patch(khb_ctx *ctx, int id, u64 alg_bytes);  // algorithmic bytes of the LAST record of that kernel, once they are known

@@ -115,6 +115,7 @@ _SIGNATURES = [
     ("khb_set_group_mode", C.c_int, [_P, C.c_int]),
     ("khb_hash_overflows", C.c_uint64, [_P]),
     ("khb_bins_counters", None, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("khb_across_counters", None, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
 
@@ -270,7 +271,7 @@ class Engine:
         return int(self.lib.khb_launch_count(self.ctx))
 
     KERNELS = {"pack": 0, "extract": 1, "radix_hist": 2, "onesweep": 3, "unique": 4, "rle_hist": 5, "partition": 6,
-               "hash_insert": 7, "hash_count": 8, "bin_partition": 9, "bin_count": 10}
+               "hash_insert": 7, "hash_count": 8, "bin_partition": 9, "bin_count": 10, "bin_across": 11}
 
     # ---- multi-GPU exchange over peer memory (csrc/peer.cu) ----
     def peer_alloc(self, world: int, rank: int, key_bytes: int, region_keys: int) -> bytes:
@@ -324,7 +325,9 @@ class Engine:
         """Minimizer-bin path: groups handed to the sort path, bins redone in hash classes, groups partitioned a second time."""
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self.lib.khb_bins_counters(self.ctx, C.byref(a), C.byref(b), C.byref(c))
-        return {"fallbacks": int(a.value), "big_bins": int(b.value), "repartitions": int(c.value)}
+        d, e = C.c_uint64(), C.c_uint64()
+        self.lib.khb_across_counters(self.ctx, C.byref(d), C.byref(e))
+        return {"fallbacks": int(a.value), "big_bins": int(b.value), "repartitions": int(c.value), "across_by_bins": int(d.value), "across_by_sort": int(e.value)}
 
     def profile_enable(self, on: bool = True):
         """Bracket every kernel launch with CUDA events (clears earlier records)."""

@@ -57,6 +57,58 @@ def _check(res, w_ref, a_ref, st_ref, n_groups):
         assert np.array_equal(x, y)
 
 
+def test_across_stage_bin_by_bin_and_by_sort(oracle, monkeypatch):
+    """The opt-in across-group stage over the segments the bins left in the store (KHB_ACROSS_MODE=bins, no sort) against the prefix sort
+    of the same store and the oracle, for both key widths; tiny tables force hash classes; a group from another path in between makes
+    the stage sort.  The switch is read once per process, so this test runs in a process of its own."""
+    import subprocess
+    import sys
+    import textwrap
+    code = textwrap.dedent("""
+        import os, sys
+        import numpy as np
+        sys.path.insert(0, os.getcwd())
+        from khoice_b200 import synth
+        from khoice_b200.engine import Engine
+        from oracle import oracle as O
+        engine = Engine(0)
+        def run_groups(groups, k):
+            engine.group_sets_reset()
+            hists = [engine.group_from_fasta(g, k, nbins=64)[0] for g in groups]
+            ha, sta = engine.across_groups(nbins=64)
+            return hists, ha, sta
+        for k in (31, 45):
+            cfg = synth.SynthConfig(n_groups=5, genomes_per_group=4, genome_len=25_000, seed=77 + k)
+            groups = [[synth.make_genome(cfg, g, i) for i in range(1, 5)] for g in range(1, 6)]
+            flat = [f for grp in groups for f in grp]
+            gid = [i for i, grp in enumerate(groups) for _ in grp]
+            w_ref, a_ref, st_ref = O.exp1(flat, gid, 5, k, nbins=64)
+            for slots in (None, "8"):
+                if slots:
+                    os.environ["KHB_ACROSS_SLOTS_LOG2"] = slots
+                before = engine.bins_counters
+                hists, ha, sta = run_groups(groups, k)
+                after = engine.bins_counters
+                assert after["across_by_bins"] == before["across_by_bins"] + 1 and after["across_by_sort"] == before["across_by_sort"], (before, after)
+                assert np.array_equal(ha, a_ref) and sta["distinct"] == st_ref["distinct"]
+                assert all(np.array_equal(hists[i], w_ref[i]) for i in range(5))
+            del os.environ["KHB_ACROSS_SLOTS_LOG2"]
+            engine.group_sets_reset()
+            for i, grp in enumerate(groups):
+                engine.set_group_mode("single-sort" if i == 2 else "auto")
+                engine.group_from_fasta(grp, k, nbins=64)
+            engine.set_group_mode("auto")
+            before = engine.bins_counters
+            ha, sta = engine.across_groups(nbins=64)
+            assert engine.bins_counters["across_by_sort"] == before["across_by_sort"] + 1
+            assert np.array_equal(ha, a_ref) and sta["distinct"] == st_ref["distinct"]
+        print("ok")
+    """)
+    env = dict(os.environ, KHB_ACROSS_MODE="bins")
+    r = subprocess.run([sys.executable, "-c", code], cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-4000:]
+
+
 @pytest.mark.parametrize("k", [17, 18, 21, 24, 27, 30, 31, 33, 40, 47, 56, 63])   # 64-bit words up to 31, 128-bit from 33
 @pytest.mark.parametrize("n_genomes", [3, 40, 70, 200])  # one chunk of genome bits, one, two and four chunks
 def test_bins_mode_equals_sort_mode_and_oracle(engine, oracle, k, n_genomes):
