@@ -656,6 +656,16 @@ static int ev_reserve(khb_ctx *ctx, u64 extra)
     ctx->ev_cap = cap;
     return KHB_OK;
 }
+// KHB_ACROSS_MODE=bins: the across-group stage counts bin by bin where the store allows it (measured slower than the sort: opt-in)
+static bool across_by_bins_wanted()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("KHB_ACROSS_MODE");
+        v = e && strcmp(e, "bins") == 0 ? 1 : 0;
+    }
+    return v == 1;
+}
 static void ev_forget(khb_ctx *ctx)
 {
     ctx->ev_ok = 0;
@@ -836,7 +846,7 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
                         khb_bins_eligible(k, n_genomes, n_sym);
         int bins_exact = 0;
         // the store's segment events (across-group stage bin by bin): kept while every retained group comes through the bins
-        const bool log_events = use_bins && keep_set && (ctx->gs_len == 0 || ctx->ev_ok);
+        const bool log_events = use_bins && keep_set && across_by_bins_wanted() && (ctx->gs_len == 0 || ctx->ev_ok);
         u32 bins_nb = 0;
         if (keep_set && ctx->gs_len == 0) {
             ev_forget(ctx);
@@ -1309,12 +1319,7 @@ int khb_across_groups(khb_ctx *ctx, uint32_t nbins, uint64_t *h_hist, khb_stats 
     if (rc) return rc;
     PhaseTimer tm(ctx);
     tm.mark();
-    static int across_bins = -1;
-    if (across_bins < 0) {
-        const char *e = getenv("KHB_ACROSS_MODE");   // bins: count bin by bin where the store allows it (measured slower than the sort: opt-in)
-        across_bins = e && strcmp(e, "bins") == 0 ? 1 : 0;
-    }
-    if (across_bins && ctx->ev_ok && ctx->ev_len && ctx->ev_nb && ctx->gs_hashed) {
+    if (across_by_bins_wanted() && ctx->ev_ok && ctx->ev_len && ctx->ev_nb && ctx->gs_hashed) {
         // every group came through the minimizer bins: count bin by bin over the segments they left (bins.cu), no sort -- 15.3 ms against
         // the sort's 12.8 ms at config 2 (profiles/r2_bench_history.md), so only on request
         u64 *d_hist = ctx->d_mail + 8, *d_runs = ctx->d_mail;
