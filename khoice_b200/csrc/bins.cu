@@ -52,6 +52,16 @@ __device__ __forceinline__ u32 mb_bin_of(u32 minhash, u32 nbins)
     return __umulhi(b, nbins);
 }
 
+#define MB_SEGS 512           // genomes whose symbol offsets a partition CTA keeps in shared memory
+__device__ __forceinline__ u32 mb_segment_of_shared(const u64 *seg_off, int nseg, u64 i)
+{
+    int lo = 0, hi = nseg;  // invariant: seg_off[lo] <= i < seg_off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (seg_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    return (u32)lo;
+}
 __device__ __forceinline__ u32 mb_segment_of(const u64 *__restrict__ seg_off, int nseg, u64 i)
 {
     int lo = 0, hi = nseg;  // invariant: seg_off[lo] <= i < seg_off[hi]
@@ -114,11 +124,14 @@ mb_partition_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid
     constexpr int CW = MB_TILE / 32 + KW + 2;     // 64-bit code words staged per tile
     constexpr int VW = MB_TILE / 32 + 4;
     __shared__ u32 A[MB_NH];                      // hashes -> suffix minima -> per-window minimum
-    __shared__ u32 P[MB_NH];                      // prefix minima
+    __shared__ __align__(16) u32 P[MB_NH];        // prefix minima
     __shared__ u32 sc[2 * CW + 2];                // the tile's symbols as 16-symbol chunks in stream order
     __shared__ u32 sv[VW];
-    __shared__ u32 cell[MB_TILE / 32 + 1];        // boundaries per 32 windows -> their exclusive prefix
-    __shared__ unsigned short blist[MB_TILE + 2]; // the tile's boundaries in window order
+    __shared__ u32 mv[VW];                        // bit (31 - i) of mv[q]: the m symbols from position 32 q + i on are all valid
+    constexpr u32 WSEG = MB_TILE / (MB_BLOCK / 32);                  // windows per warp in phase 3
+    unsigned short (*blist)[WSEG + 2] = (unsigned short (*)[WSEG + 2])P;   // per warp: the boundaries of its windows, in window order (P is free by then)
+    __shared__ u32 wcnt[MB_BLOCK / 32], wnext[MB_BLOCK / 32];        // ... how many, and the first boundary behind its windows
+    __shared__ u64 sseg[MB_SEGS + 1];             // the genomes' symbol offsets (groups of up to MB_SEGS genomes)
     const u32 tid = threadIdx.x;
     const u64 tile0 = (u64)blockIdx.x * MB_TILE;  // a multiple of 32
     const int w = k - m + 1;                      // m-mers per window
@@ -133,11 +146,26 @@ mb_partition_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid
             sc[2 * i + 1] = (u32)c;
         }
         for (u32 i = tid; i < VW; i += MB_BLOCK) sv[i] = q0 + i <= last_vw ? __ldg(valid + q0 + i) : 0u;
+        if (nseg <= MB_SEGS)
+            for (u32 i = tid; i <= (u32)nseg; i += MB_BLOCK) sseg[i] = __ldg(seg_off + i);
+    }
+    __syncthreads();
+    // validity of every m-mer start, 32 positions per word: AND of the validity stream with itself shifted by 1, 2, 4, 8 (MSB first)
+    for (u32 i = tid; i < VW; i += MB_BLOCK) {
+        const u64 x = ((u64)sv[i] << 32) | (i + 1 < VW ? sv[i + 1] : 0u);
+        const u64 y1 = x & (x << 1), y2 = y1 & (y1 << 2), y4 = y2 & (y2 << 4);
+        u64 res = ~0ull;
+        int offb = 0, rem = m;
+        if (rem >= 8) { res &= y4 << offb; offb += 8; rem -= 8; }
+        if (rem >= 4) { res &= y2 << offb; offb += 4; rem -= 4; }
+        if (rem >= 2) { res &= y1 << offb; offb += 2; rem -= 2; }
+        if (rem >= 1) { res &= x << offb; }
+        mv[i] = (u32)(res >> 32);
     }
     __syncthreads();
     // phase 1: hash of the canonical m-mer at every symbol position of the tile (0 = not an m-mer)
     {
-        const u32 sh = 32u - 2u * (u32)m, mask2m = (1u << (2 * m)) - 1u, ones_m = (1u << m) - 1u;
+        const u32 sh = 32u - 2u * (u32)m, mask2m = (1u << (2 * m)) - 1u;
         const u64 left = n_sym - tile0;            // symbols from the tile's first to the end of the stream
         const u32 j_end = left >= (u64)NH + (u64)m ? NH : (left >= (u64)m ? (u32)(left - (u64)m) + 1u : 0u);   // m-mers start below j_end
         for (u32 j = tid; j < NH; j += MB_BLOCK) {
@@ -148,9 +176,7 @@ mb_partition_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid
             r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
             r &= mask2m;
             const u32 c = fwd < r ? fwd : r;
-            const u32 vq = j >> 5;
-            const u32 vv = __funnelshift_l(sv[vq + 1], sv[vq], j & 31u);
-            const bool ok = (vv >> (32 - m)) == ones_m && j < j_end;
+            const bool ok = ((mv[j >> 5] << (j & 31u)) >> 31) != 0u && j < j_end;
             A[j] = ok ? mb_mix32(c) : 0u;
         }
     }
@@ -182,56 +208,44 @@ mb_partition_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid
         A[j] = a < p ? a : p;
     }
     __syncthreads();
-    // phase 3a: list the boundaries -- windows whose minimum differs from their predecessor's -- in window order (ballots per 32 windows,
-    // one scan over the 128 ballot counts of the tile); segment r = [blist[r], blist[r + 1]) is a run of equal minima or of non-windows
+    // phase 3a: every warp lists the boundaries of its own 512 windows -- windows whose minimum differs from their predecessor's -- in
+    // window order (one ballot per 32 windows, a running count in a register); segment r of a warp = [blist[r], blist[r + 1]) is a run of
+    // equal minima or of non-windows, and the last one ends at the first boundary behind the warp's windows
     const u32 lane = tid & 31u, wrp = tid >> 5;
-    u32 mymask = 0;
+    {
+        u32 n = 0;
 #pragma unroll 4
-    for (u32 it = 0; it < MB_TILE / MB_BLOCK; it++) {
-        const u32 j = it * MB_BLOCK + tid;
-        const u32 cur = A[j];
-        const bool bnd = j == 0 || A[j - 1] != cur;
-        const u32 mk = __ballot_sync(0xffffffffu, bnd);
-        if (lane == it) mymask = mk;
-        if (lane == 0) cell[it * (MB_BLOCK / 32) + wrp] = __popc(mk);
+        for (u32 it = 0; it < WSEG / 32; it++) {
+            const u32 j = wrp * WSEG + it * 32 + lane;
+            const u32 cur = A[j];
+            const bool bnd = j == 0 || A[j - 1] != cur;
+            const u32 mk = __ballot_sync(0xffffffffu, bnd);
+            if (bnd) blist[wrp][n + __popc(mk & lanemask_lt())] = (unsigned short)j;
+            n += __popc(mk);
+        }
+        if (lane == 0) wcnt[wrp] = n;
     }
     __syncthreads();
-    if (wrp == 0) {
-        constexpr int NC = MB_TILE / 32, PER = NC / 32;
-        u32 c[PER], sum = 0;
-#pragma unroll
-        for (int i = 0; i < PER; i++) {
-            c[i] = cell[PER * lane + i];
-            sum += c[i];
+    if (tid == 0) {
+        u32 nx = MB_TILE;
+        for (int v = MB_BLOCK / 32 - 1; v >= 0; v--) {
+            wnext[v] = nx;
+            if (wcnt[v]) nx = blist[v][0];
         }
-        const u32 inc = warp_incl_sum(sum);
-        u32 run = inc - sum;
-#pragma unroll
-        for (int i = 0; i < PER; i++) {
-            cell[PER * lane + i] = run;
-            run += c[i];
-        }
-        if (lane == 31) cell[NC] = inc;
     }
-    __syncthreads();
-#pragma unroll 4
-    for (u32 it = 0; it < MB_TILE / MB_BLOCK; it++) {
-        const u32 mk = __shfl_sync(0xffffffffu, mymask, it);
-        if ((mk >> lane) & 1u) blist[cell[it * (MB_BLOCK / 32) + wrp] + __popc(mk & lanemask_lt())] = (unsigned short)(it * MB_BLOCK + tid);
-    }
-    const u32 nbnd = cell[MB_TILE / 32];
-    if (tid == 0) blist[nbnd] = (unsigned short)MB_TILE;
     __syncthreads();
     // phase 3b: one thread per run: reserve the record slots in the bin with ONE atomicAdd, write the record(s)
-    const u32 g_first = mb_segment_of(seg_off, nseg, tile0);
-    const u64 g_first_end = __ldg(seg_off + g_first + 1);
-    for (u32 r = tid; r < nbnd; r += MB_BLOCK) {
-        const u32 j = blist[r];
+    const bool segs_shared = nseg <= MB_SEGS;
+    const u32 g_first = segs_shared ? mb_segment_of_shared(sseg, nseg, tile0) : mb_segment_of(seg_off, nseg, tile0);
+    const u64 g_first_end = segs_shared ? sseg[g_first + 1] : __ldg(seg_off + g_first + 1);
+    const u32 nbnd = wcnt[wrp];
+    for (u32 r = lane; r < nbnd; r += 32) {
+        const u32 j = blist[wrp][r];
         const u32 mh = A[j];
         if (mh == 0u) continue;
-        const u32 len = (u32)blist[r + 1] - j;
+        const u32 len = (r + 1 < nbnd ? (u32)blist[wrp][r + 1] : wnext[wrp]) - j;
         const u64 i0 = tile0 + j;
-        const u64 g = i0 < g_first_end ? g_first : mb_segment_of(seg_off, nseg, i0);
+        const u64 g = i0 < g_first_end ? g_first : segs_shared ? mb_segment_of_shared(sseg, nseg, i0) : mb_segment_of(seg_off, nseg, i0);
         const u32 region = mb_bin_of(mh, nbins) * nchunks + (u32)(g >> 6);   // one region per bin and chunk of 64 genomes
         const u32 pieces = len <= capw ? 1u : (len + capw - 1) / capw;
         const u32 at = atomicAdd(&cursor[region], pieces);
