@@ -129,6 +129,7 @@ class AcrossExchanger:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.mode = mode if self.world > 1 and hasattr(adapter, "eng") else "nccl"
         self.ready = False
+        self.region_keys = 0
         self.rounds_peer = self.rounds_nccl = 0
         self.ctrl = adapter.new_tensor(0).device if dist.is_initialized() and dist.get_backend(group) == "nccl" else torch.device("cpu")
         if self.mode == "peer" and region_keys:
@@ -142,6 +143,7 @@ class AcrossExchanger:
         eng = self.ad.eng
         if self.ready:
             self.close()
+        self.region_keys = int(region_keys)
         ok, why, handle = 1, "", bytes(64)
         try:
             handle = eng.peer_alloc(self.world, self.rank, 8 * key_words(self.k), region_keys)
@@ -186,7 +188,9 @@ class AcrossExchanger:
     def _grow_from(self, per_dest_keys: Sequence[int]):
         need = torch.tensor([max(per_dest_keys) if len(per_dest_keys) else 0], dtype=torch.int64, device=self.ctrl)
         dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
-        self._setup(max(int(need.item()) * 13 // 10, 1024))
+        # 1.3 x what this round needed -- and, when regions that existed already were too small (a k sweep: the distinct k-mers grow
+        # ~4 x per step at small k), at least twice the old size, so that a sweep re-maps the buffers O(log) times, not once per k
+        self._setup(max(int(need.item()) * 13 // 10, 2 * self.region_keys, 1024))
 
     def finish(self):
         if self.world == 1:
@@ -199,7 +203,7 @@ class AcrossExchanger:
                 self._grow_from([x // w for x in info["send_words_per_rank"]])
             return hist, info
         eng = self.ad.eng
-        hashed = eng.group_sets_hashed
+        hashed = 0 if self.k in (32, 64) else 1      # a property of k (csrc/api.cu: count_stage), the same on every rank -- also on one without groups
         counts, ovf = eng.peer_counts(self.world)
         row = torch.from_numpy(np.concatenate([counts.astype(np.int64), [1 if ovf else 0]])).to(self.ctrl)
         table = torch.empty((self.world, self.world + 1), dtype=torch.int64, device=self.ctrl)

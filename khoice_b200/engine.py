@@ -320,6 +320,14 @@ class Engine:
     def hash_overflows(self) -> int:
         return int(self.lib.khb_hash_overflows(self.ctx))
 
+    def healthy(self) -> bool:
+        """False once the context carries a sticky CUDA error (every later call would fail): a long-lived worker exits then."""
+        try:
+            self._chk(self.lib.khb_sync(self.ctx))
+            return True
+        except KhbError:
+            return False
+
     @property
     def bins_counters(self) -> dict:
         """Minimizer-bin path: groups handed to the sort path, bins redone in hash classes, groups partitioned a second time."""

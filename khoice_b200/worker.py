@@ -51,9 +51,20 @@ def request(socket_path: str, argv: List[str], cwd: Optional[str] = None, timeou
     return int(reply.get("rc", 1))
 
 
-def serve(socket_path: str, handler: Callable[[List[str]], int], ready: Optional[Callable[[], None]] = None) -> int:
+def _reply(conn, rc: int, stderr: str) -> None:
+    """A client that went away (a cancelled Snakemake job) must not take the worker down with it."""
+    try:
+        conn.sendall((json.dumps({"rc": rc, "stderr": stderr}) + "\n").encode())
+    except OSError:
+        pass
+
+
+def serve(socket_path: str, handler: Callable[[List[str]], int], ready: Optional[Callable[[], None]] = None,
+          healthy: Optional[Callable[[], bool]] = None, request_timeout: float = 30.0) -> int:
     """Server loop: accept, chdir to the client's working directory, run handler(argv), reply.  Returns the number of
-    requests served when a client sends [STOP]."""
+    requests served when a client sends [STOP].  A client that disconnects or never finishes its request line (request_timeout
+    seconds) is dropped; when `healthy()` turns false (a sticky CUDA error in the engine) the loop ends with SystemExit(3), so that
+    the rules fail loudly instead of every later request failing against a dead context."""
     if os.path.exists(socket_path):
         os.remove(socket_path)
     served = 0
@@ -68,19 +79,24 @@ def serve(socket_path: str, handler: Callable[[List[str]], int], ready: Optional
                 conn, _ = srv.accept()
                 with conn:
                     buf = b""
-                    while not buf.endswith(b"\n"):
-                        chunk = conn.recv(65536)
-                        if not chunk:
-                            break
-                        buf += chunk
+                    try:
+                        conn.settimeout(request_timeout)
+                        while not buf.endswith(b"\n"):
+                            chunk = conn.recv(65536)
+                            if not chunk:
+                                break
+                            buf += chunk
+                        conn.settimeout(None)
+                    except OSError:                                 # timeout / reset while reading the request: drop this client
+                        continue
                     try:
                         req = json.loads(buf.decode())
                         argv = [str(a) for a in req["argv"]]
                     except (ValueError, KeyError, TypeError):
-                        conn.sendall((json.dumps({"rc": 1, "stderr": "khoice-b200 worker: malformed request\n"}) + "\n").encode())
+                        _reply(conn, 1, "khoice-b200 worker: malformed request\n")
                         continue
                     if argv == [STOP]:
-                        conn.sendall((json.dumps({"rc": 0, "stderr": ""}) + "\n").encode())
+                        _reply(conn, 0, "")
                         return served
                     err = io.StringIO()
                     rc = 1
@@ -95,7 +111,9 @@ def serve(socket_path: str, handler: Callable[[List[str]], int], ready: Optional
                     finally:
                         os.chdir(home)
                     served += 1
-                    conn.sendall((json.dumps({"rc": rc, "stderr": err.getvalue()}) + "\n").encode())
+                    _reply(conn, rc, err.getvalue())
+                    if healthy is not None and not healthy():
+                        raise SystemExit(3)
         finally:
             if os.path.exists(socket_path):
                 os.remove(socket_path)
@@ -121,7 +139,7 @@ def main(argv: Optional[List[str]] = None) -> int:
     eng = Engine(a.device)                 # fails loudly without a B200
     cli.set_engine(eng)
     try:
-        n = serve(a.socket, cli.main, ready=lambda: print("khoice-b200 worker ready", flush=True))
+        n = serve(a.socket, cli.main, ready=lambda: print("khoice-b200 worker ready", flush=True), healthy=eng.healthy)
         print(f"khoice-b200 worker: served {n} requests", flush=True)
     finally:
         cli.set_engine(None)

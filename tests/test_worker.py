@@ -71,3 +71,50 @@ def test_shell_shims_forward_when_the_socket_variable_is_set(tmp_path):
     assert r.returncode == 0
     t.join(10)
     assert out["served"] == 2
+
+
+def test_worker_survives_clients_that_vanish_or_stall_and_stops_when_unhealthy(tmp_path):
+    """A client killed in mid-request (a cancelled Snakemake job), one that connects and never sends its line, and one that is gone when
+    the reply is due must not take the shared worker down; an engine with a sticky error ends the loop (SystemExit 3)."""
+    import socket
+    import time
+    from khoice_b200 import worker
+    state = {"ok": True}
+
+    def handler(argv):
+        if argv[0] == "slow":
+            time.sleep(0.3)
+        if argv[0] == "poison":
+            state["ok"] = False
+        return 0
+
+    sock = str(tmp_path / "w.sock")
+    ready = threading.Event()
+    out = {}
+
+    def run():
+        try:
+            out["served"] = worker.serve(sock, handler, ready=ready.set, healthy=lambda: state["ok"], request_timeout=0.5)
+        except SystemExit as e:
+            out["exit"] = e.code
+
+    t = threading.Thread(target=run, daemon=True)
+    t.start()
+    assert ready.wait(10)
+    c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)            # half a request, then gone
+    c.connect(sock)
+    c.sendall(b'{"argv": ["km')
+    c.close()
+    c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)            # connects and never sends a newline: dropped after the timeout
+    c.connect(sock)
+    c.sendall(b'{"argv": ["kmc"')
+    assert worker.request(sock, ["kmc", "still", "alive"]) == 0
+    c.close()
+    c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)            # gone before the reply is written
+    c.connect(sock)
+    c.sendall(b'{"argv": ["slow"], "cwd": null}\n')
+    c.close()
+    assert worker.request(sock, ["kmc", "after", "the", "broken", "pipe"]) == 0
+    assert worker.request(sock, ["poison"]) == 0                      # the request itself is answered, then the worker leaves
+    t.join(10)
+    assert out.get("exit") == 3
