@@ -708,7 +708,13 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
     u64 my_drecords = 0;
     auto flush_records = [&](u32 cls, u32 ncls) {
         const u32 nw = s_wtotal < MC_WCAP ? s_wtotal : MC_WCAP;
-        my_drecords += s_dcount < dcap ? s_dcount : dcap;
+        const u32 nd = s_dcount < dcap ? s_dcount : dcap;
+        my_drecords += nd;
+        for (u32 id = tid; id < nd; id += BLOCK) {                                 // window t of the layout belongs to record map[t]
+            const u32 len = (u32)sm.dstore[(size_t)id * (KW + 1)], woff = sm.dwoff[id];
+            for (u32 e = 0; e < len; e++) sm.map[woff + e] = (unsigned short)id;
+        }
+        __syncthreads();
         bool ok = true;
         for (u32 t0 = 0; t0 < nw; t0 += BLOCK) {                                // every lane of a warp stays in the loop: the append below is warp-wide
             const u32 t = t0 + tid;
@@ -779,8 +785,7 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
                                     *(volatile u32 *)&sm.rtab[slot] = 0u;
                                     break;
                                 }
-                                for (u32 t = woff; t < wend; t++) sm.map[t] = (unsigned short)id;
-                                sm.dwoff[id] = (unsigned short)woff;
+                                sm.dwoff[id] = (unsigned short)woff;     // its windows are entered into the map at flush time, by all threads
                                 u64 *D = sm.dstore + (size_t)id * (KW + 1);
                                 D[0] = (u64)len;
 #pragma unroll
