@@ -1,23 +1,27 @@
-// bins.cu -- the minimizer-bin group stage (default group path for 17 <= k <= 31): what `kmc` + `kmc_tools complex` compute for one
-// group (/root/reference/workflow/rules/exp_type_1.smk:156-191: per-genome canonical k-mer sets, their counter-summing union, its
+// bins.cu -- the minimizer-bin group stage (default group path for 17 <= k <= 63, k != 32): what `kmc` + `kmc_tools complex` compute for
+// one group (/root/reference/workflow/rules/exp_type_1.smk:156-191: per-genome canonical k-mer sets, their counter-summing union, its
 // histogram) WITHOUT a sort.  KMC's own idea, rebuilt for one B200: windows that share a minimizer go to the same bin as compact
 // super-k-mer records; a bin is small enough to be counted by ONE CTA in a shared-memory table of (k-mer, genome bits).
 //
-//   pass P  mb_partition_kernel   packed symbol stream -> per-bin regions of 32-byte super-k-mer records
+//   pass P  mb_partition_kernel   packed symbol stream -> regions (one per bin and chunk of 64 genomes) of 24- / 32-byte super-k-mer records
 //                                 (tile of 4096 window starts; 32-bit hashes of the canonical 13-mers; sliding minimum over the
 //                                 k - 12 hashes of a window by the van Herk / Gil-Werman prefix/suffix trick in shared memory;
 //                                 a maximal run of windows with one minimum = one record; ONE global atomicAdd per record)
 //   pass C  mb_count_kernel       persistent CTAs stream their bins' records through a double-buffered shared-memory ring with
-//                                 cp.async.bulk + mbarrier (the next bin is in flight while this one is counted), expand every
-//                                 window's canonical k-mer, insert it into an open-addressing table in shared memory, set the
-//                                 genome's bit; at the end of a bin: popcount per slot -> step_4 histogram, distinct keys
-//                                 (mixed like K2's) appended to the group-set store, table left clean for the next bin
-//   pass B  mb_bigbin_kernel      bins whose table filled up are redone with the key space split into hash classes
+//                                 cp.async.bulk + mbarrier (the next bin is in flight while this one is counted).  Two levels: every
+//                                 record is looked up in an index of the bin's DISTINCT records (content -> genome mask); only the
+//                                 distinct records are expanded into canonical k-mers and inserted into an open-addressing table in
+//                                 shared memory with their whole genome mask.  End of a bin: popcount per claimed slot -> step_4
+//                                 histogram, distinct keys (mixed like K2's) appended to the group-set store, table left clean
+//   pass B  mb_bigbin_kernel      (bin, hash class) pairs whose table filled up, redone window by window with the class split further
+//   mb_region_scan_kernel         exact region offsets for the second partition attempt after a region overflowed
+//   mb_across_kernel (+ ma_*)     OPT-IN across-group stage bin by bin over the key segments the groups left in the store (exact, but
+//                                 slower than the prefix sort: KHB_ACROSS_MODE=bins)
 //
-// HBM traffic: ~2.3 bytes per window written and read once (records) + 8 bytes per DISTINCT k-mer -- against ~100 bytes per window
-// of the prefix sort.  The bound is shared-memory work per window, not HBM.
-// Every result is exact; whatever does not fit (a bin region overflows, a table cannot hold a bin) makes the caller redo the group
-// on the sort path.
+// HBM traffic: ~2.4 bytes per window written and read once (records) + 8 / 16 bytes per DISTINCT k-mer -- against ~100 bytes per window
+// of the prefix sort.  The bound is shared-memory work and instruction issue, not HBM.
+// Every result is exact; a region that overflows makes the caller partition once more with the counted sizes, and only a class of a
+// bin that cannot be split small enough for the table sends the group to the sort path.
 #include <stdlib.h>
 
 #include "khb_common.cuh"
