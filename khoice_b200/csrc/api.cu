@@ -31,7 +31,7 @@ int khb_presence_count_impl(khb_ctx *, const u64 *, const u32 *, size_t, int, in
 size_t khb_hash_table_bytes(int, int, u64, int *, int *);
 int khb_bins_eligible(int, int, u64);
 int khb_bins_count_impl(khb_ctx *, const u64 *, const u32 *, u64, int, const u64 *, int, u32, u32, u64 *, void *, u64 *, u64 *, u64 *, int, u32, u32 *, void *, u64 *, u64,
-                        u64);
+                        u64, khb_peer_route);
 int khb_bins_across_impl(khb_ctx *, int, const void *, const void *, u64, u32, int, u32, u32, u64 *, u64 *, u64 *);
 int khb_hash_count_impl(khb_ctx *, const u64 *, const u32 *, u64, int, const u64 *, const u64 *, int, u32 *, int, int, u32, u32, u64 *, void *, u64 *, u64 *, int,
                         void *, u64 *, u32 *);
@@ -845,6 +845,7 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
         bool use_bins = !small_k && !use_hash && hashed && !pivot && (ctx->group_mode == KHB_GROUP_AUTO || ctx->group_mode == KHB_GROUP_BINS) &&
                         khb_bins_eligible(k, n_genomes, n_sym);
         int bins_exact = 0;
+        khb_peer_route bins_route = {0u, 0ull, nullptr, nullptr};
         // the store's segment events (across-group stage bin by bin): kept while every retained group comes through the bins
         const bool log_events = use_bins && keep_set && across_by_bins_wanted() && (ctx->gs_len == 0 || ctx->ev_ok);
         u32 bins_nb = 0;
@@ -864,9 +865,11 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
                 if ((rc = ev_reserve(ctx, (u64)(ctx->ev_nb ? ctx->ev_nb : n_sym / 1024 + 16) * 8 + 4096))) return rc;
                 if (bins_exact) KHB_CUDA(ctx, cudaMemcpyAsync(ctx->ev_count, &ctx->ev_len, 8, cudaMemcpyHostToDevice, ctx->stream));   // forget the failed attempt's events
             }
+            // multi-GPU: the end-of-bin passes store every distinct key straight into its owner's region (peer.cu), no separate push pass
+            if (keep_set && (rc = khb_peer_route_get(ctx, (int)W, &bins_route))) return rc;
             if ((rc = khb_bins_count_impl(ctx, d_codes, d_valid, n_sym, k, d_seg, n_genomes, KHB_COUNTER_MAX, nbins, d_hist, out_keys, d_runs, d_pairs,
                                           ctx->d_mail + 3, bins_exact, ev ? ctx->ev_nb : 0u, &bins_nb, ev ? ctx->ev_buf : nullptr, ctx->ev_count, ctx->ev_cap,
-                                          ctx->gs_len))) return rc;
+                                          ctx->gs_len, bins_route))) return rc;
             if (ev) KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 130000, ctx->ev_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
         } else if (use_hash) {
             u32 *tab = nullptr;
@@ -930,6 +933,7 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
                 ctx->bins_fallbacks++;
                 use_bins = false;
                 if (keep_set) ctx->ev_ok = 0;
+                if (bins_route.world && (rc = khb_peer_poison(ctx))) return rc;   // some of this group's keys are at their owners already: redo the round over NCCL
                 tm.n = 3;
                 goto again;
             }
@@ -974,6 +978,7 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
             }
             ctx->gs_len += d_g;
             ctx->gs_groups += 1;
+            if (use_bins && bins_route.world) khb_peer_mark_pushed(ctx);
         }
         if (stats) {
             stats->fasta_bytes = nbytes;

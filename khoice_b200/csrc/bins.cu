@@ -533,6 +533,59 @@ template <int KW> __device__ __forceinline__ void mb_slot_reset(const mc_smem &s
     if (KW == 3) sm.ttag[i] = 0u;
     else sm.tkey[i] = MB_EMPTY;
 }
+// Multi-GPU, first half: the mixed key of slot i goes back into the slot, its owner and its rank among the bin's keys for that owner into
+// the slot's bit word (the bits were counted already); second half (mb_route_store) after the owners' ranges were reserved.
+template <int KW> __device__ __forceinline__ void mb_route_note(const mc_smem &sm, u32 i, int k, u32 world, u32 *s_ocnt)
+{
+    u32 o;
+    if (KW == 3) {
+        u64 hi = sm.tkey[i], lo = sm.tlo[i];
+        kmer_mix128(hi, lo, k);
+        sm.tkey[i] = hi;
+        sm.tlo[i] = lo;
+        Key128 kk;
+        kk.lo = lo;
+        kk.hi = hi;
+        o = part_of(kk, world);
+    } else {
+        Key64 kk;
+        kk.v = kmer_mix64(sm.tkey[i], k);
+        sm.tkey[i] = kk.v;
+        o = part_of(kk, world);
+    }
+    const u32 r = atomicAdd(&s_ocnt[o], 1u);
+    sm.tbits[i] = ((u64)o << 32) | r;
+}
+template <int KW> __device__ __forceinline__ void mb_route_store(const mc_smem &sm, u32 i, const khb_peer_route &route, const u64 *s_obase, void *out, u64 at)
+{
+    const u64 w = sm.tbits[i];
+    const u32 o = (u32)(w >> 32), r = (u32)w;
+    const u64 pos = s_obase[o] + r;
+    if (KW == 3) {
+        Key128 kk;
+        kk.lo = sm.tlo[i];
+        kk.hi = sm.tkey[i];
+        if (pos < route.cap) ((Key128 *)route.dst[o])[pos] = kk;
+        if (out) ((Key128 *)out)[at] = kk;
+    } else {
+        const u64 v = sm.tkey[i];
+        if (pos < route.cap) ((u64 *)route.dst[o])[pos] = v;
+        if (out) ((u64 *)out)[at] = v;
+    }
+    sm.tbits[i] = 0ull;
+}
+// between the halves: one reservation per owner on the sender-side cursor (no remote atomics)
+__device__ __forceinline__ void mb_route_reserve(const khb_peer_route &route, u32 *s_ocnt, u64 *s_obase)
+{
+    const u32 o = threadIdx.x;
+    if (o < route.world) {
+        const u32 c = s_ocnt[o];
+        s_obase[o] = c ? atomicAdd((unsigned long long *)&route.cursor[o], (unsigned long long)c) : 0ull;
+        if (c && s_obase[o] + c > route.cap) route.cursor[64] = 1ull;   // region full: the caller redoes the round over NCCL
+        s_ocnt[o] = 0u;
+    }
+}
+
 // the k-mer of slot i, mixed like K2's keys (kmer_mix64 / kmer_mix128), to position `at` of the group-set store
 template <int KW> __device__ __forceinline__ void mb_emit(const mc_smem &sm, u32 i, void *out, u64 at, int k)
 {
@@ -571,13 +624,15 @@ __global__ void __launch_bounds__(BLOCK)
 mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32 nbins, u32 cap, int k, mc_geom geo, u32 n_genomes, u32 cs,
                 u32 thr1 /* records one pass over a bin may hold */, u32 over_cap, u64 *__restrict__ hist, void *__restrict__ out_keys,
                 u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs, u32 *__restrict__ over_list, u32 *__restrict__ over_count, u64 *__restrict__ d_stat,
-                const u64 *__restrict__ roff, mb_evlog evlog)
+                const u64 *__restrict__ roff, mb_evlog evlog, khb_peer_route route)
 {
     extern __shared__ __align__(16) unsigned char mc_raw[];
     __shared__ __align__(8) u64 bars[2];
     __shared__ mc_desc desc[2];
     __shared__ u32 s_over, s_distinct, s_dcount, s_wtotal, s_dfull;
     __shared__ u32 s_cn[MULTI ? 128 : 1];   // thread 0: records per chunk of the bin it is feeding
+    __shared__ u32 s_ocnt[64];              // multi-GPU: keys of the bin per owner ...
+    __shared__ u64 s_obase[64];             // ... and where they go in the owner's region
     __shared__ u64 s_base;
     const u32 s_log2 = geo.s_log2, S = 1u << s_log2, nchunks = geo.nchunks, hrows = geo.hrows, dcap = geo.dcap, RT = 1u << geo.rt_log2;
     const mc_smem sm = mc_carve(mc_raw, KW, geo);
@@ -598,6 +653,7 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
         s_dcount = 0;
         s_wtotal = 0;
         s_dfull = 0;
+        for (int o = 0; o < 64; o++) s_ocnt[o] = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -890,10 +946,24 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
             if (cc == 1u) n_one++;
             else if (cc == c_all) n_all++;
             else if (cc <= hrows) atomicAdd(&sm.hist[cc], 1u);
-            if (out_keys) mb_emit<KW>(sm, i, out_keys, base + j, k);
-            mb_slot_reset<KW>(sm, i);
+            if (route.world && out_keys) {
+                mb_route_note<KW>(sm, i, k, route.world, s_ocnt);     // multi-GPU: the key leaves for its owner below
+            } else {
+                if (out_keys) mb_emit<KW>(sm, i, out_keys, base + j, k);
+                mb_slot_reset<KW>(sm, i);
+            }
         }
         __syncthreads();
+        if (route.world && out_keys) {
+            mb_route_reserve(route, s_ocnt, s_obase);
+            __syncthreads();
+            for (u32 j = tid; j < nd_keys; j += BLOCK) {
+                const u32 i = sm.slots[j];
+                mb_route_store<KW>(sm, i, route, s_obase, out_keys, base + j);
+                mb_slot_reset<KW>(sm, i);
+            }
+            __syncthreads();
+        }
         if (tid == 0) s_distinct = 0;
         __syncthreads();
     }
@@ -926,10 +996,12 @@ __global__ void __launch_bounds__(MC_BLOCK)
 mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32 cap, int k, mc_geom geo, u32 n_genomes, u32 cs,
                  u64 *__restrict__ hist, void *__restrict__ out_keys, u64 *__restrict__ d_cursor, u64 *__restrict__ d_pairs,
                  const u32 *__restrict__ over_list, const u32 *__restrict__ over_count, u32 over_cap, u64 *__restrict__ flags, const u64 *__restrict__ roff,
-                 mb_evlog evlog)
+                 mb_evlog evlog, khb_peer_route route)
 {
     extern __shared__ __align__(16) unsigned char mc_raw[];
     __shared__ u32 s_over, s_distinct, ws[33];
+    __shared__ u32 s_ocnt[64];
+    __shared__ u64 s_obase[64];
     __shared__ u64 s_base;
     const u32 s_log2 = geo.s_log2, S = 1u << s_log2, nchunks = geo.nchunks, hrows = geo.hrows;
     const mc_smem sm = mc_carve(mc_raw, KW, geo);
@@ -944,6 +1016,7 @@ mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u3
         if (MULTI) sm.tcnt[i] = 0u;
     }
     for (u32 i = tid; i <= hrows; i += MC_BLOCK) sm.hist[i] = 0u;
+    if (tid < 64) s_ocnt[tid] = 0u;
     if (tid == 0) {
         s_over = 0;
         s_distinct = 0;
@@ -1038,10 +1111,24 @@ mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u3
                 pairs += c;
                 const u32 cc = c > cs ? cs : c;
                 if (cc <= hrows) atomicAdd(&sm.hist[cc], 1u);
-                if (out_keys) mb_emit<KW>(sm, i, out_keys, base + j, k);
-                mb_slot_reset<KW>(sm, i);
+                if (route.world && out_keys) {
+                    mb_route_note<KW>(sm, i, k, route.world, s_ocnt);
+                } else {
+                    if (out_keys) mb_emit<KW>(sm, i, out_keys, base + j, k);
+                    mb_slot_reset<KW>(sm, i);
+                }
             }
             __syncthreads();
+            if (route.world && out_keys) {
+                mb_route_reserve(route, s_ocnt, s_obase);
+                __syncthreads();
+                for (u32 j = tid; j < nd_keys; j += MC_BLOCK) {
+                    const u32 i = sm.slots[j];
+                    mb_route_store<KW>(sm, i, route, s_obase, out_keys, base + j);
+                    mb_slot_reset<KW>(sm, i);
+                }
+                __syncthreads();
+            }
             if (tid == 0) s_distinct = 0;
             __syncthreads();
         }
@@ -1078,7 +1165,7 @@ int khb_bins_eligible(int k, int n_genomes, u64 n_sym)
 // partition again into regions of exactly the sizes that attempt counted (they are still in the context's scratch).
 int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u64 n_sym, int k, const u64 *d_seg_off, int n_genomes, u32 cs, u32 nbins_hist,
                         u64 *d_hist, void *d_out_keys, u64 *d_runs, u64 *d_pairs, u64 *d_stat, int exact, u32 nb_fixed, u32 *nb_used, void *ev_buf,
-                        u64 *ev_count, u64 ev_cap, u64 store_base)
+                        u64 *ev_count, u64 ev_cap, u64 store_base, khb_peer_route route)
 {
     if (!khb_bins_eligible(k, n_genomes, n_sym)) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: k=%d / %d genomes not supported", k, n_genomes);
     const int KW = k <= 32 ? 2 : 3;               // record words of symbols: k - 1 + 32 windows fit 64 (k <= 32) or 96 symbols
@@ -1215,7 +1302,7 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
         evlog.cap = ev_cap;
         evlog.store_base = store_base;
         const u32 *c_list = d_over_list, *c_cnt = d_over_count;
-        void *cargs[] = {&c_rec, &c_cur, &nb_, &cap_, &k_, &geo, &n_gen, &cs_, &thr_, &ocap_, &d_hist, &keys_, &d_runs, &d_pairs, &d_over_list, &d_over_count, &d_stat, &roff, &evlog};
+        void *cargs[] = {&c_rec, &c_cur, &nb_, &cap_, &k_, &geo, &n_gen, &cs_, &thr_, &ocap_, &d_hist, &keys_, &d_runs, &d_pairs, &d_over_list, &d_over_count, &d_stat, &roff, &evlog, &route};
         if (mb_env("KHB_BINS_VERBOSE", 0))
             fprintf(stderr, "[bins] k=%d genomes=%d windows=%llu bins=%u chunks=%u cap=%u slots=2^%u dcap=%u thr1=%u rho_w=%.3f shm=%zu ctas/sm=%d block=%d\n", k, n_genomes,
                     (unsigned long long)n_sym, nb, geo.nchunks, cap, geo.s_log2, geo.dcap, thr1, rho_w, shm, per_sm, block);
@@ -1223,7 +1310,7 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
         KHB_CUDA(ctx, cudaLaunchKernel(fn, dim3(grid), dim3(block), cargs, shm, ctx->stream));
         khb_prof_end(ctx, KHB_K_BIN_COUNT, 0);
         KHB_LAUNCH_CHECK(ctx);
-        void *bargs[] = {&c_rec, &c_cur, &cap_, &k_, &geo, &n_gen, &cs_, &d_hist, &keys_, &d_runs, &d_pairs, &c_list, &c_cnt, &ocap_, &d_stat, &roff, &evlog};
+        void *bargs[] = {&c_rec, &c_cur, &cap_, &k_, &geo, &n_gen, &cs_, &d_hist, &keys_, &d_runs, &d_pairs, &c_list, &c_cnt, &ocap_, &d_stat, &roff, &evlog, &route};
         KHB_CUDA(ctx, cudaLaunchKernel(bfn, dim3((u32)ctx->num_sms * 2u), dim3(MC_BLOCK), bargs, shm, ctx->stream));
         KHB_LAUNCH_CHECK(ctx);
         mb_region_max_kernel<<<(unsigned)ctx->num_sms * 4u, 256, 0, ctx->stream>>>(d_cur, n_regions, d_stat + 3);

@@ -240,6 +240,17 @@ int khb_fail(khb_ctx *ctx, int code, const char *fmt, ...);
 int khb_cuda_fail(khb_ctx *ctx, cudaError_t e, const char *what, const char *file, int line);
 int khb_scratch_get(khb_ctx *ctx, int slot, size_t bytes, void **out);
 int khb_peer_wait(khb_ctx *ctx);  // wait for pushes in flight (before the group-set store moves)
+// Where the multi-GPU exchange wants a group's distinct keys (peer.cu): owner = part_of(key, world), region dst[owner] of `cap` keys,
+// filled through the sender-side cursor[owner]; cursor[64] != 0: some region overflowed.  world = 0: no exchange is open.
+struct khb_peer_route {
+    u32 world;
+    u64 cap;
+    u64 *cursor;
+    void *const *dst;
+};
+int khb_peer_route_get(khb_ctx *ctx, int key_bytes, khb_peer_route *out);  // for kernels that push while they emit (bins.cu)
+void khb_peer_mark_pushed(khb_ctx *ctx);                                    // ... the store's keys so far are at their owners
+int khb_peer_poison(khb_ctx *ctx);                                          // ... or not: make this round fall back to the NCCL route
 
 #define KHB_CUDA(ctx, expr)                                                           \
     do {                                                                              \

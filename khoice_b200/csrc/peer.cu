@@ -293,6 +293,41 @@ uint64_t khb_peer_region_keys(const khb_ctx *ctx) { return ctx && ctx->peer ? ct
 
 }  // extern "C"
 
+// The minimizer-bin group stage pushes every bin's distinct keys to their owners from its own end-of-bin pass (bins.cu), so that
+// khb_peer_push finds nothing left to do.  KHB_PEER_FUSE=0 keeps the separate push kernel.
+int khb_peer_route_get(khb_ctx *ctx, int key_bytes, khb_peer_route *out)
+{
+    out->world = 0;
+    out->cap = 0;
+    out->cursor = nullptr;
+    out->dst = nullptr;
+    khb_peer *pp = ctx->peer;
+    static int fuse = -1;
+    if (fuse < 0) {
+        const char *e = getenv("KHB_PEER_FUSE");
+        fuse = e ? atoi(e) : 1;
+    }
+    if (!fuse || !pp || !pp->opened || pp->key_bytes != key_bytes || pp->push_stream) return KHB_OK;
+    if (pp->pushed_upto != ctx->gs_len) return KHB_OK;   // earlier keys of the store are still waiting for khb_peer_push: keep the order simple
+    out->world = (u32)pp->world;
+    out->cap = pp->region_keys;
+    out->cursor = pp->d_cursor;
+    out->dst = pp->d_dst;
+    return KHB_OK;
+}
+void khb_peer_mark_pushed(khb_ctx *ctx)
+{
+    if (ctx->peer) ctx->peer->pushed_upto = ctx->gs_len;
+}
+int khb_peer_poison(khb_ctx *ctx)
+{
+    khb_peer *pp = ctx->peer;
+    if (!pp || !pp->opened) return KHB_OK;
+    static const u64 one = 1;
+    KHB_CUDA(ctx, cudaMemcpyAsync(pp->d_cursor + PP_MAXPARTS, &one, sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    return KHB_OK;
+}
+
 // used by khb_peer_import (api.cu owns the group-set store)
 int khb_peer_regions(khb_ctx *ctx, const void **recv, u64 *region_keys, int *world, int *key_bytes)
 {

@@ -36,6 +36,7 @@ for k in (31, 21, 47):
     w_ref, a_ref, st_ref = O.exp1(flat, gid, G, k, nbins=64)
     ex = kd.AcrossExchanger(ad, k, G, nbins=64, mode="peer", region_keys=200_000)
     assert ex.ready and eng.peer_region_keys == 200_000
+    eng.profile_enable(True)
     for rnd in range(3):                       # the regions are reused round after round
         eng.group_sets_reset()
         ex.begin()
@@ -49,6 +50,12 @@ for k in (31, 21, 47):
         tot = torch.tensor([info["local_distinct"]]); dist.all_reduce(tot)
         assert int(tot.item()) == st_ref["distinct"]           # every k-mer has exactly one owner
     assert ex.rounds_peer == 3 and ex.rounds_nccl == 0
+    # the minimizer-bin stage stores its keys into the owners' regions from its own end-of-bin pass: no push kernel runs
+    # (KHB_PEER_FUSE=0 and the push on its own stream keep the separate pass)
+    pushes = eng.profile_read()["partition"]["launches"]
+    fused = os.environ.get("KHB_PEER_FUSE", "1") != "0" and os.environ.get("KHB_PEER_ASYNC", "0") == "0"
+    assert (pushes == 0) == fused, (k, pushes, fused)
+    eng.profile_enable(False)
     ex.close()
 # a region that cannot hold a rank's share raises the overflow flag (the driver then redoes the round over NCCL)
 ex = kd.AcrossExchanger(ad, 31, G, nbins=64, mode="peer", region_keys=64)
@@ -65,14 +72,14 @@ print("peer ok", rank)
 """
 
 
-@pytest.mark.parametrize("async_push", ["0", "1"])
-def test_two_ranks_on_one_gpu_push_over_ipc(async_push):
+@pytest.mark.parametrize("async_push,fuse", [("0", "1"), ("0", "0"), ("1", "1")])
+def test_two_ranks_on_one_gpu_push_over_ipc(async_push, fuse):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     procs = []
     for rank in range(2):
-        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), KHB_PEER_ASYNC=async_push)
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), KHB_PEER_ASYNC=async_push, KHB_PEER_FUSE=fuse)
         procs.append(subprocess.Popen([sys.executable, "-c", SCRIPT % {"root": ROOT}], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     outs = []
     for p in procs:
