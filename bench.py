@@ -85,29 +85,30 @@ def workload(world: int = 1):
     return wl
 
 
-def _gen_group(args):
-    from khoice_b200 import synth
-    cfg, g, n = args
-    return g, [synth.make_genome(cfg, g, i) for i in range(1, n + 1)]
-
-
 def _gen_genome(args):
     from khoice_b200 import synth
     cfg, g, i = args
     return g, i, synth.make_genome(cfg, g, i)
 
 
-def generate_groups(cfg, group_numbers, procs, genomes=None):
-    """{group: [fasta bytes]} generated with a fork pool (must run before CUDA is initialised)."""
+def generate_groups(cfg, group_numbers, procs, genomes=None, genome_range=None):
+    """{group: [fasta bytes]} generated with a fork pool (must run before CUDA is initialised).  genome_range = (lo, hi): only the
+    genomes lo + 1 .. hi of every group (a team member's slice)."""
     n = genomes or cfg.genomes_per_group
-    if procs <= 1 or len(group_numbers) * n <= 2:
-        return dict(_gen_group((cfg, g, n)) for g in group_numbers)
-    out = {g: [None] * n for g in group_numbers}
-    jobs = [(cfg, g, i) for g in group_numbers for i in range(1, n + 1)]   # per genome: few big groups still use every worker
+    lo, hi = genome_range or (0, n)
+    if procs <= 1 or len(group_numbers) * (hi - lo) <= 2:
+        return {g: [synth_genome(cfg, g, i) for i in range(lo + 1, hi + 1)] for g in group_numbers}
+    out = {g: [None] * (hi - lo) for g in group_numbers}
+    jobs = [(cfg, g, i) for g in group_numbers for i in range(lo + 1, hi + 1)]   # per genome: few big groups still use every worker
     with mp.get_context("fork").Pool(min(procs, len(jobs))) as pool:
-        for g, i, text in pool.imap_unordered(_gen_genome, jobs, chunksize=max(1, n // 8)):
-            out[g][i - 1] = text
+        for g, i, text in pool.imap_unordered(_gen_genome, jobs, chunksize=max(1, (hi - lo) // 8)):
+            out[g][i - 1 - lo] = text
     return out
+
+
+def synth_genome(cfg, g, i):
+    from khoice_b200 import synth
+    return synth.make_genome(cfg, g, i)
 
 
 class ClockSampler:
@@ -425,15 +426,25 @@ def main():
     cfg = synth.SynthConfig(n_groups=n_groups_total, genomes_per_group=wl["genomes"], genome_len=wl["genome_len"])
 
     # 1. synthetic data for this rank's groups (fork pool: before any CUDA initialisation)
-    from khoice_b200.dist import groups_of_rank
-    mine = groups_of_rank(n_groups_total, rank, world)
+    from khoice_b200.dist import genome_slices, groups_of_rank, team_shape
+    # Teams: where whole groups do not divide evenly over the GPUs of a fixed-size job (config 4 on 8 GPUs: 20 groups), every group is
+    # sharded over the T members of a team -- genomes over members, minimizer bins over owners (dist.TeamSharder) -- and the groups are
+    # dealt to the world / T teams.  KHB_BENCH_TEAM=T forces a team size (1: whole groups).
+    T = env_int("KHB_BENCH_TEAM", 0) or (team_shape(n_groups_total, world) if wl["scaling"] == "strong" and not wl["ks"] else 1)
+    if T < 1 or world % T or T > 8 or wl["genomes"] < T:
+        raise SystemExit(f"KHB_BENCH_TEAM={T}: the team size must divide the {world} ranks, be at most 8 and at most the genomes of a group")
+    n_teams, team_idx, member = world // T, rank // T, rank % T
+    mine = groups_of_rank(n_groups_total, team_idx, n_teams)
+    slices = genome_slices(wl["genomes"], T)
+    slice_sizes = [hi - lo for lo, hi in slices]
     procs = max(1, (os.cpu_count() or 8) // max(world, 1))
     t0 = time.time()
-    groups = generate_groups(cfg, mine, min(procs, 32))
-    # N>1 parity: rank 0 recomputes one group owned by another rank
+    groups = generate_groups(cfg, mine, min(procs, 32), genome_range=slices[member] if T > 1 else None)
+    # N>1 parity: rank 0 recomputes one group owned by another rank (teams: one group of another team -- or, with a single team, its
+    # own first group -- unsharded on rank 0)
     foreign = None
     if world > 1 and rank == 0:
-        fg = groups_of_rank(n_groups_total, 1, world)
+        fg = groups_of_rank(n_groups_total, 1, n_teams) if n_teams > 1 else mine[:1]
         if fg:
             foreign = (fg[0], generate_groups(cfg, [fg[0]], min(procs, 32))[fg[0]])
     gen_s = time.time() - t0
@@ -480,6 +491,21 @@ def main():
     # straight into their owner's receive buffer over NVLink by one kernel behind the group's K5 (csrc/peer.cu); the first
     # round (a warm-up step) runs over NCCL (partition + all-to-all) and sizes the regions.  KHB_EXCHANGE=nccl keeps NCCL.
     ex = kd.AcrossExchanger(adapter, k, n_groups_total, mode=os.environ.get("KHB_EXCHANGE", "peer"))
+    ts, group_syms = None, {}
+    if T > 1:
+        team_pg = None
+        for t in range(n_teams):                # every rank creates every team's process group, in the same order
+            pg = dist.new_group(ranks=list(range(t * T, (t + 1) * T)))
+            if t == team_idx:
+                team_pg = pg
+        ts = kd.TeamSharder(eng, T, member, group=team_pg)
+        # symbols of every whole group, the same number on every member: the text bytes of all slices (an estimate is all the planner needs)
+        sz = torch.tensor([sum(len(v) for v in host_views[g]) for g in mine], dtype=torch.int64, device=dev)
+        dist.all_reduce(sz, group=team_pg)
+        group_syms = {g: int(x) for g, x in zip(mine, sz.tolist())}
+
+    def team_group(src, g, kk):
+        return ts.run_group(src, kk, wl["genomes"], slice_sizes, group_syms[g])
 
     def run_k(kk, group_fn):
         eng.group_sets_reset()
@@ -497,7 +523,9 @@ def main():
     def step_device():
         out = {}
         for kk in ks:
-            if sweep:
+            if ts:
+                out[kk] = run_k(kk, lambda i, g, kk: team_group(packed[g] if sweep else staged[g], g, kk))
+            elif sweep:
                 out[kk] = run_k(kk, lambda i, g, kk: eng.group_from_packed(packed[g], kk))
             else:
                 out[kk] = run_k(kk, lambda i, g, kk: eng.group_from_staged(staged[g], kk))
@@ -508,6 +536,8 @@ def main():
     def e2e_group(i, g, kk):
         nxt = mine[i + 1] if i + 1 < len(mine) else mine[0]
         eng.prefetch_fasta(host_views[nxt])                  # H2D of the next group overlaps this group's kernels
+        if ts:
+            return team_group(host_views[g], g, kk)
         return eng.group_from_fasta(host_views[g], kk)       # uses the prefetched copy, waits for it on the device
 
     def step_e2e():
@@ -518,6 +548,8 @@ def main():
             # config 3: H2D + K1 once per step, then the sweep on the resident 2-bit stream
             pk = {g: eng.pack_group(host_views[g]) for g in mine}
             try:
+                if ts:
+                    return {kk: run_k(kk, lambda i, g, kk: team_group(pk[g], g, kk)) for kk in ks}
                 return {kk: run_k(kk, lambda i, g, kk: eng.group_from_packed(pk[g], kk)) for kk in ks}
             finally:
                 for p in pk.values():
@@ -619,7 +651,10 @@ def main():
             O.build()
             O.set_num_threads(O.host_cores())
             t_or = time.time()
-            for label, gnum, tx in (("own", mine[0], list(host_views[mine[0]])), ("of_rank_1", fg, texts)):
+            samples = [("of_rank_1" if n_teams > 1 or T == 1 else "own", fg, texts)]
+            if T == 1:
+                samples.insert(0, ("own", mine[0], list(host_views[mine[0]])))
+            for label, gnum, tx in samples:
                 w_or, _, _ = O.exp1(tx, [0] * len(tx), 1, k)
                 eq = bool(np.array_equal(np.asarray(w_or[0][:nbins1], dtype=np.int64), within_all[k][gnum - 1, :nbins1]))
                 parity["checks"].append({"oracle_group": gnum, "which": label, "genomes": len(tx), "within_equal_oracle": eq})
@@ -661,10 +696,14 @@ def main():
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
             "dtype": "u64" if max(ks) <= 32 else "u128", "data": "synthetic",
             "config": {"workload": f"{shape_name}: {per}, k={k if not sweep else ','.join(map(str, ks))}"
-                                   + (f"; {world} GPUs, groups dealt round-robin, hash-range exchange for the across-group stage" if world > 1 else ", single B200"),
+                                   + ((f"; {world} GPUs, groups dealt round-robin" + (f" to {n_teams} team(s) of {T} GPUs, every group sharded inside its team "
+                                                                                              f"(genomes over members, minimizer bins over owners, records over NVLink)" if T > 1 else "")
+                                       + ", hash-range exchange for the across-group stage") if world > 1 else ", single B200"),
                        "k": k if not sweep else ks, "groups_total": n_groups_total, "genomes_per_group": wl["genomes"], "bases_per_step": bases_all,
                        "l2": "inputs exceed L2: every group streams >= 1 GB through a 126 MB L2; no explicit flush",
-                       "parallelism": f"groups dealt round-robin to {world} rank(s)", "data_gen_s": round(gen_s, 1),
+                       "parallelism": (f"groups dealt round-robin to {world} rank(s)" if T == 1 else
+                                       f"groups dealt round-robin to {n_teams} team(s) of {T} ranks; genome slices {slice_sizes}; "
+                                       f"{ts.retries} repartitions, {ts.setups} buffer set-ups"), "team_size": T, "data_gen_s": round(gen_s, 1),
                        "group_mode": os.environ.get("KHB_GROUP_MODE", "auto"), "bins_counters": eng.bins_counters,
                        "exchange": (f"peer-memory push (CUDA IPC over NVLink), {ex.rounds_peer} rounds; NCCL all-to-all, {ex.rounds_nccl} rounds (sizing / fallback)"
                                     if world > 1 else "none (one GPU)")},
@@ -715,6 +754,8 @@ def main():
             print("FATAL: in-run parity check failed: " + json.dumps(parity), file=sys.stderr)
             rc = 2
     ex.close()
+    if ts:
+        ts.close()
     for p in packed.values():
         p.free()
     if world > 1:

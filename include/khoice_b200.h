@@ -321,6 +321,46 @@ KHB_API int khb_peer_unmap(khb_ctx *ctx); /* drop the peers' mappings; barrier b
 KHB_API int khb_peer_close(khb_ctx *ctx);
 KHB_API uint64_t khb_peer_region_keys(const khb_ctx *ctx);
 
+/* ---- ONE group on several GPUs (csrc/team.cu, csrc/bins.cu; no reference counterpart) ----------------------------------------
+ * Steps 1-4 of one group (/root/reference/workflow/rules/exp_type_1.smk:156-191) sharded over the `team_size` <= 8 members of a
+ * team, for job shapes with fewer (or unevenly many) groups than GPUs.  The group's genomes are split into contiguous slices, one per
+ * member, every slice padded to whole chunks of 64 genome ids (slice t starts at id 64 * chunk_base[t]); the minimizer bins are split
+ * into `team_size` ranges of owners.  Each member packs its slice and partitions it into super-k-mer records (pass P of bins.cu)
+ * that it stores straight into the record buffer of the bin's owner -- peer memory over NVLink (CUDA IPC), no collective, no remote
+ * atomic: a (bin, chunk) region has exactly one writer -- followed by the region sizes.  After ONE barrier between the members
+ * (any collective of the caller; it also carries the overflow flags) every member counts the bins it owns (passes C and B): its
+ * h_hist holds the step_4 rows of ITS bins' k-mers, the sum over the members is the group's histogram, and its distinct keys go to
+ * the group-set store / the across-group exchange like those of a whole group.
+ * Every member must pass the same khb_team_group except chunk_base.  Two receive buffers alternate (parity), so a member may
+ * partition the next group while another still counts this one.  Protocol per group, on every member:
+ *     khb_team_partition_*(..., h_info);  barrier + exchange h_info[0..1] in the team;  if any member reports h_info[0] != 0 (a region
+ *     overflowed) repeat with a larger region_cap (every member);  khb_team_count. */
+typedef struct khb_team_group {
+    int32_t n_genomes_total; /* genomes of the whole group                                                        */
+    int32_t n_chunks_total;  /* sum over the members of ceil(slice genomes / 64)                                   */
+    int32_t chunk_base;      /* first chunk of THIS member's slice                                                 */
+    int32_t parity;          /* 0 / 1: which receive buffer this group uses (alternate from group to group)        */
+    uint64_t n_sym_total;    /* symbols of the whole group (an estimate will do: it sizes bins and tables)         */
+    double rho;              /* distinct k-mers per window measured on an earlier group of this shape, 0 = unknown */
+    uint32_t region_cap;     /* records per (bin, chunk) region, 0 = planner default                               */
+    uint32_t reserved;
+} khb_team_group;
+KHB_API int khb_team_alloc(khb_ctx *ctx, int team_size, int member, uint64_t half_bytes, unsigned char *handle_out /* 64 bytes */);
+KHB_API int khb_team_open(khb_ctx *ctx, const unsigned char *handles /* team_size x 64 bytes, member order */);
+KHB_API int khb_team_unmap(khb_ctx *ctx); /* drop the members' mappings; barrier in the team; then khb_team_close frees the own buffers */
+KHB_API int khb_team_close(khb_ctx *ctx);
+/* Geometry the planner derives from (k, tg): bins of the group, records per region, bytes ONE receive buffer must hold. */
+KHB_API int khb_team_plan(khb_ctx *ctx, int k, const khb_team_group *tg, uint32_t *n_bins, uint32_t *region_cap, uint64_t *half_bytes);
+/* K1 + pass P of this member's slice.  h_info[4]: [0] != 0: one of this member's regions overflowed, [1] records asked for in its
+ * fullest region, [2] symbols, [3] bases of the slice.  Returns after the member's stores have completed. */
+KHB_API int khb_team_partition_fasta(khb_ctx *ctx, int k, int n_genomes, const uint8_t *const *h_files, const size_t *h_sizes,
+                             const khb_team_group *tg, uint64_t *h_info);
+KHB_API int khb_team_partition_staged(khb_ctx *ctx, int k, int n_genomes, const uint8_t *d_fasta, const uint64_t *h_begin,
+                              const khb_team_group *tg, uint64_t *h_info);
+KHB_API int khb_team_partition_packed(khb_ctx *ctx, int k, const khb_packed *pk, const khb_team_group *tg, uint64_t *h_info);
+/* Passes C and B over the bins this member owns (after the team's barrier). */
+KHB_API int khb_team_count(khb_ctx *ctx, int k, const khb_team_group *tg, uint32_t nbins, uint64_t *h_hist, int keep_set, khb_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif

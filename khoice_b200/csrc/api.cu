@@ -37,6 +37,7 @@ int khb_hash_count_impl(khb_ctx *, const u64 *, const u32 *, u64, int, const u64
                         void *, u64 *, u32 *);
 int khb_peer_regions(khb_ctx *, const void **, u64 *, int *, int *);
 extern "C" int khb_peer_close(khb_ctx *);
+extern "C" int khb_team_close(khb_ctx *);
 int khb_pivot_across_impl(khb_ctx *, const void *, const unsigned short *, size_t, int, int, u32, u32, u32, u64 *);
 int khb_sorted_lookup_impl(khb_ctx *, const void *, u64, const void *, u64, int, u64 *);
 int khb_membership_impl(khb_ctx *, const void *, const unsigned short *, size_t, int, int, u32, int, const void *, const u64 *, int, u64 *);
@@ -211,6 +212,7 @@ int khb_destroy(khb_ctx *ctx)
     if (ctx->gs_buf) cudaFree(ctx->gs_buf);
     if (ctx->hs_tab) cudaFree(ctx->hs_tab);
     khb_peer_close(ctx);
+    khb_team_close(ctx);
     if (ctx->stage_dev) cudaFree(ctx->stage_dev);
     if (ctx->stage_next) cudaFree(ctx->stage_next);
     if (ctx->pf_tab) cudaFree(ctx->pf_tab);
@@ -1162,23 +1164,20 @@ int khb_group_prefetch_fasta(khb_ctx *ctx, int n_genomes, const uint8_t *const *
     return KHB_OK;
 }
 
-int khb_group_from_fasta(khb_ctx *ctx, int k, int n_genomes, const uint8_t *const *h_files, const size_t *h_sizes,
-                         uint32_t nbins, uint64_t *h_hist, int keep_set, khb_stats *stats)
+// The text of a group in ctx->stage_dev: the prefetched copy when it is this group's (the buffers are swapped, the stream waits for the
+// copy on the device, a deferred prefetch request is started), else a copy made now.  Records marks 0 and 1 of `tm`.
+static int fasta_acquire(khb_ctx *ctx, int n_genomes, const uint8_t *const *h_files, const size_t *h_sizes, PhaseTimer &tm, std::vector<u64> &begin)
 {
-    KHB_CHECK_CTX(ctx);
-    if (n_genomes < 1 || !h_files || !h_sizes) return khb_fail(ctx, KHB_ERR_ARG, "khb_group_from_fasta: bad arguments");
-    if (stats) memset(stats, 0, sizeof(*stats));
     if (ctx->pf_valid && ctx->pf_n == n_genomes && ctx->pf_first == (const void *)h_files[0] &&
         ctx->pf_bytes == khb_staged_size(n_genomes, h_sizes)) {
         // the text of this group was prefetched: swap staging buffers and wait for the copy on the device
         ctx->pf_valid = 0;
         uint8_t *tb = ctx->stage_dev; ctx->stage_dev = ctx->stage_next; ctx->stage_next = tb;
         size_t tc = ctx->stage_dev_cap; ctx->stage_dev_cap = ctx->stage_next_cap; ctx->stage_next_cap = tc;
-        PhaseTimer tm(ctx);
         tm.mark();
         KHB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
         tm.mark();
-        std::vector<u64> begin = ctx->pf_begin->v;
+        begin = ctx->pf_begin->v;
         if (ctx->pf_begin->deferred) {  // start copying the next group now; it overlaps this group's kernels
             ctx->pf_begin->deferred = false;
             std::vector<const uint8_t *> nf = ctx->pf_begin->d_files;
@@ -1186,9 +1185,7 @@ int khb_group_from_fasta(khb_ctx *ctx, int k, int n_genomes, const uint8_t *cons
             int prc = khb_group_prefetch_fasta(ctx, (int)nf.size(), nf.data(), ns.data());
             if (prc) return prc;
         }
-        int rc = group_from_staged_impl(ctx, k, n_genomes, ctx->stage_dev, begin.data(), nbins, (u64 *)h_hist, keep_set, stats, tm);
-        if (rc == KHB_OK) fill_times(stats, tm);
-        return rc;
+        return KHB_OK;
     }
     ctx->pf_valid = 0;
     const size_t need = khb_staged_size(n_genomes, h_sizes);
@@ -1207,15 +1204,149 @@ int khb_group_from_fasta(khb_ctx *ctx, int k, int n_genomes, const uint8_t *cons
         }
         ctx->stage_dev_cap = cap;
     }
-    PhaseTimer tm(ctx);
     tm.mark();
-    std::vector<u64> begin((size_t)n_genomes + 1);
+    begin.assign((size_t)n_genomes + 1, 0);
     int rc = khb_stage_fasta(ctx, n_genomes, h_files, h_sizes, ctx->stage_dev, ctx->stage_dev_cap, (uint64_t *)begin.data());
     if (rc) return rc;
     tm.mark();
+    return KHB_OK;
+}
+
+int khb_group_from_fasta(khb_ctx *ctx, int k, int n_genomes, const uint8_t *const *h_files, const size_t *h_sizes,
+                         uint32_t nbins, uint64_t *h_hist, int keep_set, khb_stats *stats)
+{
+    KHB_CHECK_CTX(ctx);
+    if (n_genomes < 1 || !h_files || !h_sizes) return khb_fail(ctx, KHB_ERR_ARG, "khb_group_from_fasta: bad arguments");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    PhaseTimer tm(ctx);
+    std::vector<u64> begin;
+    int rc = fasta_acquire(ctx, n_genomes, h_files, h_sizes, tm, begin);
+    if (rc) return rc;
     rc = group_from_staged_impl(ctx, k, n_genomes, ctx->stage_dev, begin.data(), nbins, (u64 *)h_hist, keep_set, stats, tm);
     if (rc == KHB_OK) fill_times(stats, tm);
     return rc;
+}
+
+// ---- one group on several GPUs (include/khoice_b200.h: khb_team_*; buffers: team.cu; kernels: bins.cu) ---------------------------------
+static int team_partition(khb_ctx *ctx, int k, const khb_packed &pk, const khb_team_group *tg, uint64_t *h_info)
+{
+    khb_team *tmm = ctx->team;
+    if (!tmm || !tmm->opened) return khb_fail(ctx, KHB_ERR_STATE, "khb_team_partition: khb_team_alloc / khb_team_open first");
+    if (!tg || !h_info) return khb_fail(ctx, KHB_ERR_ARG, "khb_team_partition: null argument");
+    if (pk.n_genomes < 1 || pk.n_genomes > 8191) return khb_fail(ctx, KHB_ERR_ARG, "khb_team_partition: %d genomes in the slice", pk.n_genomes);
+    u64 *d_seg = ctx->d_mail + 32768;
+    KHB_CUDA(ctx, cudaMemcpyAsync(d_seg, pk.seg.data(), (size_t)(pk.n_genomes + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // seg is pageable
+    u64 *d_info = ctx->d_mail + 16640;   // away from the histogram mailbox and the partition counters
+    int rc = khb_bins_team_partition_impl(ctx, pk.d_codes, pk.d_valid, pk.n_sym, k, d_seg, pk.n_genomes, tg, d_info);
+    if (rc) return rc;
+    KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 16640, d_info, 4 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the kernel is complete: its stores into the owners' buffers are visible to them
+    h_info[0] = ctx->h_mail[16640] & 1ull;
+    h_info[1] = ctx->h_mail[16643];
+    h_info[2] = pk.n_sym;
+    h_info[3] = pk.n_sym - pk.n_breaks;
+    tmm->slice_sym = pk.n_sym;
+    tmm->slice_bases = pk.n_sym - pk.n_breaks;
+    tmm->slice_fasta_bytes = pk.fasta_bytes;
+    khb_prof_patch(ctx, KHB_K_BIN_PARTITION, pk.n_sym * 3 / 8);
+    return KHB_OK;
+}
+
+int khb_team_partition_staged(khb_ctx *ctx, int k, int n_genomes, const uint8_t *d_fasta, const uint64_t *h_begin, const khb_team_group *tg, uint64_t *h_info)
+{
+    KHB_CHECK_CTX(ctx);
+    PhaseTimer tm(ctx);
+    tm.mark();
+    tm.mark();
+    khb_packed pk;
+    int rc = pack_stage(ctx, n_genomes, d_fasta, (const u64 *)h_begin, pk, tm);
+    if (rc) return rc;
+    return team_partition(ctx, k, pk, tg, h_info);
+}
+
+int khb_team_partition_fasta(khb_ctx *ctx, int k, int n_genomes, const uint8_t *const *h_files, const size_t *h_sizes, const khb_team_group *tg,
+                             uint64_t *h_info)
+{
+    KHB_CHECK_CTX(ctx);
+    if (n_genomes < 1 || !h_files || !h_sizes) return khb_fail(ctx, KHB_ERR_ARG, "khb_team_partition_fasta: bad arguments");
+    PhaseTimer tm(ctx);
+    std::vector<u64> begin;
+    int rc = fasta_acquire(ctx, n_genomes, h_files, h_sizes, tm, begin);
+    if (rc) return rc;
+    khb_packed pk;
+    if ((rc = pack_stage(ctx, n_genomes, ctx->stage_dev, begin.data(), pk, tm))) return rc;
+    return team_partition(ctx, k, pk, tg, h_info);
+}
+
+int khb_team_partition_packed(khb_ctx *ctx, int k, const khb_packed *pk, const khb_team_group *tg, uint64_t *h_info)
+{
+    KHB_CHECK_CTX(ctx);
+    if (!pk) return khb_fail(ctx, KHB_ERR_ARG, "khb_team_partition_packed: null handle");
+    return team_partition(ctx, k, *pk, tg, h_info);
+}
+
+int khb_team_plan(khb_ctx *ctx, int k, const khb_team_group *tg, uint32_t *n_bins, uint32_t *region_cap, uint64_t *half_bytes)
+{
+    KHB_CHECK_CTX(ctx);
+    u64 hb = 0;
+    int rc = khb_bins_team_plan_impl(ctx, k, tg, KHB_COUNTER_MAX, n_bins, region_cap, &hb);
+    if (rc == KHB_OK && half_bytes) *half_bytes = hb;
+    return rc;
+}
+
+int khb_team_count(khb_ctx *ctx, int k, const khb_team_group *tg, uint32_t nbins, uint64_t *h_hist, int keep_set, khb_stats *stats)
+{
+    KHB_CHECK_CTX(ctx);
+    khb_team *tmm = ctx->team;
+    if (!tmm || !tmm->opened) return khb_fail(ctx, KHB_ERR_STATE, "khb_team_count: khb_team_alloc / khb_team_open first");
+    if (!tg || !h_hist) return khb_fail(ctx, KHB_ERR_ARG, "khb_team_count: null argument");
+    if (nbins < 1 || nbins > 8192) return khb_fail(ctx, KHB_ERR_ARG, "nbins=%u outside 1..8192", nbins);
+    if (stats) memset(stats, 0, sizeof(*stats));
+    const size_t W = (size_t)khb_key_bytes(k);
+    int rc;
+    void *out_keys = nullptr;
+    khb_peer_route route = {0u, 0ull, nullptr, nullptr};
+    if (keep_set) {
+        if (ctx->gs_k && ctx->gs_hashed != 1) return khb_fail(ctx, KHB_ERR_STATE, "retained group sets use a different key encoding");
+        if ((rc = gs_reserve(ctx, k, tg->n_sym_total))) return rc;   // this member's bins hold at most every window of the group
+        ctx->gs_hashed = 1;
+        out_keys = (char *)ctx->gs_buf + ctx->gs_len * W;
+        if (ctx->gs_len == 0) ev_forget(ctx);
+        ctx->ev_ok = 0;
+        if ((rc = khb_peer_route_get(ctx, (int)W, &route))) return rc;
+    }
+    PhaseTimer tm(ctx);
+    tm.mark();
+    u64 *d_hist = ctx->d_mail + 8, *d_runs = ctx->d_mail, *d_pairs = ctx->d_mail + 1;
+    if ((rc = khb_bins_team_count_impl(ctx, k, tg, KHB_COUNTER_MAX, nbins, d_hist, out_keys, d_runs, d_pairs, ctx->d_mail + 3, route))) return rc;
+    KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, ctx->d_mail, (nbins + 9) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    tm.mark();
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_mail[3] & 3) {
+        // a class of a bin that cannot be split small enough for the table: a whole group falls back to the sort here, a sharded one cannot
+        if (route.world) khb_peer_poison(ctx);
+        return khb_fail(ctx, KHB_ERR_STATE, "khb_team_count: a bin of this group cannot be counted in shared memory; run the group unsharded");
+    }
+    ctx->bins_bigbins += ctx->h_mail[5];
+    memcpy(h_hist, ctx->h_mail + 8, ((size_t)nbins + 1) * sizeof(u64));
+    const u64 d_g = ctx->h_mail[0];
+    khb_prof_patch(ctx, KHB_K_BIN_COUNT, ctx->h_mail[4] * (k <= 32 ? 24 : 32) + d_g * W);
+    if (keep_set) {
+        ctx->gs_len += d_g;
+        ctx->gs_groups += 1;
+        if (route.world) khb_peer_mark_pushed(ctx);
+    }
+    if (stats) {
+        stats->fasta_bytes = tmm->slice_fasta_bytes;
+        stats->bases = tmm->slice_bases;
+        stats->windows = tmm->slice_sym;
+        stats->genome_distinct = ctx->h_mail[1];
+        stats->distinct = d_g;
+        stats->ms_count = tm.ms(0, 1);
+        stats->ms_total = tm.ms(0, 1);
+    }
+    return KHB_OK;
 }
 
 int khb_pack_group(khb_ctx *ctx, int n_genomes, const uint8_t *const *h_files, const size_t *h_sizes, khb_packed **out)

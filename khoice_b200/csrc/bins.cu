@@ -119,11 +119,14 @@ mb_region_max_kernel(const u32 *__restrict__ cursor, u64 n_regions, u64 *__restr
 // ---- pass P -----------------------------------------------------------------------------------------------------------------
 // Record layout (KW + 1 words of 64 bits, KW = 2 for k <= 32): word 0 = genome << 48 | windows << 40; words 1..KW = the record's
 // k - 1 + windows <= 32 * KW symbols from its first window start, MSB first, zero behind them (window e's k-mer = bits [2e, 2e + 2k)).
-template <int KW>
+// SHARD (a group sharded over the members of a team, team.cu): this member holds a slice of the group's genomes, all of them in chunks no
+// other member has, so the cursors of its regions are LOCAL (no remote atomics); the records go straight into the buffer of the bin's
+// owner (owner = bin / sh.bpo: peer memory over NVLink, or this GPU's own buffer) at the place the owner's counting pass expects them.
+template <int KW, bool SHARD>
 __global__ void __launch_bounds__(MB_BLOCK)
 mb_partition_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, u64 n_sym, u64 last_cw, u64 last_vw, int k, int m, u32 nbins,
                     const u64 *__restrict__ seg_off, int nseg, u32 nchunks, u32 *__restrict__ cursor, u64 *__restrict__ rec, u32 cap, u32 capw,
-                    const u64 *__restrict__ roff, u64 *__restrict__ flags)
+                    const u64 *__restrict__ roff, u64 *__restrict__ flags, mb_shard sh)
 {
     constexpr int CW = MB_TILE / 32 + KW + 2;     // 64-bit code words staged per tile
     constexpr int VW = MB_TILE / 32 + 4;
@@ -250,20 +253,29 @@ mb_partition_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid
         const u32 len = (r + 1 < nbnd ? (u32)blist[wrp][r + 1] : wnext[wrp]) - j;
         const u64 i0 = tile0 + j;
         const u64 g = i0 < g_first_end ? g_first : segs_shared ? mb_segment_of_shared(sseg, nseg, i0) : mb_segment_of(seg_off, nseg, i0);
-        const u32 region = mb_bin_of(mh, nbins) * nchunks + (u32)(g >> 6);   // one region per bin and chunk of 64 genomes
+        const u32 bin = mb_bin_of(mh, nbins);
+        const u32 region = bin * nchunks + (u32)(g >> 6);   // one region per bin and chunk of 64 genomes
         const u32 pieces = len <= capw ? 1u : (len + capw - 1) / capw;
         const u32 at = atomicAdd(&cursor[region], pieces);
-        if (at + pieces > mb_region_cap(roff, region, cap)) {   // the region is full: the caller partitions again with the sizes counted here
+        if (at + pieces > (SHARD ? cap : mb_region_cap(roff, region, cap))) {   // the region is full: the caller partitions again with the sizes counted here
             *flags = 1ull;
             continue;
         }
-        u64 *dst = rec + (mb_region_base(roff, region, cap) + at) * (KW + 1);
+        u64 *dst;
+        u64 gid = g;
+        if (SHARD) {
+            const u32 owner = bin / sh.bpo, lb = bin - owner * sh.bpo;
+            dst = sh.rec[owner] + (((u64)lb * sh.nchunks_total + sh.chunk_base + (u32)(g >> 6)) * cap + at) * (KW + 1);
+            gid = g + 64ull * sh.chunk_base;             // the genome's id inside the whole group
+        } else {
+            dst = rec + (mb_region_base(roff, region, cap) + at) * (KW + 1);
+        }
         for (u32 s0 = 0; s0 < len; s0 += capw) {
             const u32 pl = len - s0 < capw ? len - s0 : capw;
             const u32 rel = j + s0, t = rel >> 4, s = (rel & 15u) * 2u;
             const int nbits = 2 * (k - 1 + (int)pl);   // the record's symbols; what follows is zeroed so that equal runs give equal records
             u64 W[KW + 1];
-            W[0] = (g << 48) | ((u64)pl << 40);
+            W[0] = (gid << 48) | ((u64)pl << 40);
 #pragma unroll
             for (int e = 0; e < KW; e++) {
                 const u32 hi = __funnelshift_l(sc[t + 2 * e + 1], sc[t + 2 * e], s);
@@ -574,15 +586,24 @@ template <int KW> __device__ __forceinline__ void mb_route_store(const mc_smem &
     }
     sm.tbits[i] = 0ull;
 }
-// between the halves: one reservation per owner on the sender-side cursor (no remote atomics)
-__device__ __forceinline__ void mb_route_reserve(const khb_peer_route &route, u32 *s_ocnt, u64 *s_obase)
+// between the halves: one reservation per owner on the sender-side cursor (no remote atomics), and the owners' first positions in the
+// bin's owner-sorted order (warp 0: exclusive scan of the <= 64 counts) -- the second half writes every owner's keys as ONE contiguous
+// run of consecutive threads, which is what NVLink wants (scattered 8-byte stores reached 334 GB/s on 8 B200s, runs three times that)
+__device__ __forceinline__ void mb_route_reserve(const khb_peer_route &route, u32 *s_ocnt, u64 *s_obase, u32 *s_ostart)
 {
     const u32 o = threadIdx.x;
+    if (o < 32) {
+        const u32 c0 = o < route.world ? s_ocnt[o] : 0u, c1 = o + 32 < route.world ? s_ocnt[o + 32] : 0u;
+        const u32 i0 = warp_incl_sum(c0);
+        const u32 t0 = __shfl_sync(0xffffffffu, i0, 31);
+        const u32 i1 = warp_incl_sum(c1);
+        s_ostart[o] = i0 - c0;
+        s_ostart[o + 32] = t0 + i1 - c1;
+    }
     if (o < route.world) {
         const u32 c = s_ocnt[o];
         s_obase[o] = c ? atomicAdd((unsigned long long *)&route.cursor[o], (unsigned long long)c) : 0ull;
         if (c && s_obase[o] + c > route.cap) route.cursor[64] = 1ull;   // region full: the caller redoes the round over NCCL
-        s_ocnt[o] = 0u;
     }
 }
 
@@ -631,7 +652,7 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
     __shared__ mc_desc desc[2];
     __shared__ u32 s_over, s_distinct, s_dcount, s_wtotal, s_dfull;
     __shared__ u32 s_cn[MULTI ? 128 : 1];   // thread 0: records per chunk of the bin it is feeding
-    __shared__ u32 s_ocnt[64];              // multi-GPU: keys of the bin per owner ...
+    __shared__ u32 s_ocnt[64], s_ostart[64]; // multi-GPU: keys of the bin per owner, their first position in owner-sorted order ...
     __shared__ u64 s_obase[64];             // ... and where they go in the owner's region
     __shared__ u64 s_base;
     const u32 s_log2 = geo.s_log2, S = 1u << s_log2, nchunks = geo.nchunks, hrows = geo.hrows, dcap = geo.dcap, RT = 1u << geo.rt_log2;
@@ -955,10 +976,17 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
         }
         __syncthreads();
         if (route.world && out_keys) {
-            mb_route_reserve(route, s_ocnt, s_obase);
+            mb_route_reserve(route, s_ocnt, s_obase, s_ostart);
+            __syncthreads();
+            for (u32 j = tid; j < nd_keys; j += BLOCK) {          // owner-sorted order of the bin's keys (the window map is free at this point)
+                const u32 i = sm.slots[j];
+                const u64 w = sm.tbits[i];
+                sm.map[s_ostart[(u32)(w >> 32)] + (u32)w] = (unsigned short)i;
+            }
+            if (tid < 64) s_ocnt[tid] = 0u;
             __syncthreads();
             for (u32 j = tid; j < nd_keys; j += BLOCK) {
-                const u32 i = sm.slots[j];
+                const u32 i = sm.map[j];
                 mb_route_store<KW>(sm, i, route, s_obase, out_keys, base + j);
                 mb_slot_reset<KW>(sm, i);
             }
@@ -1000,7 +1028,7 @@ mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u3
 {
     extern __shared__ __align__(16) unsigned char mc_raw[];
     __shared__ u32 s_over, s_distinct, ws[33];
-    __shared__ u32 s_ocnt[64];
+    __shared__ u32 s_ocnt[64], s_ostart[64];
     __shared__ u64 s_obase[64];
     __shared__ u64 s_base;
     const u32 s_log2 = geo.s_log2, S = 1u << s_log2, nchunks = geo.nchunks, hrows = geo.hrows;
@@ -1120,10 +1148,17 @@ mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u3
             }
             __syncthreads();
             if (route.world && out_keys) {
-                mb_route_reserve(route, s_ocnt, s_obase);
+                mb_route_reserve(route, s_ocnt, s_obase, s_ostart);
                 __syncthreads();
                 for (u32 j = tid; j < nd_keys; j += MC_BLOCK) {
                     const u32 i = sm.slots[j];
+                    const u64 w = sm.tbits[i];
+                    sm.map[s_ostart[(u32)(w >> 32)] + (u32)w] = (unsigned short)i;
+                }
+                if (tid < 64) s_ocnt[tid] = 0u;
+                __syncthreads();
+                for (u32 j = tid; j < nd_keys; j += MC_BLOCK) {
+                    const u32 i = sm.map[j];
                     mb_route_store<KW>(sm, i, route, s_obase, out_keys, base + j);
                     mb_slot_reset<KW>(sm, i);
                 }
@@ -1158,29 +1193,43 @@ int khb_bins_eligible(int k, int n_genomes, u64 n_sym)
     return k >= 17 && k <= 63 && k != 32 && n_genomes >= 1 && n_genomes <= 8191 && n_sym >= 1 && n_sym < (1ull << 40);
 }
 
-// The group stage through minimizer bins.  d_stat: u64[4] in device memory, written here: [0] flags (1: a bin region overflowed,
-// 2: a bin could not be counted -- either way the outputs are incomplete and the caller redoes the group another way), [1] records,
-// [2] bins redone by mb_bigbin_kernel, [3] records asked for in the fullest region, [4] distinct records.  d_hist[nbins_hist + 1], d_runs (distinct k-mers = keys appended to d_out_keys), d_pairs
-// (sum over genomes of their distinct k-mers) are zeroed here.  exact != 0: the call before this one, on the same group, ended with flag 1;
-// partition again into regions of exactly the sizes that attempt counted (they are still in the context's scratch).
-int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u64 n_sym, int k, const u64 *d_seg_off, int n_genomes, u32 cs, u32 nbins_hist,
-                        u64 *d_hist, void *d_out_keys, u64 *d_runs, u64 *d_pairs, u64 *d_stat, int exact, u32 nb_fixed, u32 *nb_used, void *ev_buf,
-                        u64 *ev_count, u64 ev_cap, u64 store_base, khb_peer_route route)
+// ---- the planner: bins, regions, tables -- a pure function of its inputs, so that the members of a team (team.cu) arrive at the same geometry
+struct mb_plan_in {
+    int k, n_genomes;       // genomes of the WHOLE group
+    u32 nchunks;            // chunks of <= 64 genomes (0: ceil(n_genomes / 64))
+    u64 n_sym;              // symbols of the whole group
+    double rho_prev;        // distinct k-mers per window measured on the previous group (0: a guess from the group size)
+    u32 nb_fixed;           // != 0: this many bins
+    u32 cap_fixed;          // != 0: this many records per region
+    u32 nbins_hist;
+    int hint_k, hint_genomes;          // shape of the group before this one ...
+    u64 hint_regions, hint_max;        // ... its regions and the records asked for in its fullest one
+};
+struct mb_plan {
+    int KW, m;
+    u32 capw, nb, cap, thr1, over_cap;
+    mc_geom geo;
+    u64 n_regions;
+    size_t rec_bytes;
+    double rho_w;
+};
+static int mb_make_plan(khb_ctx *ctx, const mb_plan_in &in, mb_plan *out)
 {
-    if (!khb_bins_eligible(k, n_genomes, n_sym)) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: k=%d / %d genomes not supported", k, n_genomes);
+    const int k = in.k, n_genomes = in.n_genomes;
+    const u64 n_sym = in.n_sym;
     const int KW = k <= 32 ? 2 : 3;               // record words of symbols: k - 1 + 32 windows fit 64 (k <= 32) or 96 symbols
     const int m = 13, w = k - m + 1;
     const u32 capw = (u32)(32 * KW + 1 - k) < MB_MAXW ? (u32)(32 * KW + 1 - k) : MB_MAXW;
     double avg_len = (w + 1) * 0.5;               // windows per super-k-mer on random sequence, before the cuts at capw and at tile ends
     if (avg_len > capw) avg_len = capw;
     // distinct k-mers per window: measured on the previous group (+ 25 %), else a guess from the group size
-    double rho_w = ctx->bins_rho > 0.0 ? ctx->bins_rho * 1.25 : (n_genomes >= 32 ? 0.2 : n_genomes >= 16 ? 0.25 : n_genomes >= 4 ? 0.5 : 1.0);
+    double rho_w = in.rho_prev > 0.0 ? in.rho_prev * 1.25 : (n_genomes >= 32 ? 0.2 : n_genomes >= 16 ? 0.25 : n_genomes >= 4 ? 0.5 : 1.0);
     const long long rho_pct = mb_env("KHB_BINS_RHO_PCT", 0);   // test hook: distinct k-mers per 100 windows
     if (rho_pct > 0) rho_w = rho_pct / 100.0;
     if (rho_w > 1.0) rho_w = 1.0;
     if (rho_w < 0.005) rho_w = 0.005;
     mc_geom geo;
-    geo.nchunks = (u32)div_up((size_t)n_genomes, 64);
+    geo.nchunks = in.nchunks ? in.nchunks : (u32)div_up((size_t)n_genomes, 64);
     // Bin geometry.  All copies of a k-mer -- one per genome that holds it, avg_len windows around each -- land in one bin together, so a
     // region's load (one bin, one chunk of <= 64 genomes) comes in lumps of ~avg_len x genomes windows; ~6 lumps per region keep the largest
     // region within a few times the mean.  But a bin's distinct k-mers should fill less than half of the largest table of which two CTAs fit
@@ -1195,10 +1244,9 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
     const u64 wpb = (u64)mb_env("KHB_BINS_WPB", (long long)wpb_d);
     u64 nb64 = div_up(n_sym, wpb ? wpb : 1024);
     if (nb64 < 16) nb64 = 16;
-    if (nb_fixed) nb64 = nb_fixed;                 // the store's earlier groups were binned with this many bins: keep the bins comparable
+    if (in.nb_fixed) nb64 = in.nb_fixed;          // the store's earlier groups were binned with this many bins: keep the bins comparable
     if (nb64 > (1ull << 28)) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: group too large");
     const u32 nb = (u32)nb64;
-    if (nb_used) *nb_used = nb;
     {   // table slots: the mean bin's distinct k-mers fill ~45 % (larger bins are counted in hash classes)
         const double want = (double)(n_sym / nb + 1) * rho_w / 0.45;
         u32 l2 = 10;
@@ -1206,7 +1254,7 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
         geo.s_log2 = (u32)mb_env("KHB_BINS_SLOTS_LOG2", l2);
         if (geo.s_log2 < 8 || geo.s_log2 > 13) return khb_fail(ctx, KHB_ERR_ARG, "KHB_BINS_SLOTS_LOG2 outside 8..13");
     }
-    geo.hrows = nbins_hist < (u32)n_genomes ? nbins_hist : (u32)n_genomes;
+    geo.hrows = in.nbins_hist < (u32)n_genomes ? in.nbins_hist : (u32)n_genomes;
     geo.dcap = (u32)mb_env("KHB_BINS_DCAP", geo.nchunks > 1 ? 256 : 384);
     if (geo.dcap < 64 || geo.dcap > 4096) return khb_fail(ctx, KHB_ERR_ARG, "KHB_BINS_DCAP outside 64..4096");
     geo.rt_log2 = 7;
@@ -1218,17 +1266,114 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
     const double slack = (double)mb_env("KHB_BINS_SLACK_PCT", (double)(n_sym / nb) >= 5.0 * lump * geo.nchunks ? 400 : 600) / 100.0;
     u32 cap = ((u32)(est_records / (double)n_regions * slack) + 64u) & ~1u;   // even: every region starts 16-byte aligned
     // ... unless the group before this one had the same shape: then its fullest region (+ 40 %) is the better guide
-    if (ctx->bins_hint_k == k && ctx->bins_hint_genomes == n_genomes && ctx->bins_hint_regions > 0 && !mb_env("KHB_BINS_SLACK_PCT", 0) &&
-        (double)n_regions > 0.8 * (double)ctx->bins_hint_regions && (double)n_regions < 1.25 * (double)ctx->bins_hint_regions)
-        cap = ((u32)((double)ctx->bins_hint_max * 1.4 * (double)ctx->bins_hint_regions / (double)n_regions) + 64u) & ~1u;
-    const size_t rec_bytes = (size_t)n_regions * cap * (KW + 1) * 8;
+    if (in.hint_k == k && in.hint_genomes == n_genomes && in.hint_regions > 0 && !mb_env("KHB_BINS_SLACK_PCT", 0) &&
+        (double)n_regions > 0.8 * (double)in.hint_regions && (double)n_regions < 1.25 * (double)in.hint_regions)
+        cap = ((u32)((double)in.hint_max * 1.4 * (double)in.hint_regions / (double)n_regions) + 64u) & ~1u;
+    if (in.cap_fixed) cap = (in.cap_fixed + 1u) & ~1u;
     // Records one pass over a bin may hold so that its distinct k-mers fill at most ~55 % of the table; larger bins are counted in
     // several hash classes.
     double thr = 0.55 * (double)(1u << s_log2) / (rho_w * avg_len);
-    const u32 thr1 = thr < 8.0 ? 8u : thr > 1e9 ? 1000000000u : (u32)thr;
-    const u32 over_cap = 4 * nb;
+    out->KW = KW;
+    out->m = m;
+    out->capw = capw;
+    out->nb = nb;
+    out->cap = cap;
+    out->thr1 = thr < 8.0 ? 8u : thr > 1e9 ? 1000000000u : (u32)thr;
+    out->over_cap = 4 * nb;
+    out->geo = geo;
+    out->n_regions = n_regions;
+    out->rec_bytes = (size_t)n_regions * cap * (KW + 1) * 8;
+    out->rho_w = rho_w;
+    return KHB_OK;
+}
+
+// Passes C and B over `nb_count` bins whose regions lie in `rec` (region u = bin * nchunks + chunk at u * cap, or at roff[u]) with `cur[u]` records each.
+static int mb_launch_count(khb_ctx *ctx, const mb_plan &pl, int k, const u64 *rec, const u32 *cur, u32 nb_count, u32 n_genomes, u32 cs, u64 *d_hist, void *d_out_keys,
+                           u64 *d_runs, u64 *d_pairs, u32 *d_over_list, u32 *d_over_count, u64 *d_stat, const u64 *roff, mb_evlog evlog, khb_peer_route route, u64 n_sym)
+{
+    const int KW = pl.KW;
+    mc_geom geo = pl.geo;
     const bool multi = geo.nchunks > 1;
-    int rc;
+    size_t shm = mc_smem_bytes(KW, geo, 256);
+    if (shm > 227 * 1024) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: %zu bytes of shared memory per CTA", shm);
+    // two CTAs of 256 threads per SM at least; where the tables leave room for one CTA only, that one has 512 threads
+    const bool wide = 2 * (shm + 1024) > 227 * 1024;
+    const void *fn, *bfn;
+    if (KW == 2) {
+        fn = multi ? (wide ? (const void *)mb_count_kernel<2, true, 512> : (const void *)mb_count_kernel<2, true, 256>)
+                   : (wide ? (const void *)mb_count_kernel<2, false, 512> : (const void *)mb_count_kernel<2, false, 256>);
+        bfn = multi ? (const void *)mb_bigbin_kernel<2, true> : (const void *)mb_bigbin_kernel<2, false>;
+    } else {
+        fn = multi ? (wide ? (const void *)mb_count_kernel<3, true, 512> : (const void *)mb_count_kernel<3, true, 256>)
+                   : (wide ? (const void *)mb_count_kernel<3, false, 512> : (const void *)mb_count_kernel<3, false, 256>);
+        bfn = multi ? (const void *)mb_bigbin_kernel<3, true> : (const void *)mb_bigbin_kernel<3, false>;
+    }
+    const int block = wide ? 512 : 256;
+    shm = mc_smem_bytes(KW, geo, block);
+    int per_sm = 0;
+    KHB_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    KHB_CUDA(ctx, cudaFuncSetAttribute(bfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    KHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, shm));
+    if (per_sm < 1) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: the counting kernel does not fit an SM (%zu bytes of shared memory)", shm);
+    const long long want = mb_env("KHB_BINS_CTAS_PER_SM", 0);
+    if (want > 0 && want < per_sm) per_sm = (int)want;
+    u32 grid = (u32)ctx->num_sms * (u32)per_sm;
+    if (grid > nb_count) grid = nb_count;
+    if (grid < 1) grid = 1;
+    const u64 *c_rec = rec;
+    const u32 *c_cur = cur;
+    u32 n_gen = n_genomes, cs_ = cs, nb_ = nb_count, cap_ = pl.cap, thr_ = pl.thr1, ocap_ = pl.over_cap;
+    int k_ = k;
+    void *keys_ = d_out_keys;
+    const u32 *c_list = d_over_list, *c_cnt = d_over_count;
+    void *cargs[] = {&c_rec, &c_cur, &nb_, &cap_, &k_, &geo, &n_gen, &cs_, &thr_, &ocap_, &d_hist, &keys_, &d_runs, &d_pairs, &d_over_list, &d_over_count, &d_stat, &roff, &evlog, &route};
+    if (mb_env("KHB_BINS_VERBOSE", 0))
+        fprintf(stderr, "[bins] k=%d genomes=%u windows=%llu bins=%u (of %u) chunks=%u cap=%u slots=2^%u dcap=%u thr1=%u rho_w=%.3f shm=%zu ctas/sm=%d block=%d\n", k, n_genomes,
+                (unsigned long long)n_sym, nb_count, pl.nb, geo.nchunks, pl.cap, geo.s_log2, geo.dcap, pl.thr1, pl.rho_w, shm, per_sm, block);
+    khb_prof_begin(ctx, KHB_K_BIN_COUNT);
+    KHB_CUDA(ctx, cudaLaunchKernel(fn, dim3(grid), dim3(block), cargs, shm, ctx->stream));
+    khb_prof_end(ctx, KHB_K_BIN_COUNT, 0);
+    KHB_LAUNCH_CHECK(ctx);
+    void *bargs[] = {&c_rec, &c_cur, &cap_, &k_, &geo, &n_gen, &cs_, &d_hist, &keys_, &d_runs, &d_pairs, &c_list, &c_cnt, &ocap_, &d_stat, &roff, &evlog, &route};
+    KHB_CUDA(ctx, cudaLaunchKernel(bfn, dim3((u32)ctx->num_sms * 2u), dim3(MC_BLOCK), bargs, shm, ctx->stream));
+    KHB_LAUNCH_CHECK(ctx);
+    return KHB_OK;
+}
+
+// The group stage through minimizer bins.  d_stat: u64[4] in device memory, written here: [0] flags (1: a bin region overflowed,
+// 2: a bin could not be counted -- either way the outputs are incomplete and the caller redoes the group another way), [1] records,
+// [2] bins redone by mb_bigbin_kernel, [3] records asked for in the fullest region, [4] distinct records.  d_hist[nbins_hist + 1], d_runs (distinct k-mers = keys appended to d_out_keys), d_pairs
+// (sum over genomes of their distinct k-mers) are zeroed here.  exact != 0: the call before this one, on the same group, ended with flag 1;
+// partition again into regions of exactly the sizes that attempt counted (they are still in the context's scratch).
+int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u64 n_sym, int k, const u64 *d_seg_off, int n_genomes, u32 cs, u32 nbins_hist,
+                        u64 *d_hist, void *d_out_keys, u64 *d_runs, u64 *d_pairs, u64 *d_stat, int exact, u32 nb_fixed, u32 *nb_used, void *ev_buf,
+                        u64 *ev_count, u64 ev_cap, u64 store_base, khb_peer_route route)
+{
+    if (!khb_bins_eligible(k, n_genomes, n_sym)) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: k=%d / %d genomes not supported", k, n_genomes);
+    mb_plan_in pin;
+    pin.k = k;
+    pin.n_genomes = n_genomes;
+    pin.nchunks = 0;
+    pin.n_sym = n_sym;
+    pin.rho_prev = ctx->bins_rho;
+    pin.nb_fixed = nb_fixed;
+    pin.cap_fixed = 0;
+    pin.nbins_hist = nbins_hist;
+    pin.hint_k = ctx->bins_hint_k;
+    pin.hint_genomes = ctx->bins_hint_genomes;
+    pin.hint_regions = ctx->bins_hint_regions;
+    pin.hint_max = ctx->bins_hint_max;
+    mb_plan pl;
+    int rc = mb_make_plan(ctx, pin, &pl);
+    if (rc) return rc;
+    const int KW = pl.KW, m = pl.m;
+    const u32 capw = pl.capw, nb = pl.nb, cap = pl.cap, thr1 = pl.thr1, over_cap = pl.over_cap;
+    const mc_geom geo = pl.geo;
+    const u64 n_regions = pl.n_regions;
+    const size_t rec_bytes = pl.rec_bytes;
+    const double rho_w = pl.rho_w;
+    if (nb_used) *nb_used = nb;
+    const bool multi = geo.nchunks > 1;
     void *p;
     if ((rc = khb_scratch_get(ctx, SCR_AUX, (size_t)n_regions * 12 + (size_t)nb * 48 + 512, &p))) return rc;
     u32 *d_over_count = (u32 *)p;                 // [0] bins in the list
@@ -1256,68 +1401,185 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
     {
         const u64 tiles = div_up(n_sym, MB_TILE);
         khb_prof_begin(ctx, KHB_K_BIN_PARTITION);
+        mb_shard nosh;
+        memset(&nosh, 0, sizeof(nosh));
         if (KW == 2)
-            mb_partition_kernel<2><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, m, nb, d_seg_off, n_genomes, geo.nchunks,
-                                                                                  d_cur, (u64 *)pr, cap, capw, roff, d_stat);
+            mb_partition_kernel<2, false><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, m, nb, d_seg_off, n_genomes, geo.nchunks,
+                                                                                         d_cur, (u64 *)pr, cap, capw, roff, d_stat, nosh);
         else
-            mb_partition_kernel<3><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, m, nb, d_seg_off, n_genomes, geo.nchunks,
-                                                                                  d_cur, (u64 *)pr, cap, capw, roff, d_stat);
+            mb_partition_kernel<3, false><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, m, nb, d_seg_off, n_genomes, geo.nchunks,
+                                                                                         d_cur, (u64 *)pr, cap, capw, roff, d_stat, nosh);
         khb_prof_end(ctx, KHB_K_BIN_PARTITION, n_sym * 3 / 8);
         KHB_LAUNCH_CHECK(ctx);
     }
     {
-        size_t shm = mc_smem_bytes(KW, geo, 256);
-        if (shm > 227 * 1024) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: %zu bytes of shared memory per CTA", shm);
-        // two CTAs of 256 threads per SM at least; where the tables leave room for one CTA only, that one has 512 threads
-        const bool wide = 2 * (shm + 1024) > 227 * 1024;
-        const void *fn, *bfn;
-        if (KW == 2) {
-            fn = multi ? (wide ? (const void *)mb_count_kernel<2, true, 512> : (const void *)mb_count_kernel<2, true, 256>)
-                       : (wide ? (const void *)mb_count_kernel<2, false, 512> : (const void *)mb_count_kernel<2, false, 256>);
-            bfn = multi ? (const void *)mb_bigbin_kernel<2, true> : (const void *)mb_bigbin_kernel<2, false>;
-        } else {
-            fn = multi ? (wide ? (const void *)mb_count_kernel<3, true, 512> : (const void *)mb_count_kernel<3, true, 256>)
-                       : (wide ? (const void *)mb_count_kernel<3, false, 512> : (const void *)mb_count_kernel<3, false, 256>);
-            bfn = multi ? (const void *)mb_bigbin_kernel<3, true> : (const void *)mb_bigbin_kernel<3, false>;
-        }
-        const int block = wide ? 512 : 256;
-        shm = mc_smem_bytes(KW, geo, block);
-        int per_sm = 0;
-        KHB_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-        KHB_CUDA(ctx, cudaFuncSetAttribute(bfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-        KHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, shm));
-        if (per_sm < 1) return khb_fail(ctx, KHB_ERR_ARG, "minimizer-bin group stage: the counting kernel does not fit an SM (%zu bytes of shared memory)", shm);
-        const long long want = mb_env("KHB_BINS_CTAS_PER_SM", 0);
-        if (want > 0 && want < per_sm) per_sm = (int)want;
-        u32 grid = (u32)ctx->num_sms * (u32)per_sm;
-        if (grid > nb) grid = nb;
-        const u64 *c_rec = (const u64 *)pr;
-        const u32 *c_cur = d_cur;
-        u32 n_gen = (u32)n_genomes, cs_ = cs, nb_ = nb, cap_ = cap, thr_ = thr1, ocap_ = over_cap;
-        int k_ = k;
-        void *keys_ = d_out_keys;
         mb_evlog evlog;
         evlog.buf = (mb_event *)ev_buf;
         evlog.count = ev_count;
         evlog.cap = ev_cap;
         evlog.store_base = store_base;
-        const u32 *c_list = d_over_list, *c_cnt = d_over_count;
-        void *cargs[] = {&c_rec, &c_cur, &nb_, &cap_, &k_, &geo, &n_gen, &cs_, &thr_, &ocap_, &d_hist, &keys_, &d_runs, &d_pairs, &d_over_list, &d_over_count, &d_stat, &roff, &evlog, &route};
-        if (mb_env("KHB_BINS_VERBOSE", 0))
-            fprintf(stderr, "[bins] k=%d genomes=%d windows=%llu bins=%u chunks=%u cap=%u slots=2^%u dcap=%u thr1=%u rho_w=%.3f shm=%zu ctas/sm=%d block=%d\n", k, n_genomes,
-                    (unsigned long long)n_sym, nb, geo.nchunks, cap, geo.s_log2, geo.dcap, thr1, rho_w, shm, per_sm, block);
-        khb_prof_begin(ctx, KHB_K_BIN_COUNT);
-        KHB_CUDA(ctx, cudaLaunchKernel(fn, dim3(grid), dim3(block), cargs, shm, ctx->stream));
-        khb_prof_end(ctx, KHB_K_BIN_COUNT, 0);
-        KHB_LAUNCH_CHECK(ctx);
-        void *bargs[] = {&c_rec, &c_cur, &cap_, &k_, &geo, &n_gen, &cs_, &d_hist, &keys_, &d_runs, &d_pairs, &c_list, &c_cnt, &ocap_, &d_stat, &roff, &evlog, &route};
-        KHB_CUDA(ctx, cudaLaunchKernel(bfn, dim3((u32)ctx->num_sms * 2u), dim3(MC_BLOCK), bargs, shm, ctx->stream));
-        KHB_LAUNCH_CHECK(ctx);
+        if ((rc = mb_launch_count(ctx, pl, k, (const u64 *)pr, d_cur, nb, (u32)n_genomes, cs, d_hist, d_out_keys, d_runs, d_pairs, d_over_list, d_over_count, d_stat, roff,
+                                  evlog, route, n_sym))) return rc;
         mb_region_max_kernel<<<(unsigned)ctx->num_sms * 4u, 256, 0, ctx->stream>>>(d_cur, n_regions, d_stat + 3);
         KHB_LAUNCH_CHECK(ctx);
         ctx->bins_last_regions = n_regions;
     }
     return KHB_OK;
+}
+
+// ---- one group on several GPUs: the same two passes, the records crossing NVLink in between ------------------------------------------
+// (include/khoice_b200.h: khb_team_*).  The members of a team plan from the same numbers (mb_make_plan is a pure function), so every member
+// knows where the owner of a bin expects the records of (bin, chunk): buffer `parity` of the owner holds bpo x nchunks_total regions of `cap`
+// records, then the table of region sizes.
+struct mb_team_layout {
+    u32 bpo;              // bins per owner
+    size_t rec_bytes;     // records of one receive buffer
+    size_t cur_off;       // offset of the region sizes inside it
+    size_t need;          // bytes one receive buffer must hold
+};
+static mb_team_layout mb_team_layout_of(const mb_plan &pl, int team)
+{
+    mb_team_layout L;
+    L.bpo = (u32)div_up((size_t)pl.nb, (size_t)team);
+    L.rec_bytes = (size_t)L.bpo * pl.geo.nchunks * pl.cap * (pl.KW + 1) * 8;
+    L.cur_off = (L.rec_bytes + 255) & ~(size_t)255;
+    L.need = L.cur_off + (((size_t)L.bpo * pl.geo.nchunks * 4 + 255) & ~(size_t)255);
+    return L;
+}
+static int mb_team_plan(khb_ctx *ctx, int k, const khb_team_group *tg, u32 nbins_hist, mb_plan *pl)
+{
+    if (!tg || tg->n_genomes_total < 1 || tg->n_chunks_total < 1 || tg->n_chunks_total > 128 || tg->chunk_base < 0 || tg->chunk_base >= tg->n_chunks_total ||
+        (tg->parity != 0 && tg->parity != 1) || !tg->n_sym_total)
+        return khb_fail(ctx, KHB_ERR_ARG, "khb_team_*: bad group description");
+    if (!khb_bins_eligible(k, tg->n_genomes_total, tg->n_sym_total))
+        return khb_fail(ctx, KHB_ERR_ARG, "khb_team_*: a group is sharded through the minimizer bins only (17 <= k <= 63, k != 32); k=%d", k);
+    mb_plan_in pin;
+    pin.k = k;
+    pin.n_genomes = tg->n_genomes_total;
+    pin.nchunks = (u32)tg->n_chunks_total;
+    pin.n_sym = tg->n_sym_total;
+    pin.rho_prev = tg->rho;
+    pin.nb_fixed = 0;
+    pin.cap_fixed = tg->region_cap;
+    pin.nbins_hist = nbins_hist;
+    pin.hint_k = 0;
+    pin.hint_genomes = 0;
+    pin.hint_regions = 0;
+    pin.hint_max = 0;
+    return mb_make_plan(ctx, pin, pl);
+}
+int khb_bins_team_plan_impl(khb_ctx *ctx, int k, const khb_team_group *tg, u32 nbins_hist, u32 *nb, u32 *cap, u64 *half_bytes)
+{
+    khb_team *tm = ctx->team;
+    if (!tm) return khb_fail(ctx, KHB_ERR_STATE, "khb_team_plan: khb_team_alloc first");
+    mb_plan pl;
+    int rc = mb_team_plan(ctx, k, tg, nbins_hist, &pl);
+    if (rc) return rc;
+    const mb_team_layout L = mb_team_layout_of(pl, tm->size);
+    if (nb) *nb = pl.nb;
+    if (cap) *cap = pl.cap;
+    if (half_bytes) *half_bytes = L.need;
+    return KHB_OK;
+}
+
+// the sizes of this member's regions -> the owners' tables (the owner's counting pass reads them like the cursors of a local partition)
+__global__ void __launch_bounds__(256)
+mb_cursor_push_kernel(const u32 *__restrict__ lcur, u32 nb, u32 nchunks_mine, mb_shard sh)
+{
+    const u64 n = (u64)nb * nchunks_mine;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const u32 bin = (u32)(i / nchunks_mine), lc = (u32)(i - (u64)bin * nchunks_mine);
+        const u32 owner = bin / sh.bpo, lb = bin - owner * sh.bpo;
+        sh.cur[owner][(size_t)lb * sh.nchunks_total + sh.chunk_base + lc] = lcur[i];
+    }
+}
+
+// Pass P of this member's slice (n_genomes genomes, n_sym symbols) of a sharded group.  d_info: u64[4] device, [0] flags (1: one of this
+// member's regions overflowed), [3] records asked for in its fullest region.
+int khb_bins_team_partition_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u64 n_sym, int k, const u64 *d_seg_off, int n_genomes,
+                                 const khb_team_group *tg, u64 *d_info)
+{
+    khb_team *tm = ctx->team;
+    if (!tm || !tm->opened) return khb_fail(ctx, KHB_ERR_STATE, "khb_team_partition: khb_team_alloc / khb_team_open first");
+    mb_plan pl;
+    int rc = mb_team_plan(ctx, k, tg, KHB_COUNTER_MAX, &pl);
+    if (rc) return rc;
+    const u32 nchunks_mine = (u32)div_up((size_t)n_genomes, 64);
+    if (n_genomes < 1 || (u32)tg->chunk_base + nchunks_mine > (u32)tg->n_chunks_total)
+        return khb_fail(ctx, KHB_ERR_ARG, "khb_team_partition: %d genomes from chunk %d do not fit the group's %d chunks", n_genomes, tg->chunk_base, tg->n_chunks_total);
+    const mb_team_layout L = mb_team_layout_of(pl, tm->size);
+    if (L.need > tm->half_bytes)
+        return khb_fail(ctx, KHB_ERR_CAPACITY, "khb_team_partition: the group needs %zu bytes per receive buffer, the team allocated %zu", L.need, tm->half_bytes);
+    mb_shard sh;
+    memset(&sh, 0, sizeof(sh));
+    sh.team = (u32)tm->size;
+    sh.bpo = L.bpo;
+    sh.nchunks_total = pl.geo.nchunks;
+    sh.chunk_base = (u32)tg->chunk_base;
+    for (int t = 0; t < tm->size; t++) {
+        char *half = (char *)tm->peer_base[t] + (size_t)tg->parity * tm->half_bytes;
+        sh.rec[t] = (u64 *)half;
+        sh.cur[t] = (u32 *)(half + L.cur_off);
+    }
+    void *p;
+    const u64 n_local = (u64)pl.nb * nchunks_mine;
+    if ((rc = khb_scratch_get(ctx, SCR_TEAM, n_local * 4 + 64, &p))) return rc;
+    u32 *d_lcur = (u32 *)p;
+    KHB_CUDA(ctx, cudaMemsetAsync(d_lcur, 0, n_local * 4, ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(d_info, 0, 4 * sizeof(u64), ctx->stream));
+    if (n_sym) {
+        const u64 tiles = div_up(n_sym, MB_TILE), last_w = n_sym / 32 + 3;
+        khb_prof_begin(ctx, KHB_K_BIN_PARTITION);
+        if (pl.KW == 2)
+            mb_partition_kernel<2, true><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, pl.m, pl.nb, d_seg_off, n_genomes, nchunks_mine,
+                                                                                        d_lcur, nullptr, pl.cap, pl.capw, nullptr, d_info, sh);
+        else
+            mb_partition_kernel<3, true><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, pl.m, pl.nb, d_seg_off, n_genomes, nchunks_mine,
+                                                                                        d_lcur, nullptr, pl.cap, pl.capw, nullptr, d_info, sh);
+        khb_prof_end(ctx, KHB_K_BIN_PARTITION, n_sym * 3 / 8);
+        KHB_LAUNCH_CHECK(ctx);
+    }
+    mb_cursor_push_kernel<<<(unsigned)(div_up(n_local, 256) < 1184 ? div_up(n_local, 256) : 1184), 256, 0, ctx->stream>>>(d_lcur, pl.nb, nchunks_mine, sh);
+    KHB_LAUNCH_CHECK(ctx);
+    mb_region_max_kernel<<<(unsigned)ctx->num_sms * 4u, 256, 0, ctx->stream>>>(d_lcur, n_local, d_info + 3);
+    KHB_LAUNCH_CHECK(ctx);
+    if (mb_env("KHB_BINS_VERBOSE", 0))
+        fprintf(stderr, "[team] member %d/%d: k=%d slice=%d genomes (chunks %d..%u of %d) windows=%llu of %llu bins=%u (%u per owner) cap=%u buffer=%zu of %zu bytes\n", tm->member,
+                tm->size, k, n_genomes, tg->chunk_base, tg->chunk_base + nchunks_mine - 1, tg->n_chunks_total, (unsigned long long)n_sym, (unsigned long long)tg->n_sym_total,
+                pl.nb, L.bpo, pl.cap, L.need, tm->half_bytes);
+    return KHB_OK;
+}
+
+// Passes C and B over the bins this member owns; outputs like khb_bins_count_impl's (d_stat[0] & 2: a bin could not be counted).
+int khb_bins_team_count_impl(khb_ctx *ctx, int k, const khb_team_group *tg, u32 cs, u32 nbins_hist, u64 *d_hist, void *d_out_keys, u64 *d_runs,
+                             u64 *d_pairs, u64 *d_stat, khb_peer_route route)
+{
+    khb_team *tm = ctx->team;
+    if (!tm || !tm->opened) return khb_fail(ctx, KHB_ERR_STATE, "khb_team_count: khb_team_alloc / khb_team_open first");
+    mb_plan pl;
+    int rc = mb_team_plan(ctx, k, tg, nbins_hist, &pl);
+    if (rc) return rc;
+    const mb_team_layout L = mb_team_layout_of(pl, tm->size);
+    if (L.need > tm->half_bytes) return khb_fail(ctx, KHB_ERR_CAPACITY, "khb_team_count: the group needs %zu bytes per receive buffer, the team allocated %zu", L.need, tm->half_bytes);
+    const u64 first = (u64)tm->member * L.bpo;
+    const u32 nb_mine = first >= pl.nb ? 0u : (pl.nb - first < L.bpo ? (u32)(pl.nb - first) : L.bpo);
+    char *half = (char *)tm->recv + (size_t)tg->parity * tm->half_bytes;
+    void *p;
+    if ((rc = khb_scratch_get(ctx, SCR_AUX, (size_t)pl.nb * 48 + 512, &p))) return rc;
+    u32 *d_over_count = (u32 *)p, *d_over_list = d_over_count + 16;
+    KHB_CUDA(ctx, cudaMemsetAsync(d_over_count, 0, 64, ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, ((size_t)nbins_hist + 1) * sizeof(u64), ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(d_runs, 0, sizeof(u64), ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(d_pairs, 0, sizeof(u64), ctx->stream));
+    KHB_CUDA(ctx, cudaMemsetAsync(d_stat, 0, 5 * sizeof(u64), ctx->stream));
+    if (!nb_mine) return KHB_OK;
+    mb_evlog evlog;
+    evlog.buf = nullptr;
+    evlog.count = nullptr;
+    evlog.cap = 0;
+    evlog.store_base = 0;
+    return mb_launch_count(ctx, pl, k, (const u64 *)half, (const u32 *)(half + L.cur_off), nb_mine, (u32)tg->n_genomes_total, cs, d_hist, d_out_keys, d_runs, d_pairs,
+                           d_over_list, d_over_count, d_stat, nullptr, evlog, route, tg->n_sym_total);
 }
 
 // ---- the across-group stage, bin by bin -------------------------------------------------------------------------------------------
@@ -1689,12 +1951,14 @@ extern "C" KHB_API int khb_bins_partition(khb_ctx *ctx, const uint64_t *d_codes,
     KHB_CUDA(ctx, cudaMemsetAsync(p, 0, n_regions * 8 + 64, ctx->stream));
     if (n_symbols) {
         const u64 tiles = div_up(n_symbols, MB_TILE), last_w = n_symbols / 32 + 3;
+        mb_shard nosh;
+        memset(&nosh, 0, sizeof(nosh));
         if (KW == 2)
-            mb_partition_kernel<2><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>((const u64 *)d_codes, d_valid, n_symbols, last_w, last_w, k, m, n_bins, (const u64 *)d_seg_off,
-                                                                                  n_genomes, nchunks, d_cur, (u64 *)pr, cap, capw, nullptr, d_flag);
+            mb_partition_kernel<2, false><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>((const u64 *)d_codes, d_valid, n_symbols, last_w, last_w, k, m, n_bins, (const u64 *)d_seg_off,
+                                                                                         n_genomes, nchunks, d_cur, (u64 *)pr, cap, capw, nullptr, d_flag, nosh);
         else
-            mb_partition_kernel<3><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>((const u64 *)d_codes, d_valid, n_symbols, last_w, last_w, k, m, n_bins, (const u64 *)d_seg_off,
-                                                                                  n_genomes, nchunks, d_cur, (u64 *)pr, cap, capw, nullptr, d_flag);
+            mb_partition_kernel<3, false><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>((const u64 *)d_codes, d_valid, n_symbols, last_w, last_w, k, m, n_bins, (const u64 *)d_seg_off,
+                                                                                         n_genomes, nchunks, d_cur, (u64 *)pr, cap, capw, nullptr, d_flag, nosh);
         KHB_LAUNCH_CHECK(ctx);
         mb_region_windows_kernel<<<(unsigned)div_up(n_regions, 256), 256, 0, ctx->stream>>>((const u64 *)pr, d_cur, n_regions, cap, KW + 1, d_win);
         KHB_LAUNCH_CHECK(ctx);

@@ -225,7 +225,29 @@ struct khb_ctx {
     u32 ev_nb;          // bins of the groups in the store
     u64 across_by_bins, across_by_sort;   // performance counters
     int group_mode;    // KHB_GROUP_* (khb_set_group_mode; initial value from the environment variable KHB_GROUP_MODE)
+    struct khb_team *team;  // one group sharded over several GPUs (team.cu)
 };
+
+// ---- a group sharded over the members of a team (team.cu, bins.cu) ----------------------------------------------------------------
+#define KHB_TEAM_MAX 8
+// what the sharded partition pass needs to know: the owner of bin b is member b / bpo; its record buffer and its table of region sizes
+struct mb_shard {
+    u32 team;            // members (0: not sharded)
+    u32 bpo;             // bins per owner
+    u32 nchunks_total;   // chunks of 64 genome ids of the whole group
+    u32 chunk_base;      // first chunk of this member's slice (its genome ids start at 64 * chunk_base)
+    u64 *rec[KHB_TEAM_MAX];
+    u32 *cur[KHB_TEAM_MAX];
+};
+struct khb_team {
+    int size = 0, member = 0;
+    size_t half_bytes = 0;             // bytes of ONE of the two receive buffers
+    void *recv = nullptr;              // this member's two receive buffers
+    void *peer_base[KHB_TEAM_MAX];     // every member's (own entry = recv)
+    bool opened = false;
+    u64 slice_sym = 0, slice_bases = 0, slice_fasta_bytes = 0;   // this member's slice of the group in flight (for the stats of the count call)
+};
+
 
 // kernel ids for khb_profile_read
 enum { KHB_K_PACK = 0, KHB_K_EXTRACT = 1, KHB_K_RADIX_HIST = 2, KHB_K_ONESWEEP = 3, KHB_K_UNIQUE = 4, KHB_K_RLE = 5, KHB_K_PARTITION = 6, KHB_K_HASH_INSERT = 7, KHB_K_HASH_COUNT = 8, KHB_K_BIN_PARTITION = 9, KHB_K_BIN_COUNT = 10, KHB_K_BIN_ACROSS = 11, KHB_K_COUNT = 12 };
@@ -233,7 +255,7 @@ void khb_prof_begin(khb_ctx *ctx, int id);
 void khb_prof_end(khb_ctx *ctx, int id, u64 alg_bytes);
 void khb_prof_patch(khb_ctx *ctx, int id, u64 alg_bytes);  // algorithmic bytes of the LAST record of that kernel, once they are known
 
-enum { SCR_TILE = 0, SCR_LOOKBACK = 1, SCR_HIST = 2, SCR_MISC = 3, SCR_KEYS_A = 4, SCR_KEYS_B = 5, SCR_PACK = 6, SCR_FLAGS = 7, SCR_PAY_A = 8, SCR_PAY_B = 9, SCR_AUX = 10 };  // SCR_MISC belongs to the sort (segment tables, tickets)
+enum { SCR_TILE = 0, SCR_LOOKBACK = 1, SCR_HIST = 2, SCR_MISC = 3, SCR_KEYS_A = 4, SCR_KEYS_B = 5, SCR_PACK = 6, SCR_FLAGS = 7, SCR_PAY_A = 8, SCR_PAY_B = 9, SCR_AUX = 10, SCR_TEAM = 11 };  // SCR_MISC belongs to the sort (segment tables, tickets)
 #define KHB_NSCRATCH 12
 
 int khb_fail(khb_ctx *ctx, int code, const char *fmt, ...);
@@ -251,6 +273,12 @@ struct khb_peer_route {
 int khb_peer_route_get(khb_ctx *ctx, int key_bytes, khb_peer_route *out);  // for kernels that push while they emit (bins.cu)
 void khb_peer_mark_pushed(khb_ctx *ctx);                                    // ... the store's keys so far are at their owners
 int khb_peer_poison(khb_ctx *ctx);                                          // ... or not: make this round fall back to the NCCL route
+// one group on several GPUs (bins.cu; the entry points are in api.cu, the buffers in team.cu)
+int khb_bins_team_plan_impl(khb_ctx *ctx, int k, const khb_team_group *tg, u32 nbins_hist, u32 *nb, u32 *cap, u64 *half_bytes);
+int khb_bins_team_partition_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u64 n_sym, int k, const u64 *d_seg_off, int n_genomes,
+                                 const khb_team_group *tg, u64 *d_info);
+int khb_bins_team_count_impl(khb_ctx *ctx, int k, const khb_team_group *tg, u32 cs, u32 nbins_hist, u64 *d_hist, void *d_out_keys, u64 *d_runs,
+                             u64 *d_pairs, u64 *d_stat, khb_peer_route route);
 
 #define KHB_CUDA(ctx, expr)                                                           \
     do {                                                                              \

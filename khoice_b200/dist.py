@@ -233,6 +233,135 @@ class AcrossExchanger:
             self.ready = False
 
 
+# ---- ONE group on several GPUs ---------------------------------------------------------------------------------------------
+def team_shape(n_groups: int, world: int, max_team: int = 8) -> int:
+    """Members per team: the smallest divisor T of `world` for which the groups divide evenly over the world / T teams -- whole
+    groups where they fit (T = 1), sharded groups where dealing them whole would leave GPUs idle (20 groups on 8 GPUs: T = 2,
+    four teams of five groups each instead of 3/3/3/3/2/2/2/2)."""
+    for t in range(1, min(world, max_team) + 1):
+        if world % t == 0 and n_groups % (world // t) == 0:
+            return t
+    return 1
+
+
+def genome_slices(n_genomes: int, team_size: int) -> List[Tuple[int, int]]:
+    """[lo, hi) of every member's contiguous slice of a group's genomes (sizes differ by at most one)."""
+    q, r = divmod(n_genomes, team_size)
+    out, lo = [], 0
+    for t in range(team_size):
+        hi = lo + q + (1 if t < r else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def chunk_layout(slice_sizes: Sequence[int]) -> Tuple[List[int], int]:
+    """Every slice is padded to whole chunks of 64 genome ids, so that a (bin, chunk) region of the record buffers has exactly one
+    writer: (first chunk of every member, chunks of the whole group)."""
+    base, c = [], 0
+    for n in slice_sizes:
+        base.append(c)
+        c += -(-int(n) // 64)
+    return base, c
+
+
+class TeamSharder:
+    """Steps 1-4 of ONE group (exp_type_1.smk:156-191) on the GPUs of a team (include/khoice_b200.h: khb_team_*).
+
+    Every member holds a slice of the group's genomes.  Per group and member: K1 + the partition pass of the minimizer-bin stage,
+    whose super-k-mer records go straight into the record buffer of the bin's owner (peer memory, CUDA IPC over NVLink); ONE small
+    all-gather in the team -- the barrier behind which every member's records are at their owners, and the carrier of the overflow
+    flags, the fullest region (sizes the next group's regions) and the distinct-k-mer ratio of the previous group (sizes its
+    tables), so that all members keep planning from the same numbers --; then every member counts the bins it owns.  The partial
+    histograms add up to the group's step_4 histogram (the caller's all-reduce over all ranks does that), the distinct keys of
+    the member's bins enter its group-set store / the across-group exchange like those of a whole group.
+
+    `group`: the process group of the team (None: the default group, when the world is one team)."""
+
+    def __init__(self, eng: Engine, team_size: int, member: int, group=None):
+        self.eng, self.T, self.member, self.group = eng, int(team_size), int(member), group
+        self.ready = False
+        self.half_bytes = 0
+        self.parity = 0
+        self.hints: Dict[Tuple[int, int, int], dict] = {}     # (k, genomes, chunks) -> {"rho", "cap"} agreed in the team
+        self.prev = (0, 0, (0, 0, 0))                         # distinct k-mers / windows this member counted in the previous group, its shape
+        self.retries = self.setups = self.groups = 0
+        nccl = dist.is_initialized() and dist.get_backend(group) == "nccl"
+        self.ctrl = torch.device("cuda", eng.device) if nccl else torch.device("cpu")
+
+    def _setup(self, half_bytes: int):
+        """Collective in the team: (re)allocate the receive buffers and map everybody's."""
+        if self.ready:
+            self.close()
+        handle = self.eng.team_alloc(self.T, self.member, int(half_bytes))
+        mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(self.ctrl)
+        allh = torch.empty(64 * self.T, dtype=torch.uint8, device=self.ctrl)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        self.eng.team_open(bytes(allh.cpu().numpy().tobytes()))
+        dist.barrier(group=self.group)          # nobody stores before everybody has mapped everybody
+        self.half_bytes = int(half_bytes)
+        self.ready = True
+        self.setups += 1
+
+    def close(self):
+        """Collective in the team: every member drops its mappings before any member frees its buffers."""
+        if self.ready:
+            self.eng.team_unmap()
+            dist.barrier(group=self.group)
+            self.eng.team_close()
+            self.ready = False
+
+    def _fit(self, k: int, tg):
+        plan = self.eng.team_plan(k, tg) if self.ready else None
+        if plan is None:
+            # the plan needs a team object for its size: allocate a token first (every member takes the same path)
+            self._setup(1 << 20)
+            plan = self.eng.team_plan(k, tg)
+        if plan["half_bytes"] > self.half_bytes:
+            self._setup(plan["half_bytes"] + plan["half_bytes"] // 4)
+        return plan
+
+    def run_group(self, source, k: int, n_genomes_total: int, slice_sizes: Sequence[int], n_sym_total: int, nbins: int = COUNTER_MAX,
+                  keep_set: bool = True):
+        """`source`: this member's slice (host FASTA texts, StagedFasta or PackedGroup).  `slice_sizes`: genomes of every member's slice;
+        `n_sym_total`: symbols of the whole group -- the same estimate on every member.  Returns (partial histogram, stats)."""
+        from .engine import TeamGroup
+        if len(slice_sizes) != self.T or sum(slice_sizes) != n_genomes_total or min(slice_sizes) < 1:
+            raise ValueError(f"a team of {self.T} needs {self.T} non-empty slices of the group's {n_genomes_total} genomes, got {list(slice_sizes)}")
+        base, n_chunks = chunk_layout(slice_sizes)
+        shape = (int(k), int(n_genomes_total), int(n_chunks))
+        hint = self.hints.get(shape, {})
+        tg = TeamGroup(n_genomes_total, n_chunks, base[self.member], self.parity, int(n_sym_total), float(hint.get("rho", 0.0)),
+                       int(hint.get("cap", 0)), 0)
+        self._fit(k, tg)
+        for attempt in range(6):
+            info = self.eng.team_partition(source, k, tg)
+            row = torch.tensor([1 if info["overflow"] else 0, info["fullest_region"], self.prev[0], self.prev[1]], dtype=torch.int64, device=self.ctrl)
+            table = torch.empty((self.T, 4), dtype=torch.int64, device=self.ctrl)
+            dist.all_gather_into_tensor(table.view(-1), row, group=self.group)     # also the barrier: every member's records are at their owners
+            table = table.cpu().numpy()
+            fullest = int(table[:, 1].max())
+            if not table[:, 0].any():
+                break
+            # a region overflowed somewhere: every member partitions again into larger regions (the fullest region seen so far is a lower
+            # bound only -- senders stop counting exactly where they overflow -- hence the factor)
+            self.retries += 1
+            tg.region_cap = max(2 * fullest, 2 * int(self.eng.team_plan(k, tg)["region_cap"])) + 64
+            self._fit(k, tg)
+        else:
+            raise RuntimeError(f"team: the regions of a k={k} group of {n_genomes_total} genomes still overflow at {tg.region_cap} records")
+        hist, st = self.eng.team_count(k, tg, nbins=nbins, keep_set=keep_set)
+        # what the team agreed on before this count: the previous group's ratio (if it had this shape) and this group's fullest region
+        if self.prev[2] == shape and int(table[:, 3].sum()) > 0:
+            hint = dict(hint, rho=float(table[:, 2].sum()) / float(table[:, 3].sum()))
+        hint = dict(hint, cap=int(fullest * 1.4) + 64)
+        self.hints[shape] = hint
+        self.prev = (int(st["distinct"]), int(info["windows"]), shape)
+        self.parity ^= 1
+        self.groups += 1
+        return hist, st
+
+
 def run_exp1_k(adapter, groups: Dict[int, Sequence], n_groups_total: int, k: int, nbins: int = COUNTER_MAX, group=None):
     """One k on this rank's share.  `groups` maps the 1-based numbers of the groups this rank owns to their
     FASTA texts.  Returns (within [n_groups_total, nbins+1] uint64, across [nbins+1] uint64, stats)."""

@@ -46,6 +46,12 @@ class Stats(C.Structure):
         return {name: getattr(self, name) for name, _ in self._fields_}
 
 
+class TeamGroup(C.Structure):
+    """Mirror of ``khb_team_group``: one group as the members of a team see it (the same values on every member but chunk_base)."""
+    _fields_ = [("n_genomes_total", C.c_int32), ("n_chunks_total", C.c_int32), ("chunk_base", C.c_int32), ("parity", C.c_int32),
+                ("n_sym_total", C.c_uint64), ("rho", C.c_double), ("region_cap", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 # every symbol include/khoice_b200.h declares: (name, restype, argtypes)
 _P = C.c_void_p
 _SIGNATURES = [
@@ -112,6 +118,15 @@ _SIGNATURES = [
     ("khb_peer_unmap", C.c_int, [_P]),
     ("khb_peer_close", C.c_int, [_P]),
     ("khb_peer_region_keys", C.c_uint64, [_P]),
+    ("khb_team_alloc", C.c_int, [_P, C.c_int, C.c_int, C.c_uint64, _P]),
+    ("khb_team_open", C.c_int, [_P, _P]),
+    ("khb_team_unmap", C.c_int, [_P]),
+    ("khb_team_close", C.c_int, [_P]),
+    ("khb_team_plan", C.c_int, [_P, C.c_int, C.POINTER(TeamGroup), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
+    ("khb_team_partition_fasta", C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.POINTER(TeamGroup), _P]),
+    ("khb_team_partition_staged", C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.POINTER(TeamGroup), _P]),
+    ("khb_team_partition_packed", C.c_int, [_P, C.c_int, _P, C.POINTER(TeamGroup), _P]),
+    ("khb_team_count", C.c_int, [_P, C.c_int, C.POINTER(TeamGroup), C.c_uint32, _P, C.c_int, C.POINTER(Stats)]),
     ("khb_set_group_mode", C.c_int, [_P, C.c_int]),
     ("khb_hash_overflows", C.c_uint64, [_P]),
     ("khb_bins_counters", None, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -309,6 +324,48 @@ class Engine:
     @property
     def peer_region_keys(self) -> int:
         return int(self.lib.khb_peer_region_keys(self.ctx))
+
+    # ---- one group on several GPUs (csrc/team.cu, csrc/bins.cu; driver: dist.TeamSharder) ----
+    def team_alloc(self, team_size: int, member: int, half_bytes: int) -> bytes:
+        """Allocate this member's two record receive buffers; returns the 64-byte CUDA IPC handle for the other members."""
+        h = (C.c_ubyte * 64)()
+        self._chk(self.lib.khb_team_alloc(self.ctx, team_size, member, int(half_bytes), h))
+        return bytes(h)
+
+    def team_open(self, handles: bytes):
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        self._chk(self.lib.khb_team_open(self.ctx, buf))
+
+    def team_unmap(self):
+        self._chk(self.lib.khb_team_unmap(self.ctx))
+
+    def team_close(self):
+        self._chk(self.lib.khb_team_close(self.ctx))
+
+    def team_plan(self, k: int, tg: TeamGroup) -> dict:
+        nb, cap, hb = C.c_uint32(), C.c_uint32(), C.c_uint64()
+        self._chk(self.lib.khb_team_plan(self.ctx, k, C.byref(tg), C.byref(nb), C.byref(cap), C.byref(hb)))
+        return {"n_bins": int(nb.value), "region_cap": int(cap.value), "half_bytes": int(hb.value)}
+
+    def team_partition(self, source, k: int, tg: TeamGroup) -> dict:
+        """K1 + pass P of this member's slice; `source` is a list of host FASTA texts, a StagedFasta or a PackedGroup."""
+        info = np.zeros(4, dtype=np.uint64)
+        if isinstance(source, PackedGroup):
+            self._chk(self.lib.khb_team_partition_packed(self.ctx, k, source.handle, C.byref(tg), info.ctypes.data))
+        elif isinstance(source, StagedFasta):
+            self._chk(self.lib.khb_team_partition_staged(self.ctx, k, len(source.begin) - 1, source.buf.ptr, source.begin.ctypes.data, C.byref(tg),
+                                                         info.ctypes.data))
+        else:
+            arrs, ptrs, sizes = self._file_tables(source)
+            self._chk(self.lib.khb_team_partition_fasta(self.ctx, k, len(arrs), ptrs, sizes, C.byref(tg), info.ctypes.data))
+        return {"overflow": bool(info[0]), "fullest_region": int(info[1]), "windows": int(info[2]), "bases": int(info[3])}
+
+    def team_count(self, k: int, tg: TeamGroup, nbins: int = COUNTER_MAX, keep_set: bool = True):
+        """Passes C and B over the bins this member owns: (partial step_4 histogram, stats)."""
+        hist = np.zeros(nbins + 1, dtype=np.uint64)
+        st = Stats()
+        self._chk(self.lib.khb_team_count(self.ctx, k, C.byref(tg), nbins, hist.ctypes.data, int(keep_set), C.byref(st)))
+        return hist, st.as_dict()
 
     GROUP_MODES = {"auto": 0, "single-sort": 1, "two-sort": 2, "hash": 3, "bins": 4}
 
