@@ -491,9 +491,8 @@ def main():
     # straight into their owner's receive buffer over NVLink by one kernel behind the group's K5 (csrc/peer.cu); the first
     # round (a warm-up step) runs over NCCL (partition + all-to-all) and sizes the regions.  KHB_EXCHANGE=nccl keeps NCCL.
     ex = kd.AcrossExchanger(adapter, k, n_groups_total, mode=os.environ.get("KHB_EXCHANGE", "peer"))
-    ts, group_syms = None, {}
+    ts, group_syms, team_pg = None, {}, None
     if T > 1:
-        team_pg = None
         for t in range(n_teams):                # every rank creates every team's process group, in the same order
             pg = dist.new_group(ranks=list(range(t * T, (t + 1) * T)))
             if t == team_idx:
@@ -518,6 +517,13 @@ def main():
             nb += st["bases"]
             dsum += st["distinct"]
         ha, _ = ex.finish()
+        if ts and mine:
+            # every member holds the rows of ITS bins' k-mers; which bins those are moves with the planner's hints, the sum does not:
+            # one all-reduce in the team per k gives every member the groups' step_4 histograms
+            t = torch.from_numpy(np.stack([hs[g] for g in mine]).astype(np.int64)).to(dev)
+            dist.all_reduce(t, group=team_pg)
+            t = t.cpu().numpy().astype(np.uint64)
+            hs = {g: t[i] for i, g in enumerate(mine)}
         return hs, ha, nb, dsum
 
     def step_device():
@@ -621,7 +627,7 @@ def main():
     within_all, dsum_all = {}, {}
     for kk in ks:
         w = np.zeros((n_groups_total, nbins1 + 1), dtype=np.int64)   # last column: distinct k-mers of the group
-        for g in mine:
+        for g in (mine if member == 0 else []):      # teams: every member holds the team's sum, one of them contributes it
             w[g - 1, :nbins1] = out_dev[kk][0][g].astype(np.int64)
             w[g - 1, nbins1] = int(out_dev[kk][0][g][1:].sum())
         wt = torch.from_numpy(w).to(dev)
@@ -678,7 +684,7 @@ def main():
         # whole step against the roofline: algorithmic bytes of every kernel launched in the timed steps (this design's own
         # per-kernel contracts) / device time of the steps.  Rank 0's kernels x world.
         total_alg = float(sum(v["alg_bytes"] for v in prof.values())) * world
-        rho = dsum_all[k] / max(sum(out_dev[k][0][g][1:].astype(np.float64) @ np.arange(1, nbins1) for g in mine) * world, 1.0) if mine else 0.0
+        rho = dsum_all[k] / max(sum(out_dev[k][0][g][1:].astype(np.float64) @ np.arange(1, nbins1) for g in mine) * n_teams, 1.0) if mine else 0.0
         sv = survey_bytes_per_base(k, rho)
         pipeline = {"algorithmic_bytes_per_base": total_alg / max(bases_all * args.steps, 1.0),
                     "achieved": total_alg / (ms_dev * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",

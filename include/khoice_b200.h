@@ -334,7 +334,7 @@ KHB_API uint64_t khb_peer_region_keys(const khb_ctx *ctx);
  * Every member must pass the same khb_team_group except chunk_base.  Two receive buffers alternate (parity), so a member may
  * partition the next group while another still counts this one.  Protocol per group, on every member:
  *     khb_team_partition_*(..., h_info);  barrier + exchange h_info[0..1] in the team;  if any member reports h_info[0] != 0 (a region
- *     overflowed) repeat with a larger region_cap (every member);  khb_team_count. */
+ *     or an area overflowed) repeat with a larger region_cap / area_pct (every member);  khb_team_count. */
 typedef struct khb_team_group {
     int32_t n_genomes_total; /* genomes of the whole group                                                        */
     int32_t n_chunks_total;  /* sum over the members of ceil(slice genomes / 64)                                   */
@@ -342,8 +342,8 @@ typedef struct khb_team_group {
     int32_t parity;          /* 0 / 1: which receive buffer this group uses (alternate from group to group)        */
     uint64_t n_sym_total;    /* symbols of the whole group (an estimate will do: it sizes bins and tables)         */
     double rho;              /* distinct k-mers per window measured on an earlier group of this shape, 0 = unknown */
-    uint32_t region_cap;     /* records per (bin, chunk) region, 0 = planner default                               */
-    uint32_t reserved;
+    uint32_t region_cap;     /* records per (bin, chunk) region of the members' local partitions, 0 = planner default */
+    uint32_t area_pct;       /* room of one (sender, owner) area of the receive buffers in percent of the mean share, 0 = 250 */
 } khb_team_group;
 KHB_API int khb_team_alloc(khb_ctx *ctx, int team_size, int member, uint64_t half_bytes, unsigned char *handle_out /* 64 bytes */);
 KHB_API int khb_team_open(khb_ctx *ctx, const unsigned char *handles /* team_size x 64 bytes, member order */);
@@ -351,8 +351,9 @@ KHB_API int khb_team_unmap(khb_ctx *ctx); /* drop the members' mappings; barrier
 KHB_API int khb_team_close(khb_ctx *ctx);
 /* Geometry the planner derives from (k, tg): bins of the group, records per region, bytes ONE receive buffer must hold. */
 KHB_API int khb_team_plan(khb_ctx *ctx, int k, const khb_team_group *tg, uint32_t *n_bins, uint32_t *region_cap, uint64_t *half_bytes);
-/* K1 + pass P of this member's slice.  h_info[4]: [0] != 0: one of this member's regions overflowed, [1] records asked for in its
- * fullest region, [2] symbols, [3] bases of the slice.  Returns after the member's stores have completed. */
+/* K1 + pass P of this member's slice, then its regions packed into the owners' buffers.  h_info[4]: [0] bit 0: one of this member's
+ * regions overflowed (repeat with a larger region_cap), bit 1: one of its areas in an owner's buffer did (repeat with a larger area_pct),
+ * [1] records asked for in its fullest region, [2] symbols, [3] bases of the slice.  Returns after the member's stores have completed. */
 KHB_API int khb_team_partition_fasta(khb_ctx *ctx, int k, int n_genomes, const uint8_t *const *h_files, const size_t *h_sizes,
                              const khb_team_group *tg, uint64_t *h_info);
 KHB_API int khb_team_partition_staged(khb_ctx *ctx, int k, int n_genomes, const uint8_t *d_fasta, const uint64_t *h_begin,

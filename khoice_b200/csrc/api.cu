@@ -1242,14 +1242,16 @@ static int team_partition(khb_ctx *ctx, int k, const khb_packed &pk, const khb_t
     if (rc) return rc;
     KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 16640, d_info, 4 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the kernel is complete: its stores into the owners' buffers are visible to them
-    h_info[0] = ctx->h_mail[16640] & 1ull;
+    h_info[0] = ctx->h_mail[16640] & 3ull;
     h_info[1] = ctx->h_mail[16643];
     h_info[2] = pk.n_sym;
     h_info[3] = pk.n_sym - pk.n_breaks;
     tmm->slice_sym = pk.n_sym;
     tmm->slice_bases = pk.n_sym - pk.n_breaks;
     tmm->slice_fasta_bytes = pk.fasta_bytes;
-    khb_prof_patch(ctx, KHB_K_BIN_PARTITION, pk.n_sym * 3 / 8);
+    const u64 rec_bytes = ctx->h_mail[16641] * (k <= 32 ? 24 : 32);
+    khb_prof_patch(ctx, KHB_K_BIN_PARTITION, pk.n_sym * 3 / 8 + rec_bytes);
+    khb_prof_patch(ctx, KHB_K_PARTITION, 2 * rec_bytes);
     return KHB_OK;
 }
 

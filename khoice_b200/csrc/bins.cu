@@ -79,7 +79,13 @@ __device__ __forceinline__ u32 mb_segment_of(const u64 *__restrict__ seg_off, in
 // Region r of the record buffer: the fixed layout gives every region `cap` records at r * cap; after a region overflowed, the group is
 // partitioned again into regions of exactly the sizes the first attempt counted (roff[r] .. roff[r + 1], from mb_region_scan_kernel).
 __device__ __forceinline__ u64 mb_region_base(const u64 *__restrict__ roff, u32 r, u32 cap) { return roff ? __ldg(roff + r) : (u64)r * cap; }
-__device__ __forceinline__ u32 mb_region_cap(const u64 *__restrict__ roff, u32 r, u32 cap) { return roff ? (u32)(__ldg(roff + r + 1) - __ldg(roff + r)) : cap; }
+// (cap = MB_CAP_DENSE with roff: a team's receive buffer -- the regions lie wherever their senders packed them, roff[r] is the start of
+// region r only, and the region sizes the senders delivered are exact)
+#define MB_CAP_DENSE 0xFFFFFFFFu
+__device__ __forceinline__ u32 mb_region_cap(const u64 *__restrict__ roff, u32 r, u32 cap)
+{
+    return roff && cap != MB_CAP_DENSE ? (u32)(__ldg(roff + r + 1) - __ldg(roff + r)) : cap;
+}
 
 // exclusive prefix sums of the region sizes a first partition attempt counted (rounded up to even: 16-byte aligned regions), one CTA
 __global__ void __launch_bounds__(1024)
@@ -95,6 +101,33 @@ mb_region_scan_kernel(const u32 *__restrict__ cursor, u64 n_regions, u64 *__rest
         u64 total;
         const u64 ex = block_excl_sum<u64>(v, ws, &total);
         if (i < n_regions) roff[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) roff[n_regions] = carry;
+}
+
+// the same, four regions per thread and round (a team member packs ~10^5 regions per group: 32 rounds instead of 128)
+__global__ void __launch_bounds__(1024)
+mb_region_scan4_kernel(const u32 *__restrict__ cursor, u64 n_regions, u64 *__restrict__ roff)
+{
+    __shared__ u64 ws[33];
+    __shared__ u64 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (u64 base = 0; base < n_regions; base += 4096) {
+        const u64 i0 = base + 4ull * threadIdx.x;
+        u64 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = i0 + j < n_regions ? (((u64)cursor[i0 + j] + 1ull) & ~1ull) : 0ull;
+        u64 total;
+        u64 ex = carry + block_excl_sum<u64>(v[0] + v[1] + v[2] + v[3], ws, &total);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (i0 + j < n_regions) roff[i0 + j] = ex;
+            ex += v[j];
+        }
         __syncthreads();
         if (threadIdx.x == 0) carry += total;
         __syncthreads();
@@ -119,14 +152,13 @@ mb_region_max_kernel(const u32 *__restrict__ cursor, u64 n_regions, u64 *__restr
 // ---- pass P -----------------------------------------------------------------------------------------------------------------
 // Record layout (KW + 1 words of 64 bits, KW = 2 for k <= 32): word 0 = genome << 48 | windows << 40; words 1..KW = the record's
 // k - 1 + windows <= 32 * KW symbols from its first window start, MSB first, zero behind them (window e's k-mer = bits [2e, 2e + 2k)).
-// SHARD (a group sharded over the members of a team, team.cu): this member holds a slice of the group's genomes, all of them in chunks no
-// other member has, so the cursors of its regions are LOCAL (no remote atomics); the records go straight into the buffer of the bin's
-// owner (owner = bin / sh.bpo: peer memory over NVLink, or this GPU's own buffer) at the place the owner's counting pass expects them.
-template <int KW, bool SHARD>
+// gid_base: added to the genome ids written into the records (a team member's slice of a sharded group starts at id 64 * chunk_base;
+// team.cu) -- the regions are still indexed by the slice's own chunks.
+template <int KW>
 __global__ void __launch_bounds__(MB_BLOCK)
 mb_partition_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid, u64 n_sym, u64 last_cw, u64 last_vw, int k, int m, u32 nbins,
                     const u64 *__restrict__ seg_off, int nseg, u32 nchunks, u32 *__restrict__ cursor, u64 *__restrict__ rec, u32 cap, u32 capw,
-                    const u64 *__restrict__ roff, u64 *__restrict__ flags, mb_shard sh)
+                    const u64 *__restrict__ roff, u64 *__restrict__ flags, u32 gid_base)
 {
     constexpr int CW = MB_TILE / 32 + KW + 2;     // 64-bit code words staged per tile
     constexpr int VW = MB_TILE / 32 + 4;
@@ -253,23 +285,15 @@ mb_partition_kernel(const u64 *__restrict__ codes, const u32 *__restrict__ valid
         const u32 len = (r + 1 < nbnd ? (u32)blist[wrp][r + 1] : wnext[wrp]) - j;
         const u64 i0 = tile0 + j;
         const u64 g = i0 < g_first_end ? g_first : segs_shared ? mb_segment_of_shared(sseg, nseg, i0) : mb_segment_of(seg_off, nseg, i0);
-        const u32 bin = mb_bin_of(mh, nbins);
-        const u32 region = bin * nchunks + (u32)(g >> 6);   // one region per bin and chunk of 64 genomes
+        const u32 region = mb_bin_of(mh, nbins) * nchunks + (u32)(g >> 6);   // one region per bin and chunk of 64 genomes
         const u32 pieces = len <= capw ? 1u : (len + capw - 1) / capw;
         const u32 at = atomicAdd(&cursor[region], pieces);
-        if (at + pieces > (SHARD ? cap : mb_region_cap(roff, region, cap))) {   // the region is full: the caller partitions again with the sizes counted here
+        if (at + pieces > mb_region_cap(roff, region, cap)) {   // the region is full: the caller partitions again with the sizes counted here
             *flags = 1ull;
             continue;
         }
-        u64 *dst;
-        u64 gid = g;
-        if (SHARD) {
-            const u32 owner = bin / sh.bpo, lb = bin - owner * sh.bpo;
-            dst = sh.rec[owner] + (((u64)lb * sh.nchunks_total + sh.chunk_base + (u32)(g >> 6)) * cap + at) * (KW + 1);
-            gid = g + 64ull * sh.chunk_base;             // the genome's id inside the whole group
-        } else {
-            dst = rec + (mb_region_base(roff, region, cap) + at) * (KW + 1);
-        }
+        u64 *dst = rec + (mb_region_base(roff, region, cap) + at) * (KW + 1);
+        const u64 gid = g + gid_base;
         for (u32 s0 = 0; s0 < len; s0 += capw) {
             const u32 pl = len - s0 < capw ? len - s0 : capw;
             const u32 rel = j + s0, t = rel >> 4, s = (rel & 15u) * 2u;
@@ -1211,7 +1235,7 @@ struct mb_plan {
     mc_geom geo;
     u64 n_regions;
     size_t rec_bytes;
-    double rho_w;
+    double rho_w, est_records;
 };
 static int mb_make_plan(khb_ctx *ctx, const mb_plan_in &in, mb_plan *out)
 {
@@ -1284,6 +1308,7 @@ static int mb_make_plan(khb_ctx *ctx, const mb_plan_in &in, mb_plan *out)
     out->n_regions = n_regions;
     out->rec_bytes = (size_t)n_regions * cap * (KW + 1) * 8;
     out->rho_w = rho_w;
+    out->est_records = est_records;
     return KHB_OK;
 }
 
@@ -1401,14 +1426,12 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
     {
         const u64 tiles = div_up(n_sym, MB_TILE);
         khb_prof_begin(ctx, KHB_K_BIN_PARTITION);
-        mb_shard nosh;
-        memset(&nosh, 0, sizeof(nosh));
         if (KW == 2)
-            mb_partition_kernel<2, false><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, m, nb, d_seg_off, n_genomes, geo.nchunks,
-                                                                                         d_cur, (u64 *)pr, cap, capw, roff, d_stat, nosh);
+            mb_partition_kernel<2><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, m, nb, d_seg_off, n_genomes, geo.nchunks,
+                                                                                  d_cur, (u64 *)pr, cap, capw, roff, d_stat, 0u);
         else
-            mb_partition_kernel<3, false><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, m, nb, d_seg_off, n_genomes, geo.nchunks,
-                                                                                         d_cur, (u64 *)pr, cap, capw, roff, d_stat, nosh);
+            mb_partition_kernel<3><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, m, nb, d_seg_off, n_genomes, geo.nchunks,
+                                                                                  d_cur, (u64 *)pr, cap, capw, roff, d_stat, 0u);
         khb_prof_end(ctx, KHB_K_BIN_PARTITION, n_sym * 3 / 8);
         KHB_LAUNCH_CHECK(ctx);
     }
@@ -1433,17 +1456,27 @@ int khb_bins_count_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_valid, u6
 // records, then the table of region sizes.
 struct mb_team_layout {
     u32 bpo;              // bins per owner
-    size_t rec_bytes;     // records of one receive buffer
-    size_t cur_off;       // offset of the region sizes inside it
+    u64 n_regions;        // regions of one owner: bpo x chunks of the whole group
+    u64 area;             // records ONE sender may pack into one owner's buffer (even)
+    size_t roff_off;      // offset of the region starts (u64 per region, in records) inside a receive buffer
+    size_t cur_off;       // ... of the region sizes (u32 per region)
     size_t need;          // bytes one receive buffer must hold
 };
-static mb_team_layout mb_team_layout_of(const mb_plan &pl, int team)
+// A receive buffer: `team` sender areas of `area` records each, packed densely by their senders (a region = one contiguous run, rounded up to an
+// even number of records), then the table of region starts and the table of region sizes.  Dense on purpose: the first version kept the
+// slack layout of the local partition (region u at u * cap, ~20 % filled) and reached ~200 GB/s over NVLink; the senders' stores want
+// consecutive lines of consecutive pages.
+static mb_team_layout mb_team_layout_of(const mb_plan &pl, int team, u32 area_pct)
 {
     mb_team_layout L;
     L.bpo = (u32)div_up((size_t)pl.nb, (size_t)team);
-    L.rec_bytes = (size_t)L.bpo * pl.geo.nchunks * pl.cap * (pl.KW + 1) * 8;
-    L.cur_off = (L.rec_bytes + 255) & ~(size_t)255;
-    L.need = L.cur_off + (((size_t)L.bpo * pl.geo.nchunks * 4 + 255) & ~(size_t)255);
+    L.n_regions = (u64)L.bpo * pl.geo.nchunks;
+    const double pct = area_pct ? (double)area_pct : 250.0;     // above the mean share of a (sender, owner) pair: uneven slices, uneven bins
+    L.area = ((u64)(pl.est_records / (double)team / (double)team * pct / 100.0) + 2 * L.n_regions + 1024) & ~1ull;
+    const size_t rec_bytes = (size_t)L.area * team * (pl.KW + 1) * 8;
+    L.roff_off = (rec_bytes + 255) & ~(size_t)255;
+    L.cur_off = L.roff_off + ((L.n_regions * 8 + 255) & ~(size_t)255);
+    L.need = L.cur_off + ((L.n_regions * 4 + 255) & ~(size_t)255);
     return L;
 }
 static int mb_team_plan(khb_ctx *ctx, int k, const khb_team_group *tg, u32 nbins_hist, mb_plan *pl)
@@ -1475,23 +1508,58 @@ int khb_bins_team_plan_impl(khb_ctx *ctx, int k, const khb_team_group *tg, u32 n
     mb_plan pl;
     int rc = mb_team_plan(ctx, k, tg, nbins_hist, &pl);
     if (rc) return rc;
-    const mb_team_layout L = mb_team_layout_of(pl, tm->size);
+    const mb_team_layout L = mb_team_layout_of(pl, tm->size, tg->area_pct);
     if (nb) *nb = pl.nb;
     if (cap) *cap = pl.cap;
     if (half_bytes) *half_bytes = L.need;
     return KHB_OK;
 }
 
-// the sizes of this member's regions -> the owners' tables (the owner's counting pass reads them like the cursors of a local partition)
+// Every region of this member's partition -> the record buffer of the bin's owner, packed densely into this sender's area there, followed by
+// its start and its size (the owner's counting pass reads them like the exact layout of a local partition).  loff: exclusive prefix sums of
+// this member's region sizes rounded up to even (mb_region_scan_kernel); the regions of one owner are a contiguous index range, so a region's
+// place inside the area is its prefix minus the prefix of the owner's first region.  One warp per region; a region is one contiguous run of
+// a few KB moved as full 16-byte vectors, 512 bytes per warp instruction (records stored one by one from the partition pass itself -- the
+// first version: 32 scattered bytes per thread -- crossed NVLink at 4 GB/s).
 __global__ void __launch_bounds__(256)
-mb_cursor_push_kernel(const u32 *__restrict__ lcur, u32 nb, u32 nchunks_mine, mb_shard sh)
+mb_region_push_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ lcur, const u64 *__restrict__ loff, u32 nb, u32 nchunks_mine, u32 cap, u32 rec_words,
+                      mb_shard sh, u64 *__restrict__ info)
 {
+    const u32 lane = threadIdx.x & 31u;
     const u64 n = (u64)nb * nchunks_mine;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const u64 warps = ((u64)gridDim.x * blockDim.x) >> 5;
+    u64 moved = 0;
+    for (u64 i = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
         const u32 bin = (u32)(i / nchunks_mine), lc = (u32)(i - (u64)bin * nchunks_mine);
         const u32 owner = bin / sh.bpo, lb = bin - owner * sh.bpo;
-        sh.cur[owner][(size_t)lb * sh.nchunks_total + sh.chunk_base + lc] = lcur[i];
+        const u64 dst_region = (u64)lb * sh.nchunks_total + sh.chunk_base + lc;
+        const u32 asked = __ldg(lcur + i);
+        u32 c = asked < cap ? asked : cap;
+        const u64 at = __ldg(loff + i) - __ldg(loff + (u64)owner * sh.bpo * nchunks_mine);     // inside this sender's area of the owner's buffer
+        if (at + ((c + 1u) & ~1u) > sh.area) {     // the area is full: the team repeats the group with larger buffers
+            if (lane == 0) atomicOr((unsigned long long *)info, 2ull);
+            c = 0;
+        }
+        const u64 dst_at = (u64)sh.member * sh.area + (c ? at : 0ull);
+        if (lane == 0) {
+            sh.roff[owner][dst_region] = dst_at;
+            sh.cur[owner][dst_region] = c;
+        }
+        moved += c;
+        const uint4 *src = (const uint4 *)(rec + i * cap * rec_words);               // cap is even: every region starts 16-byte aligned
+        uint4 *dst = (uint4 *)(sh.rec[owner] + dst_at * rec_words);                  // so does every packed region (even sizes)
+        const u32 nv = (c * rec_words * 8u + 15u) >> 4;                              // an odd count of 24-byte records: 8 bytes of slack ride along
+        u32 v = lane;
+        for (; v + 96 < nv; v += 128) {
+            const uint4 a = src[v], b = src[v + 32], d = src[v + 64], e = src[v + 96];
+            dst[v] = a;
+            dst[v + 32] = b;
+            dst[v + 64] = d;
+            dst[v + 96] = e;
+        }
+        for (; v < nv; v += 32) dst[v] = src[v];
     }
+    if (lane == 0 && moved) atomicAdd((unsigned long long *)(info + 1), (unsigned long long)moved);   // records of this member's slice
 }
 
 // Pass P of this member's slice (n_genomes genomes, n_sym symbols) of a sharded group.  d_info: u64[4] device, [0] flags (1: one of this
@@ -1507,7 +1575,7 @@ int khb_bins_team_partition_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_
     const u32 nchunks_mine = (u32)div_up((size_t)n_genomes, 64);
     if (n_genomes < 1 || (u32)tg->chunk_base + nchunks_mine > (u32)tg->n_chunks_total)
         return khb_fail(ctx, KHB_ERR_ARG, "khb_team_partition: %d genomes from chunk %d do not fit the group's %d chunks", n_genomes, tg->chunk_base, tg->n_chunks_total);
-    const mb_team_layout L = mb_team_layout_of(pl, tm->size);
+    const mb_team_layout L = mb_team_layout_of(pl, tm->size, tg->area_pct);
     if (L.need > tm->half_bytes)
         return khb_fail(ctx, KHB_ERR_CAPACITY, "khb_team_partition: the group needs %zu bytes per receive buffer, the team allocated %zu", L.need, tm->half_bytes);
     mb_shard sh;
@@ -1516,30 +1584,42 @@ int khb_bins_team_partition_impl(khb_ctx *ctx, const u64 *d_codes, const u32 *d_
     sh.bpo = L.bpo;
     sh.nchunks_total = pl.geo.nchunks;
     sh.chunk_base = (u32)tg->chunk_base;
+    sh.member = (u32)tm->member;
+    sh.area = L.area;
     for (int t = 0; t < tm->size; t++) {
         char *half = (char *)tm->peer_base[t] + (size_t)tg->parity * tm->half_bytes;
         sh.rec[t] = (u64 *)half;
+        sh.roff[t] = (u64 *)(half + L.roff_off);
         sh.cur[t] = (u32 *)(half + L.cur_off);
     }
-    void *p;
+    void *p, *pr;
     const u64 n_local = (u64)pl.nb * nchunks_mine;
-    if ((rc = khb_scratch_get(ctx, SCR_TEAM, n_local * 4 + 64, &p))) return rc;
-    u32 *d_lcur = (u32 *)p;
+    const u32 RW = (u32)pl.KW + 1u;
+    if ((rc = khb_scratch_get(ctx, SCR_TEAM, n_local * 12 + 256, &p))) return rc;
+    if ((rc = khb_scratch_get(ctx, SCR_KEYS_A, (size_t)n_local * pl.cap * RW * 8 + 64, &pr))) return rc;
+    u64 *d_loff = (u64 *)p;                       // [n_local + 1] prefix sums of the region sizes
+    u32 *d_lcur = (u32 *)(d_loff + n_local + 2);
     KHB_CUDA(ctx, cudaMemsetAsync(d_lcur, 0, n_local * 4, ctx->stream));
     KHB_CUDA(ctx, cudaMemsetAsync(d_info, 0, 4 * sizeof(u64), ctx->stream));
     if (n_sym) {
-        const u64 tiles = div_up(n_sym, MB_TILE), last_w = n_sym / 32 + 3;
         khb_prof_begin(ctx, KHB_K_BIN_PARTITION);
+        // the slice is partitioned into LOCAL regions (bin, own chunk), the genome ids already those of the whole group
+        const u64 tiles = div_up(n_sym, MB_TILE), last_w = n_sym / 32 + 3;
         if (pl.KW == 2)
-            mb_partition_kernel<2, true><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, pl.m, pl.nb, d_seg_off, n_genomes, nchunks_mine,
-                                                                                        d_lcur, nullptr, pl.cap, pl.capw, nullptr, d_info, sh);
+            mb_partition_kernel<2><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, pl.m, pl.nb, d_seg_off, n_genomes, nchunks_mine,
+                                                                                  d_lcur, (u64 *)pr, pl.cap, pl.capw, nullptr, d_info, 64u * (u32)tg->chunk_base);
         else
-            mb_partition_kernel<3, true><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, pl.m, pl.nb, d_seg_off, n_genomes, nchunks_mine,
-                                                                                        d_lcur, nullptr, pl.cap, pl.capw, nullptr, d_info, sh);
+            mb_partition_kernel<3><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>(d_codes, d_valid, n_sym, last_w, last_w, k, pl.m, pl.nb, d_seg_off, n_genomes, nchunks_mine,
+                                                                                  d_lcur, (u64 *)pr, pl.cap, pl.capw, nullptr, d_info, 64u * (u32)tg->chunk_base);
         khb_prof_end(ctx, KHB_K_BIN_PARTITION, n_sym * 3 / 8);
         KHB_LAUNCH_CHECK(ctx);
     }
-    mb_cursor_push_kernel<<<(unsigned)(div_up(n_local, 256) < 1184 ? div_up(n_local, 256) : 1184), 256, 0, ctx->stream>>>(d_lcur, pl.nb, nchunks_mine, sh);
+    // ... and every region leaves for its owner as one run, packed (d_info[0] & 2: an area was too small, d_info[1]: records moved)
+    khb_prof_begin(ctx, KHB_K_PARTITION);
+    mb_region_scan4_kernel<<<1, 1024, 0, ctx->stream>>>(d_lcur, n_local, d_loff);
+    KHB_LAUNCH_CHECK(ctx);
+    mb_region_push_kernel<<<(unsigned)ctx->num_sms * 8u, 256, 0, ctx->stream>>>((const u64 *)pr, d_lcur, d_loff, pl.nb, nchunks_mine, pl.cap, RW, sh, d_info);
+    khb_prof_end(ctx, KHB_K_PARTITION, 0);
     KHB_LAUNCH_CHECK(ctx);
     mb_region_max_kernel<<<(unsigned)ctx->num_sms * 4u, 256, 0, ctx->stream>>>(d_lcur, n_local, d_info + 3);
     KHB_LAUNCH_CHECK(ctx);
@@ -1559,7 +1639,7 @@ int khb_bins_team_count_impl(khb_ctx *ctx, int k, const khb_team_group *tg, u32 
     mb_plan pl;
     int rc = mb_team_plan(ctx, k, tg, nbins_hist, &pl);
     if (rc) return rc;
-    const mb_team_layout L = mb_team_layout_of(pl, tm->size);
+    const mb_team_layout L = mb_team_layout_of(pl, tm->size, tg->area_pct);
     if (L.need > tm->half_bytes) return khb_fail(ctx, KHB_ERR_CAPACITY, "khb_team_count: the group needs %zu bytes per receive buffer, the team allocated %zu", L.need, tm->half_bytes);
     const u64 first = (u64)tm->member * L.bpo;
     const u32 nb_mine = first >= pl.nb ? 0u : (pl.nb - first < L.bpo ? (u32)(pl.nb - first) : L.bpo);
@@ -1578,8 +1658,9 @@ int khb_bins_team_count_impl(khb_ctx *ctx, int k, const khb_team_group *tg, u32 
     evlog.count = nullptr;
     evlog.cap = 0;
     evlog.store_base = 0;
+    pl.cap = MB_CAP_DENSE;      // the regions lie where their senders packed them: exact starts, exact sizes
     return mb_launch_count(ctx, pl, k, (const u64 *)half, (const u32 *)(half + L.cur_off), nb_mine, (u32)tg->n_genomes_total, cs, d_hist, d_out_keys, d_runs, d_pairs,
-                           d_over_list, d_over_count, d_stat, nullptr, evlog, route, tg->n_sym_total);
+                           d_over_list, d_over_count, d_stat, (const u64 *)(half + L.roff_off), evlog, route, tg->n_sym_total);
 }
 
 // ---- the across-group stage, bin by bin -------------------------------------------------------------------------------------------
@@ -1951,14 +2032,12 @@ extern "C" KHB_API int khb_bins_partition(khb_ctx *ctx, const uint64_t *d_codes,
     KHB_CUDA(ctx, cudaMemsetAsync(p, 0, n_regions * 8 + 64, ctx->stream));
     if (n_symbols) {
         const u64 tiles = div_up(n_symbols, MB_TILE), last_w = n_symbols / 32 + 3;
-        mb_shard nosh;
-        memset(&nosh, 0, sizeof(nosh));
         if (KW == 2)
-            mb_partition_kernel<2, false><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>((const u64 *)d_codes, d_valid, n_symbols, last_w, last_w, k, m, n_bins, (const u64 *)d_seg_off,
-                                                                                         n_genomes, nchunks, d_cur, (u64 *)pr, cap, capw, nullptr, d_flag, nosh);
+            mb_partition_kernel<2><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>((const u64 *)d_codes, d_valid, n_symbols, last_w, last_w, k, m, n_bins, (const u64 *)d_seg_off,
+                                                                                  n_genomes, nchunks, d_cur, (u64 *)pr, cap, capw, nullptr, d_flag, 0u);
         else
-            mb_partition_kernel<3, false><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>((const u64 *)d_codes, d_valid, n_symbols, last_w, last_w, k, m, n_bins, (const u64 *)d_seg_off,
-                                                                                         n_genomes, nchunks, d_cur, (u64 *)pr, cap, capw, nullptr, d_flag, nosh);
+            mb_partition_kernel<3><<<(unsigned)tiles, MB_BLOCK, 0, ctx->stream>>>((const u64 *)d_codes, d_valid, n_symbols, last_w, last_w, k, m, n_bins, (const u64 *)d_seg_off,
+                                                                                  n_genomes, nchunks, d_cur, (u64 *)pr, cap, capw, nullptr, d_flag, 0u);
         KHB_LAUNCH_CHECK(ctx);
         mb_region_windows_kernel<<<(unsigned)div_up(n_regions, 256), 256, 0, ctx->stream>>>((const u64 *)pr, d_cur, n_regions, cap, KW + 1, d_win);
         KHB_LAUNCH_CHECK(ctx);

@@ -236,8 +236,11 @@ struct mb_shard {
     u32 bpo;             // bins per owner
     u32 nchunks_total;   // chunks of 64 genome ids of the whole group
     u32 chunk_base;      // first chunk of this member's slice (its genome ids start at 64 * chunk_base)
-    u64 *rec[KHB_TEAM_MAX];
-    u32 *cur[KHB_TEAM_MAX];
+    u32 member;          // this member: it packs its regions into area `member` of every owner's buffer
+    u64 area;            // records one sender's area holds
+    u64 *rec[KHB_TEAM_MAX];   // every member's record buffer (own entry included) ...
+    u64 *roff[KHB_TEAM_MAX];  // ... its table of region starts (in records)
+    u32 *cur[KHB_TEAM_MAX];   // ... and of region sizes
 };
 struct khb_team {
     int size = 0, member = 0;

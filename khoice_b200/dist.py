@@ -332,21 +332,27 @@ class TeamSharder:
         shape = (int(k), int(n_genomes_total), int(n_chunks))
         hint = self.hints.get(shape, {})
         tg = TeamGroup(n_genomes_total, n_chunks, base[self.member], self.parity, int(n_sym_total), float(hint.get("rho", 0.0)),
-                       int(hint.get("cap", 0)), 0)
+                       int(hint.get("cap", 0)), int(hint.get("area_pct", 0)))
         self._fit(k, tg)
-        for attempt in range(6):
+        for attempt in range(8):
             info = self.eng.team_partition(source, k, tg)
-            row = torch.tensor([1 if info["overflow"] else 0, info["fullest_region"], self.prev[0], self.prev[1]], dtype=torch.int64, device=self.ctrl)
+            flags = (1 if info["overflow"] else 0) | (2 if info.get("area_overflow") else 0)
+            row = torch.tensor([flags, info["fullest_region"], self.prev[0], self.prev[1]], dtype=torch.int64, device=self.ctrl)
             table = torch.empty((self.T, 4), dtype=torch.int64, device=self.ctrl)
             dist.all_gather_into_tensor(table.view(-1), row, group=self.group)     # also the barrier: every member's records are at their owners
             table = table.cpu().numpy()
             fullest = int(table[:, 1].max())
-            if not table[:, 0].any():
+            flags = int(np.bitwise_or.reduce(table[:, 0]))
+            if not flags:
                 break
-            # a region overflowed somewhere: every member partitions again into larger regions (the fullest region seen so far is a lower
-            # bound only -- senders stop counting exactly where they overflow -- hence the factor)
+            # something was too small somewhere: every member partitions again -- into larger local regions (the senders count what was
+            # asked for, so the fullest region is known exactly) and / or into larger areas of the owners' buffers
             self.retries += 1
-            tg.region_cap = max(2 * fullest, 2 * int(self.eng.team_plan(k, tg)["region_cap"])) + 64
+            if flags & 1:
+                tg.region_cap = max(fullest + fullest // 4, 2 * int(self.eng.team_plan(k, tg)["region_cap"])) + 64
+            if flags & 2:
+                tg.area_pct = 2 * (int(tg.area_pct) or 250)
+                hint = dict(hint, area_pct=int(tg.area_pct))
             self._fit(k, tg)
         else:
             raise RuntimeError(f"team: the regions of a k={k} group of {n_genomes_total} genomes still overflow at {tg.region_cap} records")

@@ -49,7 +49,7 @@ class Stats(C.Structure):
 class TeamGroup(C.Structure):
     """Mirror of ``khb_team_group``: one group as the members of a team see it (the same values on every member but chunk_base)."""
     _fields_ = [("n_genomes_total", C.c_int32), ("n_chunks_total", C.c_int32), ("chunk_base", C.c_int32), ("parity", C.c_int32),
-                ("n_sym_total", C.c_uint64), ("rho", C.c_double), ("region_cap", C.c_uint32), ("reserved", C.c_uint32)]
+                ("n_sym_total", C.c_uint64), ("rho", C.c_double), ("region_cap", C.c_uint32), ("area_pct", C.c_uint32)]
 
 
 # every symbol include/khoice_b200.h declares: (name, restype, argtypes)
@@ -358,7 +358,8 @@ class Engine:
         else:
             arrs, ptrs, sizes = self._file_tables(source)
             self._chk(self.lib.khb_team_partition_fasta(self.ctx, k, len(arrs), ptrs, sizes, C.byref(tg), info.ctypes.data))
-        return {"overflow": bool(info[0]), "fullest_region": int(info[1]), "windows": int(info[2]), "bases": int(info[3])}
+        return {"overflow": bool(int(info[0]) & 1), "area_overflow": bool(int(info[0]) & 2), "fullest_region": int(info[1]), "windows": int(info[2]),
+                "bases": int(info[3])}
 
     def team_count(self, k: int, tg: TeamGroup, nbins: int = COUNTER_MAX, keep_set: bool = True):
         """Passes C and B over the bins this member owns: (partial step_4 histogram, stats)."""

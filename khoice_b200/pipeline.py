@@ -152,13 +152,18 @@ def run_fused(work_root: str, num_datasets: int, k_values: Optional[Sequence] = 
 
 # ---- fused mode on several GPUs ------------------------------------------------------------------------
 def run_fused_distributed(work_root: str, num_datasets: int, k_values: Optional[Sequence] = None, adapter=None, exchange: str = "peer",
-                          stubs: bool = True, report_path: Optional[str] = None) -> Dict:
+                          stubs: bool = True, report_path: Optional[str] = None, team: int = 0) -> Dict:
     """``run_fused`` under ``torchrun`` (one process per GPU, ``torch.distributed`` already initialised or initialisable from
     the environment): groups are dealt to the ranks round-robin (khoice_b200/dist.py), every rank inflates and packs only
     its own groups once and sweeps k over them; per k the across-group stage goes through ``dist.AcrossExchanger`` (peer-
     memory push, or ``exchange="nccl"``), the per-group histograms are all-reduced, and rank 0 writes the step_4 / step_8
     files, the stubs and the step_5 / step_9 CSVs -- byte-identical to a single-GPU run.  ``adapter``: tests pass a
-    stand-in; the product adapter is dist.CudaAdapter on this rank's GPU."""
+    stand-in; the product adapter is dist.CudaAdapter on this rank's GPU.
+
+    ``team``: GPUs per group.  1 = whole groups dealt to ranks; T > 1 = the ranks form world / T teams, the groups are dealt to the teams
+    and every group is sharded inside its team (dist.TeamSharder: genomes over members, minimizer bins over owners) -- for work roots
+    with fewer, or unevenly many, groups than GPUs; 0 = the smallest T that deals the groups evenly (dist.team_shape), provided every
+    k of the sweep can take the minimizer-bin path (17 <= k <= 63, k != 32) and every group has at least T genomes."""
     import torch
     import torch.distributed as tdist
     from . import dist as kd
@@ -173,7 +178,24 @@ def run_fused_distributed(work_root: str, num_datasets: int, k_values: Optional[
         adapter = kd.CudaAdapter(own_eng, torch.device("cuda", local))
     report = {"mode": "fused-distributed", "world": world, "work_root": work_root, "num_datasets": num_datasets, "k_values": k_values, "stages": []}
     t_start = time.time()
-    mine = kd.groups_of_rank(num_datasets, rank, world)
+    names = {n: genomes_of(work_root, n) for n in range(1, num_datasets + 1)}
+    shardable = all(17 <= int(k) <= 63 and int(k) != 32 for k in k_values) and hasattr(getattr(adapter, "eng", None), "team_alloc")
+    T = int(team) if team else kd.team_shape(num_datasets, world)
+    if T > 1 and not (shardable and world % T == 0 and T <= 8 and min(len(v) for v in names.values()) >= T):
+        if team:
+            raise ValueError(f"team={T}: needs a divisor of the {world} ranks (<= 8), groups of at least {T} genomes and 17 <= k <= 63, k != 32")
+        T = 1
+    n_teams, team_idx, member = world // T, rank // T, rank % T
+    mine = kd.groups_of_rank(num_datasets, team_idx, n_teams)
+    report["team_size"] = T
+    ts, team_pg, group_syms = None, None, {}
+    if T > 1:
+        for t in range(n_teams):                # every rank creates every team's process group, in the same order
+            pg = tdist.new_group(ranks=list(range(t * T, (t + 1) * T)))
+            if t == team_idx:
+                team_pg = pg
+        ts = kd.TeamSharder(adapter.eng, T, member, group=team_pg)
+    slices = {n: kd.genome_slices(len(names[n]), T) for n in names}
     packed: Dict[int, object] = {}
     ex = None             # ONE exchanger at a time: a khb_ctx holds one peer exchange (one set of mapped regions, one key width)
     reader = None
@@ -181,10 +203,11 @@ def run_fused_distributed(work_root: str, num_datasets: int, k_values: Optional[
     try:
         if rank == 0:
             write_complex_ops(work_root, k_values, num_datasets)
-        names = {n: genomes_of(work_root, n) for n in range(1, num_datasets + 1)}
         zero = np.zeros(tables.HIST_ROWS + 1, dtype=np.uint64)
         if mine:
-            reader = ingest.GroupReader({n: [os.path.join(work_root, p_genome(n, g)) for g in names[n]] for n in mine}, mine)
+            # a rank reads (inflates, packs) only what it holds: its groups, or its slice of its team's groups
+            reader = ingest.GroupReader({n: [os.path.join(work_root, p_genome(n, g)) for g in names[n][slices[n][member][0]:slices[n][member][1]]]
+                                         for n in mine}, mine)
         for k in k_values:
             ki = int(k)
             if ex is not None and kd.key_words(ki) != kd.key_words(ex.k):
@@ -199,7 +222,15 @@ def run_fused_distributed(work_root: str, num_datasets: int, k_values: Optional[
             for num in mine:
                 if num not in packed:
                     packed[num] = adapter.pack_group(reader.get(num))
-                hist, st = adapter.group_from_packed(packed[num], ki, tables.HIST_ROWS)
+                    if ts:      # symbols of the whole group: the same number on every member (sizes the team's bins and tables)
+                        nsym = torch.tensor([int(packed[num].info()["n_symbols"])], dtype=torch.int64, device=ctrl)
+                        tdist.all_reduce(nsym, group=team_pg)
+                        group_syms[num] = int(nsym.item())
+                if ts:
+                    # this member's rows: the k-mers of the bins it owns; the all-reduce below adds the members' rows up
+                    hist, st = ts.run_group(packed[num], ki, len(names[num]), [hi - lo for lo, hi in slices[num]], group_syms[num], nbins=tables.HIST_ROWS)
+                else:
+                    hist, st = adapter.group_from_packed(packed[num], ki, tables.HIST_ROWS)
                 ex.after_group()
                 within[num - 1, :-1] = hist.astype(np.int64)
                 within[num - 1, -1] = int(st["distinct"])
@@ -233,6 +264,8 @@ def run_fused_distributed(work_root: str, num_datasets: int, k_values: Optional[
             build_tables(work_root, k_values, num_datasets)
         if ex is not None:
             ex.close()
+        if ts is not None:
+            ts.close()
         tdist.barrier()
     finally:
         if reader is not None:
@@ -348,13 +381,14 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap.add_argument("--mode", choices=["fused", "fused-dist", "rules", "rules-subprocess"], default="fused",
                     help="fused-dist: under `torchrun --nproc-per-node N`, one rank per GPU")
     ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer", help="fused-dist: across-group exchange route")
+    ap.add_argument("--team", type=int, default=0, help="fused-dist: GPUs per group (1: whole groups; 0: the smallest team size that deals the groups evenly)")
     ap.add_argument("--report", default=None)
     a = ap.parse_args(argv)
     ks = a.k_values.split(",") if a.k_values else None
     if a.mode == "fused":
         rep = run_fused(a.work_root, a.num_datasets, ks, report_path=a.report)
     elif a.mode == "fused-dist":
-        rep = run_fused_distributed(a.work_root, a.num_datasets, ks, exchange=a.exchange, report_path=a.report)
+        rep = run_fused_distributed(a.work_root, a.num_datasets, ks, exchange=a.exchange, report_path=a.report, team=a.team)
         if int(os.environ.get("RANK", "0")) != 0:
             return 0
     else:

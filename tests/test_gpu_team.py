@@ -79,6 +79,14 @@ def tiny_regions(ts, k, N, sizes):
     ts.hints[(k, N, kd.chunk_layout(sizes)[1])] = {"cap": 2}
 run(2, 5, 40_000, (31, 47), seed=14, rounds=1, force=tiny_regions)
 assert ts.retries > r0, (ts.retries, r0)
+# areas of the receive buffers that are too small for a sender's share: every member partitions again, the buffers grow
+r0, s0 = ts.retries, ts.setups
+def small_areas(ts, k, N, sizes):
+    key = (k, N, kd.chunk_layout(sizes)[1])
+    if "area_pct" not in ts.hints.get(key, {}):
+        ts.hints[key] = dict(ts.hints.get(key, {}), area_pct=30)
+run(2, 6, 600_000, (31,), seed=17, rounds=1, force=small_areas)
+assert ts.retries > r0, (ts.retries, r0)
 # tables that are too small for their bins: hash classes and the big-bin pass
 os.environ["KHB_BINS_SLOTS_LOG2"] = "8"
 os.environ["KHB_BINS_RHO_PCT"] = "2"
@@ -123,3 +131,56 @@ def _spawn(world, extra_env=None):
 @pytest.mark.parametrize("world,fuse", [(2, "1"), (2, "0"), (3, "1")])
 def test_members_of_a_team_on_one_gpu(world, fuse):
     _spawn(world, {"KHB_PEER_FUSE": fuse})
+
+
+PIPELINE_SCRIPT = r"""
+import os, sys
+sys.path.insert(0, %(root)r)
+import torch.distributed as dist
+from khoice_b200 import pipeline
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rep = pipeline.run_fused_distributed(%(work)r, %(groups)d, %(ks)r, exchange="peer", team=%(team)d)
+assert rep["team_size"] == 2, rep["team_size"]
+print("pipeline ok", os.environ["RANK"])
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.parametrize("world,team", [(2, 2), (2, 0)])
+def test_work_root_driver_with_a_team_on_one_gpu(engine, tmp_path, world, team):
+    """pipeline.run_fused_distributed(team=2) with the product adapter (two processes on cuda:0, gloo control plane): every group is
+    sharded over the two ranks, and the step_4 / step_8 files and both CSVs equal the single-process run's.  team=0 picks the team
+    size itself: 3 groups on 2 ranks do not deal evenly, so it shards them too."""
+    import filecmp
+    from khoice_b200 import pipeline, synth
+    cfg = synth.SynthConfig(n_groups=3, genomes_per_group=5, genome_len=30_000, seed=78)
+    ks = ["31", "40", "21"]           # the key width changes twice
+    work, ref = str(tmp_path / "dist"), str(tmp_path / "single")
+    synth.write_dataset(cfg, work)
+    synth.write_dataset(cfg, ref)
+    pipeline.run_fused(ref, cfg.n_groups, ks, engine=engine)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = PIPELINE_SCRIPT % {"root": ROOT, "work": work, "groups": cfg.n_groups, "ks": ks, "team": team}
+    procs = [subprocess.Popen([sys.executable, "-c", script], env=dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK="0", MASTER_ADDR="127.0.0.1",
+                                                                     MASTER_PORT=str(port)), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(world)]
+    import time
+    deadline = time.time() + 600
+    while any(p.poll() is None for p in procs):
+        if any(p.poll() not in (None, 0) for p in procs) or time.time() > deadline:
+            time.sleep(2)
+            for q in procs:
+                if q.poll() is None:
+                    q.kill()
+            break
+        time.sleep(0.2)
+    outs = [p.communicate() for p in procs]
+    for r, (p, (out, err)) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"pipeline ok {r}" in out, out[-2000:] + err[-4000:]
+    for k in ks:
+        for num in range(1, cfg.n_groups + 1):
+            assert filecmp.cmp(os.path.join(work, pipeline.p_step4(k, num)), os.path.join(ref, pipeline.p_step4(k, num)), shallow=False), (k, num)
+        assert filecmp.cmp(os.path.join(work, pipeline.p_step8(k)), os.path.join(ref, pipeline.p_step8(k)), shallow=False), k
+    for f in (pipeline.P_STEP5, pipeline.P_STEP9) + pipeline.P_FINAL:
+        assert filecmp.cmp(os.path.join(work, f), os.path.join(ref, f), shallow=False), f

@@ -28,6 +28,7 @@ class FakeTeamEngine:
         self.device = 0
         self.allocs = 0
         self.partition_calls = []
+        self.adapter = None
 
     def team_alloc(self, team_size, member, half_bytes):
         self.T, self.member, self.half = team_size, member, int(half_bytes)
@@ -57,6 +58,7 @@ class FakeTeamEngine:
         return ((h >> np.uint64(33)) % np.uint64(N_BINS)).astype(np.int64)
 
     def team_partition(self, source, k, tg):
+        source = getattr(source, "texts", source)
         plan = self.team_plan(k, tg)
         assert plan["half_bytes"] <= self.half, "the driver must have grown the buffers first"
         cap, bpo = plan["region_cap"], -(-N_BINS // self.T)
@@ -95,6 +97,9 @@ class FakeTeamEngine:
         if not sets:
             return np.zeros(nbins + 1, dtype=np.uint64), {"distinct": 0}
         keys, counts = self.O.union_sum(sets, k)
+        if keep_set and self.adapter is not None:
+            self.adapter.sets.append(keys)             # the distinct k-mers of this member's bins enter its group-set store
+            self.adapter.k = k
         return self.O.histogram(counts, nbins), {"distinct": int(keys.shape[0])}
 
 
@@ -164,3 +169,70 @@ def test_team_shapes():
     assert chunk_layout([50, 50]) == ([0, 1], 2)
     assert chunk_layout([65, 65]) == ([0, 2], 4)
     assert chunk_layout([64, 1, 130]) == ([0, 1, 2], 5)
+
+
+# ---- the work-root driver with teams (pipeline.run_fused_distributed(team=T)) on the stand-in ------------------------------------
+class _Packed:
+    def __init__(self, texts, O):
+        self.texts, self.O = list(texts), O
+
+    def info(self):
+        return {"n_symbols": sum(len(t) for t in self.texts)}
+
+    def free(self):
+        pass
+
+
+def _pipeline_worker(rank, world, port, root, shared, ks, team):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from khoice_b200 import dist as kd, pipeline
+    from test_dist_gloo import OracleAdapter
+    kd.init_from_env("gloo")
+
+    class Adapter(OracleAdapter):
+        def __init__(self, k):
+            super().__init__(k)
+            self.eng = FakeTeamEngine(os.path.join(shared, f"team{rank // max(team, 1)}"), 1 << 20)
+            self.eng.adapter = self
+
+        def pack_group(self, files):
+            return _Packed(files, self.O)
+
+        def group_from_packed(self, packed, k, nbins):
+            self.k = k
+            return self.group(packed.texts, k, nbins)
+
+    os.makedirs(os.path.join(shared, f"team{rank // max(team, 1)}"), exist_ok=True)
+    ad = Adapter(int(ks[0]))
+    rep = pipeline.run_fused_distributed(root, 3, ks, adapter=ad, exchange="nccl", team=team)
+    assert rep["team_size"] == team and rep["world"] == world
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,team", [(2, 2), (4, 2), (3, 3)])
+def test_work_root_driver_with_teams_writes_the_single_process_files(tmp_path, oracle, world, team):
+    """3 groups of 4 genomes: one team of 2, two teams of 2 (groups dealt 2 / 1), one team of 3 -- the step_4 / step_8 histogram files
+    are those of the oracle whatever the sharding."""
+    from khoice_b200 import pipeline, synth, tables
+    cfg = synth.SynthConfig(n_groups=3, genomes_per_group=4, genome_len=7_000, seed=5)
+    root = str(tmp_path / "w")
+    synth.write_dataset(cfg, root)
+    ks = ["21", "35"]
+    shared = str(tmp_path / "shared")
+    os.makedirs(shared)
+    mp.spawn(_pipeline_worker, args=(world, _free_port(), root, shared, ks, team), nprocs=world, join=True)
+    flat, gid = [], []
+    for g in range(1, 4):
+        for i in range(1, 5):
+            flat.append(synth.make_genome(cfg, g, i))
+            gid.append(g - 1)
+    for k in ks:
+        w_ref, a_ref, _ = oracle.exp1(flat, gid, 3, int(k), nbins=tables.HIST_ROWS)
+        for num in range(1, 4):
+            got = tables.read_histogram_file(os.path.join(root, pipeline.p_step4(k, num)))
+            assert got == [int(x) for x in w_ref[num - 1][1:]], (k, num)
+        assert tables.read_histogram_file(os.path.join(root, pipeline.p_step8(k))) == [int(x) for x in a_ref[1:]], k
+    assert os.path.exists(os.path.join(root, pipeline.P_STEP5)) and os.path.exists(os.path.join(root, pipeline.P_STEP9))
