@@ -317,6 +317,10 @@ KHB_API int khb_peer_begin(khb_ctx *ctx);
 KHB_API int khb_peer_push(khb_ctx *ctx);
 KHB_API int khb_peer_counts(khb_ctx *ctx, uint64_t *h_counts /* [world] */, int *overflow);
 KHB_API int khb_peer_import(khb_ctx *ctx, const uint64_t *h_recv_counts /* [world] */, int k, int n_groups, int hashed);
+/* khb_peer_import + khb_across_groups without the copy in between: the pushed regions are sorted where they lie (the first radix pass
+ * gathers them) and counted; h_hist = the step_8 rows of this rank's hash range.  The retained group sets are forgotten. */
+KHB_API int khb_peer_across(khb_ctx *ctx, const uint64_t *h_recv_counts /* [world] */, int k, int n_groups, int hashed, uint32_t nbins,
+                    uint64_t *h_hist, khb_stats *stats);
 KHB_API int khb_peer_unmap(khb_ctx *ctx); /* drop the peers' mappings; barrier between the ranks; then khb_peer_close frees the own buffer */
 KHB_API int khb_peer_close(khb_ctx *ctx);
 KHB_API uint64_t khb_peer_region_keys(const khb_ctx *ctx);

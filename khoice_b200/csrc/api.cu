@@ -21,6 +21,7 @@ int khb_sort_hist_buffer(khb_ctx *, int, u32 **);
 int khb_remix_impl(khb_ctx *, void *, size_t, int, int);
 int khb_sort_keys_impl(khb_ctx *, void *, void *, const u64 *, int, int, int *);
 int khb_sort_bits_impl(khb_ctx *, void *, void *, const u64 *, int, int, int, int, int *, unsigned short *, unsigned short *, int hist_ready = 0);
+int khb_sort_gathered_impl(khb_ctx *, void *, void *, const u64 *, const u64 *, int, int, int, int, int *);
 int khb_resolve_unique_impl(khb_ctx *, const void *, size_t, int, int, void *, u64 *);
 int khb_resolve_count_impl(khb_ctx *, const void *, size_t, int, int, u32, u32, u64 *, void *, u64 *);
 int khb_pairs_count_impl(khb_ctx *, const void *, const unsigned short *, size_t, int, int, u32, u32, u32, u64 *, void *, u64 *, u64 *, int, void *, u64 *);
@@ -847,7 +848,7 @@ static int count_stage(khb_ctx *ctx, int k, const khb_packed &pk, u32 nbins, u64
         bool use_bins = !small_k && !use_hash && hashed && !pivot && (ctx->group_mode == KHB_GROUP_AUTO || ctx->group_mode == KHB_GROUP_BINS) &&
                         khb_bins_eligible(k, n_genomes, n_sym);
         int bins_exact = 0;
-        khb_peer_route bins_route = {0u, 0ull, nullptr, nullptr};
+        khb_peer_route bins_route = {0u, 0u, 0ull, nullptr, nullptr};
         // the store's segment events (across-group stage bin by bin): kept while every retained group comes through the bins
         const bool log_events = use_bins && keep_set && across_by_bins_wanted() && (ctx->gs_len == 0 || ctx->ev_ok);
         u32 bins_nb = 0;
@@ -1308,7 +1309,7 @@ int khb_team_count(khb_ctx *ctx, int k, const khb_team_group *tg, uint32_t nbins
     const size_t W = (size_t)khb_key_bytes(k);
     int rc;
     void *out_keys = nullptr;
-    khb_peer_route route = {0u, 0ull, nullptr, nullptr};
+    khb_peer_route route = {0u, 0u, 0ull, nullptr, nullptr};
     if (keep_set) {
         if (ctx->gs_k && ctx->gs_hashed != 1) return khb_fail(ctx, KHB_ERR_STATE, "retained group sets use a different key encoding");
         if ((rc = gs_reserve(ctx, k, tg->n_sym_total))) return rc;   // this member's bins hold at most every window of the group
@@ -1587,6 +1588,67 @@ int khb_peer_import(khb_ctx *ctx, const uint64_t *h_recv_counts, int k, int n_gr
     }
     ctx->gs_groups = n_groups;
     ctx->ev_ok = 0;
+    return KHB_OK;
+}
+
+// khb_peer_import + khb_across_groups in one call, without the copy in between: the regions the ranks pushed here are sorted where they
+// lie -- the first radix pass reads them piece by piece (radix_sort.cu: gathered input) and writes one contiguous array, the following
+// passes ping-pong between that array and the receive buffer itself -- and the run-length count gives the step_8 histogram of this rank's
+// hash range.  The retained group sets are forgotten (they were pushed).  Same barrier rules as khb_peer_import.
+int khb_peer_across(khb_ctx *ctx, const uint64_t *h_recv_counts, int k, int n_groups, int hashed, uint32_t nbins, uint64_t *h_hist, khb_stats *stats)
+{
+    KHB_CHECK_CTX(ctx);
+    const void *recv;
+    u64 region;
+    int world, kb;
+    int rc = khb_peer_regions(ctx, &recv, &region, &world, &kb);
+    if (rc) return rc;
+    if (!h_recv_counts || !h_hist || k < 1 || k > 64 || khb_key_bytes(k) != kb || nbins < 1 || nbins > 8192)
+        return khb_fail(ctx, KHB_ERR_ARG, "khb_peer_across: bad arguments");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    std::vector<u64> pos((size_t)world), len((size_t)world);
+    u64 n = 0;
+    for (int s = 0; s < world; s++) {
+        if (h_recv_counts[s] > region) return khb_fail(ctx, KHB_ERR_ARG, "khb_peer_across: rank %d reports %llu keys, a region holds %llu", s, (u64)h_recv_counts[s], region);
+        pos[s] = (u64)s * region;
+        len[s] = h_recv_counts[s];
+        n += h_recv_counts[s];
+    }
+    ctx->gs_len = 0;
+    ctx->gs_groups = 0;
+    ctx->gs_k = 0;
+    ctx->ev_ok = 0;
+    const size_t W = (size_t)kb;
+    void *p;
+    if ((rc = khb_scratch_get(ctx, SCR_KEYS_A, (n + 4) * W, &p))) return rc;
+    PhaseTimer tm(ctx);
+    tm.mark();
+    ctx->across_by_sort++;
+    int in_tmp = 0, fb, np;
+    khb_prefix_plan(k, n, &fb, &np);
+    if (!hashed) { fb = 0; np = (2 * k + 7) / 8; }
+    u64 *d_hist = ctx->d_mail + 8, *d_runs = ctx->d_mail;
+    if (n) {
+        if ((rc = khb_sort_gathered_impl(ctx, (void *)recv, p, pos.data(), len.data(), world, (int)W, fb, np, &in_tmp))) return rc;
+        tm.mark();
+        if ((rc = khb_resolve_count_impl(ctx, in_tmp ? p : recv, n, k, fb, KHB_COUNTER_MAX, nbins, d_hist, nullptr, d_runs))) return rc;
+    } else {
+        tm.mark();
+        KHB_CUDA(ctx, cudaMemsetAsync(ctx->d_mail, 0, (nbins + 9) * sizeof(u64), ctx->stream));
+    }
+    KHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, ctx->d_mail, (nbins + 9) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    tm.mark();
+    KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(h_hist, ctx->h_mail + 8, ((size_t)nbins + 1) * sizeof(u64));
+    if (stats) {
+        stats->windows = n;
+        stats->genome_distinct = n;
+        stats->distinct = ctx->h_mail[0];
+        stats->ms_sort2 = tm.ms(0, 1);
+        stats->ms_count = tm.ms(1, 2);
+        stats->ms_total = tm.ms(0, 2);
+        stats->passes_group = np;
+    }
     return KHB_OK;
 }
 

@@ -571,7 +571,7 @@ template <int KW> __device__ __forceinline__ void mb_slot_reset(const mc_smem &s
 }
 // Multi-GPU, first half: the mixed key of slot i goes back into the slot, its owner and its rank among the bin's keys for that owner into
 // the slot's bit word (the bits were counted already); second half (mb_route_store) after the owners' ranges were reserved.
-template <int KW> __device__ __forceinline__ void mb_route_note(const mc_smem &sm, u32 i, int k, u32 world, u32 *s_ocnt)
+template <int KW> __device__ __forceinline__ u32 mb_route_owner(const mc_smem &sm, u32 i, int k, u32 world)
 {
     u32 o;
     if (KW == 3) {
@@ -589,6 +589,11 @@ template <int KW> __device__ __forceinline__ void mb_route_note(const mc_smem &s
         sm.tkey[i] = kk.v;
         o = part_of(kk, world);
     }
+    return o;
+}
+template <int KW> __device__ __forceinline__ void mb_route_note(const mc_smem &sm, u32 i, int k, u32 world, u32 *s_ocnt)
+{
+    const u32 o = mb_route_owner<KW>(sm, i, k, world);
     const u32 r = atomicAdd(&s_ocnt[o], 1u);
     sm.tbits[i] = ((u64)o << 32) | r;
 }
@@ -972,12 +977,15 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
             continue;
         }
         const u32 nd_keys = s_distinct;
-        if (tid == 0 && nd_keys) {
-            s_base = atomicAdd((unsigned long long *)d_cursor, (unsigned long long)nd_keys);
-            if (out_keys) mb_log_event(evlog, d.bin, nd_keys, s_base, d_stat);
+        const bool routed = route.world && out_keys;
+        if (!routed) {      // (routed: the bin's place in the local store is reserved together with its places at the owners, further down)
+            if (tid == 0 && nd_keys) {
+                s_base = atomicAdd((unsigned long long *)d_cursor, (unsigned long long)nd_keys);
+                if (out_keys) mb_log_event(evlog, d.bin, nd_keys, s_base, d_stat);
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        const u64 base = s_base;
+        const u64 base = routed ? 0ull : s_base;
         for (u32 j = tid; j < nd_keys; j += BLOCK) {
             const u32 i = sm.slots[j];
             u32 c = (u32)__popcll(sm.tbits[i]);
@@ -991,7 +999,7 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
             if (cc == 1u) n_one++;
             else if (cc == c_all) n_all++;
             else if (cc <= hrows) atomicAdd(&sm.hist[cc], 1u);
-            if (route.world && out_keys) {
+            if (routed) {
                 mb_route_note<KW>(sm, i, k, route.world, s_ocnt);     // multi-GPU: the key leaves for its owner below
             } else {
                 if (out_keys) mb_emit<KW>(sm, i, out_keys, base + j, k);
@@ -999,19 +1007,31 @@ mb_count_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u32
             }
         }
         __syncthreads();
-        if (route.world && out_keys) {
+        if (routed) {
+            // ONE round trip to L2 per bin for all reservations: the owners' ranges (threads 0 .. world - 1) and the local store's (thread 64).
+            // With the local reservation up front (as in the unrouted case) every bin waited for two dependent atomics: +0.2 ms per config-2 group
+            if (tid == 64 && nd_keys) {
+                s_base = atomicAdd((unsigned long long *)d_cursor, (unsigned long long)nd_keys);
+                mb_log_event(evlog, d.bin, nd_keys, s_base, d_stat);
+            }
             mb_route_reserve(route, s_ocnt, s_obase, s_ostart);
             __syncthreads();
-            for (u32 j = tid; j < nd_keys; j += BLOCK) {          // owner-sorted order of the bin's keys (the window map is free at this point)
-                const u32 i = sm.slots[j];
-                const u64 w = sm.tbits[i];
-                sm.map[s_ostart[(u32)(w >> 32)] + (u32)w] = (unsigned short)i;
+            const u64 lbase = s_base;
+            if (route.flags & 1u) {
+                // KHB_PEER_SORTED=1: the bin's keys in owner-sorted order (the window map is free at this point), so that every owner's keys
+                // leave as one run of consecutive threads.  Off by default: the NVLink side is far from its limit here (~140 GB/s asked of
+                // it) and the extra pass costs instructions (2 B200s: 2.32 against 2.28 ms per group, profiles/r2_bench_history.md)
+                for (u32 j = tid; j < nd_keys; j += BLOCK) {
+                    const u32 i = sm.slots[j];
+                    const u64 w = sm.tbits[i];
+                    sm.map[s_ostart[(u32)(w >> 32)] + (u32)w] = (unsigned short)i;
+                }
+                __syncthreads();
             }
             if (tid < 64) s_ocnt[tid] = 0u;
-            __syncthreads();
             for (u32 j = tid; j < nd_keys; j += BLOCK) {
-                const u32 i = sm.map[j];
-                mb_route_store<KW>(sm, i, route, s_obase, out_keys, base + j);
+                const u32 i = (route.flags & 1u) ? sm.map[j] : sm.slots[j];
+                mb_route_store<KW>(sm, i, route, s_obase, out_keys, lbase + j);
                 mb_slot_reset<KW>(sm, i);
             }
             __syncthreads();
@@ -1174,15 +1194,9 @@ mb_bigbin_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cursor, u3
             if (route.world && out_keys) {
                 mb_route_reserve(route, s_ocnt, s_obase, s_ostart);
                 __syncthreads();
+                if (tid < 64) s_ocnt[tid] = 0u;
                 for (u32 j = tid; j < nd_keys; j += MC_BLOCK) {
                     const u32 i = sm.slots[j];
-                    const u64 w = sm.tbits[i];
-                    sm.map[s_ostart[(u32)(w >> 32)] + (u32)w] = (unsigned short)i;
-                }
-                if (tid < 64) s_ocnt[tid] = 0u;
-                __syncthreads();
-                for (u32 j = tid; j < nd_keys; j += MC_BLOCK) {
-                    const u32 i = sm.map[j];
                     mb_route_store<KW>(sm, i, route, s_obase, out_keys, base + j);
                     mb_slot_reset<KW>(sm, i);
                 }

@@ -269,6 +269,7 @@ int khb_peer_wait(khb_ctx *ctx);  // wait for pushes in flight (before the group
 // filled through the sender-side cursor[owner]; cursor[64] != 0: some region overflowed.  world = 0: no exchange is open.
 struct khb_peer_route {
     u32 world;
+    u32 flags;      // bit 0: store every bin's keys in owner-sorted order (KHB_PEER_SORTED=1)
     u64 cap;
     u64 *cursor;
     void *const *dst;

@@ -298,6 +298,7 @@ uint64_t khb_peer_region_keys(const khb_ctx *ctx) { return ctx && ctx->peer ? ct
 int khb_peer_route_get(khb_ctx *ctx, int key_bytes, khb_peer_route *out)
 {
     out->world = 0;
+    out->flags = 0;
     out->cap = 0;
     out->cursor = nullptr;
     out->dst = nullptr;
@@ -309,7 +310,13 @@ int khb_peer_route_get(khb_ctx *ctx, int key_bytes, khb_peer_route *out)
     }
     if (!fuse || !pp || !pp->opened || pp->key_bytes != key_bytes || pp->push_stream) return KHB_OK;
     if (pp->pushed_upto != ctx->gs_len) return KHB_OK;   // earlier keys of the store are still waiting for khb_peer_push: keep the order simple
+    static int sorted = -1;
+    if (sorted < 0) {
+        const char *e = getenv("KHB_PEER_SORTED");
+        sorted = e ? atoi(e) : 0;
+    }
     out->world = (u32)pp->world;
+    out->flags = sorted ? 1u : 0u;
     out->cap = pp->region_keys;
     out->cursor = pp->d_cursor;
     out->dst = pp->d_dst;

@@ -21,6 +21,7 @@
 // Algorithmic bytes per key of width W: W (histogram read) + P x 2W (read + write per pass).
 #include "khb_common.cuh"
 #include <stdlib.h>
+#include <vector>
 
 #include "lookback.cuh"
 
@@ -57,7 +58,8 @@ __device__ __forceinline__ int find_segment(const u64 *__restrict__ seg_tile, in
 template <typename Key>
 __global__ void __launch_bounds__(RS_BLOCK)
 radix_hist_kernel(const Key *__restrict__ in, const u64 *__restrict__ seg_off, const u64 *__restrict__ seg_tile,
-                  int nseg, u64 ntiles, int npass, int first_bit, u32 *__restrict__ hist /* [nseg][npass][256] */, u32 TILE)
+                  int nseg, u64 ntiles, int npass, int first_bit, u32 *__restrict__ hist /* [nseg][npass][256] */, u32 TILE,
+                  const u64 *__restrict__ gather /* see onesweep_kernel */)
 {
     extern __shared__ u32 sh[];  // [npass][256]
     const u32 tid = threadIdx.x;
@@ -70,7 +72,8 @@ radix_hist_kernel(const Key *__restrict__ in, const u64 *__restrict__ seg_off, c
     int cur = -1;
     for (u64 t = t0; t < t1; t++) {
         const int seg = find_segment(seg_tile, nseg, t);
-        if (seg != cur) {
+        const int hseg = gather ? 0 : seg;     // gathered pieces are ONE logical segment: one histogram
+        if (hseg != cur) {
             if (cur >= 0) {
                 __syncthreads();
                 for (int i = tid; i < npass * 256; i += RS_BLOCK) {
@@ -80,14 +83,15 @@ radix_hist_kernel(const Key *__restrict__ in, const u64 *__restrict__ seg_off, c
                 }
                 __syncthreads();
             }
-            cur = seg;
+            cur = hseg;
         }
         const u64 begin = seg_off[seg] + (t - seg_tile[seg]) * TILE;
         const u64 end = seg_off[seg + 1];
         const u32 n = (u32)(end - begin < (u64)TILE ? end - begin : (u64)TILE);
+        const Key *src = gather ? in + gather[seg] + (t - seg_tile[seg]) * TILE : in + begin;
 #pragma unroll 4
         for (u32 i = tid; i < n; i += RS_BLOCK) {
-            const Key key = in[begin + i];
+            const Key key = src[i];
             for (int p = 0; p < npass; p++) atomicAdd(&sh[p * 256 + key_digit(key, first_bit + 8 * p)], 1u);
         }
     }
@@ -201,8 +205,12 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const unsigne
                 unsigned short *__restrict__ pout, const u64 *__restrict__ seg_off,
                 const u64 *__restrict__ seg_tile, int nseg, int pass_row, int shift, int npass,
                 const u32 *__restrict__ bin_base /* [nseg][npass][256], exclusive */, u64 *__restrict__ lookback,
-                u32 *__restrict__ ticket, u32 epoch, int debug_nolb)
+                u32 *__restrict__ ticket, u32 epoch, int debug_nolb, const u64 *__restrict__ gather)
 {
+    // gather != nullptr (first pass of the multi-GPU across-group stage, api.cu: khb_peer_across): the "segments" are PIECES of one logical
+    // array -- piece s holds the keys [seg_off[s], seg_off[s + 1]) of it and lies at in + gather[s] (a region of the peer receive buffer,
+    // written by rank s) -- so the input is read piece by piece, a partial tile at the end of every piece, while the prefix chain, the
+    // digit offsets and the output are those of a single segment: the pass sorts the concatenation without anybody concatenating it.
     constexpr int TILE = BLOCK * ITEMS;
     constexpr int NW = BLOCK / 32;
     constexpr int LBW = 2;  // look-back window: predecessors fetched per hop
@@ -236,12 +244,14 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const unsigne
     __syncthreads();
     const u64 tile = s_tile;
     const int seg = s_seg;
-    const u64 first_tile = seg_tile[seg];
-    const u64 seg_begin = seg_off[seg];
+    const u64 piece_rel = tile - seg_tile[seg];
+    const u64 first_tile = gather ? 0ull : seg_tile[seg];
+    const u64 seg_begin = gather ? 0ull : seg_off[seg];
     const u64 rel = tile - first_tile;  // position of this tile in its segment's chain
-    const u64 begin = seg_begin + rel * TILE;
+    const u64 begin = seg_off[seg] + piece_rel * TILE;
     const u64 seg_end = seg_off[seg + 1];
     const u32 n = (u32)(seg_end - begin < (u64)TILE ? seg_end - begin : (u64)TILE);
+    const int oseg = gather ? 0 : seg;  // segment of the digit offsets
     PHASE_MARK(0);  // ticket + segment lookup
 
     // load: warp-striped, memory order = (warp, item, lane)
@@ -250,7 +260,7 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const unsigne
 #pragma unroll
     for (int r = 0; r < (ITEMS + 1) / 2; r++) rank2[r] = 0;
     const u32 wbase = warp * (32 * ITEMS);
-    const Key *src = in + begin + wbase + lane;
+    const Key *src = (gather ? in + gather[seg] + piece_rel * TILE : in + begin) + wbase + lane;
     u32 pay2[PAY ? (ITEMS + 1) / 2 : 1];  // two payloads per register
     if (wbase + 32 * ITEMS <= n) {
 #pragma unroll
@@ -390,7 +400,7 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const unsigne
     // finish the look-back (256 digit threads) unless it already ran right after the early count (EARLY 2)
     if (tid < 256) {
         if (EARLY != 2) excl = debug_nolb ? 0u : lookback_finish<LBW>(lbcol, rel, win, count, epoch);  // debug_nolb: timing experiment only (wrong output)
-        glob_off[tid] = bin_base[((size_t)seg * npass + pass_row) * 256 + tid] + excl - dstart;
+        glob_off[tid] = bin_base[((size_t)oseg * npass + pass_row) * 256 + tid] + excl - dstart;
     }
     PHASE_MARK(6);  // look-back (thread 0's column)
     __syncthreads();
@@ -409,9 +419,15 @@ onesweep_kernel(const Key *__restrict__ in, Key *__restrict__ out, const unsigne
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
+// First pass over gathered pieces (onesweep_kernel: gather): d_in[s] = where piece s lies inside the input buffer; from the second pass on the
+// keys are one contiguous segment described by d_off1 / d_tile1 (two entries each) with ntiles1 tiles.
+struct RsGather {
+    const u64 *d_in, *d_off1, *d_tile1;
+    u64 ntiles1;
+};
 template <typename Key, int BLOCK, int ITEMS, int MINB, int MATCH, int PAY = 0, int EARLY = 0>
 static int launch_passes(khb_ctx *ctx, Key *src, Key *dst, unsigned short *psrc, unsigned short *pdst, const u64 *d_off, const u64 *d_tile, int nseg, int npass, int first_bit,
-                         u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket)
+                         u64 ntiles, u64 n_keys, const u32 *d_hist, u64 *d_lb, u32 *d_ticket, const RsGather *gat)
 {
     constexpr int TILE = BLOCK * ITEMS;
     constexpr int NW = BLOCK / 32;
@@ -430,8 +446,12 @@ static int launch_passes(khb_ctx *ctx, Key *src, Key *dst, unsigned short *psrc,
 #endif
     for (int pass = 0; pass < npass; pass++) {
         khb_prof_begin(ctx, KHB_K_ONESWEEP);
-        onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH, PAY, EARLY><<<(unsigned)ntiles, BLOCK, shm, ctx->stream>>>(
-            src, dst, psrc, pdst, d_off, d_tile, nseg, pass, first_bit + 8 * pass, npass, d_hist, d_lb, d_ticket + pass, (u32)(pass + 1), nolb);
+        if (gat && pass > 0)
+            onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH, PAY, EARLY><<<(unsigned)gat->ntiles1, BLOCK, shm, ctx->stream>>>(
+                src, dst, psrc, pdst, gat->d_off1, gat->d_tile1, 1, pass, first_bit + 8 * pass, npass, d_hist, d_lb, d_ticket + pass, (u32)(pass + 1), nolb, nullptr);
+        else
+            onesweep_kernel<Key, BLOCK, ITEMS, MINB, MATCH, PAY, EARLY><<<(unsigned)ntiles, BLOCK, shm, ctx->stream>>>(
+                src, dst, psrc, pdst, d_off, d_tile, nseg, pass, first_bit + 8 * pass, npass, d_hist, d_lb, d_ticket + pass, (u32)(pass + 1), nolb, gat ? gat->d_in : nullptr);
         KHB_LAUNCH_CHECK(ctx);
         khb_prof_end(ctx, KHB_K_ONESWEEP, 2 * n_keys * (sizeof(Key) + (PAY ? 2 : 0)));  // read + write every key (+ payload) once
         Key *t = src; src = dst; dst = t;
@@ -479,13 +499,13 @@ static u32 variant_tile(int v, size_t W)
 template <typename Key>
 static int dispatch_passes(khb_ctx *ctx, int v, Key *src, Key *dst, unsigned short *psrc, unsigned short *pdst, const u64 *d_off,
                            const u64 *d_tile, int nseg, int npass, int first_bit, u64 ntiles, u64 n_keys, const u32 *d_hist,
-                           u64 *d_lb, u32 *d_ticket);
+                           u64 *d_lb, u32 *d_ticket, const RsGather *gat);
 
-#define KHB_PASS_ARGS ctx, src, dst, psrc, pdst, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket
+#define KHB_PASS_ARGS ctx, src, dst, psrc, pdst, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket, gat
 template <>
 int dispatch_passes<Key64>(khb_ctx *ctx, int v, Key64 *src, Key64 *dst, unsigned short *psrc, unsigned short *pdst, const u64 *d_off,
                            const u64 *d_tile, int nseg, int npass, int first_bit, u64 ntiles, u64 n_keys, const u32 *d_hist,
-                           u64 *d_lb, u32 *d_ticket)
+                           u64 *d_lb, u32 *d_ticket, const RsGather *gat)
 {
     if (psrc) {  // keys + 16-bit payload
         if (v == 41) return launch_passes<Key64, 512, 16, 2, 2, 1>(KHB_PASS_ARGS);
@@ -508,7 +528,7 @@ int dispatch_passes<Key64>(khb_ctx *ctx, int v, Key64 *src, Key64 *dst, unsigned
 template <>
 int dispatch_passes<Key128>(khb_ctx *ctx, int v, Key128 *src, Key128 *dst, unsigned short *psrc, unsigned short *pdst, const u64 *d_off,
                             const u64 *d_tile, int nseg, int npass, int first_bit, u64 ntiles, u64 n_keys, const u32 *d_hist,
-                            u64 *d_lb, u32 *d_ticket)
+                            u64 *d_lb, u32 *d_ticket, const RsGather *gat)
 {
     if (v == 31) {  // 6 keys per thread (3072-key tiles): the earlier default, 3.4 % slower per pass (k = 47: 146.4 vs 141.5 ms per step)
         if (psrc) return launch_passes<Key128, 512, 6, 2, 2, 1>(KHB_PASS_ARGS);
@@ -522,8 +542,11 @@ int dispatch_passes<Key128>(khb_ctx *ctx, int v, Key128 *src, Key128 *dst, unsig
 
 template <typename Key>
 static int sort_impl(khb_ctx *ctx, Key *d_keys, Key *d_tmp, unsigned short *d_pay, unsigned short *d_pay_tmp, const u64 *h_seg_off,
-                     int nseg, int first_bit, int npass, int *result_in_tmp, int hist_ready)
+                     int nseg, int first_bit, int npass, int *result_in_tmp, int hist_ready, const u64 *h_gather = nullptr)
 {
+    // h_gather != nullptr: the nseg "segments" are pieces of ONE array to be sorted; piece s lies at d_keys + h_gather[s] (keys).  The
+    // first pass reads them in place and writes d_tmp contiguously; from then on d_tmp and d_keys[0 .. n) ping-pong as usual (the caller
+    // guarantees that d_keys holds n keys from its start and that the pieces may be overwritten once they are read).
     // hist_ready: the SCR_HIST scratch already holds the raw digit counts [1][npass][256] of the single segment (K2 counted
     // them while it produced the keys, khb_sort_hist_buffer), so the histogram sweep over the keys is skipped
     const int v = sort_variant();
@@ -549,17 +572,30 @@ static int sort_impl(khb_ctx *ctx, Key *d_keys, Key *d_tmp, unsigned short *d_pa
     if (ntiles >= (1ull << 32)) { free(h_tab); return khb_fail(ctx, KHB_ERR_ARG, "sort: too many tiles"); }
 
     void *p;
-    int rc = khb_scratch_get(ctx, SCR_MISC, sizeof(u64) * 2 * ((size_t)nseg + 1) + 256, &p);
+    int rc = khb_scratch_get(ctx, SCR_MISC, sizeof(u64) * 3 * ((size_t)nseg + 1) + 64 + 256, &p);
     if (rc) { free(h_tab); return rc; }
     u64 *d_off = (u64 *)p, *d_tile = d_off + nseg + 1;
-    u32 *d_ticket = (u32 *)(d_tile + nseg + 1);  // 64 tickets max (one per pass)
+    u64 *d_gat = d_tile + nseg + 1;              // [nseg + 1] piece positions, then the single-segment tables [2] + [2] (gathered input only)
+    u32 *d_ticket = (u32 *)(d_gat + nseg + 1 + 8);  // 64 tickets max (one per pass)
     // synchronous small copy: h_tab is pageable and freed right after
     KHB_CUDA(ctx, cudaMemcpyAsync(d_off, h_tab, sizeof(u64) * 2 * ((size_t)nseg + 1), cudaMemcpyHostToDevice, ctx->stream));
+    RsGather gat_s, *gat = nullptr;
+    u64 h_one[4] = {0, n_keys, 0, div_up(n_keys, TILE)};
+    if (h_gather) {
+        if (d_pay) { free(h_tab); return khb_fail(ctx, KHB_ERR_ARG, "sort: gathered input carries no payload"); }
+        KHB_CUDA(ctx, cudaMemcpyAsync(d_gat, h_gather, sizeof(u64) * (size_t)nseg, cudaMemcpyHostToDevice, ctx->stream));
+        KHB_CUDA(ctx, cudaMemcpyAsync(d_gat + nseg + 1, h_one, sizeof(h_one), cudaMemcpyHostToDevice, ctx->stream));
+        gat_s.d_in = d_gat;
+        gat_s.d_off1 = d_gat + nseg + 1;
+        gat_s.d_tile1 = d_gat + nseg + 3;
+        gat_s.ntiles1 = h_one[3];
+        gat = &gat_s;
+    }
     KHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     free(h_tab);
     KHB_CUDA(ctx, cudaMemsetAsync(d_ticket, 0, 64 * sizeof(u32), ctx->stream));
 
-    const size_t hist_bytes = (size_t)nseg * npass * 256 * sizeof(u32);
+    const size_t hist_bytes = (size_t)(gat ? 1 : nseg) * npass * 256 * sizeof(u32);
     rc = khb_scratch_get(ctx, SCR_HIST, hist_bytes, &p);
     if (rc) return rc;
     u32 *d_hist = (u32 *)p;
@@ -577,15 +613,16 @@ static int sort_impl(khb_ctx *ctx, Key *d_keys, Key *d_tmp, unsigned short *d_pa
         const size_t shm = (size_t)npass * 256 * sizeof(u32);
         khb_prof_begin(ctx, KHB_K_RADIX_HIST);
         if (!hist_ready) {
-            radix_hist_kernel<Key><<<(unsigned)grid, RS_BLOCK, shm, ctx->stream>>>(d_keys, d_off, d_tile, nseg, ntiles, npass, first_bit, d_hist, TILE);
+            radix_hist_kernel<Key><<<(unsigned)grid, RS_BLOCK, shm, ctx->stream>>>(d_keys, d_off, d_tile, nseg, ntiles, npass, first_bit, d_hist, TILE,
+                                                                                   gat ? gat->d_in : nullptr);
             KHB_LAUNCH_CHECK(ctx);
         }
-        const int nhist = nseg * npass;
+        const int nhist = (gat ? 1 : nseg) * npass;
         radix_scan_kernel<<<(unsigned)div_up(nhist, 8), 256, 0, ctx->stream>>>(d_hist, nhist);
         KHB_LAUNCH_CHECK(ctx);
         khb_prof_end(ctx, KHB_K_RADIX_HIST, hist_ready ? 0 : n_keys * sizeof(Key));
     }
-    rc = dispatch_passes<Key>(ctx, v, d_keys, d_tmp, d_pay, d_pay_tmp, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket);
+    rc = dispatch_passes<Key>(ctx, v, d_keys, d_tmp, d_pay, d_pay_tmp, d_off, d_tile, nseg, npass, first_bit, ntiles, n_keys, d_hist, d_lb, d_ticket, gat);
     if (rc) return rc;
     *result_in_tmp = (npass & 1);
     return KHB_OK;
@@ -603,6 +640,21 @@ int khb_sort_hist_buffer(khb_ctx *ctx, int npass, u32 **d_hist)
     KHB_CUDA(ctx, cudaMemsetAsync(p, 0, bytes, ctx->stream));
     *d_hist = (u32 *)p;
     return KHB_OK;
+}
+
+// One array given as `npieces` pieces inside d_buf (piece s: h_len[s] keys at d_buf + h_pos[s]; d_buf holds at least the sum of the lengths from
+// its start, and the pieces may be overwritten): sorted by the digits like a single segment, without concatenating it first.
+int khb_sort_gathered_impl(khb_ctx *ctx, void *d_buf, void *d_tmp, const u64 *h_pos, const u64 *h_len, int npieces, int key_bytes, int first_bit, int npass,
+                           int *result_in_tmp)
+{
+    if ((key_bytes != 8 && key_bytes != 16) || npieces < 1 || npass < 1 || npass > 16 || first_bit < 0 || first_bit + 8 * npass > 8 * key_bytes + 7)
+        return khb_fail(ctx, KHB_ERR_ARG, "sort (gathered): bad arguments");
+    std::vector<u64> off((size_t)npieces + 1, 0);
+    for (int s = 0; s < npieces; s++) off[s + 1] = off[s] + h_len[s];
+    if (off[npieces] >= (1ull << 32)) return khb_fail(ctx, KHB_ERR_ARG, "sort (gathered): >= 2^32 keys");
+    *result_in_tmp = 0;
+    return key_bytes == 8 ? sort_impl<Key64>(ctx, (Key64 *)d_buf, (Key64 *)d_tmp, nullptr, nullptr, off.data(), npieces, first_bit, npass, result_in_tmp, 0, h_pos)
+                          : sort_impl<Key128>(ctx, (Key128 *)d_buf, (Key128 *)d_tmp, nullptr, nullptr, off.data(), npieces, first_bit, npass, result_in_tmp, 0, h_pos);
 }
 
 int khb_sort_bits_impl(khb_ctx *ctx, void *d_keys, void *d_tmp, const u64 *h_seg_off, int nseg, int key_bytes, int first_bit, int npass,

@@ -214,8 +214,12 @@ class AcrossExchanger:
             self.rounds_nccl += 1
             self._grow_from([int(x) for x in table[self.rank, : self.world]])
             return hist, info
-        eng.peer_import(table[:, self.rank].astype(np.uint64), self.k, self.n_groups, hashed)
-        hist, st = self.ad.across(self.nbins)
+        if hasattr(eng, "peer_across") and os.environ.get("KHB_PEER_GATHER", "1") != "0":
+            # the pushed regions are sorted where they lie: no import copy (KHB_PEER_GATHER=0 keeps import + across)
+            hist, st = eng.peer_across(table[:, self.rank].astype(np.uint64), self.k, self.n_groups, hashed, nbins=self.nbins)
+        else:
+            eng.peer_import(table[:, self.rank].astype(np.uint64), self.k, self.n_groups, hashed)
+            hist, st = self.ad.across(self.nbins)
         dev = self.ad.new_tensor(0).device
         h = torch.from_numpy(np.ascontiguousarray(hist).astype(np.int64)).to(dev if self.ctrl.type != "cpu" else self.ctrl)
         dist.all_reduce(h, op=dist.ReduceOp.SUM, group=self.group)           # also orders the next round's pushes behind this import

@@ -115,6 +115,7 @@ _SIGNATURES = [
     ("khb_peer_push", C.c_int, [_P]),
     ("khb_peer_counts", C.c_int, [_P, _P, C.POINTER(C.c_int)]),
     ("khb_peer_import", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int]),
+    ("khb_peer_across", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_uint32, _P, C.POINTER(Stats)]),
     ("khb_peer_unmap", C.c_int, [_P]),
     ("khb_peer_close", C.c_int, [_P]),
     ("khb_peer_region_keys", C.c_uint64, [_P]),
@@ -314,6 +315,14 @@ class Engine:
     def peer_import(self, recv_counts, k: int, n_groups: int, hashed: bool):
         rc = np.ascontiguousarray(recv_counts, dtype=np.uint64)
         self._chk(self.lib.khb_peer_import(self.ctx, rc.ctypes.data, k, n_groups, int(hashed)))
+
+    def peer_across(self, recv_counts, k: int, n_groups: int, hashed: bool, nbins: int = COUNTER_MAX):
+        """peer_import + across_groups without the copy in between (the first radix pass gathers the pushed regions)."""
+        rc = np.ascontiguousarray(recv_counts, dtype=np.uint64)
+        hist = np.zeros(nbins + 1, dtype=np.uint64)
+        st = Stats()
+        self._chk(self.lib.khb_peer_across(self.ctx, rc.ctypes.data, k, n_groups, int(hashed), nbins, hist.ctypes.data, C.byref(st)))
+        return hist, st.as_dict()
 
     def peer_unmap(self):
         self._chk(self.lib.khb_peer_unmap(self.ctx))
