@@ -15,6 +15,9 @@
 //                                 histogram, distinct keys (mixed like K2's) appended to the group-set store, table left clean
 //   pass B  mb_bigbin_kernel      (bin, hash class) pairs whose table filled up, redone window by window with the class split further
 //   mb_region_scan_kernel         exact region offsets for the second partition attempt after a region overflowed
+//   mb_region_scan4_kernel,       ONE group on several GPUs (a team, team.cu; khb_bins_team_*): a member partitions its slice of the genomes
+//   mb_region_push_kernel         locally, then one warp per region packs the region into the sender's area of the record buffer of the bin's
+//                                 owner (peer memory over NVLink); the owner counts its bins with passes C and B unchanged
 //   mb_across_kernel (+ ma_*)     OPT-IN across-group stage bin by bin over the key segments the groups left in the store (exact, but
 //                                 slower than the prefix sort: KHB_ACROSS_MODE=bins)
 //
