@@ -329,9 +329,9 @@ KHB_API uint64_t khb_peer_region_keys(const khb_ctx *ctx);
  * Steps 1-4 of one group (/root/reference/workflow/rules/exp_type_1.smk:156-191) sharded over the `team_size` <= 8 members of a
  * team, for job shapes with fewer (or unevenly many) groups than GPUs.  The group's genomes are split into contiguous slices, one per
  * member, every slice padded to whole chunks of 64 genome ids (slice t starts at id 64 * chunk_base[t]); the minimizer bins are split
- * into `team_size` ranges of owners.  Each member packs its slice and partitions it into super-k-mer records (pass P of bins.cu)
- * that it stores straight into the record buffer of the bin's owner -- peer memory over NVLink (CUDA IPC), no collective, no remote
- * atomic: a (bin, chunk) region has exactly one writer -- followed by the region sizes.  After ONE barrier between the members
+ * into `team_size` ranges of owners.  Each member packs its slice, partitions it into super-k-mer records (pass P of bins.cu) and
+ * copies every region, as one run, into its own area of the record buffer of the bin's owner -- peer memory over NVLink (CUDA IPC),
+ * no collective, no remote atomic: a (bin, chunk) region has exactly one writer -- followed by the region's start and size.  After ONE barrier between the members
  * (any collective of the caller; it also carries the overflow flags) every member counts the bins it owns (passes C and B): its
  * h_hist holds the step_4 rows of ITS bins' k-mers, the sum over the members is the group's histogram, and its distinct keys go to
  * the group-set store / the across-group exchange like those of a whole group.
